@@ -1,0 +1,189 @@
+"""Generate the committed golden fixtures by running the REAL reference (/root/reference) on CPU.
+
+    python tests/golden/make_golden.py          # writes tests/golden/*.pt
+
+Fixtures (all fp32, produced by the unmodified reference code through the shims in ref_harness.py):
+  text_tiny.pt    tiny text-only BERSON (vendored BertModel): state_dict, ragged + full inputs,
+                  prepare_berson_inputs output, encode 10-tuple, per-step log-probs and beam
+                  indices, final permutations, training loss.
+  mm_tiny.pt      tiny LXRT + CLIP-ViT multimodal BERSON (ViT adapter of SURVEY §8(c)); images are
+                  regenerated from the stored seed (a checksum guards RNG drift).
+  decode_full.pt  full-width (H=768) decode stage: reference beam_search_pointer fed with seeded
+                  synthetic `encode` outputs and seeded head weights, for
+                  N in {5,6,10} x W in {1,4,8,16}: per-step beam indices / log-probs / permutation.
+                  Weights and inputs are regenerated from seeds by oracle.synth (too big to commit).
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import ref_harness as rh  # noqa: E402
+from oracle import berson_oracle as O  # noqa: E402
+from oracle import synth  # noqa: E402
+
+torch.set_grad_enabled(False)
+torch.set_num_threads(1)  # deterministic summation order for the committed numbers
+
+TINY = dict(vocab_size_or_config_json_file=1000, hidden_size=128, num_hidden_layers=2,
+            num_attention_heads=2, intermediate_size=512, max_position_embeddings=256)
+TINY_VIT = dict(embed_dim=64, image_resolution=224, vision_layers=2, vision_width=128, vision_patch_size=32)
+DEAD = ("visual_model.transformer.", "visual_model.token_embedding", "visual_model.positional_embedding",
+        "visual_model.ln_final", "visual_model.text_projection", "visual_model.logit_scale")
+
+
+def traced_beam(ns, args, model, berson_inputs):
+    """Run reference beam_search_pointer while recording model.step log-probs and Beam.step picks."""
+    rec = []
+    orig_step = model.step
+    orig_bstep = ns.gen.Beam.step
+
+    def step(*a, **k):
+        h, c, logp = orig_step(*a, **k)
+        rec.append(dict(logp=logp.clone()))
+        return h, c, logp
+
+    def bstep(self, prob, prev_beam, f_done):
+        pre = prob.new_tensor(prev_beam.scores)
+        score = prob + pre.unsqueeze(-1).expand_as(prob)
+        k = min(self.beam_size, score.numel())
+        s, ix = score.view(-1).topk(k, largest=False)
+        rec[-1].update(score=s.clone(), beam_ix=(ix // prob.size(1)).clone(),
+                       tok_ix=(ix - (ix // prob.size(1)) * prob.size(1)).clone())
+        return orig_bstep(self, prob, prev_beam, f_done)
+
+    model.step = step
+    ns.gen.Beam.step = bstep
+    try:
+        perm = ns.berson.beam_search_pointer(args, model, **berson_inputs)
+    finally:
+        model.step = orig_step
+        ns.gen.Beam.step = orig_bstep
+    return perm, rec
+
+
+ENC_NAMES = ["sents", "para", "hc", "key", "cls", "cls_mat", "cls_score", "score_mat", "his1", "his2"]
+
+
+def run_case(ns, model, args, ids, labels, images):
+    tok = rh.StubTokenizer()
+    inputs = {"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": labels}
+    if images is not None:
+        inputs["images"] = images
+    bi = ns.prep.prepare_berson_inputs(inputs, tok, args=args)
+    enc = model.encode(**bi)
+    encd = {}
+    for n, t in zip(ENC_NAMES, enc):
+        if n == "hc":
+            encd["h0"], encd["c0"] = t[0].clone(), t[1].clone()
+        else:
+            encd[n] = t.clone()
+    bi = ns.prep.prepare_berson_inputs(inputs, tok, args=args)
+    perm, rec = traced_beam(ns, args, model, bi)
+    prep = {k: v.clone() for k, v in bi.items() if torch.is_tensor(v) and k != "images"}
+    return dict(ids=ids.clone(), labels=labels.clone(), prep=prep, enc=encd, steps=rec, perm=perm)
+
+
+def ragged_manual(n_steps, vocab, seed):
+    g = torch.Generator().manual_seed(seed)
+    rows = []
+    for _ in range(n_steps):
+        ln = int(torch.randint(5, 30, (1,), generator=g))
+        rows.append(torch.cat([torch.tensor([101]), torch.randint(200, vocab, (ln,), generator=g), torch.tensor([102])]))
+    ids = torch.cat(rows)[None]
+    return ids, torch.randperm(n_steps, generator=g)[None]
+
+
+def gen_text(ns):
+    out = dict(cfg=dict(TINY), ff_size=256, cases=[])
+    for N, W in ((5, 4), (5, 1), (6, 8), (10, 16)):
+        args = rh.make_args(N, W)
+        args.ff_size = 256
+        model = rh.build_text_model(ns, TINY, args, seed=0)
+        if "sd" not in out:
+            out["sd"] = {k: v.clone() for k, v in model.state_dict().items()}
+        ids, labels, _ = O.synthetic_manuals(2, N, 24, vocab=1000, seed=10 + N)
+        for b in range(2):
+            c = run_case(ns, model, args, ids[b:b + 1], labels[b:b + 1], None)
+            c.update(N=N, W=W, kind="full")
+            out["cases"].append(c)
+        rid, rlab = ragged_manual(N, 1000, 20 + N)
+        c = run_case(ns, model, args, rid, rlab, None)
+        c.update(N=N, W=W, kind="ragged")
+        out["cases"].append(c)
+    # training loss (modeling_bert.py:943-1174), batch of 3 five-step manuals
+    args = rh.make_args(5, 4)
+    args.ff_size = 256
+    model = rh.build_text_model(ns, TINY, args, seed=0)
+    ids, labels, _ = O.synthetic_manuals(3, 5, 24, vocab=1000, seed=33)
+    bi = ns.prep.prepare_berson_inputs({"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": labels},
+                                       rh.StubTokenizer(), args=args)
+    out["loss_case"] = dict(ids=ids, labels=labels, loss=model._forward(**bi)[0].clone())
+    return out
+
+
+def gen_mm(ns):
+    out = dict(cfg=dict(TINY), vit=dict(TINY_VIT), ff_size=256, cases=[])
+    for N, W, L in ((5, 4, 64), (6, 8, 16)):
+        args = rh.make_args(N, W, multimodal=True)
+        args.ff_size = 256
+        model = rh.build_multimodal_model(ns, TINY, args, TINY_VIT, seed=0)
+        if "sd" not in out:
+            out["sd"] = {k: v.clone() for k, v in model.state_dict().items() if not any(d in k for d in DEAD)}
+        seed = 40 + N
+        ids, labels, images = O.synthetic_manuals(1, N, L, vocab=1000, image_px=224, seed=seed)
+        c = run_case(ns, model, args, ids, labels, images)
+        # intermediate tower / joint outputs of the inner model for stage-wise parity
+        bi = ns.prep.prepare_berson_inputs({"input_ids": ids, "attention_mask": torch.ones_like(ids),
+                                            "labels": labels, "images": images}, rh.StubTokenizer(), args=args)
+        B, P, Lt = bi["input_ids"].shape
+        im = bi["images"].reshape(B * P * 2, 3, 224, 224)
+        tower = model.bert.encoder.visual_model.visual(im, skip_last_layer=True, img_len=2)
+        (lang, visn), pooled = model.bert(input_ids=bi["input_ids"].reshape(B * P, Lt),
+                                          token_type_ids=bi["token_type_ids"].reshape(B * P, Lt),
+                                          attention_mask=bi["attention_mask"].reshape(B * P, Lt), visual_feats=im)
+        c.update(N=N, W=W, L=L, seed=seed, image_checksum=float(images.double().sum()),
+                 tower=tower[:3].clone(), lang=lang[:3].clone(), visn=visn[:3].clone(), pooled=pooled.clone())
+        out["cases"].append(c)
+    return out
+
+
+def gen_decode_full(ns):
+    H = 768
+    out = dict(H=H, cases=[])
+    full = dict(vocab_size_or_config_json_file=64, hidden_size=H, num_hidden_layers=1, num_attention_heads=12,
+                intermediate_size=64, max_position_embeddings=8)
+    for N in (5, 6, 10):
+        for W in (1, 4, 8, 16):
+            args = rh.make_args(N, W)
+            args.ff_size = 64
+            model = rh.build_text_model(ns, full, args, seed=0)
+            heads = synth.decode_head_weights(H, seed=7)
+            missing = model.load_state_dict(heads, strict=False)
+            assert not missing.unexpected_keys
+            enc = synth.synthetic_encode(N, H, seed=100 + N)
+            tup = (enc["sents"], enc["para"], (enc["h0"], enc["c0"]), enc["key"], enc["cls"], enc["cls_mat"],
+                   enc["cls_score"], enc["score_mat"], enc["his1"], enc["his2"])
+            model.encode = lambda *a, _t=tup, **k: tuple(x.clone() if torch.is_tensor(x) else tuple(y.clone() for y in x) for x in _t)
+            dummy = dict(input_ids=torch.zeros(1, N * (N - 1), 4, dtype=torch.long),
+                         passage_length=torch.tensor([N]))
+            perm, rec = traced_beam(ns, args, model, dummy)
+            out["cases"].append(dict(N=N, W=W, enc_seed=100 + N, head_seed=7, perm=perm, steps=rec))
+    return out
+
+
+def main():
+    ns = rh.load()
+    torch.save(gen_text(ns), os.path.join(HERE, "text_tiny.pt"))
+    torch.save(gen_mm(ns), os.path.join(HERE, "mm_tiny.pt"))
+    torch.save(gen_decode_full(ns), os.path.join(HERE, "decode_full.pt"))
+    for f in ("text_tiny.pt", "mm_tiny.pt", "decode_full.pt"):
+        print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
