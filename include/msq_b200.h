@@ -1,0 +1,124 @@
+/* msq_b200.h — C ABI of the B200-native (sm_100a) multimodal step-ordering hot path.
+ *
+ * Drop-in boundary for telin0411/multimodal_sequencing.  The reference is pure Python/PyTorch: the
+ * functions below are what its nn.Module methods bind to (ctypes stubs in INTEGRATION.md; the host
+ * mirror lives in multimodal_sequencing_b200/).  Conventions:
+ *   - every function returns 0 on success, non-zero on failure; msq_last_error() gives the message
+ *     (the Python side raises RuntimeError, matching the reference's exception-based error style);
+ *   - pointers named *_dev are device pointers (caller-owned, e.g. torch tensors' data_ptr()),
+ *     pointers named *_host are host pointers; `stream` is a cudaStream_t passed as void*;
+ *   - nothing synchronises unless stated; outputs are valid after the stream is synchronised;
+ *   - integer inputs are int64 (torch.long) exactly as the reference passes them.
+ * No CPU fallback exists: without a CUDA device every compute entry point fails.
+ */
+#ifndef MSQ_B200_H
+#define MSQ_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct msq_model msq_model;
+
+/* Model geometry.  Mirrors BertConfig (models/berson/configuration_bert.py:77-90), the CLIP visual
+ * tower constructor (models/CLIP/clip/model.py:308-323) and the BERSON hyper-parameters hard-coded
+ * in trainers/train.py:2012-2022. */
+typedef struct msq_config {
+  int32_t hidden;        /* 768 */
+  int32_t layers;        /* 12  */
+  int32_t heads;         /* 12 (head dim must be 64) */
+  int32_t inter;         /* 3072 */
+  int32_t vocab;         /* 30522 */
+  int32_t max_pos;       /* 512 */
+  int32_t type_vocab;    /* 2 */
+  int32_t vit_width;     /* 768; 0 = text-only inner BertModel (models/berson/modeling_bert.py:563) */
+  int32_t vit_layers;    /* 12 */
+  int32_t vit_patch;     /* 32 */
+  int32_t vit_res;       /* 224 */
+  int32_t para_heads;    /* 8 */
+  int32_t para_ff;       /* 3072 */
+  int32_t para_layers;   /* 2 */
+  int32_t precise;       /* 0: bf16 tcgen05 tensor-core encoder; 1: fp32 FFMA encoder (parity mode) */
+  int32_t reserved;
+} msq_config;
+
+const char* msq_last_error(void);
+int msq_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t msq_launch_count(void);
+/* 1 if the tcgen05/TMA GEMM path can be used on the current device (sm_100), else 0 */
+int msq_tc_available(void);
+
+/* ---- model lifetime ------------------------------------------------------------------------ */
+int msq_model_create(const msq_config* cfg, msq_model** out);
+void msq_model_destroy(msq_model* m);
+/* Register one fp32 parameter by its reference state_dict key, e.g.
+ * "bert.encoder.layer.0.attention.self.query.weight".  Data is copied (device -> device). */
+int msq_model_set_weight(msq_model* m, const char* name, const float* data_dev, int64_t numel, void* stream);
+/* Build the packed device-side weights (fused QKV, bf16 copies, gate-interleaved LSTM, pw_k blocks).
+ * Fails with the list of missing keys if the state_dict was incomplete. */
+int msq_model_pack(msq_model* m, void* stream);
+
+/* ---- encoders -------------------------------------------------------------------------------
+ * msq_vit_forward       CLIP VisualTransformer.forward, pair-joint variant, skip_last_layer=True
+ *                       (models/CLIP/clip/model.py:262-305).  images_dev [n_img,3,S,S] fp32 are UNIQUE
+ *                       images; img_index_dev [R*2] int32 maps (pair row, slot) -> image.  out [R,1+2g^2,W].
+ * msq_inner_forward     LXRTModel.forward BERSON mode (models/CLIP/src/lxrt/modeling.py:1513-1598) or,
+ *                       when the model is text-only, BertModel.forward
+ *                       (models/berson/modeling_bert.py:613-663).  ids/tt/mask [R,Lt] int64.
+ *                       lang_dev [R,Lt,H], visn_dev [R,Lv,H] (or NULL), pooled_dev [R,H] (or NULL). */
+int msq_vit_forward(msq_model* m, const float* images_dev, int64_t n_img, const int32_t* img_index_dev, int64_t R,
+                    float* out_dev, void* stream);
+int msq_inner_forward(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev, int64_t R,
+                      int32_t Lt, const float* images_dev, int64_t n_img, const int32_t* img_index_dev, float* lang_dev,
+                      float* visn_dev, float* pooled_dev, void* stream);
+
+/* ---- BertForOrdering.encode (models/berson/modeling_bert.py:1239-1366) ------------------------
+ * B manuals of N steps, P = N(N-1) pair rows each.  sep_dev [B*P,2] int64.  Outputs (any may be
+ * NULL): sents [B,N,H], para [B,N,H], h0 [B,H], key [B,N,H], cls [B*P,H], cls_mat [B,N,N,H],
+ * cls_score [B*P,2], score_mat/his1/his2 [B,N,N,2], top_vec [B*P,Lt,H]. */
+typedef struct msq_encode_out {
+  float *sents, *para, *h0, *key, *cls, *cls_mat, *cls_score, *score_mat, *his1, *his2, *top_vec;
+} msq_encode_out;
+int msq_encode(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev,
+               const int64_t* sep_dev, int64_t B, int32_t N, int32_t Lt, const float* images_dev, int64_t n_img,
+               const int32_t* img_index_dev, const msq_encode_out* out, void* stream);
+
+/* ---- pointer decoder + beam search (modeling_bert.py:1368-1402, 1411-1552; generator.py:15-38) --
+ * Consumes encode outputs (device, fp32): sents/key [B,N,H], h0 [B,H], cls_mat [B,N,N,H],
+ * score_mat [B,N,N,2].  perm_dev [B,N] int32 receives the predicted order.  Optional traces:
+ * trace_ix [B,N-1,W] int32 (flat beam*N+step picks, -1 padded), trace_cost [B,N-1,W],
+ * trace_logp [B,N-1,W,N]. */
+int msq_beam_search(msq_model* m, const float* sents_dev, const float* key_dev, const float* h0_dev,
+                    const float* cls_mat_dev, const float* score_mat_dev, int64_t B, int32_t N, int32_t beam,
+                    int32_t* perm_dev, int32_t* trace_ix_dev, float* trace_cost_dev, float* trace_logp_dev, void* stream);
+
+/* ---- whole path on device-resident inputs: encode + beam search ------------------------------- */
+int msq_order_manuals_dev(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev,
+                          const int64_t* sep_dev, int64_t B, int32_t N, int32_t Lt, const float* images_dev,
+                          int64_t n_img, const int32_t* img_index_dev, int32_t beam, int32_t* perm_dev, void* stream);
+
+/* ---- whole path from HOST buffers (berson_pointer_network, modeling_bert.py:1405-1408, batched):
+ * copies the inputs host->device, runs encode + beam search, copies perm back and synchronises the
+ * stream.  Host buffers should be pinned for full H2D bandwidth. */
+int msq_order_manuals_host(msq_model* m, const int64_t* ids_host, const int64_t* tt_host, const int64_t* mask_host,
+                           const int64_t* sep_host, int64_t B, int32_t N, int32_t Lt, const float* images_host,
+                           int64_t n_img, const int32_t* img_index_host, int32_t beam, int32_t* perm_host, void* stream);
+
+/* ---- building blocks exposed for kernel-level parity tests and the bench's roofline lines ------ */
+/* C[M,N] = act(A[M,K] W[N,K]^T + bias) + resid.  dtype: 0 = fp32 in/out (FFMA), 1 = bf16 in / fp32 out
+ * (tcgen05), 2 = bf16 in / bf16 out (tcgen05).  act: 0 none, 1 erf-GELU, 2 QuickGELU, 3 tanh, 4 tanh-GELU. */
+int msq_gemm(int32_t dtype, const void* A_dev, const void* W_dev, const float* bias_dev, const float* resid_dev,
+             void* C_dev, int64_t M, int32_t N, int32_t K, int32_t act, void* stream);
+/* dtype 0 fp32, 1 bf16.  y = LN(x) (x always fp32 [rows,H]); writes out_dev in dtype. */
+int msq_layernorm(int32_t dtype, const float* x_dev, int64_t rows, int32_t H, const float* gamma_dev,
+                  const float* beta_dev, float eps, void* out_dev, void* stream);
+/* qkv [R*L, 3*heads*64] -> ctx [R*L, heads*64]; mask_add_dev [R, mask_len] additive key mask or NULL. */
+int msq_attention(int32_t dtype, const void* qkv_dev, int64_t R, int32_t L, int32_t heads, float scale,
+                  const float* mask_add_dev, int32_t mask_len, void* ctx_dev, void* stream);
+int msq_f32_to_bf16(const float* src_dev, void* dst_dev, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,919 @@
+// C-ABI entry points (include/msq_b200.h) and the host-side orchestration of the step-ordering path:
+// weight registry + packing, workspace arena, encoder stacks (CLIP ViT pair tower, joint BERT,
+// text-only BERT), BERSON pooling, paragraph encoder, decode pre-projections and the beam-search launch.
+// All device work is enqueued on the caller's stream; one micro-batch of manuals is encoded at a time.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/msq_b200.h"
+#include "kernels.cuh"
+
+namespace msq {
+
+static thread_local char g_err[2048] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  int reserve(size_t bytes, cudaStream_t st) {
+    if (bytes <= cap) return MSQ_OK;
+    MSQ_CUDA(cudaStreamSynchronize(st));
+    if (base) MSQ_CUDA(cudaFree(base));
+    base = nullptr;
+    cap = 0;
+    MSQ_CUDA(cudaMalloc(&base, bytes));
+    cap = bytes;
+    return MSQ_OK;
+  }
+  void reset() { off = 0; }
+  template <typename T> T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+// first pass with base == nullptr measures, second pass hands out pointers
+struct Planner {
+  Arena* a;
+  bool measure;
+  size_t need = 0;
+  template <typename T> T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    if (measure) { need += bytes; return nullptr; }
+    return a->take<T>(n);
+  }
+};
+
+struct Lin {           // y = x W^T + b
+  const float* w32 = nullptr;
+  const bf16* w16 = nullptr;
+  const float* b = nullptr;
+  int N = 0, K = 0, ld = 0;
+};
+struct LNp { const float* g = nullptr; const float* b = nullptr; };
+
+struct BertLayerW { Lin qkv, out, up, down; LNp ln1, ln2; };
+struct VitLayerW { Lin qkv, out, fc, proj; LNp ln1, ln2; };
+struct ParaLayerW { Lin qkv, fin, w1, w2; LNp ln_in, ln_ff; };
+
+}  // namespace msq
+
+using namespace msq;
+
+struct msq_model {
+  msq_config cfg;
+  std::unordered_map<std::string, std::pair<float*, int64_t>> raw;
+  std::vector<void*> owned;
+  bool packed = false;
+  std::string prefix_inner = "bert.";
+  // packed
+  const float *word = nullptr, *pos = nullptr, *type = nullptr;
+  LNp emb_ln;
+  std::vector<BertLayerW> bert;
+  Lin pooler;
+  bool has_pooler = false;
+  // vit
+  Lin conv1, visn_fc;
+  const float *vit_cls = nullptr, *vit_pos = nullptr;
+  LNp ln_pre, ln_post, visn_ln;
+  std::vector<VitLayerW> vit;
+  // berson heads
+  Lin sent_tran, key_lin, xg_lin, t4_lin;
+  const float *w2 = nullptr, *b2 = nullptr, *w_rel = nullptr, *b_rel = nullptr, *w_in2 = nullptr;
+  std::vector<ParaLayerW> para;
+  LNp para_ln;
+  DecodeWeights dec;
+  int Kp = 0;  // padded H+2
+  Arena ws;
+  ~msq_model() {
+    for (auto& kv : raw) cudaFree(kv.second.first);
+    for (void* p : owned) cudaFree(p);
+    if (ws.base) cudaFree(ws.base);
+  }
+};
+
+namespace msq {
+
+static int get_raw(msq_model* m, const std::string& name, int64_t numel, const float** out, std::string* missing) {
+  auto it = m->raw.find(name);
+  if (it == m->raw.end()) {
+    if (missing) { *missing += name + " "; *out = nullptr; return MSQ_OK; }
+    set_error("missing weight %s", name.c_str());
+    return MSQ_ERR_WEIGHT;
+  }
+  if (numel >= 0 && it->second.second != numel) {
+    set_error("weight %s has %lld elements, expected %lld", name.c_str(), (long long)it->second.second, (long long)numel);
+    return MSQ_ERR_WEIGHT;
+  }
+  *out = it->second.first;
+  return MSQ_OK;
+}
+
+template <typename T> static int dev_alloc(msq_model* m, size_t n, T** out) {
+  void* p = nullptr;
+  MSQ_CUDA(cudaMalloc(&p, n * sizeof(T)));
+  m->owned.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return MSQ_OK;
+}
+
+// build a Lin from an fp32 [N,K] weight already on device (optionally padded to Kp columns)
+static int make_lin(msq_model* m, const float* w, const float* b, int N, int K, int Kp, bool want16, Lin* out,
+                    cudaStream_t st) {
+  out->N = N; out->K = Kp; out->ld = Kp; out->b = b;
+  if (Kp != K) {
+    float* wp;
+    MSQ_TRY(dev_alloc(m, (size_t)N * Kp, &wp));
+    MSQ_TRY(pack_pad<float>(w, N, K, Kp, wp, st));
+    out->w32 = wp;
+  } else {
+    out->w32 = w;
+  }
+  if (want16) {
+    bf16* w16;
+    MSQ_TRY(dev_alloc(m, (size_t)N * Kp, &w16));
+    MSQ_TRY(pack_pad<bf16>(w, N, K, Kp, w16, st));
+    out->w16 = w16;
+  }
+  return MSQ_OK;
+}
+
+__global__ void concat_rows_kernel(const float* a, const float* b, const float* c, int64_t na, int64_t nb, int64_t nc,
+                                   float* out) {
+  const int64_t total = na + nb + nc;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = i < na ? a[i] : (i < na + nb ? b[i - na] : c[i - na - nb]);
+}
+static int concat3(msq_model* m, const float* a, const float* b, const float* c, int64_t na, int64_t nb, int64_t nc,
+                   const float** out, cudaStream_t st) {
+  float* p;
+  MSQ_TRY(dev_alloc(m, (size_t)(na + nb + nc), &p));
+  concat_rows_kernel<<<256, 256, 0, st>>>(a, b, c, na, nb, nc, p);
+  MSQ_LAUNCH_CHECK();
+  *out = p;
+  return MSQ_OK;
+}
+
+// LSTM / pw_k repacks
+__global__ void pack_lstm_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b_ih,
+                                 const float* __restrict__ b_hh, int H, float* __restrict__ wih_perm,
+                                 float* __restrict__ bias_perm, float* __restrict__ whh_t) {
+  const int64_t total = (int64_t)4 * H * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / H), k = (int)(i % H);  // row = g*H + u in torch's (i,f,g,o) order
+    const int g = row / H, u = row % H, col = 4 * u + g;
+    wih_perm[(int64_t)col * H + k] = w_ih[i];
+    whh_t[(int64_t)k * 4 * H + col] = w_hh[i];
+    if (k == 0) bias_perm[col] = b_ih[row] + b_hh[row];
+  }
+}
+__global__ void transpose_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst) {
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    dst[(int64_t)c * rows + r] = src[i];
+  }
+}
+// pw_k.weight [H, 4*(H+2)] -> [4H, Kp]: row blk*H + o, col c  <- w[o, blk*(H+2) + c]
+__global__ void pack_pwk_kernel(const float* __restrict__ w, int H, int Kp, float* __restrict__ dst) {
+  const int D = H + 2;
+  const int64_t total = (int64_t)4 * H * Kp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / Kp), c = (int)(i % Kp), blk = row / H, o = row % H;
+    dst[i] = c < D ? w[(int64_t)o * 4 * D + blk * D + c] : 0.f;
+  }
+}
+__global__ void mask_add_kernel(const int64_t* __restrict__ mask, int64_t n, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (1.0f - (float)mask[i]) * -10000.0f;
+}
+// R0[b,i,j,:] = [cls_mat ; softmax(score_mat) ; 0]  (rela_encode, modeling_bert.py:919-925)
+__global__ void build_r0_kernel(const float* __restrict__ cls_mat, const float* __restrict__ score_mat, int64_t cells, int H,
+                                int Kp, float* __restrict__ r0) {
+  const int64_t cell = blockIdx.x;
+  if (cell >= cells) return;
+  const float z0 = score_mat[cell * 2], z1 = score_mat[cell * 2 + 1];
+  const float mx = fmaxf(z0, z1), e0 = expf(z0 - mx), e1 = expf(z1 - mx);
+  for (int d = threadIdx.x; d < Kp; d += blockDim.x)
+    r0[cell * Kp + d] = d < H ? cls_mat[cell * H + d] : (d == H ? e0 / (e0 + e1) : (d == H + 1 ? e1 / (e0 + e1) : 0.f));
+}
+// sents_ext[b, n, :] = sents[b, n, :] for n < N, zeros for n == N
+__global__ void sents_ext_kernel(const float* __restrict__ sents, int64_t B, int N, int H, float* __restrict__ out) {
+  const int64_t total = B * (N + 1) * (int64_t)H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % H);
+    const int64_t row = i / H, b = row / (N + 1);
+    const int n = (int)(row % (N + 1));
+    out[i] = n < N ? sents[(b * N + n) * H + d] : 0.f;
+  }
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ s, bf16* __restrict__ d, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = __float2bfloat16_rn(s[i]);
+}
+
+static bool use_tc(const msq_model* m) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("MSQ_FORCE_SIMT"); forced = (e && e[0] == '1') ? 1 : 0; }
+  return !m->cfg.precise && !forced && gemm_tc_selftest_supported();
+}
+
+// C = act(A W^T + b) + resid, A in T, output in TO
+template <typename T, typename TO>
+static int run_gemm(const msq_model* m, const T* A, int lda, const Lin& w, const float* resid, int ldr, TO* C, int ldc,
+                    int64_t M, int act, cudaStream_t st, bool with_bias = true) {
+  GemmArgs g;
+  g.A = A; g.bias = with_bias ? w.b : nullptr; g.resid = resid; g.C = C; g.C2 = nullptr;
+  g.M = M; g.N = w.N; g.K = w.K; g.lda = lda; g.ldw = w.ld; g.ldc = ldc; g.ldr = ldr; g.act = act;
+  if constexpr (sizeof(T) == 4) {
+    g.W = w.w32;
+    return gemm_simt<float, TO>(g, st);
+  } else {
+    g.W = w.w16;
+    MSQ_REQUIRE(w.w16 != nullptr, "bf16 weight copy missing");
+    if (use_tc(m)) return gemm_tc<TO>(g, st);
+    return gemm_simt<bf16, TO>(g, st);
+  }
+}
+
+}  // namespace msq
+
+// =====================================================================================================
+// model lifetime
+// =====================================================================================================
+
+extern "C" const char* msq_last_error(void) { return g_err; }
+extern "C" int msq_version(void) { return 100; }
+extern "C" int64_t msq_launch_count(void) { return g_launches.load(); }
+extern "C" int msq_tc_available(void) { return gemm_tc_selftest_supported(); }
+
+extern "C" int msq_model_create(const msq_config* cfg, msq_model** out) {
+  MSQ_REQUIRE(cfg && out, "null argument");
+  MSQ_REQUIRE(cfg->hidden % 128 == 0 && cfg->hidden <= 1024, "hidden=%d must be a multiple of 128, <= 1024", cfg->hidden);
+  MSQ_REQUIRE(cfg->heads * 64 == cfg->hidden, "head dim must be 64 (hidden=%d heads=%d)", cfg->hidden, cfg->heads);
+  MSQ_REQUIRE(cfg->inter % 16 == 0 && cfg->layers >= 1, "bad inter/layers");
+  if (cfg->vit_width) {
+    MSQ_REQUIRE(cfg->vit_width % 128 == 0 && cfg->vit_width <= 1024, "vit_width=%d unsupported", cfg->vit_width);
+    MSQ_REQUIRE(cfg->vit_res % cfg->vit_patch == 0 && cfg->vit_patch % 4 == 0, "vit patch/res");
+  }
+  MSQ_REQUIRE(cfg->para_heads >= 1 && cfg->hidden % cfg->para_heads == 0 && cfg->para_ff % 16 == 0, "bad paragraph config");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: this library has no CPU fallback");
+    return MSQ_ERR_CUDA;
+  }
+  msq_model* m = new msq_model();
+  m->cfg = *cfg;
+  *out = m;
+  return MSQ_OK;
+}
+
+extern "C" void msq_model_destroy(msq_model* m) { delete m; }
+
+extern "C" int msq_model_set_weight(msq_model* m, const char* name, const float* data_dev, int64_t numel, void* stream) {
+  MSQ_REQUIRE(m && name && data_dev && numel > 0, "bad argument");
+  MSQ_REQUIRE(!m->packed, "model already packed");
+  float* p = nullptr;
+  MSQ_CUDA(cudaMalloc(&p, numel * sizeof(float)));
+  MSQ_CUDA(cudaMemcpyAsync(p, data_dev, numel * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  auto it = m->raw.find(name);
+  if (it != m->raw.end()) { cudaFree(it->second.first); m->raw.erase(it); }
+  m->raw[name] = {p, numel};
+  return MSQ_OK;
+}
+
+extern "C" int msq_model_pack(msq_model* m, void* stream) {
+  MSQ_REQUIRE(m && !m->packed, "bad state");
+  cudaStream_t st = (cudaStream_t)stream;
+  const msq_config& c = m->cfg;
+  const int H = c.hidden;
+  const bool w16 = !c.precise;
+  std::string miss;
+  const std::string P = m->prefix_inner;
+  auto W = [&](const std::string& n, int64_t numel) { const float* p; get_raw(m, n, numel, &p, &miss); return p; };
+  // first make sure everything is there (collect all missing names)
+  std::vector<std::string> need;
+  auto lin_names = [&](const std::string& n) { need.push_back(n + ".weight"); need.push_back(n + ".bias"); };
+  for (const char* e : {"embeddings.word_embeddings.weight", "embeddings.position_embeddings.weight",
+                        "embeddings.token_type_embeddings.weight", "embeddings.LayerNorm.weight", "embeddings.LayerNorm.bias"})
+    need.push_back(P + e);
+  for (int l = 0; l < c.layers; ++l) {
+    const std::string b = P + "encoder.layer." + std::to_string(l) + ".";
+    for (const char* e : {"attention.self.query", "attention.self.key", "attention.self.value", "attention.output.dense",
+                          "attention.output.LayerNorm", "intermediate.dense", "output.dense", "output.LayerNorm"})
+      lin_names(b + e);
+  }
+  if (c.vit_width) {
+    const std::string v = P + "encoder.visual_model.visual.";
+    need.push_back(v + "conv1.weight"); need.push_back(v + "class_embedding"); need.push_back(v + "positional_embedding");
+    lin_names(v + "ln_pre"); lin_names(v + "ln_post");
+    for (int l = 0; l < c.vit_layers; ++l) {
+      const std::string b = v + "transformer.resblocks." + std::to_string(l) + ".";
+      need.push_back(b + "attn.in_proj_weight"); need.push_back(b + "attn.in_proj_bias");
+      for (const char* e : {"attn.out_proj", "ln_1", "mlp.c_fc", "mlp.c_proj", "ln_2"}) lin_names(b + e);
+    }
+    lin_names(P + "encoder.visn_fc.visn_fc"); lin_names(P + "encoder.visn_fc.visn_layer_norm");
+  }
+  for (int l = 0; l < c.para_layers; ++l) {
+    const std::string b = "encoder.transformer_inter." + std::to_string(l) + ".";
+    for (const char* e : {"self_attn.linear_keys", "self_attn.linear_values", "self_attn.linear_query", "self_attn.final_linear",
+                          "feed_forward.w_1", "feed_forward.w_2", "feed_forward.layer_norm", "layer_norm"})
+      lin_names(b + e);
+  }
+  lin_names("encoder.layer_norm"); lin_names("key_linear"); lin_names("query_linear"); lin_names("tanh_linear");
+  for (const char* e : {"decoder.weight_ih_l0", "decoder.weight_hh_l0", "decoder.bias_ih_l0", "decoder.bias_hh_l0", "pw_k.weight",
+                        "two_level_encoder.linear_in_2.weight"})
+    need.push_back(e);
+  for (const char* e : {"two_level_encoder.sentence_tran", "two_level_encoder.sentence_tran_2",
+                        "two_level_encoder.pairwise_relationship", "two_level_encoder.h1_relationship",
+                        "two_level_encoder.h2_relationship"})
+    lin_names(e);
+  for (auto& n : need)
+    if (!m->raw.count(n)) miss += n + " ";
+  if (!miss.empty()) {
+    set_error("state_dict incomplete, missing: %.1800s", miss.c_str());
+    return MSQ_ERR_WEIGHT;
+  }
+
+  // ---- embeddings + BERT stack
+  m->word = W(P + "embeddings.word_embeddings.weight", (int64_t)c.vocab * H);
+  m->pos = W(P + "embeddings.position_embeddings.weight", (int64_t)c.max_pos * H);
+  m->type = W(P + "embeddings.token_type_embeddings.weight", (int64_t)c.type_vocab * H);
+  m->emb_ln = {W(P + "embeddings.LayerNorm.weight", H), W(P + "embeddings.LayerNorm.bias", H)};
+  if (!m->word || !m->pos || !m->type) return MSQ_ERR_WEIGHT;
+  m->bert.resize(c.layers);
+  for (int l = 0; l < c.layers; ++l) {
+    const std::string b = P + "encoder.layer." + std::to_string(l) + ".";
+    BertLayerW& L = m->bert[l];
+    const float *wq, *bq;
+    MSQ_TRY(concat3(m, W(b + "attention.self.query.weight", (int64_t)H * H), W(b + "attention.self.key.weight", (int64_t)H * H),
+                    W(b + "attention.self.value.weight", (int64_t)H * H), (int64_t)H * H, (int64_t)H * H, (int64_t)H * H, &wq, st));
+    MSQ_TRY(concat3(m, W(b + "attention.self.query.bias", H), W(b + "attention.self.key.bias", H),
+                    W(b + "attention.self.value.bias", H), H, H, H, &bq, st));
+    MSQ_TRY(make_lin(m, wq, bq, 3 * H, H, H, w16, &L.qkv, st));
+    MSQ_TRY(make_lin(m, W(b + "attention.output.dense.weight", (int64_t)H * H), W(b + "attention.output.dense.bias", H), H, H, H,
+                     w16, &L.out, st));
+    MSQ_TRY(make_lin(m, W(b + "intermediate.dense.weight", (int64_t)c.inter * H), W(b + "intermediate.dense.bias", c.inter),
+                     c.inter, H, H, w16, &L.up, st));
+    MSQ_TRY(make_lin(m, W(b + "output.dense.weight", (int64_t)H * c.inter), W(b + "output.dense.bias", H), H, c.inter, c.inter,
+                     w16, &L.down, st));
+    L.ln1 = {W(b + "attention.output.LayerNorm.weight", H), W(b + "attention.output.LayerNorm.bias", H)};
+    L.ln2 = {W(b + "output.LayerNorm.weight", H), W(b + "output.LayerNorm.bias", H)};
+  }
+  if (m->raw.count(P + "pooler.dense.weight")) {
+    MSQ_TRY(make_lin(m, W(P + "pooler.dense.weight", (int64_t)H * H), W(P + "pooler.dense.bias", H), H, H, H, false, &m->pooler, st));
+    m->has_pooler = true;
+  }
+  // ---- ViT tower
+  if (c.vit_width) {
+    const int Wd = c.vit_width, g = c.vit_res / c.vit_patch, Kc = 3 * c.vit_patch * c.vit_patch;
+    const std::string v = P + "encoder.visual_model.visual.";
+    MSQ_TRY(make_lin(m, W(v + "conv1.weight", (int64_t)Wd * Kc), nullptr, Wd, Kc, Kc, w16, &m->conv1, st));
+    m->vit_cls = W(v + "class_embedding", Wd);
+    m->vit_pos = W(v + "positional_embedding", (int64_t)(g * g + 1) * Wd);
+    m->ln_pre = {W(v + "ln_pre.weight", Wd), W(v + "ln_pre.bias", Wd)};
+    m->ln_post = {W(v + "ln_post.weight", Wd), W(v + "ln_post.bias", Wd)};
+    m->vit.resize(c.vit_layers);
+    for (int l = 0; l < c.vit_layers; ++l) {
+      const std::string b = v + "transformer.resblocks." + std::to_string(l) + ".";
+      VitLayerW& L = m->vit[l];
+      MSQ_TRY(make_lin(m, W(b + "attn.in_proj_weight", (int64_t)3 * Wd * Wd), W(b + "attn.in_proj_bias", 3 * Wd), 3 * Wd, Wd, Wd,
+                       w16, &L.qkv, st));
+      MSQ_TRY(make_lin(m, W(b + "attn.out_proj.weight", (int64_t)Wd * Wd), W(b + "attn.out_proj.bias", Wd), Wd, Wd, Wd, w16, &L.out, st));
+      MSQ_TRY(make_lin(m, W(b + "mlp.c_fc.weight", (int64_t)4 * Wd * Wd), W(b + "mlp.c_fc.bias", 4 * Wd), 4 * Wd, Wd, Wd, w16, &L.fc, st));
+      MSQ_TRY(make_lin(m, W(b + "mlp.c_proj.weight", (int64_t)4 * Wd * Wd), W(b + "mlp.c_proj.bias", Wd), Wd, 4 * Wd, 4 * Wd, w16,
+                       &L.proj, st));
+      L.ln1 = {W(b + "ln_1.weight", Wd), W(b + "ln_1.bias", Wd)};
+      L.ln2 = {W(b + "ln_2.weight", Wd), W(b + "ln_2.bias", Wd)};
+    }
+    MSQ_TRY(make_lin(m, W(P + "encoder.visn_fc.visn_fc.weight", (int64_t)H * Wd), W(P + "encoder.visn_fc.visn_fc.bias", H), H, Wd, Wd,
+                     w16, &m->visn_fc, st));
+    m->visn_ln = {W(P + "encoder.visn_fc.visn_layer_norm.weight", H), W(P + "encoder.visn_fc.visn_layer_norm.bias", H)};
+  }
+  // ---- BERSON heads
+  const std::string T = "two_level_encoder.";
+  MSQ_TRY(make_lin(m, W(T + "sentence_tran.weight", (int64_t)H * H), W(T + "sentence_tran.bias", H), H, H, H, w16, &m->sent_tran, st));
+  m->w2 = W(T + "sentence_tran_2.weight", H);
+  m->b2 = W(T + "sentence_tran_2.bias", 1);
+  m->w_in2 = W(T + "linear_in_2.weight", H);
+  MSQ_TRY(concat3(m, W(T + "pairwise_relationship.weight", 2 * H), W(T + "h1_relationship.weight", 2 * H),
+                  W(T + "h2_relationship.weight", 2 * H), 2 * H, 2 * H, 2 * H, &m->w_rel, st));
+  MSQ_TRY(concat3(m, W(T + "pairwise_relationship.bias", 2), W(T + "h1_relationship.bias", 2), W(T + "h2_relationship.bias", 2), 2, 2,
+                  2, &m->b_rel, st));
+  m->para.resize(c.para_layers);
+  for (int l = 0; l < c.para_layers; ++l) {
+    const std::string b = "encoder.transformer_inter." + std::to_string(l) + ".";
+    ParaLayerW& L = m->para[l];
+    const float *wq, *bq;
+    MSQ_TRY(concat3(m, W(b + "self_attn.linear_query.weight", (int64_t)H * H), W(b + "self_attn.linear_keys.weight", (int64_t)H * H),
+                    W(b + "self_attn.linear_values.weight", (int64_t)H * H), (int64_t)H * H, (int64_t)H * H, (int64_t)H * H, &wq, st));
+    MSQ_TRY(concat3(m, W(b + "self_attn.linear_query.bias", H), W(b + "self_attn.linear_keys.bias", H),
+                    W(b + "self_attn.linear_values.bias", H), H, H, H, &bq, st));
+    MSQ_TRY(make_lin(m, wq, bq, 3 * H, H, H, false, &L.qkv, st));
+    MSQ_TRY(make_lin(m, W(b + "self_attn.final_linear.weight", (int64_t)H * H), W(b + "self_attn.final_linear.bias", H), H, H, H, false,
+                     &L.fin, st));
+    MSQ_TRY(make_lin(m, W(b + "feed_forward.w_1.weight", (int64_t)c.para_ff * H), W(b + "feed_forward.w_1.bias", c.para_ff), c.para_ff,
+                     H, H, false, &L.w1, st));
+    MSQ_TRY(make_lin(m, W(b + "feed_forward.w_2.weight", (int64_t)H * c.para_ff), W(b + "feed_forward.w_2.bias", H), H, c.para_ff,
+                     c.para_ff, false, &L.w2, st));
+    L.ln_in = {W(b + "layer_norm.weight", H), W(b + "layer_norm.bias", H)};
+    L.ln_ff = {W(b + "feed_forward.layer_norm.weight", H), W(b + "feed_forward.layer_norm.bias", H)};
+  }
+  m->para_ln = {W("encoder.layer_norm.weight", H), W("encoder.layer_norm.bias", H)};
+  MSQ_TRY(make_lin(m, W("key_linear.weight", (int64_t)2 * H * H), W("key_linear.bias", H), H, 2 * H, 2 * H, false, &m->key_lin, st));
+  // decoder repacks
+  {
+    float *wih_perm, *bias_perm, *whh_t, *wq_t, *wpw4;
+    m->Kp = ((H + 2) + 15) / 16 * 16;
+    MSQ_TRY(dev_alloc(m, (size_t)4 * H * H, &wih_perm));
+    MSQ_TRY(dev_alloc(m, (size_t)4 * H, &bias_perm));
+    MSQ_TRY(dev_alloc(m, (size_t)4 * H * H, &whh_t));
+    MSQ_TRY(dev_alloc(m, (size_t)H * H, &wq_t));
+    MSQ_TRY(dev_alloc(m, (size_t)4 * H * m->Kp, &wpw4));
+    pack_lstm_kernel<<<512, 256, 0, st>>>(W("decoder.weight_ih_l0", (int64_t)4 * H * H), W("decoder.weight_hh_l0", (int64_t)4 * H * H),
+                                          W("decoder.bias_ih_l0", 4 * H), W("decoder.bias_hh_l0", 4 * H), H, wih_perm, bias_perm, whh_t);
+    MSQ_LAUNCH_CHECK();
+    transpose_kernel<<<256, 256, 0, st>>>(W("query_linear.weight", (int64_t)H * H), H, H, wq_t);
+    MSQ_LAUNCH_CHECK();
+    pack_pwk_kernel<<<512, 256, 0, st>>>(W("pw_k.weight", (int64_t)H * 4 * (H + 2)), H, m->Kp, wpw4);
+    MSQ_LAUNCH_CHECK();
+    m->xg_lin.w32 = wih_perm; m->xg_lin.b = bias_perm; m->xg_lin.N = 4 * H; m->xg_lin.K = H; m->xg_lin.ld = H;
+    m->t4_lin.w32 = wpw4; m->t4_lin.b = nullptr; m->t4_lin.N = 4 * H; m->t4_lin.K = m->Kp; m->t4_lin.ld = m->Kp;
+    m->dec.whh_t = whh_t; m->dec.wq_t = wq_t; m->dec.bq = W("query_linear.bias", H);
+    m->dec.wt = W("tanh_linear.weight", H);
+    float bt = 0.f;
+    MSQ_CUDA(cudaMemcpyAsync(&bt, W("tanh_linear.bias", 1), sizeof(float), cudaMemcpyDeviceToHost, st));
+    MSQ_CUDA(cudaStreamSynchronize(st));
+    m->dec.bt = bt;
+  }
+  if (!miss.empty()) {
+    set_error("state_dict incomplete, missing: %.1800s", miss.c_str());
+    return MSQ_ERR_WEIGHT;
+  }
+  MSQ_CUDA(cudaStreamSynchronize(st));
+  m->packed = true;
+  return MSQ_OK;
+}
+
+// =====================================================================================================
+// encoder orchestration
+// =====================================================================================================
+namespace msq {
+
+struct VitBufs {
+  void* apatch; float* patch; float* xv; void* y; void* qkv; void* ctx; void* hbuf;
+};
+constexpr int64_t IMG_CHUNK = 1024;  // images per im2col + patch-embed GEMM launch
+
+template <typename T>
+static void plan_vit(const msq_config& c, Planner& p, int64_t n_img, int64_t R, VitBufs* b) {
+  const int g2 = (c.vit_res / c.vit_patch) * (c.vit_res / c.vit_patch), Lv = 1 + 2 * g2, Wd = c.vit_width;
+  const int Kc = 3 * c.vit_patch * c.vit_patch;
+  b->apatch = p.take<T>((size_t)min(n_img, IMG_CHUNK) * g2 * Kc);
+  b->patch = p.take<float>((size_t)n_img * g2 * Wd);
+  b->xv = p.take<float>((size_t)R * Lv * Wd);
+  b->y = p.take<T>((size_t)R * Lv * Wd);
+  b->qkv = p.take<T>((size_t)R * Lv * 3 * Wd);
+  b->ctx = p.take<T>((size_t)R * Lv * Wd);
+  b->hbuf = p.take<T>((size_t)R * Lv * 4 * Wd);
+}
+
+// conv1 (32x32 / stride 32, no bias) as im2col + GEMM over all UNIQUE images -> b.patch [n_img*g2, W]
+template <typename T>
+static int run_patch_embed(msq_model* m, const float* images, int64_t n_img, VitBufs& b, cudaStream_t st) {
+  const msq_config& c = m->cfg;
+  const int g = c.vit_res / c.vit_patch, g2 = g * g, Wd = c.vit_width;
+  const int64_t img_elems = (int64_t)3 * c.vit_res * c.vit_res;
+  for (int64_t i0 = 0; i0 < n_img; i0 += IMG_CHUNK) {
+    const int64_t n = min(IMG_CHUNK, n_img - i0);
+    MSQ_TRY(im2col<T>(images + i0 * img_elems, n, c.vit_res, c.vit_patch, (T*)b.apatch, st));
+    MSQ_TRY((run_gemm<T, float>(m, (const T*)b.apatch, m->conv1.K, m->conv1, nullptr, 0, b.patch + i0 * g2 * Wd, Wd, n * g2, ACT_NONE,
+                                st, false)));
+  }
+  return MSQ_OK;
+}
+
+// token assembly + ln_pre + the residual blocks for R pair rows; xv holds the final residual stream
+// (ln_post is applied by the caller).  img_index [R*2] addresses rows of b.patch by image.
+template <typename T>
+static int run_vit(msq_model* m, const int32_t* img_index, int64_t R, VitBufs& b, cudaStream_t st) {
+  const msq_config& c = m->cfg;
+  const int g = c.vit_res / c.vit_patch, g2 = g * g, Lv = 1 + 2 * g2, Wd = c.vit_width, heads = Wd / 64;
+  const int64_t Mv = R * Lv;
+  MSQ_TRY(vit_assemble(b.patch, img_index, R, 2, g2, Wd, m->vit_cls, m->vit_pos, m->ln_pre.g, m->ln_pre.b, 1e-5f, b.xv, st));
+  for (auto& L : m->vit) {
+    MSQ_TRY(layernorm<T>(b.xv, Mv, Wd, L.ln1.g, L.ln1.b, 1e-5f, nullptr, (T*)b.y, 0, 0, 0, st));
+    MSQ_TRY((run_gemm<T, T>(m, (const T*)b.y, Wd, L.qkv, nullptr, 0, (T*)b.qkv, 3 * Wd, Mv, ACT_NONE, st)));
+    MSQ_TRY(attention<T>((const T*)b.qkv, R, Lv, heads, 64, 0.125f, nullptr, 0, 0, (T*)b.ctx, st));
+    MSQ_TRY((run_gemm<T, float>(m, (const T*)b.ctx, Wd, L.out, b.xv, Wd, b.xv, Wd, Mv, ACT_NONE, st)));
+    MSQ_TRY(layernorm<T>(b.xv, Mv, Wd, L.ln2.g, L.ln2.b, 1e-5f, nullptr, (T*)b.y, 0, 0, 0, st));
+    MSQ_TRY((run_gemm<T, T>(m, (const T*)b.y, Wd, L.fc, nullptr, 0, (T*)b.hbuf, 4 * Wd, Mv, ACT_QUICK_GELU, st)));
+    MSQ_TRY((run_gemm<T, float>(m, (const T*)b.hbuf, 4 * Wd, L.proj, b.xv, Wd, b.xv, Wd, Mv, ACT_NONE, st)));
+  }
+  return MSQ_OK;
+}
+
+struct JointBufs {
+  float* x; void* xt; float* tmp; void* qkv; void* ctx; void* hbuf; float* mask_add; float* vtmp;
+};
+
+template <typename T>
+static void plan_joint(const msq_config& c, Planner& p, int64_t R, int Lt, int Lj, JointBufs* b) {
+  const int H = c.hidden;
+  b->x = p.take<float>((size_t)R * Lj * H);
+  b->xt = p.take<T>((size_t)R * Lj * H);
+  b->tmp = p.take<float>((size_t)R * Lj * H);
+  b->qkv = p.take<T>((size_t)R * Lj * 3 * H);
+  b->ctx = p.take<T>((size_t)R * Lj * H);
+  b->hbuf = p.take<T>((size_t)R * Lj * c.inter);
+  b->mask_add = p.take<float>((size_t)R * Lt);
+  b->vtmp = nullptr;
+}
+
+// inner encoder for R pair rows -> b.x holds the final joint stream [R, Lj, H] (fp32), b.xt its T copy
+template <typename T>
+static int run_inner(msq_model* m, const int64_t* ids, const int64_t* tt, const int64_t* mask, int64_t R, int Lt,
+                     const int32_t* img_index, VitBufs& vb, JointBufs& jb, cudaStream_t st) {
+  const msq_config& c = m->cfg;
+  const int H = c.hidden;
+  const bool mm = c.vit_width != 0 && img_index != nullptr;
+  const int g2 = mm ? (c.vit_res / c.vit_patch) * (c.vit_res / c.vit_patch) : 0;
+  const int Lv = mm ? 1 + 2 * g2 : 0, Lj = Lt + Lv;
+  MSQ_REQUIRE(Lt <= c.max_pos, "Lt=%d exceeds max_position_embeddings=%d", Lt, c.max_pos);
+  const int64_t Mj = R * Lj;
+  MSQ_TRY(embed_ln<T>(ids, tt, R, Lt, Lj, H, m->word, m->pos, m->type, m->emb_ln.g, m->emb_ln.b, 1e-12f, jb.x, (T*)jb.xt, st));
+  mask_add_kernel<<<ceil_div(R * Lt, 256), 256, 0, st>>>(mask, R * Lt, jb.mask_add);
+  MSQ_LAUNCH_CHECK();
+  if (mm) {
+    MSQ_TRY(run_vit<T>(m, img_index, R, vb, st));
+    const int Wd = c.vit_width;
+    const int64_t Mv = R * Lv;
+    MSQ_TRY(layernorm<T>(vb.xv, Mv, Wd, m->ln_post.g, m->ln_post.b, 1e-5f, nullptr, (T*)vb.y, 0, 0, 0, st));
+    // visn_fc output reuses the (now free) fp32 tmp buffer of the joint stream
+    MSQ_TRY((run_gemm<T, float>(m, (const T*)vb.y, Wd, m->visn_fc, nullptr, 0, jb.tmp, H, Mv, ACT_NONE, st)));
+    MSQ_TRY(layernorm<T>(jb.tmp, Mv, H, m->visn_ln.g, m->visn_ln.b, 1e-12f, jb.x, (T*)jb.xt, Lv, Lj, Lt, st));
+  }
+  for (auto& L : m->bert) {
+    MSQ_TRY((run_gemm<T, T>(m, (const T*)jb.xt, H, L.qkv, nullptr, 0, (T*)jb.qkv, 3 * H, Mj, ACT_NONE, st)));
+    MSQ_TRY(attention<T>((const T*)jb.qkv, R, Lj, c.heads, 64, 0.125f, jb.mask_add, Lt, Lt, (T*)jb.ctx, st));
+    MSQ_TRY((run_gemm<T, float>(m, (const T*)jb.ctx, H, L.out, jb.x, H, jb.tmp, H, Mj, ACT_NONE, st)));
+    MSQ_TRY(layernorm<T>(jb.tmp, Mj, H, L.ln1.g, L.ln1.b, 1e-12f, jb.x, (T*)jb.xt, 0, 0, 0, st));
+    MSQ_TRY((run_gemm<T, T>(m, (const T*)jb.xt, H, L.up, nullptr, 0, (T*)jb.hbuf, c.inter, Mj, ACT_GELU_ERF, st)));
+    MSQ_TRY((run_gemm<T, float>(m, (const T*)jb.hbuf, c.inter, L.down, jb.x, H, jb.tmp, H, Mj, ACT_NONE, st)));
+    MSQ_TRY(layernorm<T>(jb.tmp, Mj, H, L.ln2.g, L.ln2.b, 1e-12f, jb.x, (T*)jb.xt, 0, 0, 0, st));
+  }
+  return MSQ_OK;
+}
+
+struct HeadBufs {   // whole batch, fp32
+  float *mix, *rel6, *sents, *r0, *para, *pa, *pb, *pn, *pqkv, *pctx, *pff, *h0, *keyin, *key, *sents_ext, *xg, *t4;
+  void *topt, *ttb;
+};
+
+template <typename T>
+static void plan_heads(const msq_config& c, Planner& p, int64_t B, int N, int64_t Rc, int Lt, int Kp, HeadBufs* h) {
+  const int H = c.hidden;
+  const int64_t R = B * N * (N - 1);
+  h->topt = p.take<T>((size_t)Rc * Lt * H);
+  h->ttb = p.take<T>((size_t)Rc * Lt * H);
+  h->mix = p.take<float>((size_t)R * 2 * H);
+  h->rel6 = p.take<float>((size_t)R * 6);
+  h->sents = p.take<float>((size_t)B * N * H);
+  h->r0 = p.take<float>((size_t)B * N * N * Kp);
+  h->para = p.take<float>((size_t)B * N * H);
+  h->pa = p.take<float>((size_t)B * N * H);
+  h->pb = p.take<float>((size_t)B * N * H);
+  h->pn = p.take<float>((size_t)B * N * H);
+  h->pqkv = p.take<float>((size_t)B * N * 3 * H);
+  h->pctx = p.take<float>((size_t)B * N * H);
+  h->pff = p.take<float>((size_t)B * N * c.para_ff);
+  h->h0 = p.take<float>((size_t)B * H);
+  h->keyin = p.take<float>((size_t)B * N * 2 * H);
+  h->key = p.take<float>((size_t)B * N * H);
+  h->sents_ext = p.take<float>((size_t)B * (N + 1) * H);
+  h->xg = p.take<float>((size_t)B * (N + 1) * 4 * H);
+  h->t4 = p.take<float>((size_t)B * N * N * 4 * H);
+}
+
+static int run_gemm32(const float* A, int lda, const Lin& w, const float* resid, int ldr, float* C, int ldc, int64_t M, int act,
+                      cudaStream_t st) {
+  GemmArgs g;
+  g.A = A; g.W = w.w32; g.bias = w.b; g.resid = resid; g.C = C; g.C2 = nullptr;
+  g.M = M; g.N = w.N; g.K = w.K; g.lda = lda; g.ldw = w.ld; g.ldc = ldc; g.ldr = ldr; g.act = act;
+  return gemm_simt<float, float>(g, st);
+}
+
+// paragraph encoder + key projection for B manuals (fp32): sents -> para, h0, key
+// (models/berson/encoder.py:46-59, 9-29; models/berson/neural.py:30-33; modeling_bert.py:1343-1357)
+static int run_paragraph(msq_model* m, HeadBufs& h, int64_t B, int N, cudaStream_t st) {
+  const msq_config& c = m->cfg;
+  const int H = c.hidden;
+  const int64_t M = B * N;
+  const float* x = h.sents;  // mask_cls is all ones: x * mask == x
+  for (size_t l = 0; l < m->para.size(); ++l) {
+    ParaLayerW& L = m->para[l];
+    const float* y = x;
+    if (l != 0) {
+      MSQ_TRY(layernorm<float>(x, M, H, L.ln_in.g, L.ln_in.b, 1e-6f, h.pn, nullptr, 0, 0, 0, st));
+      y = h.pn;
+    }
+    MSQ_TRY(run_gemm32(y, H, L.qkv, nullptr, 0, h.pqkv, 3 * H, M, ACT_NONE, st));
+    MSQ_TRY(para_attention(h.pqkv, B, N, c.para_heads, H, h.pctx, st));
+    MSQ_TRY(run_gemm32(h.pctx, H, L.fin, x, H, h.pa, H, M, ACT_NONE, st));                   // out = attn + x
+    MSQ_TRY(layernorm<float>(h.pa, M, H, L.ln_ff.g, L.ln_ff.b, 1e-6f, h.pn, nullptr, 0, 0, 0, st));
+    MSQ_TRY(run_gemm32(h.pn, H, L.w1, nullptr, 0, h.pff, c.para_ff, M, ACT_GELU_TANH, st));
+    MSQ_TRY(run_gemm32(h.pff, c.para_ff, L.w2, h.pa, H, h.pb, H, M, ACT_NONE, st));          // x' = ffn + out
+    x = h.pb;
+  }
+  MSQ_TRY(layernorm<float>(x, M, H, m->para_ln.g, m->para_ln.b, 1e-6f, h.para, nullptr, 0, 0, 0, st));
+  MSQ_TRY(para_finish(h.sents, h.para, B, N, H, h.h0, h.keyin, st));
+  MSQ_TRY(run_gemm32(h.keyin, 2 * H, m->key_lin, nullptr, 0, h.key, H, M, ACT_NONE, st));
+  return MSQ_OK;
+}
+
+// decode pre-projections + beam search from (sents, key, h0, r0)
+static int run_decode(msq_model* m, const float* sents, const float* key, const float* h0, const float* r0, float* sents_ext,
+                      float* xg, float* t4, int64_t B, int N, int beam, int32_t* perm, int32_t* tr_ix, float* tr_cost,
+                      float* tr_logp, cudaStream_t st) {
+  const int H = m->cfg.hidden;
+  sents_ext_kernel<<<ceil_div(B * (N + 1) * (int64_t)H, 256), 256, 0, st>>>(sents, B, N, H, sents_ext);
+  MSQ_LAUNCH_CHECK();
+  MSQ_TRY(run_gemm32(sents_ext, H, m->xg_lin, nullptr, 0, xg, 4 * H, B * (N + 1), ACT_NONE, st));
+  MSQ_TRY(run_gemm32(r0, m->Kp, m->t4_lin, nullptr, 0, t4, 4 * H, B * N * N, ACT_NONE, st));
+  if (tr_ix) MSQ_CUDA(cudaMemsetAsync(tr_ix, 0xff, (size_t)B * (N - 1) * beam * sizeof(int32_t), st));
+  DecodeIO io;
+  io.xg = xg; io.t4 = t4; io.key0 = key; io.h0 = h0; io.B = B; io.N = N; io.W = beam; io.H = H;
+  io.perm = perm; io.trace_ix = tr_ix; io.trace_cost = tr_cost; io.trace_logp = tr_logp;
+  return beam_search(m->dec, io, st);
+}
+
+static int chunk_manuals() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MSQ_CHUNK_MANUALS"); v = e ? atoi(e) : 32; if (v < 1) v = 1; }
+  return v;
+}
+
+// Full path for B manuals.  images are UNIQUE images [n_img,3,S,S]; img_index [B*P*2] indexes them.
+template <typename T>
+static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const int64_t* mask, const int64_t* sep, int64_t B, int N,
+                    int Lt, const float* images, int64_t n_img, const int32_t* img_index, const msq_encode_out* out, int beam,
+                    int32_t* perm, cudaStream_t st) {
+  const msq_config& c = m->cfg;
+  MSQ_REQUIRE(m->packed, "msq_model_pack() has not been called");
+  MSQ_REQUIRE(N >= 2 && N <= 16, "N=%d out of range [2,16]", N);
+  MSQ_REQUIRE(!(c.vit_width != 0 && images == nullptr), "multimodal model needs images");
+  const int H = c.hidden, P = N * (N - 1);
+  const bool mm = c.vit_width != 0;
+  const int g2 = mm ? (c.vit_res / c.vit_patch) * (c.vit_res / c.vit_patch) : 0;
+  const int Lv = mm ? 1 + 2 * g2 : 0, Lj = Lt + Lv;
+  const int64_t R = B * P;
+  const int64_t Bc = min((int64_t)chunk_manuals(), B), Rc = Bc * P;
+
+  VitBufs vb{}; JointBufs jb{}; HeadBufs hb{};
+  for (int pass = 0; pass < 2; ++pass) {
+    Planner p{&m->ws, pass == 0};
+    if (pass == 1) m->ws.reset();
+    if (mm) plan_vit<T>(c, p, n_img, Rc, &vb);
+    plan_joint<T>(c, p, Rc, Lt, Lj, &jb);
+    plan_heads<T>(c, p, B, N, Rc, Lt, m->Kp, &hb);
+    if (pass == 0) MSQ_TRY(m->ws.reserve(p.need + 4096, st));
+  }
+  if (mm) MSQ_TRY(run_patch_embed<T>(m, images, n_img, vb, st));  // once per UNIQUE image, not per pair slot
+
+  for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+    const int64_t bc = min(Bc, B - b0), rc = bc * P, r0 = b0 * P;
+    MSQ_TRY((run_inner<T>(m, ids + r0 * Lt, tt + r0 * Lt, mask + r0 * Lt, rc, Lt, mm ? img_index + r0 * 2 : nullptr, vb, jb, st)));
+    // ---- pooling for this chunk
+    MSQ_TRY((gather_rows<float, T>(jb.x, rc * Lt, H, Lt, Lj, 0, (T*)hb.topt, st)));
+    MSQ_TRY((run_gemm<T, T>(m, (const T*)hb.topt, H, m->sent_tran, nullptr, 0, (T*)hb.ttb, H, rc * Lt, ACT_TANH, st)));
+    MSQ_TRY(token_pool<T>((const T*)hb.ttb, jb.x, rc, Lt, Lj, H, m->w2, m->b2, sep + r0 * 2, m->w_rel, m->b_rel, hb.mix + r0 * 2 * H,
+                          hb.rel6 + r0 * 6, st));
+    const int64_t cell0 = b0 * N * N;
+    MSQ_TRY(edge_pool(hb.mix + r0 * 2 * H, jb.x, hb.rel6 + r0 * 6, bc, N, Lj, H, m->w_in2, hb.sents + b0 * N * H,
+                      hb.r0 + cell0 * m->Kp, m->Kp, out && out->cls_mat ? out->cls_mat + cell0 * H : nullptr,
+                      out && out->score_mat ? out->score_mat + cell0 * 2 : nullptr, out && out->his1 ? out->his1 + cell0 * 2 : nullptr,
+                      out && out->his2 ? out->his2 + cell0 * 2 : nullptr, out && out->cls ? out->cls + r0 * H : nullptr, st));
+    if (out && out->top_vec) MSQ_TRY((gather_rows<float, float>(jb.x, rc * Lt, H, Lt, Lj, 0, out->top_vec + r0 * Lt * H, st)));
+  }
+  MSQ_TRY(run_paragraph(m, hb, B, N, st));
+  if (out) {
+    auto cp = [&](float* dst, const float* src, size_t n) -> int {
+      if (dst) MSQ_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      return MSQ_OK;
+    };
+    MSQ_TRY(cp(out->sents, hb.sents, (size_t)B * N * H));
+    MSQ_TRY(cp(out->para, hb.para, (size_t)B * N * H));
+    MSQ_TRY(cp(out->h0, hb.h0, (size_t)B * H));
+    MSQ_TRY(cp(out->key, hb.key, (size_t)B * N * H));
+    if (out->cls_score) MSQ_CUDA(cudaMemcpy2DAsync(out->cls_score, 2 * sizeof(float), hb.rel6, 6 * sizeof(float), 2 * sizeof(float),
+                                                   (size_t)R, cudaMemcpyDeviceToDevice, st));
+  }
+  if (perm)
+    MSQ_TRY(run_decode(m, hb.sents, hb.key, hb.h0, hb.r0, hb.sents_ext, hb.xg, hb.t4, B, N, beam, perm, nullptr, nullptr, nullptr, st));
+  return MSQ_OK;
+}
+
+}  // namespace msq
+
+// =====================================================================================================
+// C ABI: encoders / encode / decode / whole path
+// =====================================================================================================
+
+extern "C" int msq_vit_forward(msq_model* m, const float* images_dev, int64_t n_img, const int32_t* img_index_dev, int64_t R,
+                               float* out_dev, void* stream) {
+  MSQ_REQUIRE(m && m->packed && m->cfg.vit_width, "model has no visual tower / not packed");
+  cudaStream_t st = (cudaStream_t)stream;
+  const msq_config& c = m->cfg;
+  const int g2 = (c.vit_res / c.vit_patch) * (c.vit_res / c.vit_patch), Lv = 1 + 2 * g2;
+  VitBufs vb{};
+  auto go = [&](auto tag) -> int {
+    using T = decltype(tag);
+    for (int pass = 0; pass < 2; ++pass) {
+      Planner p{&m->ws, pass == 0};
+      if (pass == 1) m->ws.reset();
+      plan_vit<T>(c, p, n_img, R, &vb);
+      if (pass == 0) MSQ_TRY(m->ws.reserve(p.need + 4096, st));
+    }
+    MSQ_TRY(run_patch_embed<T>(m, images_dev, n_img, vb, st));
+    MSQ_TRY(run_vit<T>(m, img_index_dev, R, vb, st));
+    return layernorm<float>(vb.xv, R * Lv, c.vit_width, m->ln_post.g, m->ln_post.b, 1e-5f, out_dev, nullptr, 0, 0, 0, st);
+  };
+  return c.precise ? go(float()) : go(bf16());
+}
+
+extern "C" int msq_inner_forward(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev, int64_t R,
+                                 int32_t Lt, const float* images_dev, int64_t n_img, const int32_t* img_index_dev, float* lang_dev,
+                                 float* visn_dev, float* pooled_dev, void* stream) {
+  MSQ_REQUIRE(m && m->packed, "model not packed");
+  cudaStream_t st = (cudaStream_t)stream;
+  const msq_config& c = m->cfg;
+  const bool mm = c.vit_width != 0 && images_dev != nullptr;
+  const int g2 = mm ? (c.vit_res / c.vit_patch) * (c.vit_res / c.vit_patch) : 0, Lv = mm ? 1 + 2 * g2 : 0, Lj = Lt + Lv;
+  const int H = c.hidden;
+  VitBufs vb{}; JointBufs jb{};
+  auto go = [&](auto tag) -> int {
+    using T = decltype(tag);
+    for (int pass = 0; pass < 2; ++pass) {
+      Planner p{&m->ws, pass == 0};
+      if (pass == 1) m->ws.reset();
+      if (mm) plan_vit<T>(c, p, n_img, R, &vb);
+      plan_joint<T>(c, p, R, Lt, Lj, &jb);
+      if (pass == 0) MSQ_TRY(m->ws.reserve(p.need + 4096, st));
+    }
+    if (mm) MSQ_TRY(run_patch_embed<T>(m, images_dev, n_img, vb, st));
+    MSQ_TRY((run_inner<T>(m, ids_dev, tt_dev, mask_dev, R, Lt, mm ? img_index_dev : nullptr, vb, jb, st)));
+    if (lang_dev) MSQ_TRY((gather_rows<float, float>(jb.x, R * Lt, H, Lt, Lj, 0, lang_dev, st)));
+    if (visn_dev && mm) MSQ_TRY((gather_rows<float, float>(jb.x, R * Lv, H, Lv, Lj, Lt, visn_dev, st)));
+    if (pooled_dev) {
+      MSQ_REQUIRE(m->has_pooler, "model has no pooler.dense weights");
+      MSQ_TRY(run_gemm32(jb.x, Lj * H, m->pooler, nullptr, 0, pooled_dev, H, R, ACT_NONE, st));
+    }
+    return MSQ_OK;
+  };
+  return c.precise ? go(float()) : go(bf16());
+}
+
+extern "C" int msq_encode(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev,
+                          const int64_t* sep_dev, int64_t B, int32_t N, int32_t Lt, const float* images_dev, int64_t n_img,
+                          const int32_t* img_index_dev, const msq_encode_out* out, void* stream) {
+  MSQ_REQUIRE(m && out, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m->cfg.precise)
+    return run_path<float>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, out, 0, nullptr, st);
+  return run_path<bf16>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, out, 0, nullptr, st);
+}
+
+extern "C" int msq_order_manuals_dev(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev,
+                                     const int64_t* sep_dev, int64_t B, int32_t N, int32_t Lt, const float* images_dev,
+                                     int64_t n_img, const int32_t* img_index_dev, int32_t beam, int32_t* perm_dev, void* stream) {
+  MSQ_REQUIRE(m && perm_dev, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m->cfg.precise)
+    return run_path<float>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, nullptr, beam, perm_dev, st);
+  return run_path<bf16>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, nullptr, beam, perm_dev, st);
+}
+
+extern "C" int msq_beam_search(msq_model* m, const float* sents_dev, const float* key_dev, const float* h0_dev,
+                               const float* cls_mat_dev, const float* score_mat_dev, int64_t B, int32_t N, int32_t beam,
+                               int32_t* perm_dev, int32_t* trace_ix_dev, float* trace_cost_dev, float* trace_logp_dev, void* stream) {
+  MSQ_REQUIRE(m && m->packed, "model not packed");
+  MSQ_REQUIRE(N >= 2 && N <= 16, "N=%d out of range", N);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = m->cfg.hidden;
+  float *r0 = nullptr, *sents_ext = nullptr, *xg = nullptr, *t4 = nullptr;
+  for (int pass = 0; pass < 2; ++pass) {
+    Planner p{&m->ws, pass == 0};
+    if (pass == 1) m->ws.reset();
+    r0 = p.take<float>((size_t)B * N * N * m->Kp);
+    sents_ext = p.take<float>((size_t)B * (N + 1) * H);
+    xg = p.take<float>((size_t)B * (N + 1) * 4 * H);
+    t4 = p.take<float>((size_t)B * N * N * 4 * H);
+    if (pass == 0) MSQ_TRY(m->ws.reserve(p.need + 4096, st));
+  }
+  if (B == 0) return MSQ_OK;
+  build_r0_kernel<<<(unsigned)(B * N * N), 128, 0, st>>>(cls_mat_dev, score_mat_dev, B * N * N, H, m->Kp, r0);
+  MSQ_LAUNCH_CHECK();
+  return run_decode(m, sents_dev, key_dev, h0_dev, r0, sents_ext, xg, t4, B, N, beam, perm_dev, trace_ix_dev, trace_cost_dev,
+                    trace_logp_dev, st);
+}
+
+extern "C" int msq_order_manuals_host(msq_model* m, const int64_t* ids_host, const int64_t* tt_host, const int64_t* mask_host,
+                                      const int64_t* sep_host, int64_t B, int32_t N, int32_t Lt, const float* images_host,
+                                      int64_t n_img, const int32_t* img_index_host, int32_t beam, int32_t* perm_host, void* stream) {
+  MSQ_REQUIRE(m && m->packed && perm_host, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t R = B * N * (N - 1);
+  const size_t n_tok = (size_t)R * Lt, img_elems = images_host ? (size_t)n_img * 3 * m->cfg.vit_res * m->cfg.vit_res : 0;
+  // staging buffers live outside the workspace arena (which run_path re-plans)
+  static thread_local char* stage = nullptr;
+  static thread_local size_t stage_cap = 0;
+  const size_t need = 3 * n_tok * 8 + (size_t)R * 2 * 8 + img_elems * 4 + (size_t)R * 2 * 4 + (size_t)B * N * 4 + 8 * 256;
+  if (need > stage_cap) {
+    MSQ_CUDA(cudaStreamSynchronize(st));
+    if (stage) MSQ_CUDA(cudaFree(stage));
+    stage = nullptr; stage_cap = 0;
+    MSQ_CUDA(cudaMalloc(&stage, need));
+    stage_cap = need;
+  }
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { char* p = stage + off; off += (bytes + 255) & ~size_t(255); return p; };
+  int64_t* ids = (int64_t*)carve(n_tok * 8);
+  int64_t* tt = (int64_t*)carve(n_tok * 8);
+  int64_t* mask = (int64_t*)carve(n_tok * 8);
+  int64_t* sep = (int64_t*)carve((size_t)R * 2 * 8);
+  float* img = (float*)carve(img_elems * 4);
+  int32_t* idx = (int32_t*)carve((size_t)R * 2 * 4);
+  int32_t* perm = (int32_t*)carve((size_t)B * N * 4);
+  MSQ_CUDA(cudaMemcpyAsync(ids, ids_host, n_tok * 8, cudaMemcpyHostToDevice, st));
+  MSQ_CUDA(cudaMemcpyAsync(tt, tt_host, n_tok * 8, cudaMemcpyHostToDevice, st));
+  MSQ_CUDA(cudaMemcpyAsync(mask, mask_host, n_tok * 8, cudaMemcpyHostToDevice, st));
+  MSQ_CUDA(cudaMemcpyAsync(sep, sep_host, (size_t)R * 2 * 8, cudaMemcpyHostToDevice, st));
+  if (images_host) {
+    MSQ_CUDA(cudaMemcpyAsync(img, images_host, img_elems * 4, cudaMemcpyHostToDevice, st));
+    MSQ_CUDA(cudaMemcpyAsync(idx, img_index_host, (size_t)R * 2 * 4, cudaMemcpyHostToDevice, st));
+  }
+  MSQ_TRY(msq_order_manuals_dev(m, ids, tt, mask, sep, B, N, Lt, images_host ? img : nullptr, n_img, images_host ? idx : nullptr, beam,
+                                perm, stream));
+  MSQ_CUDA(cudaMemcpyAsync(perm_host, perm, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
+  MSQ_CUDA(cudaStreamSynchronize(st));
+  return MSQ_OK;
+}
+
+// =====================================================================================================
+// building blocks for kernel-level tests / roofline lines
+// =====================================================================================================
+
+extern "C" int msq_gemm(int32_t dtype, const void* A_dev, const void* W_dev, const float* bias_dev, const float* resid_dev,
+                        void* C_dev, int64_t M, int32_t N, int32_t K, int32_t act, void* stream) {
+  GemmArgs g;
+  g.A = A_dev; g.W = W_dev; g.bias = bias_dev; g.resid = resid_dev; g.C = C_dev; g.C2 = nullptr;
+  g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldc = N; g.ldr = N; g.act = act;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case 0: return gemm_simt<float, float>(g, st);
+    case 1: return gemm_tc<float>(g, st);
+    case 2: return gemm_tc<bf16>(g, st);
+    case 3: return gemm_simt<bf16, float>(g, st);
+    case 4: return gemm_simt<bf16, bf16>(g, st);
+  }
+  set_error("msq_gemm: unknown dtype %d", dtype);
+  return MSQ_ERR_ARG;
+}
+
+extern "C" int msq_layernorm(int32_t dtype, const float* x_dev, int64_t rows, int32_t H, const float* gamma_dev,
+                             const float* beta_dev, float eps, void* out_dev, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == 0) return layernorm<float>(x_dev, rows, H, gamma_dev, beta_dev, eps, (float*)out_dev, nullptr, 0, 0, 0, st);
+  return layernorm<bf16>(x_dev, rows, H, gamma_dev, beta_dev, eps, nullptr, (bf16*)out_dev, 0, 0, 0, st);
+}
+
+extern "C" int msq_attention(int32_t dtype, const void* qkv_dev, int64_t R, int32_t L, int32_t heads, float scale,
+                             const float* mask_add_dev, int32_t mask_len, void* ctx_dev, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == 0)
+    return attention<float>((const float*)qkv_dev, R, L, heads, 64, scale, mask_add_dev, mask_len, mask_len, (float*)ctx_dev, st);
+  return attention<bf16>((const bf16*)qkv_dev, R, L, heads, 64, scale, mask_add_dev, mask_len, mask_len, (bf16*)ctx_dev, st);
+}
+
+extern "C" int msq_f32_to_bf16(const float* src_dev, void* dst_dev, int64_t n, void* stream) {
+  if (n == 0) return MSQ_OK;
+  f32_to_bf16_kernel<<<(int)min((int64_t)148 * 8, (n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src_dev, (bf16*)dst_dev, n);
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}

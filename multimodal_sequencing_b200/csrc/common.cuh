@@ -1,0 +1,90 @@
+// Shared device/host helpers for the sm_100a kernels of the step-ordering path.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define MSQ_OK 0
+#define MSQ_ERR_ARG 1
+#define MSQ_ERR_CUDA 2
+#define MSQ_ERR_WEIGHT 3
+#define MSQ_ERR_STATE 4
+
+namespace msq {
+
+typedef __nv_bfloat16 bf16;
+
+void set_error(const char* fmt, ...);
+
+#define MSQ_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      msq::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return MSQ_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define MSQ_LAUNCH_CHECK()                                                                       \
+  do {                                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                                        \
+    if (e__ != cudaSuccess) {                                                                    \
+      msq::set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return MSQ_ERR_CUDA;                                                                       \
+    }                                                                                            \
+    msq::count_launch();                                                                         \
+  } while (0)
+
+#define MSQ_REQUIRE(cond, ...)       \
+  do {                               \
+    if (!(cond)) {                   \
+      msq::set_error(__VA_ARGS__);   \
+      return MSQ_ERR_ARG;            \
+    }                                \
+  } while (0)
+
+#define MSQ_TRY(expr)              \
+  do {                             \
+    int rc__ = (expr);             \
+    if (rc__ != MSQ_OK) return rc__; \
+  } while (0)
+
+void count_launch();
+
+// activation selectors for GEMM epilogues
+enum Act { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_QUICK_GELU = 2, ACT_TANH = 3, ACT_GELU_TANH = 4 };
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case ACT_GELU_ERF: return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    case ACT_QUICK_GELU: return x / (1.0f + __expf(-1.702f * x));
+    case ACT_TANH: return tanhf(x);
+    case ACT_GELU_TANH: {
+      float u = 0.79788456080286535588f * (x + 0.044715f * x * x * x);
+      return 0.5f * x * (1.0f + tanhf(u));
+    }
+    default: return x;
+  }
+}
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace msq

@@ -1,0 +1,275 @@
+// Pointer-network decoder with batched beam search over step permutations — ONE persistent kernel
+// for all N-1 decode steps of a group of manuals (state stays in shared memory between steps; no host
+// sync, no per-step launches).  Each step fuses: LSTM cell -> query projection -> masked pointer
+// scoring over the remaining steps -> log-softmax -> per-manual top-k over (beam x step) -> beam
+// expansion, permutation-mask update and parent re-gather of (h, c).
+//
+// Replaces (telin0411/multimodal_sequencing):
+//   BertForOrdering.step            models/berson/modeling_bert.py:1368-1402
+//   beam_search_pointer loop body   models/berson/modeling_bert.py:1472-1552
+//   Beam.step                       models/berson/generator.py:15-38  (== models/beam.py with `//`)
+//
+// Base-tensor formulation: the reference re-materialises a per-beam
+// [W,N,N,H+2] relation tensor, zeroes it in place and re-gathers it every step.  Here the relation
+// tensor R0 of a manual is projected ONCE through the four column blocks of pw_k
+// (T4 = [A1|A2|F|G], a GEMM done before this kernel) and a step only gathers rows of T4:
+//   keys[k] = A1[last,k] + A2[last2,k] + (sum_{j in Rem, j!=k} F[k,j] + sum_{i in Rem, i!=k} G[i,k]) / N
+// Per-beam state is just (picked sequence, h, c, cost).  Likewise W_ih x_t is a row gather of
+// XG = sents W_ih^T + b_ih + b_hh.  All arithmetic is fp32 with a fixed summation order.
+// Ties in the top-k are broken by the lowest flat index beam*N+step.
+#include "kernels.cuh"
+
+namespace msq {
+
+constexpr int DC_MAXN = 16;
+constexpr int DC_THREADS = 256;
+
+template <int ROWS>
+__global__ void __launch_bounds__(DC_THREADS) beam_search_kernel(DecodeWeights w, DecodeIO io, int G) {
+  extern __shared__ __align__(16) float smf[];
+  const int H = io.H, N = io.N, W = io.W;
+  float* hs = smf;                 // [ROWS][H]  h (input of the step), later q
+  float* hn = hs + ROWS * H;       // [ROWS][H]  h'
+  float* cs = hn + ROWS * H;       // [ROWS][H]  c (updated in place)
+  __shared__ float cost[ROWS], ncost[ROWS];
+  __shared__ float e[ROWS][DC_MAXN];
+  __shared__ uint8_t seq[ROWS][DC_MAXN], nseq[ROWS][DC_MAXN];
+  __shared__ int parent[ROWS];
+  __shared__ int nlive[ROWS], nnlive[ROWS];  // per manual slot g (g < G <= ROWS)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t b0 = (int64_t)blockIdx.x * G;
+  const int Gc = (int)min((int64_t)G, io.B - b0);  // manuals handled by this CTA
+  const int H4 = 4 * H;
+
+  // ---- init: one live beam per manual with h = h0, c = 0, cost 0
+  for (int i = tid; i < ROWS * H; i += DC_THREADS) {
+    const int r = i / H, d = i % H, g = r / W;
+    hs[i] = (g < Gc && r % W == 0) ? io.h0[(b0 + g) * H + d] : 0.f;
+    cs[i] = 0.f;
+  }
+  if (tid < ROWS) { cost[tid] = 0.f; nlive[tid] = 1; }
+  __syncthreads();
+
+  for (int t = 0; t < N - 1; ++t) {
+    // ---- 1. LSTM cell for every live row: gates = XG[prev] + W_hh h ; thread owns hidden unit u
+    for (int u = tid; u < H; u += DC_THREADS) {
+      float4 acc[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        const int g = r / W, wslot = r % W;
+        if (g < Gc && wslot < nlive[g]) {
+          const int prev = t == 0 ? N : seq[r][t - 1];
+          acc[r] = *reinterpret_cast<const float4*>(io.xg + ((b0 + g) * (N + 1) + prev) * (int64_t)H4 + 4 * u);
+        } else {
+          acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      const float* wp = w.whh_t + 4 * u;
+      float4 wn[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) wn[i] = *reinterpret_cast<const float4*>(wp + (int64_t)i * H4);
+      for (int k = 0; k < H; k += 4) {
+        float4 wc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wc[i] = wn[i];
+        if (k + 4 < H) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) wn[i] = *reinterpret_cast<const float4*>(wp + (int64_t)(k + 4 + i) * H4);
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+          const float4 hv = *reinterpret_cast<const float4*>(hs + r * H + k);
+          const float hk[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[r].x = fmaf(wc[i].x, hk[i], acc[r].x);
+            acc[r].y = fmaf(wc[i].y, hk[i], acc[r].y);
+            acc[r].z = fmaf(wc[i].z, hk[i], acc[r].z);
+            acc[r].w = fmaf(wc[i].w, hk[i], acc[r].w);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        const float ig = 1.f / (1.f + expf(-acc[r].x)), fg = 1.f / (1.f + expf(-acc[r].y));
+        const float gg = tanhf(acc[r].z), og = 1.f / (1.f + expf(-acc[r].w));
+        const float c2 = fg * cs[r * H + u] + ig * gg;
+        cs[r * H + u] = c2;
+        hn[r * H + u] = og * tanhf(c2);
+      }
+    }
+    __syncthreads();
+
+    // ---- 2. q = W_q h' + b_q  (written over hs)
+    for (int j4 = tid; j4 < H / 4; j4 += DC_THREADS) {
+      float4 acc[ROWS];
+      const float4 bq = *reinterpret_cast<const float4*>(w.bq + 4 * j4);
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) acc[r] = bq;
+      const float* wp = w.wq_t + 4 * j4;
+      for (int k = 0; k < H; k += 4) {
+        float4 wc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wc[i] = *reinterpret_cast<const float4*>(wp + (int64_t)(k + i) * H);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+          const float4 hv = *reinterpret_cast<const float4*>(hn + r * H + k);
+          const float hk[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[r].x = fmaf(wc[i].x, hk[i], acc[r].x);
+            acc[r].y = fmaf(wc[i].y, hk[i], acc[r].y);
+            acc[r].z = fmaf(wc[i].z, hk[i], acc[r].z);
+            acc[r].w = fmaf(wc[i].w, hk[i], acc[r].w);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) *reinterpret_cast<float4*>(hs + r * H + 4 * j4) = acc[r];
+    }
+    __syncthreads();
+
+    // ---- 3. pointer scores e[r][k] = w_t . tanh(q + keys[k] + key0[k]) + b_t ; one warp per (row, k)
+    for (int task = warp; task < ROWS * N; task += DC_THREADS / 32) {
+      const int r = task / N, k = task % N, g = r / W, wslot = r % W;
+      if (g >= Gc || wslot >= nlive[g]) continue;
+      uint32_t picked = 0;
+      for (int i = 0; i < t; ++i) picked |= 1u << seq[r][i];
+      if (picked >> k & 1u) {
+        if (lane == 0) e[r][k] = -1e9f;
+        continue;
+      }
+      const float* t4 = io.t4 + (b0 + g) * (int64_t)N * N * H4;
+      const float* k0 = io.key0 + ((b0 + g) * N + k) * (int64_t)H;
+      const float* a1 = t >= 1 ? t4 + ((int64_t)seq[r][t - 1] * N + k) * H4 : nullptr;
+      const float* a2 = t >= 2 ? t4 + ((int64_t)seq[r][t - 2] * N + k) * H4 + H : nullptr;
+      float part = 0.f;
+      for (int d = lane; d < H; d += 32) {
+        float fs = 0.f, gs = 0.f;
+        for (int j = 0; j < N; ++j)
+          if (j != k && !(picked >> j & 1u)) {
+            fs += t4[((int64_t)k * N + j) * H4 + 2 * H + d];
+            gs += t4[((int64_t)j * N + k) * H4 + 3 * H + d];
+          }
+        float key = fs / (float)N + gs / (float)N;
+        if (a1) key += a1[d];
+        if (a2) key += a2[d];
+        part = fmaf(w.wt[d], tanhf(hs[r * H + d] + key + k0[d]), part);
+      }
+      part = warp_sum(part);
+      if (lane == 0) e[r][k] = part + w.bt;
+    }
+    __syncthreads();
+
+    // ---- 4. log-softmax per live row; e <- candidate cost J - logp
+    if (tid < ROWS) {
+      const int r = tid, g = r / W, wslot = r % W;
+      if (g < Gc && wslot < nlive[g]) {
+        float mx = -INFINITY, s = 0.f;
+        for (int k = 0; k < N; ++k) mx = fmaxf(mx, e[r][k]);
+        for (int k = 0; k < N; ++k) s += expf(e[r][k] - mx);
+        const float lse = logf(s);
+        for (int k = 0; k < N; ++k) {
+          const float logp = (e[r][k] - mx) - lse;
+          if (io.trace_logp) io.trace_logp[(((b0 + g) * (N - 1) + t) * W + wslot) * N + k] = logp;
+          e[r][k] = -logp + cost[r];
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- 5. per-manual top-k (ascending cost, ties -> lowest flat index) by rank counting
+    for (int c = tid; c < Gc * W * N; c += DC_THREADS) {
+      const int g = c / (W * N), flat = c % (W * N), wslot = flat / N, k = flat % N;
+      const int live = nlive[g];
+      if (wslot >= live) continue;
+      const int numel = live * N, kk = min(W, numel);
+      const float mine = e[g * W + wslot][k];
+      int rank = 0;
+      for (int o = 0; o < numel; ++o) {
+        const float v = e[g * W + o / N][o % N];
+        rank += (v < mine) || (v == mine && o < flat);
+      }
+      if (rank < kk) {
+        const int nr = g * W + rank;
+        parent[nr] = g * W + wslot;
+        ncost[nr] = mine;
+        for (int i = 0; i < t; ++i) nseq[nr][i] = seq[g * W + wslot][i];
+        nseq[nr][t] = (uint8_t)k;
+        if (io.trace_ix) io.trace_ix[((b0 + g) * (N - 1) + t) * W + rank] = flat;
+        if (io.trace_cost) io.trace_cost[((b0 + g) * (N - 1) + t) * W + rank] = mine;
+      }
+      if (flat == 0) nnlive[g] = kk;
+    }
+    __syncthreads();
+
+    // ---- 6. expand: re-gather (h', c) by parent; each thread owns whole columns -> no hazard
+    for (int d = tid; d < H; d += DC_THREADS) {
+      float hv[ROWS], cv[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        const int g = r / W;
+        const bool on = g < Gc && (r % W) < nnlive[g];
+        hv[r] = on ? hn[parent[r] * H + d] : 0.f;
+        cv[r] = on ? cs[parent[r] * H + d] : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) { hs[r * H + d] = hv[r]; cs[r * H + d] = cv[r]; }
+    }
+    if (tid < ROWS) {
+      const int g = tid / W;
+      if (g < Gc && (tid % W) < nnlive[g]) {
+        cost[tid] = ncost[tid];
+        for (int i = 0; i <= t; ++i) seq[tid][i] = nseq[tid][i];
+      }
+    }
+    __syncthreads();
+    if (tid < ROWS) nlive[tid] = nnlive[tid];
+    __syncthreads();
+  }
+
+  // ---- best hypothesis = slot 0 (lowest cost); the one unused index goes last (modeling_bert.py:1549-1550)
+  if (tid < Gc) {
+    const int r = tid * W;
+    uint32_t picked = 0;
+    for (int i = 0; i < N - 1; ++i) {
+      io.perm[(b0 + tid) * N + i] = seq[r][i];
+      picked |= 1u << seq[r][i];
+    }
+    int last = 0;
+    while (last < N - 1 && (picked >> last & 1u)) ++last;
+    io.perm[(b0 + tid) * N + N - 1] = last;
+  }
+}
+
+template <int ROWS>
+static int launch_beam(const DecodeWeights& w, const DecodeIO& io, int G, cudaStream_t st) {
+  const size_t smem = (size_t)3 * ROWS * io.H * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    MSQ_CUDA(cudaFuncSetAttribute(beam_search_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  beam_search_kernel<ROWS><<<ceil_div(io.B, G), DC_THREADS, smem, st>>>(w, io, G);
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+
+int beam_search(const DecodeWeights& w, const DecodeIO& io, cudaStream_t st) {
+  MSQ_REQUIRE(io.N >= 2 && io.N <= DC_MAXN, "beam_search: N=%d out of range [2,%d]", io.N, DC_MAXN);
+  MSQ_REQUIRE(io.W >= 1 && io.W <= 16, "beam_search: beam width %d out of range [1,16]", io.W);
+  MSQ_REQUIRE(io.H % 4 == 0 && io.H <= 1024, "beam_search: H=%d unsupported", io.H);
+  if (io.B == 0) return MSQ_OK;
+  // rows per CTA: enough manuals to reuse each weight row across ~16 beams, but never fewer CTAs than
+  // needed to give every SM work when B is large.
+  int G = 16 / io.W;
+  if (G < 1) G = 1;
+  while (G > 1 && ceil_div(io.B, G) < 148) G /= 2;
+  const int rows = G * io.W;
+  if (rows <= 4) return launch_beam<4>(w, io, G, st);
+  if (rows <= 8) return launch_beam<8>(w, io, G, st);
+  return launch_beam<16>(w, io, G, st);
+}
+
+}  // namespace msq

@@ -1,0 +1,338 @@
+// bf16 tensor-core GEMM for sm_100a: C = act(A W^T + bias) + resid with fp32 accumulation in TMEM.
+//
+//   * operands A [M,K] and W [N,K] (both K-major bf16) are streamed global -> shared by TMA
+//     (cp.async.bulk.tensor, 128B swizzle) through a 4-stage mbarrier ring;
+//   * one elected thread issues tcgen05.mma (cta_group::1, 128 x 256 x 16 per instruction) reading
+//     the swizzled tiles through shared-memory matrix descriptors, accumulating into TMEM;
+//   * the 512 TMEM columns hold TWO 128x256 fp32 accumulators so the epilogue of tile i overlaps the
+//     MMAs of tile i+1; 8 epilogue warps read TMEM with tcgen05.ld, apply bias / activation /
+//     residual in registers and store bf16 or fp32 rows;
+//   * persistent: one CTA per SM walks tiles m-fastest so CTAs running together share the weight tile
+//     in L2.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc/dealloc), 2..9 = epilogue.
+//
+// Replaces the cuBLAS calls behind every nn.Linear of the encoders: CLIP ViT blocks
+// (models/CLIP/clip/model.py:204-226, conv1 263), joint BERT layers
+// (models/CLIP/src/lxrt/modeling.py:373-507), visn_fc (585-602) and HierarchicalAttention.sentence_tran
+// (models/berson/modeling_bert.py:697).
+#include <cuda.h>
+
+#include "kernels.cuh"
+
+namespace msq {
+
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2, TC_B_BYTES = TC_BN * TC_BK * 2, TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_EPI_WARPS = 8, TC_THREADS = (2 + TC_EPI_WARPS) * 32;
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t TC_SPIN_LIMIT = 1u << 26;
+
+struct TcEpi {
+  const float* bias;
+  const float* resid;
+  void* C;
+  int64_t M;
+  int N, ldc, ldr, act;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > TC_SPIN_LIMIT) {  // a lost arrival would otherwise hang the GPU: fail loudly instead
+      printf("gemm_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <typename TO> __device__ __forceinline__ void epi_store8(TO* p, const float* v);
+template <> __device__ __forceinline__ void epi_store8<float>(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void epi_store8<bf16>(bf16* p, const float* v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, TcEpi ep, int num_m,
+               int num_n, int num_k) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES;
+  // barrier layout (8 B each): full[4] | empty[4] | tmem_full[2] | tmem_empty[2] | tmem base slot
+  const uint32_t full0 = bars, empty0 = bars + 8 * TC_STAGES, tfull0 = bars + 16 * TC_STAGES, tempty0 = tfull0 + 16;
+  const uint32_t tslot = tempty0 + 16;
+  uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tslot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + TC_STAGES * TC_STAGE_BYTES + 16 * TC_STAGES + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = num_m * num_n;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, TC_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tslot_gen;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t sa = base + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+          mbar_expect_tx(full0 + 8 * stage, TC_STAGE_BYTES);
+          tma_load_2d(sa, &tma_a, kb * TC_BK, m_blk * TC_BM, full0 + 8 * stage);
+          tma_load_2d(sb, &tma_b, kb * TC_BK, n_blk * TC_BN, full0 + 8 * stage);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=F32 [4,6), A=BF16 [7,10), B=BF16 [10,13), K-major A/B, N>>3 [17,23), M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * TC_BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t da = umma_desc_sw128(sa + k * 32), db = umma_desc_sw128(sb + k * 32);
+            umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty0 + 8 * stage);  // frees the smem slot when these MMAs have read it
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull0 + 8 * acc);  // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (8 warps) =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may touch
+    const int half = (warp - 2) >> 2;       // column half: 0 -> [0,128), 1 -> [128,256)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    TO* C = reinterpret_cast<TO*>(ep.C);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      mbar_wait(tfull0 + 8 * acc, acc_phase);
+      tc_fence_after();
+      const int64_t row = (int64_t)m_blk * TC_BM + q * 32 + lane;
+      const bool row_ok = row < ep.M;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        const int col0 = n_blk * TC_BN + half * 128 + ch * 32;
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_BN + half * 128 + ch * 32, raw);
+        if (row_ok && col0 < ep.N) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = col0 + j * 8;
+            if (col < ep.N) {  // N % 8 == 0
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[j * 8 + i]);
+              if (ep.bias) {
+                const float4 b0 = *reinterpret_cast<const float4*>(ep.bias + col), b1 = *reinterpret_cast<const float4*>(ep.bias + col + 4);
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              if (ep.act != ACT_NONE) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], ep.act);
+              }
+              if (ep.resid) {
+                const float* rp = ep.resid + row * ep.ldr + col;
+                const float4 r0 = *reinterpret_cast<const float4*>(rp), r1 = *reinterpret_cast<const float4*>(rp + 4);
+                v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+              }
+              epi_store8<TO>(C + row * ep.ldc + col, v);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int gemm_tc_selftest_supported() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return cached = 0;
+  cached = (prop.major == 10 && get_encode_fn() != nullptr) ? 1 : 0;
+  return cached;
+}
+
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int K, int ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld K=%d ld=%d", (int)r, (long long)rows, K, ld);
+    return MSQ_ERR_CUDA;
+  }
+  return MSQ_OK;
+}
+
+template <typename TO>
+int gemm_tc(const GemmArgs& g, cudaStream_t st) {
+  MSQ_REQUIRE(gemm_tc_selftest_supported(), "gemm_tc: tcgen05 path needs an sm_100 device and cuTensorMapEncodeTiled");
+  MSQ_REQUIRE(g.K % TC_BK == 0 && g.N % 8 == 0 && g.lda % 8 == 0 && g.ldw % 8 == 0 && g.ldc % 8 == 0,
+              "gemm_tc: K=%d N=%d lda=%d ldw=%d ldc=%d not supported", g.K, g.N, g.lda, g.ldw, g.ldc);
+  MSQ_REQUIRE(((uintptr_t)g.A & 15) == 0 && ((uintptr_t)g.W & 15) == 0 && ((uintptr_t)g.C & 15) == 0, "gemm_tc: unaligned pointer");
+  MSQ_REQUIRE(g.C2 == nullptr, "gemm_tc: second output unsupported");
+  if (g.M == 0) return MSQ_OK;
+  CUtensorMap ma, mb;
+  MSQ_TRY(make_map(&ma, g.A, g.M, g.K, g.lda, TC_BM));
+  MSQ_TRY(make_map(&mb, g.W, g.N, g.K, g.ldw, TC_BN));
+  static int sms = 0;
+  static bool configured[2] = {false, false};
+  if (!sms) {
+    int dev = 0;
+    MSQ_CUDA(cudaGetDevice(&dev));
+    MSQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int which = sizeof(TO) == 4 ? 0 : 1;
+  if (!configured[which]) {
+    MSQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    configured[which] = true;
+  }
+  TcEpi ep;
+  ep.bias = g.bias; ep.resid = g.resid; ep.C = g.C; ep.M = g.M; ep.N = g.N; ep.ldc = g.ldc; ep.ldr = g.ldr; ep.act = g.act;
+  const int num_m = ceil_div(g.M, TC_BM), num_n = ceil_div(g.N, TC_BN), num_k = g.K / TC_BK;
+  const int64_t tiles = (int64_t)num_m * num_n;
+  const int grid = (int)min((int64_t)sms, tiles);
+  gemm_tc_kernel<TO><<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, ep, num_m, num_n, num_k);
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+template int gemm_tc<float>(const GemmArgs&, cudaStream_t);
+template int gemm_tc<bf16>(const GemmArgs&, cudaStream_t);
+
+}  // namespace msq

@@ -1,0 +1,77 @@
+// Internal launcher prototypes (host side).  Every launcher returns an MSQ_* status and enqueues on
+// the given stream; nothing synchronises.
+#pragma once
+#include "common.cuh"
+
+namespace msq {
+
+// ---- elementwise.cu
+template <typename T>
+int layernorm(const float* x, int64_t rows, int H, const float* gamma, const float* beta, float eps, float* out_f,
+              T* out_t, int in_group, int out_group, int out_off, cudaStream_t st);
+template <typename T>
+int embed_ln(const int64_t* ids, const int64_t* tts, int64_t R, int Lt, int Lj, int H, const float* word, const float* pos,
+             const float* type, const float* gamma, const float* beta, float eps, float* out_f, T* out_t, cudaStream_t st);
+int vit_assemble(const float* patch, const int32_t* img_index, int64_t R, int il, int g2, int W, const float* cls,
+                 const float* pos, const float* gamma, const float* beta, float eps, float* out, cudaStream_t st);
+template <typename T> int im2col(const float* img, int64_t n, int S, int P, T* out, cudaStream_t st);
+template <typename TI, typename TO>
+int gather_rows(const TI* src, int64_t rows, int H, int group, int src_group, int off, TO* dst, cudaStream_t st);
+template <typename TO> int pack_pad(const float* src, int64_t rows, int K, int Kp, TO* dst, cudaStream_t st);
+
+// ---- gemm_simt.cu : C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual), fp32 FFMA accumulate
+struct GemmArgs {
+  const void* A;       // [M, lda]  (TA)
+  const void* W;       // [N, ldw]  (TA)
+  const float* bias;   // [N] or null
+  const float* resid;  // [M, ldr] fp32 or null (added after act)
+  void* C;             // [M, ldc]  (TO)
+  float* C2;           // optional second fp32 output (same ldc) or null
+  int64_t M;
+  int N, K, lda, ldw, ldc, ldr;
+  int act;
+};
+template <typename TA, typename TO> int gemm_simt(const GemmArgs& g, cudaStream_t st);
+
+// ---- gemm_tc.cu : same contract, bf16 operands on tcgen05 tensor cores (TMA-fed, TMEM accumulators)
+template <typename TO> int gemm_tc(const GemmArgs& g, cudaStream_t st);
+int gemm_tc_selftest_supported();
+
+// ---- attention.cu : ctx[r, t, h*64 + d] = softmax(q k^T / sqrt(d) + mask) v over the L tokens of row-group r
+template <typename T>
+int attention(const T* qkv, int64_t R, int L, int heads, int dhead, float scale, const float* key_mask_add, int mask_ld,
+              int mask_len, T* ctx, cudaStream_t st);
+
+// ---- pooling.cu
+template <typename T>
+int token_pool(const T* tt, const float* x, int64_t R, int Lt, int Lj, int H, const float* w2, const float* b2,
+               const int64_t* sep, const float* w_rel, const float* b_rel, float* mix, float* rel6, cudaStream_t st);
+int edge_pool(const float* mix, const float* x, const float* rel6, int64_t B, int N, int Lj, int H, const float* w_in2,
+              float* sents, float* r0, int r0_ld, float* cls_mat, float* score_mat, float* his1, float* his2, float* cls_out,
+              cudaStream_t st);
+int para_attention(const float* qkv, int64_t B, int N, int heads, int H, float* ctx, cudaStream_t st);
+int para_finish(const float* sents, const float* para, int64_t B, int N, int H, float* h0, float* keyin, cudaStream_t st);
+
+// ---- decode.cu
+struct DecodeWeights {
+  const float* whh_t;   // [H][4H] gate-interleaved: col 4*u+g
+  const float* wq_t;    // [H][H]
+  const float* bq;      // [H]
+  const float* wt;      // [H] tanh_linear.weight
+  float bt;             // tanh_linear.bias
+};
+struct DecodeIO {
+  const float* xg;     // [B, N+1, 4H] gate-interleaved input projections; row N = bias only (t = 0)
+  const float* t4;     // [B, N*N, 4H] = (A1|A2|F|G) blocks of H
+  const float* key0;   // [B, N, H]
+  const float* h0;     // [B, H]
+  int64_t B;
+  int N, W, H;
+  int32_t* perm;       // [B, N] out
+  int32_t* trace_ix;   // optional [B, N-1, W] flat index beam*N+tok per step (or -1)
+  float* trace_cost;   // optional [B, N-1, W]
+  float* trace_logp;   // optional [B, N-1, W, N]
+};
+int beam_search(const DecodeWeights& w, const DecodeIO& io, cudaStream_t st);
+
+}  // namespace msq

@@ -1,0 +1,276 @@
+"""Host side of the B200 step-ordering path: weight hand-over, pair expansion, and thin wrappers over
+the C ABI (include/msq_b200.h).  PyTorch is used for device memory and streams only.
+
+Reference call sites mirrored here (telin0411/multimodal_sequencing):
+  prepare_berson_inputs      models/berson/process_inputs_for_berson.py:13-79  -> OrderingEngine.prepare
+  BertForOrdering.encode     models/berson/modeling_bert.py:1239-1366         -> OrderingEngine.encode
+  beam_search_pointer        models/berson/modeling_bert.py:1411-1552         -> OrderingEngine.beam_search
+  berson_pointer_network     models/berson/modeling_bert.py:1405-1408         -> OrderingEngine.order / order_host
+"""
+import ctypes as C
+import itertools
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+_DEAD = ("visual_model.transformer.", "visual_model.token_embedding", "visual_model.positional_embedding",
+         "visual_model.ln_final", "visual_model.text_projection", "visual_model.logit_scale")
+
+
+def pairs_generator(n):
+    """All (i<j) pairs in lexicographic order, then the mirrored list
+    (models/berson/process_inputs_for_berson.py:246-261)."""
+    one = [[a, b] for a, b in itertools.combinations(range(n), 2)]
+    return one + [[b, a] for a, b in one], 2 * len(one)
+
+
+@dataclass
+class PairBatch:
+    """One batch of manuals expanded to ordered pairs.  Images stay UNIQUE ([B*N,3,S,S]); the pair ->
+    image relation is the int32 table `img_index` (the reference materialises [B,P,2,3,S,S] instead,
+    process_inputs_for_berson.py:82-97)."""
+    input_ids: torch.Tensor        # [B,P,Lt] int64
+    attention_mask: torch.Tensor   # [B,P,Lt] int64
+    token_type_ids: torch.Tensor   # [B,P,Lt] int64
+    sep_positions: torch.Tensor    # [B,P,2]  int64
+    pairs_list: torch.Tensor       # [B,P,2]  int64
+    pairwise_labels: torch.Tensor  # [B,P]    int64
+    ground_truth: torch.Tensor     # [B,N]    int64
+    n_steps: int
+    images: Optional[torch.Tensor] = None     # [B*N,3,S,S] fp32
+    img_index: Optional[torch.Tensor] = None  # [B,P,2] int32
+
+    @property
+    def B(self):
+        return self.input_ids.shape[0]
+
+    @property
+    def Lt(self):
+        return self.input_ids.shape[2]
+
+    def to(self, device, non_blocking=False):
+        kw = {}
+        for k, v in self.__dict__.items():
+            kw[k] = v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v
+        return PairBatch(**kw)
+
+    def reference_dict(self, materialize_images=True):
+        """The dict prepare_berson_inputs returns (process_inputs_for_berson.py:46-79)."""
+        B, P = self.input_ids.shape[:2]
+        d = {
+            "input_ids": self.input_ids, "attention_mask": self.attention_mask, "token_type_ids": self.token_type_ids,
+            "pairs_list": self.pairs_list,
+            "passage_length": torch.full((B,), self.n_steps, dtype=torch.long, device=self.input_ids.device),
+            "pairs_num": torch.full((B,), P, dtype=torch.long, device=self.input_ids.device),
+            "sep_positions": self.sep_positions, "ground_truth": self.ground_truth,
+            "mask_cls": torch.ones((B, self.n_steps), dtype=torch.long, device=self.input_ids.device),
+            "pairwise_labels": self.pairwise_labels, "cuda": "cuda:0",
+        }
+        if self.images is not None and materialize_images:
+            d["images"] = self.images[self.img_index.long()]  # [B,P,2,3,S,S]
+        return d
+
+
+def prepare_pairs(input_ids, labels, n_steps, images=None, cls_id=101, sep_id=102, pad_id=0):
+    """Manual -> P = N(N-1) ordered pairs (host logic of process_inputs_for_berson.py:113-243,264-368).
+
+    input_ids [B,L] int64 rows of concatenated `[CLS] ... [SEP]` steps; labels [B,N]; images [B,N,3,S,S]."""
+    input_ids = torch.as_tensor(input_ids).cpu()
+    labels = torch.as_tensor(labels).cpu()
+    B = input_ids.shape[0]
+    N = n_steps
+    pairs, P = pairs_generator(N)
+    pi = torch.tensor(pairs)  # [P,2]
+    is_cls, is_sep = input_ids == cls_id, input_ids == sep_id
+    if not (is_cls.sum(1) == N).all() or not (is_sep.sum(1) == N).all():
+        raise AssertionError("every manual must hold exactly max_story_length [CLS]..[SEP] steps")
+    starts = is_cls.nonzero()[:, 1].view(B, N)
+    ends = is_sep.nonzero()[:, 1].view(B, N)
+    lens = ends - starts + 1                               # [B,N]
+    l1, l2 = lens[:, pi[:, 0]], lens[:, pi[:, 1]]          # [B,P]
+    Lt = int((l1 + l2).max())
+    pos = torch.arange(Lt)[None, None, :]
+    in1 = pos < l1[..., None]
+    in2 = (pos >= l1[..., None]) & (pos < (l1 + l2)[..., None])
+    src = torch.where(in1, starts[:, pi[:, 0]][..., None] + pos,
+                      starts[:, pi[:, 1]][..., None] + pos - l1[..., None]).clamp_(0, input_ids.shape[1] - 1)
+    ids = torch.gather(input_ids[:, None, :].expand(B, P, -1), 2, src)
+    valid = in1 | in2
+    ids = torch.where(valid, ids, torch.full_like(ids, pad_id))
+    am = torch.where(valid, torch.ones_like(ids), torch.full_like(ids, pad_id))
+    tt = (in2 & (cls_id != 0)).long()
+    sep = torch.stack([l1 - 1, l1 + l2 - 1], -1)
+    # pairwise label = 1 iff the ground-truth position of i precedes that of j (162-172)
+    posn = torch.argsort(labels, dim=1)  # posn[b, step] = index of `step` inside labels[b]
+    plab = (posn[:, pi[:, 0]] < posn[:, pi[:, 1]]).long()
+    img = idx = None
+    if images is not None:
+        images = torch.as_tensor(images)
+        img = images.reshape(B * N, *images.shape[2:]).float().contiguous()
+        idx = (torch.arange(B)[:, None, None] * N + pi[None]).int().contiguous()
+    return PairBatch(ids.contiguous(), am.contiguous(), tt.contiguous(), sep.contiguous(),
+                     pi[None].expand(B, P, 2).contiguous(), plab, labels.clone(), N, img, idx)
+
+
+class OrderingEngine:
+    """Owns one packed device model (msq_model) and runs the path through the C ABI."""
+
+    def __init__(self, state_dict, config, precise=False, device="cuda:0", inner_prefix="bert."):
+        if not torch.cuda.is_available():
+            raise RuntimeError("multimodal_sequencing_b200 needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        vit = config.get("vit")
+        self.cfg = dict(config)
+        self.H = config["hidden_size"]
+        c = _lib.MsqConfig(
+            hidden=config["hidden_size"], layers=config["num_hidden_layers"], heads=config["num_attention_heads"],
+            inter=config["intermediate_size"], vocab=config["vocab_size"], max_pos=config["max_position_embeddings"],
+            type_vocab=config.get("type_vocab_size", 2), vit_width=vit["vision_width"] if vit else 0,
+            vit_layers=vit["vision_layers"] if vit else 0, vit_patch=vit["vision_patch_size"] if vit else 0,
+            vit_res=vit["image_resolution"] if vit else 0, para_heads=config.get("para_heads", 8),
+            para_ff=config.get("para_ff", 3072), para_layers=config.get("para_layers", 2), precise=int(bool(precise)),
+            reserved=0)
+        self.multimodal = bool(vit)
+        self.vit = vit
+        self.precise = bool(precise)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.msq_model_create(C.byref(c), C.byref(self._h)))
+            st = self._stream()
+            for k, v in state_dict.items():
+                if not torch.is_tensor(v) or not v.is_floating_point() or any(d in k for d in _DEAD):
+                    continue
+                if inner_prefix != "bert." and k.startswith(inner_prefix):
+                    k = "bert." + k[len(inner_prefix):]
+                t = v.detach().to(self.device, torch.float32).contiguous()
+                _lib.check(self.lib.msq_model_set_weight(self._h, k.encode(), t.data_ptr(), t.numel(), st))
+            torch.cuda.synchronize(self.device)
+            _lib.check(self.lib.msq_model_pack(self._h, st))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                self.lib.msq_model_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
+
+    def launch_count(self):
+        return int(self.lib.msq_launch_count())
+
+    prepare = staticmethod(prepare_pairs)
+
+    # ------------------------------------------------------------------------------------------
+    def vit_forward(self, images, img_index, R):
+        """CLIP VisualTransformer pair tower (models/CLIP/clip/model.py:262-305, skip_last_layer=True)."""
+        g = self.vit["image_resolution"] // self.vit["vision_patch_size"]
+        out = torch.empty(R, 1 + 2 * g * g, self.vit["vision_width"], device=self.device)
+        images = images.to(self.device, torch.float32).contiguous()
+        img_index = img_index.to(self.device, torch.int32).contiguous()
+        _lib.check(self.lib.msq_vit_forward(self._h, self._p(images), images.shape[0], self._p(img_index), R,
+                                            self._p(out), self._stream()))
+        return out
+
+    def inner_forward(self, ids, tt, mask, images=None, img_index=None, want_pooled=False):
+        """LXRTModel.forward / BertModel.forward on R pair rows -> (lang, visn|None, pooled|None)."""
+        ids = ids.to(self.device, torch.long).contiguous()
+        tt = tt.to(self.device, torch.long).contiguous()
+        mask = mask.to(self.device, torch.long).contiguous()
+        R, Lt = ids.shape
+        lang = torch.empty(R, Lt, self.H, device=self.device)
+        visn = pooled = None
+        n_img = 0
+        if self.multimodal and images is not None:
+            images = images.to(self.device, torch.float32).contiguous()
+            img_index = img_index.to(self.device, torch.int32).contiguous()
+            g = self.vit["image_resolution"] // self.vit["vision_patch_size"]
+            visn = torch.empty(R, 1 + 2 * g * g, self.H, device=self.device)
+            n_img = images.shape[0]
+        if want_pooled:
+            pooled = torch.empty(R, self.H, device=self.device)
+        _lib.check(self.lib.msq_inner_forward(self._h, self._p(ids), self._p(tt), self._p(mask), R, Lt,
+                                              self._p(images if visn is not None else None), n_img,
+                                              self._p(img_index if visn is not None else None), self._p(lang),
+                                              self._p(visn), self._p(pooled), self._stream()))
+        return lang, visn, pooled
+
+    def encode(self, batch: PairBatch, want_top_vec=False):
+        """BertForOrdering.encode -> dict with the reference's 10-tuple tensors (fp32, on device)."""
+        b = batch.to(self.device)
+        B, P, Lt = b.input_ids.shape
+        N, H, dev = b.n_steps, self.H, self.device
+        o = dict(sents=torch.empty(B, N, H, device=dev), para=torch.empty(B, N, H, device=dev),
+                 h0=torch.empty(B, H, device=dev), key=torch.empty(B, N, H, device=dev),
+                 cls=torch.empty(B * P, H, device=dev), cls_mat=torch.empty(B, N, N, H, device=dev),
+                 cls_score=torch.empty(B * P, 2, device=dev), score_mat=torch.empty(B, N, N, 2, device=dev),
+                 his1=torch.empty(B, N, N, 2, device=dev), his2=torch.empty(B, N, N, 2, device=dev))
+        if want_top_vec:
+            o["top_vec"] = torch.empty(B * P, Lt, H, device=dev)
+        eo = _lib.MsqEncodeOut(**{k: (o[k].data_ptr() if k in o else None) for k, _ in _lib.MsqEncodeOut._fields_})
+        n_img = 0 if b.images is None else b.images.shape[0]
+        _lib.check(self.lib.msq_encode(self._h, self._p(b.input_ids), self._p(b.token_type_ids),
+                                       self._p(b.attention_mask), self._p(b.sep_positions), B, N, Lt,
+                                       self._p(b.images), n_img, self._p(b.img_index), C.byref(eo), self._stream()))
+        o["c0"] = torch.zeros_like(o["h0"])
+        return o
+
+    def beam_search(self, enc, n_steps, beam, trace=False):
+        """beam_search_pointer for B manuals at once.  Returns perm [B,N] int32 (+ trace dict)."""
+        f = lambda t: t.to(self.device, torch.float32).contiguous()
+        sents, key, h0 = f(enc["sents"]), f(enc["key"]), f(enc["h0"]).reshape(-1, self.H)
+        cls_mat, score_mat = f(enc["cls_mat"]), f(enc["score_mat"])
+        B, N = sents.shape[0], n_steps
+        perm = torch.empty(B, N, dtype=torch.int32, device=self.device)
+        tr = None
+        if trace:
+            tr = dict(ix=torch.empty(B, N - 1, beam, dtype=torch.int32, device=self.device),
+                      cost=torch.zeros(B, N - 1, beam, device=self.device),
+                      logp=torch.zeros(B, N - 1, beam, N, device=self.device))
+        _lib.check(self.lib.msq_beam_search(self._h, self._p(sents), self._p(key), self._p(h0), self._p(cls_mat),
+                                            self._p(score_mat), B, N, beam, self._p(perm),
+                                            self._p(tr["ix"] if tr else None), self._p(tr["cost"] if tr else None),
+                                            self._p(tr["logp"] if tr else None), self._stream()))
+        return (perm, tr) if trace else perm
+
+    def order_device(self, batch: PairBatch, beam):
+        """encode + beam search on device-resident inputs; returns perm [B,N] int32 (device, async)."""
+        b = batch
+        B, P, Lt = b.input_ids.shape
+        perm = torch.empty(B, b.n_steps, dtype=torch.int32, device=self.device)
+        n_img = 0 if b.images is None else b.images.shape[0]
+        _lib.check(self.lib.msq_order_manuals_dev(self._h, self._p(b.input_ids), self._p(b.token_type_ids),
+                                                  self._p(b.attention_mask), self._p(b.sep_positions), B, b.n_steps, Lt,
+                                                  self._p(b.images), n_img, self._p(b.img_index), beam, self._p(perm),
+                                                  self._stream()))
+        return perm
+
+    def order_host(self, batch: PairBatch, beam, perm_out=None):
+        """Whole path from HOST (ideally pinned) buffers, H2D and D2H included; synchronous."""
+        b = batch
+        B, P, Lt = b.input_ids.shape
+        if perm_out is None:
+            perm_out = torch.empty(B, b.n_steps, dtype=torch.int32).pin_memory()
+        n_img = 0 if b.images is None else b.images.shape[0]
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.msq_order_manuals_host(self._h, self._p(b.input_ids), self._p(b.token_type_ids),
+                                                       self._p(b.attention_mask), self._p(b.sep_positions), B, b.n_steps,
+                                                       Lt, self._p(b.images), n_img, self._p(b.img_index), beam,
+                                                       self._p(perm_out), self._stream()))
+        return perm_out
+
+    def order(self, input_ids, labels, n_steps, beam, images=None, cls_id=101, sep_id=102, pad_id=0):
+        """berson_pointer_network for a batch of manuals: list of permutations (python ints)."""
+        batch = prepare_pairs(input_ids, labels, n_steps, images, cls_id, sep_id, pad_id).to(self.device)
+        return self.order_device(batch, beam).cpu().tolist()

@@ -1,0 +1,314 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything goes through the C ABI
+(libmsq_b200.so via ctypes); the oracle (oracle/berson_oracle.py, CPU) is only the checker.
+
+Tolerances (north_star): fp32 ("precise") path within 1e-5 relative of the reference quantities,
+bf16 tensor-core path reported against a looser, documented bound (bf16 unit round-off is 3.9e-3, so
+1e-3 element-wise is not attainable by any bf16-operand GEMM);
+integer / index work (permutations, beam indices, pair tables) bit-exact."""
+import math
+import os
+
+import pytest
+import torch
+
+from oracle import berson_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+REL_FP32 = 1e-5     # fp32 path: max |a-b| <= REL_FP32 * max(1, max|b|) (x4 head-room for summation order at depth)
+ENC = ["sents", "para", "h0", "key", "cls", "cls_mat", "cls_score", "score_mat", "his1", "his2"]
+
+
+def _engine(sd, cfg, precise):
+    from multimodal_sequencing_b200 import OrderingEngine
+    return OrderingEngine(sd, cfg, precise=precise)
+
+
+def _cfg_from_golden(g):
+    c = g["cfg"]
+    return dict(hidden_size=c["hidden_size"], num_hidden_layers=c["num_hidden_layers"],
+                num_attention_heads=c["num_attention_heads"], intermediate_size=c["intermediate_size"],
+                vocab_size=c["vocab_size_or_config_json_file"], max_position_embeddings=c["max_position_embeddings"],
+                vit=g.get("vit"), para_ff=g["ff_size"])
+
+
+def _close(a, b, rel, what=""):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    err = (a - b).abs().max().item()
+    bound = rel * max(1.0, b.abs().max().item())
+    assert err <= bound, "%s: max err %.3e > %.3e" % (what, err, bound)
+    return err
+
+
+def _check_trace(tr, b, steps, W, N):
+    """bit-exact beam indices against the reference's per-step (beam_ix, tok_ix)."""
+    for t, s in enumerate(steps):
+        k = s["beam_ix"].numel()
+        flat = (s["beam_ix"] * N + s["tok_ix"]).int()
+        got = tr["ix"][b, t, :k].cpu()
+        assert torch.equal(got, flat), "step %d beam indices differ: %s vs %s" % (t, got.tolist(), flat.tolist())
+        assert (tr["ix"][b, t, k:] == -1).all()
+        _close(tr["cost"][b, t, :k], s["score"], 4 * REL_FP32, "beam cost")
+        w = s["logp"].shape[0]
+        got_lp, ref_lp = tr["logp"][b, t, :w].cpu(), s["logp"]
+        live = ref_lp > -1e8                       # already-picked steps carry -1e9 on both sides
+        assert (got_lp[~live] < -1e8).all()
+        _close(got_lp[live], ref_lp[live], 4 * REL_FP32, "log-prob")
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel-level
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("M,N,K,act", [(300, 768, 768, 0), (129, 2304, 768, 1), (1000, 768, 3072, 2), (64, 128, 784, 3),
+                                       (5, 3072, 768, 4)])
+def test_gemm_fp32_ffma(M, N, K, act):
+    import ctypes as C
+    from multimodal_sequencing_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + N)
+    A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05
+    bias, resid = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    ref = A.double() @ W.double().t() + bias.double()
+    ref = {0: lambda x: x, 1: O.gelu_erf, 2: O.quick_gelu, 3: torch.tanh, 4: O.gelu_tanh}[act](ref) + resid.double()
+    Ad, Wd, bd, rd = A.cuda(), W.cuda(), bias.cuda(), resid.cuda()
+    out = torch.empty(M, N, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.msq_gemm(0, Ad.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), out.data_ptr(), M, N, K, act, st))
+    torch.cuda.synchronize()
+    _close(out, ref.float(), 2e-5, "ffma gemm")
+
+
+@pytest.mark.parametrize("M,N,K,act,out_bf16", [(128, 256, 64, 0, False), (300, 768, 768, 0, False), (4540, 2304, 768, 0, True),
+                                                (1980, 3072, 768, 2, True), (777, 768, 3072, 1, False), (50, 128, 128, 3, True)])
+def test_gemm_tcgen05(M, N, K, act, out_bf16):
+    """tcgen05/TMA GEMM against a float64 product of the SAME bf16-rounded operands: the only error
+    left is fp32 accumulation order (+ one bf16 rounding of the output when out_bf16)."""
+    import ctypes as C
+    from multimodal_sequencing_b200 import _lib
+    lib = _lib.load()
+    assert lib.msq_tc_available() == 1, "tcgen05 path unavailable on this device"
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).bfloat16()
+    W = (torch.randn(N, K, generator=g) * 0.05).bfloat16()
+    bias, resid = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    ref = A.double() @ W.double().t() + bias.double()
+    ref = {0: lambda x: x, 1: O.gelu_erf, 2: O.quick_gelu, 3: torch.tanh}[act](ref) + resid.double()
+    Ad, Wd, bd, rd = A.cuda(), W.cuda(), bias.cuda(), resid.cuda()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.msq_gemm(2 if out_bf16 else 1, Ad.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), out.data_ptr(),
+                            M, N, K, act, st))
+    torch.cuda.synchronize()
+    _close(out, ref.float(), 8e-3 if out_bf16 else 3e-5, "tcgen05 gemm")
+
+
+@pytest.mark.parametrize("H,eps", [(768, 1e-12), (128, 1e-5), (1024, 1e-6)])
+def test_layernorm(H, eps):
+    import ctypes as C
+    from multimodal_sequencing_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(H)
+    x, gamma, beta = torch.randn(1001, H, generator=g) * 3 + 1, torch.randn(H, generator=g), torch.randn(H, generator=g)
+    ref = torch.nn.functional.layer_norm(x.double(), (H,), gamma.double(), beta.double(), eps).float()
+    xd, gd, bd = x.cuda(), gamma.cuda(), beta.cuda()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out = torch.empty_like(xd)
+    _lib.check(lib.msq_layernorm(0, xd.data_ptr(), 1001, H, gd.data_ptr(), bd.data_ptr(), eps, out.data_ptr(), st))
+    outb = torch.empty_like(xd, dtype=torch.bfloat16)
+    _lib.check(lib.msq_layernorm(1, xd.data_ptr(), 1001, H, gd.data_ptr(), bd.data_ptr(), eps, outb.data_ptr(), st))
+    torch.cuda.synchronize()
+    _close(out, ref, 1e-5, "layernorm fp32")
+    _close(outb, ref, 8e-3, "layernorm bf16")
+
+
+@pytest.mark.parametrize("L,heads,masked", [(227, 12, True), (99, 12, False), (40, 2, True)])
+def test_attention(L, heads, masked):
+    import ctypes as C
+    from multimodal_sequencing_b200 import _lib
+    lib = _lib.load()
+    R, D = 3, 64
+    g = torch.Generator().manual_seed(L)
+    qkv = torch.randn(R * L, 3 * heads * D, generator=g)
+    mlen = L // 2 + 3
+    mask = torch.zeros(R, mlen)
+    mask[:, mlen - 5:] = -10000.0
+    q, k, v = (t.reshape(R, L, heads, D).permute(0, 2, 1, 3).double() for t in qkv.split(heads * D, -1))
+    s = q @ k.transpose(-1, -2) / 8.0
+    if masked:
+        full = torch.zeros(R, L, dtype=torch.float64)
+        full[:, :mlen] = mask
+        s = s + full[:, None, None, :]
+    ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(R * L, heads * D).float()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    qd, md = qkv.cuda(), mask.cuda()
+    out = torch.empty(R * L, heads * D, device="cuda")
+    _lib.check(lib.msq_attention(0, qd.data_ptr(), R, L, heads, 0.125, md.data_ptr() if masked else None, mlen if masked else 0,
+                                 out.data_ptr(), st))
+    qb = qd.bfloat16()
+    outb = torch.empty(R * L, heads * D, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.msq_attention(1, qb.data_ptr(), R, L, heads, 0.125, md.data_ptr() if masked else None, mlen if masked else 0,
+                                 outb.data_ptr(), st))
+    torch.cuda.synchronize()
+    _close(out, ref, 1e-5, "attention fp32")
+    _close(outb, ref, 3e-2, "attention bf16")
+
+
+# ---------------------------------------------------------------------------------------------
+# golden fixtures produced by the REAL reference
+# ---------------------------------------------------------------------------------------------
+
+def test_decode_full_width_golden(golden_dir):
+    """H=768 decode stage fed with identical (seeded) encode outputs: bit-exact beam indices and
+    permutations for N in {5,6,10} x W in {1,4,8,16} against the reference's beam_search_pointer."""
+    g = torch.load(os.path.join(golden_dir, "decode_full.pt"), weights_only=False)
+    H = g["H"]
+    cfg = dict(hidden_size=H, num_hidden_layers=1, num_attention_heads=12, intermediate_size=64, vocab_size=64,
+               max_position_embeddings=8, vit=None, para_ff=64)
+    sd = synth.full_state_dict(cfg, None, seed=0, ff=64)
+    sd.update(synth.decode_head_weights(H, 7))
+    eng = _engine(sd, cfg, precise=True)
+    for c in g["cases"]:
+        enc = synth.synthetic_encode(c["N"], H, c["enc_seed"])
+        perm, tr = eng.beam_search(enc, c["N"], c["W"], trace=True)
+        torch.cuda.synchronize()
+        assert perm[0].tolist() == c["perm"], (c["N"], c["W"], perm[0].tolist(), c["perm"])
+        _check_trace(tr, 0, c["steps"], c["W"], c["N"])
+
+
+def test_decode_batched_equals_single(golden_dir):
+    """batched beam search (a new capability) must reproduce the per-manual results exactly."""
+    H = 768
+    cfg = dict(hidden_size=H, num_hidden_layers=1, num_attention_heads=12, intermediate_size=64, vocab_size=64,
+               max_position_embeddings=8, vit=None, para_ff=64)
+    sd = synth.full_state_dict(cfg, None, seed=0, ff=64)
+    eng = _engine(sd, cfg, precise=True)
+    for N, W, B in ((5, 4, 37), (10, 16, 9), (6, 8, 20), (5, 1, 300)):
+        enc = synth.synthetic_encode(N, H, seed=500 + N, B=B)
+        perm = eng.beam_search(enc, N, W).cpu()
+        for b in (0, 1, B // 2, B - 1):
+            one = {k: (v[b:b + 1] if v.shape[0] == B else v[:, b:b + 1]) for k, v in enc.items() if k in ("sents", "key", "cls_mat", "score_mat")}
+            one["h0"] = enc["h0"][:, b:b + 1]
+            assert eng.beam_search(one, N, W).cpu()[0].tolist() == perm[b].tolist()
+            assert sorted(perm[b].tolist()) == list(range(N))
+        ref = O.beam_search(sd, enc, N, W, manual=B - 1)
+        assert perm[B - 1].tolist() == ref
+
+
+@pytest.mark.parametrize("precise", [True, False])
+def test_text_tiny_golden(golden_dir, precise):
+    g = torch.load(os.path.join(golden_dir, "text_tiny.pt"), weights_only=False)
+    eng = _engine(g["sd"], _cfg_from_golden(g), precise)
+    n_equal = 0
+    for c in g["cases"]:
+        pb = eng.prepare(c["ids"], c["labels"], c["N"])
+        enc = eng.encode(pb)
+        torch.cuda.synchronize()
+        if precise:
+            for k in ENC:
+                _close(enc[k].reshape(c["enc"][k].shape), c["enc"][k], 4 * REL_FP32, k)
+            perm, tr = eng.beam_search(enc, c["N"], c["W"], trace=True)
+            assert perm[0].tolist() == c["perm"]
+            _check_trace(tr, 0, c["steps"], c["W"], c["N"])
+            assert eng.order(c["ids"], c["labels"], c["N"], c["W"]) == [c["perm"]]
+        else:
+            for k in ENC:
+                _close(enc[k].reshape(c["enc"][k].shape), c["enc"][k], 3e-2, k)
+            # decode stage stays fp32: identical encoder outputs in -> identical permutation out
+            perm = eng.beam_search(c["enc"], c["N"], c["W"])
+            assert perm[0].tolist() == c["perm"]
+            n_equal += eng.order(c["ids"], c["labels"], c["N"], c["W"]) == [c["perm"]]
+    if not precise:
+        print("bf16 end-to-end permutation agreement: %d / %d" % (n_equal, len(g["cases"])))
+
+
+@pytest.mark.parametrize("precise", [True, False])
+def test_mm_tiny_golden(golden_dir, precise):
+    g = torch.load(os.path.join(golden_dir, "mm_tiny.pt"), weights_only=False)
+    eng = _engine(g["sd"], _cfg_from_golden(g), precise)
+    rel = 4 * REL_FP32 if precise else 3e-2
+    for c in g["cases"]:
+        ids, labels, images = O.synthetic_manuals(1, c["N"], c["L"], vocab=1000, image_px=224, seed=c["seed"])
+        pb = eng.prepare(ids, labels, c["N"], images)
+        # stage-wise: tower, inner model
+        P = pb.input_ids.shape[1]
+        tower = eng.vit_forward(pb.images, pb.img_index.reshape(-1, 2)[:3], 3)
+        _close(tower, c["tower"], rel, "vit tower")
+        lang, visn, pooled = eng.inner_forward(pb.input_ids[0], pb.token_type_ids[0], pb.attention_mask[0], pb.images,
+                                               pb.img_index[0], want_pooled=True)
+        _close(lang[:3], c["lang"], rel, "lang")
+        _close(visn[:3], c["visn"], rel, "visn")
+        _close(pooled, c["pooled"], rel, "pooled")
+        enc = eng.encode(pb)
+        for k in ENC:
+            _close(enc[k].reshape(c["enc"][k].shape), c["enc"][k], rel, k)
+        if precise:
+            perm, tr = eng.beam_search(enc, c["N"], c["W"], trace=True)
+            assert perm[0].tolist() == c["perm"]
+            _check_trace(tr, 0, c["steps"], c["W"], c["N"])
+            assert eng.order(ids, labels, c["N"], c["W"], images) == [c["perm"]]
+            hp = eng.order_host(eng.prepare(ids, labels, c["N"], images), c["W"])
+            assert hp.tolist() == [c["perm"]]
+        else:
+            assert eng.beam_search(c["enc"], c["N"], c["W"])[0].tolist() == c["perm"]
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size model (BERT-base + ViT-B/32) against the oracle run on the box's host cores
+# ---------------------------------------------------------------------------------------------
+
+def _full_cfg(mm):
+    cfg = dict(synth.BERT_BASE)
+    cfg.update(vit=dict(synth.VIT_B32) if mm else None, para_ff=3072)
+    return cfg
+
+
+@pytest.mark.parametrize("mm", [False, True])
+def test_full_size_vs_oracle(mm):
+    cfg = _full_cfg(mm)
+    sd = synth.full_state_dict(cfg, cfg["vit"], seed=0)
+    N, W, B = 5, 4, 2
+    ids, labels, images = O.synthetic_manuals(B, N, 64, image_px=224 if mm else None, seed=1)
+    torch.set_num_threads(os.cpu_count() or 1)
+    ocfg = dict(num_hidden_layers=12, num_attention_heads=12, vit=cfg["vit"])
+    inp = O.prepare_inputs(ids, labels, N, images)
+    oenc = O.encode(sd, ocfg, inp)
+    operm = [O.beam_search(sd, oenc, N, W, b) for b in range(B)]
+    for precise in (True, False):
+        eng = _engine(sd, cfg, precise)
+        pb = eng.prepare(ids, labels, N, images)
+        enc = eng.encode(pb, want_top_vec=True)
+        torch.cuda.synchronize()
+        errs = {k: _close(enc[k].reshape(oenc[k].shape), oenc[k], (1e-4 if precise else 5e-2), k) for k in ENC + ["top_vec"]}
+        print("full-size %s %s max-abs errors: %s" % ("mm" if mm else "text", "fp32" if precise else "bf16",
+                                                      {k: "%.2e" % v for k, v in errs.items()}))
+        # decode: identical encoder outputs in -> identical permutations out (bit-exact index work)
+        assert eng.beam_search(oenc, N, W).cpu().tolist() == operm
+        perm = eng.order(ids, labels, N, W, images)
+        if precise:
+            assert perm == operm
+            assert O.cal_result(labels.tolist(), perm) == O.cal_result(labels.tolist(), operm)
+        else:
+            print("bf16 end-to-end permutations equal oracle: %s" % (perm == operm))
+        del eng
+        torch.cuda.empty_cache()
+
+
+def test_full_size_batch_invariance_and_chunking():
+    """Size-independent properties at the benchmark configuration: every output is a permutation;
+    results do not depend on batch composition or on the micro-batch (chunk) boundaries; reruns are
+    bit-identical."""
+    cfg = _full_cfg(True)
+    sd = synth.full_state_dict(cfg, cfg["vit"], seed=0)
+    eng = _engine(sd, cfg, precise=False)
+    N, W, B = 5, 4, 40  # > MSQ_CHUNK_MANUALS (32): crosses a chunk boundary
+    ids, labels, images = O.synthetic_manuals(B, N, 64, image_px=224, seed=5)
+    full = eng.order(ids, labels, N, W, images)
+    assert all(sorted(p) == list(range(N)) for p in full)
+    assert eng.order(ids, labels, N, W, images) == full
+    for sl in (slice(0, 1), slice(31, 33), slice(39, 40)):
+        assert eng.order(ids[sl], labels[sl], N, W, images[sl]) == full[sl]
+    hp = eng.order_host(eng.prepare(ids, labels, N, images), W)
+    assert hp.tolist() == full
