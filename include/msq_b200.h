@@ -49,6 +49,12 @@ int64_t msq_launch_count(void);
 /* 1 if the tcgen05/TMA GEMM path can be used on the current device (sm_100), else 0 */
 int msq_tc_available(void);
 
+/* Per-launch CUDA-event timing of the dominant kernel (the tcgen05 GEMM), for bench.py's roofline line:
+ * events are recorded on the launching stream around every GEMM launch while enabled; msq_profile_read
+ * synchronises and returns the summed duration (ms), algorithmic FLOPs (2*M*N*K) and launch count. */
+int msq_profile_enable(int32_t on);
+int msq_profile_read(double* total_ms, double* total_flops, int64_t* launches);
+
 /* ---- model lifetime ------------------------------------------------------------------------ */
 int msq_model_create(const msq_config* cfg, msq_model** out);
 void msq_model_destroy(msq_model* m);

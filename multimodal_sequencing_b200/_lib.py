@@ -26,6 +26,8 @@ SIGNATURES = {
     "msq_version": (C.c_int, []),
     "msq_launch_count": (_I64, []),
     "msq_tc_available": (C.c_int, []),
+    "msq_profile_enable": (C.c_int, [_I32]),
+    "msq_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I64)]),
     "msq_model_create": (C.c_int, [C.POINTER(MsqConfig), C.POINTER(_P)]),
     "msq_model_destroy": (None, [_P]),
     "msq_model_set_weight": (C.c_int, [_P, C.c_char_p, _P, _I64, _P]),

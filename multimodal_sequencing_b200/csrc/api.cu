@@ -27,6 +27,39 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// ---- per-launch event profile (bench.py roofline): events bracket each tcgen05 GEMM launch on its stream
+struct Profile {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // pairs: begin, end
+  std::vector<double> flops;
+  size_t used = 0;               // pairs recorded
+  double acc_ms = 0, acc_flops = 0;
+  int64_t acc_launches = 0;
+};
+static Profile g_prof;
+constexpr size_t PROF_MAX_PAIRS = 8192;
+
+void profile_mark(cudaStream_t st, bool end, double flops) {
+  if (!g_prof.on) return;
+  if (!end) {
+    if (g_prof.used >= PROF_MAX_PAIRS) return;
+    if (g_prof.ev.size() < 2 * (g_prof.used + 1)) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      g_prof.ev.push_back(a);
+      g_prof.ev.push_back(b);
+      g_prof.flops.push_back(0.0);
+    }
+    cudaEventRecord(g_prof.ev[2 * g_prof.used], st);
+  } else {
+    if (g_prof.used >= PROF_MAX_PAIRS) return;
+    cudaEventRecord(g_prof.ev[2 * g_prof.used + 1], st);
+    g_prof.flops[g_prof.used] = flops;
+    ++g_prof.used;
+  }
+}
+
 struct Arena {
   char* base = nullptr;
   size_t cap = 0, off = 0;
@@ -262,6 +295,30 @@ extern "C" const char* msq_last_error(void) { return g_err; }
 extern "C" int msq_version(void) { return 100; }
 extern "C" int64_t msq_launch_count(void) { return g_launches.load(); }
 extern "C" int msq_tc_available(void) { return gemm_tc_selftest_supported(); }
+
+extern "C" int msq_profile_enable(int32_t on) {
+  g_prof.on = on != 0;
+  g_prof.used = 0;
+  g_prof.acc_ms = g_prof.acc_flops = 0;
+  g_prof.acc_launches = 0;
+  return MSQ_OK;
+}
+// Synchronises the device, folds the recorded event pairs into the totals and returns them.
+extern "C" int msq_profile_read(double* total_ms, double* total_flops, int64_t* launches) {
+  MSQ_CUDA(cudaDeviceSynchronize());
+  for (size_t i = 0; i < g_prof.used; ++i) {
+    float ms = 0.f;
+    MSQ_CUDA(cudaEventElapsedTime(&ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+    g_prof.acc_ms += ms;
+    g_prof.acc_flops += g_prof.flops[i];
+    ++g_prof.acc_launches;
+  }
+  g_prof.used = 0;
+  if (total_ms) *total_ms = g_prof.acc_ms;
+  if (total_flops) *total_flops = g_prof.acc_flops;
+  if (launches) *launches = g_prof.acc_launches;
+  return MSQ_OK;
+}
 
 extern "C" int msq_model_create(const msq_config* cfg, msq_model** out) {
   MSQ_REQUIRE(cfg && out, "null argument");

@@ -25,7 +25,7 @@ constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2, TC_B_BYTES = TC_BN * TC_BK * 2, TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_EPI_WARPS = 8, TC_THREADS = (2 + TC_EPI_WARPS) * 32;
 constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr uint32_t TC_SPIN_LIMIT = 1u << 26;
+constexpr long long TC_WAIT_CYCLES = 4000000000ll;  // ~2 s: a lost arrival must not hang the GPU
 
 struct TcEpi {
   const float* bias;
@@ -41,7 +41,8 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
+  uint32_t done = 0;
+  long long t0 = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -51,7 +52,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    if (++spins > TC_SPIN_LIMIT) {  // a lost arrival would otherwise hang the GPU: fail loudly instead
+    if (t0 == 0) t0 = clock64();
+    if (clock64() - t0 > TC_WAIT_CYCLES) {  // fail loudly instead of hanging
       printf("gemm_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }
@@ -328,8 +330,10 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   const int num_m = ceil_div(g.M, TC_BM), num_n = ceil_div(g.N, TC_BN), num_k = g.K / TC_BK;
   const int64_t tiles = (int64_t)num_m * num_n;
   const int grid = (int)min((int64_t)sms, tiles);
+  profile_mark(st, false, 0.0);
   gemm_tc_kernel<TO><<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, ep, num_m, num_n, num_k);
   MSQ_LAUNCH_CHECK();
+  profile_mark(st, true, 2.0 * (double)g.M * (double)g.N * (double)g.K);
   return MSQ_OK;
 }
 template int gemm_tc<float>(const GemmArgs&, cudaStream_t);

@@ -5,6 +5,9 @@
 
 namespace msq {
 
+// ---- api.cu : optional per-launch CUDA-event profile of the dominant (tcgen05 GEMM) kernel
+void profile_mark(cudaStream_t st, bool end, double flops);
+
 // ---- elementwise.cu
 template <typename T>
 int layernorm(const float* x, int64_t rows, int H, const float* gamma, const float* beta, float eps, float* out_f,
