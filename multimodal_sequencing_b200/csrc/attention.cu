@@ -6,7 +6,9 @@
 //           models/berson/modeling_bert.py:208-241): scores / sqrt(d) + mask(-10000), softmax, P V;
 //           nn.MultiheadAttention inside ResidualAttentionBlock  models/CLIP/clip/model.py:204-226.
 // Input layout: qkv [R*L, 3*heads*64] rows = tokens, columns = (q | k | v), each heads x 64.
-#include "kernels.cuh"
+#include <stdlib.h>
+
+#include "tc_common.cuh"
 
 namespace msq {
 
@@ -89,12 +91,207 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attention_simt_kernel(const T* 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// tcgen05 version (bf16): one CTA per (token group, head), 128 threads.
+//   TMA loads Q (<= 2 tiles of 128 rows), K and V ([KP keys] x 64, 128B swizzle) straight out of the
+//   packed qkv activation; S = Q K^T is ONE tcgen05.mma chain (M=128, N=KP, K=64) into TMEM; each
+//   thread owns one query row (TMEM lane): two passes over its S row (max, then exp2 / sum), P is written
+//   back over S as packed bf16 (tcgen05.st) and O = P V runs as a TMEM-A ("TS") tcgen05.mma chain with
+//   V consumed MN-major from the same swizzled tile (no transpose anywhere); O is normalised by the
+//   row sum in the epilogue.  TMEM columns: S [0,KP), P [0,KP/2), O [KP/2, KP/2+64).
+//   KP = 256 -> 2 CTAs/SM (96 KB smem, 256 TMEM columns each); KP = 128 -> 4 CTAs/SM.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
+template <int KP>
+__global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant__ CUtensorMap map_q,
+                                                           const __grid_constant__ CUtensorMap map_kv, int L, int heads,
+                                                           float scale_l2e, const float* __restrict__ mask_add, int mask_ld,
+                                                           int mask_len, bf16* __restrict__ ctx) {
+  constexpr int Q_BYTES = 128 * 64 * 2, KV_BYTES = KP * 64 * 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base, sK = base + 2 * Q_BYTES, sV = sK + KV_BYTES, sM = sV + KV_BYTES;
+  float* maskf = reinterpret_cast<float*>(gen + 2 * Q_BYTES + 2 * KV_BYTES);
+  const uint32_t bars = sM + KP * 4;  // bar_load | bar_s | bar_o | tmem slot
+  volatile uint32_t* tslot_gen = reinterpret_cast<volatile uint32_t*>(gen + 2 * Q_BYTES + 2 * KV_BYTES + KP * 4 + 24);
+  const uint32_t bar_load = bars, bar_s = bars + 8, bar_o = bars + 16, tslot = bars + 24;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int nqt = (L + 127) >> 7;
+  const float LOG2E = 1.4426950408889634f;
+
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(KP) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int key = tid; key < KP; key += 128)
+    maskf[key] = key < L ? ((mask_add != nullptr && key < mask_len) ? mask_add[(int64_t)r * mask_ld + key] * LOG2E : 0.f) : -INFINITY;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot_gen;
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_load, (uint32_t)(nqt * Q_BYTES + 2 * KV_BYTES));
+    const int row0 = r * L;
+    tma_load_2d(sK, &map_kv, heads * AT_D + h * AT_D, row0, bar_load);
+    tma_load_2d(sV, &map_kv, 2 * heads * AT_D + h * AT_D, row0, bar_load);
+    for (int qt = 0; qt < nqt; ++qt) tma_load_2d(sQ + qt * Q_BYTES, &map_q, h * AT_D, row0 + qt * 128, bar_load);
+  }
+  mbar_wait(bar_load, 0);
+
+  // instruction descriptors: D=F32, A=B=BF16; S: N=KP, A/B K-major; PV: N=64, B MN-major (bit 16)
+  const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KP >> 3) << 17) | (8u << 24);
+  const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | (8u << 24);
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+
+  for (int qt = 0; qt < nqt; ++qt) {
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem, umma_desc_sw128(sQ + qt * Q_BYTES + k * 32), umma_desc_sw128(sK + k * 32), idesc_s, k != 0);
+      umma_commit(bar_s);
+    }
+    mbar_wait(bar_s, qt & 1);
+    __syncwarp();
+    tc_fence_after();
+
+    // ---- softmax over this thread's query row
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int j = 0; j < KP / 32; ++j) {
+      uint32_t raw[32];
+      tmem_ld32(lane_addr + j * 32, raw);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(raw[i]), scale_l2e, maskf[j * 32 + i]));
+    }
+    float sum = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < KP / 32; ++j) {
+      uint32_t raw[32], pk[16];
+      tmem_ld32(lane_addr + j * 32, raw);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float p0 = exp2f(fmaf(__uint_as_float(raw[2 * i]), scale_l2e, maskf[j * 32 + 2 * i]) - mx);
+        const float p1 = exp2f(fmaf(__uint_as_float(raw[2 * i + 1]), scale_l2e, maskf[j * 32 + 2 * i + 1]) - mx);
+        sum += p0 + p1;
+        __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);  // .x (low half) = even key
+        pk[i] = *reinterpret_cast<uint32_t*>(&b);
+      }
+      tmem_st16(lane_addr + j * 16, pk);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < KP / 16; ++kk)
+        umma_bf16_ts(tmem + KP / 2, tmem + kk * 8, umma_desc_sw128(sV + kk * 2048), idesc_o, kk != 0);
+      umma_commit(bar_o);
+    }
+    mbar_wait(bar_o, qt & 1);
+    __syncwarp();
+    tc_fence_after();
+
+    const int q = qt * 128 + warp * 32 + lane;
+    const float inv = 1.0f / sum;
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
+      uint32_t raw[32];
+      tmem_ld32(lane_addr + KP / 2 + j * 32, raw);
+      if (q < L) {
+        bf16* op = ctx + ((int64_t)r * L + q) * (heads * AT_D) + h * AT_D + j * 32;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          __nv_bfloat162 a = __floats2bfloat162_rn(__uint_as_float(raw[8 * i]) * inv, __uint_as_float(raw[8 * i + 1]) * inv);
+          __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(raw[8 * i + 2]) * inv, __uint_as_float(raw[8 * i + 3]) * inv);
+          __nv_bfloat162 c = __floats2bfloat162_rn(__uint_as_float(raw[8 * i + 4]) * inv, __uint_as_float(raw[8 * i + 5]) * inv);
+          __nv_bfloat162 d = __floats2bfloat162_rn(__uint_as_float(raw[8 * i + 6]) * inv, __uint_as_float(raw[8 * i + 7]) * inv);
+          u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+          u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+          *reinterpret_cast<uint4*>(op + 8 * i) = u;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // every row has drained S/P/O before the next tile's MMAs overwrite them
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(KP) : "memory");
+  }
+}
+
+template <int KP>
+static int launch_attention_tc(const bf16* qkv, int64_t R, int L, int heads, float scale, const float* mask_add, int mask_ld,
+                               int mask_len, bf16* ctx, cudaStream_t st) {
+  CUtensorMap mq, mkv;
+  const int ld = 3 * heads * AT_D;
+  MSQ_TRY(make_map_bf16(&mq, qkv, R * L, ld, ld, AT_D, 128));
+  MSQ_TRY(make_map_bf16(&mkv, qkv, R * L, ld, ld, AT_D, KP));
+  constexpr int SMEM = 2 * 128 * 64 * 2 + 2 * KP * 64 * 2 + KP * 4 + 64 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    MSQ_CUDA(cudaFuncSetAttribute(attention_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  attention_tc_kernel<KP><<<(unsigned)(R * heads), 128, SMEM, st>>>(mq, mkv, L, heads, scale * 1.4426950408889634f, mask_add,
+                                                                    mask_ld, mask_len, ctx);
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+
+static bool attention_use_tc() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MSQ_ATTN_SIMT"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v && tc_supported_impl();
+}
+
 template <typename T>
 int attention(const T* qkv, int64_t R, int L, int heads, int dhead, float scale, const float* key_mask_add, int mask_ld,
               int mask_len, T* ctx, cudaStream_t st) {
   MSQ_REQUIRE(dhead == AT_D, "attention: head dim %d != 64", dhead);
   MSQ_REQUIRE(L >= 1 && L <= 320, "attention: sequence length %d out of range", L);
   if (R == 0) return MSQ_OK;
+  if constexpr (sizeof(T) == 2) {
+    if (attention_use_tc() && L <= 256 && (((uintptr_t)qkv) & 15) == 0) {
+      if (L <= 128)
+        return launch_attention_tc<128>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
+      return launch_attention_tc<256>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
+    }
+  }
   const int Lpad = (L + 31) & ~31;
   const size_t smem = sizeof(float) * ((size_t)L * 65 + (size_t)L * AT_D + ((L + 3) & ~3) + AT_WARPS * AT_D + AT_WARPS * Lpad);
   static size_t configured_f = 0, configured_b = 0;

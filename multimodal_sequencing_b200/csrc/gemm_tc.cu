@@ -7,17 +7,16 @@
 //   * the 512 TMEM columns hold TWO 128x256 fp32 accumulators so the epilogue of tile i overlaps the
 //     MMAs of tile i+1; 8 epilogue warps read TMEM with tcgen05.ld, apply bias / activation /
 //     residual in registers and store bf16 or fp32 rows;
-//   * persistent: one CTA per SM walks tiles m-fastest so CTAs running together share the weight tile
-//     in L2.
+//   * persistent: one CTA per SM walks tiles n-fastest, so the CTAs running together cover all N tiles of
+//     a few M blocks: every A tile is fetched from HBM once and re-read from L2, the (small) weight
+//     matrix stays L2-resident.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc/dealloc), 2..9 = epilogue.
 //
 // Replaces the cuBLAS calls behind every nn.Linear of the encoders: CLIP ViT blocks
 // (models/CLIP/clip/model.py:204-226, conv1 263), joint BERT layers
 // (models/CLIP/src/lxrt/modeling.py:373-507), visn_fc (585-602) and HierarchicalAttention.sentence_tran
 // (models/berson/modeling_bert.py:697).
-#include <cuda.h>
-
-#include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace msq {
 
@@ -25,7 +24,6 @@ constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2, TC_B_BYTES = TC_BN * TC_BK * 2, TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_EPI_WARPS = 8, TC_THREADS = (2 + TC_EPI_WARPS) * 32;
 constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr long long TC_WAIT_CYCLES = 4000000000ll;  // ~2 s: a lost arrival must not hang the GPU
 
 struct TcEpi {
   const float* bias;
@@ -34,79 +32,6 @@ struct TcEpi {
   int64_t M;
   int N, ldc, ldr, act;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  long long t0 = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (t0 == 0) t0 = clock64();
-    if (clock64() - t0 > TC_WAIT_CYCLES) {  // fail loudly instead of hanging
-      printf("gemm_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset: 8 rows x 128 B
-  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 template <typename TO> __device__ __forceinline__ void epi_store8(TO* p, const float* v);
 template <> __device__ __forceinline__ void epi_store8<float>(float* p, const float* v) {
@@ -160,7 +85,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        const int n_blk = tile % num_n, m_blk = tile / num_n;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t sa = base + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
@@ -206,8 +131,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint32_t acc_phase = 0;
     TO* C = reinterpret_cast<TO*>(ep.C);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int n_blk = tile % num_n, m_blk = tile / num_n;
       mbar_wait(tfull0 + 8 * acc, acc_phase);
+      __syncwarp();
       tc_fence_after();
       const int64_t row = (int64_t)m_blk * TC_BM + q * 32 + lane;
       const bool row_ok = row < ep.M;
@@ -259,48 +185,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
 // ---- host side ------------------------------------------------------------------------------------
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-int gemm_tc_selftest_supported() {
-  static int cached = -1;
-  if (cached >= 0) return cached;
-  int dev = 0;
-  cudaDeviceProp prop;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return cached = 0;
-  cached = (prop.major == 10 && get_encode_fn() != nullptr) ? 1 : 0;
-  return cached;
-}
-
-static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int K, int ld, int box_rows) {
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld K=%d ld=%d", (int)r, (long long)rows, K, ld);
-    return MSQ_ERR_CUDA;
-  }
-  return MSQ_OK;
-}
+int gemm_tc_selftest_supported() { return tc_supported_impl(); }
 
 template <typename TO>
 int gemm_tc(const GemmArgs& g, cudaStream_t st) {
@@ -311,8 +196,8 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   MSQ_REQUIRE(g.C2 == nullptr, "gemm_tc: second output unsupported");
   if (g.M == 0) return MSQ_OK;
   CUtensorMap ma, mb;
-  MSQ_TRY(make_map(&ma, g.A, g.M, g.K, g.lda, TC_BM));
-  MSQ_TRY(make_map(&mb, g.W, g.N, g.K, g.ldw, TC_BN));
+  MSQ_TRY(make_map_bf16(&ma, g.A, g.M, g.K, g.lda, TC_BK, TC_BM));
+  MSQ_TRY(make_map_bf16(&mb, g.W, g.N, g.K, g.ldw, TC_BK, TC_BN));
   static int sms = 0;
   static bool configured[2] = {false, false};
   if (!sms) {
