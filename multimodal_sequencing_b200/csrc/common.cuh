@@ -79,6 +79,40 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// Cheap variants for the tensor-core epilogues, whose results are rounded to bf16 (or feed a bf16 GEMM):
+// erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7), tanh through MUFU ex2/rcp only (2 SFU ops per element).
+__device__ __forceinline__ float apply_act_fast(float x, int act) {
+  switch (act) {
+    case ACT_GELU_ERF: {
+      const float z = fabsf(x) * 0.70710678118654752440f;
+      const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+      float p = fmaf(1.061405429f, t, -1.453152027f);
+      p = fmaf(p, t, 1.421413741f);
+      p = fmaf(p, t, -0.284496736f);
+      p = fmaf(p, t, 0.254829592f);
+      const float e = fmaf(-p * t, ex2_approx(-1.4426950408889634f * z * z), 1.0f);  // erf(|x|/sqrt2)
+      return 0.5f * x * (1.0f + copysignf(e, x));
+    }
+    case ACT_QUICK_GELU: return x * rcp_approx(1.0f + ex2_approx(-2.4554669595930157f * x));
+    case ACT_TANH: {
+      const float e = ex2_approx(-2.8853900817779268f * fabsf(x));
+      return copysignf((1.0f - e) * rcp_approx(1.0f + e), x);
+    }
+    default: return apply_act(x, act);
+  }
+}
+
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f(float v);

@@ -7,7 +7,11 @@
 //   * the 512 TMEM columns hold TWO 128x256 fp32 accumulators so the epilogue of tile i overlaps the
 //     MMAs of tile i+1; 8 epilogue warps read TMEM with tcgen05.ld, apply bias / activation /
 //     residual in registers and store bf16 or fp32 rows;
-//   * persistent: one CTA per SM walks tiles n-fastest, so the CTAs running together cover all N tiles of
+//   * PAIR variant: a 2-CTA cluster (two SMs of one TPC) owns a 256 x 256 tile; each CTA stages its own
+//     128 rows of A and 128 rows of W and ONE thread of the leader CTA issues tcgen05.mma.cta_group::2
+//     (M=256) which reads both CTAs' shared memory: L2->SM operand traffic per FLOP drops by 1/3 versus
+//     the 128 x 256 single-CTA tile (the single-CTA kernel is L2-bandwidth bound at ~45% of tensor peak);
+//   * persistent: one CTA (pair) per SM (pair) walks tiles n-fastest, so the CTAs running together cover all N tiles of
 //     a few M blocks: every A tile is fetched from HBM once and re-read from L2, the (small) weight
 //     matrix stays L2-resident.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc/dealloc), 2..9 = epilogue.
@@ -16,14 +20,24 @@
 // (models/CLIP/clip/model.py:204-226, conv1 263), joint BERT layers
 // (models/CLIP/src/lxrt/modeling.py:373-507), visn_fc (585-602) and HierarchicalAttention.sentence_tran
 // (models/berson/modeling_bert.py:697).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace msq {
 
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 4;
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 2, TC_B_BYTES = TC_BN * TC_BK * 2, TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_EPI_WARPS = 8, TC_THREADS = (2 + TC_EPI_WARPS) * 32;
-constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+template <bool PAIR> struct TcCfg {
+  static constexpr int STAGES = PAIR ? 6 : 4;
+  static constexpr int B_ROWS = PAIR ? 128 : 256;            // rows of W staged per CTA and stage
+  static constexpr int B_BYTES = B_ROWS * TC_BK * 2;
+  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  static constexpr int TILE_M = PAIR ? 256 : 128;            // rows of C per scheduling unit (CTA or CTA pair)
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TC_EPI_WARPS * 128 * 4 /*bias*/;
+};
 
 struct TcEpi {
   const float* bias;
@@ -32,6 +46,46 @@ struct TcEpi {
   int64_t M;
   int N, ldc, ldr, act;
 };
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are credited to an mbarrier given by its shared::cluster address
+// (the leader CTA's barrier when issued by the peer CTA of a pair)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit to the barrier at the same shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
 
 template <typename TO> __device__ __forceinline__ void epi_store8(TO* p, const float* v);
 template <> __device__ __forceinline__ void epi_store8<float>(float* p, const float* v) {
@@ -47,120 +101,177 @@ template <> __device__ __forceinline__ void epi_store8<bf16>(bf16* p, const floa
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-template <typename TO>
+template <typename TO, bool PAIR, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, TcEpi ep, int num_m,
                int num_n, int num_k) {
+  using Cfg = TcCfg<PAIR>;
+  constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES;
-  // barrier layout (8 B each): full[4] | empty[4] | tmem_full[2] | tmem_empty[2] | tmem base slot
-  const uint32_t full0 = bars, empty0 = bars + 8 * TC_STAGES, tfull0 = bars + 16 * TC_STAGES, tempty0 = tfull0 + 16;
+  const uint32_t bars = base + STAGES * STAGE_BYTES;
+  // barrier layout (8 B each): full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem base slot
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
   const uint32_t tslot = tempty0 + 16;
   uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
-  volatile uint32_t* tslot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + TC_STAGES * TC_STAGE_BYTES + 16 * TC_STAGES + 32);
+  volatile uint32_t* tslot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 16 * STAGES + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = num_m * num_n;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;            // 0 = leader CTA of the pair
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, TC_EPI_WARPS); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, TC_EPI_WARPS * (PAIR ? 2 : 1)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrival / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tslot_gen;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA stages its own rows) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
         const int n_blk = tile % num_n, m_blk = tile / num_n;
+        const int a_row = m_blk * Cfg::TILE_M + (int)rank * TC_BM, b_row = n_blk * TC_BN + (int)rank * Cfg::B_ROWS;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          const uint32_t sa = base + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
-          mbar_expect_tx(full0 + 8 * stage, TC_STAGE_BYTES);
-          tma_load_2d(sa, &tma_a, kb * TC_BK, m_blk * TC_BM, full0 + 8 * stage);
-          tma_load_2d(sb, &tma_b, kb * TC_BK, n_blk * TC_BN, full0 + 8 * stage);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + TC_A_BYTES;
+          if (PAIR) {
+            const uint32_t lead_full = mapa_rank(full0 + 8 * stage, 0);
+            if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * STAGE_BYTES);
+            tma_load_2d_pair(sa, &tma_a, kb * TC_BK, a_row, lead_full);
+            tma_load_2d_pair(sb, &tma_b, kb * TC_BK, b_row, lead_full);
+          } else {
+            mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
+            tma_load_2d(sa, &tma_a, kb * TC_BK, a_row, full0 + 8 * stage);
+            tma_load_2d(sb, &tma_b, kb * TC_BK, b_row, full0 + 8 * stage);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
       // instruction descriptor: D=F32 [4,6), A=BF16 [7,10), B=BF16 [10,13), K-major A/B, N>>3 [17,23), M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(Cfg::TILE_M >> 4) << 24);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * TC_BN;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t sa = base + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+          const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + TC_A_BYTES;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             const uint64_t da = umma_desc_sw128(sa + k * 32), db = umma_desc_sw128(sb + k * 32);
-            umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0);
+            if (PAIR) umma_bf16_pair(tmem_d, da, db, idesc, (kb | k) != 0);
+            else umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0);
           }
-          umma_commit(empty0 + 8 * stage);  // frees the smem slot when these MMAs have read it
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+          if (PAIR) umma_commit_pair(empty0 + 8 * stage); else umma_commit(empty0 + 8 * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull0 + 8 * acc);  // accumulator complete
+        if (PAIR) umma_commit_pair(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc);  // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue (8 warps) =====================
+    // ===================== epilogue (8 warps per CTA) =====================
+    // Each warp owns 32 TMEM lanes (rows) x 128 columns = 4 chunks of 32 columns.  Software pipeline:
+    // the residual rows of the first chunk and the bias slice are fetched BEFORE the accumulator is
+    // ready; inside a tile, the TMEM load and residual fetch of chunk c+1 are in flight while chunk c
+    // is converted and stored, so DRAM / TMEM latency is off the critical path.
     const int q = warp & 3;                 // TMEM lane quarter this warp may touch
     const int half = (warp - 2) >> 2;       // column half: 0 -> [0,128), 1 -> [128,256)
+    float* bias_s = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256) + (warp - 2) * 128;
     int acc = 0;
     uint32_t acc_phase = 0;
     TO* C = reinterpret_cast<TO*>(ep.C);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = unit; tile < num_tiles; tile += num_units) {
       const int n_blk = tile % num_n, m_blk = tile / num_n;
+      const int64_t row = (int64_t)m_blk * Cfg::TILE_M + (int)rank * TC_BM + q * 32 + lane;
+      const bool row_ok = row < ep.M;
+      const int colw = n_blk * TC_BN + half * 128;   // first column of this warp
+      const bool use_res = ep.resid != nullptr;
+      float4 res[8];
+      auto fetch_res = [&](int ch, float4* dst) {
+        const int c0 = colw + ch * 32;
+        const float* rp = ep.resid + row * ep.ldr + c0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          dst[i] = (row_ok && c0 + 4 * i < ep.N) ? __ldg(reinterpret_cast<const float4*>(rp + 4 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      if (use_res) fetch_res(0, res);
+      {
+        const int c = colw + lane * 4;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.bias && c < ep.N) b = __ldg(reinterpret_cast<const float4*>(ep.bias + c));
+        __syncwarp();
+        *reinterpret_cast<float4*>(bias_s + lane * 4) = b;
+        __syncwarp();
+      }
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       __syncwarp();
       tc_fence_after();
-      const int64_t row = (int64_t)m_blk * TC_BM + q * 32 + lane;
-      const bool row_ok = row < ep.M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_BN + half * 128;
+      uint32_t raw[32], raw_next[32];
+      float4 res_next[8];
+      tmem_ld32_nowait(taddr, raw_next);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) res_next[i] = res[i];
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
-        const int col0 = n_blk * TC_BN + half * 128 + ch * 32;
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_BN + half * 128 + ch * 32, raw);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; ++i) raw[i] = raw_next[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) res[i] = res_next[i];
+        if (ch + 1 < 4) {
+          tmem_ld32_nowait(taddr + (ch + 1) * 32, raw_next);
+          if (use_res) fetch_res(ch + 1, res_next);
+        }
+        const int col0 = colw + ch * 32;
         if (row_ok && col0 < ep.N) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int col = col0 + j * 8;
             if (col < ep.N) {  // N % 8 == 0
               float v[8];
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch * 32 + j * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch * 32 + j * 8 + 4);
+              v[0] = __uint_as_float(raw[j * 8 + 0]) + b0.x; v[1] = __uint_as_float(raw[j * 8 + 1]) + b0.y;
+              v[2] = __uint_as_float(raw[j * 8 + 2]) + b0.z; v[3] = __uint_as_float(raw[j * 8 + 3]) + b0.w;
+              v[4] = __uint_as_float(raw[j * 8 + 4]) + b1.x; v[5] = __uint_as_float(raw[j * 8 + 5]) + b1.y;
+              v[6] = __uint_as_float(raw[j * 8 + 6]) + b1.z; v[7] = __uint_as_float(raw[j * 8 + 7]) + b1.w;
+              if (ACT != ACT_NONE) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[j * 8 + i]);
-              if (ep.bias) {
-                const float4 b0 = *reinterpret_cast<const float4*>(ep.bias + col), b1 = *reinterpret_cast<const float4*>(ep.bias + col + 4);
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                for (int i = 0; i < 8; ++i) v[i] = apply_act_fast(v[i], ACT);
               }
-              if (ep.act != ACT_NONE) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], ep.act);
-              }
-              if (ep.resid) {
-                const float* rp = ep.resid + row * ep.ldr + col;
-                const float4 r0 = *reinterpret_cast<const float4*>(rp), r1 = *reinterpret_cast<const float4*>(rp + 4);
+              if (use_res) {
+                const float4 r0 = res[2 * j], r1 = res[2 * j + 1];
                 v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
               }
               epi_store8<TO>(C + row * ep.ldc + col, v);
@@ -170,22 +281,77 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (lane == 0) {
+        // the leader's MMA thread may reuse this accumulator only when BOTH CTAs have drained it
+        if (PAIR) mbar_arrive_cluster(mapa_rank(tempty0 + 8 * acc, 0)); else mbar_arrive(tempty0 + 8 * acc);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // no CTA exits (or frees TMEM) while its peer may still signal / read it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
 }
 
 // ---- host side ------------------------------------------------------------------------------------
 
 int gemm_tc_selftest_supported() { return tc_supported_impl(); }
+
+template <typename TO, bool PAIR, int ACT>
+static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
+  using Cfg = TcCfg<PAIR>;
+  CUtensorMap ma, mb;
+  MSQ_TRY(make_map_bf16(&ma, g.A, g.M, g.K, g.lda, TC_BK, TC_BM));
+  MSQ_TRY(make_map_bf16(&mb, g.W, g.N, g.K, g.ldw, TC_BK, Cfg::B_ROWS));
+  static bool configured = false;
+  if (!configured) {
+    MSQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TO, PAIR, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    configured = true;
+  }
+  TcEpi ep;
+  ep.bias = g.bias; ep.resid = g.resid; ep.C = g.C; ep.M = g.M; ep.N = g.N; ep.ldc = g.ldc; ep.ldr = g.ldr; ep.act = g.act;
+  const int num_m = ceil_div(g.M, Cfg::TILE_M), num_n = ceil_div(g.N, TC_BN), num_k = g.K / TC_BK;
+  const int64_t tiles = (int64_t)num_m * num_n;
+  profile_mark(st, false, 0.0);
+  if (PAIR) {
+    const int pairs = (int)min((int64_t)(sms / 2), tiles);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MSQ_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<TO, PAIR, ACT>, ma, mb, ep, num_m, num_n, num_k));
+  } else {
+    const int grid = (int)min((int64_t)sms, tiles);
+    gemm_tc_kernel<TO, PAIR, ACT><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ma, mb, ep, num_m, num_n, num_k);
+  }
+  MSQ_LAUNCH_CHECK();
+  profile_mark(st, true, 2.0 * (double)g.M * (double)g.N * (double)g.K);
+  return MSQ_OK;
+}
+
+template <typename TO, bool PAIR>
+static int launch_gemm_tc(const GemmArgs& g, int sms, cudaStream_t st) {
+  switch (g.act) {
+    case ACT_NONE: return launch_gemm_tc_act<TO, PAIR, ACT_NONE>(g, sms, st);
+    case ACT_GELU_ERF: return launch_gemm_tc_act<TO, PAIR, ACT_GELU_ERF>(g, sms, st);
+    case ACT_QUICK_GELU: return launch_gemm_tc_act<TO, PAIR, ACT_QUICK_GELU>(g, sms, st);
+    case ACT_TANH: return launch_gemm_tc_act<TO, PAIR, ACT_TANH>(g, sms, st);
+  }
+  set_error("gemm_tc: activation %d not supported on the tensor-core path", g.act);
+  return MSQ_ERR_ARG;
+}
 
 template <typename TO>
 int gemm_tc(const GemmArgs& g, cudaStream_t st) {
@@ -195,31 +361,17 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   MSQ_REQUIRE(((uintptr_t)g.A & 15) == 0 && ((uintptr_t)g.W & 15) == 0 && ((uintptr_t)g.C & 15) == 0, "gemm_tc: unaligned pointer");
   MSQ_REQUIRE(g.C2 == nullptr, "gemm_tc: second output unsupported");
   if (g.M == 0) return MSQ_OK;
-  CUtensorMap ma, mb;
-  MSQ_TRY(make_map_bf16(&ma, g.A, g.M, g.K, g.lda, TC_BK, TC_BM));
-  MSQ_TRY(make_map_bf16(&mb, g.W, g.N, g.K, g.ldw, TC_BK, TC_BN));
-  static int sms = 0;
-  static bool configured[2] = {false, false};
+  static int sms = 0, force_single = -1;
   if (!sms) {
     int dev = 0;
     MSQ_CUDA(cudaGetDevice(&dev));
     MSQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int which = sizeof(TO) == 4 ? 0 : 1;
-  if (!configured[which]) {
-    MSQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    configured[which] = true;
-  }
-  TcEpi ep;
-  ep.bias = g.bias; ep.resid = g.resid; ep.C = g.C; ep.M = g.M; ep.N = g.N; ep.ldc = g.ldc; ep.ldr = g.ldr; ep.act = g.act;
-  const int num_m = ceil_div(g.M, TC_BM), num_n = ceil_div(g.N, TC_BN), num_k = g.K / TC_BK;
-  const int64_t tiles = (int64_t)num_m * num_n;
-  const int grid = (int)min((int64_t)sms, tiles);
-  profile_mark(st, false, 0.0);
-  gemm_tc_kernel<TO><<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, ep, num_m, num_n, num_k);
-  MSQ_LAUNCH_CHECK();
-  profile_mark(st, true, 2.0 * (double)g.M * (double)g.N * (double)g.K);
-  return MSQ_OK;
+  if (force_single < 0) { const char* e = getenv("MSQ_GEMM_1CTA"); force_single = (e && e[0] == '1') ? 1 : 0; }
+  // CTA pairs pay off once there are enough 256 x 256 tiles to occupy most SM pairs
+  const int64_t pair_tiles = (int64_t)ceil_div(g.M, 256) * ceil_div(g.N, TC_BN);
+  if (!force_single && pair_tiles >= sms / 4) return launch_gemm_tc<TO, true>(g, sms, st);
+  return launch_gemm_tc<TO, false>(g, sms, st);
 }
 template int gemm_tc<float>(const GemmArgs&, cudaStream_t);
 template int gemm_tc<bf16>(const GemmArgs&, cudaStream_t);
