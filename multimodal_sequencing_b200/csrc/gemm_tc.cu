@@ -31,12 +31,16 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_EPI_WARPS = 8, TC_THREADS = (2 + TC_EPI_WARPS) * 32;
 
 template <bool PAIR> struct TcCfg {
-  static constexpr int STAGES = PAIR ? 6 : 4;
+  static constexpr int STAGES = 4;
+  // PAIR: the epilogue stages 32-row x 128-byte output boxes in shared memory (2 per warp) and writes
+  // them with TMA bulk tensor stores (full-line, asynchronous) instead of per-thread 16-byte stores.
+  static constexpr bool TMA_STORE = PAIR;
+  static constexpr int STAGING_BYTES = TMA_STORE ? TC_EPI_WARPS * 2 * 4096 : 0;
   static constexpr int B_ROWS = PAIR ? 128 : 256;            // rows of W staged per CTA and stage
   static constexpr int B_BYTES = B_ROWS * TC_BK * 2;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   static constexpr int TILE_M = PAIR ? 256 : 128;            // rows of C per scheduling unit (CTA or CTA pair)
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TC_EPI_WARPS * 128 * 4 /*bias*/;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TC_EPI_WARPS * 128 * 4 /*bias*/;
 };
 
 struct TcEpi {
@@ -103,18 +107,19 @@ template <> __device__ __forceinline__ void epi_store8<bf16>(bf16* p, const floa
 
 template <typename TO, bool PAIR, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, TcEpi ep, int num_m,
-               int num_n, int num_k) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_c, TcEpi ep, int num_m, int num_n, int num_k) {
   using Cfg = TcCfg<PAIR>;
   constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = base + STAGES * STAGE_BYTES;
+  const uint32_t staging0 = base + STAGES * STAGE_BYTES;  // [EPI_WARPS][2][4096], 1024-aligned
+  const uint32_t bars = staging0 + Cfg::STAGING_BYTES;
   // barrier layout (8 B each): full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem base slot
   const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
   const uint32_t tslot = tempty0 + 16;
   uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
-  volatile uint32_t* tslot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 16 * STAGES + 32);
+  volatile uint32_t* tslot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + Cfg::STAGING_BYTES + 16 * STAGES + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = num_m * num_n;
@@ -125,6 +130,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+    if (Cfg::TMA_STORE) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_c) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, TC_EPI_WARPS * (PAIR ? 2 : 1)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -206,7 +212,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // is converted and stored, so DRAM / TMEM latency is off the critical path.
     const int q = warp & 3;                 // TMEM lane quarter this warp may touch
     const int half = (warp - 2) >> 2;       // column half: 0 -> [0,128), 1 -> [128,256)
-    float* bias_s = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256) + (warp - 2) * 128;
+    float* bias_s = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + Cfg::STAGING_BYTES + 256) + (warp - 2) * 128;
+    const uint32_t stg = staging0 + (warp - 2) * 8192;  // this warp's two staging boxes
+    int stg_use = 0;                                       // boxes handed to the TMA so far (parity selects the buffer)
     int acc = 0;
     uint32_t acc_phase = 0;
     TO* C = reinterpret_cast<TO*>(ep.C);
@@ -254,7 +262,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (use_res) fetch_res(ch + 1, res_next);
         }
         const int col0 = colw + ch * 32;
-        if (row_ok && col0 < ep.N) {
+        if (Cfg::TMA_STORE) {
+          // ---- registers -> swizzled staging box -> TMA store.  A box is 32 rows x 128 B: 32 fp32 columns
+          // (one chunk) or 64 bf16 columns (two chunks).  16-byte piece c of row r sits at r*128 + ((c ^ (r&7))<<4).
+          constexpr bool F32 = sizeof(TO) == 4;
+          const bool new_box = F32 || (ch & 1) == 0;
+          if (new_box) {
+            if (lane == 0) tma_store_wait_read<1>();   // the box used two stores ago has been read out
+            __syncwarp();
+          }
+          const uint32_t box = stg + (stg_use & 1) * 4096;
+          const uint32_t rowp = box + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float v[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch * 32 + j * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch * 32 + j * 8 + 4);
+            v[0] = __uint_as_float(raw[j * 8 + 0]) + b0.x; v[1] = __uint_as_float(raw[j * 8 + 1]) + b0.y;
+            v[2] = __uint_as_float(raw[j * 8 + 2]) + b0.z; v[3] = __uint_as_float(raw[j * 8 + 3]) + b0.w;
+            v[4] = __uint_as_float(raw[j * 8 + 4]) + b1.x; v[5] = __uint_as_float(raw[j * 8 + 5]) + b1.y;
+            v[6] = __uint_as_float(raw[j * 8 + 6]) + b1.z; v[7] = __uint_as_float(raw[j * 8 + 7]) + b1.w;
+            if (ACT != ACT_NONE) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = apply_act_fast(v[i], ACT);
+            }
+            if (use_res) {
+              const float4 r0 = res[2 * j], r1 = res[2 * j + 1];
+              v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+            }
+            if (F32) {
+              st_shared_v4(rowp + (((2 * j) ^ (lane & 7)) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+              st_shared_v4(rowp + (((2 * j + 1) ^ (lane & 7)) << 4), __float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+            } else {
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+              st_shared_v4(rowp + ((((ch & 1) * 4 + j) ^ (lane & 7)) << 4), *reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                           *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+            }
+          }
+          if (F32 || (ch & 1) == 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int box_col = F32 ? col0 : col0 - 32;
+              if (box_col < ep.N) tma_store_2d(&tma_c, box, box_col, (int)(row - lane));
+              tma_store_commit();
+            }
+            ++stg_use;
+          }
+        } else if (row_ok && col0 < ep.N) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int col = col0 + j * 8;
@@ -289,6 +345,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   }
 
+  if (Cfg::TMA_STORE && warp >= 2 && lane == 0) tma_store_wait_read<0>();
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();  // no CTA exits (or frees TMEM) while its peer may still signal / read it
@@ -309,6 +366,8 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
   CUtensorMap ma, mb;
   MSQ_TRY(make_map_bf16(&ma, g.A, g.M, g.K, g.lda, TC_BK, TC_BM));
   MSQ_TRY(make_map_bf16(&mb, g.W, g.N, g.K, g.ldw, TC_BK, Cfg::B_ROWS));
+  CUtensorMap mc = ma;
+  if (Cfg::TMA_STORE) MSQ_TRY(make_map_2d(&mc, g.C, g.M, g.N, g.ldc, 128 / (int)sizeof(TO), 32, sizeof(TO) == 4));
   static bool configured = false;
   if (!configured) {
     MSQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TO, PAIR, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -331,10 +390,10 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MSQ_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<TO, PAIR, ACT>, ma, mb, ep, num_m, num_n, num_k));
+    MSQ_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<TO, PAIR, ACT>, ma, mb, mc, ep, num_m, num_n, num_k));
   } else {
     const int grid = (int)min((int64_t)sms, tiles);
-    gemm_tc_kernel<TO, PAIR, ACT><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ma, mb, ep, num_m, num_n, num_k);
+    gemm_tc_kernel<TO, PAIR, ACT><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ma, mb, mc, ep, num_m, num_n, num_k);
   }
   MSQ_LAUNCH_CHECK();
   profile_mark(st, true, 2.0 * (double)g.M * (double)g.N * (double)g.K);
