@@ -99,6 +99,15 @@ int msq_beam_search(msq_model* m, const float* sents_dev, const float* key_dev, 
                     const float* cls_mat_dev, const float* score_mat_dev, int64_t B, int32_t N, int32_t beam,
                     int32_t* perm_dev, int32_t* trace_ix_dev, float* trace_cost_dev, float* trace_logp_dev, void* stream);
 
+/* One decode step with the reference's materialised per-beam tensors: BertForOrdering.step
+ * (modeling_bert.py:1368-1402).  prev_y/h/c [Wb,H]; key0 [N,H]; pointed_mask [Wb,N] uint8;
+ * rela_vec [Wb,N,N,H+2] is zeroed IN PLACE where rela_mask == 0 (as the reference does); hist1/hist2 like
+ * rela_vec; rela/l1/l2 masks [Wb,N,N] uint8.  Outputs h,c [Wb,H], logp [Wb,N]. */
+int msq_decode_step(msq_model* m, const float* prev_y_dev, const float* h_dev, const float* c_dev, const float* key0_dev,
+                    const uint8_t* pointed_mask_dev, float* rela_vec_dev, const uint8_t* rela_mask_dev,
+                    const float* hist1_dev, const float* hist2_dev, const uint8_t* l1_mask_dev, const uint8_t* l2_mask_dev,
+                    int32_t Wb, int32_t N, float* h_out_dev, float* c_out_dev, float* logp_out_dev, void* stream);
+
 /* ---- whole path on device-resident inputs: encode + beam search ------------------------------- */
 int msq_order_manuals_dev(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev,
                           const int64_t* sep_dev, int64_t B, int32_t N, int32_t Lt, const float* images_dev,

@@ -113,7 +113,7 @@ struct msq_model {
   msq_config cfg;
   std::unordered_map<std::string, std::pair<float*, int64_t>> raw;
   std::vector<void*> owned;
-  bool packed = false;
+  bool packed = false, has_bert = false, has_vit = false, has_heads = false;
   std::string prefix_inner = "bert.";
   // packed
   const float *word = nullptr, *pos = nullptr, *type = nullptr;
@@ -127,7 +127,8 @@ struct msq_model {
   LNp ln_pre, ln_post, visn_ln;
   std::vector<VitLayerW> vit;
   // berson heads
-  Lin sent_tran, key_lin, xg_lin, t4_lin;
+  Lin sent_tran, key_lin, xg_lin, t4_lin, pwk_raw, wih_raw, whh_raw, wq_raw;
+  int Kp4 = 0;
   const float *w2 = nullptr, *b2 = nullptr, *w_rel = nullptr, *b_rel = nullptr, *w_in2 = nullptr;
   std::vector<ParaLayerW> para;
   LNp para_ln;
@@ -324,7 +325,7 @@ extern "C" int msq_model_create(const msq_config* cfg, msq_model** out) {
   MSQ_REQUIRE(cfg && out, "null argument");
   MSQ_REQUIRE(cfg->hidden % 128 == 0 && cfg->hidden <= 1024, "hidden=%d must be a multiple of 128, <= 1024", cfg->hidden);
   MSQ_REQUIRE(cfg->heads * 64 == cfg->hidden, "head dim must be 64 (hidden=%d heads=%d)", cfg->hidden, cfg->heads);
-  MSQ_REQUIRE(cfg->inter % 16 == 0 && cfg->layers >= 1, "bad inter/layers");
+  MSQ_REQUIRE(cfg->inter % 16 == 0 && cfg->layers >= 0, "bad inter/layers");
   if (cfg->vit_width) {
     MSQ_REQUIRE(cfg->vit_width % 128 == 0 && cfg->vit_width <= 1024, "vit_width=%d unsupported", cfg->vit_width);
     MSQ_REQUIRE(cfg->vit_res % cfg->vit_patch == 0 && cfg->vit_patch % 4 == 0, "vit patch/res");
@@ -367,16 +368,22 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
   // first make sure everything is there (collect all missing names)
   std::vector<std::string> need;
   auto lin_names = [&](const std::string& n) { need.push_back(n + ".weight"); need.push_back(n + ".bias"); };
+  // three weight groups, each optional as a whole: inner BERT stack, CLIP visual tower, BERSON heads
+  m->has_bert = m->raw.count(P + "embeddings.word_embeddings.weight") != 0;
+  m->has_vit = c.vit_width != 0 && m->raw.count(P + "encoder.visual_model.visual.conv1.weight") != 0;
+  m->has_heads = m->raw.count("key_linear.weight") != 0;
+  MSQ_REQUIRE(m->has_bert || m->has_vit || m->has_heads, "no known weights registered");
+  if (m->has_bert)
   for (const char* e : {"embeddings.word_embeddings.weight", "embeddings.position_embeddings.weight",
                         "embeddings.token_type_embeddings.weight", "embeddings.LayerNorm.weight", "embeddings.LayerNorm.bias"})
     need.push_back(P + e);
-  for (int l = 0; l < c.layers; ++l) {
+  for (int l = 0; m->has_bert && l < c.layers; ++l) {
     const std::string b = P + "encoder.layer." + std::to_string(l) + ".";
     for (const char* e : {"attention.self.query", "attention.self.key", "attention.self.value", "attention.output.dense",
                           "attention.output.LayerNorm", "intermediate.dense", "output.dense", "output.LayerNorm"})
       lin_names(b + e);
   }
-  if (c.vit_width) {
+  if (m->has_vit) {
     const std::string v = P + "encoder.visual_model.visual.";
     need.push_back(v + "conv1.weight"); need.push_back(v + "class_embedding"); need.push_back(v + "positional_embedding");
     lin_names(v + "ln_pre"); lin_names(v + "ln_post");
@@ -385,14 +392,15 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
       need.push_back(b + "attn.in_proj_weight"); need.push_back(b + "attn.in_proj_bias");
       for (const char* e : {"attn.out_proj", "ln_1", "mlp.c_fc", "mlp.c_proj", "ln_2"}) lin_names(b + e);
     }
-    lin_names(P + "encoder.visn_fc.visn_fc"); lin_names(P + "encoder.visn_fc.visn_layer_norm");
+    if (m->has_bert) { lin_names(P + "encoder.visn_fc.visn_fc"); lin_names(P + "encoder.visn_fc.visn_layer_norm"); }
   }
-  for (int l = 0; l < c.para_layers; ++l) {
+  for (int l = 0; m->has_heads && l < c.para_layers; ++l) {
     const std::string b = "encoder.transformer_inter." + std::to_string(l) + ".";
     for (const char* e : {"self_attn.linear_keys", "self_attn.linear_values", "self_attn.linear_query", "self_attn.final_linear",
                           "feed_forward.w_1", "feed_forward.w_2", "feed_forward.layer_norm", "layer_norm"})
       lin_names(b + e);
   }
+  if (m->has_heads) {
   lin_names("encoder.layer_norm"); lin_names("key_linear"); lin_names("query_linear"); lin_names("tanh_linear");
   for (const char* e : {"decoder.weight_ih_l0", "decoder.weight_hh_l0", "decoder.bias_ih_l0", "decoder.bias_hh_l0", "pw_k.weight",
                         "two_level_encoder.linear_in_2.weight"})
@@ -401,6 +409,7 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
                         "two_level_encoder.pairwise_relationship", "two_level_encoder.h1_relationship",
                         "two_level_encoder.h2_relationship"})
     lin_names(e);
+  }
   for (auto& n : need)
     if (!m->raw.count(n)) miss += n + " ";
   if (!miss.empty()) {
@@ -409,6 +418,7 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
   }
 
   // ---- embeddings + BERT stack
+  if (m->has_bert) {
   m->word = W(P + "embeddings.word_embeddings.weight", (int64_t)c.vocab * H);
   m->pos = W(P + "embeddings.position_embeddings.weight", (int64_t)c.max_pos * H);
   m->type = W(P + "embeddings.token_type_embeddings.weight", (int64_t)c.type_vocab * H);
@@ -437,8 +447,9 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
     MSQ_TRY(make_lin(m, W(P + "pooler.dense.weight", (int64_t)H * H), W(P + "pooler.dense.bias", H), H, H, H, false, &m->pooler, st));
     m->has_pooler = true;
   }
+  }
   // ---- ViT tower
-  if (c.vit_width) {
+  if (m->has_vit) {
     const int Wd = c.vit_width, g = c.vit_res / c.vit_patch, Kc = 3 * c.vit_patch * c.vit_patch;
     const std::string v = P + "encoder.visual_model.visual.";
     MSQ_TRY(make_lin(m, W(v + "conv1.weight", (int64_t)Wd * Kc), nullptr, Wd, Kc, Kc, w16, &m->conv1, st));
@@ -459,11 +470,14 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
       L.ln1 = {W(b + "ln_1.weight", Wd), W(b + "ln_1.bias", Wd)};
       L.ln2 = {W(b + "ln_2.weight", Wd), W(b + "ln_2.bias", Wd)};
     }
-    MSQ_TRY(make_lin(m, W(P + "encoder.visn_fc.visn_fc.weight", (int64_t)H * Wd), W(P + "encoder.visn_fc.visn_fc.bias", H), H, Wd, Wd,
-                     w16, &m->visn_fc, st));
-    m->visn_ln = {W(P + "encoder.visn_fc.visn_layer_norm.weight", H), W(P + "encoder.visn_fc.visn_layer_norm.bias", H)};
+    if (m->has_bert) {
+      MSQ_TRY(make_lin(m, W(P + "encoder.visn_fc.visn_fc.weight", (int64_t)H * Wd), W(P + "encoder.visn_fc.visn_fc.bias", H), H, Wd, Wd,
+                       w16, &m->visn_fc, st));
+      m->visn_ln = {W(P + "encoder.visn_fc.visn_layer_norm.weight", H), W(P + "encoder.visn_fc.visn_layer_norm.bias", H)};
+    }
   }
   // ---- BERSON heads
+  if (m->has_heads) {
   const std::string T = "two_level_encoder.";
   MSQ_TRY(make_lin(m, W(T + "sentence_tran.weight", (int64_t)H * H), W(T + "sentence_tran.bias", H), H, H, H, w16, &m->sent_tran, st));
   m->w2 = W(T + "sentence_tran_2.weight", H);
@@ -518,6 +532,13 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
     MSQ_CUDA(cudaMemcpyAsync(&bt, W("tanh_linear.bias", 1), sizeof(float), cudaMemcpyDeviceToHost, st));
     MSQ_CUDA(cudaStreamSynchronize(st));
     m->dec.bt = bt;
+    // raw-layout copies for the step-by-step API (msq_decode_step): pw_k padded to a multiple of 16 columns
+    m->Kp4 = (4 * (H + 2) + 15) / 16 * 16;
+    MSQ_TRY(make_lin(m, W("pw_k.weight", (int64_t)H * 4 * (H + 2)), nullptr, H, 4 * (H + 2), m->Kp4, false, &m->pwk_raw, st));
+    MSQ_TRY(make_lin(m, W("decoder.weight_ih_l0", (int64_t)4 * H * H), W("decoder.bias_ih_l0", 4 * H), 4 * H, H, H, false, &m->wih_raw, st));
+    MSQ_TRY(make_lin(m, W("decoder.weight_hh_l0", (int64_t)4 * H * H), W("decoder.bias_hh_l0", 4 * H), 4 * H, H, H, false, &m->whh_raw, st));
+    MSQ_TRY(make_lin(m, W("query_linear.weight", (int64_t)H * H), W("query_linear.bias", H), H, H, H, false, &m->wq_raw, st));
+  }
   }
   if (!miss.empty()) {
     set_error("state_dict incomplete, missing: %.1800s", miss.c_str());
@@ -733,6 +754,8 @@ static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const i
                     int32_t* perm, cudaStream_t st) {
   const msq_config& c = m->cfg;
   MSQ_REQUIRE(m->packed, "msq_model_pack() has not been called");
+  MSQ_REQUIRE(m->has_bert && m->has_heads, "model lacks the inner encoder or the BERSON head weights");
+  MSQ_REQUIRE(c.vit_width == 0 || m->has_vit, "model lacks the visual tower weights");
   MSQ_REQUIRE(N >= 2 && N <= 16, "N=%d out of range [2,16]", N);
   MSQ_REQUIRE(!(c.vit_width != 0 && images == nullptr), "multimodal model needs images");
   const int H = c.hidden, P = N * (N - 1);
@@ -794,7 +817,7 @@ static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const i
 
 extern "C" int msq_vit_forward(msq_model* m, const float* images_dev, int64_t n_img, const int32_t* img_index_dev, int64_t R,
                                float* out_dev, void* stream) {
-  MSQ_REQUIRE(m && m->packed && m->cfg.vit_width, "model has no visual tower / not packed");
+  MSQ_REQUIRE(m && m->packed && m->has_vit, "model has no visual tower / not packed");
   cudaStream_t st = (cudaStream_t)stream;
   const msq_config& c = m->cfg;
   const int g2 = (c.vit_res / c.vit_patch) * (c.vit_res / c.vit_patch), Lv = 1 + 2 * g2;
@@ -817,10 +840,10 @@ extern "C" int msq_vit_forward(msq_model* m, const float* images_dev, int64_t n_
 extern "C" int msq_inner_forward(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev, int64_t R,
                                  int32_t Lt, const float* images_dev, int64_t n_img, const int32_t* img_index_dev, float* lang_dev,
                                  float* visn_dev, float* pooled_dev, void* stream) {
-  MSQ_REQUIRE(m && m->packed, "model not packed");
+  MSQ_REQUIRE(m && m->packed && m->has_bert, "model not packed / no inner encoder weights");
   cudaStream_t st = (cudaStream_t)stream;
   const msq_config& c = m->cfg;
-  const bool mm = c.vit_width != 0 && images_dev != nullptr;
+  const bool mm = m->has_vit && images_dev != nullptr;
   const int g2 = mm ? (c.vit_res / c.vit_patch) * (c.vit_res / c.vit_patch) : 0, Lv = mm ? 1 + 2 * g2 : 0, Lj = Lt + Lv;
   const int H = c.hidden;
   VitBufs vb{}; JointBufs jb{};
@@ -869,7 +892,7 @@ extern "C" int msq_order_manuals_dev(msq_model* m, const int64_t* ids_dev, const
 extern "C" int msq_beam_search(msq_model* m, const float* sents_dev, const float* key_dev, const float* h0_dev,
                                const float* cls_mat_dev, const float* score_mat_dev, int64_t B, int32_t N, int32_t beam,
                                int32_t* perm_dev, int32_t* trace_ix_dev, float* trace_cost_dev, float* trace_logp_dev, void* stream) {
-  MSQ_REQUIRE(m && m->packed, "model not packed");
+  MSQ_REQUIRE(m && m->packed && m->has_heads, "model not packed / no BERSON head weights");
   MSQ_REQUIRE(N >= 2 && N <= 16, "N=%d out of range", N);
   cudaStream_t st = (cudaStream_t)stream;
   const int H = m->cfg.hidden;
@@ -888,6 +911,42 @@ extern "C" int msq_beam_search(msq_model* m, const float* sents_dev, const float
   MSQ_LAUNCH_CHECK();
   return run_decode(m, sents_dev, key_dev, h0_dev, r0, sents_ext, xg, t4, B, N, beam, perm_dev, trace_ix_dev, trace_cost_dev,
                     trace_logp_dev, st);
+}
+
+// BertForOrdering.step with the reference's materialised tensors (modeling_bert.py:1368-1402)
+extern "C" int msq_decode_step(msq_model* m, const float* prev_y_dev, const float* h_dev, const float* c_dev, const float* key0_dev,
+                               const uint8_t* pointed_mask_dev, float* rela_vec_dev, const uint8_t* rela_mask_dev,
+                               const float* hist1_dev, const float* hist2_dev, const uint8_t* l1_mask_dev,
+                               const uint8_t* l2_mask_dev, int32_t Wb, int32_t N, float* h_out_dev, float* c_out_dev,
+                               float* logp_out_dev, void* stream) {
+  MSQ_REQUIRE(m && m->packed && m->has_heads, "model not packed / no BERSON head weights");
+  MSQ_REQUIRE(Wb >= 1 && N >= 2 && N <= 16, "bad Wb/N");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = m->cfg.hidden;
+  float *g1 = nullptr, *g2 = nullptr, *q = nullptr, *pw = nullptr, *keys = nullptr;
+  for (int pass = 0; pass < 2; ++pass) {
+    Planner p{&m->ws, pass == 0};
+    if (pass == 1) m->ws.reset();
+    g1 = p.take<float>((size_t)Wb * 4 * H);
+    g2 = p.take<float>((size_t)Wb * 4 * H);
+    q = p.take<float>((size_t)Wb * H);
+    pw = p.take<float>((size_t)Wb * N * m->Kp4);
+    keys = p.take<float>((size_t)Wb * N * H);
+    if (pass == 0) MSQ_TRY(m->ws.reserve(p.need + 4096, st));
+  }
+  MSQ_TRY(run_gemm32(prev_y_dev, H, m->wih_raw, nullptr, 0, g1, 4 * H, Wb, ACT_NONE, st));
+  MSQ_TRY(run_gemm32(h_dev, H, m->whh_raw, g1, 4 * H, g2, 4 * H, Wb, ACT_NONE, st));
+  MSQ_TRY(decode_step_lstm(g2, c_dev, Wb, H, h_out_dev, c_out_dev, st));
+  MSQ_TRY(run_gemm32(h_out_dev, H, m->wq_raw, nullptr, 0, q, H, Wb, ACT_NONE, st));
+  StepIO io;
+  io.rela = rela_vec_dev; io.rela_mask = rela_mask_dev; io.hist1 = hist1_dev; io.hist2 = hist2_dev; io.l1 = l1_mask_dev;
+  io.l2 = l2_mask_dev; io.Wb = Wb; io.N = N; io.H = H; io.Kp4 = m->Kp4; io.pw = pw;
+  MSQ_TRY(decode_step_parts(io, st));
+  GemmArgs g;
+  g.A = pw; g.W = m->pwk_raw.w32; g.bias = nullptr; g.resid = nullptr; g.C = keys; g.C2 = nullptr;
+  g.M = (int64_t)Wb * N; g.N = H; g.K = m->Kp4; g.lda = m->Kp4; g.ldw = m->Kp4; g.ldc = H; g.ldr = 0; g.act = ACT_NONE;
+  MSQ_TRY((gemm_simt<float, float>(g, st)));
+  return decode_step_score(q, keys, key0_dev, pointed_mask_dev, m->dec.wt, m->dec.bt, Wb, N, H, logp_out_dev, st);
 }
 
 extern "C" int msq_order_manuals_host(msq_model* m, const int64_t* ids_host, const int64_t* tt_host, const int64_t* mask_host,

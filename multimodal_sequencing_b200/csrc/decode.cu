@@ -272,4 +272,102 @@ int beam_search(const DecodeWeights& w, const DecodeIO& io, cudaStream_t st) {
   return launch_beam<16>(w, io, G, st);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Step-by-step API parity: BertForOrdering.step with the reference's MATERIALISED per-beam tensors
+// (models/berson/modeling_bert.py:1368-1402).  Not used by the fused search above; it exists so that the
+// reference's own beam_search_pointer loop can drive the CUDA path one step at a time.
+// ---------------------------------------------------------------------------------------------------
+
+// rela_vec.masked_fill_(rela_mask == 0, 0)   (in place, 1385)
+__global__ void step_zero_rela_kernel(float* __restrict__ rela, const uint8_t* __restrict__ rela_mask, int64_t cells, int D) {
+  const int64_t cell = blockIdx.x;
+  if (cell >= cells || rela_mask[cell]) return;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) rela[cell * D + d] = 0.f;
+}
+
+// pw[b,k,:] = [left1 ; left2 ; forw ; back ; 0-pad]   (1381-1389); one block per (beam, k)
+__global__ void __launch_bounds__(256) step_pw_kernel(const float* __restrict__ rela, const float* __restrict__ hist1,
+                                                      const float* __restrict__ hist2, const uint8_t* __restrict__ l1,
+                                                      const uint8_t* __restrict__ l2, int N, int D, int Kp4, float* __restrict__ pw) {
+  const int b = blockIdx.x / N, k = blockIdx.x % N;
+  float* out = pw + (int64_t)blockIdx.x * Kp4;
+  const int64_t base = (int64_t)b * N * N;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float a1 = 0.f, a2 = 0.f, f = 0.f, g = 0.f;
+    for (int i = 0; i < N; ++i) {
+      const int64_t ik = base + (int64_t)i * N + k, ki = base + (int64_t)k * N + i;
+      if (l1[ik]) a1 += hist1[ik * D + d];
+      if (l2[ik]) a2 += hist2[ik * D + d];
+      f += rela[ki * D + d];   // mean over dim 2 (j) of row k
+      g += rela[ik * D + d];   // mean over dim 1 (i) of column k
+    }
+    out[d] = a1;
+    out[D + d] = a2;
+    out[2 * D + d] = f / (float)N;
+    out[3 * D + d] = g / (float)N;
+  }
+  for (int d = 4 * D + threadIdx.x; d < Kp4; d += blockDim.x) out[d] = 0.f;
+}
+
+// gates [Wb,4H] in torch order (i|f|g|o) -> h', c'
+__global__ void step_lstm_kernel(const float* __restrict__ gates, const float* __restrict__ c_in, int64_t Wb, int H,
+                                 float* __restrict__ h_out, float* __restrict__ c_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Wb * H) return;
+  const int64_t b = i / H;
+  const int u = (int)(i % H);
+  const float* g = gates + b * 4 * H;
+  const float ig = 1.f / (1.f + expf(-g[u])), fg = 1.f / (1.f + expf(-g[H + u]));
+  const float gg = tanhf(g[2 * H + u]), og = 1.f / (1.f + expf(-g[3 * H + u]));
+  const float c2 = fg * c_in[i] + ig * gg;
+  c_out[i] = c2;
+  h_out[i] = og * tanhf(c2);
+}
+
+// e = w_t . tanh(q + keys + key0) + b_t ; masked_fill(pointed, -1e9) ; log_softmax   (1392-1400); block per beam
+__global__ void __launch_bounds__(256) step_score_kernel(const float* __restrict__ q, const float* __restrict__ keys,
+                                                         const float* __restrict__ key0, const uint8_t* __restrict__ pointed,
+                                                         const float* __restrict__ wt, float bt, int N, int H,
+                                                         float* __restrict__ logp) {
+  __shared__ float e[DC_MAXN];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < N; k += blockDim.x >> 5) {
+    float part = 0.f;
+    for (int d = lane; d < H; d += 32)
+      part = fmaf(wt[d], tanhf(q[(int64_t)b * H + d] + keys[((int64_t)b * N + k) * H + d] + key0[(int64_t)k * H + d]), part);
+    part = warp_sum(part);
+    if (lane == 0) e[k] = pointed[(int64_t)b * N + k] ? -1e9f : part + bt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mx = -INFINITY, s = 0.f;
+    for (int k = 0; k < N; ++k) mx = fmaxf(mx, e[k]);
+    for (int k = 0; k < N; ++k) s += expf(e[k] - mx);
+    const float lse = logf(s);
+    for (int k = 0; k < N; ++k) logp[(int64_t)b * N + k] = (e[k] - mx) - lse;
+  }
+}
+
+int decode_step_parts(const StepIO& io, cudaStream_t st) {
+  MSQ_REQUIRE(io.N >= 2 && io.N <= DC_MAXN, "decode_step: N=%d out of range", io.N);
+  const int D = io.H + 2;
+  step_zero_rela_kernel<<<(unsigned)((int64_t)io.Wb * io.N * io.N), 128, 0, st>>>(io.rela, io.rela_mask, (int64_t)io.Wb * io.N * io.N, D);
+  MSQ_LAUNCH_CHECK();
+  step_pw_kernel<<<(unsigned)(io.Wb * io.N), 256, 0, st>>>(io.rela, io.hist1, io.hist2, io.l1, io.l2, io.N, D, io.Kp4, io.pw);
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+int decode_step_lstm(const float* gates, const float* c_in, int64_t Wb, int H, float* h_out, float* c_out, cudaStream_t st) {
+  step_lstm_kernel<<<ceil_div(Wb * H, 256), 256, 0, st>>>(gates, c_in, Wb, H, h_out, c_out);
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+int decode_step_score(const float* q, const float* keys, const float* key0, const uint8_t* pointed, const float* wt, float bt,
+                      int64_t Wb, int N, int H, float* logp, cudaStream_t st) {
+  step_score_kernel<<<(unsigned)Wb, 256, 0, st>>>(q, keys, key0, pointed, wt, bt, N, H, logp);
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+
 }  // namespace msq

@@ -76,5 +76,17 @@ struct DecodeIO {
   float* trace_logp;   // optional [B, N-1, W, N]
 };
 int beam_search(const DecodeWeights& w, const DecodeIO& io, cudaStream_t st);
+struct StepIO {
+  float* rela;                 // [Wb,N,N,H+2] zeroed in place where rela_mask == 0
+  const uint8_t* rela_mask;    // [Wb,N,N]
+  const float *hist1, *hist2;  // [Wb,N,N,H+2]
+  const uint8_t *l1, *l2;      // [Wb,N,N]
+  int Wb, N, H, Kp4;
+  float* pw;                   // [Wb*N, Kp4] out
+};
+int decode_step_parts(const StepIO& io, cudaStream_t st);
+int decode_step_lstm(const float* gates, const float* c_in, int64_t Wb, int H, float* h_out, float* c_out, cudaStream_t st);
+int decode_step_score(const float* q, const float* keys, const float* key0, const uint8_t* pointed, const float* wt, float bt,
+                      int64_t Wb, int N, int H, float* logp, cudaStream_t st);
 
 }  // namespace msq

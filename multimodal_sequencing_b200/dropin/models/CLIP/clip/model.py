@@ -1,0 +1,105 @@
+"""models/CLIP/clip/model.py of the reference, visual-tower surface: CLIP(...).visual(x, skip_last_layer=True)
+(model.py:242-323).  Parameter names match the reference so CLIP checkpoints load unchanged; the forward is
+the pair-joint ViT tower of csrc (patch-embed GEMM, fused token assembly + ln_pre, 12 residual blocks on
+tcgen05 GEMMs / fused attention, ln_post)."""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from multimodal_sequencing_b200.engine import OrderingEngine
+
+
+class LayerNorm(nn.LayerNorm):
+    """model.py:190-196 (fp32 LayerNorm, eps 1e-5): parameter holder."""
+
+
+class QuickGELU(nn.Module):
+    """model.py:199-201; evaluated in the GEMM epilogue on the device path."""
+
+    def forward(self, x):
+        return x * torch.sigmoid(1.702 * x)
+
+
+class ResidualAttentionBlock(nn.Module):
+    """model.py:204-226 (parameter holder: attn.in_proj_*, attn.out_proj, ln_1, mlp.c_fc, mlp.c_proj, ln_2)."""
+
+    def __init__(self, d_model, n_head, attn_mask=None):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(d_model, n_head)
+        self.ln_1 = LayerNorm(d_model)
+        self.mlp = nn.Sequential(OrderedDict([("c_fc", nn.Linear(d_model, d_model * 4)), ("gelu", QuickGELU()),
+                                              ("c_proj", nn.Linear(d_model * 4, d_model))]))
+        self.ln_2 = LayerNorm(d_model)
+
+
+class Transformer(nn.Module):
+    def __init__(self, width, layers, heads, attn_mask=None):
+        super().__init__()
+        self.width, self.layers = width, layers
+        self.resblocks = nn.Sequential(*[ResidualAttentionBlock(width, heads, attn_mask) for _ in range(layers)])
+
+
+class VisualTransformer(nn.Module):
+    """model.py:242-305.  forward(x [R*img_len,3,S,S]) -> [R, 1 + img_len*g*g, width] (skip_last_layer=True)."""
+
+    def __init__(self, input_resolution, patch_size, width, layers, heads, output_dim, img_len=None):
+        super().__init__()
+        self.input_resolution, self.output_dim, self.heads, self.img_len = input_resolution, output_dim, heads, img_len
+        self.patch_size, self.width, self.layers = patch_size, width, layers
+        self.conv1 = nn.Conv2d(3, width, kernel_size=patch_size, stride=patch_size, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.ln_pre = LayerNorm(width)
+        self.transformer = Transformer(width, layers, heads)
+        self.ln_post = LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+
+    def vit_config(self):
+        return dict(embed_dim=self.output_dim, image_resolution=self.input_resolution, vision_layers=self.layers,
+                    vision_width=self.width, vision_patch_size=self.patch_size)
+
+    def _engine(self):
+        sig = tuple(p._version for p in self.parameters())
+        if self.__dict__.get("_eng") is None or self.__dict__.get("_eng_sig") != sig:
+            dev = self.conv1.weight.device
+            if dev.type != "cuda":
+                raise RuntimeError("the B200 path has no CPU fallback: move the model to a CUDA device first")
+            cfg = dict(hidden_size=self.width, num_hidden_layers=0, num_attention_heads=self.width // 64,
+                       intermediate_size=4 * self.width, vocab_size=1, max_position_embeddings=1, vit=self.vit_config())
+            sd = {"bert.encoder.visual_model.visual." + k: v for k, v in self.state_dict().items()}
+            self.__dict__["_eng"] = OrderingEngine(sd, cfg, device=dev, precise=bool(getattr(self, "precise", False)))
+            self.__dict__["_eng_sig"] = sig
+        return self.__dict__["_eng"]
+
+    def forward(self, x, skip_last_layer=False, text_embedding=None, text_mask=None, img_len=None):
+        if not skip_last_layer or text_embedding is not None:
+            # the `x @ proj` tail feeds a visn_fc of the wrong width in the reference and the
+            # vilt-style joint branch is off by default (param.py:243-279): neither is on the scoped path
+            raise NotImplementedError("only the skip_last_layer=True tower (ln_post tokens) is on the ordering path")
+        il = self.img_len or img_len or 2
+        if il != 2:
+            raise NotImplementedError("BERSON feeds image PAIRS (max_subsample_image_length = 2)")
+        R = x.shape[0] // il
+        idx = torch.arange(R * il, dtype=torch.int32, device=x.device)
+        with torch.no_grad():
+            return self._engine().vit_forward(x, idx, R)
+
+
+class CLIP(nn.Module):
+    """model.py:307-367.  Only the visual tower is built: the text tower is dead weight on this path
+    (63.4 M parameters the reference allocates and never runs)."""
+
+    def __init__(self, embed_dim, image_resolution, vision_layers, vision_width, vision_patch_size, context_length,
+                 vocab_size, transformer_width, transformer_heads, transformer_layers, img_len=None, img_only=False):
+        super().__init__()
+        if isinstance(vision_layers, (tuple, list)):
+            raise NotImplementedError("CLIP RN50 / AttentionPool2d tower is a later row of the scope table (SURVEY §8(f).3)")
+        self.context_length, self.img_only = context_length, img_only
+        self.visual = VisualTransformer(image_resolution, vision_patch_size, vision_width, vision_layers, vision_width // 64,
+                                        embed_dim, img_len=img_len)
+
+    @property
+    def dtype(self):
+        return self.visual.conv1.weight.dtype

@@ -1,0 +1,100 @@
+"""models/CLIP/src/lxrt/modeling.py of the reference, BERSON surface: BertConfig (147-232) and LXRTModel
+(1456-1598) in CLIP / visualbert-style mode.  Same constructor kwargs, forward signature and state_dict
+keys; the forward is msq_inner_forward (ViT pair tower -> visn_fc -> joint BERT)."""
+import torch
+import torch.nn as nn
+
+from multimodal_sequencing_b200.engine import OrderingEngine
+from models.berson.modeling_bert import _bert_layer, _holder, _init_bert_weights
+from models.CLIP.clip.model import CLIP
+
+CLIP_CONFIGS = {
+    # clip.load("ViT-B/32") geometry (models/CLIP/clip/model.py:471-508 rebuilds it from the checkpoint)
+    "ViT-B/32": dict(embed_dim=512, image_resolution=224, vision_layers=12, vision_width=768, vision_patch_size=32),
+}
+
+
+class BertConfig(object):
+    """lxrt/modeling.py:147-210."""
+
+    def __init__(self, vocab_size_or_config_json_file, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                 intermediate_size=3072, hidden_act="gelu", hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1,
+                 max_position_embeddings=512, type_vocab_size=2, initializer_range=0.02):
+        self.vocab_size = vocab_size_or_config_json_file
+        self.hidden_size, self.num_hidden_layers, self.num_attention_heads = hidden_size, num_hidden_layers, num_attention_heads
+        self.hidden_act, self.intermediate_size = hidden_act, intermediate_size
+        self.hidden_dropout_prob, self.attention_probs_dropout_prob = hidden_dropout_prob, attention_probs_dropout_prob
+        self.max_position_embeddings, self.type_vocab_size, self.initializer_range = max_position_embeddings, type_vocab_size, initializer_range
+
+
+class LXRTModel(nn.Module):
+    """lxrt/modeling.py:1456-1598.  kwargs as the reference: multimodal_text_part, multimodal_img_part, cls_id,
+    sep_id, max_story_length, hl_include_objectives, mlm_ignore_index, clip_model_name, num_labels
+    (+ clip_config=dict(...) to override the tower geometry, e.g. for small test models)."""
+
+    def __init__(self, config, **kwargs):
+        super().__init__()
+        self.config = config
+        if kwargs.get("multimodal_text_part") or kwargs.get("multimodal_img_part"):
+            raise NotImplementedError("text-only / image-only LXRT parts are outside the scoped path")
+        if kwargs.get("num_labels") is not None:
+            raise NotImplementedError("topo-sort classifier mode is a later row of the scope table (SURVEY §8(f).4)")
+        name = kwargs.get("clip_model_name", "ViT-B/32")
+        vit = kwargs.get("clip_config") or CLIP_CONFIGS.get(name)
+        if vit is None:
+            raise NotImplementedError("visual backbone %r: only the ViT tower is built (RN50 is SURVEY §8(f).3)" % name)
+        self.vit_config = dict(vit)
+        self.cls_id, self.sep_id = kwargs.get("cls_id"), kwargs.get("sep_id")
+        H = config.hidden_size
+        self.embeddings = _holder(word_embeddings=nn.Embedding(config.vocab_size, H, padding_idx=0),
+                                  position_embeddings=nn.Embedding(config.max_position_embeddings, H, padding_idx=0),
+                                  token_type_embeddings=nn.Embedding(config.type_vocab_size, H, padding_idx=0),
+                                  LayerNorm=nn.LayerNorm(H, eps=1e-12))
+        enc = _holder(layer=nn.ModuleList([_bert_layer(H, config.intermediate_size, 1e-12) for _ in range(config.num_hidden_layers)]),
+                      visn_fc=_holder(visn_fc=nn.Linear(vit["vision_width"], H), visn_layer_norm=nn.LayerNorm(H, eps=1e-12),
+                                      box_fc=nn.Linear(4, H), box_layer_norm=nn.LayerNorm(H, eps=1e-12)),
+                      visual_model=CLIP(vit["embed_dim"], vit["image_resolution"], vit["vision_layers"], vit["vision_width"],
+                                        vit["vision_patch_size"], 77, 49408, 512, 8, 12,
+                                        img_len=2, img_only=True))
+        # RN-only embeddings the reference allocates regardless of the backbone (lxrt/modeling.py:828-831, 621-705);
+        # never read on the ViT path ("RN" guard, 1014) but present in its checkpoints
+        F = vit["vision_width"]
+        enc.visual_pos = _holder(x_position_embedding=nn.Embedding(25, F), y_position_embedding=nn.Embedding(25, F))
+        enc.visual_token_type = _holder(token_type_embedding=nn.Embedding(5, F))
+        enc.skip_last_layer = True  # oracle decision for the ViT tower
+        self.encoder = enc
+        self.pooler = _holder(dense=nn.Linear(H, H))
+        self.apply(lambda m: _init_bert_weights(m, config.initializer_range))  # 1464: re-initialises the tower's Linears too
+
+    def _engine(self):
+        sig = tuple(p._version for p in self.parameters())
+        if self.__dict__.get("_eng") is None or self.__dict__.get("_eng_sig") != sig:
+            dev = self.pooler.dense.weight.device
+            if dev.type != "cuda":
+                raise RuntimeError("the B200 path has no CPU fallback: move the model to a CUDA device first")
+            c = self.config
+            cfg = dict(hidden_size=c.hidden_size, num_hidden_layers=c.num_hidden_layers, num_attention_heads=c.num_attention_heads,
+                       intermediate_size=c.intermediate_size, vocab_size=c.vocab_size,
+                       max_position_embeddings=c.max_position_embeddings, type_vocab_size=c.type_vocab_size, vit=self.vit_config)
+            sd = {"bert." + k: v for k, v in self.state_dict().items()}
+            self.__dict__["_eng"] = OrderingEngine(sd, cfg, device=dev, precise=bool(getattr(self, "precise", False)))
+            self.__dict__["_eng_sig"] = sig
+        return self.__dict__["_eng"]
+
+    def forward(self, input_ids, token_type_ids=None, attention_mask=None, visual_feats=None, visual_attention_mask=None,
+                pretraining_objective=None, labels=None):
+        if pretraining_objective is not None or visual_attention_mask is not None:
+            raise NotImplementedError("pre-training objectives are outside the scoped path (SURVEY §2 row 18)")
+        if attention_mask is None:
+            attention_mask = torch.ones_like(input_ids)
+        if token_type_ids is None:
+            token_type_ids = torch.zeros_like(input_ids)
+        R = input_ids.shape[0]
+        idx = None
+        if visual_feats is not None:
+            assert visual_feats.shape[0] == 2 * R, "BERSON mode feeds two images per pair row"
+            idx = torch.arange(2 * R, dtype=torch.int32, device=visual_feats.device)
+        with torch.no_grad():
+            lang, visn, pooled = self._engine().inner_forward(input_ids, token_type_ids, attention_mask, visual_feats, idx,
+                                                              want_pooled=True)
+        return (lang, visn), pooled

@@ -1,0 +1,271 @@
+"""models/berson/modeling_bert.py of the reference, hot-path surface only: BertConfig, BertModel,
+HierarchicalAttention (parameter holder), BertForOrdering, berson_pointer_network, beam_search_pointer.
+
+Same constructors, forward signatures and state_dict keys; the arithmetic runs in
+libmsq_b200.so through multimodal_sequencing_b200.OrderingEngine.  Reference lines are cited per method.
+Training (`forward` -> loss, modeling_bert.py:943-1237) is a later row of the scope table and raises."""
+import types
+
+import torch
+import torch.nn as nn
+
+from multimodal_sequencing_b200.engine import OrderingEngine, PairBatch
+from .process_inputs_for_berson import prepare_berson_inputs
+from .generator import Beam
+
+
+class BertConfig(object):
+    """models/berson/configuration_bert.py:46-112 (the attributes the path reads)."""
+
+    def __init__(self, vocab_size_or_config_json_file=30522, hidden_size=768, num_hidden_layers=12,
+                 num_attention_heads=12, intermediate_size=3072, hidden_act="gelu", hidden_dropout_prob=0.1,
+                 attention_probs_dropout_prob=0.1, max_position_embeddings=512, type_vocab_size=2,
+                 initializer_range=0.02, layer_norm_eps=1e-12, **kwargs):
+        self.vocab_size = vocab_size_or_config_json_file
+        self.hidden_size = hidden_size
+        self.num_hidden_layers = num_hidden_layers
+        self.num_attention_heads = num_attention_heads
+        self.intermediate_size = intermediate_size
+        self.hidden_act = hidden_act
+        self.hidden_dropout_prob = hidden_dropout_prob
+        self.attention_probs_dropout_prob = attention_probs_dropout_prob
+        self.max_position_embeddings = max_position_embeddings
+        self.type_vocab_size = type_vocab_size
+        self.initializer_range = initializer_range
+        self.layer_norm_eps = layer_norm_eps
+        self.num_labels = kwargs.pop("num_labels", 2)
+        self.wrapper_model_with_heatmap = kwargs.pop("wrapper_model_with_heatmap", False)
+        self.v_feature_size = kwargs.pop("v_feature_size", 1024)
+        self.output_attentions = False
+        self.output_hidden_states = False
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+
+def _holder(**mods):
+    m = nn.Module()
+    for k, v in mods.items():
+        m.add_module(k, v)
+    return m
+
+
+def _bert_layer(H, inter, eps):
+    """parameter names of BertLayer (modeling_bert.py:324-337)."""
+    return _holder(
+        attention=_holder(self=_holder(query=nn.Linear(H, H), key=nn.Linear(H, H), value=nn.Linear(H, H)),
+                          output=_holder(dense=nn.Linear(H, H), LayerNorm=nn.LayerNorm(H, eps=eps))),
+        intermediate=_holder(dense=nn.Linear(H, inter)),
+        output=_holder(dense=nn.Linear(inter, H), LayerNorm=nn.LayerNorm(H, eps=eps)))
+
+
+def _init_bert_weights(module, std):
+    """BertPreTrainedModel._init_weights (modeling_bert.py:464-474)."""
+    if isinstance(module, (nn.Linear, nn.Embedding)):
+        module.weight.data.normal_(mean=0.0, std=std)
+    elif isinstance(module, nn.LayerNorm):
+        module.bias.data.zero_()
+        module.weight.data.fill_(1.0)
+    if isinstance(module, nn.Linear) and module.bias is not None:
+        module.bias.data.zero_()
+
+
+class _EngineOwner:
+    """Lazily (re)builds the packed device model whenever a parameter changed (version counters)."""
+
+    def _engine_config(self):
+        raise NotImplementedError
+
+    def _engine_state(self):
+        return self.state_dict()
+
+    def engine(self):
+        sig = tuple(p._version for p in self.parameters()) + (tuple(id(p) for p in self.parameters()),)
+        eng = self.__dict__.get("_eng")
+        if eng is None or self.__dict__.get("_eng_sig") != sig:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("the B200 path has no CPU fallback: move the model to a CUDA device first")
+            eng = OrderingEngine(self._engine_state(), self._engine_config(), device=dev,
+                                 precise=bool(getattr(self, "precise", False)))
+            self.__dict__["_eng"], self.__dict__["_eng_sig"] = eng, sig
+        return eng
+
+
+class BertModel(nn.Module, _EngineOwner):
+    """Text-only inner encoder (modeling_bert.py:563-663): forward -> (sequence_output, sequence_output[:, 0])."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        H = config.hidden_size
+        self.embeddings = _holder(word_embeddings=nn.Embedding(config.vocab_size, H, padding_idx=0),
+                                  position_embeddings=nn.Embedding(config.max_position_embeddings, H),
+                                  token_type_embeddings=nn.Embedding(config.type_vocab_size, H),
+                                  LayerNorm=nn.LayerNorm(H, eps=config.layer_norm_eps))
+        self.encoder = _holder(layer=nn.ModuleList(
+            [_bert_layer(H, config.intermediate_size, config.layer_norm_eps) for _ in range(config.num_hidden_layers)]))
+        self.apply(lambda m: _init_bert_weights(m, config.initializer_range))
+
+    def _engine_config(self):
+        c = self.config
+        return dict(hidden_size=c.hidden_size, num_hidden_layers=c.num_hidden_layers,
+                    num_attention_heads=c.num_attention_heads, intermediate_size=c.intermediate_size,
+                    vocab_size=c.vocab_size, max_position_embeddings=c.max_position_embeddings,
+                    type_vocab_size=c.type_vocab_size, vit=None)
+
+    def _engine_state(self):
+        return {"bert." + k: v for k, v in self.state_dict().items()}
+
+    def forward(self, input_ids, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None):
+        if position_ids is not None or head_mask is not None:
+            raise NotImplementedError("position_ids / head_mask are not used on the ordering path")
+        if attention_mask is None:
+            attention_mask = torch.ones_like(input_ids)
+        if token_type_ids is None:
+            token_type_ids = torch.zeros_like(input_ids)
+        with torch.no_grad():
+            seq, _, _ = self.engine().inner_forward(input_ids, token_type_ids, attention_mask)
+        return seq, seq[:, 0]
+
+
+class HierarchicalAttention(nn.Module):
+    """Parameter holder with the reference's names (modeling_bert.py:666-684); the pooling itself is
+    csrc/pooling.cu, reached through BertForOrdering.encode."""
+
+    def __init__(self, config, args=None):
+        super().__init__()
+        H = config.hidden_size
+        self.linear_in_2 = nn.Linear(H, 1, bias=False)
+        self.sentence_tran = nn.Linear(H, H)
+        self.sentence_tran_2 = nn.Linear(H, 1)
+        self.pairwise_relationship = nn.Linear(H, 2)
+        self.h1_relationship = nn.Linear(H, 2)
+        self.h2_relationship = nn.Linear(H, 2)
+        self.args = args
+
+
+class _ParaLayer(nn.Module):
+    def __init__(self, H, ff):
+        super().__init__()
+        self.self_attn = _holder(linear_keys=nn.Linear(H, H), linear_values=nn.Linear(H, H), linear_query=nn.Linear(H, H),
+                                 final_linear=nn.Linear(H, H))
+        self.feed_forward = _holder(w_1=nn.Linear(H, ff), w_2=nn.Linear(ff, H), layer_norm=nn.LayerNorm(H, eps=1e-6))
+        self.layer_norm = nn.LayerNorm(H, eps=1e-6)
+
+
+class TransformerInterEncoder(nn.Module):
+    """Parameter holder of models/berson/encoder.py:32-44."""
+
+    def __init__(self, d_model, d_ff, heads, dropout, num_inter_layers=0):
+        super().__init__()
+        self.d_model, self.heads, self.d_ff, self.num_inter_layers = d_model, heads, d_ff, num_inter_layers
+        self.transformer_inter = nn.ModuleList([_ParaLayer(d_model, d_ff) for _ in range(num_inter_layers)])
+        self.layer_norm = nn.LayerNorm(d_model, eps=1e-6)
+
+
+class BertForOrdering(nn.Module, _EngineOwner):
+    """models/berson/modeling_bert.py:825-1402."""
+
+    def __init__(self, config, args, inner_model=None, tokenizer=None, load_inner_model=False, **kwargs):
+        super().__init__()
+        if tokenizer is None:
+            self.bert = BertModel(config)
+        else:
+            self.bert = inner_model if load_inner_model else BertModel(config)
+            self.tokenizer = tokenizer
+        self.config, self.args = config, args
+        if getattr(config, "wrapper_model_with_heatmap", False):
+            raise NotImplementedError("heat-map head (models/heatmap_module.py) is missing from the reference too")
+        H = config.hidden_size
+        self.num_labels, self.hidden_size = config.num_labels, H
+        self.classifier = nn.Linear(H, config.num_labels)
+        self.encoder = TransformerInterEncoder(H, args.ff_size, args.heads, args.para_dropout, args.inter_layers)
+        self.key_linear = nn.Linear(H * 2, H)
+        self.query_linear = nn.Linear(H, H)
+        self.tanh_linear = nn.Linear(H, 1)
+        self.decoder = nn.LSTM(H, H, batch_first=True)
+        self.two_level_encoder = HierarchicalAttention(config, args=args)
+        self.pairwise_loss_lam = args.pairwise_loss_lam
+        if getattr(args, "multimodal_loss", False):
+            raise NotImplementedError("multimodal_loss objective is outside the scoped path (SURVEY §2 row 18)")
+        self.pw_k = nn.Linear((H + 2) * 4, H, False)
+        for name, mod in self.named_modules():      # init_weights() (913): heads only, the inner model keeps its own
+            if not name.startswith("bert"):
+                _init_bert_weights(mod, config.initializer_range)
+
+    # ---- engine plumbing ---------------------------------------------------------------------
+    def _engine_config(self):
+        c = self.config
+        inner = self.bert
+        vit = getattr(inner, "vit_config", None)
+        ic = getattr(inner, "config", c)
+        return dict(hidden_size=c.hidden_size, num_hidden_layers=ic.num_hidden_layers,
+                    num_attention_heads=ic.num_attention_heads, intermediate_size=ic.intermediate_size,
+                    vocab_size=ic.vocab_size, max_position_embeddings=ic.max_position_embeddings,
+                    type_vocab_size=getattr(ic, "type_vocab_size", 2), vit=vit, para_heads=self.args.heads,
+                    para_ff=self.args.ff_size, para_layers=self.args.inter_layers)
+
+    def equip(self, critic):
+        self.critic = critic
+
+    def rela_encode(self, cls_output_matrix_nn, cls_score_matrix_nn):
+        """modeling_bert.py:919-925 (tiny glue, kept as the reference writes it)."""
+        return torch.cat((cls_output_matrix_nn, torch.softmax(cls_score_matrix_nn, -1)), -1)
+
+    def history_encode(self, cls_output_matrix_nn, cls_score_matrix_nn_his1, cls_score_matrix_nn_his2):
+        """modeling_bert.py:927-935."""
+        return (torch.cat((cls_output_matrix_nn, torch.softmax(cls_score_matrix_nn_his1, -1)), -1),
+                torch.cat((cls_output_matrix_nn, torch.softmax(cls_score_matrix_nn_his2, -1)), -1))
+
+    def forward(self, inputs):
+        raise NotImplementedError("teacher-forced training loss (modeling_bert.py:943-1237) is a later row of the "
+                                  "scope table (SURVEY.md §8(f).2); this build covers evaluation / inference")
+
+    # ---- encode ------------------------------------------------------------------------------
+    def encode(self, input_ids, attention_mask=None, token_type_ids=None, pairs_list=None, passage_length=None,
+               pairs_num=None, sep_positions=None, ground_truth=None, mask_cls=None, pairwise_labels=None, cuda=None,
+               head_mask=None, images=None, _pair_batch=None):
+        """modeling_bert.py:1239-1366 -> the same 10-tuple."""
+        B, P, Lt = input_ids.shape
+        N = int(passage_length[0])
+        if _pair_batch is not None:
+            pb = _pair_batch
+        else:
+            img = idx = None
+            if images is not None:   # materialised [B,P,2,3,S,S] as the reference passes it
+                img = images.reshape(B * P * 2, *images.shape[3:])
+                idx = torch.arange(B * P * 2, dtype=torch.int32).reshape(B, P, 2)
+            pb = PairBatch(input_ids, attention_mask, token_type_ids, sep_positions, pairs_list, pairwise_labels,
+                           ground_truth, N, img, idx)
+        with torch.no_grad():
+            e = self.engine().encode(pb)
+        hcn = (e["h0"].unsqueeze(0), e["c0"].unsqueeze(0))
+        return (e["sents"], e["para"], hcn, e["key"], e["cls"], e["cls_mat"], e["cls_score"], e["score_mat"], e["his1"],
+                e["his2"])
+
+    # ---- one decode step ---------------------------------------------------------------------
+    def step(self, prev_y, prev_handc, original_keys, mask, rela_vec, rela_mask, hist_left1, hist_left2, l1_mask, l2_mask):
+        """modeling_bert.py:1368-1402 (rela_vec is zeroed in place, as there)."""
+        with torch.no_grad():
+            return self.engine().decode_step(prev_y, prev_handc, original_keys, mask, rela_vec, rela_mask, hist_left1,
+                                             hist_left2, l1_mask, l2_mask)
+
+
+def berson_pointer_network(args, model, tokenizer, inputs):
+    """modeling_bert.py:1405-1408."""
+    berson_inputs = prepare_berson_inputs(inputs, tokenizer, args=args)
+    return beam_search_pointer(args, model, **berson_inputs)
+
+
+def beam_search_pointer(args, model, input_ids, attention_mask=None, token_type_ids=None, pairs_list=None,
+                        passage_length=None, pairs_num=None, sep_positions=None, ground_truth=None, mask_cls=None,
+                        pairwise_labels=None, cuda=None, head_mask=None, images=None, _pair_batch=None):
+    """modeling_bert.py:1411-1552: encode + beam search, fused on the device.  One manual -> list[int] like the
+    reference; a batch of manuals -> list of lists (batched beam search is a new capability)."""
+    (sents, _, hcn, key, _, cls_mat, _, score_mat, _, _) = model.encode(
+        input_ids, attention_mask, token_type_ids, pairs_list, passage_length, pairs_num, sep_positions, ground_truth,
+        mask_cls, pairwise_labels, cuda, head_mask, images=images, _pair_batch=_pair_batch)
+    N = int(passage_length[0])
+    enc = dict(sents=sents, key=key, h0=hcn[0], cls_mat=cls_mat, score_mat=score_mat)
+    perm = model.engine().beam_search(enc, N, args.beam_size).cpu().tolist()
+    return perm[0] if len(perm) == 1 else perm

@@ -244,6 +244,28 @@ class OrderingEngine:
                                             self._p(tr["logp"] if tr else None), self._stream()))
         return (perm, tr) if trace else perm
 
+    def decode_step(self, prev_y, prev_handc, original_keys, mask, rela_vec, rela_mask, hist_left1, hist_left2,
+                    l1_mask, l2_mask):
+        """BertForOrdering.step (modeling_bert.py:1368-1402) with the reference's materialised tensors.
+        rela_vec is zeroed IN PLACE where rela_mask == 0, exactly as the reference does."""
+        dev, H = self.device, self.H
+        f = lambda t: t.to(dev, torch.float32).contiguous()
+        u8 = lambda t: (t != 0).to(dev, torch.uint8).contiguous()
+        Wb, N = mask.shape
+        x = f(prev_y).reshape(Wb, H)
+        h, c = f(prev_handc[0]).reshape(Wb, H), f(prev_handc[1]).reshape(Wb, H)
+        key0 = f(original_keys).reshape(N, H)
+        if not (rela_vec.is_cuda and rela_vec.dtype == torch.float32 and rela_vec.is_contiguous()):
+            raise ValueError("rela_vec must be a contiguous fp32 CUDA tensor (it is updated in place)")
+        h1, h2 = f(hist_left1), f(hist_left2)
+        pm, rm, m1, m2 = u8(mask), u8(rela_mask), u8(l1_mask), u8(l2_mask)
+        ho, co = torch.empty(1, Wb, H, device=dev), torch.empty(1, Wb, H, device=dev)
+        logp = torch.empty(Wb, N, device=dev)
+        _lib.check(self.lib.msq_decode_step(self._h, self._p(x), self._p(h), self._p(c), self._p(key0), self._p(pm),
+                                            self._p(rela_vec), self._p(rm), self._p(h1), self._p(h2), self._p(m1),
+                                            self._p(m2), Wb, N, self._p(ho), self._p(co), self._p(logp), self._stream()))
+        return ho, co, logp
+
     def order_device(self, batch: PairBatch, beam):
         """encode + beam search on device-resident inputs; returns perm [B,N] int32 (device, async)."""
         b = batch

@@ -1,0 +1,177 @@
+"""The drop-in mirror of the reference's module interface (multimodal_sequencing_b200/dropin): same import
+paths, constructors, state_dict keys (CPU checks) and — on the GPU — the reference's own call sequence
+(berson_pointer_network, and beam_search_pointer's step-by-step loop through model.step + Beam) reproducing
+the reference-generated fixtures."""
+import os
+import types
+
+import pytest
+import torch
+
+from multimodal_sequencing_b200 import dropin
+
+dropin.install()
+from models.beam import Beam  # noqa: E402
+from models.berson import BertConfig, BertForOrdering, beam_search_pointer  # noqa: E402
+from models.berson.modeling_bert import berson_pointer_network  # noqa: E402
+from models.CLIP.src.lxrt.modeling import BertConfig as LxrtBertConfig  # noqa: E402
+from models.CLIP.src.lxrt.modeling import LXRTModel  # noqa: E402
+from oracle import berson_oracle as O  # noqa: E402
+
+torch.set_grad_enabled(False)
+
+
+class Tok:
+    cls_token, sep_token, pad_token = "[CLS]", "[SEP]", "[PAD]"
+
+    def convert_tokens_to_ids(self, t):
+        return {"[CLS]": 101, "[SEP]": 102, "[PAD]": 0}[t]
+
+
+def _args(N, W, ff, device="cpu", mm=False):
+    return types.SimpleNamespace(ff_size=ff, heads=8, para_dropout=0.1, inter_layers=2, beam_size=W, pairwise_loss_lam=0.6,
+                                 multimodal_loss=False, additional_wrapper_level_objectives=None, device=device,
+                                 multimodal=mm, use_multimodal_model=False, multimodal_model_type="clip" if mm else None,
+                                 multimodal_img_part=False, per_seq_max_length=64, max_story_length=N)
+
+
+def _build(g, N, W, device="cpu"):
+    c = g["cfg"]
+    cfg = BertConfig(c["vocab_size_or_config_json_file"], hidden_size=c["hidden_size"], num_hidden_layers=c["num_hidden_layers"],
+                     num_attention_heads=c["num_attention_heads"], intermediate_size=c["intermediate_size"],
+                     max_position_embeddings=c["max_position_embeddings"])
+    mm = g.get("vit") is not None
+    args = _args(N, W, g["ff_size"], device, mm)
+    if mm:
+        inner = LXRTModel(LxrtBertConfig(c["vocab_size_or_config_json_file"], hidden_size=c["hidden_size"],
+                                         num_hidden_layers=c["num_hidden_layers"], num_attention_heads=c["num_attention_heads"],
+                                         intermediate_size=c["intermediate_size"],
+                                         max_position_embeddings=c["max_position_embeddings"]),
+                          clip_model_name="ViT-B/32", clip_config=g["vit"], cls_id=101, sep_id=102, max_story_length=N)
+        model = BertForOrdering(cfg, args, tokenizer=Tok())
+        model.bert = inner
+    else:
+        model = BertForOrdering(cfg, args, tokenizer=None)
+    return model, args
+
+
+@pytest.mark.parametrize("name", ["text_tiny.pt", "mm_tiny.pt"])
+def test_state_dict_keys_match_reference(golden_dir, name):
+    g = torch.load(os.path.join(golden_dir, name), weights_only=False)
+    model, _ = _build(g, 5, 4)
+    missing, unexpected = model.load_state_dict(g["sd"], strict=False)
+    assert not unexpected, unexpected
+    assert all("proj" in k or "box_" in k for k in missing), missing  # tensors make_golden did not need to save
+    for k, v in g["sd"].items():
+        assert model.state_dict()[k].shape == v.shape, k
+
+
+def test_beam_matches_generator_semantics():
+    prev = Beam(4)
+    prev.candidates, prev.scores = [[]], [0]
+    done, remain = Beam(4).step(torch.tensor([[0.3, 0.1, 0.2]]), prev, lambda c: len(c) == 2)
+    assert done == [] and remain == [0, 0, 0]
+
+
+def test_training_forward_is_declared_out_of_scope(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "text_tiny.pt"), weights_only=False)
+    model, _ = _build(g, 5, 4)
+    with pytest.raises(NotImplementedError):
+        model({"input_ids": None})
+
+
+def _reference_style_search(args, model, berson_inputs):
+    """beam_search_pointer's loop exactly as the reference writes it (modeling_bert.py:1429-1552), driving
+    OUR model.encode / model.step / Beam one step at a time."""
+    bi = {k: v for k, v in berson_inputs.items() if k not in ("cuda", "_pair_batch")}
+    (sentences, _, dec_init, original_keys, _, cls_mat, _, score_mat, _, _) = model.encode(**bi)
+    num_sen = int(bi["passage_length"][0])
+    sentences, original_keys = sentences[:, :num_sen, :], original_keys[:, :num_sen, :]
+    document = sentences.squeeze(0)
+    T, H = document.size()
+    dev = document.device
+    rela_vec = model.rela_encode(cls_mat, score_mat).contiguous()
+    hist_left1, hist_left2 = model.history_encode(cls_mat, score_mat, score_mat)
+    eye_zeros = (1 - torch.eye(T, device=dev)).byte()
+    W = args.beam_size
+    prev_beam = Beam(W)
+    prev_beam.candidates, prev_beam.scores = [[]], [0]
+    target_t, valid_size, hyp_list, logps = T - 1, W, [], []
+    f_done = lambda x: len(x) == target_t
+    for t in range(target_t):
+        candidates = prev_beam.candidates
+        if t == 0:
+            dec_input = sentences.new_zeros(1, 1, H)
+            pointed_mask = sentences.new_zeros(1, T).byte()
+            rela_mask = eye_zeros.unsqueeze(0).clone()
+            l1_mask, l2_mask = torch.zeros_like(rela_mask), torch.zeros_like(rela_mask)
+        else:
+            index = torch.tensor([c[-1] for c in candidates], device=dev)
+            dec_input = document[index].unsqueeze(1)
+            ar = torch.arange(index.size(0), device=dev)
+            pointed_mask[ar, index] = 1
+            rela_mask[ar, :, index] = 0
+            rela_mask[ar, index] = 0
+            l1_mask, l2_mask = torch.zeros_like(rela_mask), torch.zeros_like(rela_mask)
+            l1_mask[ar, index, :] = 1
+            if t > 1:
+                l2_mask[ar, torch.tensor([c[-2] for c in candidates], device=dev), :] = 1
+        dec_h, dec_c, log_prob = model.step(dec_input, dec_init, original_keys, pointed_mask, rela_vec, rela_mask,
+                                            hist_left1, hist_left2, l1_mask, l2_mask)
+        logps.append(log_prob.cpu())
+        next_beam = Beam(valid_size)
+        done_list, remain_list = next_beam.step(-log_prob, prev_beam, f_done)
+        hyp_list.extend(done_list)
+        valid_size -= len(done_list)
+        if valid_size == 0:
+            break
+        ix = torch.tensor(remain_list, device=dev)
+        dec_init = (dec_h.index_select(1, ix), dec_c.index_select(1, ix))
+        pointed_mask, rela_mask = pointed_mask.index_select(0, ix), rela_mask.index_select(0, ix)
+        rela_vec = rela_vec.index_select(0, ix).contiguous()
+        hist_left1, hist_left2 = hist_left1.index_select(0, ix), hist_left2.index_select(0, ix)
+        prev_beam = next_beam
+    best = sorted(hyp_list, key=lambda h: h[1])[0][0]
+    best = best + [sorted(set(range(T)) - set(best))[0]]
+    return best, logps
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["text_tiny.pt", "mm_tiny.pt"])
+def test_dropin_reproduces_reference_fixtures(golden_dir, name):
+    g = torch.load(os.path.join(golden_dir, name), weights_only=False)
+    mm = g.get("vit") is not None
+    for c in g["cases"]:
+        model, args = _build(g, c["N"], c["W"], "cuda")
+        model.load_state_dict(g["sd"], strict=False)
+        model = model.cuda().eval()
+        for mod in model.modules():   # fp32 parity mode for every engine owner (wrapper, inner model, tower)
+            mod.precise = True
+        images = None
+        if mm:
+            _, _, images = O.synthetic_manuals(1, c["N"], c["L"], vocab=1000, image_px=224, seed=c["seed"])
+        inputs = {"input_ids": c["ids"], "attention_mask": torch.ones_like(c["ids"]), "labels": c["labels"]}
+        if mm:
+            inputs["images"] = images
+        # (1) the reference's top-level call
+        assert berson_pointer_network(args, model, Tok(), dict(inputs)) == c["perm"]
+        # (2) the reference's own step-by-step loop through model.step + Beam
+        from models.berson.process_inputs_for_berson import prepare_berson_inputs
+        best, logps = _reference_style_search(args, model, prepare_berson_inputs(dict(inputs), Tok(), args=args))
+        assert best == c["perm"]
+        for lp, s in zip(logps, c["steps"]):
+            live = s["logp"] > -1e8
+            assert (lp[live] - s["logp"][live]).abs().max() < 4e-5
+        # (3) inner model stand-alone, same signature as LXRTModel.forward / BertModel.forward
+        pb = prepare_berson_inputs(dict(inputs), Tok(), args=args)
+        B, P, Lt = pb["input_ids"].shape
+        ids2, tt2, am2 = (pb[k].reshape(B * P, Lt) for k in ("input_ids", "token_type_ids", "attention_mask"))
+        if mm:
+            im = pb["images"].reshape(B * P * 2, 3, 224, 224)
+            (lang, visn), pooled = model.bert(ids2, token_type_ids=tt2, attention_mask=am2, visual_feats=im)
+            assert (lang[:3].cpu() - c["lang"]).abs().max() < 4e-5 and (pooled.cpu() - c["pooled"]).abs().max() < 4e-5
+            tower = model.bert.encoder.visual_model.visual(im[:6], skip_last_layer=True, img_len=2)
+            assert (tower.cpu() - c["tower"]).abs().max() < 4e-5
+        else:
+            seq, pooled = model.bert(ids2, attention_mask=am2, token_type_ids=tt2)
+            assert (pooled.cpu() - c["enc"]["cls"]).abs().max() < 4e-5
