@@ -93,10 +93,11 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attention_simt_kernel(const T* 
 
 
 // ---------------------------------------------------------------------------------------------------
-// tcgen05 version (bf16): one CTA per (token group, head), 128 threads.
+// tcgen05 version (bf16): one CTA per (token group, head), 256 threads (two per query row).
 //   TMA loads Q (<= 2 tiles of 128 rows), K and V ([KP keys] x 64, 128B swizzle) straight out of the
 //   packed qkv activation; S = Q K^T is ONE tcgen05.mma chain (M=128, N=KP, K=64) into TMEM; each
-//   thread owns one query row (TMEM lane): two passes over its S row (max, then exp2 / sum), P is written
+//   pair of threads owns one query row (TMEM lane), half the keys each: two passes over S (max, then exp2 / sum,
+//   combined through shared memory), P is written
 //   back over S as packed bf16 (tcgen05.st) and O = P V runs as a TMEM-A ("TS") tcgen05.mma chain with
 //   V consumed MN-major from the same swizzled tile (no transpose anywhere); O is normalised by the
 //   row sum in the epilogue.  TMEM columns: S [0,KP), P [0,KP/2), O [KP/2, KP/2+64).
@@ -120,26 +121,29 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
 }
 
 template <int KP>
-__global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant__ CUtensorMap map_q,
+__global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant__ CUtensorMap map_q,
                                                            const __grid_constant__ CUtensorMap map_kv, int L, int heads,
                                                            float scale_l2e, const float* __restrict__ mask_add, int mask_ld,
                                                            int mask_len, bf16* __restrict__ ctx) {
   constexpr int Q_BYTES = 128 * 64 * 2, KV_BYTES = KP * 64 * 2;
+  constexpr int CH = KP / 64;  // 32-column chunks per thread: two threads share a query row, half the keys each
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sQ = base, sK = base + 2 * Q_BYTES, sV = sK + KV_BYTES, sM = sV + KV_BYTES;
-  float* maskf = reinterpret_cast<float*>(gen + 2 * Q_BYTES + 2 * KV_BYTES);
-  const uint32_t bars = sM + KP * 4;  // bar_load | bar_s | bar_o | tmem slot
-  volatile uint32_t* tslot_gen = reinterpret_cast<volatile uint32_t*>(gen + 2 * Q_BYTES + 2 * KV_BYTES + KP * 4 + 24);
+  const uint32_t sQ = base, sK = base + 2 * Q_BYTES, sV = sK + KV_BYTES;
+  float* maskf = reinterpret_cast<float*>(gen + 2 * Q_BYTES + 2 * KV_BYTES);  // [KP] additive mask * log2(e), -inf beyond L
+  float* red = maskf + KP;                                                     // [2 (max|sum)][2 halves][128 rows]
+  const uint32_t bars = base + 2 * Q_BYTES + 2 * KV_BYTES + KP * 4 + 2048;     // bar_load | bar_s | bar_o | tmem slot
+  volatile uint32_t* tslot_gen = reinterpret_cast<volatile uint32_t*>(gen + 2 * Q_BYTES + 2 * KV_BYTES + KP * 4 + 2048 + 24);
   const uint32_t bar_load = bars, bar_s = bars + 8, bar_o = bars + 16, tslot = bars + 24;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, half = warp >> 2, trow = quarter * 32 + lane;
   const int r = blockIdx.x / heads, h = blockIdx.x % heads;
   const int nqt = (L + 127) >> 7;
   const float LOG2E = 1.4426950408889634f;
 
-  if (tid == 0) {
+  if (warp == 1 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
     mbar_init(bar_load, 1);
@@ -148,14 +152,20 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(KP) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int key = tid; key < KP; key += 128)
-    maskf[key] = key < L ? ((mask_add != nullptr && key < mask_len) ? mask_add[(int64_t)r * mask_ld + key] * LOG2E : 0.f) : -INFINITY;
+  int any_mask = 0;
+  for (int key = tid; key < KP; key += 256) {
+    float m = -INFINITY;
+    if (key < L) {
+      m = (mask_add != nullptr && key < mask_len) ? mask_add[(int64_t)r * mask_ld + key] * LOG2E : 0.f;
+      any_mask |= (m != 0.f);
+    }
+    maskf[key] = m;
+  }
   tc_fence_before();
-  __syncthreads();
+  const bool masked = __syncthreads_or(any_mask) != 0;  // block-uniform: the common all-visible case skips the mask reads
   tc_fence_after();
   const uint32_t tmem = *tslot_gen;
 
@@ -171,7 +181,8 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
   // instruction descriptors: D=F32, A=B=BF16; S: N=KP, A/B K-major; PV: N=64, B MN-major (bit 16)
   const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KP >> 3) << 17) | (8u << 24);
   const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | (8u << 24);
-  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+  const int col0 = half * (KP / 2);  // first key column of this thread
 
   for (int qt = 0; qt < nqt; ++qt) {
     if (tid == 0) {
@@ -185,30 +196,62 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
     __syncwarp();
     tc_fence_after();
 
-    // ---- softmax over this thread's query row
+    // ---- pass 1: row maximum (in the log2 domain) over this thread's half of the keys
     float mx = -INFINITY;
 #pragma unroll 1
-    for (int j = 0; j < KP / 32; ++j) {
+    for (int j = 0; j < CH; ++j) {
       uint32_t raw[32];
-      tmem_ld32(lane_addr + j * 32, raw);
+      tmem_ld32(lane_addr + col0 + j * 32, raw);
+      const int k0 = col0 + j * 32;
+      if (masked || k0 + 32 > L) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(raw[i]), scale_l2e, maskf[j * 32 + i]));
-    }
-    float sum = 0.f;
-#pragma unroll 1
-    for (int j = 0; j < KP / 32; ++j) {
-      uint32_t raw[32], pk[16];
-      tmem_ld32(lane_addr + j * 32, raw);
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(raw[i]), scale_l2e, maskf[k0 + i]));
+      } else {
+        float m2 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float p0 = exp2f(fmaf(__uint_as_float(raw[2 * i]), scale_l2e, maskf[j * 32 + 2 * i]) - mx);
-        const float p1 = exp2f(fmaf(__uint_as_float(raw[2 * i + 1]), scale_l2e, maskf[j * 32 + 2 * i + 1]) - mx);
-        sum += p0 + p1;
-        __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);  // .x (low half) = even key
-        pk[i] = *reinterpret_cast<uint32_t*>(&b);
+        for (int i = 0; i < 32; ++i) m2 = fmaxf(m2, __uint_as_float(raw[i]));
+        mx = fmaxf(mx, m2 * scale_l2e);
       }
-      tmem_st16(lane_addr + j * 16, pk);
     }
+    red[half * 128 + trow] = mx;
+    __syncthreads();
+    mx = fmaxf(red[trow], red[128 + trow]);
+
+    // ---- pass 2: p = 2^(s*c + mask - max); packed bf16 P kept in registers until every S read is done
+    float sum = 0.f;
+    uint32_t pk[CH][16];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      uint32_t raw[32];
+      tmem_ld32(lane_addr + col0 + j * 32, raw);
+      const int k0 = col0 + j * 32;
+      if (masked || k0 + 32 > L) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), scale_l2e, maskf[k0 + 2 * i]) - mx);
+          const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), scale_l2e, maskf[k0 + 2 * i + 1]) - mx);
+          sum += p0 + p1;
+          __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);  // .x (low half) = even key
+          pk[j][i] = *reinterpret_cast<uint32_t*>(&b);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), scale_l2e, -mx));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), scale_l2e, -mx));
+          sum += p0 + p1;
+          __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
+          pk[j][i] = *reinterpret_cast<uint32_t*>(&b);
+        }
+      }
+    }
+    red[256 + half * 128 + trow] = sum;
+    tc_fence_before();
+    __syncthreads();  // all S columns have been read by both halves: P may now overwrite them
+    tc_fence_after();
+    sum = red[256 + trow] + red[256 + 128 + trow];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) tmem_st16(lane_addr + half * (KP / 4) + j * 16, pk[j]);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     tc_fence_before();
     __syncthreads();
@@ -224,14 +267,14 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
     __syncwarp();
     tc_fence_after();
 
-    const int q = qt * 128 + warp * 32 + lane;
+    // ---- O = (P V) / sum : this thread stores 32 of the row's 64 output columns
+    const int q = qt * 128 + trow;
     const float inv = 1.0f / sum;
-#pragma unroll 1
-    for (int j = 0; j < 2; ++j) {
+    {
       uint32_t raw[32];
-      tmem_ld32(lane_addr + KP / 2 + j * 32, raw);
+      tmem_ld32(lane_addr + KP / 2 + half * 32, raw);
       if (q < L) {
-        bf16* op = ctx + ((int64_t)r * L + q) * (heads * AT_D) + h * AT_D + j * 32;
+        bf16* op = ctx + ((int64_t)r * L + q) * (heads * AT_D) + h * AT_D + half * 32;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 u;
@@ -261,13 +304,13 @@ static int launch_attention_tc(const bf16* qkv, int64_t R, int L, int heads, flo
   const int ld = 3 * heads * AT_D;
   MSQ_TRY(make_map_bf16(&mq, qkv, R * L, ld, ld, AT_D, 128));
   MSQ_TRY(make_map_bf16(&mkv, qkv, R * L, ld, ld, AT_D, KP));
-  constexpr int SMEM = 2 * 128 * 64 * 2 + 2 * KP * 64 * 2 + KP * 4 + 64 + 1024;
+  constexpr int SMEM = 2 * 128 * 64 * 2 + 2 * KP * 64 * 2 + KP * 4 + 2048 + 64 + 1024;
   static bool configured = false;
   if (!configured) {
     MSQ_CUDA(cudaFuncSetAttribute(attention_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  attention_tc_kernel<KP><<<(unsigned)(R * heads), 128, SMEM, st>>>(mq, mkv, L, heads, scale * 1.4426950408889634f, mask_add,
+  attention_tc_kernel<KP><<<(unsigned)(R * heads), 256, SMEM, st>>>(mq, mkv, L, heads, scale * 1.4426950408889634f, mask_add,
                                                                     mask_ld, mask_len, ctx);
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
