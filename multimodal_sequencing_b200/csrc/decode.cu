@@ -66,27 +66,32 @@ __global__ void __launch_bounds__(DC_THREADS) beam_search_kernel(DecodeWeights w
         }
       }
       const float* wp = w.whh_t + 4 * u;
-      float4 wn[4];
+      // weights stream from L2: keep KU rows in flight beyond the KU being consumed (the loop is latency bound)
+      constexpr int KU = 8;
+      float4 wn[KU];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) wn[i] = *reinterpret_cast<const float4*>(wp + (int64_t)i * H4);
-      for (int k = 0; k < H; k += 4) {
-        float4 wc[4];
+      for (int i = 0; i < KU; ++i) wn[i] = __ldg(reinterpret_cast<const float4*>(wp + (int64_t)i * H4));
+      for (int k = 0; k < H; k += KU) {
+        float4 wc[KU];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) wc[i] = wn[i];
-        if (k + 4 < H) {
+        for (int i = 0; i < KU; ++i) wc[i] = wn[i];
+        if (k + KU < H) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) wn[i] = *reinterpret_cast<const float4*>(wp + (int64_t)(k + 4 + i) * H4);
+          for (int i = 0; i < KU; ++i) wn[i] = __ldg(reinterpret_cast<const float4*>(wp + (int64_t)(k + KU + i) * H4));
         }
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
-          const float4 hv = *reinterpret_cast<const float4*>(hs + r * H + k);
-          const float hk[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            acc[r].x = fmaf(wc[i].x, hk[i], acc[r].x);
-            acc[r].y = fmaf(wc[i].y, hk[i], acc[r].y);
-            acc[r].z = fmaf(wc[i].z, hk[i], acc[r].z);
-            acc[r].w = fmaf(wc[i].w, hk[i], acc[r].w);
+          for (int kk = 0; kk < KU; kk += 4) {
+            const float4 hv = *reinterpret_cast<const float4*>(hs + r * H + k + kk);
+            const float hk[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              acc[r].x = fmaf(wc[kk + i].x, hk[i], acc[r].x);
+              acc[r].y = fmaf(wc[kk + i].y, hk[i], acc[r].y);
+              acc[r].z = fmaf(wc[kk + i].z, hk[i], acc[r].z);
+              acc[r].w = fmaf(wc[kk + i].w, hk[i], acc[r].w);
+            }
           }
         }
       }
@@ -108,20 +113,31 @@ __global__ void __launch_bounds__(DC_THREADS) beam_search_kernel(DecodeWeights w
 #pragma unroll
       for (int r = 0; r < ROWS; ++r) acc[r] = bq;
       const float* wp = w.wq_t + 4 * j4;
-      for (int k = 0; k < H; k += 4) {
-        float4 wc[4];
+      constexpr int KU = 8;
+      float4 wn[KU];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) wc[i] = *reinterpret_cast<const float4*>(wp + (int64_t)(k + i) * H);
+      for (int i = 0; i < KU; ++i) wn[i] = __ldg(reinterpret_cast<const float4*>(wp + (int64_t)i * H));
+      for (int k = 0; k < H; k += KU) {
+        float4 wc[KU];
+#pragma unroll
+        for (int i = 0; i < KU; ++i) wc[i] = wn[i];
+        if (k + KU < H) {
+#pragma unroll
+          for (int i = 0; i < KU; ++i) wn[i] = __ldg(reinterpret_cast<const float4*>(wp + (int64_t)(k + KU + i) * H));
+        }
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
-          const float4 hv = *reinterpret_cast<const float4*>(hn + r * H + k);
-          const float hk[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            acc[r].x = fmaf(wc[i].x, hk[i], acc[r].x);
-            acc[r].y = fmaf(wc[i].y, hk[i], acc[r].y);
-            acc[r].z = fmaf(wc[i].z, hk[i], acc[r].z);
-            acc[r].w = fmaf(wc[i].w, hk[i], acc[r].w);
+          for (int kk = 0; kk < KU; kk += 4) {
+            const float4 hv = *reinterpret_cast<const float4*>(hn + r * H + k + kk);
+            const float hk[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              acc[r].x = fmaf(wc[kk + i].x, hk[i], acc[r].x);
+              acc[r].y = fmaf(wc[kk + i].y, hk[i], acc[r].y);
+              acc[r].z = fmaf(wc[kk + i].z, hk[i], acc[r].z);
+              acc[r].w = fmaf(wc[kk + i].w, hk[i], acc[r].w);
+            }
           }
         }
       }
@@ -259,7 +275,7 @@ static int launch_beam(const DecodeWeights& w, const DecodeIO& io, int G, cudaSt
 int beam_search(const DecodeWeights& w, const DecodeIO& io, cudaStream_t st) {
   MSQ_REQUIRE(io.N >= 2 && io.N <= DC_MAXN, "beam_search: N=%d out of range [2,%d]", io.N, DC_MAXN);
   MSQ_REQUIRE(io.W >= 1 && io.W <= 16, "beam_search: beam width %d out of range [1,16]", io.W);
-  MSQ_REQUIRE(io.H % 4 == 0 && io.H <= 1024, "beam_search: H=%d unsupported", io.H);
+  MSQ_REQUIRE(io.H % 8 == 0 && io.H <= 1024, "beam_search: H=%d unsupported", io.H);
   if (io.B == 0) return MSQ_OK;
   // rows per CTA: enough manuals to reuse each weight row across ~16 beams, but never fewer CTAs than
   // needed to give every SM work when B is large.

@@ -7,7 +7,7 @@
 
 namespace msq {
 
-constexpr int SG_BM = 128, SG_BN = 128, SG_BK = 16, SG_LD = 132;
+constexpr int SG_BK = 16;
 
 template <typename T> struct Load8;
 template <> struct Load8<float> {
@@ -35,6 +35,27 @@ template <> struct Load8<bf16> {
   }
 };
 
+template <typename T, int KV> struct LoadK {
+  static __device__ __forceinline__ void load(const T* p, bool ok, float* v) { Load8<T>::load(p, ok, v); }
+};
+template <> struct LoadK<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, bool ok, float* v) {
+    float4 a = ok ? *reinterpret_cast<const float4*>(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  }
+};
+template <> struct LoadK<bf16, 4> {
+  static __device__ __forceinline__ void load(const bf16* p, bool ok, float* v) {
+    if (ok) {
+      uint2 u = *reinterpret_cast<const uint2*>(p);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+      v[0] = __low2float(h[0]); v[1] = __high2float(h[0]); v[2] = __low2float(h[1]); v[3] = __high2float(h[1]);
+    } else {
+      v[0] = v[1] = v[2] = v[3] = 0.f;
+    }
+  }
+};
+
 template <typename TO> __device__ __forceinline__ void store4(TO* p, float4 v);
 template <> __device__ __forceinline__ void store4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 template <> __device__ __forceinline__ void store4<bf16>(bf16* p, float4 v) {
@@ -45,68 +66,81 @@ template <> __device__ __forceinline__ void store4<bf16>(bf16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = u;
 }
 
-template <typename TA, typename TO>
+// TILE = 128: 8x8 micro-tile (large M);  TILE = 64: 4x4 micro-tile, 4x the CTAs (the M <= ~1k GEMMs behind
+// the decoder would otherwise occupy a third of the SMs)
+template <typename TA, typename TO, int TILE>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A, const TA* __restrict__ W,
                                                         const float* __restrict__ bias, const float* __restrict__ resid,
                                                         TO* __restrict__ C, float* __restrict__ C2, int64_t M, int N, int K,
                                                         int lda, int ldw, int ldc, int ldr, int act) {
+  constexpr int SG_BM = TILE, SG_BN = TILE, SG_LD = TILE + 4, TM = TILE / 16, HM = TM / 2;
+  constexpr int KV = TILE == 128 ? 8 : 4;  // k elements each thread stages per tile row
   __shared__ __align__(16) float As[2][SG_BK][SG_LD];
   __shared__ __align__(16) float Bs[2][SG_BK][SG_LD];
   const int tid = threadIdx.x;
   const int64_t m0 = (int64_t)blockIdx.y * SG_BM;
   const int n0 = blockIdx.x * SG_BN;
-  const int lrow = tid & 127, lk = (tid >> 7) * 8;
+  const int lrow = tid % TILE, lk = (tid / TILE) * KV;
   const bool a_ok = (m0 + lrow) < M, b_ok = (n0 + lrow) < N;
   const TA* ap = A + (m0 + lrow) * (int64_t)lda + lk;
   const TA* bp = W + (int64_t)(n0 + lrow) * ldw + lk;
   const int ty = tid >> 4, tx = tid & 15;
 
-  float acc[8][8];
+  float acc[TM][TM];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TM; ++j) acc[i][j] = 0.f;
 
   float ra[8], rb[8];
-  Load8<TA>::load(ap, a_ok, ra);
-  Load8<TA>::load(bp, b_ok, rb);
+  LoadK<TA, KV>::load(ap, a_ok, ra);
+  LoadK<TA, KV>::load(bp, b_ok, rb);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { As[0][lk + i][lrow] = ra[i]; Bs[0][lk + i][lrow] = rb[i]; }
+  for (int i = 0; i < KV; ++i) { As[0][lk + i][lrow] = ra[i]; Bs[0][lk + i][lrow] = rb[i]; }
   __syncthreads();
 
   const int nk = K / SG_BK;
   for (int kt = 0; kt < nk; ++kt) {
     const int cur = kt & 1;
     if (kt + 1 < nk) {
-      Load8<TA>::load(ap + (kt + 1) * SG_BK, a_ok, ra);
-      Load8<TA>::load(bp + (kt + 1) * SG_BK, b_ok, rb);
+      LoadK<TA, KV>::load(ap + (kt + 1) * SG_BK, a_ok, ra);
+      LoadK<TA, KV>::load(bp + (kt + 1) * SG_BK, b_ok, rb);
     }
 #pragma unroll
     for (int k = 0; k < SG_BK; ++k) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
-      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float av[TM], bv[TM];
+      if (TILE == 128) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
+        av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[TM - 4] = a1.x; av[TM - 3] = a1.y; av[TM - 2] = a1.z; av[TM - 1] = a1.w;
+        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[TM - 4] = b1.x; bv[TM - 3] = b1.y; bv[TM - 2] = b1.z; bv[TM - 1] = b1.w;
+      } else {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+        av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
+        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < TM; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     if (kt + 1 < nk) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { As[cur ^ 1][lk + i][lrow] = ra[i]; Bs[cur ^ 1][lk + i][lrow] = rb[i]; }
+      for (int i = 0; i < KV; ++i) { As[cur ^ 1][lk + i][lrow] = ra[i]; Bs[cur ^ 1][lk + i][lrow] = rb[i]; }
     }
     __syncthreads();
   }
+  (void)HM;
 
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < TM; ++i) {
     const int64_t row = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
     if (row >= M) continue;
 #pragma unroll
-    for (int jh = 0; jh < 2; ++jh) {
+    for (int jh = 0; jh < TM / 4; ++jh) {
       const int col = n0 + jh * 64 + tx * 4;
       if (col >= N) continue;  // N % 4 == 0
       float4 v = make_float4(acc[i][jh * 4 + 0], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
@@ -130,9 +164,16 @@ int gemm_simt(const GemmArgs& g, cudaStream_t st) {
   MSQ_REQUIRE(g.K % SG_BK == 0 && g.N % 4 == 0 && g.lda % 8 == 0 && g.ldw % 8 == 0 && g.ldc % 4 == 0,
               "gemm_simt: K=%d N=%d lda=%d ldw=%d ldc=%d not supported", g.K, g.N, g.lda, g.ldw, g.ldc);
   if (g.M == 0) return MSQ_OK;
-  dim3 grid(ceil_div(g.N, SG_BN), ceil_div(g.M, SG_BM));
-  gemm_simt_kernel<TA, TO><<<grid, 256, 0, st>>>((const TA*)g.A, (const TA*)g.W, g.bias, g.resid, (TO*)g.C, g.C2, g.M, g.N,
-                                                 g.K, g.lda, g.ldw, g.ldc, g.ldr, g.act);
+  // small problems: 64x64 tiles give 4x the CTAs (fills the 148 SMs when M is a few hundred rows)
+  if ((int64_t)ceil_div(g.N, 128) * ceil_div(g.M, 128) < 2 * 148) {
+    dim3 grid(ceil_div(g.N, 64), ceil_div(g.M, 64));
+    gemm_simt_kernel<TA, TO, 64><<<grid, 256, 0, st>>>((const TA*)g.A, (const TA*)g.W, g.bias, g.resid, (TO*)g.C, g.C2, g.M,
+                                                        g.N, g.K, g.lda, g.ldw, g.ldc, g.ldr, g.act);
+  } else {
+    dim3 grid(ceil_div(g.N, 128), ceil_div(g.M, 128));
+    gemm_simt_kernel<TA, TO, 128><<<grid, 256, 0, st>>>((const TA*)g.A, (const TA*)g.W, g.bias, g.resid, (TO*)g.C, g.C2, g.M,
+                                                         g.N, g.K, g.lda, g.ldw, g.ldc, g.ldr, g.act);
+  }
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }

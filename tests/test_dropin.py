@@ -80,6 +80,39 @@ def test_training_forward_is_declared_out_of_scope(golden_dir):
         model({"input_ids": None})
 
 
+def test_cal_result_matches_reference_formula():
+    from models.berson.eval import cal_result
+    truth = [[0, 1, 2, 3, 4], [2, 0, 1, 4, 3], [4, 3, 2, 1, 0]]
+    pred = [[0, 1, 2, 3, 4], [0, 2, 1, 4, 3], [0, 1, 2, 3, 4]]
+    got = cal_result(truth, pred)
+    want = O.cal_result(truth, pred)
+    assert all(abs(a - b) < 1e-12 for a, b in zip(got, want))
+    assert got[1] == 1 / 3 and abs(got[2] - (1 + 0.8 - 1) / 3) < 1e-12
+
+
+@pytest.mark.gpu
+def test_berson_evaluate_batched(golden_dir, tmp_path):
+    """berson_evaluate (models/berson/eval.py:39) with a DataLoader batch of 3 manuals: artefacts + metrics."""
+    from models.berson.eval import berson_evaluate
+    g = torch.load(os.path.join(golden_dir, "text_tiny.pt"), weights_only=False)
+    cases = [c for c in g["cases"] if c["N"] == 5 and c["W"] == 4 and c["kind"] == "full"]
+    model, args = _build(g, 5, 4, "cuda")
+    model.load_state_dict(g["sd"], strict=False)
+    model = model.cuda().eval()
+    for mod in model.modules():
+        mod.precise = True
+    ids = torch.cat([c["ids"] for c in cases])
+    labels = torch.cat([c["labels"] for c in cases])
+    ds = torch.utils.data.TensorDataset(ids, torch.ones_like(ids), torch.zeros_like(ids), labels, torch.arange(len(cases)))
+    args.task_names, args.output_dir, args.per_gpu_eval_batch_size, args.n_gpu = ["wikihow"], str(tmp_path), 3, 1
+    args.local_rank, args.max_eval_steps = -1, 0
+    res = berson_evaluate(args, model, lambda *a, **k: ds, Tok())
+    want = O.cal_result(labels.tolist(), [c["perm"] for c in cases])
+    assert abs(res["acc_dev"] - want[0]) < 1e-12 and res["pmr_dev"] == want[1] and abs(res["taus_dev"] - want[2]) < 1e-12
+    lines = open(os.path.join(str(tmp_path), "output_order.txt")).read().strip().split("\n")
+    assert lines == ["%s|||%s" % (" ".join(map(str, c["perm"])), " ".join(map(str, c["labels"][0].tolist()))) for c in cases]
+
+
 def _reference_style_search(args, model, berson_inputs):
     """beam_search_pointer's loop exactly as the reference writes it (modeling_bert.py:1429-1552), driving
     OUR model.encode / model.step / Beam one step at a time."""
