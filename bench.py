@@ -243,6 +243,10 @@ def main():
         return
 
     pk = peaks()
+    traffic = None  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    tp = os.path.join(ROOT, "profiles", "r1_gemm_tc_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("traffic_bytes_per_launch")
     total = world * B * args.steps
     value = total / (ms_total / 1e3)
     e2e = total / (e2e_ms / 1e3)
@@ -257,7 +261,9 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "msq::gemm_tc_kernel (tcgen05 bf16 GEMM, all encoder linears)",
                          "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                         "frac": (ach / pk["tf_sust"]) if ach else None, "traffic": None,
+                         "frac": (ach / pk["tf_sust"]) if ach else None, "traffic": traffic,
+                         "traffic_note": "mean dram read+write bytes per launch over 8 BERT-layer GEMM launches at 640 pair rows, "
+                                         "ncu --set full (profiles/r1_gemm_tc_traffic.json); algorithmic bytes beside it there",
                          "peak_source": pk["src"] + ", bf16_tflops_sustained (kernel timed inside a long step)",
                          "launches_timed": pl.value, "kernel_ms_per_step": pm.value / args.steps,
                          "kernel_share_of_step": (pm.value / args.steps) / (ms_total / args.steps),
