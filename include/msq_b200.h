@@ -90,6 +90,14 @@ int msq_encode(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, cons
                const int64_t* sep_dev, int64_t B, int32_t N, int32_t Lt, const float* images_dev, int64_t n_img,
                const int32_t* img_index_dev, const msq_encode_out* out, void* stream);
 
+/* ---- BertForOrdering._forward loss VALUE (modeling_bert.py:943-1174: teacher-forced pointer NLL / (N-1) + lam *
+ * pairwise NLL / P, batch mean), forward only (no gradients in this build).  ground_truth_dev [B,N] int32 =
+ * the target order, pairwise_labels_dev [B,P] int64, perm_scratch_dev [B,N] int32 workspace, loss_dev 1 float. */
+int msq_training_loss(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev,
+                      const int64_t* sep_dev, int64_t B, int32_t N, int32_t Lt, const float* images_dev, int64_t n_img,
+                      const int32_t* img_index_dev, const int32_t* ground_truth_dev, const int64_t* pairwise_labels_dev,
+                      float lam, int32_t* perm_scratch_dev, float* loss_dev, void* stream);
+
 /* ---- pointer decoder + beam search (modeling_bert.py:1368-1402, 1411-1552; generator.py:15-38) --
  * Consumes encode outputs (device, fp32): sents/key [B,N,H], h0 [B,H], cls_mat [B,N,N,H],
  * score_mat [B,N,N,2].  perm_dev [B,N] int32 receives the predicted order.  Optional traces:

@@ -35,6 +35,7 @@ SIGNATURES = {
     "msq_vit_forward": (C.c_int, [_P, _P, _I64, _P, _I64, _P, _P]),
     "msq_inner_forward": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _I64, _P, _P, _P, _P, _P]),
     "msq_encode": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, C.POINTER(MsqEncodeOut), _P]),
+    "msq_training_loss": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P, _P, _F, _P, _P, _P]),
     "msq_beam_search": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
     "msq_decode_step": (C.c_int, [_P] * 12 + [_I32, _I32, _P, _P, _P, _P]),
     "msq_order_manuals_dev": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _I32, _P, _P]),

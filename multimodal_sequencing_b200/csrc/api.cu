@@ -262,6 +262,29 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ s, bf16* __restrict
     d[i] = __float2bfloat16_rn(s[i]);
 }
 
+// loss = mean_b nll_b / (N - 1 + 1e-20) + lam * mean_b (sum_p -log softmax(cls_score_p)[label_p]) / (P + 1e-20)
+// (modeling_bert.py:1140-1174).  rel6 rows hold the pairwise_relationship logits in columns 0..1.
+__global__ void training_loss_kernel(const float* __restrict__ nll, const float* __restrict__ rel6, const int64_t* __restrict__ labels,
+                                     int64_t B, int N, float lam, float* __restrict__ out) {
+  __shared__ float sh[256];
+  const int P = N * (N - 1);
+  float a = 0.f;
+  for (int64_t i = threadIdx.x; i < B * P; i += blockDim.x) {
+    const float z0 = rel6[i * 6], z1 = rel6[i * 6 + 1];
+    const float mx = fmaxf(z0, z1), lse = mx + logf(expf(z0 - mx) + expf(z1 - mx));
+    a += (lse - (labels[i] ? z1 : z0)) / ((float)P + 1e-20f);
+  }
+  float p = 0.f;
+  for (int64_t b = threadIdx.x; b < B; b += blockDim.x) p += nll[b] / ((float)N + 1e-20f - 1.f);
+  sh[threadIdx.x] = p + lam * a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0] / (float)B;
+}
+
 static bool use_tc(const msq_model* m) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("MSQ_FORCE_SIMT"); forced = (e && e[0] == '1') ? 1 : 0; }
@@ -728,7 +751,7 @@ static int run_paragraph(msq_model* m, HeadBufs& h, int64_t B, int N, cudaStream
 // decode pre-projections + beam search from (sents, key, h0, r0)
 static int run_decode(msq_model* m, const float* sents, const float* key, const float* h0, const float* r0, float* sents_ext,
                       float* xg, float* t4, int64_t B, int N, int beam, int32_t* perm, int32_t* tr_ix, float* tr_cost,
-                      float* tr_logp, cudaStream_t st) {
+                      float* tr_logp, cudaStream_t st, const int32_t* forced = nullptr, float* final_cost = nullptr) {
   const int H = m->cfg.hidden;
   sents_ext_kernel<<<ceil_div(B * (N + 1) * (int64_t)H, 256), 256, 0, st>>>(sents, B, N, H, sents_ext);
   MSQ_LAUNCH_CHECK();
@@ -738,6 +761,7 @@ static int run_decode(msq_model* m, const float* sents, const float* key, const 
   DecodeIO io;
   io.xg = xg; io.t4 = t4; io.key0 = key; io.h0 = h0; io.B = B; io.N = N; io.W = beam; io.H = H;
   io.perm = perm; io.trace_ix = tr_ix; io.trace_cost = tr_cost; io.trace_logp = tr_logp;
+  io.forced = forced; io.final_cost = final_cost;
   return beam_search(m->dec, io, st);
 }
 
@@ -751,7 +775,8 @@ static int chunk_manuals() {
 template <typename T>
 static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const int64_t* mask, const int64_t* sep, int64_t B, int N,
                     int Lt, const float* images, int64_t n_img, const int32_t* img_index, const msq_encode_out* out, int beam,
-                    int32_t* perm, cudaStream_t st) {
+                    int32_t* perm, cudaStream_t st, const int32_t* forced = nullptr, const int64_t* pair_labels = nullptr,
+                    float lam = 0.f, float* loss_out = nullptr) {
   const msq_config& c = m->cfg;
   MSQ_REQUIRE(m->packed, "msq_model_pack() has not been called");
   MSQ_REQUIRE(m->has_bert && m->has_heads, "model lacks the inner encoder or the BERSON head weights");
@@ -804,8 +829,16 @@ static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const i
     if (out->cls_score) MSQ_CUDA(cudaMemcpy2DAsync(out->cls_score, 2 * sizeof(float), hb.rel6, 6 * sizeof(float), 2 * sizeof(float),
                                                    (size_t)R, cudaMemcpyDeviceToDevice, st));
   }
-  if (perm)
+  if (perm && !forced)
     MSQ_TRY(run_decode(m, hb.sents, hb.key, hb.h0, hb.r0, hb.sents_ext, hb.xg, hb.t4, B, N, beam, perm, nullptr, nullptr, nullptr, st));
+  if (forced) {
+    // teacher-forced NLL of the ground-truth order + lam * pairwise NLL (modeling_bert.py:1098-1174), forward only
+    float* nll = hb.pn;  // [B] scratch (paragraph buffers are free again)
+    MSQ_TRY(run_decode(m, hb.sents, hb.key, hb.h0, hb.r0, hb.sents_ext, hb.xg, hb.t4, B, N, 1, perm, nullptr, nullptr, nullptr, st, forced,
+                       nll));
+    training_loss_kernel<<<1, 256, 0, st>>>(nll, hb.rel6, pair_labels, B, N, lam, loss_out);
+    MSQ_LAUNCH_CHECK();
+  }
   return MSQ_OK;
 }
 
@@ -887,6 +920,20 @@ extern "C" int msq_order_manuals_dev(msq_model* m, const int64_t* ids_dev, const
   if (m->cfg.precise)
     return run_path<float>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, nullptr, beam, perm_dev, st);
   return run_path<bf16>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, nullptr, beam, perm_dev, st);
+}
+
+// BertForOrdering._forward loss VALUE (modeling_bert.py:943-1174, default objectives), forward only
+extern "C" int msq_training_loss(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev,
+                                 const int64_t* sep_dev, int64_t B, int32_t N, int32_t Lt, const float* images_dev, int64_t n_img,
+                                 const int32_t* img_index_dev, const int32_t* ground_truth_dev, const int64_t* pairwise_labels_dev,
+                                 float lam, int32_t* perm_scratch_dev, float* loss_dev, void* stream) {
+  MSQ_REQUIRE(m && ground_truth_dev && pairwise_labels_dev && perm_scratch_dev && loss_dev, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m->cfg.precise)
+    return run_path<float>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, nullptr, 1,
+                           perm_scratch_dev, st, ground_truth_dev, pairwise_labels_dev, lam, loss_dev);
+  return run_path<bf16>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, nullptr, 1, perm_scratch_dev,
+                        st, ground_truth_dev, pairwise_labels_dev, lam, loss_dev);
 }
 
 extern "C" int msq_beam_search(msq_model* m, const float* sents_dev, const float* key_dev, const float* h0_dev,

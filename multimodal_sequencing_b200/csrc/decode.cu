@@ -200,12 +200,19 @@ __global__ void __launch_bounds__(DC_THREADS) beam_search_kernel(DecodeWeights w
       const int g = c / (W * N), flat = c % (W * N), wslot = flat / N, k = flat % N;
       const int live = nlive[g];
       if (wslot >= live) continue;
-      const int numel = live * N, kk = min(W, numel);
+      const int numel = live * N;
+      int kk = min(W, numel);
       const float mine = e[g * W + wslot][k];
       int rank = 0;
-      for (int o = 0; o < numel; ++o) {
-        const float v = e[g * W + o / N][o % N];
-        rank += (v < mine) || (v == mine && o < flat);
+      if (io.forced) {
+        // teacher forcing (training loss, modeling_bert.py:998-1078): the single hypothesis follows the target order
+        kk = 1;
+        rank = (wslot == 0 && k == io.forced[(b0 + g) * N + t]) ? 0 : 1;
+      } else {
+        for (int o = 0; o < numel; ++o) {
+          const float v = e[g * W + o / N][o % N];
+          rank += (v < mine) || (v == mine && o < flat);
+        }
       }
       if (rank < kk) {
         const int nr = g * W + rank;
@@ -256,6 +263,7 @@ __global__ void __launch_bounds__(DC_THREADS) beam_search_kernel(DecodeWeights w
     int last = 0;
     while (last < N - 1 && (picked >> last & 1u)) ++last;
     io.perm[(b0 + tid) * N + N - 1] = last;
+    if (io.final_cost) io.final_cost[b0 + tid] = cost[r];  // = sum_t -log p(pick_t): the NLL when teacher-forced
   }
 }
 

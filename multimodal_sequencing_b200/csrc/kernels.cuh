@@ -74,6 +74,8 @@ struct DecodeIO {
   int32_t* trace_ix;   // optional [B, N-1, W] flat index beam*N+tok per step (or -1)
   float* trace_cost;   // optional [B, N-1, W]
   float* trace_logp;   // optional [B, N-1, W, N]
+  const int32_t* forced;  // optional [B, N]: teacher-forced picks (W must be 1)
+  float* final_cost;      // optional [B]: cost of the best hypothesis
 };
 int beam_search(const DecodeWeights& w, const DecodeIO& io, cudaStream_t st);
 struct StepIO {

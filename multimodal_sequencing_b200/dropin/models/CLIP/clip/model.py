@@ -61,7 +61,7 @@ class VisualTransformer(nn.Module):
                     vision_width=self.width, vision_patch_size=self.patch_size)
 
     def _engine(self):
-        sig = tuple(p._version for p in self.parameters())
+        sig = tuple(p._version for p in self.parameters()) + (bool(getattr(self, "precise", False)),)
         if self.__dict__.get("_eng") is None or self.__dict__.get("_eng_sig") != sig:
             dev = self.conv1.weight.device
             if dev.type != "cuda":

@@ -37,8 +37,11 @@ class LXRTModel(nn.Module):
         self.config = config
         if kwargs.get("multimodal_text_part") or kwargs.get("multimodal_img_part"):
             raise NotImplementedError("text-only / image-only LXRT parts are outside the scoped path")
-        if kwargs.get("num_labels") is not None:
-            raise NotImplementedError("topo-sort classifier mode is a later row of the scope table (SURVEY §8(f).4)")
+        # topo-sort pairwise classifier mode (lxrt/modeling.py:1502-1511): RobertaClassificationHead on the pooled CLS
+        self.topo_sort = kwargs.get("num_labels") is not None
+        if self.topo_sort:
+            self.num_labels = kwargs["num_labels"]
+            config.num_labels = self.num_labels
         name = kwargs.get("clip_model_name", "ViT-B/32")
         vit = kwargs.get("clip_config") or CLIP_CONFIGS.get(name)
         if vit is None:
@@ -64,10 +67,12 @@ class LXRTModel(nn.Module):
         enc.skip_last_layer = True  # oracle decision for the ViT tower
         self.encoder = enc
         self.pooler = _holder(dense=nn.Linear(H, H))
+        if self.topo_sort:
+            self.classifier = _holder(dense=nn.Linear(H, H), out_proj=nn.Linear(H, self.num_labels))
         self.apply(lambda m: _init_bert_weights(m, config.initializer_range))  # 1464: re-initialises the tower's Linears too
 
     def _engine(self):
-        sig = tuple(p._version for p in self.parameters())
+        sig = tuple(p._version for p in self.parameters()) + (bool(getattr(self, "precise", False)),)
         if self.__dict__.get("_eng") is None or self.__dict__.get("_eng_sig") != sig:
             dev = self.pooler.dense.weight.device
             if dev.type != "cuda":
@@ -91,10 +96,21 @@ class LXRTModel(nn.Module):
             token_type_ids = torch.zeros_like(input_ids)
         R = input_ids.shape[0]
         idx = None
+        if self.topo_sort and visual_feats is not None and visual_feats.dim() == 5:   # [R, img_len, 3, S, S] (1516-1518)
+            visual_feats = visual_feats.reshape(-1, *visual_feats.shape[2:])
         if visual_feats is not None:
             assert visual_feats.shape[0] == 2 * R, "BERSON mode feeds two images per pair row"
             idx = torch.arange(2 * R, dtype=torch.int32, device=visual_feats.device)
         with torch.no_grad():
             lang, visn, pooled = self._engine().inner_forward(input_ids, token_type_ids, attention_mask, visual_feats, idx,
                                                               want_pooled=True)
+        if self.topo_sort:
+            # RobertaClassificationHead on pooled_output.unsqueeze(1) (1586-1594): dense -> tanh -> out_proj (eval: no dropout)
+            with torch.no_grad():
+                eng = self._engine()
+                hid = eng.linear(pooled, self.classifier.dense.weight, self.classifier.dense.bias, act=3)
+                logits = eng.linear(hid, self.classifier.out_proj.weight, self.classifier.out_proj.bias)
+            if labels is not None:
+                return torch.nn.functional.cross_entropy(logits, labels.to(logits.device)), logits
+            return (logits,)
         return (lang, visn), pooled

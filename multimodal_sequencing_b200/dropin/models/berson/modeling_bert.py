@@ -79,7 +79,8 @@ class _EngineOwner:
         return self.state_dict()
 
     def engine(self):
-        sig = tuple(p._version for p in self.parameters()) + (tuple(id(p) for p in self.parameters()),)
+        sig = tuple(p._version for p in self.parameters()) + (tuple(id(p) for p in self.parameters()),
+                                                               bool(getattr(self, "precise", False)))
         eng = self.__dict__.get("_eng")
         if eng is None or self.__dict__.get("_eng_sig") != sig:
             dev = next(self.parameters()).device
@@ -218,8 +219,32 @@ class BertForOrdering(nn.Module, _EngineOwner):
                 torch.cat((cls_output_matrix_nn, torch.softmax(cls_score_matrix_nn_his2, -1)), -1))
 
     def forward(self, inputs):
-        raise NotImplementedError("teacher-forced training loss (modeling_bert.py:943-1237) is a later row of the "
-                                  "scope table (SURVEY.md §8(f).2); this build covers evaluation / inference")
+        """modeling_bert.py:937-941 -> (loss,).  The loss VALUE (pointer NLL + lam * pairwise NLL, 943-1174) is
+        computed on the device, forward only: there is no backward in this build, so calling
+        it in train() mode raises instead of silently not learning."""
+        if self.training:
+            raise NotImplementedError("backward / fine-tuning is a later row of the scope table (SURVEY.md §8(f).2); "
+                                      "call model.eval() to obtain the validation loss")
+        berson_inputs = inputs
+        if getattr(self, "tokenizer", None) is not None:
+            berson_inputs = prepare_berson_inputs(berson_inputs, self.tokenizer, args=self.args)
+        return self._forward(**berson_inputs)
+
+    def _forward(self, input_ids, attention_mask=None, token_type_ids=None, pairs_list=None, passage_length=None,
+                 pairs_num=None, sep_positions=None, ground_truth=None, mask_cls=None, pairwise_labels=None, cuda=None,
+                 head_mask=None, images=None, _pair_batch=None):
+        B, P, Lt = input_ids.shape
+        N = int(passage_length[0])
+        pb = _pair_batch
+        if pb is None:
+            img = idx = None
+            if images is not None:
+                img = images.reshape(B * P * 2, *images.shape[3:])
+                idx = torch.arange(B * P * 2, dtype=torch.int32).reshape(B, P, 2)
+            pb = PairBatch(input_ids, attention_mask, token_type_ids, sep_positions, pairs_list, pairwise_labels,
+                           ground_truth, N, img, idx)
+        with torch.no_grad():
+            return (self.engine().training_loss(pb, self.pairwise_loss_lam),)
 
     # ---- encode ------------------------------------------------------------------------------
     def encode(self, input_ids, attention_mask=None, token_type_ids=None, pairs_list=None, passage_length=None,

@@ -226,6 +226,38 @@ class OrderingEngine:
         o["c0"] = torch.zeros_like(o["h0"])
         return o
 
+    def linear(self, x, weight, bias=None, act=0):
+        """y = act(x W^T + b) in fp32 on the FFMA GEMM (small heads, e.g. the topo-sort classifier).
+        act: 0 none, 1 erf-GELU, 2 QuickGELU, 3 tanh, 4 tanh-GELU."""
+        x = x.to(self.device, torch.float32).contiguous()
+        M, K = x.shape
+        N = weight.shape[0]
+        Np, Kp = (N + 3) // 4 * 4, (K + 15) // 16 * 16
+        w = torch.zeros(Np, Kp, device=self.device)
+        w[:N, :K] = weight.detach().to(self.device, torch.float32)
+        b = torch.zeros(Np, device=self.device)
+        if bias is not None:
+            b[:N] = bias.detach().to(self.device, torch.float32)
+        if Kp != K:
+            x = torch.nn.functional.pad(x, (0, Kp - K)).contiguous()
+        out = torch.empty(M, Np, device=self.device)
+        _lib.check(self.lib.msq_gemm(0, self._p(x), self._p(w), self._p(b), None, self._p(out), M, Np, Kp, act, self._stream()))
+        return out[:, :N]
+
+    def training_loss(self, batch: PairBatch, lam=0.6):
+        """BertForOrdering._forward loss value (modeling_bert.py:943-1174), forward only -> 0-d device tensor."""
+        b = batch.to(self.device)
+        B, P, Lt = b.input_ids.shape
+        gt = b.ground_truth.to(torch.int32).contiguous()
+        perm = torch.empty(B, b.n_steps, dtype=torch.int32, device=self.device)
+        loss = torch.zeros(1, device=self.device)
+        n_img = 0 if b.images is None else b.images.shape[0]
+        _lib.check(self.lib.msq_training_loss(self._h, self._p(b.input_ids), self._p(b.token_type_ids), self._p(b.attention_mask),
+                                              self._p(b.sep_positions), B, b.n_steps, Lt, self._p(b.images), n_img,
+                                              self._p(b.img_index), self._p(gt), self._p(b.pairwise_labels.contiguous()),
+                                              float(lam), self._p(perm), self._p(loss), self._stream()))
+        return loss[0]
+
     def beam_search(self, enc, n_steps, beam, trace=False):
         """beam_search_pointer for B manuals at once.  Returns perm [B,N] int32 (+ trace dict)."""
         f = lambda t: t.to(self.device, torch.float32).contiguous()

@@ -176,12 +176,45 @@ def gen_decode_full(ns):
     return out
 
 
+def gen_topo(ns, mm):
+    """LXRTModel in topo-sort classifier mode (lxrt/modeling.py:1502-1511, 1586-1594; used by
+    trainers/eval.py:topological_inference 509-520).  Inner weights = mm_tiny.pt's `bert.*`; only the
+    classifier head and the reference logits are stored."""
+    import contextlib
+    import io
+    torch.manual_seed(123)
+    ns.fake_clip._vit_cfg = dict(TINY_VIT)
+    ns.param.VISUAL_CONFIG.set_visual_dims(TINY_VIT["vision_width"], 4)
+    ns.param.VISUAL_CONFIG.clip_model_name = "ViT-B/32"
+    cfg = ns.lxrt.BertConfig(**TINY)
+    cfg.classifier_dropout = None  # attribute newer transformers' RobertaClassificationHead reads
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ns.lxrt.LXRTModel(cfg, multimodal_text_part=False, multimodal_img_part=False, cls_id=101, sep_id=102,
+                              max_story_length=5, clip_model_name="ViT-B/32", num_labels=2)
+    m.encoder.skip_last_layer = True
+    inner = {k[len("bert."):]: v for k, v in mm["sd"].items() if k.startswith("bert.")}
+    res = m.load_state_dict(inner, strict=False)
+    assert not res.unexpected_keys
+    with torch.no_grad():
+        m.classifier.out_proj.weight.normal_(0, 0.5)  # spread the logits (the 0.02 init gives ~1e-2 values)
+    m.eval()
+    seed, R = 61, 6
+    ids, labels, images = O.synthetic_manuals(1, 5, 16, vocab=1000, image_px=224, seed=seed)
+    inp = O.prepare_inputs(ids, labels, 5, images)
+    out = m(inp["input_ids"][0, :R], attention_mask=inp["attention_mask"][0, :R], token_type_ids=inp["token_type_ids"][0, :R],
+            visual_feats=inp["images"][0, :R])
+    return dict(seed=seed, R=R, logits=out[0].clone(), image_checksum=float(images.double().sum()),
+                classifier={k: v.clone() for k, v in m.state_dict().items() if k.startswith("classifier.")})
+
+
 def main():
     ns = rh.load()
     torch.save(gen_text(ns), os.path.join(HERE, "text_tiny.pt"))
-    torch.save(gen_mm(ns), os.path.join(HERE, "mm_tiny.pt"))
+    mm = gen_mm(ns)
+    torch.save(mm, os.path.join(HERE, "mm_tiny.pt"))
+    torch.save(gen_topo(ns, mm), os.path.join(HERE, "topo_tiny.pt"))
     torch.save(gen_decode_full(ns), os.path.join(HERE, "decode_full.pt"))
-    for f in ("text_tiny.pt", "mm_tiny.pt", "decode_full.pt"):
+    for f in ("text_tiny.pt", "mm_tiny.pt", "topo_tiny.pt", "decode_full.pt"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 

@@ -73,11 +73,30 @@ def test_beam_matches_generator_semantics():
     assert done == [] and remain == [0, 0, 0]
 
 
-def test_training_forward_is_declared_out_of_scope(golden_dir):
+def test_training_mode_is_declared_out_of_scope(golden_dir):
     g = torch.load(os.path.join(golden_dir, "text_tiny.pt"), weights_only=False)
     model, _ = _build(g, 5, 4)
+    model.train()
     with pytest.raises(NotImplementedError):
         model({"input_ids": None})
+
+
+@pytest.mark.gpu
+def test_validation_loss_matches_reference(golden_dir):
+    """BertForOrdering._forward loss value (modeling_bert.py:943-1174) against the reference's own number."""
+    g = torch.load(os.path.join(golden_dir, "text_tiny.pt"), weights_only=False)
+    lc = g["loss_case"]
+    model, args = _build(g, 5, 4, "cuda")
+    model.load_state_dict(g["sd"], strict=False)
+    model = model.cuda().eval()
+    for mod in model.modules():
+        mod.precise = True
+    model.tokenizer = Tok()
+    (loss,) = model({"input_ids": lc["ids"], "attention_mask": torch.ones_like(lc["ids"]), "labels": lc["labels"]})
+    assert abs(loss.item() - lc["loss"].item()) < 1e-5, (loss.item(), lc["loss"].item())
+    model.precise = False   # bf16 encoder: same loss within the bf16 bound
+    (loss16,) = model({"input_ids": lc["ids"], "attention_mask": torch.ones_like(lc["ids"]), "labels": lc["labels"]})
+    assert abs(loss16.item() - lc["loss"].item()) < 2e-2
 
 
 def test_cal_result_matches_reference_formula():
@@ -208,3 +227,33 @@ def test_dropin_reproduces_reference_fixtures(golden_dir, name):
         else:
             seq, pooled = model.bert(ids2, attention_mask=am2, token_type_ids=tt2)
             assert (pooled.cpu() - c["enc"]["cls"]).abs().max() < 4e-5
+
+
+@pytest.mark.gpu
+def test_lxrt_topo_sort_classifier_mode(golden_dir):
+    """LXRTModel(..., num_labels=2) as the pairwise classifier of trainers/eval.py:topological_inference
+    (lxrt/modeling.py:1502-1511, 1586-1594): logits against the reference's."""
+    mm = torch.load(os.path.join(golden_dir, "mm_tiny.pt"), weights_only=False)
+    t = torch.load(os.path.join(golden_dir, "topo_tiny.pt"), weights_only=False)
+    c = mm["cfg"]
+    model = LXRTModel(LxrtBertConfig(c["vocab_size_or_config_json_file"], hidden_size=c["hidden_size"],
+                                     num_hidden_layers=c["num_hidden_layers"], num_attention_heads=c["num_attention_heads"],
+                                     intermediate_size=c["intermediate_size"], max_position_embeddings=c["max_position_embeddings"]),
+                      clip_model_name="ViT-B/32", clip_config=mm["vit"], cls_id=101, sep_id=102, max_story_length=5, num_labels=2)
+    sd = {k[len("bert."):]: v for k, v in mm["sd"].items() if k.startswith("bert.")}
+    sd.update(t["classifier"])
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all("proj" in k or "box_" in k for k in missing), (missing, unexpected)
+    model = model.cuda().eval()
+    model.precise = True
+    ids, labels, images = O.synthetic_manuals(1, 5, 16, vocab=1000, image_px=224, seed=t["seed"])
+    assert abs(float(images.double().sum()) - t["image_checksum"]) < 1e-6
+    inp = O.prepare_inputs(ids, labels, 5, images)
+    R = t["R"]
+    (logits,) = model(inp["input_ids"][0, :R].cuda(), attention_mask=inp["attention_mask"][0, :R].cuda(),
+                      token_type_ids=inp["token_type_ids"][0, :R].cuda(), visual_feats=inp["images"][0, :R].cuda())
+    assert (logits.cpu() - t["logits"]).abs().max() < 2e-5
+    loss, _ = model(inp["input_ids"][0, :R].cuda(), attention_mask=inp["attention_mask"][0, :R].cuda(),
+                    token_type_ids=inp["token_type_ids"][0, :R].cuda(), visual_feats=inp["images"][0, :R].cuda(),
+                    labels=torch.zeros(R, dtype=torch.long))
+    assert abs(loss.item() - torch.nn.functional.cross_entropy(t["logits"], torch.zeros(R, dtype=torch.long)).item()) < 2e-5
