@@ -312,3 +312,63 @@ def test_full_size_batch_invariance_and_chunking():
         assert eng.order(ids[sl], labels[sl], N, W, images[sl]) == full[sl]
     hp = eng.order_host(eng.prepare(ids, labels, N, images), W)
     assert hp.tolist() == full
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases of the decode / host boundary
+# ---------------------------------------------------------------------------------------------
+
+def _decode_engine(H=768):
+    cfg = dict(hidden_size=H, num_hidden_layers=1, num_attention_heads=H // 64, intermediate_size=64, vocab_size=64,
+               max_position_embeddings=8, vit=None, para_ff=64)
+    sd = synth.full_state_dict(cfg, None, seed=0, ff=64)
+    return _engine(sd, cfg, precise=True), sd
+
+
+@pytest.mark.parametrize("N,W", [(2, 1), (2, 16), (3, 16), (4, 16), (16, 1), (16, 16), (9, 3)])
+def test_decode_edge_sizes_vs_oracle(N, W):
+    """smallest / largest manuals and beams wider than the number of valid candidates (the reference then
+    selects masked candidates with cost ~1e9, generator.py:19-22): final permutation equals the oracle's."""
+    eng, sd = _decode_engine()
+    for seed in (1, 2, 3):
+        enc = synth.synthetic_encode(N, 768, seed=900 + seed + N, B=3)
+        perm = eng.beam_search(enc, N, W).cpu().tolist()
+        for b in range(3):
+            assert perm[b] == O.beam_search(sd, enc, N, W, manual=b), (N, W, seed, b)
+            assert sorted(perm[b]) == list(range(N))
+
+
+def test_decode_rejects_out_of_range():
+    eng, _ = _decode_engine()
+    enc = synth.synthetic_encode(5, 768, seed=1)
+    with pytest.raises(RuntimeError):
+        eng.beam_search(enc, 5, 17)          # beam > 16
+    enc1 = synth.synthetic_encode(17, 768, seed=1)
+    with pytest.raises(RuntimeError):
+        eng.beam_search(enc1, 17, 4)         # N > 16
+
+
+def test_empty_batch_is_a_no_op():
+    eng, _ = _decode_engine()
+    enc = synth.synthetic_encode(5, 768, seed=1, B=1)
+    empty = {k: (v[:0] if v.shape[0] == 1 else v[:, :0]) for k, v in enc.items()}
+    assert eng.beam_search(empty, 5, 4).shape == (0, 5)
+
+
+def test_roberta_style_token_types_and_ragged_batch():
+    """cls_id == 0 (RoBERTa) -> all-zero token types (process_inputs_for_berson.py:205-208); a ragged batch of
+    manuals (different step lengths -> padded pair rows + attention masks) through the device path."""
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "text_tiny.pt"), weights_only=False)
+    eng = _engine(g["sd"], _cfg_from_golden(g), True)
+    rag = [c for c in g["cases"] if c["kind"] == "ragged" and c["N"] == 5]
+    full = [c for c in g["cases"] if c["kind"] == "full" and c["N"] == 5 and c["W"] == 4]
+    # pad the ragged manual's id row to the length of the full ones and batch them together
+    L = max(c["ids"].shape[1] for c in rag + full)
+    ids = torch.stack([torch.nn.functional.pad(c["ids"][0], (0, L - c["ids"].shape[1])) for c in rag + full])
+    labels = torch.cat([c["labels"] for c in rag + full])
+    perms = eng.order(ids, labels, 5, 4)
+    ocfg = dict(num_hidden_layers=2, num_attention_heads=2, vit=None)
+    assert perms == O.order_manuals(g["sd"], ocfg, ids, labels, 5, 4)
+    rob = ids.clone().masked_fill(ids == 0, 1).masked_fill(ids == 101, 0)   # <s> = 0, <pad> = 1
+    pb = eng.prepare(rob, labels, 5, cls_id=0, sep_id=102, pad_id=1)
+    assert int(pb.token_type_ids.sum()) == 0 and int((pb.input_ids == 0).sum()) == 2 * 20 * len(labels)
