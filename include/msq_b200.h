@@ -116,6 +116,15 @@ int msq_decode_step(msq_model* m, const float* prev_y_dev, const float* h_dev, c
                     const float* hist1_dev, const float* hist2_dev, const uint8_t* l1_mask_dev, const uint8_t* l2_mask_dev,
                     int32_t Wb, int32_t N, float* h_out_dev, float* c_out_dev, float* logp_out_dev, void* stream);
 
+/* models/pointer_module.py, p1 variant: LSTMPointerModule.forward (pointer_module.py:690-749) over LSTMDecoder /
+ * LSTMAttention (616-678).  enc [B,N,H] = hidden states at the [CLS] positions, cls [B,H] = sequence_output[:,0],
+ * y [B,N] int64 labels; W1,W2 [U,H], V [U], W_ih [4H,2H], W_hh [4H,H], biases [4H] (torch LSTM layout).
+ * preds [B,N] (float, as the reference stores them), ce_scratch [B], loss = sum_t mean_b CE_t / B (1 float). */
+int msq_pointer_p1(const float* enc_dev, const float* cls_dev, const int64_t* y_dev, const float* w1_dev, const float* w2_dev,
+                   const float* v_dev, const float* wih_dev, const float* whh_dev, const float* bih_dev, const float* bhh_dev,
+                   int64_t B, int32_t N, int32_t H, int32_t U, float* preds_dev, float* ce_scratch_dev, float* loss_dev,
+                   void* stream);
+
 /* ---- whole path on device-resident inputs: encode + beam search ------------------------------- */
 int msq_order_manuals_dev(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev,
                           const int64_t* sep_dev, int64_t B, int32_t N, int32_t Lt, const float* images_dev,

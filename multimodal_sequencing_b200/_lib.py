@@ -38,6 +38,7 @@ SIGNATURES = {
     "msq_training_loss": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P, _P, _F, _P, _P, _P]),
     "msq_beam_search": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
     "msq_decode_step": (C.c_int, [_P] * 12 + [_I32, _I32, _P, _P, _P, _P]),
+    "msq_pointer_p1": (C.c_int, [_P] * 10 + [_I64, _I32, _I32, _I32, _P, _P, _P, _P]),
     "msq_order_manuals_dev": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _I32, _P, _P]),
     "msq_order_manuals_host": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _I32, _P, _P]),
     "msq_gemm": (C.c_int, [_I32, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P]),

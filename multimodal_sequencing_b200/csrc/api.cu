@@ -26,6 +26,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MSQ_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
 
 // ---- per-launch event profile (bench.py roofline): events bracket each tcgen05 GEMM launch on its stream
 struct Profile {
@@ -190,6 +195,7 @@ static int make_lin(msq_model* m, const float* w, const float* b, int N, int K, 
 
 __global__ void concat_rows_kernel(const float* a, const float* b, const float* c, int64_t na, int64_t nb, int64_t nc,
                                    float* out) {
+  pdl_sync();
   const int64_t total = na + nb + nc;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = i < na ? a[i] : (i < na + nb ? b[i - na] : c[i - na - nb]);
@@ -198,7 +204,7 @@ static int concat3(msq_model* m, const float* a, const float* b, const float* c,
                    const float** out, cudaStream_t st) {
   float* p;
   MSQ_TRY(dev_alloc(m, (size_t)(na + nb + nc), &p));
-  concat_rows_kernel<<<256, 256, 0, st>>>(a, b, c, na, nb, nc, p);
+  MSQ_CUDA(launch_k(concat_rows_kernel, dim3(256), dim3(256), 0, st, a, b, c, na, nb, nc, p));
   MSQ_LAUNCH_CHECK();
   *out = p;
   return MSQ_OK;
@@ -208,6 +214,7 @@ static int concat3(msq_model* m, const float* a, const float* b, const float* c,
 __global__ void pack_lstm_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b_ih,
                                  const float* __restrict__ b_hh, int H, float* __restrict__ wih_perm,
                                  float* __restrict__ bias_perm, float* __restrict__ whh_t) {
+  pdl_sync();
   const int64_t total = (int64_t)4 * H * H;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int row = (int)(i / H), k = (int)(i % H);  // row = g*H + u in torch's (i,f,g,o) order
@@ -218,6 +225,7 @@ __global__ void pack_lstm_kernel(const float* __restrict__ w_ih, const float* __
   }
 }
 __global__ void transpose_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst) {
+  pdl_sync();
   const int64_t total = (int64_t)rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i % cols);
@@ -226,6 +234,7 @@ __global__ void transpose_kernel(const float* __restrict__ src, int rows, int co
 }
 // pw_k.weight [H, 4*(H+2)] -> [4H, Kp]: row blk*H + o, col c  <- w[o, blk*(H+2) + c]
 __global__ void pack_pwk_kernel(const float* __restrict__ w, int H, int Kp, float* __restrict__ dst) {
+  pdl_sync();
   const int D = H + 2;
   const int64_t total = (int64_t)4 * H * Kp;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -234,12 +243,14 @@ __global__ void pack_pwk_kernel(const float* __restrict__ w, int H, int Kp, floa
   }
 }
 __global__ void mask_add_kernel(const int64_t* __restrict__ mask, int64_t n, float* __restrict__ out) {
+  pdl_sync();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = (1.0f - (float)mask[i]) * -10000.0f;
 }
 // R0[b,i,j,:] = [cls_mat ; softmax(score_mat) ; 0]  (rela_encode, modeling_bert.py:919-925)
 __global__ void build_r0_kernel(const float* __restrict__ cls_mat, const float* __restrict__ score_mat, int64_t cells, int H,
                                 int Kp, float* __restrict__ r0) {
+  pdl_sync();
   const int64_t cell = blockIdx.x;
   if (cell >= cells) return;
   const float z0 = score_mat[cell * 2], z1 = score_mat[cell * 2 + 1];
@@ -249,6 +260,7 @@ __global__ void build_r0_kernel(const float* __restrict__ cls_mat, const float* 
 }
 // sents_ext[b, n, :] = sents[b, n, :] for n < N, zeros for n == N
 __global__ void sents_ext_kernel(const float* __restrict__ sents, int64_t B, int N, int H, float* __restrict__ out) {
+  pdl_sync();
   const int64_t total = B * (N + 1) * (int64_t)H;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int d = (int)(i % H);
@@ -258,6 +270,7 @@ __global__ void sents_ext_kernel(const float* __restrict__ sents, int64_t B, int
   }
 }
 __global__ void f32_to_bf16_kernel(const float* __restrict__ s, bf16* __restrict__ d, int64_t n) {
+  pdl_sync();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     d[i] = __float2bfloat16_rn(s[i]);
 }
@@ -266,6 +279,7 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ s, bf16* __restrict
 // (modeling_bert.py:1140-1174).  rel6 rows hold the pairwise_relationship logits in columns 0..1.
 __global__ void training_loss_kernel(const float* __restrict__ nll, const float* __restrict__ rel6, const int64_t* __restrict__ labels,
                                      int64_t B, int N, float lam, float* __restrict__ out) {
+  pdl_sync();
   __shared__ float sh[256];
   const int P = N * (N - 1);
   float a = 0.f;
@@ -540,12 +554,11 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
     MSQ_TRY(dev_alloc(m, (size_t)4 * H * H, &whh_t));
     MSQ_TRY(dev_alloc(m, (size_t)H * H, &wq_t));
     MSQ_TRY(dev_alloc(m, (size_t)4 * H * m->Kp, &wpw4));
-    pack_lstm_kernel<<<512, 256, 0, st>>>(W("decoder.weight_ih_l0", (int64_t)4 * H * H), W("decoder.weight_hh_l0", (int64_t)4 * H * H),
-                                          W("decoder.bias_ih_l0", 4 * H), W("decoder.bias_hh_l0", 4 * H), H, wih_perm, bias_perm, whh_t);
+    MSQ_CUDA(launch_k(pack_lstm_kernel, dim3(512), dim3(256), 0, st, W("decoder.weight_ih_l0", (int64_t)4 * H * H), W("decoder.weight_hh_l0", (int64_t)4 * H * H), W("decoder.bias_ih_l0", 4 * H), W("decoder.bias_hh_l0", 4 * H), H, wih_perm, bias_perm, whh_t));
     MSQ_LAUNCH_CHECK();
-    transpose_kernel<<<256, 256, 0, st>>>(W("query_linear.weight", (int64_t)H * H), H, H, wq_t);
+    MSQ_CUDA(launch_k(transpose_kernel, dim3(256), dim3(256), 0, st, W("query_linear.weight", (int64_t)H * H), H, H, wq_t));
     MSQ_LAUNCH_CHECK();
-    pack_pwk_kernel<<<512, 256, 0, st>>>(W("pw_k.weight", (int64_t)H * 4 * (H + 2)), H, m->Kp, wpw4);
+    MSQ_CUDA(launch_k(pack_pwk_kernel, dim3(512), dim3(256), 0, st, W("pw_k.weight", (int64_t)H * 4 * (H + 2)), H, m->Kp, wpw4));
     MSQ_LAUNCH_CHECK();
     m->xg_lin.w32 = wih_perm; m->xg_lin.b = bias_perm; m->xg_lin.N = 4 * H; m->xg_lin.K = H; m->xg_lin.ld = H;
     m->t4_lin.w32 = wpw4; m->t4_lin.b = nullptr; m->t4_lin.N = 4 * H; m->t4_lin.K = m->Kp; m->t4_lin.ld = m->Kp;
@@ -659,7 +672,7 @@ static int run_inner(msq_model* m, const int64_t* ids, const int64_t* tt, const 
   MSQ_REQUIRE(Lt <= c.max_pos, "Lt=%d exceeds max_position_embeddings=%d", Lt, c.max_pos);
   const int64_t Mj = R * Lj;
   MSQ_TRY(embed_ln<T>(ids, tt, R, Lt, Lj, H, m->word, m->pos, m->type, m->emb_ln.g, m->emb_ln.b, 1e-12f, jb.x, (T*)jb.xt, st));
-  mask_add_kernel<<<ceil_div(R * Lt, 256), 256, 0, st>>>(mask, R * Lt, jb.mask_add);
+  MSQ_CUDA(launch_k(mask_add_kernel, dim3(ceil_div(R * Lt, 256)), dim3(256), 0, st, mask, R * Lt, jb.mask_add));
   MSQ_LAUNCH_CHECK();
   if (mm) {
     MSQ_TRY(run_vit<T>(m, img_index, R, vb, st));
@@ -753,7 +766,7 @@ static int run_decode(msq_model* m, const float* sents, const float* key, const 
                       float* xg, float* t4, int64_t B, int N, int beam, int32_t* perm, int32_t* tr_ix, float* tr_cost,
                       float* tr_logp, cudaStream_t st, const int32_t* forced = nullptr, float* final_cost = nullptr) {
   const int H = m->cfg.hidden;
-  sents_ext_kernel<<<ceil_div(B * (N + 1) * (int64_t)H, 256), 256, 0, st>>>(sents, B, N, H, sents_ext);
+  MSQ_CUDA(launch_k(sents_ext_kernel, dim3(ceil_div(B * (N + 1) * (int64_t)H, 256)), dim3(256), 0, st, sents, B, N, H, sents_ext));
   MSQ_LAUNCH_CHECK();
   MSQ_TRY(run_gemm32(sents_ext, H, m->xg_lin, nullptr, 0, xg, 4 * H, B * (N + 1), ACT_NONE, st));
   MSQ_TRY(run_gemm32(r0, m->Kp, m->t4_lin, nullptr, 0, t4, 4 * H, B * N * N, ACT_NONE, st));
@@ -836,7 +849,7 @@ static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const i
     float* nll = hb.pn;  // [B] scratch (paragraph buffers are free again)
     MSQ_TRY(run_decode(m, hb.sents, hb.key, hb.h0, hb.r0, hb.sents_ext, hb.xg, hb.t4, B, N, 1, perm, nullptr, nullptr, nullptr, st, forced,
                        nll));
-    training_loss_kernel<<<1, 256, 0, st>>>(nll, hb.rel6, pair_labels, B, N, lam, loss_out);
+    MSQ_CUDA(launch_k(training_loss_kernel, dim3(1), dim3(256), 0, st, nll, hb.rel6, pair_labels, B, N, lam, loss_out));
     MSQ_LAUNCH_CHECK();
   }
   return MSQ_OK;
@@ -954,7 +967,7 @@ extern "C" int msq_beam_search(msq_model* m, const float* sents_dev, const float
     if (pass == 0) MSQ_TRY(m->ws.reserve(p.need + 4096, st));
   }
   if (B == 0) return MSQ_OK;
-  build_r0_kernel<<<(unsigned)(B * N * N), 128, 0, st>>>(cls_mat_dev, score_mat_dev, B * N * N, H, m->Kp, r0);
+  MSQ_CUDA(launch_k(build_r0_kernel, dim3((unsigned)(B * N * N)), dim3(128), 0, st, cls_mat_dev, score_mat_dev, B * N * N, H, m->Kp, r0));
   MSQ_LAUNCH_CHECK();
   return run_decode(m, sents_dev, key_dev, h0_dev, r0, sents_ext, xg, t4, B, N, beam, perm_dev, trace_ix_dev, trace_cost_dev,
                     trace_logp_dev, st);
@@ -994,6 +1007,16 @@ extern "C" int msq_decode_step(msq_model* m, const float* prev_y_dev, const floa
   g.M = (int64_t)Wb * N; g.N = H; g.K = m->Kp4; g.lda = m->Kp4; g.ldw = m->Kp4; g.ldc = H; g.ldr = 0; g.act = ACT_NONE;
   MSQ_TRY((gemm_simt<float, float>(g, st)));
   return decode_step_score(q, keys, key0_dev, pointed_mask_dev, m->dec.wt, m->dec.bt, Wb, N, H, logp_out_dev, st);
+}
+
+// models/pointer_module.py p1: LSTMPointerModule.forward (690-749).  Stand-alone: weights are passed directly.
+extern "C" int msq_pointer_p1(const float* enc_dev, const float* cls_dev, const int64_t* y_dev, const float* w1_dev,
+                              const float* w2_dev, const float* v_dev, const float* wih_dev, const float* whh_dev,
+                              const float* bih_dev, const float* bhh_dev, int64_t B, int32_t N, int32_t H, int32_t U,
+                              float* preds_dev, float* ce_scratch_dev, float* loss_dev, void* stream) {
+  MSQ_REQUIRE(enc_dev && cls_dev && y_dev && preds_dev && ce_scratch_dev && loss_dev, "null argument");
+  return pointer_p1(enc_dev, cls_dev, y_dev, w1_dev, w2_dev, v_dev, wih_dev, whh_dev, bih_dev, bhh_dev, B, N, H, U, preds_dev,
+                    ce_scratch_dev, loss_dev, (cudaStream_t)stream);
 }
 
 extern "C" int msq_order_manuals_host(msq_model* m, const int64_t* ids_host, const int64_t* tt_host, const int64_t* mask_host,
@@ -1076,7 +1099,7 @@ extern "C" int msq_attention(int32_t dtype, const void* qkv_dev, int64_t R, int3
 
 extern "C" int msq_f32_to_bf16(const float* src_dev, void* dst_dev, int64_t n, void* stream) {
   if (n == 0) return MSQ_OK;
-  f32_to_bf16_kernel<<<(int)min((int64_t)148 * 8, (n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src_dev, (bf16*)dst_dev, n);
+  MSQ_CUDA(launch_k(f32_to_bf16_kernel, dim3((int)min((int64_t)148 * 8, (n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, src_dev, (bf16*)dst_dev, n));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }

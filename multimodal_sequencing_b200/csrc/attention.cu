@@ -20,6 +20,7 @@ template <typename T>
 __global__ void __launch_bounds__(AT_WARPS * 32) attention_simt_kernel(const T* __restrict__ qkv, int L, int heads,
                                                                        float scale, const float* __restrict__ mask_add,
                                                                        int mask_ld, int mask_len, T* __restrict__ ctx) {
+  pdl_sync();
   extern __shared__ __align__(16) float sm[];
   const int r = blockIdx.x / heads, h = blockIdx.x % heads;
   const int ld = 3 * heads * AT_D;
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(KP) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_sync();  // barrier init / TMEM allocation above overlap the previous kernel's tail
   int any_mask = 0;
   for (int key = tid; key < KP; key += 256) {
     float m = -INFINITY;
@@ -310,8 +312,7 @@ static int launch_attention_tc(const bf16* qkv, int64_t R, int L, int heads, flo
     MSQ_CUDA(cudaFuncSetAttribute(attention_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  attention_tc_kernel<KP><<<(unsigned)(R * heads), 256, SMEM, st>>>(mq, mkv, L, heads, scale * 1.4426950408889634f, mask_add,
-                                                                    mask_ld, mask_len, ctx);
+  MSQ_CUDA(launch_k(attention_tc_kernel<KP>, dim3((unsigned)(R * heads)), dim3(256), SMEM, st, mq, mkv, L, heads, scale * 1.4426950408889634f, mask_add, mask_ld, mask_len, ctx));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -343,8 +344,7 @@ int attention(const T* qkv, int64_t R, int L, int heads, int dhead, float scale,
     MSQ_CUDA(cudaFuncSetAttribute(attention_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  attention_simt_kernel<T><<<(unsigned)(R * heads), AT_WARPS * 32, smem, st>>>(qkv, L, heads, scale, key_mask_add, mask_ld,
-                                                                               mask_len, ctx);
+  MSQ_CUDA(launch_k(attention_simt_kernel<T>, dim3((unsigned)(R * heads)), dim3(AT_WARPS * 32), smem, st, qkv, L, heads, scale, key_mask_add, mask_ld, mask_len, ctx));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }

@@ -26,6 +26,7 @@ constexpr int DC_THREADS = 256;
 
 template <int ROWS>
 __global__ void __launch_bounds__(DC_THREADS) beam_search_kernel(DecodeWeights w, DecodeIO io, int G) {
+  pdl_sync();
   extern __shared__ __align__(16) float smf[];
   const int H = io.H, N = io.N, W = io.W;
   float* hs = smf;                 // [ROWS][H]  h (input of the step), later q
@@ -275,7 +276,7 @@ static int launch_beam(const DecodeWeights& w, const DecodeIO& io, int G, cudaSt
     MSQ_CUDA(cudaFuncSetAttribute(beam_search_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  beam_search_kernel<ROWS><<<ceil_div(io.B, G), DC_THREADS, smem, st>>>(w, io, G);
+  MSQ_CUDA(launch_k(beam_search_kernel<ROWS>, dim3(ceil_div(io.B, G)), dim3(DC_THREADS), smem, st, w, io, G));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -305,6 +306,7 @@ int beam_search(const DecodeWeights& w, const DecodeIO& io, cudaStream_t st) {
 
 // rela_vec.masked_fill_(rela_mask == 0, 0)   (in place, 1385)
 __global__ void step_zero_rela_kernel(float* __restrict__ rela, const uint8_t* __restrict__ rela_mask, int64_t cells, int D) {
+  pdl_sync();
   const int64_t cell = blockIdx.x;
   if (cell >= cells || rela_mask[cell]) return;
   for (int d = threadIdx.x; d < D; d += blockDim.x) rela[cell * D + d] = 0.f;
@@ -314,6 +316,7 @@ __global__ void step_zero_rela_kernel(float* __restrict__ rela, const uint8_t* _
 __global__ void __launch_bounds__(256) step_pw_kernel(const float* __restrict__ rela, const float* __restrict__ hist1,
                                                       const float* __restrict__ hist2, const uint8_t* __restrict__ l1,
                                                       const uint8_t* __restrict__ l2, int N, int D, int Kp4, float* __restrict__ pw) {
+  pdl_sync();
   const int b = blockIdx.x / N, k = blockIdx.x % N;
   float* out = pw + (int64_t)blockIdx.x * Kp4;
   const int64_t base = (int64_t)b * N * N;
@@ -337,6 +340,7 @@ __global__ void __launch_bounds__(256) step_pw_kernel(const float* __restrict__ 
 // gates [Wb,4H] in torch order (i|f|g|o) -> h', c'
 __global__ void step_lstm_kernel(const float* __restrict__ gates, const float* __restrict__ c_in, int64_t Wb, int H,
                                  float* __restrict__ h_out, float* __restrict__ c_out) {
+  pdl_sync();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Wb * H) return;
   const int64_t b = i / H;
@@ -354,6 +358,7 @@ __global__ void __launch_bounds__(256) step_score_kernel(const float* __restrict
                                                          const float* __restrict__ key0, const uint8_t* __restrict__ pointed,
                                                          const float* __restrict__ wt, float bt, int N, int H,
                                                          float* __restrict__ logp) {
+  pdl_sync();
   __shared__ float e[DC_MAXN];
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = warp; k < N; k += blockDim.x >> 5) {
@@ -376,20 +381,141 @@ __global__ void __launch_bounds__(256) step_score_kernel(const float* __restrict
 int decode_step_parts(const StepIO& io, cudaStream_t st) {
   MSQ_REQUIRE(io.N >= 2 && io.N <= DC_MAXN, "decode_step: N=%d out of range", io.N);
   const int D = io.H + 2;
-  step_zero_rela_kernel<<<(unsigned)((int64_t)io.Wb * io.N * io.N), 128, 0, st>>>(io.rela, io.rela_mask, (int64_t)io.Wb * io.N * io.N, D);
+  MSQ_CUDA(launch_k(step_zero_rela_kernel, dim3((unsigned)((int64_t)io.Wb * io.N * io.N)), dim3(128), 0, st, io.rela, io.rela_mask, (int64_t)io.Wb * io.N * io.N, D));
   MSQ_LAUNCH_CHECK();
-  step_pw_kernel<<<(unsigned)(io.Wb * io.N), 256, 0, st>>>(io.rela, io.hist1, io.hist2, io.l1, io.l2, io.N, D, io.Kp4, io.pw);
+  MSQ_CUDA(launch_k(step_pw_kernel, dim3((unsigned)(io.Wb * io.N)), dim3(256), 0, st, io.rela, io.hist1, io.hist2, io.l1, io.l2, io.N, D, io.Kp4, io.pw));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
 int decode_step_lstm(const float* gates, const float* c_in, int64_t Wb, int H, float* h_out, float* c_out, cudaStream_t st) {
-  step_lstm_kernel<<<ceil_div(Wb * H, 256), 256, 0, st>>>(gates, c_in, Wb, H, h_out, c_out);
+  MSQ_CUDA(launch_k(step_lstm_kernel, dim3(ceil_div(Wb * H, 256)), dim3(256), 0, st, gates, c_in, Wb, H, h_out, c_out));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
 int decode_step_score(const float* q, const float* keys, const float* key0, const uint8_t* pointed, const float* wt, float bt,
                       int64_t Wb, int N, int H, float* logp, cudaStream_t st) {
-  step_score_kernel<<<(unsigned)Wb, 256, 0, st>>>(q, keys, key0, pointed, wt, bt, N, H, logp);
+  MSQ_CUDA(launch_k(step_score_kernel, dim3((unsigned)Wb), dim3(256), 0, st, q, keys, key0, pointed, wt, bt, N, H, logp));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// models/pointer_module.py p1 path: LSTMPointerModule.forward (690-749) over LSTMDecoder (651-678) and
+// LSTMAttention (616-648).  Dead code in the reference but named by the scope: greedy
+// pointer decoding WITHOUT a permutation mask, additive attention V.tanh(W1 e + W2 h), LSTM input
+// [context ; previous pick], cross-entropy against y at every step.  One CTA per manual.
+// ---------------------------------------------------------------------------------------------------
+constexpr int PM_MAXN = 16, PM_MAXU = 32;
+
+__global__ void __launch_bounds__(256) pointer_p1_kernel(const float* __restrict__ enc, const float* __restrict__ cls,
+                                                         const int64_t* __restrict__ y, const float* __restrict__ W1,
+                                                         const float* __restrict__ W2, const float* __restrict__ V,
+                                                         const float* __restrict__ Wih, const float* __restrict__ Whh,
+                                                         const float* __restrict__ bih, const float* __restrict__ bhh, int N, int H,
+                                                         int U, float* __restrict__ preds, float* __restrict__ ce_sum) {
+  pdl_sync();
+  extern __shared__ float sm[];
+  float* h = sm;            // [H]
+  float* c = h + H;         // [H]
+  float* x = c + H;         // [2H]  = [context ; dec_in]
+  float* gates = x + 2 * H; // [4H]
+  __shared__ float e1[PM_MAXN][PM_MAXU], e2[PM_MAXU], uj[PM_MAXN], aj[PM_MAXN];
+  __shared__ int pred;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  const float* eb = enc + (int64_t)b * N * H;
+  for (int d = tid; d < H; d += blockDim.x) {
+    h[d] = c[d] = cls[(int64_t)b * H + d];  // hs = (encoder_cls, encoder_cls) (700-701)
+    x[H + d] = cls[(int64_t)b * H + d];     // dec_in = encoder_cls (712)
+  }
+  for (int nu = warp; nu < N * U; nu += nw) {  // W1 e_n is step independent
+    const int n = nu / U, u = nu % U;
+    float a = 0.f;
+    for (int d = lane; d < H; d += 32) a = fmaf(W1[(int64_t)u * H + d], eb[(int64_t)n * H + d], a);
+    a = warp_sum(a);
+    if (lane == 0) e1[n][u] = a;
+  }
+  __syncthreads();
+  float ce = 0.f;
+  for (int t = 0; t < N; ++t) {
+    for (int u = warp; u < U; u += nw) {  // W2 h_t with the hidden state BEFORE this step's LSTM update (663)
+      float a = 0.f;
+      for (int d = lane; d < H; d += 32) a = fmaf(W2[(int64_t)u * H + d], h[d], a);
+      a = warp_sum(a);
+      if (lane == 0) e2[u] = a;
+    }
+    __syncthreads();
+    if (tid < N) {
+      float a = 0.f;
+      for (int u = 0; u < U; ++u) a = fmaf(V[u], tanhf(e1[tid][u] + e2[u]), a);
+      uj[tid] = a;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float mx = -INFINITY, s = 0.f;
+      int arg = 0;
+      for (int n = 0; n < N; ++n) if (uj[n] > mx) { mx = uj[n]; arg = n; }
+      for (int n = 0; n < N; ++n) { aj[n] = expf(uj[n] - mx); s += aj[n]; }
+      for (int n = 0; n < N; ++n) aj[n] /= s;
+      pred = arg;                                                  // softmax(att_w).argmax (726)
+      ce += -((uj[(int)y[(int64_t)b * N + t]] - mx) - logf(s));    // F.cross_entropy(att_w, y[:, t]) (742)
+      preds[(int64_t)b * N + t] = (float)arg;
+    }
+    __syncthreads();
+    for (int d = tid; d < H; d += blockDim.x) {
+      float a = 0.f;
+      for (int n = 0; n < N; ++n) a = fmaf(aj[n], eb[(int64_t)n * H + d], a);
+      x[d] = a;  // di_prime (645-646); x[H..2H) still holds the current dec_in
+    }
+    __syncthreads();
+    for (int row = warp; row < 4 * H; row += nw) {  // gates = W_ih [di ; x] + b_ih + W_hh h + b_hh
+      float a = 0.f;
+      const float* wi = Wih + (int64_t)row * 2 * H;
+      const float* wh = Whh + (int64_t)row * H;
+      for (int d = lane; d < 2 * H; d += 32) a = fmaf(wi[d], x[d], a);
+      for (int d = lane; d < H; d += 32) a = fmaf(wh[d], h[d], a);
+      a = warp_sum(a);
+      if (lane == 0) gates[row] = a + bih[row] + bhh[row];
+    }
+    __syncthreads();
+    for (int d = tid; d < H; d += blockDim.x) {
+      const float ig = 1.f / (1.f + expf(-gates[d])), fg = 1.f / (1.f + expf(-gates[H + d]));
+      const float gg = tanhf(gates[2 * H + d]), og = 1.f / (1.f + expf(-gates[3 * H + d]));
+      const float c2 = fg * c[d] + ig * gg;
+      c[d] = c2;
+      h[d] = og * tanhf(c2);
+      x[H + d] = eb[(int64_t)pred * H + d];  // next dec_in = encoder_out[pred] (735-737)
+    }
+    __syncthreads();
+  }
+  if (tid == 0) ce_sum[b] = ce;
+}
+
+// batch_loss = (sum_t mean_b CE_t) / B   (742, 747: the reference divides by the batch size twice)
+__global__ void pointer_p1_loss_kernel(const float* __restrict__ ce_sum, int64_t B, float* __restrict__ loss) {
+  pdl_sync();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int64_t b = 0; b < B; ++b) s += ce_sum[b];
+    loss[0] = s / (float)B / (float)B;
+  }
+}
+
+int pointer_p1(const float* enc, const float* cls, const int64_t* y, const float* W1, const float* W2, const float* V,
+               const float* Wih, const float* Whh, const float* bih, const float* bhh, int64_t B, int N, int H, int U, float* preds,
+               float* ce_scratch, float* loss, cudaStream_t st) {
+  MSQ_REQUIRE(N >= 1 && N <= PM_MAXN && U >= 1 && U <= PM_MAXU && H <= 2048, "pointer_p1: N=%d U=%d H=%d out of range", N, U, H);
+  if (B == 0) return MSQ_OK;
+  const size_t smem = (size_t)8 * H * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    MSQ_CUDA(cudaFuncSetAttribute(pointer_p1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  MSQ_CUDA(launch_k(pointer_p1_kernel, dim3((unsigned)B), dim3(256), smem, st, enc, cls, y, W1, W2, V, Wih, Whh, bih, bhh, N, H, U, preds,
+                    ce_scratch));
+  MSQ_LAUNCH_CHECK();
+  MSQ_CUDA(launch_k(pointer_p1_loss_kernel, dim3(1), dim3(32), 0, st, (const float*)ce_scratch, B, loss));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, float* __restrict__ out_f, T* __restrict__ out_t,
                                                         int in_group, int out_group, int out_off) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -91,8 +92,7 @@ int layernorm(const float* x, int64_t rows, int H, const float* gamma, const flo
               T* out_t, int in_group, int out_group, int out_off, cudaStream_t st) {
   MSQ_REQUIRE(H % 128 == 0 && H <= LN_MAX_VEC * 128, "layernorm: H=%d must be a multiple of 128 and <= 1024", H);
   if (rows == 0) return MSQ_OK;
-  layernorm_kernel<T><<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, H, gamma, beta, eps, out_f, out_t, in_group, out_group,
-                                                         out_off);
+  MSQ_CUDA(launch_k(layernorm_kernel<T>, dim3(ceil_div(rows, 8)), dim3(256), 0, st, x, rows, H, gamma, beta, eps, out_f, out_t, in_group, out_group, out_off));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const int64_t* __restrict
                                                        const float* __restrict__ pos, const float* __restrict__ type,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float eps, float* __restrict__ out_f, T* __restrict__ out_t) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R * Lt) return;
@@ -134,8 +135,7 @@ int embed_ln(const int64_t* ids, const int64_t* tts, int64_t R, int Lt, int Lj, 
              const float* type, const float* gamma, const float* beta, float eps, float* out_f, T* out_t, cudaStream_t st) {
   MSQ_REQUIRE(H % 128 == 0 && H <= LN_MAX_VEC * 128, "embed_ln: H=%d unsupported", H);
   if (R == 0) return MSQ_OK;
-  embed_ln_kernel<T><<<ceil_div(R * Lt, 8), 256, 0, st>>>(ids, tts, R, Lt, Lj, H, word, pos, type, gamma, beta, eps, out_f,
-                                                          out_t);
+  MSQ_CUDA(launch_k(embed_ln_kernel<T>, dim3(ceil_div(R * Lt, 8)), dim3(256), 0, st, ids, tts, R, Lt, Lj, H, word, pos, type, gamma, beta, eps, out_f, out_t));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(256) vit_assemble_kernel(const float* __restri
                                                            int W, const float* __restrict__ cls, const float* __restrict__ pos,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            float eps, float* __restrict__ out) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int Lv = 1 + il * g2;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -185,8 +186,7 @@ int vit_assemble(const float* patch, const int32_t* img_index, int64_t R, int il
                  const float* pos, const float* gamma, const float* beta, float eps, float* out, cudaStream_t st) {
   MSQ_REQUIRE(W % 128 == 0 && W <= LN_MAX_VEC * 128, "vit_assemble: width=%d unsupported", W);
   if (R == 0) return MSQ_OK;
-  vit_assemble_kernel<<<ceil_div(R * (1 + il * g2), 8), 256, 0, st>>>(patch, img_index, R, il, g2, W, cls, pos, gamma,
-                                                                      beta, eps, out);
+  MSQ_CUDA(launch_k(vit_assemble_kernel, dim3(ceil_div(R * (1 + il * g2), 8)), dim3(256), 0, st, patch, img_index, R, il, g2, W, cls, pos, gamma, beta, eps, out));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -195,6 +195,7 @@ int vit_assemble(const float* patch, const int32_t* img_index, int64_t R, int il
 template <typename T>
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ img, int64_t n, int S, int P,
                                                      T* __restrict__ out) {
+  pdl_sync();
   const int g = S / P;
   const int K = 3 * P * P;
   const int64_t total4 = n * g * g * (int64_t)(K / 4);
@@ -214,7 +215,7 @@ int im2col(const float* img, int64_t n, int S, int P, T* out, cudaStream_t st) {
   MSQ_REQUIRE(S % P == 0 && P % 4 == 0, "im2col: S=%d P=%d unsupported", S, P);
   if (n == 0) return MSQ_OK;
   const int64_t total4 = n * (S / P) * (S / P) * (int64_t)(3 * P * P / 4);
-  im2col_kernel<T><<<(int)min((int64_t)148 * 16, (total4 + 255) / 256), 256, 0, st>>>(img, n, S, P, out);
+  MSQ_CUDA(launch_k(im2col_kernel<T>, dim3((int)min((int64_t)148 * 16, (total4 + 255) / 256)), dim3(256), 0, st, img, n, S, P, out));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -225,6 +226,7 @@ template int im2col<bf16>(const float*, int64_t, int, int, bf16*, cudaStream_t);
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const TI* __restrict__ src, int64_t rows, int H, int group,
                                                           int src_group, int off, TO* __restrict__ dst) {
+  pdl_sync();
   const int64_t total4 = rows * (H / 4);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / (H / 4);
@@ -239,8 +241,7 @@ int gather_rows(const TI* src, int64_t rows, int H, int group, int src_group, in
   MSQ_REQUIRE(H % 4 == 0, "gather_rows: H=%d", H);
   if (rows == 0) return MSQ_OK;
   const int64_t total4 = rows * (H / 4);
-  gather_rows_kernel<TI, TO><<<(int)min((int64_t)148 * 16, (total4 + 255) / 256), 256, 0, st>>>(src, rows, H, group,
-                                                                                               src_group, off, dst);
+  MSQ_CUDA(launch_k(gather_rows_kernel<TI, TO>, dim3((int)min((int64_t)148 * 16, (total4 + 255) / 256)), dim3(256), 0, st, src, rows, H, group, src_group, off, dst));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -251,6 +252,7 @@ template int gather_rows<bf16, bf16>(const bf16*, int64_t, int, int, int, int, b
 // weight packing: dst[r, 0..Kp) = src[r, 0..K) zero padded, with dtype conversion (row-major [rows, K])
 template <typename TO>
 __global__ void pack_pad_kernel(const float* __restrict__ src, int64_t rows, int K, int Kp, TO* __restrict__ dst) {
+  pdl_sync();
   const int64_t total = rows * Kp;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / Kp;
@@ -261,7 +263,7 @@ __global__ void pack_pad_kernel(const float* __restrict__ src, int64_t rows, int
 template <typename TO>
 int pack_pad(const float* src, int64_t rows, int K, int Kp, TO* dst, cudaStream_t st) {
   if (rows == 0) return MSQ_OK;
-  pack_pad_kernel<TO><<<(int)min((int64_t)148 * 8, (rows * Kp + 255) / 256), 256, 0, st>>>(src, rows, K, Kp, dst);
+  MSQ_CUDA(launch_k(pack_pad_kernel<TO>, dim3((int)min((int64_t)148 * 8, (rows * Kp + 255) / 256)), dim3(256), 0, st, src, rows, K, Kp, dst));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }

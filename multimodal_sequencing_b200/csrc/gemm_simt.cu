@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
                                                         const float* __restrict__ bias, const float* __restrict__ resid,
                                                         TO* __restrict__ C, float* __restrict__ C2, int64_t M, int N, int K,
                                                         int lda, int ldw, int ldc, int ldr, int act) {
+  pdl_sync();
   constexpr int SG_BM = TILE, SG_BN = TILE, SG_LD = TILE + 4, TM = TILE / 16, HM = TM / 2;
   constexpr int KV = TILE == 128 ? 8 : 4;  // k elements each thread stages per tile row
   __shared__ __align__(16) float As[2][SG_BK][SG_LD];
@@ -167,12 +168,10 @@ int gemm_simt(const GemmArgs& g, cudaStream_t st) {
   // small problems: 64x64 tiles give 4x the CTAs (fills the 148 SMs when M is a few hundred rows)
   if ((int64_t)ceil_div(g.N, 128) * ceil_div(g.M, 128) < 2 * 148) {
     dim3 grid(ceil_div(g.N, 64), ceil_div(g.M, 64));
-    gemm_simt_kernel<TA, TO, 64><<<grid, 256, 0, st>>>((const TA*)g.A, (const TA*)g.W, g.bias, g.resid, (TO*)g.C, g.C2, g.M,
-                                                        g.N, g.K, g.lda, g.ldw, g.ldc, g.ldr, g.act);
+    MSQ_CUDA(launch_k(gemm_simt_kernel<TA, TO, 64>, dim3(grid), dim3(256), 0, st, (const TA*)g.A, (const TA*)g.W, g.bias, g.resid, (TO*)g.C, g.C2, g.M, g.N, g.K, g.lda, g.ldw, g.ldc, g.ldr, g.act));
   } else {
     dim3 grid(ceil_div(g.N, 128), ceil_div(g.M, 128));
-    gemm_simt_kernel<TA, TO, 128><<<grid, 256, 0, st>>>((const TA*)g.A, (const TA*)g.W, g.bias, g.resid, (TO*)g.C, g.C2, g.M,
-                                                         g.N, g.K, g.lda, g.ldw, g.ldc, g.ldr, g.act);
+    MSQ_CUDA(launch_k(gemm_simt_kernel<TA, TO, 128>, dim3(grid), dim3(256), 0, st, (const TA*)g.A, (const TA*)g.W, g.bias, g.resid, (TO*)g.C, g.C2, g.M, g.N, g.K, g.lda, g.ldw, g.ldc, g.ldr, g.act));
   }
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;

@@ -149,6 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (PAIR) cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrival / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tslot_gen;
+  pdl_sync();  // everything above (barriers, TMEM, cluster rendezvous) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA stages its own rows) =====================
@@ -385,15 +386,17 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     MSQ_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<TO, PAIR, ACT>, ma, mb, mc, ep, num_m, num_n, num_k));
   } else {
     const int grid = (int)min((int64_t)sms, tiles);
-    gemm_tc_kernel<TO, PAIR, ACT><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ma, mb, mc, ep, num_m, num_n, num_k);
+    MSQ_CUDA(launch_k(gemm_tc_kernel<TO, PAIR, ACT>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM, st, ma, mb, mc, ep, num_m, num_n, num_k));
   }
   MSQ_LAUNCH_CHECK();
   profile_mark(st, true, 2.0 * (double)g.M * (double)g.N * (double)g.K);

@@ -91,4 +91,8 @@ int decode_step_lstm(const float* gates, const float* c_in, int64_t Wb, int H, f
 int decode_step_score(const float* q, const float* keys, const float* key0, const uint8_t* pointed, const float* wt, float bt,
                       int64_t Wb, int N, int H, float* logp, cudaStream_t st);
 
+int pointer_p1(const float* enc, const float* cls, const int64_t* y, const float* W1, const float* W2, const float* V,
+               const float* Wih, const float* Whh, const float* bih, const float* bhh, int64_t B, int N, int H, int U, float* preds,
+               float* ce_scratch, float* loss, cudaStream_t st);
+
 }  // namespace msq

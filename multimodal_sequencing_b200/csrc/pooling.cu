@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(256) token_pool_kernel(const T* __restrict__ t
                                                          const int64_t* __restrict__ sep, const float* __restrict__ w_rel,
                                                          const float* __restrict__ b_rel, float* __restrict__ mix,
                                                          float* __restrict__ rel6) {
+  pdl_sync();
   extern __shared__ float sm[];
   float* score = sm;        // [Lt]
   float* p0 = sm + Lt;      // [Lt]
@@ -77,7 +78,7 @@ template <typename T>
 int token_pool(const T* tt, const float* x, int64_t R, int Lt, int Lj, int H, const float* w2, const float* b2,
                const int64_t* sep, const float* w_rel, const float* b_rel, float* mix, float* rel6, cudaStream_t st) {
   if (R == 0) return MSQ_OK;
-  token_pool_kernel<T><<<(unsigned)R, 256, 3 * Lt * sizeof(float), st>>>(tt, x, Lt, Lj, H, w2, b2, sep, w_rel, b_rel, mix, rel6);
+  MSQ_CUDA(launch_k(token_pool_kernel<T>, dim3((unsigned)R), dim3(256), 3 * Lt * sizeof(float), st, tt, x, Lt, Lj, H, w2, b2, sep, w_rel, b_rel, mix, rel6));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(256) edge_pool_kernel(const float* __restrict_
                                                         float* __restrict__ r0, int r0_ld, float* __restrict__ cls_mat,
                                                         float* __restrict__ score_mat, float* __restrict__ his1,
                                                         float* __restrict__ his2, float* __restrict__ cls_out) {
+  pdl_sync();
   __shared__ int e_pair[2 * PL_MAXN], e_side[2 * PL_MAXN];
   __shared__ float e_w[2 * PL_MAXN];
   const int b = blockIdx.x / N, s = blockIdx.x % N;
@@ -175,8 +177,7 @@ int edge_pool(const float* mix, const float* x, const float* rel6, int64_t B, in
   MSQ_REQUIRE(N >= 2 && N <= PL_MAXN, "edge_pool: N=%d out of range [2,%d]", N, PL_MAXN);
   MSQ_REQUIRE((score_mat == nullptr) == (his1 == nullptr) && (his1 == nullptr) == (his2 == nullptr), "edge_pool: tables");
   if (B == 0) return MSQ_OK;
-  edge_pool_kernel<<<(unsigned)(B * N), 256, 0, st>>>(mix, x, rel6, N, Lj, H, w_in2, sents, r0, r0_ld, cls_mat, score_mat, his1,
-                                                      his2, cls_out);
+  MSQ_CUDA(launch_k(edge_pool_kernel, dim3((unsigned)(B * N)), dim3(256), 0, st, mix, x, rel6, N, Lj, H, w_in2, sents, r0, r0_ld, cls_mat, score_mat, his1, his2, cls_out));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -185,6 +186,7 @@ int edge_pool(const float* mix, const float* x, const float* rel6, int64_t B, in
 // (every manual has exactly N steps, process_inputs_for_berson.py:133).
 __global__ void __launch_bounds__(128) para_attention_kernel(const float* __restrict__ qkv, int N, int heads, int H,
                                                              float* __restrict__ ctx) {
+  pdl_sync();
   __shared__ float s[PL_MAXN][PL_MAXN + 1];
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int d = H / heads;
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(128) para_attention_kernel(const float* __rest
 int para_attention(const float* qkv, int64_t B, int N, int heads, int H, float* ctx, cudaStream_t st) {
   MSQ_REQUIRE(N <= PL_MAXN && H % heads == 0, "para_attention: N=%d heads=%d H=%d", N, heads, H);
   if (B == 0) return MSQ_OK;
-  para_attention_kernel<<<(unsigned)(B * heads), 128, 0, st>>>(qkv, N, heads, H, ctx);
+  MSQ_CUDA(launch_k(para_attention_kernel, dim3((unsigned)(B * heads)), dim3(128), 0, st, qkv, N, heads, H, ctx));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -226,6 +228,7 @@ int para_attention(const float* qkv, int64_t B, int N, int heads, int H, float* 
 // h0[b] = sum_s para[b,s] / (N + 1e-20);  keyin[b,s] = [sents[b,s] ; para[b,s]]
 __global__ void __launch_bounds__(256) para_finish_kernel(const float* __restrict__ sents, const float* __restrict__ para, int N,
                                                           int H, float* __restrict__ h0, float* __restrict__ keyin) {
+  pdl_sync();
   const int b = blockIdx.x;
   const float den = (float)N + 1e-20f;
   for (int d = threadIdx.x; d < H; d += blockDim.x) {
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(256) para_finish_kernel(const float* __restric
 
 int para_finish(const float* sents, const float* para, int64_t B, int N, int H, float* h0, float* keyin, cudaStream_t st) {
   if (B == 0) return MSQ_OK;
-  para_finish_kernel<<<(unsigned)B, 256, 0, st>>>(sents, para, N, H, h0, keyin);
+  MSQ_CUDA(launch_k(para_finish_kernel, dim3((unsigned)B), dim3(256), 0, st, sents, para, N, H, h0, keyin));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }

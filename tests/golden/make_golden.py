@@ -207,6 +207,36 @@ def gen_topo(ns, mm):
                 classifier={k: v.clone() for k, v in m.state_dict().items() if k.startswith("classifier.")})
 
 
+def gen_pointer_p1(ns):
+    """models/pointer_module.py::PointerOutput, p1 variant (dead code in the reference, SURVEY §0.4 / §3.5):
+    LSTMPointerModule greedy decoding + CE loss on random hidden states."""
+    import types
+    import transformers
+    import transformers.file_utils as fu
+    transformers.__dict__["AdamW"] = torch.optim.AdamW               # symbols of transformers 3.4 the module imports
+    if not hasattr(fu, "requires_sklearn"):
+        fu.requires_sklearn = lambda *a, **k: None
+    if not hasattr(fu, "is_sklearn_available"):
+        fu.is_sklearn_available = lambda: True
+    from models import pointer_module as pm
+    torch.manual_seed(11)
+    H, N, B, L = 128, 5, 3, 40
+    cfg = types.SimpleNamespace(hierarchical_version="p1", hidden_size=H, max_story_length=N, hl_include_objectives=None, cls_id=101)
+    m = pm.PointerOutput(cfg).eval()
+    for p_ in m.parameters():
+        p_.data.mul_(3.0)   # spread the attention logits
+    ids = torch.randint(200, 900, (B, L))
+    for b in range(B):
+        posn = torch.randperm(L - 1)[:N - 1].add(1).sort().values
+        ids[b, 0] = 101
+        ids[b, posn] = 101
+    seq = torch.randn(B, L + 7, H)   # text + a few visual positions
+    labels = torch.stack([torch.randperm(N) for _ in range(B)])
+    loss, out = m({"input_ids": ids, "labels": labels}, seq)
+    sd = {k: v.clone() for k, v in m.state_dict().items() if not k.startswith("lstm_pointer.")}
+    return dict(H=H, N=N, sd=sd, ids=ids, seq=seq, labels=labels, loss=loss.clone(), outputs=out.clone())
+
+
 def main():
     ns = rh.load()
     torch.save(gen_text(ns), os.path.join(HERE, "text_tiny.pt"))
@@ -214,7 +244,8 @@ def main():
     torch.save(mm, os.path.join(HERE, "mm_tiny.pt"))
     torch.save(gen_topo(ns, mm), os.path.join(HERE, "topo_tiny.pt"))
     torch.save(gen_decode_full(ns), os.path.join(HERE, "decode_full.pt"))
-    for f in ("text_tiny.pt", "mm_tiny.pt", "topo_tiny.pt", "decode_full.pt"):
+    torch.save(gen_pointer_p1(ns), os.path.join(HERE, "pointer_p1.pt"))
+    for f in ("text_tiny.pt", "mm_tiny.pt", "topo_tiny.pt", "decode_full.pt", "pointer_p1.pt"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 

@@ -257,3 +257,32 @@ def test_lxrt_topo_sort_classifier_mode(golden_dir):
                     token_type_ids=inp["token_type_ids"][0, :R].cuda(), visual_feats=inp["images"][0, :R].cuda(),
                     labels=torch.zeros(R, dtype=torch.long))
     assert abs(loss.item() - torch.nn.functional.cross_entropy(t["logits"], torch.zeros(R, dtype=torch.long)).item()) < 2e-5
+
+
+def test_pointer_module_state_dict_keys(golden_dir):
+    from models.pointer_module import PointerOutput
+    g = torch.load(os.path.join(golden_dir, "pointer_p1.pt"), weights_only=False)
+    cfg = types.SimpleNamespace(hierarchical_version="p1", hidden_size=g["H"], max_story_length=g["N"], hl_include_objectives=None,
+                                cls_id=101)
+    m = PointerOutput(cfg)
+    keys = set(m.state_dict().keys())
+    assert set(g["sd"].keys()) <= keys and {k.replace("lstm_decoder.", "lstm_pointer.decoder.") for k in g["sd"]} <= keys
+    with pytest.raises(NotImplementedError):
+        PointerOutput(types.SimpleNamespace(hierarchical_version="p0", hidden_size=768, max_story_length=5))
+
+
+@pytest.mark.gpu
+def test_pointer_module_p1_matches_reference(golden_dir):
+    """PointerOutput.forward / LSTMPointerModule (models/pointer_module.py:153-576, 690-749) vs the reference's outputs."""
+    from models.pointer_module import PointerOutput
+    g = torch.load(os.path.join(golden_dir, "pointer_p1.pt"), weights_only=False)
+    cfg = types.SimpleNamespace(hierarchical_version="p1", hidden_size=g["H"], max_story_length=g["N"], hl_include_objectives=None,
+                                cls_id=101)
+    m = PointerOutput(cfg)
+    m.load_state_dict(g["sd"], strict=False)
+    m = m.cuda().eval()
+    loss, out = m({"input_ids": g["ids"].cuda(), "labels": g["labels"].cuda()}, g["seq"].cuda())
+    assert torch.equal(out.cpu(), g["outputs"])                      # greedy picks: bit-exact index work
+    assert abs(loss.item() - g["loss"].item()) < 1e-5 * max(1.0, abs(g["loss"].item()))
+    (out2,) = m({"input_ids": g["ids"].cuda()}, g["seq"].cuda())
+    assert torch.equal(out2.cpu(), g["outputs"])
