@@ -142,6 +142,11 @@ int msq_order_manuals_host(msq_model* m, const int64_t* ids_host, const int64_t*
  * (tcgen05), 2 = bf16 in / bf16 out (tcgen05).  act: 0 none, 1 erf-GELU, 2 QuickGELU, 3 tanh, 4 tanh-GELU. */
 int msq_gemm(int32_t dtype, const void* A_dev, const void* W_dev, const float* bias_dev, const float* resid_dev,
              void* C_dev, int64_t M, int32_t N, int32_t K, int32_t act, void* stream);
+/* Fused v = A W^T + bias + resid ; y = LayerNorm(v) (tcgen05, cluster of N/256 CTAs; N in {256,512,768}, K % 64 == 0).
+ * A [M,K], W [N,K] bf16; resid [M,N] fp32 (may alias C).  C [M,N] fp32 <- (raw32 ? v : y);  C2 [M,N] bf16 <- y. */
+int msq_gemm_ln(const void* A_dev, const void* W_dev, const float* bias_dev, const float* resid_dev, const float* gamma_dev,
+                const float* beta_dev, float eps, float* C_dev, void* C2_dev, int64_t M, int32_t N, int32_t K, int32_t raw32,
+                void* stream);
 /* dtype 0 fp32, 1 bf16.  y = LN(x) (x always fp32 [rows,H]); writes out_dev in dtype. */
 int msq_layernorm(int32_t dtype, const float* x_dev, int64_t rows, int32_t H, const float* gamma_dev,
                   const float* beta_dev, float eps, void* out_dev, void* stream);

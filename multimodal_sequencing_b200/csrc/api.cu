@@ -623,14 +623,35 @@ static int run_patch_embed(msq_model* m, const float* images, int64_t n_img, Vit
   return MSQ_OK;
 }
 
-// token assembly + ln_pre + the residual blocks for R pair rows; xv holds the final residual stream
-// (ln_post is applied by the caller).  img_index [R*2] addresses rows of b.patch by image.
+// token assembly + ln_pre + the residual blocks for R pair rows; b.xv holds the final residual stream and b.y
+// ln_post(x) in the GEMM operand type.  img_index [R*2] addresses rows of b.patch by image.
 template <typename T>
 static int run_vit(msq_model* m, const int32_t* img_index, int64_t R, VitBufs& b, cudaStream_t st) {
   const msq_config& c = m->cfg;
   const int g = c.vit_res / c.vit_patch, g2 = g * g, Lv = 1 + 2 * g2, Wd = c.vit_width, heads = Wd / 64;
   const int64_t Mv = R * Lv;
   MSQ_TRY(vit_assemble(b.patch, img_index, R, 2, g2, Wd, m->vit_cls, m->vit_pos, m->ln_pre.g, m->ln_pre.b, 1e-5f, b.xv, st));
+  if constexpr (sizeof(T) == 2) {
+    if (use_tc(m) && gemm_ln_enabled() && gemm_ln_supported(Wd, Wd) && gemm_ln_supported(Wd, 4 * Wd)) {
+      // fused path: every residual GEMM also emits LayerNorm(x) (bf16) for the NEXT GEMM -- ln_2 after out_proj,
+      // the next block's ln_1 (ln_post after the last block) after c_proj.  b.y ends up holding ln_post(x).
+      const size_t nl = m->vit.size();
+      if (nl) MSQ_TRY(layernorm<T>(b.xv, Mv, Wd, m->vit[0].ln1.g, m->vit[0].ln1.b, 1e-5f, nullptr, (T*)b.y, 0, 0, 0, st));
+      for (size_t l = 0; l < nl; ++l) {
+        VitLayerW& L = m->vit[l];
+        const LNp& nxt = l + 1 < nl ? m->vit[l + 1].ln1 : m->ln_post;
+        MSQ_TRY((run_gemm<T, T>(m, (const T*)b.y, Wd, L.qkv, nullptr, 0, (T*)b.qkv, 3 * Wd, Mv, ACT_NONE, st)));
+        MSQ_TRY(attention<T>((const T*)b.qkv, R, Lv, heads, 64, 0.125f, nullptr, 0, 0, (T*)b.ctx, st));
+        MSQ_TRY(gemm_ln((const bf16*)b.ctx, Wd, L.out.w16, L.out.ld, L.out.b, b.xv, Wd, L.ln2.g, L.ln2.b, 1e-5f, b.xv, (bf16*)b.y, Mv, Wd,
+                        Wd, true, st));
+        MSQ_TRY((run_gemm<T, T>(m, (const T*)b.y, Wd, L.fc, nullptr, 0, (T*)b.hbuf, 4 * Wd, Mv, ACT_QUICK_GELU, st)));
+        MSQ_TRY(gemm_ln((const bf16*)b.hbuf, 4 * Wd, L.proj.w16, L.proj.ld, L.proj.b, b.xv, Wd, nxt.g, nxt.b, 1e-5f, b.xv, (bf16*)b.y, Mv,
+                        Wd, 4 * Wd, true, st));
+      }
+      if (nl == 0) MSQ_TRY(layernorm<T>(b.xv, Mv, Wd, m->ln_post.g, m->ln_post.b, 1e-5f, nullptr, (T*)b.y, 0, 0, 0, st));
+      return MSQ_OK;
+    }
+  }
   for (auto& L : m->vit) {
     MSQ_TRY(layernorm<T>(b.xv, Mv, Wd, L.ln1.g, L.ln1.b, 1e-5f, nullptr, (T*)b.y, 0, 0, 0, st));
     MSQ_TRY((run_gemm<T, T>(m, (const T*)b.y, Wd, L.qkv, nullptr, 0, (T*)b.qkv, 3 * Wd, Mv, ACT_NONE, st)));
@@ -640,6 +661,7 @@ static int run_vit(msq_model* m, const int32_t* img_index, int64_t R, VitBufs& b
     MSQ_TRY((run_gemm<T, T>(m, (const T*)b.y, Wd, L.fc, nullptr, 0, (T*)b.hbuf, 4 * Wd, Mv, ACT_QUICK_GELU, st)));
     MSQ_TRY((run_gemm<T, float>(m, (const T*)b.hbuf, 4 * Wd, L.proj, b.xv, Wd, b.xv, Wd, Mv, ACT_NONE, st)));
   }
+  MSQ_TRY(layernorm<T>(b.xv, Mv, Wd, m->ln_post.g, m->ln_post.b, 1e-5f, nullptr, (T*)b.y, 0, 0, 0, st));  // b.y = ln_post(x)
   return MSQ_OK;
 }
 
@@ -678,19 +700,31 @@ static int run_inner(msq_model* m, const int64_t* ids, const int64_t* tt, const 
     MSQ_TRY(run_vit<T>(m, img_index, R, vb, st));
     const int Wd = c.vit_width;
     const int64_t Mv = R * Lv;
-    MSQ_TRY(layernorm<T>(vb.xv, Mv, Wd, m->ln_post.g, m->ln_post.b, 1e-5f, nullptr, (T*)vb.y, 0, 0, 0, st));
-    // visn_fc output reuses the (now free) fp32 tmp buffer of the joint stream
+    // vb.y == ln_post(x); visn_fc output reuses the (now free) fp32 tmp buffer of the joint stream
     MSQ_TRY((run_gemm<T, float>(m, (const T*)vb.y, Wd, m->visn_fc, nullptr, 0, jb.tmp, H, Mv, ACT_NONE, st)));
     MSQ_TRY(layernorm<T>(jb.tmp, Mv, H, m->visn_ln.g, m->visn_ln.b, 1e-12f, jb.x, (T*)jb.xt, Lv, Lj, Lt, st));
   }
+  bool fused = false;
+  if constexpr (sizeof(T) == 2) fused = use_tc(m) && gemm_ln_enabled() && gemm_ln_supported(H, H) && gemm_ln_supported(H, c.inter);
   for (auto& L : m->bert) {
     MSQ_TRY((run_gemm<T, T>(m, (const T*)jb.xt, H, L.qkv, nullptr, 0, (T*)jb.qkv, 3 * H, Mj, ACT_NONE, st)));
     MSQ_TRY(attention<T>((const T*)jb.qkv, R, Lj, c.heads, 64, 0.125f, jb.mask_add, Lt, Lt, (T*)jb.ctx, st));
-    MSQ_TRY((run_gemm<T, float>(m, (const T*)jb.ctx, H, L.out, jb.x, H, jb.tmp, H, Mj, ACT_NONE, st)));
-    MSQ_TRY(layernorm<T>(jb.tmp, Mj, H, L.ln1.g, L.ln1.b, 1e-12f, jb.x, (T*)jb.xt, 0, 0, 0, st));
+    if (fused) {
+      // x <- LN(dense(ctx) + x) written in place (fp32) together with its bf16 copy: no pre-LN round trip through HBM
+      MSQ_TRY(gemm_ln((const bf16*)jb.ctx, H, L.out.w16, L.out.ld, L.out.b, jb.x, H, L.ln1.g, L.ln1.b, 1e-12f, jb.x, (bf16*)jb.xt, Mj, H, H,
+                      false, st));
+    } else {
+      MSQ_TRY((run_gemm<T, float>(m, (const T*)jb.ctx, H, L.out, jb.x, H, jb.tmp, H, Mj, ACT_NONE, st)));
+      MSQ_TRY(layernorm<T>(jb.tmp, Mj, H, L.ln1.g, L.ln1.b, 1e-12f, jb.x, (T*)jb.xt, 0, 0, 0, st));
+    }
     MSQ_TRY((run_gemm<T, T>(m, (const T*)jb.xt, H, L.up, nullptr, 0, (T*)jb.hbuf, c.inter, Mj, ACT_GELU_ERF, st)));
-    MSQ_TRY((run_gemm<T, float>(m, (const T*)jb.hbuf, c.inter, L.down, jb.x, H, jb.tmp, H, Mj, ACT_NONE, st)));
-    MSQ_TRY(layernorm<T>(jb.tmp, Mj, H, L.ln2.g, L.ln2.b, 1e-12f, jb.x, (T*)jb.xt, 0, 0, 0, st));
+    if (fused) {
+      MSQ_TRY(gemm_ln((const bf16*)jb.hbuf, c.inter, L.down.w16, L.down.ld, L.down.b, jb.x, H, L.ln2.g, L.ln2.b, 1e-12f, jb.x,
+                      (bf16*)jb.xt, Mj, H, c.inter, false, st));
+    } else {
+      MSQ_TRY((run_gemm<T, float>(m, (const T*)jb.hbuf, c.inter, L.down, jb.x, H, jb.tmp, H, Mj, ACT_NONE, st)));
+      MSQ_TRY(layernorm<T>(jb.tmp, Mj, H, L.ln2.g, L.ln2.b, 1e-12f, jb.x, (T*)jb.xt, 0, 0, 0, st));
+    }
   }
   return MSQ_OK;
 }
@@ -1080,6 +1114,13 @@ extern "C" int msq_gemm(int32_t dtype, const void* A_dev, const void* W_dev, con
   }
   set_error("msq_gemm: unknown dtype %d", dtype);
   return MSQ_ERR_ARG;
+}
+
+extern "C" int msq_gemm_ln(const void* A_dev, const void* W_dev, const float* bias_dev, const float* resid_dev,
+                           const float* gamma_dev, const float* beta_dev, float eps, float* C_dev, void* C2_dev, int64_t M, int32_t N,
+                           int32_t K, int32_t raw32, void* stream) {
+  return gemm_ln((const bf16*)A_dev, K, (const bf16*)W_dev, K, bias_dev, resid_dev, N, gamma_dev, beta_dev, eps, C_dev, (bf16*)C2_dev, M, N,
+                 K, raw32 != 0, (cudaStream_t)stream);
 }
 
 extern "C" int msq_layernorm(int32_t dtype, const float* x_dev, int64_t rows, int32_t H, const float* gamma_dev,

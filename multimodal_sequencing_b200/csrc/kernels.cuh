@@ -40,6 +40,12 @@ template <typename TA, typename TO> int gemm_simt(const GemmArgs& g, cudaStream_
 template <typename TO> int gemm_tc(const GemmArgs& g, cudaStream_t st);
 int gemm_tc_selftest_supported();
 
+// ---- gemm_ln.cu : GEMM + bias + residual + LayerNorm fused (cluster of N/256 CTAs), bf16 operands
+bool gemm_ln_supported(int N, int K);
+bool gemm_ln_enabled();
+int gemm_ln(const bf16* A, int lda, const bf16* W, int ldw, const float* bias, const float* resid, int ldr, const float* gamma,
+            const float* beta, float eps, float* C, bf16* C2, int64_t M, int N, int K, bool raw32, cudaStream_t st);
+
 // ---- attention.cu : ctx[r, t, h*64 + d] = softmax(q k^T / sqrt(d) + mask) v over the L tokens of row-group r
 template <typename T>
 int attention(const T* qkv, int64_t R, int L, int heads, int dhead, float scale, const float* key_mask_add, int mask_ld,

@@ -105,6 +105,32 @@ def test_gemm_tcgen05(M, N, K, act, out_bf16):
     _close(out, ref.float(), 8e-3 if out_bf16 else 3e-5, "tcgen05 gemm")
 
 
+@pytest.mark.parametrize("M,N,K,raw32,inplace", [(1000, 768, 768, False, True), (4540, 768, 3072, False, False),
+                                                  (1980, 768, 768, True, True), (130, 256, 128, True, False), (37000, 768, 768, False, True)])
+def test_gemm_layernorm_fused(M, N, K, raw32, inplace):
+    """cluster-fused GEMM + bias + residual + LayerNorm against float64 on the same bf16-rounded operands."""
+    import ctypes as C
+    from multimodal_sequencing_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).bfloat16()
+    W = (torch.randn(N, K, generator=g) * 0.05).bfloat16()
+    bias, resid = torch.randn(N, generator=g), torch.randn(M, N, generator=g) * 2
+    gamma, beta = torch.randn(N, generator=g), torch.randn(N, generator=g)
+    v = A.double() @ W.double().t() + bias.double() + resid.double()
+    y = torch.nn.functional.layer_norm(v, (N,), gamma.double(), beta.double(), 1e-5)
+    Ad, Wd, bd, gd, be = A.cuda(), W.cuda(), bias.cuda(), gamma.cuda(), beta.cuda()
+    rd = resid.cuda()
+    out = rd if inplace else torch.empty(M, N, device="cuda")
+    out2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.msq_gemm_ln(Ad.data_ptr(), Wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), gd.data_ptr(), be.data_ptr(), 1e-5,
+                               out.data_ptr(), out2.data_ptr(), M, N, K, int(raw32), st))
+    torch.cuda.synchronize()
+    _close(out, (v if raw32 else y).float(), 5e-5, "gemm_ln fp32 stream")
+    _close(out2, y.float(), 8e-3, "gemm_ln bf16 copy")
+
+
 @pytest.mark.parametrize("H,eps", [(768, 1e-12), (128, 1e-5), (1024, 1e-6)])
 def test_layernorm(H, eps):
     import ctypes as C
