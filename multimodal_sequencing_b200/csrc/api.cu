@@ -610,12 +610,12 @@ static void plan_vit(const msq_config& c, Planner& p, int64_t n_img, int64_t R, 
 
 // conv1 (32x32 / stride 32, no bias) as im2col + GEMM over all UNIQUE images -> b.patch [n_img*g2, W]
 template <typename T>
-static int run_patch_embed(msq_model* m, const float* images, int64_t n_img, VitBufs& b, cudaStream_t st) {
+static int run_patch_embed(msq_model* m, const float* images, int64_t n_img, VitBufs& b, cudaStream_t st, int64_t first = 0) {
   const msq_config& c = m->cfg;
   const int g = c.vit_res / c.vit_patch, g2 = g * g, Wd = c.vit_width;
   const int64_t img_elems = (int64_t)3 * c.vit_res * c.vit_res;
-  for (int64_t i0 = 0; i0 < n_img; i0 += IMG_CHUNK) {
-    const int64_t n = min(IMG_CHUNK, n_img - i0);
+  for (int64_t i0 = first; i0 < first + n_img; i0 += IMG_CHUNK) {
+    const int64_t n = min(IMG_CHUNK, first + n_img - i0);
     MSQ_TRY(im2col<T>(images + i0 * img_elems, n, c.vit_res, c.vit_patch, (T*)b.apatch, st));
     MSQ_TRY((run_gemm<T, float>(m, (const T*)b.apatch, m->conv1.K, m->conv1, nullptr, 0, b.patch + i0 * g2 * Wd, Wd, n * g2, ACT_NONE,
                                 st, false)));
@@ -823,7 +823,7 @@ template <typename T>
 static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const int64_t* mask, const int64_t* sep, int64_t B, int N,
                     int Lt, const float* images, int64_t n_img, const int32_t* img_index, const msq_encode_out* out, int beam,
                     int32_t* perm, cudaStream_t st, const int32_t* forced = nullptr, const int64_t* pair_labels = nullptr,
-                    float lam = 0.f, float* loss_out = nullptr) {
+                    float lam = 0.f, float* loss_out = nullptr, const cudaEvent_t* img_ready = nullptr) {
   const msq_config& c = m->cfg;
   MSQ_REQUIRE(m->packed, "msq_model_pack() has not been called");
   MSQ_REQUIRE(m->has_bert && m->has_heads, "model lacks the inner encoder or the BERSON head weights");
@@ -846,10 +846,17 @@ static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const i
     plan_heads<T>(c, p, B, N, Rc, Lt, m->Kp, &hb);
     if (pass == 0) MSQ_TRY(m->ws.reserve(p.need + 4096, st));
   }
-  if (mm) MSQ_TRY(run_patch_embed<T>(m, images, n_img, vb, st));  // once per UNIQUE image, not per pair slot
+  // patch embedding once per UNIQUE image, not per pair slot.  When the caller streams the images in manual order
+  // (img_ready != nullptr: images of manuals [b0, b0+bc) are rows [b0*N, (b0+bc)*N), one event per micro-batch),
+  // each micro-batch embeds its own images as soon as its host->device copy has landed.
+  if (mm && !img_ready) MSQ_TRY(run_patch_embed<T>(m, images, n_img, vb, st));
 
   for (int64_t b0 = 0; b0 < B; b0 += Bc) {
     const int64_t bc = min(Bc, B - b0), rc = bc * P, r0 = b0 * P;
+    if (mm && img_ready) {
+      MSQ_CUDA(cudaStreamWaitEvent(st, img_ready[b0 / Bc], 0));
+      MSQ_TRY(run_patch_embed<T>(m, images, bc * N, vb, st, b0 * N));
+    }
     MSQ_TRY((run_inner<T>(m, ids + r0 * Lt, tt + r0 * Lt, mask + r0 * Lt, rc, Lt, mm ? img_index + r0 * 2 : nullptr, vb, jb, st)));
     // ---- pooling for this chunk
     MSQ_TRY((gather_rows<float, T>(jb.x, rc * Lt, H, Lt, Lj, 0, (T*)hb.topt, st)));
@@ -1084,12 +1091,45 @@ extern "C" int msq_order_manuals_host(msq_model* m, const int64_t* ids_host, con
   MSQ_CUDA(cudaMemcpyAsync(tt, tt_host, n_tok * 8, cudaMemcpyHostToDevice, st));
   MSQ_CUDA(cudaMemcpyAsync(mask, mask_host, n_tok * 8, cudaMemcpyHostToDevice, st));
   MSQ_CUDA(cudaMemcpyAsync(sep, sep_host, (size_t)R * 2 * 8, cudaMemcpyHostToDevice, st));
+  const cudaEvent_t* ready = nullptr;
   if (images_host) {
-    MSQ_CUDA(cudaMemcpyAsync(img, images_host, img_elems * 4, cudaMemcpyHostToDevice, st));
     MSQ_CUDA(cudaMemcpyAsync(idx, img_index_host, (size_t)R * 2 * 4, cudaMemcpyHostToDevice, st));
+    // images in manual order (row b*N+i, every pair of manual b points into [b*N, (b+1)*N)): upload them micro-batch by
+    // micro-batch on a copy stream so that only the first micro-batch's copy is exposed.
+    const int P2 = N * (N - 1) * 2;
+    bool local = n_img == B * N;
+    for (int64_t i = 0; local && i < R * 2; ++i) {
+      const int64_t b = i / P2;
+      local = img_index_host[i] >= b * N && img_index_host[i] < (b + 1) * N;
+    }
+    static thread_local cudaStream_t copy_st = nullptr;
+    static thread_local std::vector<cudaEvent_t> evs;
+    const int64_t Bc = min((int64_t)chunk_manuals(), B);
+    const int64_t nchunks = (B + Bc - 1) / Bc;
+    if (local && nchunks > 1) {
+      if (!copy_st) MSQ_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
+      while ((int64_t)evs.size() < nchunks) {
+        cudaEvent_t e;
+        MSQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        evs.push_back(e);
+      }
+      const size_t per_img = (size_t)3 * m->cfg.vit_res * m->cfg.vit_res;
+      for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t i0 = c * Bc * N, n = min(Bc, B - c * Bc) * N;
+        MSQ_CUDA(cudaMemcpyAsync(img + i0 * per_img, images_host + i0 * per_img, n * per_img * 4, cudaMemcpyHostToDevice, copy_st));
+        MSQ_CUDA(cudaEventRecord(evs[c], copy_st));
+      }
+      ready = evs.data();
+    } else {
+      MSQ_CUDA(cudaMemcpyAsync(img, images_host, img_elems * 4, cudaMemcpyHostToDevice, st));
+    }
   }
-  MSQ_TRY(msq_order_manuals_dev(m, ids, tt, mask, sep, B, N, Lt, images_host ? img : nullptr, n_img, images_host ? idx : nullptr, beam,
-                                perm, stream));
+  if (m->cfg.precise)
+    MSQ_TRY(run_path<float>(m, ids, tt, mask, sep, B, N, Lt, images_host ? img : nullptr, n_img, images_host ? idx : nullptr, nullptr, beam,
+                            perm, st, nullptr, nullptr, 0.f, nullptr, ready));
+  else
+    MSQ_TRY(run_path<bf16>(m, ids, tt, mask, sep, B, N, Lt, images_host ? img : nullptr, n_img, images_host ? idx : nullptr, nullptr, beam,
+                           perm, st, nullptr, nullptr, 0.f, nullptr, ready));
   MSQ_CUDA(cudaMemcpyAsync(perm_host, perm, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
   MSQ_CUDA(cudaStreamSynchronize(st));
   return MSQ_OK;
