@@ -540,3 +540,82 @@ def synthetic_manuals(B, n_steps, tokens_per_step=64, vocab=30522, image_px=None
     if image_px:
         images = torch.randn(B, n_steps, 3, image_px, image_px, generator=g)
     return ids, labels, images
+
+
+# --------------------------------------------------------------------------------------------
+# a5 — CLIP ModifiedResNet tower (the reference's wired default backbone) + RN-only LXRT embeddings
+# --------------------------------------------------------------------------------------------
+
+
+def _bn(sd, name, x):
+    """eval-mode BatchNorm2d (running statistics, eps 1e-5)."""
+    w, b, m, v = sd[name + ".weight"], sd[name + ".bias"], sd[name + ".running_mean"], sd[name + ".running_var"]
+    return (x - m[None, :, None, None]) / torch.sqrt(v[None, :, None, None] + 1e-5) * w[None, :, None, None] + b[None, :, None, None]
+
+
+def _bottleneck(sd, pre, x, stride):
+    """models/CLIP/clip/model.py:10-53: 1x1 -> 3x3 -> (avgpool) -> 1x1, anti-aliased down-sampling branch."""
+    out = torch.relu(_bn(sd, pre + "bn1", F.conv2d(x, sd[pre + "conv1.weight"])))
+    out = torch.relu(_bn(sd, pre + "bn2", F.conv2d(out, sd[pre + "conv2.weight"], padding=1)))
+    if stride > 1:
+        out = F.avg_pool2d(out, stride)
+    out = _bn(sd, pre + "bn3", F.conv2d(out, sd[pre + "conv3.weight"]))
+    identity = x
+    if (pre + "downsample.0.weight") in sd:
+        identity = F.avg_pool2d(x, stride) if stride > 1 else x
+        identity = _bn(sd, pre + "downsample.1", F.conv2d(identity, sd[pre + "downsample.0.weight"]))
+    return torch.relu(out + identity)
+
+
+def rn_pair_tower(sd, pre, images, rn, img_len=2):
+    """ModifiedResNet.forward + AttentionPool2d.forward (clip/model.py:171-187, 71-125), skip_last_layer=False
+    (as hard-wired, lxrt/modeling.py:783).  images [R*img_len,3,S,S] -> [R, 1 + img_len*g*g, 2*output_dim].
+
+    Quirk reproduced (model.py:76): the NCHW feature maps of a pair are reshaped [R, C, g*g*img_len] WITHOUT moving the
+    image axis, so token t / channel c' reads flat element c'*(g*g*img_len) + t of the pair's [img, C, g*g] block."""
+    x = images
+    for i in (1, 2, 3):
+        x = torch.relu(_bn(sd, pre + "bn%d" % i, F.conv2d(x, sd[pre + "conv%d.weight" % i], stride=2 if i == 1 else 1, padding=1)))
+    x = F.avg_pool2d(x, 2)
+    for li, nblk in enumerate(rn["vision_layers"], start=1):
+        for bi in range(nblk):
+            x = _bottleneck(sd, pre + "layer%d.%d." % (li, bi), x, 2 if (li > 1 and bi == 0) else 1)
+    a = pre + "attnpool."
+    R = x.shape[0] // img_len
+    C, g2 = x.shape[1], x.shape[2] * x.shape[3]
+    t = x.reshape(R, C, g2 * img_len).permute(2, 0, 1)                      # (HW*il) R C
+    t = torch.cat([t.mean(dim=0, keepdim=True), t], dim=0)
+    pos = sd[a + "positional_embedding"]
+    t = t + torch.cat([pos] + [pos[:g2]] * (img_len - 1), dim=0)[:, None, :]
+    heads = rn["vision_width"] * 32 // 64
+    d = C // heads
+    L = t.shape[0]
+    q = (t @ sd[a + "q_proj.weight"].t() + sd[a + "q_proj.bias"]).reshape(L, R, heads, d).permute(1, 2, 0, 3) * (d ** -0.5)
+    k = (t @ sd[a + "k_proj.weight"].t() + sd[a + "k_proj.bias"]).reshape(L, R, heads, d).permute(1, 2, 0, 3)
+    v = (t @ sd[a + "v_proj.weight"].t() + sd[a + "v_proj.bias"]).reshape(L, R, heads, d).permute(1, 2, 0, 3)
+    o = (torch.softmax(q @ k.transpose(-1, -2), -1) @ v).permute(0, 2, 1, 3).reshape(R, L, C)
+    o = o @ sd[a + "c_proj.weight"].t() + sd[a + "c_proj.bias"]
+    return torch.cat([o, o], dim=-1)                                        # model.py:106
+
+
+def lxrt_forward_rn(sd, cfg, ids, tt, attention_mask, images, pre="bert."):
+    """LXRTModel.forward with the RN backbone as wired (lxrt/modeling.py:874-882, 1014-1030, 1063-1107):
+    tower -> + LinearPositionEmbedding (x/y, 621-660) -> + VisualTokenTypeEmbedding (663-705) -> visn_fc -> joint BERT."""
+    rn = cfg["rn"]
+    tower = rn_pair_tower(sd, pre + "encoder.visual_model.visual.", images, rn)
+    g = rn["image_resolution"] // 32
+    xe, ye = sd[pre + "encoder.visual_pos.x_position_embedding.weight"][:g], sd[pre + "encoder.visual_pos.y_position_embedding.weight"][:g]
+    pe = (xe[:, None, :] + ye[None, :, :]).reshape(g * g, -1)
+    pe = torch.cat([pe[0:1], pe, pe], dim=0)                                # skip_last_layer=False, img_len=2 (649-651)
+    te = sd[pre + "encoder.visual_token_type.token_type_embedding.weight"]
+    type_ids = torch.zeros(1 + 2 * g * g, dtype=torch.long)
+    type_ids[1 + g * g:1 + 2 * g * g] = 1                                    # 691-696
+    v = tower + pe[None] + te[type_ids][None]
+    v = _ln(sd, pre + "encoder.visn_fc.visn_layer_norm", _lin(sd, pre + "encoder.visn_fc.visn_fc", v), 1e-12)
+    emb = bert_embeddings(sd, pre + "embeddings.", ids, tt, 1e-12)
+    R, Lt = ids.shape
+    joint = torch.cat([emb, v], dim=1)
+    m = torch.cat([ext_mask(attention_mask), torch.zeros(R, 1, 1, v.shape[1])], dim=-1)
+    for i in range(cfg["num_hidden_layers"]):
+        joint = bert_layer(sd, pre + "encoder.layer.%d." % i, joint, m, cfg["num_attention_heads"], 1e-12)
+    return joint[:, :Lt], joint[:, Lt:], _lin(sd, pre + "pooler.dense", joint[:, 0])
