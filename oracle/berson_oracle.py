@@ -312,10 +312,10 @@ def encode(sd, cfg, inp):
     B, P, Lt = ids.shape
     N = int(inp["passage_length"][0])
     ids2, am2, tt2 = ids.reshape(B * P, Lt), inp["attention_mask"].reshape(B * P, Lt), inp["token_type_ids"].reshape(B * P, Lt)
-    if cfg.get("vit") is not None and inp.get("images") is not None:
+    if (cfg.get("vit") is not None or cfg.get("rn") is not None) and inp.get("images") is not None:
         im = inp["images"]
         im = im.reshape(B * P * 2, *im.shape[3:])
-        top_vec, visn, _ = lxrt_forward(sd, cfg, ids2, tt2, am2, im)
+        top_vec, visn, _ = (lxrt_forward_rn if cfg.get("rn") is not None else lxrt_forward)(sd, cfg, ids2, tt2, am2, im)
         cls = top_vec[:, 0]
     else:
         top_vec, cls = text_bert(sd, cfg, ids2, am2, tt2)

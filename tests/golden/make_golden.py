@@ -152,6 +152,36 @@ def gen_mm(ns):
     return out
 
 
+TINY_RN = dict(embed_dim=256, image_resolution=224, vision_layers=(1, 2, 1, 1), vision_width=16)
+
+
+def gen_mm_rn(ns):
+    """The reference's wired default backbone ("RN50": ModifiedResNet + AttentionPool2d, visual_pos / visual_token_type
+    embeddings) on a narrow tower -- same code path as RN50, width 16 instead of 64."""
+    out = dict(cfg=dict(TINY), rn=dict(TINY_RN), ff_size=256, cases=[])
+    for N, W, L in ((5, 4, 32),):
+        args = rh.make_args(N, W, multimodal=True)
+        args.ff_size = 256
+        model = rh.build_multimodal_model(ns, TINY, args, seed=0, rn_cfg=TINY_RN)
+        out["sd"] = {k: v.clone() for k, v in model.state_dict().items()
+                     if not any(d in k for d in DEAD) and v.is_floating_point()}
+        seed = 60 + N
+        ids, labels, images = O.synthetic_manuals(1, N, L, vocab=1000, image_px=224, seed=seed)
+        c = run_case(ns, model, args, ids, labels, images)
+        bi = ns.prep.prepare_berson_inputs({"input_ids": ids, "attention_mask": torch.ones_like(ids),
+                                            "labels": labels, "images": images}, rh.StubTokenizer(), args=args)
+        B, P, Lt = bi["input_ids"].shape
+        im = bi["images"].reshape(B * P * 2, 3, 224, 224)
+        tower = model.bert.encoder.visual_model.visual(im[:6], img_len=2)
+        (lang, visn), pooled = model.bert(input_ids=bi["input_ids"].reshape(B * P, Lt),
+                                          token_type_ids=bi["token_type_ids"].reshape(B * P, Lt),
+                                          attention_mask=bi["attention_mask"].reshape(B * P, Lt), visual_feats=im)
+        c.update(N=N, W=W, L=L, seed=seed, image_checksum=float(images.double().sum()),
+                 tower=tower[:3].clone(), lang=lang[:3].clone(), visn=visn[:3].clone(), pooled=pooled.clone())
+        out["cases"].append(c)
+    return out
+
+
 def gen_decode_full(ns):
     H = 768
     out = dict(H=H, cases=[])
@@ -239,13 +269,18 @@ def gen_pointer_p1(ns):
 
 def main():
     ns = rh.load()
+    if "--only-rn" in sys.argv:   # regenerate just the RN fixture (each generator seeds itself)
+        torch.save(gen_mm_rn(ns), os.path.join(HERE, "mm_rn_tiny.pt"))
+        print("mm_rn_tiny.pt", os.path.getsize(os.path.join(HERE, "mm_rn_tiny.pt")) // 1024, "KiB")
+        return
     torch.save(gen_text(ns), os.path.join(HERE, "text_tiny.pt"))
     mm = gen_mm(ns)
     torch.save(mm, os.path.join(HERE, "mm_tiny.pt"))
     torch.save(gen_topo(ns, mm), os.path.join(HERE, "topo_tiny.pt"))
+    torch.save(gen_mm_rn(ns), os.path.join(HERE, "mm_rn_tiny.pt"))
     torch.save(gen_decode_full(ns), os.path.join(HERE, "decode_full.pt"))
     torch.save(gen_pointer_p1(ns), os.path.join(HERE, "pointer_p1.pt"))
-    for f in ("text_tiny.pt", "mm_tiny.pt", "topo_tiny.pt", "decode_full.pt", "pointer_p1.pt"):
+    for f in ("text_tiny.pt", "mm_tiny.pt", "topo_tiny.pt", "mm_rn_tiny.pt", "decode_full.pt", "pointer_p1.pt"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 

@@ -87,6 +87,8 @@ def load():
     fake_clip._vit_cfg = dict(embed_dim=512, image_resolution=224, vision_layers=12, vision_width=768,
                               vision_patch_size=32)
 
+    fake_clip._rn_cfg = dict(embed_dim=1024, image_resolution=224, vision_layers=(3, 4, 6, 3), vision_width=64)
+
     def clip_load(name, device="cpu", jit=False, img_len=None, img_only=False):
         if name == "ViT-B/32":
             c = fake_clip._vit_cfg
@@ -94,8 +96,9 @@ def load():
                                     c["vision_patch_size"], 77, 49408, 512, 8, 12, img_len=img_len,
                                     img_only=img_only)
         elif name == "RN50":
-            m = clip_model_mod.CLIP(1024, 224, (3, 4, 6, 3), 64, None, 77, 49408, 512, 8, 12, img_len=img_len,
-                                    img_only=img_only)
+            c = fake_clip._rn_cfg
+            m = clip_model_mod.CLIP(c["embed_dim"], c["image_resolution"], tuple(c["vision_layers"]), c["vision_width"],
+                                    None, 77, 49408, 512, 8, 12, img_len=img_len, img_only=img_only)
         else:
             raise RuntimeError(name)
         return m.eval().float(), None
@@ -150,14 +153,21 @@ def build_text_model(ns, cfg_kwargs, args, seed=0):
     return m.eval()
 
 
-def build_multimodal_model(ns, cfg_kwargs, args, vit_cfg=None, seed=0):
-    """BertForOrdering around LXRTModel + CLIP ViT tower (train.py:1869-1880, 2024-2028)."""
+def build_multimodal_model(ns, cfg_kwargs, args, vit_cfg=None, seed=0, rn_cfg=None):
+    """BertForOrdering around LXRTModel + CLIP tower (train.py:1869-1880, 2024-2028).  vit_cfg -> ViT-B/32-shaped tower
+    with skip_last_layer=True; rn_cfg -> the "RN50" ModifiedResNet branch exactly as wired (skip_last_layer=False,
+    visual_feat_dim = 2*embed_dim), BatchNorm statistics randomised so eval-mode BN is not the identity."""
     torch.manual_seed(seed)
-    if vit_cfg is not None:
-        ns.fake_clip._vit_cfg = dict(vit_cfg)
-    width = ns.fake_clip._vit_cfg["vision_width"]
+    name = "RN50" if rn_cfg is not None else "ViT-B/32"
+    if rn_cfg is not None:
+        ns.fake_clip._rn_cfg = dict(rn_cfg)
+        width = 2 * rn_cfg["embed_dim"]
+    else:
+        if vit_cfg is not None:
+            ns.fake_clip._vit_cfg = dict(vit_cfg)
+        width = ns.fake_clip._vit_cfg["vision_width"]
     ns.param.VISUAL_CONFIG.set_visual_dims(width, 4)
-    ns.param.VISUAL_CONFIG.clip_model_name = "ViT-B/32"
+    ns.param.VISUAL_CONFIG.clip_model_name = name
     cfg = ns.BersonBertConfig(**cfg_kwargs)
     cfg.wrapper_model_with_heatmap = False
     cfg.v_feature_size = 1024
@@ -168,8 +178,17 @@ def build_multimodal_model(ns, cfg_kwargs, args, vit_cfg=None, seed=0):
     with contextlib.redirect_stdout(io.StringIO()):
         inner = ns.lxrt.LXRTModel(lxcfg, multimodal_text_part=False, multimodal_img_part=False,
                                   cls_id=101, sep_id=102, max_story_length=args.max_story_length,
-                                  clip_model_name="ViT-B/32")
-    inner.encoder.skip_last_layer = True
+                                  clip_model_name=name)
+    if rn_cfg is None:
+        inner.encoder.skip_last_layer = True
+    else:
+        g = torch.Generator().manual_seed(seed + 77)
+        for mod in inner.encoder.visual_model.visual.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=g) * 0.1)
+                mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) * 0.5 + 0.75)
+                mod.weight.data.copy_(torch.rand(mod.weight.shape, generator=g) * 0.5 + 0.75)
+                mod.bias.data.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)
     m = ns.berson.BertForOrdering(cfg, args, tokenizer=StubTokenizer())
     m.bert = inner
     return m.eval()

@@ -20,7 +20,7 @@ def _load(golden_dir, name):
 def _cfg(g):
     c = g["cfg"]
     return dict(num_hidden_layers=c["num_hidden_layers"], num_attention_heads=c["num_attention_heads"],
-                vit=g.get("vit"))
+                vit=g.get("vit"), rn=g.get("rn"))
 
 
 def _check_case(sd, cfg, c, images=None):
@@ -68,6 +68,25 @@ def test_mm_tiny(golden_dir):
         lang, visn, pooled = O.lxrt_forward(g["sd"], _cfg(g), inp["input_ids"].reshape(B * P, Lt)[:3],
                                             inp["token_type_ids"].reshape(B * P, Lt)[:3],
                                             inp["attention_mask"].reshape(B * P, Lt)[:3], im[:6])
+        assert (lang - c["lang"]).abs().max() < TOL and (visn - c["visn"]).abs().max() < TOL
+        assert (pooled - c["pooled"][:3]).abs().max() < TOL
+
+
+def test_mm_rn_tiny(golden_dir):
+    """The "RN50" branch (ModifiedResNet + AttentionPool2d + visual_pos / visual_token_type) on a narrow tower."""
+    g = _load(golden_dir, "mm_rn_tiny.pt")
+    for c in g["cases"]:
+        ids, labels, images = O.synthetic_manuals(1, c["N"], c["L"], vocab=1000, image_px=224, seed=c["seed"])
+        assert abs(float(images.double().sum()) - c["image_checksum"]) < 1e-6, "torch RNG drift"
+        _check_case(g["sd"], _cfg(g), c, images)
+        inp = O.prepare_inputs(ids, labels, c["N"], images)
+        B, P, Lt = inp["input_ids"].shape
+        im = inp["images"].reshape(B * P * 2, 3, 224, 224)
+        tower = O.rn_pair_tower(g["sd"], "bert.encoder.visual_model.visual.", im[:6], g["rn"])
+        assert (tower - c["tower"]).abs().max() < TOL
+        lang, visn, pooled = O.lxrt_forward_rn(g["sd"], _cfg(g), inp["input_ids"].reshape(B * P, Lt)[:3],
+                                               inp["token_type_ids"].reshape(B * P, Lt)[:3],
+                                               inp["attention_mask"].reshape(B * P, Lt)[:3], im[:6])
         assert (lang - c["lang"]).abs().max() < TOL and (visn - c["visn"]).abs().max() < TOL
         assert (pooled - c["pooled"][:3]).abs().max() < TOL
 
