@@ -40,6 +40,14 @@ typedef struct msq_config {
   int32_t para_layers;   /* 2 */
   int32_t precise;       /* 0: bf16 tcgen05 tensor-core encoder; 1: fp32 FFMA encoder (parity mode) */
   int32_t reserved;
+  /* CLIP ModifiedResNet backbone ("RN50", models/CLIP/clip/model.py:128-187), the reference's wired default
+   * (param.py VISUAL_CONFIG.clip_model_name).  rn_width != 0 selects it; then vit_width must hold the tower's
+   * OUTPUT feature size 2*rn_embed (model.py:106 concatenates the pooled tokens with themselves), vit_layers 0,
+   * vit_patch 32 (total stride), vit_res the image size. */
+  int32_t rn_width;      /* 64 */
+  int32_t rn_blocks[4];  /* 3,4,6,3 */
+  int32_t rn_embed;      /* 1024 (attnpool output_dim) */
+  int32_t reserved2[2];
 } msq_config;
 
 const char* msq_last_error(void);

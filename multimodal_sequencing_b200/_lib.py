@@ -12,7 +12,8 @@ LIB_PATH = os.path.join(HERE, "libmsq_b200.so")
 class MsqConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "hidden", "layers", "heads", "inter", "vocab", "max_pos", "type_vocab", "vit_width", "vit_layers",
-        "vit_patch", "vit_res", "para_heads", "para_ff", "para_layers", "precise", "reserved")]
+        "vit_patch", "vit_res", "para_heads", "para_ff", "para_layers", "precise", "reserved", "rn_width",
+        "rn_blocks0", "rn_blocks1", "rn_blocks2", "rn_blocks3", "rn_embed", "reserved2", "reserved3")]
 
 
 class MsqEncodeOut(C.Structure):

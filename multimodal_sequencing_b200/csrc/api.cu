@@ -109,6 +109,7 @@ struct LNp { const float* g = nullptr; const float* b = nullptr; };
 struct BertLayerW { Lin qkv, out, up, down; LNp ln1, ln2; };
 struct VitLayerW { Lin qkv, out, fc, proj; LNp ln1, ln2; };
 struct ParaLayerW { Lin qkv, fin, w1, w2; LNp ln_in, ln_ff; };
+struct RnBlockW { Lin c1, c2, c3, ds; bool has_ds = false; int stride = 1, cin = 0, planes = 0; };
 
 }  // namespace msq
 
@@ -131,6 +132,10 @@ struct msq_model {
   const float *vit_cls = nullptr, *vit_pos = nullptr;
   LNp ln_pre, ln_post, visn_ln;
   std::vector<VitLayerW> vit;
+  // CLIP ModifiedResNet tower (cfg.rn_width != 0)
+  Lin rn_stem[3], rn_qkv, rn_cproj;
+  std::vector<RnBlockW> rn_blocks;
+  const float *rn_pos = nullptr, *rn_posadd = nullptr;
   // berson heads
   Lin sent_tran, key_lin, xg_lin, t4_lin, pwk_raw, wih_raw, whh_raw, wq_raw;
   int Kp4 = 0;
@@ -299,6 +304,9 @@ __global__ void training_loss_kernel(const float* __restrict__ nll, const float*
   if (threadIdx.x == 0) out[0] = sh[0] / (float)B;
 }
 
+// K of a convolution GEMM, padded so that the tcgen05 path (64-wide K slabs) applies whenever K >= 64
+static int rn_kpad(int K) { return K < 64 ? (K + 15) / 16 * 16 : (K + 63) / 64 * 64; }
+
 static bool use_tc(const msq_model* m) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("MSQ_FORCE_SIMT"); forced = (e && e[0] == '1') ? 1 : 0; }
@@ -318,7 +326,8 @@ static int run_gemm(const msq_model* m, const T* A, int lda, const Lin& w, const
   } else {
     g.W = w.w16;
     MSQ_REQUIRE(w.w16 != nullptr, "bf16 weight copy missing");
-    if (use_tc(m)) return gemm_tc<TO>(g, st);
+    // narrow convolutions of the ResNet stem (K = 27 -> 32, N = 32) stay on the FFMA kernel
+    if (use_tc(m) && g.K % 64 == 0 && g.N % 8 == 0 && ldc % 8 == 0) return gemm_tc<TO>(g, st);
     return gemm_simt<bf16, TO>(g, st);
   }
 }
@@ -363,7 +372,12 @@ extern "C" int msq_model_create(const msq_config* cfg, msq_model** out) {
   MSQ_REQUIRE(cfg->hidden % 128 == 0 && cfg->hidden <= 1024, "hidden=%d must be a multiple of 128, <= 1024", cfg->hidden);
   MSQ_REQUIRE(cfg->heads * 64 == cfg->hidden, "head dim must be 64 (hidden=%d heads=%d)", cfg->hidden, cfg->heads);
   MSQ_REQUIRE(cfg->inter % 16 == 0 && cfg->layers >= 0, "bad inter/layers");
-  if (cfg->vit_width) {
+  if (cfg->rn_width) {
+    MSQ_REQUIRE(cfg->rn_width % 8 == 0 && cfg->rn_embed % 32 == 0 && cfg->vit_width == 2 * cfg->rn_embed && cfg->vit_layers == 0 &&
+                    cfg->vit_patch == 32 && cfg->vit_res % 32 == 0,
+                "ResNet tower: need rn_width %% 8 == 0, vit_width == 2*rn_embed, vit_layers == 0, vit_patch == 32");
+    for (int i = 0; i < 4; ++i) MSQ_REQUIRE(cfg->rn_blocks[i] >= 1, "rn_blocks[%d]=%d", i, cfg->rn_blocks[i]);
+  } else if (cfg->vit_width) {
     MSQ_REQUIRE(cfg->vit_width % 128 == 0 && cfg->vit_width <= 1024, "vit_width=%d unsupported", cfg->vit_width);
     MSQ_REQUIRE(cfg->vit_res % cfg->vit_patch == 0 && cfg->vit_patch % 4 == 0, "vit patch/res");
   }
@@ -401,7 +415,11 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
   const bool w16 = !c.precise;
   std::string miss;
   const std::string P = m->prefix_inner;
-  auto W = [&](const std::string& n, int64_t numel) { const float* p; get_raw(m, n, numel, &p, &miss); return p; };
+  auto W = [&](const std::string& n, int64_t numel) {
+    const float* p = nullptr;
+    if (get_raw(m, n, numel, &p, &miss) != MSQ_OK) { miss += n + "(wrong size) "; p = nullptr; }
+    return p;
+  };
   // first make sure everything is there (collect all missing names)
   std::vector<std::string> need;
   auto lin_names = [&](const std::string& n) { need.push_back(n + ".weight"); need.push_back(n + ".bias"); };
@@ -420,7 +438,25 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
                           "attention.output.LayerNorm", "intermediate.dense", "output.dense", "output.LayerNorm"})
       lin_names(b + e);
   }
-  if (m->has_vit) {
+  auto bn_names = [&](const std::string& n) { for (const char* e : {".weight", ".bias", ".running_mean", ".running_var"}) need.push_back(n + e); };
+  if (m->has_vit && c.rn_width) {
+    const std::string v = P + "encoder.visual_model.visual.";
+    for (int i = 1; i <= 3; ++i) { need.push_back(v + "conv" + std::to_string(i) + ".weight"); bn_names(v + "bn" + std::to_string(i)); }
+    for (int s = 0; s < 4; ++s)
+      for (int b = 0; b < c.rn_blocks[s]; ++b) {
+        const std::string k = v + "layer" + std::to_string(s + 1) + "." + std::to_string(b) + ".";
+        for (int i = 1; i <= 3; ++i) { need.push_back(k + "conv" + std::to_string(i) + ".weight"); bn_names(k + "bn" + std::to_string(i)); }
+        if (b == 0) { need.push_back(k + "downsample.0.weight"); bn_names(k + "downsample.1"); }
+      }
+    need.push_back(v + "attnpool.positional_embedding");
+    for (const char* e : {"attnpool.q_proj", "attnpool.k_proj", "attnpool.v_proj", "attnpool.c_proj"}) lin_names(v + e);
+    if (m->has_bert) {
+      need.push_back(P + "encoder.visual_pos.x_position_embedding.weight");
+      need.push_back(P + "encoder.visual_pos.y_position_embedding.weight");
+      need.push_back(P + "encoder.visual_token_type.token_type_embedding.weight");
+      lin_names(P + "encoder.visn_fc.visn_fc"); lin_names(P + "encoder.visn_fc.visn_layer_norm");
+    }
+  } else if (m->has_vit) {
     const std::string v = P + "encoder.visual_model.visual.";
     need.push_back(v + "conv1.weight"); need.push_back(v + "class_embedding"); need.push_back(v + "positional_embedding");
     lin_names(v + "ln_pre"); lin_names(v + "ln_post");
@@ -485,6 +521,67 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
     m->has_pooler = true;
   }
   }
+  // ---- ModifiedResNet tower: BatchNorm folded into [Cout, kh*kw*Cin] GEMM weights
+  if (m->has_vit && c.rn_width) {
+    const std::string v = P + "encoder.visual_model.visual.";
+    const int w = c.rn_width, Cf = 32 * w, E = c.rn_embed, F = 2 * E, g = c.vit_res / 32, g2 = g * g;
+    auto conv = [&](const std::string& cw, const std::string& bn, int cout, int cin, int k, Lin* out) -> int {
+      const int K = k * k * cin;
+      MSQ_REQUIRE(k != 1 || rn_kpad(K) == K, "ResNet tower: 1x1 convolution with %d input channels is not GEMM-aligned", cin);
+      float *wf, *bf;
+      MSQ_TRY(dev_alloc(m, (size_t)cout * K, &wf));
+      MSQ_TRY(dev_alloc(m, (size_t)cout, &bf));
+      const float *pw = W(cw, (int64_t)cout * K), *pg = W(bn + ".weight", cout), *pb = W(bn + ".bias", cout),
+                  *pm = W(bn + ".running_mean", cout), *pv = W(bn + ".running_var", cout);
+      if (!pw || !pg || !pb || !pm || !pv) return MSQ_ERR_WEIGHT;
+      MSQ_TRY(rn_fold(pw, pg, pb, pm, pv, cout, cin, k, wf, bf, st));
+      return make_lin(m, wf, bf, cout, K, rn_kpad(K), w16, out, st);
+    };
+    MSQ_TRY(conv(v + "conv1.weight", v + "bn1", w / 2, 3, 3, &m->rn_stem[0]));
+    MSQ_TRY(conv(v + "conv2.weight", v + "bn2", w / 2, w / 2, 3, &m->rn_stem[1]));
+    MSQ_TRY(conv(v + "conv3.weight", v + "bn3", w, w / 2, 3, &m->rn_stem[2]));
+    int cin = w;
+    for (int s = 0; s < 4; ++s)
+      for (int b = 0; b < c.rn_blocks[s]; ++b) {
+        const std::string k = v + "layer" + std::to_string(s + 1) + "." + std::to_string(b) + ".";
+        RnBlockW B;
+        B.planes = w << s; B.cin = cin; B.stride = (b == 0 && s > 0) ? 2 : 1; B.has_ds = b == 0;
+        MSQ_TRY(conv(k + "conv1.weight", k + "bn1", B.planes, cin, 1, &B.c1));
+        MSQ_TRY(conv(k + "conv2.weight", k + "bn2", B.planes, B.planes, 3, &B.c2));
+        MSQ_TRY(conv(k + "conv3.weight", k + "bn3", 4 * B.planes, B.planes, 1, &B.c3));
+        if (B.has_ds) MSQ_TRY(conv(k + "downsample.0.weight", k + "downsample.1", 4 * B.planes, cin, 1, &B.ds));
+        cin = 4 * B.planes;
+        m->rn_blocks.push_back(B);
+      }
+    const std::string a = v + "attnpool.";
+    m->rn_pos = W(a + "positional_embedding", (int64_t)(g2 + 1) * Cf);
+    const float *wq, *bq;
+    MSQ_TRY(concat3(m, W(a + "q_proj.weight", (int64_t)Cf * Cf), W(a + "k_proj.weight", (int64_t)Cf * Cf), W(a + "v_proj.weight", (int64_t)Cf * Cf),
+                    (int64_t)Cf * Cf, (int64_t)Cf * Cf, (int64_t)Cf * Cf, &wq, st));
+    MSQ_TRY(concat3(m, W(a + "q_proj.bias", Cf), W(a + "k_proj.bias", Cf), W(a + "v_proj.bias", Cf), Cf, Cf, Cf, &bq, st));
+    MSQ_TRY(make_lin(m, wq, bq, 3 * Cf, Cf, Cf, w16, &m->rn_qkv, st));
+    MSQ_TRY(make_lin(m, W(a + "c_proj.weight", (int64_t)E * Cf), W(a + "c_proj.bias", E), E, Cf, Cf, w16, &m->rn_cproj, st));
+    if (m->has_bert) {
+      auto tab = [&](const std::string& n) -> const float* {   // embedding tables: only the first rows are addressed
+        auto it = m->raw.find(n);
+        return it == m->raw.end() ? nullptr : it->second.first;
+      };
+      const float* xe = tab(P + "encoder.visual_pos.x_position_embedding.weight");
+      const float* ye = tab(P + "encoder.visual_pos.y_position_embedding.weight");
+      const float* te = tab(P + "encoder.visual_token_type.token_type_embedding.weight");
+      MSQ_REQUIRE(m->raw[P + "encoder.visual_pos.x_position_embedding.weight"].second >= (int64_t)g * F &&
+                      m->raw[P + "encoder.visual_pos.y_position_embedding.weight"].second >= (int64_t)g * F &&
+                      m->raw[P + "encoder.visual_token_type.token_type_embedding.weight"].second >= (int64_t)2 * F,
+                  "visual_pos / visual_token_type tables are smaller than the %dx%d grid needs", g, g);
+      float* pa;
+      MSQ_TRY(dev_alloc(m, (size_t)(1 + 2 * g2) * F, &pa));
+      MSQ_TRY(rn_posadd(xe, ye, te, g, F, pa, st));
+      m->rn_posadd = pa;
+      MSQ_TRY(make_lin(m, W(P + "encoder.visn_fc.visn_fc.weight", (int64_t)H * F), W(P + "encoder.visn_fc.visn_fc.bias", H), H, F, F,
+                       w16, &m->visn_fc, st));
+      m->visn_ln = {W(P + "encoder.visn_fc.visn_layer_norm.weight", H), W(P + "encoder.visn_fc.visn_layer_norm.bias", H)};
+    }
+  } else
   // ---- ViT tower
   if (m->has_vit) {
     const int Wd = c.vit_width, g = c.vit_res / c.vit_patch, Kc = 3 * c.vit_patch * c.vit_patch;
@@ -592,6 +689,8 @@ namespace msq {
 
 struct VitBufs {
   void* apatch; float* patch; float* xv; void* y; void* qkv; void* ctx; void* hbuf;
+  // ModifiedResNet trunk scratch (per image chunk): block input / 1x1 out / 3x3 out / pooled copies, fp32 residual + shortcut
+  void *rX, *rO1, *rO2, *rP1, *rP2; float *rF0, *rF1;
 };
 constexpr int64_t IMG_CHUNK = 1024;  // images per im2col + patch-embed GEMM launch
 
@@ -665,6 +764,117 @@ static int run_vit(msq_model* m, const int32_t* img_index, int64_t R, VitBufs& b
   return MSQ_OK;
 }
 
+// ---- CLIP ModifiedResNet tower ---------------------------------------------------------------------
+constexpr int64_t RN_IMG_CHUNK = 64;  // images per trunk pass (bounds the im2col scratch: 8 MB / image in bf16 at width 64)
+
+struct RnDims { size_t a = 0, t = 0, f = 0; };  // per-image element counts: im2col rows, operand-type maps, fp32 maps
+static RnDims rn_dims(const msq_config& c) {
+  RnDims d;
+  auto up = [](size_t& x, size_t v) { if (v > x) x = v; };
+  const int w = c.rn_width, w2 = w / 2;
+  size_t H = c.vit_res / 2;
+  up(d.a, H * H * rn_kpad(27)); up(d.a, H * H * rn_kpad(9 * w2));
+  up(d.t, H * H * w);
+  H /= 2;
+  size_t cin = w;
+  for (int s = 0; s < 4; ++s)
+    for (int b = 0; b < c.rn_blocks[s]; ++b) {
+      const size_t p = (size_t)w << s, st = (b == 0 && s > 0) ? 2 : 1, Ho = H / st;
+      up(d.t, H * H * cin); up(d.t, H * H * p); up(d.a, H * H * rn_kpad(9 * (int)p));
+      up(d.t, Ho * Ho * 4 * p); up(d.f, Ho * Ho * 4 * p);
+      H = Ho; cin = 4 * p;
+    }
+  return d;
+}
+
+template <typename T>
+static void plan_rn(const msq_config& c, Planner& p, int64_t n_img, int64_t R, VitBufs* b) {
+  const int g2 = (c.vit_res / 32) * (c.vit_res / 32), Lv = 1 + 2 * g2, Cf = 32 * c.rn_width, E = c.rn_embed;
+  const RnDims d = rn_dims(c);
+  const size_t nc = (size_t)min(n_img, RN_IMG_CHUNK);
+  b->apatch = p.take<T>(nc * d.a);
+  b->rX = p.take<T>(nc * d.t); b->rO1 = p.take<T>(nc * d.t); b->rO2 = p.take<T>(nc * d.t);
+  b->rP1 = p.take<T>(nc * d.t); b->rP2 = p.take<T>(nc * d.t);
+  b->rF0 = p.take<float>(nc * d.f); b->rF1 = p.take<float>(nc * d.f);
+  b->patch = p.take<float>((size_t)n_img * g2 * Cf);     // trunk output, NHWC, per UNIQUE image
+  b->hbuf = p.take<T>((size_t)R * Lv * Cf);               // attnpool token matrix
+  b->qkv = p.take<T>((size_t)R * Lv * 3 * Cf);
+  b->ctx = p.take<T>((size_t)R * Lv * Cf);
+  b->xv = p.take<float>((size_t)R * Lv * E);              // c_proj output
+  b->y = p.take<T>((size_t)R * Lv * 2 * E);               // cat(o, o) + visual_pos + visual_token_type
+}
+
+// stem + the four bottleneck stages over UNIQUE images [first, first + n_img) -> b.patch rows [img, g2, 32*width]
+template <typename T>
+static int run_rn_trunk(msq_model* m, const float* images, int64_t n_img, VitBufs& b, cudaStream_t st, int64_t first = 0) {
+  const msq_config& c = m->cfg;
+  const int S = c.vit_res, w = c.rn_width, Cf = 32 * w, g2 = (S / 32) * (S / 32);
+  const int64_t img_elems = (int64_t)3 * S * S;
+  T *A = (T*)b.apatch, *X = (T*)b.rX, *O1 = (T*)b.rO1, *O2 = (T*)b.rO2, *P1 = (T*)b.rP1, *P2 = (T*)b.rP2;
+  for (int64_t i0 = first; i0 < first + n_img; i0 += RN_IMG_CHUNK) {
+    const int64_t n = min(RN_IMG_CHUNK, first + n_img - i0);
+    int H = S / 2;
+    int64_t M = n * H * H;
+    MSQ_TRY(rn_im2col_stem<T>(images + i0 * img_elems, n, S, m->rn_stem[0].K, A, st));
+    MSQ_TRY((run_gemm<T, T>(m, A, m->rn_stem[0].K, m->rn_stem[0], nullptr, 0, O1, w / 2, M, ACT_RELU, st)));
+    MSQ_TRY(rn_im2col3<T>(O1, n, H, H, w / 2, m->rn_stem[1].K, A, st));
+    MSQ_TRY((run_gemm<T, T>(m, A, m->rn_stem[1].K, m->rn_stem[1], nullptr, 0, O2, w / 2, M, ACT_RELU, st)));
+    MSQ_TRY(rn_im2col3<T>(O2, n, H, H, w / 2, m->rn_stem[2].K, A, st));
+    MSQ_TRY((run_gemm<T, T>(m, A, m->rn_stem[2].K, m->rn_stem[2], nullptr, 0, O1, w, M, ACT_RELU, st)));
+    MSQ_TRY(rn_avgpool2<T>(O1, n, H, H, w, X, st));
+    H /= 2;
+    for (const RnBlockW& B : m->rn_blocks) {
+      const int p = B.planes, Ho = H / B.stride;
+      M = n * H * H;
+      const int64_t Mo = n * Ho * Ho;
+      MSQ_TRY((run_gemm<T, T>(m, X, B.cin, B.c1, nullptr, 0, O1, p, M, ACT_RELU, st)));
+      MSQ_TRY(rn_im2col3<T>(O1, n, H, H, p, B.c2.K, A, st));
+      MSQ_TRY((run_gemm<T, T>(m, A, B.c2.K, B.c2, nullptr, 0, O2, p, M, ACT_RELU, st)));
+      const T *o2 = O2, *xs = X;
+      if (B.stride > 1) {
+        MSQ_TRY(rn_avgpool2<T>(O2, n, H, H, p, P1, st));
+        MSQ_TRY(rn_avgpool2<T>(X, n, H, H, B.cin, P2, st));
+        o2 = P1; xs = P2;
+      }
+      if (B.has_ds) MSQ_TRY((run_gemm<T, float>(m, xs, B.cin, B.ds, nullptr, 0, b.rF1, 4 * p, Mo, ACT_NONE, st)));
+      MSQ_TRY((run_gemm<T, float>(m, o2, p, B.c3, B.has_ds ? b.rF1 : b.rF0, 4 * p, b.rF0, 4 * p, Mo, ACT_NONE, st)));
+      MSQ_TRY(rn_relu_cast<T>(b.rF0, Mo * 4 * p, X, st));
+      H = Ho;
+    }
+    MSQ_CUDA(cudaMemcpyAsync(b.patch + i0 * g2 * Cf, b.rF0, (size_t)n * g2 * Cf * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  return MSQ_OK;
+}
+
+// AttentionPool2d over R pair rows: token matrix (reference's reshape quirk included) -> MHA over all 1+2g^2 tokens ->
+// c_proj -> b.xv [R*Lv, E] fp32; b.y = cat(o, o) + posadd in the GEMM operand type (input of visn_fc).
+template <typename T>
+static int run_rn_pool(msq_model* m, const int32_t* img_index, int64_t R, VitBufs& b, cudaStream_t st) {
+  const msq_config& c = m->cfg;
+  const int g2 = (c.vit_res / 32) * (c.vit_res / 32), Lv = 1 + 2 * g2, Cf = 32 * c.rn_width, E = c.rn_embed;
+  const int64_t Mv = R * Lv;
+  MSQ_TRY(rn_tokens<T>(b.patch, img_index, R, g2, Cf, m->rn_pos, (T*)b.hbuf, st));
+  MSQ_TRY((run_gemm<T, T>(m, (const T*)b.hbuf, Cf, m->rn_qkv, nullptr, 0, (T*)b.qkv, 3 * Cf, Mv, ACT_NONE, st)));
+  MSQ_TRY(attention<T>((const T*)b.qkv, R, Lv, Cf / 64, 64, 0.125f, nullptr, 0, 0, (T*)b.ctx, st));
+  MSQ_TRY((run_gemm<T, float>(m, (const T*)b.ctx, Cf, m->rn_cproj, nullptr, 0, b.xv, E, Mv, ACT_NONE, st)));
+  if (m->rn_posadd) MSQ_TRY(rn_finish<T>(b.xv, Mv, Lv, E, m->rn_posadd, (T*)b.y, st));
+  return MSQ_OK;
+}
+
+// backbone dispatch: per-image part (patch embedding / ResNet trunk) and per-pair part (transformer / attention pool)
+template <typename T>
+static void plan_visual(const msq_config& c, Planner& p, int64_t n_img, int64_t R, VitBufs* b) {
+  if (c.rn_width) plan_rn<T>(c, p, n_img, R, b); else plan_vit<T>(c, p, n_img, R, b);
+}
+template <typename T>
+static int run_visual_images(msq_model* m, const float* images, int64_t n_img, VitBufs& b, cudaStream_t st, int64_t first = 0) {
+  return m->cfg.rn_width ? run_rn_trunk<T>(m, images, n_img, b, st, first) : run_patch_embed<T>(m, images, n_img, b, st, first);
+}
+template <typename T>
+static int run_visual_pairs(msq_model* m, const int32_t* img_index, int64_t R, VitBufs& b, cudaStream_t st) {
+  return m->cfg.rn_width ? run_rn_pool<T>(m, img_index, R, b, st) : run_vit<T>(m, img_index, R, b, st);
+}
+
 struct JointBufs {
   float* x; void* xt; float* tmp; void* qkv; void* ctx; void* hbuf; float* mask_add; float* vtmp;
 };
@@ -697,7 +907,7 @@ static int run_inner(msq_model* m, const int64_t* ids, const int64_t* tt, const 
   MSQ_CUDA(launch_k(mask_add_kernel, dim3(ceil_div(R * Lt, 256)), dim3(256), 0, st, mask, R * Lt, jb.mask_add));
   MSQ_LAUNCH_CHECK();
   if (mm) {
-    MSQ_TRY(run_vit<T>(m, img_index, R, vb, st));
+    MSQ_TRY(run_visual_pairs<T>(m, img_index, R, vb, st));
     const int Wd = c.vit_width;
     const int64_t Mv = R * Lv;
     // vb.y == ln_post(x); visn_fc output reuses the (now free) fp32 tmp buffer of the joint stream
@@ -841,7 +1051,7 @@ static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const i
   for (int pass = 0; pass < 2; ++pass) {
     Planner p{&m->ws, pass == 0};
     if (pass == 1) m->ws.reset();
-    if (mm) plan_vit<T>(c, p, n_img, Rc, &vb);
+    if (mm) plan_visual<T>(c, p, n_img, Rc, &vb);
     plan_joint<T>(c, p, Rc, Lt, Lj, &jb);
     plan_heads<T>(c, p, B, N, Rc, Lt, m->Kp, &hb);
     if (pass == 0) MSQ_TRY(m->ws.reserve(p.need + 4096, st));
@@ -849,13 +1059,13 @@ static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const i
   // patch embedding once per UNIQUE image, not per pair slot.  When the caller streams the images in manual order
   // (img_ready != nullptr: images of manuals [b0, b0+bc) are rows [b0*N, (b0+bc)*N), one event per micro-batch),
   // each micro-batch embeds its own images as soon as its host->device copy has landed.
-  if (mm && !img_ready) MSQ_TRY(run_patch_embed<T>(m, images, n_img, vb, st));
+  if (mm && !img_ready) MSQ_TRY(run_visual_images<T>(m, images, n_img, vb, st));
 
   for (int64_t b0 = 0; b0 < B; b0 += Bc) {
     const int64_t bc = min(Bc, B - b0), rc = bc * P, r0 = b0 * P;
     if (mm && img_ready) {
       MSQ_CUDA(cudaStreamWaitEvent(st, img_ready[b0 / Bc], 0));
-      MSQ_TRY(run_patch_embed<T>(m, images, bc * N, vb, st, b0 * N));
+      MSQ_TRY(run_visual_images<T>(m, images, bc * N, vb, st, b0 * N));
     }
     MSQ_TRY((run_inner<T>(m, ids + r0 * Lt, tt + r0 * Lt, mask + r0 * Lt, rc, Lt, mm ? img_index + r0 * 2 : nullptr, vb, jb, st)));
     // ---- pooling for this chunk
@@ -914,11 +1124,12 @@ extern "C" int msq_vit_forward(msq_model* m, const float* images_dev, int64_t n_
     for (int pass = 0; pass < 2; ++pass) {
       Planner p{&m->ws, pass == 0};
       if (pass == 1) m->ws.reset();
-      plan_vit<T>(c, p, n_img, R, &vb);
+      plan_visual<T>(c, p, n_img, R, &vb);
       if (pass == 0) MSQ_TRY(m->ws.reserve(p.need + 4096, st));
     }
-    MSQ_TRY(run_patch_embed<T>(m, images_dev, n_img, vb, st));
-    MSQ_TRY(run_vit<T>(m, img_index_dev, R, vb, st));
+    MSQ_TRY(run_visual_images<T>(m, images_dev, n_img, vb, st));
+    MSQ_TRY(run_visual_pairs<T>(m, img_index_dev, R, vb, st));
+    if (c.rn_width) return rn_finish<float>(vb.xv, R * Lv, Lv, c.rn_embed, nullptr, out_dev, st);  // cat([x, x]) (model.py:106)
     return layernorm<float>(vb.xv, R * Lv, c.vit_width, m->ln_post.g, m->ln_post.b, 1e-5f, out_dev, nullptr, 0, 0, 0, st);
   };
   return c.precise ? go(float()) : go(bf16());
@@ -939,11 +1150,11 @@ extern "C" int msq_inner_forward(msq_model* m, const int64_t* ids_dev, const int
     for (int pass = 0; pass < 2; ++pass) {
       Planner p{&m->ws, pass == 0};
       if (pass == 1) m->ws.reset();
-      if (mm) plan_vit<T>(c, p, n_img, R, &vb);
+      if (mm) plan_visual<T>(c, p, n_img, R, &vb);
       plan_joint<T>(c, p, R, Lt, Lj, &jb);
       if (pass == 0) MSQ_TRY(m->ws.reserve(p.need + 4096, st));
     }
-    if (mm) MSQ_TRY(run_patch_embed<T>(m, images_dev, n_img, vb, st));
+    if (mm) MSQ_TRY(run_visual_images<T>(m, images_dev, n_img, vb, st));
     MSQ_TRY((run_inner<T>(m, ids_dev, tt_dev, mask_dev, R, Lt, mm ? img_index_dev : nullptr, vb, jb, st)));
     if (lang_dev) MSQ_TRY((gather_rows<float, float>(jb.x, R * Lt, H, Lt, Lj, 0, lang_dev, st)));
     if (visn_dev && mm) MSQ_TRY((gather_rows<float, float>(jb.x, R * Lv, H, Lv, Lj, Lt, visn_dev, st)));

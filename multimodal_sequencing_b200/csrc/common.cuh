@@ -78,7 +78,7 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
 }
 
 // activation selectors for GEMM epilogues
-enum Act { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_QUICK_GELU = 2, ACT_TANH = 3, ACT_GELU_TANH = 4 };
+enum Act { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_QUICK_GELU = 2, ACT_TANH = 3, ACT_GELU_TANH = 4, ACT_RELU = 5 };
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -96,6 +96,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     case ACT_GELU_ERF: return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
     case ACT_QUICK_GELU: return x / (1.0f + __expf(-1.702f * x));
     case ACT_TANH: return tanhf(x);
+    case ACT_RELU: return fmaxf(x, 0.f);
     case ACT_GELU_TANH: {
       float u = 0.79788456080286535588f * (x + 0.044715f * x * x * x);
       return 0.5f * x * (1.0f + tanhf(u));
@@ -141,6 +142,7 @@ __device__ __forceinline__ float apply_act_fast(float x, int act) {
       return fmaf(hx, tanh_approx(0.851f * x), hx);
     }
     case ACT_TANH: return tanh_approx(x);
+    case ACT_RELU: return fmaxf(x, 0.f);
     default: return apply_act(x, act);
   }
 }

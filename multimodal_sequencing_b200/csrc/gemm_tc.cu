@@ -410,6 +410,7 @@ static int launch_gemm_tc(const GemmArgs& g, int sms, cudaStream_t st) {
     case ACT_GELU_ERF: return launch_gemm_tc_act<TO, PAIR, ACT_GELU_ERF>(g, sms, st);
     case ACT_QUICK_GELU: return launch_gemm_tc_act<TO, PAIR, ACT_QUICK_GELU>(g, sms, st);
     case ACT_TANH: return launch_gemm_tc_act<TO, PAIR, ACT_TANH>(g, sms, st);
+    case ACT_RELU: return launch_gemm_tc_act<TO, PAIR, ACT_RELU>(g, sms, st);
   }
   set_error("gemm_tc: activation %d not supported on the tensor-core path", g.act);
   return MSQ_ERR_ARG;

@@ -22,6 +22,18 @@ template <typename TI, typename TO>
 int gather_rows(const TI* src, int64_t rows, int H, int group, int src_group, int off, TO* dst, cudaStream_t st);
 template <typename TO> int pack_pad(const float* src, int64_t rows, int K, int Kp, TO* dst, cudaStream_t st);
 
+// ---- rn.cu : CLIP ModifiedResNet helpers (NHWC activations; convolutions run as im2col + GEMM)
+int rn_fold(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, int Cout, int Cin, int k,
+            float* wf, float* bf, cudaStream_t st);
+int rn_posadd(const float* xe, const float* ye, const float* te, int g, int F, float* out, cudaStream_t st);
+template <typename T> int rn_im2col_stem(const float* img, int64_t n, int S, int Kp, T* out, cudaStream_t st);
+template <typename T> int rn_im2col3(const T* x, int64_t n, int H, int W, int C, int Kp, T* out, cudaStream_t st);
+template <typename T> int rn_avgpool2(const T* x, int64_t n, int H, int W, int C, T* out, cudaStream_t st);
+template <typename T> int rn_relu_cast(float* x, int64_t n, T* out, cudaStream_t st);
+template <typename T>
+int rn_tokens(const float* feat, const int32_t* img_index, int64_t R, int g2, int C, const float* pos, T* out, cudaStream_t st);
+template <typename T> int rn_finish(const float* o, int64_t rows, int L, int E, const float* posadd, T* out, cudaStream_t st);
+
 // ---- gemm_simt.cu : C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual), fp32 FFMA accumulate
 struct GemmArgs {
   const void* A;       // [M, lda]  (TA)

@@ -1,0 +1,256 @@
+// CLIP ModifiedResNet tower ("RN50", the reference's wired default backbone): the HBM-bound helpers around the
+// convolution GEMMs.  Activations are NHWC so that every convolution is `im2col rows x [Cout, kh*kw*Cin]^T` on the
+// same tcgen05 / FFMA GEMMs as the transformer layers; eval-mode BatchNorm is folded into the weights at pack time.
+//
+// Reference ops replaced (telin0411/multimodal_sequencing):
+//   Bottleneck.forward        models/CLIP/clip/model.py:10-53   (1x1 -> 3x3 -> AvgPool -> 1x1, AvgPool+1x1 shortcut)
+//   ModifiedResNet.forward    models/CLIP/clip/model.py:171-187 (3-conv stem, AvgPool2d(2), 4 stages, attnpool)
+//   AttentionPool2d.forward   models/CLIP/clip/model.py:71-125  (pair-joint token matrix, mean token, pos-emb,
+//                                                               MHA over all 1+2g^2 tokens, c_proj, cat([x,x]))
+//   LinearPositionEmbedding / VisualTokenTypeEmbedding  models/CLIP/src/lxrt/modeling.py:621-705
+#include "kernels.cuh"
+
+namespace msq {
+
+namespace {
+template <typename T> struct V4;
+template <> struct V4<float> {
+  static __device__ __forceinline__ float4 load(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void store(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct V4<bf16> {
+  static __device__ __forceinline__ float4 load(const bf16* p) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x), b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+  }
+  static __device__ __forceinline__ void store(bf16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+inline dim3 grid_for(int64_t work) { return dim3((unsigned)max((int64_t)1, min((int64_t)148 * 16, (work + 255) / 256))); }
+}  // namespace
+
+// ---- pack time: conv weight [Cout, Cin, k, k] + eval BatchNorm -> GEMM weight [Cout, k*k*Cin] ((ky,kx,c) order) + bias
+__global__ void rn_fold_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var, int Cout, int Cin, int k,
+                               float* __restrict__ wf, float* __restrict__ bf) {
+  pdl_sync();
+  const int K = k * k * Cin;
+  const int64_t total = (int64_t)Cout * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i / K), col = (int)(i % K);
+    const int c = col % Cin, kk = col / Cin, ky = kk / k, kx = kk % k;
+    const float s = gamma[o] / sqrtf(var[o] + 1e-5f);
+    wf[i] = w[(((int64_t)o * Cin + c) * k + ky) * k + kx] * s;
+    if (col == 0) bf[o] = beta[o] - mean[o] * s;
+  }
+}
+int rn_fold(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, int Cout, int Cin, int k,
+            float* wf, float* bf, cudaStream_t st) {
+  MSQ_CUDA(launch_k(rn_fold_kernel, grid_for((int64_t)Cout * Cin * k * k), dim3(256), 0, st, w, gamma, beta, mean, var, Cout, Cin, k,
+                    wf, bf));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+
+// ---- pack time: posadd[t, :] = x_emb[cell / g] + y_emb[cell % g] + type_emb[t > g2]   (t = 0: cell 0; lxrt/modeling.py:649-651, 691-696)
+__global__ void rn_posadd_kernel(const float* __restrict__ xe, const float* __restrict__ ye, const float* __restrict__ te, int g,
+                                 int F, float* __restrict__ out) {
+  pdl_sync();
+  const int g2 = g * g, L = 1 + 2 * g2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L * F; i += gridDim.x * blockDim.x) {
+    const int t = i / F, f = i % F;
+    const int cell = t == 0 ? 0 : (t - 1) % g2;
+    out[i] = xe[(cell / g) * F + f] + ye[(cell % g) * F + f] + te[(t > g2 ? 1 : 0) * F + f];
+  }
+}
+int rn_posadd(const float* xe, const float* ye, const float* te, int g, int F, float* out, cudaStream_t st) {
+  MSQ_CUDA(launch_k(rn_posadd_kernel, grid_for((int64_t)(1 + 2 * g * g) * F), dim3(256), 0, st, xe, ye, te, g, F, out));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+
+// ---- stem conv1: 3x3 / stride 2 / pad 1 over NCHW fp32 images -> rows [n*(S/2)^2, Kp], col = (ky*3+kx)*3 + c
+template <typename T>
+__global__ void __launch_bounds__(256) rn_im2col_stem_kernel(const float* __restrict__ img, int64_t n, int S, int Kp,
+                                                             T* __restrict__ out) {
+  pdl_sync();
+  const int Ho = S / 2;
+  const int64_t total = n * Ho * Ho * (int64_t)Kp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int col = (int)(i % Kp);
+    const int64_t row = i / Kp;
+    float v = 0.f;
+    if (col < 27) {
+      const int c = col % 3, kk = col / 3, ky = kk / 3, kx = kk % 3;
+      const int64_t im = row / (Ho * Ho);
+      const int oy = (int)(row % (Ho * Ho)) / Ho, ox = (int)(row % (Ho * Ho)) % Ho;
+      const int y = oy * 2 - 1 + ky, x = ox * 2 - 1 + kx;
+      if (y >= 0 && y < S && x >= 0 && x < S) v = img[((im * 3 + c) * S + y) * (int64_t)S + x];
+    }
+    out[i] = from_f<T>(v);
+  }
+}
+template <typename T>
+int rn_im2col_stem(const float* img, int64_t n, int S, int Kp, T* out, cudaStream_t st) {
+  MSQ_REQUIRE(S % 2 == 0 && Kp >= 27, "rn_im2col_stem: S=%d Kp=%d", S, Kp);
+  if (n == 0) return MSQ_OK;
+  MSQ_CUDA(launch_k(rn_im2col_stem_kernel<T>, grid_for(n * (S / 2) * (S / 2) * (int64_t)Kp), dim3(256), 0, st, img, n, S, Kp, out));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+template int rn_im2col_stem<float>(const float*, int64_t, int, int, float*, cudaStream_t);
+template int rn_im2col_stem<bf16>(const float*, int64_t, int, int, bf16*, cudaStream_t);
+
+// ---- 3x3 / stride 1 / pad 1 over NHWC -> rows [n*H*W, Kp], col = (ky*3+kx)*C + c  (4 channels per thread)
+template <typename T>
+__global__ void __launch_bounds__(256) rn_im2col3_kernel(const T* __restrict__ x, int64_t n, int H, int W, int C, int Kp,
+                                                         T* __restrict__ out) {
+  pdl_sync();
+  const int K4 = Kp / 4;
+  const int64_t total = n * H * W * (int64_t)K4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int col = (int)(i % K4) * 4;
+    const int64_t row = i / K4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < 9 * C) {
+      const int c = col % C, kk = col / C, ky = kk / 3, kx = kk % 3;
+      const int64_t im = row / (H * W);
+      const int oy = (int)(row % (H * W)) / W, ox = (int)(row % (H * W)) % W;
+      const int y = oy - 1 + ky, xx = ox - 1 + kx;
+      if (y >= 0 && y < H && xx >= 0 && xx < W) v = V4<T>::load(x + ((im * H + y) * W + xx) * (int64_t)C + c);
+    }
+    V4<T>::store(out + row * Kp + col, v);
+  }
+}
+template <typename T>
+int rn_im2col3(const T* x, int64_t n, int H, int W, int C, int Kp, T* out, cudaStream_t st) {
+  MSQ_REQUIRE(C % 4 == 0 && Kp % 4 == 0 && Kp >= 9 * C, "rn_im2col3: C=%d Kp=%d", C, Kp);
+  if (n == 0) return MSQ_OK;
+  MSQ_CUDA(launch_k(rn_im2col3_kernel<T>, grid_for(n * H * W * (int64_t)(Kp / 4)), dim3(256), 0, st, x, n, H, W, C, Kp, out));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+template int rn_im2col3<float>(const float*, int64_t, int, int, int, int, float*, cudaStream_t);
+template int rn_im2col3<bf16>(const bf16*, int64_t, int, int, int, int, bf16*, cudaStream_t);
+
+// ---- AvgPool2d(2) over NHWC
+template <typename T>
+__global__ void __launch_bounds__(256) rn_avgpool2_kernel(const T* __restrict__ x, int64_t n, int H, int W, int C,
+                                                          T* __restrict__ out) {
+  pdl_sync();
+  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  const int64_t total = n * Ho * Wo * (int64_t)C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const int64_t pix = i / C4, im = pix / (Ho * Wo);
+    const int oy = (int)(pix % (Ho * Wo)) / Wo, ox = (int)(pix % (Ho * Wo)) % Wo;
+    const T* p = x + ((im * H + 2 * oy) * W + 2 * ox) * (int64_t)C + c;
+    const float4 a = V4<T>::load(p), b = V4<T>::load(p + C), d = V4<T>::load(p + (int64_t)W * C), e = V4<T>::load(p + (int64_t)W * C + C);
+    V4<T>::store(out + pix * C + c, make_float4((a.x + b.x + d.x + e.x) * 0.25f, (a.y + b.y + d.y + e.y) * 0.25f,
+                                                (a.z + b.z + d.z + e.z) * 0.25f, (a.w + b.w + d.w + e.w) * 0.25f));
+  }
+}
+template <typename T>
+int rn_avgpool2(const T* x, int64_t n, int H, int W, int C, T* out, cudaStream_t st) {
+  MSQ_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "rn_avgpool2: H=%d W=%d C=%d", H, W, C);
+  if (n == 0) return MSQ_OK;
+  MSQ_CUDA(launch_k(rn_avgpool2_kernel<T>, grid_for(n * (H / 2) * (W / 2) * (int64_t)(C / 4)), dim3(256), 0, st, x, n, H, W, C, out));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+template int rn_avgpool2<float>(const float*, int64_t, int, int, int, float*, cudaStream_t);
+template int rn_avgpool2<bf16>(const bf16*, int64_t, int, int, int, bf16*, cudaStream_t);
+
+// ---- x <- relu(x) in place (fp32 residual stream) + operand-type copy for the next convolution
+template <typename T>
+__global__ void __launch_bounds__(256) rn_relu_cast_kernel(float* __restrict__ x, int64_t n4, T* __restrict__ out) {
+  pdl_sync();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = *reinterpret_cast<float4*>(x + i * 4);
+    v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    *reinterpret_cast<float4*>(x + i * 4) = v;
+    V4<T>::store(out + i * 4, v);
+  }
+}
+template <typename T>
+int rn_relu_cast(float* x, int64_t n, T* out, cudaStream_t st) {
+  MSQ_REQUIRE(n % 4 == 0, "rn_relu_cast: n=%lld", (long long)n);
+  if (n == 0) return MSQ_OK;
+  MSQ_CUDA(launch_k(rn_relu_cast_kernel<T>, grid_for(n / 4), dim3(256), 0, st, x, n / 4, out));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+template int rn_relu_cast<float>(float*, int64_t, float*, cudaStream_t);
+template int rn_relu_cast<bf16>(float*, int64_t, bf16*, cudaStream_t);
+
+// ---- AttentionPool2d token matrix for R pair rows.  feat [n_img, g2, C] fp32 (NHWC).  The reference reshapes the NCHW
+// maps of a pair [2, C, g2] to [C, 2*g2] WITHOUT moving the image axis (model.py:76), so token t / channel c' is flat
+// element f = c'*(2*g2) + t of that block: image f / (C*g2), channel (f % (C*g2)) / g2, cell f % g2.
+// out[r, 0, :] = mean over tokens + pos[0];  out[r, 1+t, :] = token + pos[1+t] (t < g2) or pos[t-g2] (t >= g2).
+template <typename T>
+__global__ void __launch_bounds__(128) rn_tokens_kernel(const float* __restrict__ feat, const int32_t* __restrict__ img_index,
+                                                        int g2, int C, const float* __restrict__ pos, T* __restrict__ out) {
+  pdl_sync();
+  const int64_t r = blockIdx.x;
+  const int cp = blockIdx.y * blockDim.x + threadIdx.x;
+  if (cp >= C) return;
+  const int L2 = 2 * g2;
+  const float* f0 = feat + (int64_t)img_index[r * 2] * g2 * C;
+  const float* f1 = feat + (int64_t)img_index[r * 2 + 1] * g2 * C;
+  T* o = out + r * (int64_t)(1 + L2) * C + cp;
+  float sum = 0.f;
+  for (int t = 0; t < L2; ++t) {
+    const int f = cp * L2 + t, im = f / (C * g2), rem = f % (C * g2), c = rem / g2, p = rem % g2;
+    const float v = (im ? f1 : f0)[(int64_t)p * C + c];
+    sum += v;
+    const int pr = t < g2 ? 1 + t : t - g2;
+    o[(int64_t)(1 + t) * C] = from_f<T>(v + pos[(int64_t)pr * C + cp]);
+  }
+  o[0] = from_f<T>(sum / (float)L2 + pos[cp]);
+}
+template <typename T>
+int rn_tokens(const float* feat, const int32_t* img_index, int64_t R, int g2, int C, const float* pos, T* out, cudaStream_t st) {
+  if (R == 0) return MSQ_OK;
+  MSQ_CUDA(launch_k(rn_tokens_kernel<T>, dim3((unsigned)R, (unsigned)ceil_div(C, 128)), dim3(128), 0, st, feat, img_index, g2, C, pos, out));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+template int rn_tokens<float>(const float*, const int32_t*, int64_t, int, int, const float*, float*, cudaStream_t);
+template int rn_tokens<bf16>(const float*, const int32_t*, int64_t, int, int, const float*, bf16*, cudaStream_t);
+
+// ---- tower output: out[row, :] = cat(o[row], o[row]) (+ posadd[row % L])   (model.py:106, lxrt/modeling.py:1014-1030)
+template <typename T>
+__global__ void __launch_bounds__(256) rn_finish_kernel(const float* __restrict__ o, int64_t rows, int L, int E,
+                                                        const float* __restrict__ posadd, T* __restrict__ out) {
+  pdl_sync();
+  const int F4 = 2 * E / 4;
+  const int64_t total = rows * F4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F4) * 4;
+    const int64_t row = i / F4;
+    float4 v = *reinterpret_cast<const float4*>(o + row * E + (f % E));
+    if (posadd) {
+      const float4 a = *reinterpret_cast<const float4*>(posadd + (row % L) * (int64_t)(2 * E) + f);
+      v = make_float4(v.x + a.x, v.y + a.y, v.z + a.z, v.w + a.w);
+    }
+    V4<T>::store(out + row * 2 * E + f, v);
+  }
+}
+template <typename T>
+int rn_finish(const float* o, int64_t rows, int L, int E, const float* posadd, T* out, cudaStream_t st) {
+  MSQ_REQUIRE(E % 4 == 0, "rn_finish: E=%d", E);
+  if (rows == 0) return MSQ_OK;
+  MSQ_CUDA(launch_k(rn_finish_kernel<T>, grid_for(rows * (2 * E / 4)), dim3(256), 0, st, o, rows, L, E, posadd, out));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+template int rn_finish<float>(const float*, int64_t, int, int, const float*, float*, cudaStream_t);
+template int rn_finish<bf16>(const float*, int64_t, int, int, const float*, bf16*, cudaStream_t);
+
+}  // namespace msq

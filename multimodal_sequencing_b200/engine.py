@@ -123,7 +123,9 @@ class OrderingEngine:
             raise RuntimeError("multimodal_sequencing_b200 needs a CUDA device (no CPU fallback)")
         self.lib = _lib.load()
         self.device = torch.device(device)
-        vit = config.get("vit")
+        vit, rn = config.get("vit"), config.get("rn")
+        if vit and rn:
+            raise ValueError("config names both a ViT and a ResNet visual tower")
         self.cfg = dict(config)
         self.H = config["hidden_size"]
         c = _lib.MsqConfig(
@@ -134,8 +136,17 @@ class OrderingEngine:
             vit_res=vit["image_resolution"] if vit else 0, para_heads=config.get("para_heads", 8),
             para_ff=config.get("para_ff", 3072), para_layers=config.get("para_layers", 2), precise=int(bool(precise)),
             reserved=0)
-        self.multimodal = bool(vit)
-        self.vit = vit
+        if rn:
+            # CLIP ModifiedResNet (clip/model.py:128-187): the tower hands 2*embed_dim features per token to visn_fc
+            blocks = tuple(rn["vision_layers"])
+            c.vit_width, c.vit_layers, c.vit_patch, c.vit_res = 2 * rn["embed_dim"], 0, 32, rn["image_resolution"]
+            c.rn_width, c.rn_embed = rn["vision_width"], rn["embed_dim"]
+            c.rn_blocks0, c.rn_blocks1, c.rn_blocks2, c.rn_blocks3 = blocks
+        self.multimodal = bool(vit or rn)
+        self.vit, self.rn = vit, rn
+        # visual tokens per pair row and their feature width as the tower returns them
+        self._grid = (vit["image_resolution"] // vit["vision_patch_size"]) if vit else (rn["image_resolution"] // 32 if rn else 0)
+        self._vis_width = vit["vision_width"] if vit else (2 * rn["embed_dim"] if rn else 0)
         self.precise = bool(precise)
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -174,9 +185,10 @@ class OrderingEngine:
 
     # ------------------------------------------------------------------------------------------
     def vit_forward(self, images, img_index, R):
-        """CLIP VisualTransformer pair tower (models/CLIP/clip/model.py:262-305, skip_last_layer=True)."""
-        g = self.vit["image_resolution"] // self.vit["vision_patch_size"]
-        out = torch.empty(R, 1 + 2 * g * g, self.vit["vision_width"], device=self.device)
+        """CLIP pair tower: VisualTransformer (models/CLIP/clip/model.py:262-305, skip_last_layer=True) or
+        ModifiedResNet + AttentionPool2d (model.py:171-187, 71-125, skip_last_layer=False)."""
+        g = self._grid
+        out = torch.empty(R, 1 + 2 * g * g, self._vis_width, device=self.device)
         images = images.to(self.device, torch.float32).contiguous()
         img_index = img_index.to(self.device, torch.int32).contiguous()
         _lib.check(self.lib.msq_vit_forward(self._h, self._p(images), images.shape[0], self._p(img_index), R,
@@ -195,7 +207,7 @@ class OrderingEngine:
         if self.multimodal and images is not None:
             images = images.to(self.device, torch.float32).contiguous()
             img_index = img_index.to(self.device, torch.int32).contiguous()
-            g = self.vit["image_resolution"] // self.vit["vision_patch_size"]
+            g = self._grid
             visn = torch.empty(R, 1 + 2 * g * g, self.H, device=self.device)
             n_img = images.shape[0]
         if want_pooled:

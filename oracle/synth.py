@@ -135,18 +135,76 @@ def vit_weights(pre, width, layers, patch, res, seed):
     return sd
 
 
+def rn_weights(pre, rn, seed):
+    """CLIP ModifiedResNet parameters (clip/model.py:128-187): kaiming-uniform convolutions, BatchNorm affine and
+    running statistics drawn away from the identity (a trained tower's are), attnpool as CLIP initialises it."""
+    g = _g(seed)
+    sd = {}
+    w, E = rn["vision_width"], rn["embed_dim"]
+    C = 32 * w
+
+    def conv(name, cout, cin, k):
+        bound = math.sqrt(6.0 / (cin * k * k))  # He-uniform keeps activations O(1) through ~50 ReLU convolutions
+        sd[name + ".weight"] = (torch.rand(cout, cin, k, k, generator=g) * 2 - 1) * bound
+
+    def bn(name, c, gain=1.0):
+        sd[name + ".weight"] = (torch.rand(c, generator=g) * 0.5 + 0.75) * gain
+        sd[name + ".bias"] = torch.randn(c, generator=g) * 0.1
+        sd[name + ".running_mean"] = torch.randn(c, generator=g) * 0.1
+        sd[name + ".running_var"] = torch.rand(c, generator=g) * 0.5 + 0.75
+
+    conv(pre + "conv1", w // 2, 3, 3); bn(pre + "bn1", w // 2)
+    conv(pre + "conv2", w // 2, w // 2, 3); bn(pre + "bn2", w // 2)
+    conv(pre + "conv3", w, w // 2, 3); bn(pre + "bn3", w)
+    cin = w
+    for s, nblk in enumerate(rn["vision_layers"]):
+        p = w << s
+        for b in range(nblk):
+            k = pre + "layer%d.%d." % (s + 1, b)
+            conv(k + "conv1", p, cin, 1); bn(k + "bn1", p)
+            conv(k + "conv2", p, p, 3); bn(k + "bn2", p)
+            conv(k + "conv3", 4 * p, p, 1); bn(k + "bn3", 4 * p, gain=0.5)
+            if b == 0:
+                conv(k + "downsample.0", 4 * p, cin, 1); bn(k + "downsample.1", 4 * p, gain=0.5)
+            cin = 4 * p
+    n_tok = (rn["image_resolution"] // 32) ** 2 + 1
+    sd[pre + "attnpool.positional_embedding"] = torch.randn(n_tok, C, generator=g) / C ** 0.5
+    std = C ** -0.5
+    for n, o in (("q_proj", C), ("k_proj", C), ("v_proj", C), ("c_proj", E)):
+        sd[pre + "attnpool.%s.weight" % n] = torch.randn(o, C, generator=g) * std
+        sd[pre + "attnpool.%s.bias" % n] = torch.randn(o, generator=g) * 0.02
+    return sd
+
+
+def rn_lxrt_extras(pre, rn, H, seed):
+    """visual_pos / visual_token_type / visn_fc of the RN branch (lxrt/modeling.py:621-705, 874-882) after init_bert_weights."""
+    g = _g(seed)
+    F = 2 * rn["embed_dim"]
+    return {pre + "encoder.visual_pos.x_position_embedding.weight": _normal(g, 25, F),
+            pre + "encoder.visual_pos.y_position_embedding.weight": _normal(g, 25, F),
+            pre + "encoder.visual_token_type.token_type_embedding.weight": _normal(g, 5, F),
+            pre + "encoder.visn_fc.visn_fc.weight": _normal(g, H, F),
+            pre + "encoder.visn_fc.visn_fc.bias": torch.zeros(H),
+            pre + "encoder.visn_fc.visn_layer_norm.weight": torch.ones(H),
+            pre + "encoder.visn_fc.visn_layer_norm.bias": torch.zeros(H)}
+
+
+RN50 = dict(embed_dim=1024, image_resolution=224, vision_layers=(3, 4, 6, 3), vision_width=64)
 BERT_BASE = dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
                  vocab_size=30522, max_position_embeddings=512)
 VIT_B32 = dict(embed_dim=512, image_resolution=224, vision_layers=12, vision_width=768, vision_patch_size=32)
 
 
-def full_state_dict(cfg=None, vit=None, seed=0, ff=3072):
-    """Seeded state_dict of a whole BertForOrdering (+ LXRT/ViT inner model when `vit` is given)."""
+def full_state_dict(cfg=None, vit=None, seed=0, ff=3072, rn=None):
+    """Seeded state_dict of a whole BertForOrdering (+ LXRT and the ViT / ResNet tower when `vit` / `rn` is given)."""
     cfg = dict(BERT_BASE if cfg is None else cfg)
     H = cfg["hidden_size"]
     sd = berson_head_weights(H, ff=ff, seed=seed + 3)
     sd.update(bert_weights("bert.", H, cfg["num_hidden_layers"], cfg["intermediate_size"], cfg["vocab_size"],
-                           cfg["max_position_embeddings"], seed + 11, lxrt=vit is not None))
+                           cfg["max_position_embeddings"], seed + 11, lxrt=vit is not None or rn is not None))
+    if rn is not None:
+        sd.update(rn_weights("bert.encoder.visual_model.visual.", rn, seed + 23))
+        sd.update(rn_lxrt_extras("bert.", rn, H, seed + 17))
     if vit is not None:
         g = _g(seed + 17)
         W = vit["vision_width"]

@@ -31,7 +31,7 @@ def _cfg_from_golden(g):
     return dict(hidden_size=c["hidden_size"], num_hidden_layers=c["num_hidden_layers"],
                 num_attention_heads=c["num_attention_heads"], intermediate_size=c["intermediate_size"],
                 vocab_size=c["vocab_size_or_config_json_file"], max_position_embeddings=c["max_position_embeddings"],
-                vit=g.get("vit"), para_ff=g["ff_size"])
+                vit=g.get("vit"), rn=g.get("rn"), para_ff=g["ff_size"])
 
 
 def _close(a, b, rel, what=""):
@@ -279,6 +279,53 @@ def test_mm_tiny_golden(golden_dir, precise):
             assert hp.tolist() == [c["perm"]]
         else:
             assert eng.beam_search(c["enc"], c["N"], c["W"])[0].tolist() == c["perm"]
+
+
+@pytest.mark.parametrize("precise", [True, False])
+def test_mm_rn_tiny_golden(golden_dir, precise):
+    """The reference's default "RN50" wiring (ModifiedResNet + AttentionPool2d, visual_pos / visual_token_type) on a
+    narrow tower, against what the reference itself produced."""
+    g = torch.load(os.path.join(golden_dir, "mm_rn_tiny.pt"), weights_only=False)
+    eng = _engine(g["sd"], _cfg_from_golden(g), precise)
+    rel = 4 * REL_FP32 if precise else 3e-2
+    for c in g["cases"]:
+        ids, labels, images = O.synthetic_manuals(1, c["N"], c["L"], vocab=1000, image_px=224, seed=c["seed"])
+        pb = eng.prepare(ids, labels, c["N"], images)
+        tower = eng.vit_forward(pb.images, pb.img_index.reshape(-1, 2)[:3], 3)
+        _close(tower, c["tower"], rel, "resnet tower")
+        lang, visn, pooled = eng.inner_forward(pb.input_ids[0], pb.token_type_ids[0], pb.attention_mask[0], pb.images,
+                                               pb.img_index[0], want_pooled=True)
+        _close(lang[:3], c["lang"], rel, "lang")
+        _close(visn[:3], c["visn"], rel, "visn")
+        _close(pooled, c["pooled"], rel, "pooled")
+        enc = eng.encode(pb)
+        for k in ENC:
+            _close(enc[k].reshape(c["enc"][k].shape), c["enc"][k], rel, k)
+        if precise:
+            perm, tr = eng.beam_search(enc, c["N"], c["W"], trace=True)
+            assert perm[0].tolist() == c["perm"]
+            _check_trace(tr, 0, c["steps"], c["W"], c["N"])
+            assert eng.order(ids, labels, c["N"], c["W"], images) == [c["perm"]]
+            hp = eng.order_host(eng.prepare(ids, labels, c["N"], images), c["W"])
+            assert hp.tolist() == [c["perm"]]
+
+
+@pytest.mark.parametrize("precise", [True, False])
+def test_resnet_tower_width64_vs_oracle(precise):
+    """ModifiedResNet at RN50's channel widths (64..2048, one block per stage) so that every convolution GEMM takes the
+    shape class it has in the real tower (tcgen05 for K >= 64 in bf16 mode); 70 unique images span two trunk chunks."""
+    rn = dict(embed_dim=256, image_resolution=224, vision_layers=(1, 1, 1, 1), vision_width=64)
+    pre = "bert.encoder.visual_model.visual."
+    sd = synth.rn_weights(pre, rn, 5)
+    cfg = dict(hidden_size=128, num_hidden_layers=0, num_attention_heads=2, intermediate_size=512, vocab_size=16,
+               max_position_embeddings=16, rn=rn)
+    eng = _engine(sd, cfg, precise)
+    images = torch.randn(70, 3, 224, 224, generator=torch.Generator().manual_seed(2))
+    idx = torch.tensor([[0, 1], [1, 0], [69, 3], [64, 63], [5, 5]], dtype=torch.int32)
+    got = eng.vit_forward(images, idx, idx.shape[0])
+    ref = O.rn_pair_tower(sd, pre, images[idx.reshape(-1).long()], rn)
+    err = _close(got, ref, 8 * REL_FP32 if precise else 3e-2, "resnet tower (width 64)")
+    print("resnet tower width 64 precise=%s max err %.3e (max |ref| %.3f)" % (precise, err, ref.abs().max().item()))
 
 
 # ---------------------------------------------------------------------------------------------
