@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="manuals per step per GPU")
     ap.add_argument("--precise", action="store_true", help="fp32 FFMA parity mode instead of bf16 tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--backbone", default="vit", choices=["vit", "rn50"],
+                    help="visual tower: ViT-B/32 (BASELINE configs[1], the headline) or the reference's wired default RN50")
     return ap.parse_args()
 
 
@@ -94,8 +96,15 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def config_dict(batch, n_gpus):
-    return {"workload": "configs[1]: multimodal BERSON + CLIP ViT-B/32, 5 steps x 64 tokens + 224px images, beam=4, eval",
+def _towers(backbone):
+    from oracle import synth
+    return (dict(synth.VIT_B32), None) if backbone == "vit" else (None, dict(synth.RN50))
+
+
+def config_dict(batch, n_gpus, backbone="vit"):
+    return {"workload": ("configs[1]: multimodal BERSON + CLIP ViT-B/32, 5 steps x 64 tokens + 224px images, beam=4, eval"
+                         if backbone == "vit" else
+                         "configs[1] with the reference's wired RN50 tower instead of ViT-B/32 (secondary line, not the headline)"),
             "manuals_per_step_per_gpu": batch, "n_steps": N_STEPS, "beam": BEAM, "tokens_per_step": TOKENS,
             "pairs_per_manual": N_STEPS * (N_STEPS - 1), "joint_tokens_per_pair": 227,
             "parallelism": "manuals sharded by rank, no data-path collective (dp%d)" % n_gpus,
@@ -103,7 +112,7 @@ def config_dict(batch, n_gpus):
                   (batch * N_STEPS * 3 * IMG * IMG * 4 / 1e6)}
 
 
-def cpu_reference_run(max_manuals, budget_s, seed=1):
+def cpu_reference_run(max_manuals, budget_s, seed=1, backbone="vit"):
     """Oracle port of berson_pointer_network on the host cores (reference semantics: one manual per call)."""
     import torch
     from oracle import berson_oracle as O
@@ -111,8 +120,9 @@ def cpu_reference_run(max_manuals, budget_s, seed=1):
     torch.set_grad_enabled(False)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = dict(num_hidden_layers=12, num_attention_heads=12, vit=dict(synth.VIT_B32))
-    sd = synth.full_state_dict(None, synth.VIT_B32, seed=0)
+    vit, rn = _towers(backbone)
+    cfg = dict(num_hidden_layers=12, num_attention_heads=12, vit=vit, rn=rn)
+    sd = synth.full_state_dict(None, vit, seed=0, rn=rn)
     ids, labels, images = O.synthetic_manuals(max_manuals, N_STEPS, TOKENS, image_px=IMG, seed=seed)
     times = []
     t_start = time.time()
@@ -130,7 +140,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     n = args.steps + args.warmup
-    times, cores = cpu_reference_run(n, budget_s=170.0)
+    times, cores = cpu_reference_run(n, budget_s=170.0, backbone=args.backbone)
     timed = times[min(args.warmup, max(0, len(times) - 1)):]
     ms = 1e3 * sum(timed) / len(timed)
     val = 1e3 / ms
@@ -139,7 +149,7 @@ def run_reference(args, rank):
     line = {"metric": "5-step manuals ordered/sec (beam=4)", "value": val, "unit": "manuals/s", "impl": "reference",
             "n_gpus": args.gpus, "steps": len(timed), "warmup": len(times) - len(timed), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(1, args.gpus),
+            "config": config_dict(1, args.gpus, args.backbone),
             "cpu_baseline": {"value": val, "unit": "manuals/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "manuals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -170,8 +180,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = dict(synth.BERT_BASE)
-    cfg.update(vit=dict(synth.VIT_B32), para_ff=3072)
-    sd = synth.full_state_dict(cfg, cfg["vit"], seed=0)
+    vit, rn = _towers(args.backbone)
+    cfg.update(vit=vit, rn=rn, para_ff=3072)
+    sd = synth.full_state_dict(cfg, vit, seed=0, rn=rn)
     eng = OrderingEngine(sd, cfg, precise=args.precise, device=dev)
     del sd
     lib = _lib.load()
@@ -254,7 +265,7 @@ def main():
     line = {"metric": "5-step manuals ordered/sec (beam=4)", "value": value, "unit": "manuals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precise else "bf16", "data": "synthetic",
-            "config": config_dict(B, world), "impl": "ours",
+            "config": config_dict(B, world, args.backbone), "impl": "ours",
             "e2e": {"value": e2e, "unit": "manuals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "OrderingEngine.order_host -> msq_order_manuals_host (pinned host buffers)"},
             "gpu_launches": launches,
@@ -270,7 +281,7 @@ def main():
                          "whole_step_tflops_per_gpu": FLOP_PER_MANUAL * B * args.steps / (ms_total / 1e3) / 1e12},
             }
     if not args.no_cpu_baseline and world == 1:
-        times, cores = cpu_reference_run(3, budget_s=25.0)
+        times, cores = cpu_reference_run(3, budget_s=25.0, backbone=args.backbone)
         timed = times[1:] if len(times) > 1 else times
         cv = len(timed) / sum(timed)
         line["cpu_baseline"] = {"value": cv, "unit": "manuals/s", "cores": cores, "kind": "port",

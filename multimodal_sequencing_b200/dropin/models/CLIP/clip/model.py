@@ -87,6 +87,96 @@ class VisualTransformer(nn.Module):
             return self._engine().vit_forward(x, idx, R)
 
 
+class Bottleneck(nn.Module):
+    """model.py:10-53 (parameter holder).  conv1/bn1 (1x1) -> conv2/bn2 (3x3) -> AvgPool2d(stride) -> conv3/bn3 (1x1),
+    shortcut `downsample` = AvgPool2d + 1x1 conv + BN when the shape changes; all of it runs as im2col + GEMM with the
+    BatchNorm folded in (csrc/rn.cu, api.cu run_rn_trunk)."""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1):
+        super().__init__()
+        self.conv1, self.bn1 = nn.Conv2d(inplanes, planes, 1, bias=False), nn.BatchNorm2d(planes)
+        self.conv2, self.bn2 = nn.Conv2d(planes, planes, 3, padding=1, bias=False), nn.BatchNorm2d(planes)
+        self.conv3, self.bn3 = nn.Conv2d(planes, planes * 4, 1, bias=False), nn.BatchNorm2d(planes * 4)
+        self.stride, self.downsample = stride, None
+        if stride > 1 or inplanes != planes * 4:
+            self.downsample = nn.Sequential(OrderedDict([("-1", nn.AvgPool2d(stride)),
+                                                         ("0", nn.Conv2d(inplanes, planes * 4, 1, stride=1, bias=False)),
+                                                         ("1", nn.BatchNorm2d(planes * 4))]))
+
+
+class AttentionPool2d(nn.Module):
+    """model.py:55-125 (parameter holder): positional_embedding, q/k/v/c_proj, and the token_type_embedding table the
+    reference allocates for img_len > 1 but only reads behind a disabled flag."""
+
+    def __init__(self, spacial_dim, embed_dim, num_heads, output_dim=None, img_len=None):
+        super().__init__()
+        self.img_len, self.num_heads, self.embed_dim = img_len, num_heads, embed_dim
+        self.positional_embedding = nn.Parameter(torch.randn(spacial_dim ** 2 + 1, embed_dim) / embed_dim ** 0.5)
+        self.k_proj = nn.Linear(embed_dim, embed_dim)
+        self.q_proj = nn.Linear(embed_dim, embed_dim)
+        self.v_proj = nn.Linear(embed_dim, embed_dim)
+        self.c_proj = nn.Linear(embed_dim, output_dim or embed_dim)
+        if img_len is not None and img_len > 1:
+            self.token_type_embedding = nn.Embedding(5, embed_dim)
+
+
+class ModifiedResNet(nn.Module):
+    """model.py:128-187.  forward(x [R*img_len,3,S,S]) -> [R, 1 + img_len*(S/32)^2, 2*output_dim]: 3-conv stem, AvgPool,
+    four bottleneck stages, AttentionPool2d over the PAIR's tokens, concatenated with itself (model.py:106)."""
+
+    def __init__(self, layers, output_dim, heads, input_resolution=224, width=64, img_len=None):
+        super().__init__()
+        self.output_dim, self.input_resolution, self.width, self.layers, self.img_len = output_dim, input_resolution, width, tuple(layers), img_len
+        self.conv1, self.bn1 = nn.Conv2d(3, width // 2, kernel_size=3, stride=2, padding=1, bias=False), nn.BatchNorm2d(width // 2)
+        self.conv2, self.bn2 = nn.Conv2d(width // 2, width // 2, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(width // 2)
+        self.conv3, self.bn3 = nn.Conv2d(width // 2, width, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(width)
+        self._inplanes = width
+        self.layer1 = self._make_layer(width, layers[0])
+        self.layer2 = self._make_layer(width * 2, layers[1], stride=2)
+        self.layer3 = self._make_layer(width * 4, layers[2], stride=2)
+        self.layer4 = self._make_layer(width * 8, layers[3], stride=2)
+        self.attnpool = AttentionPool2d(input_resolution // 32, width * 32, heads, output_dim, img_len=img_len)
+
+    def _make_layer(self, planes, blocks, stride=1):
+        mods = [Bottleneck(self._inplanes, planes, stride)]
+        self._inplanes = planes * Bottleneck.expansion
+        mods += [Bottleneck(self._inplanes, planes) for _ in range(1, blocks)]
+        return nn.Sequential(*mods)
+
+    def rn_config(self):
+        return dict(embed_dim=self.output_dim, image_resolution=self.input_resolution, vision_layers=self.layers,
+                    vision_width=self.width)
+
+    def _engine(self):
+        tensors = list(self.parameters()) + list(self.buffers())
+        sig = tuple(t._version for t in tensors) + (bool(getattr(self, "precise", False)),)
+        if self.__dict__.get("_eng") is None or self.__dict__.get("_eng_sig") != sig:
+            dev = self.conv1.weight.device
+            if dev.type != "cuda":
+                raise RuntimeError("the B200 path has no CPU fallback: move the model to a CUDA device first")
+            cfg = dict(hidden_size=128, num_hidden_layers=0, num_attention_heads=2, intermediate_size=512, vocab_size=1,
+                       max_position_embeddings=1, rn=self.rn_config())
+            sd = {"bert.encoder.visual_model.visual." + k: v for k, v in self.state_dict().items()}
+            self.__dict__["_eng"] = OrderingEngine(sd, cfg, device=dev, precise=bool(getattr(self, "precise", False)))
+            self.__dict__["_eng_sig"] = sig
+        return self.__dict__["_eng"]
+
+    def forward(self, x, skip_last_layer=False, text_embedding=None, text_mask=None, img_len=None):
+        if skip_last_layer or text_embedding is not None:
+            # LXRTModel hard-wires skip_last_layer=False for this tower (lxrt/modeling.py:783)
+            raise NotImplementedError("the ordering path runs the ResNet tower with its attention pool (skip_last_layer=False)")
+        if self.training:
+            raise NotImplementedError("BatchNorm is folded for inference; training the tower is outside the drop-in's path")
+        il = self.img_len or img_len or 2
+        if il != 2:
+            raise NotImplementedError("BERSON feeds image PAIRS (max_subsample_image_length = 2)")
+        R = x.shape[0] // il
+        idx = torch.arange(R * il, dtype=torch.int32, device=x.device)
+        with torch.no_grad():
+            return self._engine().vit_forward(x, idx, R)
+
+
 class CLIP(nn.Module):
     """model.py:307-367.  Only the visual tower is built: the text tower is dead weight on this path
     (63.4 M parameters the reference allocates and never runs)."""
@@ -94,11 +184,13 @@ class CLIP(nn.Module):
     def __init__(self, embed_dim, image_resolution, vision_layers, vision_width, vision_patch_size, context_length,
                  vocab_size, transformer_width, transformer_heads, transformer_layers, img_len=None, img_only=False):
         super().__init__()
-        if isinstance(vision_layers, (tuple, list)):
-            raise NotImplementedError("CLIP RN50 / AttentionPool2d tower is a later row of the scope table (SURVEY §8(f).3)")
         self.context_length, self.img_only = context_length, img_only
-        self.visual = VisualTransformer(image_resolution, vision_patch_size, vision_width, vision_layers, vision_width // 64,
-                                        embed_dim, img_len=img_len)
+        if isinstance(vision_layers, (tuple, list)):
+            self.visual = ModifiedResNet(vision_layers, embed_dim, vision_width * 32 // 64, image_resolution, vision_width,
+                                         img_len=img_len)
+        else:
+            self.visual = VisualTransformer(image_resolution, vision_patch_size, vision_width, vision_layers,
+                                            vision_width // 64, embed_dim, img_len=img_len)
 
     @property
     def dtype(self):

@@ -1,6 +1,7 @@
 """models/CLIP/src/lxrt/modeling.py of the reference, BERSON surface: BertConfig (147-232) and LXRTModel
 (1456-1598) in CLIP / visualbert-style mode.  Same constructor kwargs, forward signature and state_dict
-keys; the forward is msq_inner_forward (ViT pair tower -> visn_fc -> joint BERT)."""
+keys; the forward is msq_inner_forward (ViT or ResNet pair tower -> [+ visual_pos +
+visual_token_type for the ResNet] -> visn_fc -> joint BERT)."""
 import torch
 import torch.nn as nn
 
@@ -11,6 +12,8 @@ from models.CLIP.clip.model import CLIP
 CLIP_CONFIGS = {
     # clip.load("ViT-B/32") geometry (models/CLIP/clip/model.py:471-508 rebuilds it from the checkpoint)
     "ViT-B/32": dict(embed_dim=512, image_resolution=224, vision_layers=12, vision_width=768, vision_patch_size=32),
+    # the reference's wired default (param.py VISUAL_CONFIG.clip_model_name): ModifiedResNet + AttentionPool2d
+    "RN50": dict(embed_dim=1024, image_resolution=224, vision_layers=(3, 4, 6, 3), vision_width=64, vision_patch_size=None),
 }
 
 
@@ -45,8 +48,12 @@ class LXRTModel(nn.Module):
         name = kwargs.get("clip_model_name", "ViT-B/32")
         vit = kwargs.get("clip_config") or CLIP_CONFIGS.get(name)
         if vit is None:
-            raise NotImplementedError("visual backbone %r: only the ViT tower is built (RN50 is SURVEY §8(f).3)" % name)
+            raise NotImplementedError("visual backbone %r: the towers built are %s" % (name, sorted(CLIP_CONFIGS)))
         self.vit_config = dict(vit)
+        self.is_resnet = isinstance(vit["vision_layers"], (tuple, list))
+        # features per visual token handed to visn_fc (VISUAL_CONFIG.visual_feat_dim): ViT width, or 2*embed_dim for the
+        # ResNet whose attention pool returns cat([x, x]) (clip/model.py:106)
+        F = 2 * vit["embed_dim"] if self.is_resnet else vit["vision_width"]
         self.cls_id, self.sep_id = kwargs.get("cls_id"), kwargs.get("sep_id")
         H = config.hidden_size
         self.embeddings = _holder(word_embeddings=nn.Embedding(config.vocab_size, H, padding_idx=0),
@@ -54,17 +61,17 @@ class LXRTModel(nn.Module):
                                   token_type_embeddings=nn.Embedding(config.type_vocab_size, H, padding_idx=0),
                                   LayerNorm=nn.LayerNorm(H, eps=1e-12))
         enc = _holder(layer=nn.ModuleList([_bert_layer(H, config.intermediate_size, 1e-12) for _ in range(config.num_hidden_layers)]),
-                      visn_fc=_holder(visn_fc=nn.Linear(vit["vision_width"], H), visn_layer_norm=nn.LayerNorm(H, eps=1e-12),
+                      visn_fc=_holder(visn_fc=nn.Linear(F, H), visn_layer_norm=nn.LayerNorm(H, eps=1e-12),
                                       box_fc=nn.Linear(4, H), box_layer_norm=nn.LayerNorm(H, eps=1e-12)),
                       visual_model=CLIP(vit["embed_dim"], vit["image_resolution"], vit["vision_layers"], vit["vision_width"],
-                                        vit["vision_patch_size"], 77, 49408, 512, 8, 12,
+                                        vit.get("vision_patch_size"), 77, 49408, 512, 8, 12,
                                         img_len=2, img_only=True))
-        # RN-only embeddings the reference allocates regardless of the backbone (lxrt/modeling.py:828-831, 621-705);
-        # never read on the ViT path ("RN" guard, 1014) but present in its checkpoints
-        F = vit["vision_width"]
+        # embeddings the reference allocates regardless of the backbone (lxrt/modeling.py:828-831, 621-705); added to the
+        # tower output on the ResNet path only ("RN" guard, 1014) but present in every checkpoint
         enc.visual_pos = _holder(x_position_embedding=nn.Embedding(25, F), y_position_embedding=nn.Embedding(25, F))
         enc.visual_token_type = _holder(token_type_embedding=nn.Embedding(5, F))
-        enc.skip_last_layer = True  # oracle decision for the ViT tower
+        # ViT: oracle decision; ResNet: hard-wired False (lxrt/modeling.py:783)
+        enc.skip_last_layer = not self.is_resnet
         self.encoder = enc
         self.pooler = _holder(dense=nn.Linear(H, H))
         if self.topo_sort:
@@ -72,7 +79,7 @@ class LXRTModel(nn.Module):
         self.apply(lambda m: _init_bert_weights(m, config.initializer_range))  # 1464: re-initialises the tower's Linears too
 
     def _engine(self):
-        sig = tuple(p._version for p in self.parameters()) + (bool(getattr(self, "precise", False)),)
+        sig = tuple(t._version for t in list(self.parameters()) + list(self.buffers())) + (bool(getattr(self, "precise", False)),)
         if self.__dict__.get("_eng") is None or self.__dict__.get("_eng_sig") != sig:
             dev = self.pooler.dense.weight.device
             if dev.type != "cuda":
@@ -80,7 +87,8 @@ class LXRTModel(nn.Module):
             c = self.config
             cfg = dict(hidden_size=c.hidden_size, num_hidden_layers=c.num_hidden_layers, num_attention_heads=c.num_attention_heads,
                        intermediate_size=c.intermediate_size, vocab_size=c.vocab_size,
-                       max_position_embeddings=c.max_position_embeddings, type_vocab_size=c.type_vocab_size, vit=self.vit_config)
+                       max_position_embeddings=c.max_position_embeddings, type_vocab_size=c.type_vocab_size)
+            cfg["rn" if self.is_resnet else "vit"] = self.vit_config
             sd = {"bert." + k: v for k, v in self.state_dict().items()}
             self.__dict__["_eng"] = OrderingEngine(sd, cfg, device=dev, precise=bool(getattr(self, "precise", False)))
             self.__dict__["_eng_sig"] = sig

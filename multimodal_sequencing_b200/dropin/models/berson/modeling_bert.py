@@ -79,8 +79,8 @@ class _EngineOwner:
         return self.state_dict()
 
     def engine(self):
-        sig = tuple(p._version for p in self.parameters()) + (tuple(id(p) for p in self.parameters()),
-                                                               bool(getattr(self, "precise", False)))
+        tensors = list(self.parameters()) + list(self.buffers())   # buffers: BatchNorm statistics of the ResNet tower
+        sig = tuple(t._version for t in tensors) + (tuple(id(t) for t in tensors), bool(getattr(self, "precise", False)))
         eng = self.__dict__.get("_eng")
         if eng is None or self.__dict__.get("_eng_sig") != sig:
             dev = next(self.parameters()).device
@@ -199,8 +199,11 @@ class BertForOrdering(nn.Module, _EngineOwner):
         c = self.config
         inner = self.bert
         vit = getattr(inner, "vit_config", None)
+        rn = None
+        if vit is not None and getattr(inner, "is_resnet", False):
+            vit, rn = None, vit
         ic = getattr(inner, "config", c)
-        return dict(hidden_size=c.hidden_size, num_hidden_layers=ic.num_hidden_layers,
+        return dict(rn=rn, hidden_size=c.hidden_size, num_hidden_layers=ic.num_hidden_layers,
                     num_attention_heads=ic.num_attention_heads, intermediate_size=ic.intermediate_size,
                     vocab_size=ic.vocab_size, max_position_embeddings=ic.max_position_embeddings,
                     type_vocab_size=getattr(ic, "type_vocab_size", 2), vit=vit, para_heads=self.args.heads,

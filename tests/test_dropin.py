@@ -40,14 +40,15 @@ def _build(g, N, W, device="cpu"):
     cfg = BertConfig(c["vocab_size_or_config_json_file"], hidden_size=c["hidden_size"], num_hidden_layers=c["num_hidden_layers"],
                      num_attention_heads=c["num_attention_heads"], intermediate_size=c["intermediate_size"],
                      max_position_embeddings=c["max_position_embeddings"])
-    mm = g.get("vit") is not None
+    mm = g.get("vit") is not None or g.get("rn") is not None
     args = _args(N, W, g["ff_size"], device, mm)
     if mm:
         inner = LXRTModel(LxrtBertConfig(c["vocab_size_or_config_json_file"], hidden_size=c["hidden_size"],
                                          num_hidden_layers=c["num_hidden_layers"], num_attention_heads=c["num_attention_heads"],
                                          intermediate_size=c["intermediate_size"],
                                          max_position_embeddings=c["max_position_embeddings"]),
-                          clip_model_name="ViT-B/32", clip_config=g["vit"], cls_id=101, sep_id=102, max_story_length=N)
+                          clip_model_name="RN50" if g.get("rn") else "ViT-B/32", clip_config=g.get("rn") or g["vit"],
+                          cls_id=101, sep_id=102, max_story_length=N)
         model = BertForOrdering(cfg, args, tokenizer=Tok())
         model.bert = inner
     else:
@@ -55,7 +56,7 @@ def _build(g, N, W, device="cpu"):
     return model, args
 
 
-@pytest.mark.parametrize("name", ["text_tiny.pt", "mm_tiny.pt"])
+@pytest.mark.parametrize("name", ["text_tiny.pt", "mm_tiny.pt", "mm_rn_tiny.pt"])
 def test_state_dict_keys_match_reference(golden_dir, name):
     g = torch.load(os.path.join(golden_dir, name), weights_only=False)
     model, _ = _build(g, 5, 4)
@@ -189,10 +190,10 @@ def _reference_style_search(args, model, berson_inputs):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["text_tiny.pt", "mm_tiny.pt"])
+@pytest.mark.parametrize("name", ["text_tiny.pt", "mm_tiny.pt", "mm_rn_tiny.pt"])
 def test_dropin_reproduces_reference_fixtures(golden_dir, name):
     g = torch.load(os.path.join(golden_dir, name), weights_only=False)
-    mm = g.get("vit") is not None
+    mm = g.get("vit") is not None or g.get("rn") is not None
     for c in g["cases"]:
         model, args = _build(g, c["N"], c["W"], "cuda")
         model.load_state_dict(g["sd"], strict=False)
@@ -222,7 +223,10 @@ def test_dropin_reproduces_reference_fixtures(golden_dir, name):
             im = pb["images"].reshape(B * P * 2, 3, 224, 224)
             (lang, visn), pooled = model.bert(ids2, token_type_ids=tt2, attention_mask=am2, visual_feats=im)
             assert (lang[:3].cpu() - c["lang"]).abs().max() < 4e-5 and (pooled.cpu() - c["pooled"]).abs().max() < 4e-5
-            tower = model.bert.encoder.visual_model.visual(im[:6], skip_last_layer=True, img_len=2)
+            if g.get("rn"):
+                tower = model.bert.encoder.visual_model.visual(im[:6], img_len=2)
+            else:
+                tower = model.bert.encoder.visual_model.visual(im[:6], skip_last_layer=True, img_len=2)
             assert (tower.cpu() - c["tower"]).abs().max() < 4e-5
         else:
             seq, pooled = model.bert(ids2, attention_mask=am2, token_type_ids=tt2)

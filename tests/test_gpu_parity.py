@@ -334,18 +334,18 @@ def test_resnet_tower_width64_vs_oracle(precise):
 
 def _full_cfg(mm):
     cfg = dict(synth.BERT_BASE)
-    cfg.update(vit=dict(synth.VIT_B32) if mm else None, para_ff=3072)
+    cfg.update(vit=dict(synth.VIT_B32) if mm is True else None, rn=dict(synth.RN50) if mm == "rn50" else None, para_ff=3072)
     return cfg
 
 
-@pytest.mark.parametrize("mm", [False, True])
+@pytest.mark.parametrize("mm", [False, True, "rn50"])
 def test_full_size_vs_oracle(mm):
     cfg = _full_cfg(mm)
-    sd = synth.full_state_dict(cfg, cfg["vit"], seed=0)
+    sd = synth.full_state_dict(cfg, cfg["vit"], seed=0, rn=cfg["rn"])
     N, W, B = 5, 4, 2
     ids, labels, images = O.synthetic_manuals(B, N, 64, image_px=224 if mm else None, seed=1)
     torch.set_num_threads(os.cpu_count() or 1)
-    ocfg = dict(num_hidden_layers=12, num_attention_heads=12, vit=cfg["vit"])
+    ocfg = dict(num_hidden_layers=12, num_attention_heads=12, vit=cfg["vit"], rn=cfg["rn"])
     inp = O.prepare_inputs(ids, labels, N, images)
     oenc = O.encode(sd, ocfg, inp)
     operm = [O.beam_search(sd, oenc, N, W, b) for b in range(B)]
@@ -355,7 +355,7 @@ def test_full_size_vs_oracle(mm):
         enc = eng.encode(pb, want_top_vec=True)
         torch.cuda.synchronize()
         errs = {k: _close(enc[k].reshape(oenc[k].shape), oenc[k], (1e-4 if precise else 5e-2), k) for k in ENC + ["top_vec"]}
-        print("full-size %s %s max-abs errors: %s" % ("mm" if mm else "text", "fp32" if precise else "bf16",
+        print("full-size %s %s max-abs errors: %s" % ({False: "text", True: "mm"}.get(mm, mm), "fp32" if precise else "bf16",
                                                       {k: "%.2e" % v for k, v in errs.items()}))
         # decode: identical encoder outputs in -> identical permutations out (bit-exact index work)
         assert eng.beam_search(oenc, N, W).cpu().tolist() == operm
