@@ -150,6 +150,18 @@ int msq_order_manuals_host(msq_model* m, const int64_t* ids_host, const int64_t*
  * (tcgen05), 2 = bf16 in / bf16 out (tcgen05).  act: 0 none, 1 erf-GELU, 2 QuickGELU, 3 tanh, 4 tanh-GELU. */
 int msq_gemm(int32_t dtype, const void* A_dev, const void* W_dev, const float* bias_dev, const float* resid_dev,
              void* C_dev, int64_t M, int32_t N, int32_t K, int32_t act, void* stream);
+/* tcgen05 GEMM with a DEFERRED LayerNorm in its epilogue (bf16 operands; kernel-level entry used by tests and
+ * scripts/kernel_bench.py; the encoders call the same code internally).  The LayerNorm between two sub-layers
+ * (lxrt/modeling.py:432,486; clip/model.py:221-225) is never materialised:
+ *   mode 1 (fold)      C = act(rstd_m (A W'^T - mu_m svec) + bias)   A = bf16 copy of the RAW stream, W' = gamma*W,
+ *                      bias = b + W beta, svec[n] = sum_k W'[n,k]; mu / rstd from stats_in [M, sp_in, 2] partial sums
+ *   mode 2 (residual)  C = A W^T + bias + LN(resid) in fp32 (raw resid when stats_in is NULL; gamma/beta in
+ *                      svec_or_gamma/beta), plus C2bf = bf16(C) and stats_out [M, 2*ceil(N/256), 2] = per-row partial
+ *                      (sum, sum of squares) of C over 128-column groups. */
+int msq_gemm_deferred_ln(int32_t mode, int32_t out_bf16, const void* A_dev, const void* W_dev, const float* bias_dev,
+                         const float* resid_dev, const float* svec_or_gamma_dev, const float* beta_dev,
+                         const float* stats_in_dev, int32_t sp_in, int32_t ln_dim, float eps, void* C_dev, void* C2bf_dev,
+                         float* stats_out_dev, int64_t M, int32_t N, int32_t K, int32_t act, void* stream);
 /* Fused v = A W^T + bias + resid ; y = LayerNorm(v) (tcgen05, cluster of N/256 CTAs; N in {256,512,768}, K % 64 == 0).
  * A [M,K], W [N,K] bf16; resid [M,N] fp32 (may alias C).  C [M,N] fp32 <- (raw32 ? v : y);  C2 [M,N] bf16 <- y. */
 int msq_gemm_ln(const void* A_dev, const void* W_dev, const float* bias_dev, const float* resid_dev, const float* gamma_dev,

@@ -43,6 +43,7 @@ SIGNATURES = {
     "msq_order_manuals_dev": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _I32, _P, _P]),
     "msq_order_manuals_host": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _I32, _P, _P]),
     "msq_gemm": (C.c_int, [_I32, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P]),
+    "msq_gemm_deferred_ln": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _F, _P, _P, _P, _I64, _I32, _I32, _I32, _P]),
     "msq_gemm_ln": (C.c_int, [_P, _P, _P, _P, _P, _P, _F, _P, _P, _I64, _I32, _I32, _I32, _P]),
     "msq_layernorm": (C.c_int, [_I32, _P, _I64, _I32, _P, _P, _F, _P, _P]),
     "msq_attention": (C.c_int, [_I32, _P, _I64, _I32, _I32, _F, _P, _I32, _P, _P]),

@@ -9,6 +9,7 @@
 #include <atomic>
 #include <string>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "../../include/msq_b200.h"
@@ -105,9 +106,12 @@ struct Lin {           // y = x W^T + b
   int N = 0, K = 0, ld = 0;
 };
 struct LNp { const float* g = nullptr; const float* b = nullptr; };
+// a linear layer with the LayerNorm in front of it folded in: lin.w16 = bf16(gamma_k W[n,k]), lin.b = b + W beta,
+// svec[n] = sum_k lin.w16[n,k]  (GemmArgs EPI_LNFOLD)
+struct LinF { Lin lin; const float* svec = nullptr; };
 
-struct BertLayerW { Lin qkv, out, up, down; LNp ln1, ln2; };
-struct VitLayerW { Lin qkv, out, fc, proj; LNp ln1, ln2; };
+struct BertLayerW { Lin qkv, out, up, down; LNp ln1, ln2; LinF qkv_f, up_f; };   // qkv_f folds the PREVIOUS layer's ln2, up_f this layer's ln1
+struct VitLayerW { Lin qkv, out, fc, proj; LNp ln1, ln2; LinF qkv_f, fc_f; };    // qkv_f folds ln_1, fc_f ln_2
 struct ParaLayerW { Lin qkv, fin, w1, w2; LNp ln_in, ln_ff; };
 struct RnBlockW { Lin c1, c2, c3, ds; bool has_ds = false; int stride = 1, cin = 0, planes = 0; };
 
@@ -129,6 +133,8 @@ struct msq_model {
   bool has_pooler = false;
   // vit
   Lin conv1, visn_fc;
+  LinF visn_fc_f;   // visn_fc with the ViT's ln_post folded in
+  bool folded = false;
   const float *vit_cls = nullptr, *vit_pos = nullptr;
   LNp ln_pre, ln_post, visn_ln;
   std::vector<VitLayerW> vit;
@@ -307,6 +313,51 @@ __global__ void training_loss_kernel(const float* __restrict__ nll, const float*
 // K of a convolution GEMM, padded so that the tcgen05 path (64-wide K slabs) applies whenever K >= 64
 static int rn_kpad(int K) { return K < 64 ? (K + 15) / 16 * 16 : (K + 63) / 64 * 64; }
 
+// Fold a LayerNorm into the linear layer that consumes it (one block per output feature n):
+//   wf[n,k] = bf16(gamma_k w[n,k]);  svec[n] = sum_k float(wf[n,k]);  bf[n] = b[n] + sum_k beta_k w[n,k]
+__global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ w, int ldw, const float* __restrict__ b,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta, int K,
+                                                      bf16* __restrict__ wf, float* __restrict__ svec, float* __restrict__ bf) {
+  pdl_sync();
+  __shared__ float sh[2][8];
+  const int n = blockIdx.x;
+  float s = 0.f, t = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float wv = w[(int64_t)n * ldw + k];
+    const bf16 r = __float2bfloat16_rn(gamma[k] * wv);
+    wf[(int64_t)n * K + k] = r;
+    s += __bfloat162float(r);
+    t = fmaf(beta[k], wv, t);
+  }
+  s = warp_sum(s); t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = t; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int i = 0; i < 8; ++i) { a += sh[0][i]; c += sh[1][i]; }
+    svec[n] = a;
+    bf[n] = (b ? b[n] : 0.f) + c;
+  }
+}
+static int make_folded(msq_model* m, const Lin& src, const LNp& ln, LinF* out, cudaStream_t st) {
+  bf16* wf; float *sv, *bf;
+  MSQ_TRY(dev_alloc(m, (size_t)src.N * src.K, &wf));
+  MSQ_TRY(dev_alloc(m, (size_t)src.N, &sv));
+  MSQ_TRY(dev_alloc(m, (size_t)src.N, &bf));
+  MSQ_CUDA(launch_k(fold_ln_kernel, dim3(src.N), dim3(256), 0, st, src.w32, src.ld, src.b, ln.g, ln.b, src.K, wf, sv, bf));
+  MSQ_LAUNCH_CHECK();
+  out->lin = src; out->lin.w32 = nullptr; out->lin.w16 = wf; out->lin.b = bf; out->lin.ld = src.K; out->svec = sv;
+  return MSQ_OK;
+}
+
+// Rows per slab of a residual-GEMM -> LayerNorm pair.  The pre-LN sum goes through a small scratch buffer that is
+// REUSED by every slab, so it is written and re-read in L2 (126 MB) and never travels to HBM.  0 = whole micro-batch.
+static int64_t slab_rows() {
+  static int64_t v = -1;
+  if (v < 0) { const char* e = getenv("MSQ_SLAB_ROWS"); v = e ? atoll(e) : 0; if (v < 0) v = 0; }
+  return v;
+}
+
 static bool use_tc(const msq_model* m) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("MSQ_FORCE_SIMT"); forced = (e && e[0] == '1') ? 1 : 0; }
@@ -330,6 +381,37 @@ static int run_gemm(const msq_model* m, const T* A, int lda, const Lin& w, const
     if (use_tc(m) && g.K % 64 == 0 && g.N % 8 == 0 && ldc % 8 == 0) return gemm_tc<TO>(g, st);
     return gemm_simt<bf16, TO>(g, st);
   }
+}
+
+// ---- deferred LayerNorm on the tensor-core path: a stream is kept RAW (fp32 Y + bf16 copy + per-row
+// partial sums); the LayerNorm that follows it is applied inside the consumers' epilogues and never materialised.
+static bool ln_fold_enabled(const msq_model* m) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MSQ_LNFOLD"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v && use_tc(m);
+}
+struct LnPending { const float* stats = nullptr; int sp = 0; LNp ln; float eps = 0.f; int dim = 0; };
+
+// C = act(LN_pending(Y) W^T + b) computed from the bf16 copy of the raw stream
+template <typename TO>
+static int run_gemm_fold(const bf16* Yt, int lda, const LinF& w, const LnPending& ln, TO* C, int ldc, int64_t M, int act, cudaStream_t st) {
+  GemmArgs g;
+  g.A = Yt; g.W = w.lin.w16; g.bias = w.lin.b; g.resid = nullptr; g.C = C; g.C2 = nullptr;
+  g.M = M; g.N = w.lin.N; g.K = w.lin.K; g.lda = lda; g.ldw = w.lin.ld; g.ldc = ldc; g.ldr = 0; g.act = act;
+  g.mode = EPI_LNFOLD; g.svec = w.svec; g.stats_in = ln.stats; g.sp_in = ln.sp; g.ln_inv_dim = 1.0f / (float)ln.dim; g.ln_eps = ln.eps;
+  return gemm_tc<TO>(g, st);
+}
+// Y <- A W^T + b + (ln ? LN_pending(Y) : Y) in place, plus its bf16 copy Yt and the partial row sums of the new Y
+static int run_gemm_resln(const bf16* A, int lda, const Lin& w, float* Y, bf16* Yt, const LnPending* ln, float* stats_out, int64_t M,
+                          cudaStream_t st) {
+  GemmArgs g;
+  g.A = A; g.W = w.w16; g.bias = w.b; g.resid = Y; g.C = Y; g.C2 = nullptr;
+  g.M = M; g.N = w.N; g.K = w.K; g.lda = lda; g.ldw = w.ld; g.ldc = w.N; g.ldr = w.N; g.act = ACT_NONE;
+  g.mode = EPI_RESLN; g.C2bf = Yt; g.stats_out = stats_out;
+  if (ln) {
+    g.svec = ln->ln.g; g.beta = ln->ln.b; g.stats_in = ln->stats; g.sp_in = ln->sp; g.ln_inv_dim = 1.0f / (float)ln->dim; g.ln_eps = ln->eps;
+  }
+  return gemm_tc<float>(g, st);
 }
 
 }  // namespace msq
@@ -515,6 +597,11 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
                      w16, &L.down, st));
     L.ln1 = {W(b + "attention.output.LayerNorm.weight", H), W(b + "attention.output.LayerNorm.bias", H)};
     L.ln2 = {W(b + "output.LayerNorm.weight", H), W(b + "output.LayerNorm.bias", H)};
+    if (w16 && miss.empty()) {   // deferred-LayerNorm copies (tensor-core path only)
+      MSQ_TRY(make_folded(m, L.up, L.ln1, &L.up_f, st));
+      if (l >= 1) MSQ_TRY(make_folded(m, L.qkv, m->bert[l - 1].ln2, &L.qkv_f, st));
+      m->folded = true;
+    }
   }
   if (m->raw.count(P + "pooler.dense.weight")) {
     MSQ_TRY(make_lin(m, W(P + "pooler.dense.weight", (int64_t)H * H), W(P + "pooler.dense.bias", H), H, H, H, false, &m->pooler, st));
@@ -603,11 +690,17 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
                        &L.proj, st));
       L.ln1 = {W(b + "ln_1.weight", Wd), W(b + "ln_1.bias", Wd)};
       L.ln2 = {W(b + "ln_2.weight", Wd), W(b + "ln_2.bias", Wd)};
+      if (w16 && miss.empty()) {
+        MSQ_TRY(make_folded(m, L.qkv, L.ln1, &L.qkv_f, st));
+        MSQ_TRY(make_folded(m, L.fc, L.ln2, &L.fc_f, st));
+        m->folded = true;
+      }
     }
     if (m->has_bert) {
       MSQ_TRY(make_lin(m, W(P + "encoder.visn_fc.visn_fc.weight", (int64_t)H * Wd), W(P + "encoder.visn_fc.visn_fc.bias", H), H, Wd, Wd,
                        w16, &m->visn_fc, st));
       m->visn_ln = {W(P + "encoder.visn_fc.visn_layer_norm.weight", H), W(P + "encoder.visn_fc.visn_layer_norm.bias", H)};
+      if (w16 && miss.empty()) MSQ_TRY(make_folded(m, m->visn_fc, m->ln_post, &m->visn_fc_f, st));
     }
   }
   // ---- BERSON heads
@@ -691,6 +784,10 @@ struct VitBufs {
   void* apatch; float* patch; float* xv; void* y; void* qkv; void* ctx; void* hbuf;
   // ModifiedResNet trunk scratch (per image chunk): block input / 1x1 out / 3x3 out / pooled copies, fp32 residual + shortcut
   void *rX, *rO1, *rO2, *rP1, *rP2; float *rF0, *rF1;
+  // deferred LayerNorm: partial row sums of the raw stream, and (set by run_vit) the ln_post still pending on b.y
+  float* st[2];
+  LnPending post;
+  bool post_pending;
 };
 constexpr int64_t IMG_CHUNK = 1024;  // images per im2col + patch-embed GEMM launch
 
@@ -705,6 +802,9 @@ static void plan_vit(const msq_config& c, Planner& p, int64_t n_img, int64_t R, 
   b->qkv = p.take<T>((size_t)R * Lv * 3 * Wd);
   b->ctx = p.take<T>((size_t)R * Lv * Wd);
   b->hbuf = p.take<T>((size_t)R * Lv * 4 * Wd);
+  const size_t sp = 2 * (size_t)ceil_div(Wd, 256);
+  b->st[0] = p.take<float>((size_t)R * Lv * sp * 2);
+  b->st[1] = p.take<float>((size_t)R * Lv * sp * 2);
 }
 
 // conv1 (32x32 / stride 32, no bias) as im2col + GEMM over all UNIQUE images -> b.patch [n_img*g2, W]
@@ -730,7 +830,31 @@ static int run_vit(msq_model* m, const int32_t* img_index, int64_t R, VitBufs& b
   const int g = c.vit_res / c.vit_patch, g2 = g * g, Lv = 1 + 2 * g2, Wd = c.vit_width, heads = Wd / 64;
   const int64_t Mv = R * Lv;
   MSQ_TRY(vit_assemble(b.patch, img_index, R, 2, g2, Wd, m->vit_cls, m->vit_pos, m->ln_pre.g, m->ln_pre.b, 1e-5f, b.xv, st));
+  b.post_pending = false;
   if constexpr (sizeof(T) == 2) {
+    if (ln_fold_enabled(m) && m->folded && !m->vit.empty() && !gemm_ln_enabled()) {
+      // Deferred LayerNorm: the residual stream x stays raw (fp32 b.xv + bf16 copy b.y + per-row partial sums written by
+      // the residual GEMMs); ln_2 / the next ln_1 / ln_post are applied inside the consuming GEMMs' epilogues.
+      const int sp = 2 * ceil_div(Wd, 256);
+      const size_t nl = m->vit.size();
+      MSQ_TRY(layernorm<T>(b.xv, Mv, Wd, m->vit[0].ln1.g, m->vit[0].ln1.b, 1e-5f, nullptr, (T*)b.y, 0, 0, 0, st));
+      LnPending pend;
+      pend.sp = sp; pend.eps = 1e-5f; pend.dim = Wd;
+      for (size_t l = 0; l < nl; ++l) {
+        VitLayerW& L = m->vit[l];
+        if (l == 0) MSQ_TRY((run_gemm<T, T>(m, (const T*)b.y, Wd, L.qkv, nullptr, 0, (T*)b.qkv, 3 * Wd, Mv, ACT_NONE, st)));
+        else MSQ_TRY(run_gemm_fold<bf16>((const bf16*)b.y, Wd, L.qkv_f, pend, (bf16*)b.qkv, 3 * Wd, Mv, ACT_NONE, st));
+        MSQ_TRY(attention<T>((const T*)b.qkv, R, Lv, heads, 64, 0.125f, nullptr, 0, 0, (T*)b.ctx, st));
+        MSQ_TRY(run_gemm_resln((const bf16*)b.ctx, Wd, L.out, b.xv, (bf16*)b.y, nullptr, b.st[0], Mv, st));
+        pend.stats = b.st[0]; pend.ln = L.ln2;
+        MSQ_TRY(run_gemm_fold<bf16>((const bf16*)b.y, Wd, L.fc_f, pend, (bf16*)b.hbuf, 4 * Wd, Mv, ACT_QUICK_GELU, st));
+        MSQ_TRY(run_gemm_resln((const bf16*)b.hbuf, 4 * Wd, L.proj, b.xv, (bf16*)b.y, nullptr, b.st[1], Mv, st));
+        pend.stats = b.st[1]; pend.ln = l + 1 < nl ? m->vit[l + 1].ln1 : m->ln_post;
+      }
+      b.post = pend;           // b.y is the RAW stream; ln_post is folded into visn_fc by the caller
+      b.post_pending = true;
+      return MSQ_OK;
+    }
     if (use_tc(m) && gemm_ln_enabled() && gemm_ln_supported(Wd, Wd) && gemm_ln_supported(Wd, 4 * Wd)) {
       // fused path: every residual GEMM also emits LayerNorm(x) (bf16) for the NEXT GEMM -- ln_2 after out_proj,
       // the next block's ln_1 (ln_post after the last block) after c_proj.  b.y ends up holding ln_post(x).
@@ -751,17 +875,26 @@ static int run_vit(msq_model* m, const int32_t* img_index, int64_t R, VitBufs& b
       return MSQ_OK;
     }
   }
+  if (!m->vit.empty()) MSQ_TRY(layernorm<T>(b.xv, Mv, Wd, m->vit[0].ln1.g, m->vit[0].ln1.b, 1e-5f, nullptr, (T*)b.y, 0, 0, 0, st));
   for (auto& L : m->vit) {
-    MSQ_TRY(layernorm<T>(b.xv, Mv, Wd, L.ln1.g, L.ln1.b, 1e-5f, nullptr, (T*)b.y, 0, 0, 0, st));
     MSQ_TRY((run_gemm<T, T>(m, (const T*)b.y, Wd, L.qkv, nullptr, 0, (T*)b.qkv, 3 * Wd, Mv, ACT_NONE, st)));
     MSQ_TRY(attention<T>((const T*)b.qkv, R, Lv, heads, 64, 0.125f, nullptr, 0, 0, (T*)b.ctx, st));
-    MSQ_TRY((run_gemm<T, float>(m, (const T*)b.ctx, Wd, L.out, b.xv, Wd, b.xv, Wd, Mv, ACT_NONE, st)));
-    MSQ_TRY(layernorm<T>(b.xv, Mv, Wd, L.ln2.g, L.ln2.b, 1e-5f, nullptr, (T*)b.y, 0, 0, 0, st));
+    const int64_t sl = slab_rows() ? slab_rows() : Mv;
+    for (int64_t r0 = 0; r0 < Mv; r0 += sl) {   // x += out_proj(ctx); y = ln_2(x), slab by slab (the LN reads x from L2)
+      const int64_t nr = min(sl, Mv - r0);
+      MSQ_TRY((run_gemm<T, float>(m, (const T*)b.ctx + r0 * Wd, Wd, L.out, b.xv + r0 * Wd, Wd, b.xv + r0 * Wd, Wd, nr, ACT_NONE, st)));
+      MSQ_TRY(layernorm<T>(b.xv + r0 * Wd, nr, Wd, L.ln2.g, L.ln2.b, 1e-5f, nullptr, (T*)b.y + r0 * Wd, 0, 0, 0, st));
+    }
     MSQ_TRY((run_gemm<T, T>(m, (const T*)b.y, Wd, L.fc, nullptr, 0, (T*)b.hbuf, 4 * Wd, Mv, ACT_QUICK_GELU, st)));
-    MSQ_TRY((run_gemm<T, float>(m, (const T*)b.hbuf, 4 * Wd, L.proj, b.xv, Wd, b.xv, Wd, Mv, ACT_NONE, st)));
+    const LNp& nxt = (&L == &m->vit.back()) ? m->ln_post : (&L + 1)->ln1;
+    for (int64_t r0 = 0; r0 < Mv; r0 += sl) {   // x += c_proj(h); y = next block's ln_1(x) (ln_post after the last block)
+      const int64_t nr = min(sl, Mv - r0);
+      MSQ_TRY((run_gemm<T, float>(m, (const T*)b.hbuf + r0 * 4 * Wd, 4 * Wd, L.proj, b.xv + r0 * Wd, Wd, b.xv + r0 * Wd, Wd, nr, ACT_NONE, st)));
+      MSQ_TRY(layernorm<T>(b.xv + r0 * Wd, nr, Wd, nxt.g, nxt.b, 1e-5f, nullptr, (T*)b.y + r0 * Wd, 0, 0, 0, st));
+    }
   }
-  MSQ_TRY(layernorm<T>(b.xv, Mv, Wd, m->ln_post.g, m->ln_post.b, 1e-5f, nullptr, (T*)b.y, 0, 0, 0, st));  // b.y = ln_post(x)
-  return MSQ_OK;
+  if (m->vit.empty()) MSQ_TRY(layernorm<T>(b.xv, Mv, Wd, m->ln_post.g, m->ln_post.b, 1e-5f, nullptr, (T*)b.y, 0, 0, 0, st));
+  return MSQ_OK;  // b.y = ln_post(x)
 }
 
 // ---- CLIP ModifiedResNet tower ---------------------------------------------------------------------
@@ -877,6 +1010,7 @@ static int run_visual_pairs(msq_model* m, const int32_t* img_index, int64_t R, V
 
 struct JointBufs {
   float* x; void* xt; float* tmp; void* qkv; void* ctx; void* hbuf; float* mask_add; float* vtmp;
+  float* st[2];   // deferred LayerNorm: partial row sums (ping-pong: a residual GEMM reads one set and writes the other)
 };
 
 template <typename T>
@@ -890,6 +1024,9 @@ static void plan_joint(const msq_config& c, Planner& p, int64_t R, int Lt, int L
   b->hbuf = p.take<T>((size_t)R * Lj * c.inter);
   b->mask_add = p.take<float>((size_t)R * Lt);
   b->vtmp = nullptr;
+  const size_t sp = 2 * (size_t)ceil_div(H, 256);
+  b->st[0] = p.take<float>((size_t)R * Lj * sp * 2);
+  b->st[1] = p.take<float>((size_t)R * Lj * sp * 2);
 }
 
 // inner encoder for R pair rows -> b.x holds the final joint stream [R, Lj, H] (fp32), b.xt its T copy
@@ -911,11 +1048,38 @@ static int run_inner(msq_model* m, const int64_t* ids, const int64_t* tt, const 
     const int Wd = c.vit_width;
     const int64_t Mv = R * Lv;
     // vb.y == ln_post(x); visn_fc output reuses the (now free) fp32 tmp buffer of the joint stream
-    MSQ_TRY((run_gemm<T, float>(m, (const T*)vb.y, Wd, m->visn_fc, nullptr, 0, jb.tmp, H, Mv, ACT_NONE, st)));
+    if (vb.post_pending) MSQ_TRY(run_gemm_fold<float>((const bf16*)vb.y, Wd, m->visn_fc_f, vb.post, jb.tmp, H, Mv, ACT_NONE, st));
+    else MSQ_TRY((run_gemm<T, float>(m, (const T*)vb.y, Wd, m->visn_fc, nullptr, 0, jb.tmp, H, Mv, ACT_NONE, st)));
     MSQ_TRY(layernorm<T>(jb.tmp, Mv, H, m->visn_ln.g, m->visn_ln.b, 1e-12f, jb.x, (T*)jb.xt, Lv, Lj, Lt, st));
   }
   bool fused = false;
   if constexpr (sizeof(T) == 2) fused = use_tc(m) && gemm_ln_enabled() && gemm_ln_supported(H, H) && gemm_ln_supported(H, c.inter);
+  if constexpr (sizeof(T) == 2) {
+    if (ln_fold_enabled(m) && m->folded && !fused && !m->bert.empty()) {
+      // Deferred LayerNorm through the post-LN BERT stack: jb.x / jb.xt hold the RAW sums (dense(...) + residual), the
+      // LayerNorm after each sub-layer lives in the consumers: folded into the next QKV / intermediate GEMM and applied
+      // to the residual operand inside the next residual GEMM's epilogue.  Only the stack's final output is normalised
+      // by a kernel of its own.
+      LnPending pend;
+      pend.sp = 2 * ceil_div(H, 256); pend.eps = 1e-12f; pend.dim = H;
+      bool have = false;
+      int cur = 0;
+      for (auto& L : m->bert) {
+        if (have) MSQ_TRY(run_gemm_fold<bf16>((const bf16*)jb.xt, H, L.qkv_f, pend, (bf16*)jb.qkv, 3 * H, Mj, ACT_NONE, st));
+        else MSQ_TRY((run_gemm<T, T>(m, (const T*)jb.xt, H, L.qkv, nullptr, 0, (T*)jb.qkv, 3 * H, Mj, ACT_NONE, st)));
+        MSQ_TRY(attention<T>((const T*)jb.qkv, R, Lj, c.heads, 64, 0.125f, jb.mask_add, Lt, Lt, (T*)jb.ctx, st));
+        MSQ_TRY(run_gemm_resln((const bf16*)jb.ctx, H, L.out, jb.x, (bf16*)jb.xt, have ? &pend : nullptr, jb.st[cur ^ 1], Mj, st));
+        cur ^= 1; pend.stats = jb.st[cur]; pend.ln = L.ln1; have = true;
+        MSQ_TRY(run_gemm_fold<bf16>((const bf16*)jb.xt, H, L.up_f, pend, (bf16*)jb.hbuf, c.inter, Mj, ACT_GELU_ERF, st));
+        MSQ_TRY(run_gemm_resln((const bf16*)jb.hbuf, c.inter, L.down, jb.x, (bf16*)jb.xt, &pend, jb.st[cur ^ 1], Mj, st));
+        cur ^= 1; pend.stats = jb.st[cur]; pend.ln = L.ln2;
+      }
+      MSQ_TRY(layernorm<T>(jb.x, Mj, H, pend.ln.g, pend.ln.b, 1e-12f, jb.tmp, (T*)jb.xt, 0, 0, 0, st));
+      std::swap(jb.x, jb.tmp);   // callers read the final stream from jb.x
+      return MSQ_OK;
+    }
+  }
+  const int64_t sl = slab_rows() ? slab_rows() : Mj;
   for (auto& L : m->bert) {
     MSQ_TRY((run_gemm<T, T>(m, (const T*)jb.xt, H, L.qkv, nullptr, 0, (T*)jb.qkv, 3 * H, Mj, ACT_NONE, st)));
     MSQ_TRY(attention<T>((const T*)jb.qkv, R, Lj, c.heads, 64, 0.125f, jb.mask_add, Lt, Lt, (T*)jb.ctx, st));
@@ -924,16 +1088,22 @@ static int run_inner(msq_model* m, const int64_t* ids, const int64_t* tt, const 
       MSQ_TRY(gemm_ln((const bf16*)jb.ctx, H, L.out.w16, L.out.ld, L.out.b, jb.x, H, L.ln1.g, L.ln1.b, 1e-12f, jb.x, (bf16*)jb.xt, Mj, H, H,
                       false, st));
     } else {
-      MSQ_TRY((run_gemm<T, float>(m, (const T*)jb.ctx, H, L.out, jb.x, H, jb.tmp, H, Mj, ACT_NONE, st)));
-      MSQ_TRY(layernorm<T>(jb.tmp, Mj, H, L.ln1.g, L.ln1.b, 1e-12f, jb.x, (T*)jb.xt, 0, 0, 0, st));
+      for (int64_t r0 = 0; r0 < Mj; r0 += sl) {
+        const int64_t nr = min(sl, Mj - r0);
+        MSQ_TRY((run_gemm<T, float>(m, (const T*)jb.ctx + r0 * H, H, L.out, jb.x + r0 * H, H, jb.tmp, H, nr, ACT_NONE, st)));
+        MSQ_TRY(layernorm<T>(jb.tmp, nr, H, L.ln1.g, L.ln1.b, 1e-12f, jb.x + r0 * H, (T*)jb.xt + r0 * H, 0, 0, 0, st));
+      }
     }
     MSQ_TRY((run_gemm<T, T>(m, (const T*)jb.xt, H, L.up, nullptr, 0, (T*)jb.hbuf, c.inter, Mj, ACT_GELU_ERF, st)));
     if (fused) {
       MSQ_TRY(gemm_ln((const bf16*)jb.hbuf, c.inter, L.down.w16, L.down.ld, L.down.b, jb.x, H, L.ln2.g, L.ln2.b, 1e-12f, jb.x,
                       (bf16*)jb.xt, Mj, H, c.inter, false, st));
     } else {
-      MSQ_TRY((run_gemm<T, float>(m, (const T*)jb.hbuf, c.inter, L.down, jb.x, H, jb.tmp, H, Mj, ACT_NONE, st)));
-      MSQ_TRY(layernorm<T>(jb.tmp, Mj, H, L.ln2.g, L.ln2.b, 1e-12f, jb.x, (T*)jb.xt, 0, 0, 0, st));
+      for (int64_t r0 = 0; r0 < Mj; r0 += sl) {
+        const int64_t nr = min(sl, Mj - r0);
+        MSQ_TRY((run_gemm<T, float>(m, (const T*)jb.hbuf + r0 * c.inter, c.inter, L.down, jb.x + r0 * H, H, jb.tmp, H, nr, ACT_NONE, st)));
+        MSQ_TRY(layernorm<T>(jb.tmp, nr, H, L.ln2.g, L.ln2.b, 1e-12f, jb.x + r0 * H, (T*)jb.xt + r0 * H, 0, 0, 0, st));
+      }
     }
   }
   return MSQ_OK;
@@ -1365,6 +1535,19 @@ extern "C" int msq_gemm(int32_t dtype, const void* A_dev, const void* W_dev, con
   }
   set_error("msq_gemm: unknown dtype %d", dtype);
   return MSQ_ERR_ARG;
+}
+
+extern "C" int msq_gemm_deferred_ln(int32_t mode, int32_t out_bf16, const void* A_dev, const void* W_dev, const float* bias_dev,
+                                    const float* resid_dev, const float* svec_or_gamma_dev, const float* beta_dev,
+                                    const float* stats_in_dev, int32_t sp_in, int32_t ln_dim, float eps, void* C_dev, void* C2bf_dev,
+                                    float* stats_out_dev, int64_t M, int32_t N, int32_t K, int32_t act, void* stream) {
+  MSQ_REQUIRE(mode == EPI_LNFOLD || mode == EPI_RESLN, "msq_gemm_deferred_ln: mode %d", mode);
+  GemmArgs g;
+  g.A = A_dev; g.W = W_dev; g.bias = bias_dev; g.resid = resid_dev; g.C = C_dev; g.C2 = nullptr;
+  g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldc = N; g.ldr = N; g.act = act;
+  g.mode = mode; g.svec = svec_or_gamma_dev; g.beta = beta_dev; g.stats_in = stats_in_dev; g.sp_in = sp_in;
+  g.ln_inv_dim = ln_dim > 0 ? 1.0f / (float)ln_dim : 0.f; g.ln_eps = eps; g.stats_out = stats_out_dev; g.C2bf = C2bf_dev;
+  return out_bf16 ? gemm_tc<bf16>(g, (cudaStream_t)stream) : gemm_tc<float>(g, (cudaStream_t)stream);
 }
 
 extern "C" int msq_gemm_ln(const void* A_dev, const void* W_dev, const float* bias_dev, const float* resid_dev,

@@ -131,9 +131,10 @@ __device__ __forceinline__ float tanh_approx(float x) {
 __device__ __forceinline__ float apply_act_fast(float x, int act) {
   switch (act) {
     case ACT_GELU_ERF: {
-      const float xc = fminf(fmaxf(x, -6.0f), 6.0f);  // the fit holds on [-8,8]; tanh has saturated to +-1 well before 6
-      const float x2 = xc * xc;
-      const float p = xc * fmaf(x2, fmaf(x2, -3.58618502e-04f, 3.70495807e-02f), 7.97459395e-01f);
+      // the fit holds on [-8,8]; beyond |x| = 6 the polynomial is frozen at its (positive) value there, so p keeps
+      // growing linearly and tanh stays saturated at +-1: one clamp instead of two
+      const float x2 = fminf(x * x, 36.0f);
+      const float p = x * fmaf(x2, fmaf(x2, -3.58618502e-04f, 3.70495807e-02f), 7.97459395e-01f);
       const float hx = 0.5f * x;
       return fmaf(hx, tanh_approx(p), hx);
     }

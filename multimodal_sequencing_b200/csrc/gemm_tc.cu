@@ -30,17 +30,20 @@ constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_EPI_WARPS = 8, TC_THREADS = (2 + TC_EPI_WARPS) * 32;
 
-template <bool PAIR> struct TcCfg {
+template <bool PAIR, int MODE = 0> struct TcCfg {
   static constexpr int STAGES = 4;
   // PAIR: the epilogue stages 32-row x 128-byte output boxes in shared memory (2 per warp) and writes
   // them with TMA bulk tensor stores (full-line, asynchronous) instead of per-thread 16-byte stores.
   static constexpr bool TMA_STORE = PAIR;
-  static constexpr int STAGING_BYTES = TMA_STORE ? TC_EPI_WARPS * 2 * 4096 : 0;
+  static constexpr int STAGING_F32 = TMA_STORE ? TC_EPI_WARPS * 2 * 4096 : 0;
+  // EPI_RESLN: one more box per warp for the bf16 copy, 32 rows x 32 columns (64-byte rows, 64B swizzle), stored every chunk
+  static constexpr int STAGING_BYTES = STAGING_F32 + ((TMA_STORE && MODE == 2) ? TC_EPI_WARPS * 2048 : 0);
+  static constexpr int VECS = MODE == 0 ? 1 : (MODE == 1 ? 2 : 3);   // per-column vectors held per warp: bias | svec/gamma | beta
   static constexpr int B_ROWS = PAIR ? 128 : 256;            // rows of W staged per CTA and stage
   static constexpr int B_BYTES = B_ROWS * TC_BK * 2;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   static constexpr int TILE_M = PAIR ? 256 : 128;            // rows of C per scheduling unit (CTA or CTA pair)
-  static constexpr int SMEM = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TC_EPI_WARPS * 128 * 4 /*bias*/;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/ + VECS * TC_EPI_WARPS * 128 * 4;
 };
 
 struct TcEpi {
@@ -49,7 +52,48 @@ struct TcEpi {
   void* C;
   int64_t M;
   int N, ldc, ldr, act;
+  // deferred LayerNorm (GemmArgs)
+  const float* svec;
+  const float* beta;
+  const float* stats_in;
+  float* stats_out;
+  bf16* C2;
+  int sp_in;
+  float inv_dim, eps;
 };
+
+// 8 consecutive output columns of one row: accumulator -> value to store (see GemmArgs for the modes)
+template <int ACT, int MODE>
+__device__ __forceinline__ void epi_compute8(float* v, const uint32_t* raw, const float* bias8, const float* s8, const float* beta8,
+                                             float ra, float rc, bool has_ln, bool use_res, const float4& r0, const float4& r1) {
+  const float4 b0 = *reinterpret_cast<const float4*>(bias8), b1 = *reinterpret_cast<const float4*>(bias8 + 4);
+  const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  if (MODE == 1) {
+    const float4 s0 = *reinterpret_cast<const float4*>(s8), s1 = *reinterpret_cast<const float4*>(s8 + 4);
+    const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(ra, __uint_as_float(raw[i]), fmaf(rc, sv[i], b[i]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[i]) + b[i];
+  }
+  if (ACT != ACT_NONE) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = apply_act_fast(v[i], ACT);
+  }
+  if (use_res) {
+    float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    if (MODE == 2 && has_ln) {
+      const float4 g0 = *reinterpret_cast<const float4*>(s8), g1 = *reinterpret_cast<const float4*>(s8 + 4);
+      const float4 e0 = *reinterpret_cast<const float4*>(beta8), e1 = *reinterpret_cast<const float4*>(beta8 + 4);
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bt[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = fmaf(fmaf(ra, r[i], rc), gm[i], bt[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += r[i];
+  }
+}
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -105,11 +149,13 @@ template <> __device__ __forceinline__ void epi_store8<bf16>(bf16* p, const floa
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-template <typename TO, bool PAIR, int ACT>
+template <typename TO, bool PAIR, int ACT, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const __grid_constant__ CUtensorMap tma_c, TcEpi ep, int num_m, int num_n, int num_k) {
-  using Cfg = TcCfg<PAIR>;
+               const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_c2, TcEpi ep, int num_m, int num_n,
+               int num_k) {
+  using Cfg = TcCfg<PAIR, MODE>;
+  static_assert(MODE != 2 || sizeof(TO) == 4, "EPI_RESLN writes the fp32 stream (+ its bf16 copy)");
   constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -131,6 +177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
     if (Cfg::TMA_STORE) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_c) : "memory");
+    if (Cfg::TMA_STORE && MODE == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_c2) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, TC_EPI_WARPS * (PAIR ? 2 : 1)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -214,17 +261,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int q = warp & 3;                 // TMEM lane quarter this warp may touch
     const int half = (warp - 2) >> 2;       // column half: 0 -> [0,128), 1 -> [128,256)
     float* bias_s = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + Cfg::STAGING_BYTES + 256) + (warp - 2) * 128;
+    float* svec_s = bias_s + TC_EPI_WARPS * 128;   // MODE 1: s_n; MODE 2: gamma of the LayerNorm pending on the residual
+    float* beta_s = svec_s + TC_EPI_WARPS * 128;   // MODE 2: its beta
     const uint32_t stg = staging0 + (warp - 2) * 8192;  // this warp's two staging boxes
+    const uint32_t stg2 = staging0 + Cfg::STAGING_F32 + (warp - 2) * 2048;  // MODE 2: bf16 box (32 rows x 32 columns)
     int stg_use = 0;                                       // boxes handed to the TMA so far (parity selects the buffer)
     int acc = 0;
     uint32_t acc_phase = 0;
     TO* C = reinterpret_cast<TO*>(ep.C);
+    const bool use_res = ep.resid != nullptr;
+    // residual rows are pulled into L2 one tile ahead (no registers held): the epilogue of a K=768 residual GEMM is
+    // HBM-latency bound otherwise, with only one 32-column chunk of loads in flight per thread
+    auto prefetch_res = [&](int t) {
+      if (!use_res || t >= num_tiles) return;
+      const int64_t r2 = (int64_t)(t / num_n) * Cfg::TILE_M + (int)rank * TC_BM + q * 32 + lane;
+      const int c2 = (t % num_n) * TC_BN + half * 128;
+      if (r2 >= ep.M) return;
+      const float* p = ep.resid + r2 * ep.ldr + c2;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (c2 + 32 * i < ep.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 32 * i));
+    };
+    prefetch_res(unit);
     for (int tile = unit; tile < num_tiles; tile += num_units) {
       const int n_blk = tile % num_n, m_blk = tile / num_n;
       const int64_t row = (int64_t)m_blk * Cfg::TILE_M + (int)rank * TC_BM + q * 32 + lane;
       const bool row_ok = row < ep.M;
       const int colw = n_blk * TC_BN + half * 128;   // first column of this warp
-      const bool use_res = ep.resid != nullptr;
+      prefetch_res(tile + num_units);
       float4 res[8];
       auto fetch_res = [&](int ch, float4* dst) {
         const int c0 = colw + ch * 32;
@@ -238,10 +302,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int c = colw + lane * 4;
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ep.bias && c < ep.N) b = __ldg(reinterpret_cast<const float4*>(ep.bias + c));
+        float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), bt = sv;
+        if (MODE >= 1 && ep.svec && c < ep.N) sv = __ldg(reinterpret_cast<const float4*>(ep.svec + c));
+        if (MODE == 2 && ep.beta && c < ep.N) bt = __ldg(reinterpret_cast<const float4*>(ep.beta + c));
         __syncwarp();
         *reinterpret_cast<float4*>(bias_s + lane * 4) = b;
+        if (MODE >= 1) *reinterpret_cast<float4*>(svec_s + lane * 4) = sv;
+        if (MODE == 2) *reinterpret_cast<float4*>(beta_s + lane * 4) = bt;
         __syncwarp();
       }
+      // pending LayerNorm of this row: ra = rstd, rc = -rstd * mean, from the partial sums of the producer
+      float ra = 1.f, rc = 0.f;
+      const bool has_ln = MODE != 0 && ep.stats_in != nullptr;
+      if (has_ln && row_ok) {
+        float s1 = 0.f, s2 = 0.f;
+        const float2* sp = reinterpret_cast<const float2*>(ep.stats_in) + row * ep.sp_in;
+        for (int i = 0; i < ep.sp_in; ++i) { const float2 t = __ldg(sp + i); s1 += t.x; s2 += t.y; }
+        const float mu = s1 * ep.inv_dim;
+        ra = rsqrtf(fmaxf(s2 * ep.inv_dim - mu * mu, 0.f) + ep.eps);
+        rc = -ra * mu;
+      }
+      float st_sum = 0.f, st_sq = 0.f;   // MODE 2: statistics of the row segment this thread writes
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       __syncwarp();
       tc_fence_after();
@@ -269,7 +350,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           constexpr bool F32 = sizeof(TO) == 4;
           const bool new_box = F32 || (ch & 1) == 0;
           if (new_box) {
-            if (lane == 0) tma_store_wait_read<1>();   // the box used two stores ago has been read out
+            // the fp32 box used two chunks ago has been read out; MODE 2 commits the bf16 box of a chunk BEFORE its fp32 box,
+            // so "all but the newest group" also covers the single bf16 box of the previous chunk
+            if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
           }
           const uint32_t box = stg + (stg_use & 1) * 4096;
@@ -277,19 +360,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float v[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch * 32 + j * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch * 32 + j * 8 + 4);
-            v[0] = __uint_as_float(raw[j * 8 + 0]) + b0.x; v[1] = __uint_as_float(raw[j * 8 + 1]) + b0.y;
-            v[2] = __uint_as_float(raw[j * 8 + 2]) + b0.z; v[3] = __uint_as_float(raw[j * 8 + 3]) + b0.w;
-            v[4] = __uint_as_float(raw[j * 8 + 4]) + b1.x; v[5] = __uint_as_float(raw[j * 8 + 5]) + b1.y;
-            v[6] = __uint_as_float(raw[j * 8 + 6]) + b1.z; v[7] = __uint_as_float(raw[j * 8 + 7]) + b1.w;
-            if (ACT != ACT_NONE) {
+            epi_compute8<ACT, MODE>(v, raw + j * 8, bias_s + ch * 32 + j * 8, svec_s + ch * 32 + j * 8, beta_s + ch * 32 + j * 8, ra, rc,
+                                    has_ln, use_res, res[2 * j], res[2 * j + 1]);
+            if (MODE == 2) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = apply_act_fast(v[i], ACT);
-            }
-            if (use_res) {
-              const float4 r0 = res[2 * j], r1 = res[2 * j + 1];
-              v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+              for (int i = 0; i < 8; ++i) { st_sum += v[i]; st_sq = fmaf(v[i], v[i], st_sq); }
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+              // 64-byte rows, 64B swizzle: 16-byte piece j of row r sits at r*64 + ((j ^ ((r >> 1) & 3)) << 4)
+              st_shared_v4(stg2 + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), *reinterpret_cast<uint32_t*>(&p0),
+                           *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
             }
             if (F32) {
               st_shared_v4(rowp + (((2 * j) ^ (lane & 7)) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
@@ -306,6 +386,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             __syncwarp();
             if (lane == 0) {
               const int box_col = F32 ? col0 : col0 - 32;
+              if (MODE == 2) {
+                if (col0 < ep.N) tma_store_2d(&tma_c2, stg2, col0, (int)(row - lane));
+                tma_store_commit();
+              }
               if (box_col < ep.N) tma_store_2d(&tma_c, box, box_col, (int)(row - lane));
               tma_store_commit();
             }
@@ -317,25 +401,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const int col = col0 + j * 8;
             if (col < ep.N) {  // N % 8 == 0
               float v[8];
-              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch * 32 + j * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch * 32 + j * 8 + 4);
-              v[0] = __uint_as_float(raw[j * 8 + 0]) + b0.x; v[1] = __uint_as_float(raw[j * 8 + 1]) + b0.y;
-              v[2] = __uint_as_float(raw[j * 8 + 2]) + b0.z; v[3] = __uint_as_float(raw[j * 8 + 3]) + b0.w;
-              v[4] = __uint_as_float(raw[j * 8 + 4]) + b1.x; v[5] = __uint_as_float(raw[j * 8 + 5]) + b1.y;
-              v[6] = __uint_as_float(raw[j * 8 + 6]) + b1.z; v[7] = __uint_as_float(raw[j * 8 + 7]) + b1.w;
-              if (ACT != ACT_NONE) {
+              epi_compute8<ACT, MODE>(v, raw + j * 8, bias_s + ch * 32 + j * 8, svec_s + ch * 32 + j * 8, beta_s + ch * 32 + j * 8, ra, rc,
+                                      has_ln, use_res, res[2 * j], res[2 * j + 1]);
+              if (MODE == 2) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = apply_act_fast(v[i], ACT);
-              }
-              if (use_res) {
-                const float4 r0 = res[2 * j], r1 = res[2 * j + 1];
-                v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+                for (int i = 0; i < 8; ++i) { st_sum += v[i]; st_sq = fmaf(v[i], v[i], st_sq); }
+                epi_store8<bf16>(ep.C2 + row * ep.ldc + col, v);
               }
               epi_store8<TO>(C + row * ep.ldc + col, v);
             }
           }
         }
       }
+      if (MODE == 2 && ep.stats_out && row_ok)
+        reinterpret_cast<float2*>(ep.stats_out)[row * (2 * num_n) + n_blk * 2 + half] = make_float2(st_sum, st_sq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -361,21 +440,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
 int gemm_tc_selftest_supported() { return tc_supported_impl(); }
 
-template <typename TO, bool PAIR, int ACT>
+template <typename TO, bool PAIR, int ACT, int MODE>
 static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
-  using Cfg = TcCfg<PAIR>;
+  using Cfg = TcCfg<PAIR, MODE>;
   CUtensorMap ma, mb;
   MSQ_TRY(make_map_bf16(&ma, g.A, g.M, g.K, g.lda, TC_BK, TC_BM));
   MSQ_TRY(make_map_bf16(&mb, g.W, g.N, g.K, g.ldw, TC_BK, Cfg::B_ROWS));
   CUtensorMap mc = ma;
+  CUtensorMap mc2 = ma;
   if (Cfg::TMA_STORE) MSQ_TRY(make_map_2d(&mc, g.C, g.M, g.N, g.ldc, 128 / (int)sizeof(TO), 32, sizeof(TO) == 4));
+  if (Cfg::TMA_STORE && MODE == 2) MSQ_TRY(make_map_2d(&mc2, g.C2bf, g.M, g.N, g.ldc, 32, 32, false, true));
   static bool configured = false;
   if (!configured) {
-    MSQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TO, PAIR, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    MSQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TO, PAIR, ACT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     configured = true;
   }
   TcEpi ep;
   ep.bias = g.bias; ep.resid = g.resid; ep.C = g.C; ep.M = g.M; ep.N = g.N; ep.ldc = g.ldc; ep.ldr = g.ldr; ep.act = g.act;
+  ep.svec = g.svec; ep.beta = g.beta; ep.stats_in = g.stats_in; ep.stats_out = g.stats_out; ep.C2 = (bf16*)g.C2bf; ep.sp_in = g.sp_in;
+  ep.inv_dim = g.ln_inv_dim; ep.eps = g.ln_eps;
   const int num_m = ceil_div(g.M, Cfg::TILE_M), num_n = ceil_div(g.N, TC_BN), num_k = g.K / TC_BK;
   const int64_t tiles = (int64_t)num_m * num_n;
   profile_mark(st, false, 0.0);
@@ -393,10 +476,10 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
     attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    MSQ_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<TO, PAIR, ACT>, ma, mb, mc, ep, num_m, num_n, num_k));
+    MSQ_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<TO, PAIR, ACT, MODE>, ma, mb, mc, mc2, ep, num_m, num_n, num_k));
   } else {
     const int grid = (int)min((int64_t)sms, tiles);
-    MSQ_CUDA(launch_k(gemm_tc_kernel<TO, PAIR, ACT>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM, st, ma, mb, mc, ep, num_m, num_n, num_k));
+    MSQ_CUDA(launch_k(gemm_tc_kernel<TO, PAIR, ACT, MODE>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM, st, ma, mb, mc, mc2, ep, num_m, num_n, num_k));
   }
   MSQ_LAUNCH_CHECK();
   profile_mark(st, true, 2.0 * (double)g.M * (double)g.N * (double)g.K);
@@ -405,12 +488,31 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
 
 template <typename TO, bool PAIR>
 static int launch_gemm_tc(const GemmArgs& g, int sms, cudaStream_t st) {
+  if (g.mode == EPI_RESLN) {
+    if constexpr (sizeof(TO) == 4) {
+      MSQ_REQUIRE(g.act == ACT_NONE && g.C2bf && g.stats_out && g.resid, "gemm_tc: EPI_RESLN needs resid, C2bf, stats_out and no activation");
+      return launch_gemm_tc_act<TO, PAIR, ACT_NONE, 2>(g, sms, st);
+    } else {
+      set_error("gemm_tc: EPI_RESLN writes an fp32 stream");
+      return MSQ_ERR_ARG;
+    }
+  }
+  if (g.mode == EPI_LNFOLD) {
+    MSQ_REQUIRE(g.svec && g.stats_in && g.sp_in > 0, "gemm_tc: EPI_LNFOLD needs svec and stats_in");
+    switch (g.act) {
+      case ACT_NONE: return launch_gemm_tc_act<TO, PAIR, ACT_NONE, 1>(g, sms, st);
+      case ACT_GELU_ERF: return launch_gemm_tc_act<TO, PAIR, ACT_GELU_ERF, 1>(g, sms, st);
+      case ACT_QUICK_GELU: return launch_gemm_tc_act<TO, PAIR, ACT_QUICK_GELU, 1>(g, sms, st);
+    }
+    set_error("gemm_tc: activation %d not instantiated for EPI_LNFOLD", g.act);
+    return MSQ_ERR_ARG;
+  }
   switch (g.act) {
-    case ACT_NONE: return launch_gemm_tc_act<TO, PAIR, ACT_NONE>(g, sms, st);
-    case ACT_GELU_ERF: return launch_gemm_tc_act<TO, PAIR, ACT_GELU_ERF>(g, sms, st);
-    case ACT_QUICK_GELU: return launch_gemm_tc_act<TO, PAIR, ACT_QUICK_GELU>(g, sms, st);
-    case ACT_TANH: return launch_gemm_tc_act<TO, PAIR, ACT_TANH>(g, sms, st);
-    case ACT_RELU: return launch_gemm_tc_act<TO, PAIR, ACT_RELU>(g, sms, st);
+    case ACT_NONE: return launch_gemm_tc_act<TO, PAIR, ACT_NONE, 0>(g, sms, st);
+    case ACT_GELU_ERF: return launch_gemm_tc_act<TO, PAIR, ACT_GELU_ERF, 0>(g, sms, st);
+    case ACT_QUICK_GELU: return launch_gemm_tc_act<TO, PAIR, ACT_QUICK_GELU, 0>(g, sms, st);
+    case ACT_TANH: return launch_gemm_tc_act<TO, PAIR, ACT_TANH, 0>(g, sms, st);
+    case ACT_RELU: return launch_gemm_tc_act<TO, PAIR, ACT_RELU, 0>(g, sms, st);
   }
   set_error("gemm_tc: activation %d not supported on the tensor-core path", g.act);
   return MSQ_ERR_ARG;

@@ -35,6 +35,9 @@ int rn_tokens(const float* feat, const int32_t* img_index, int64_t R, int g2, in
 template <typename T> int rn_finish(const float* o, int64_t rows, int L, int E, const float* posadd, T* out, cudaStream_t st);
 
 // ---- gemm_simt.cu : C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual), fp32 FFMA accumulate
+// epilogue modes of the tensor-core GEMM (deferred LayerNorm, see gemm_tc.cu)
+enum { EPI_PLAIN = 0, EPI_LNFOLD = 1, EPI_RESLN = 2 };
+
 struct GemmArgs {
   const void* A;       // [M, lda]  (TA)
   const void* W;       // [N, ldw]  (TA)
@@ -45,6 +48,21 @@ struct GemmArgs {
   int64_t M;
   int N, K, lda, ldw, ldc, ldr;
   int act;
+  // ---- deferred LayerNorm (gemm_tc only).  A LayerNorm "pending" on a stream Y is described by per-row partial sums
+  // stats [M, sp, 2] = (sum y, sum y^2) over column groups, its gamma/beta and eps; it is never materialised:
+  //   EPI_LNFOLD  A is the bf16 copy of the RAW stream, W carries gamma (W' = gamma_k W[n,k]), bias carries
+  //               b + W beta, svec[n] = sum_k W'[n,k]:  C = act(rstd_m (acc - mu_m svec_n) + bias_n)
+  //   EPI_RESLN   C = acc + bias + LN_pending(resid) (raw resid when stats_in is null); also writes the bf16 copy C2bf
+  //               and the partial statistics of the rows it produced (stats_out [M, 2*ceil(N/256), 2]), i.e. the
+  //               NEXT pending LayerNorm's input.  svec/beta hold gamma/beta of the LayerNorm pending on resid.
+  int mode = EPI_PLAIN;
+  const float* svec = nullptr;
+  const float* beta = nullptr;
+  const float* stats_in = nullptr;
+  int sp_in = 0;
+  float ln_inv_dim = 0.f, ln_eps = 0.f;
+  float* stats_out = nullptr;
+  void* C2bf = nullptr;
 };
 template <typename TA, typename TO> int gemm_simt(const GemmArgs& g, cudaStream_t st);
 

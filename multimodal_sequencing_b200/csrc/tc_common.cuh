@@ -139,18 +139,21 @@ inline int tc_supported_impl() {
 
 // 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld; box = box_cols x box_rows,
 // 128-byte swizzle (box_cols * 2 bytes must be 128), out-of-bounds elements read as zero.
-inline int make_map_2d(CUtensorMap* map, const void* ptr, int64_t rows, int K, int ld, int box_cols, int box_rows, bool f32);
+inline int make_map_2d(CUtensorMap* map, const void* ptr, int64_t rows, int K, int ld, int box_cols, int box_rows, bool f32,
+                       bool swizzle64 = false);
 inline int make_map_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int K, int ld, int box_cols, int box_rows) {
   return make_map_2d(map, ptr, rows, K, ld, box_cols, box_rows, false);
 }
-// element type bf16 or fp32; box_cols * sizeof(elem) must be 128 bytes (one swizzle row)
-inline int make_map_2d(CUtensorMap* map, const void* ptr, int64_t rows, int K, int ld, int box_cols, int box_rows, bool f32) {
+// element type bf16 or fp32; box_cols * sizeof(elem) must be 128 bytes (one swizzle row), or 64 bytes with swizzle64
+inline int make_map_2d(CUtensorMap* map, const void* ptr, int64_t rows, int K, int ld, int box_cols, int box_rows, bool f32,
+                       bool swizzle64) {
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = get_encode_fn()(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld K=%d ld=%d", (int)r, (long long)rows, K, ld);

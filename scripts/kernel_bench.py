@@ -73,6 +73,41 @@ def bench_gemm():
         del A, W, out, res
 
 
+def bench_deferred():
+    """The deferred-LayerNorm epilogues next to the plain GEMM + separate LayerNorm they replace (BERT layer shapes)."""
+    M, H, I = 145280, 768, 3072
+    sp = 6
+    gam, bet = torch.ones(H, device=dev), torch.zeros(H, device=dev)
+    stats = torch.zeros(M, sp, 2, device=dev)
+    stats[:, :, 1] = 128.0
+    stats_o = torch.empty(M, sp, 2, device=dev)
+    y = torch.randn(M, H, device=dev)
+    yt = y.bfloat16()
+    for name, N, K, act in (("qkv", 3 * H, H, 0), ("ffn_up_gelu", I, H, 1)):
+        W = (torch.randn(N, K, device=dev) * 0.02).bfloat16()
+        bias, sv = torch.zeros(N, device=dev), torch.zeros(N, device=dev)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        ms0 = timed(lambda: lib.msq_gemm(2, yt.data_ptr(), W.data_ptr(), bias.data_ptr(), None, out.data_ptr(), M, N, K, act, st()), iters=8)
+        ms1 = timed(lambda: lib.msq_gemm_deferred_ln(1, 1, yt.data_ptr(), W.data_ptr(), bias.data_ptr(), None, sv.data_ptr(), None,
+                                                     stats.data_ptr(), sp, H, 1e-12, out.data_ptr(), None, None, M, N, K, act, st()), iters=8)
+        print(json.dumps(dict(kernel="gemm_tc " + name, plain_ms=ms0, folded_ms=ms1, tflops_folded=2.0 * M * N * K / ms1 / 1e9)))
+        del W, out
+    ln_ms = timed(lambda: lib.msq_layernorm(1, y.data_ptr(), M, H, gam.data_ptr(), bet.data_ptr(), 1e-12, yt.data_ptr(), st()))
+    for name, K in (("out_proj", H), ("ffn_down", I)):
+        A = torch.randn(M, K, device=dev).bfloat16()
+        W = (torch.randn(H, K, device=dev) * 0.02).bfloat16()
+        bias = torch.zeros(H, device=dev)
+        tmp = torch.empty(M, H, device=dev)
+        ms0 = timed(lambda: lib.msq_gemm(1, A.data_ptr(), W.data_ptr(), bias.data_ptr(), y.data_ptr(), tmp.data_ptr(), M, H, K, 0, st()), iters=8)
+        ms1 = timed(lambda: lib.msq_gemm_deferred_ln(2, 0, A.data_ptr(), W.data_ptr(), bias.data_ptr(), y.data_ptr(), gam.data_ptr(),
+                                                     bet.data_ptr(), stats.data_ptr(), sp, H, 1e-12, y.data_ptr(), yt.data_ptr(),
+                                                     stats_o.data_ptr(), M, H, K, 0, st()), iters=8)
+        byt = M * (K * 2 + H * (4 + 4 + 2))
+        print(json.dumps(dict(kernel="gemm_tc " + name, plain_ms=ms0, layernorm_ms=ln_ms, plain_plus_ln_ms=ms0 + ln_ms, deferred_ms=ms1,
+                              deferred_gbs=byt / ms1 / 1e6, deferred_tflops=2.0 * M * H * K / ms1 / 1e9)))
+        del A, W, tmp
+
+
 def bench_attn():
     for L, masked in ((227, True), (99, False)):
         R, heads = 640, 12
@@ -104,6 +139,6 @@ def bench_decode():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ln", "gemm", "attn", "decode"]
+    which = sys.argv[1:] or ["ln", "gemm", "deferred", "attn", "decode"]
     for w in which:
-        {"ln": bench_ln, "gemm": bench_gemm, "attn": bench_attn, "decode": bench_decode}[w]()
+        {"ln": bench_ln, "gemm": bench_gemm, "deferred": bench_deferred, "attn": bench_attn, "decode": bench_decode}[w]()

@@ -131,6 +131,66 @@ def test_gemm_layernorm_fused(M, N, K, raw32, inplace):
     _close(out2, y.float(), 8e-3, "gemm_ln bf16 copy")
 
 
+@pytest.mark.parametrize("M,H,inter,act", [(1000, 768, 3072, 1), (4540, 768, 3072, 2), (130, 128, 512, 1), (37000, 768, 768, 0)])
+def test_gemm_deferred_layernorm(M, H, inter, act):
+    """The deferred-LayerNorm epilogues chained as in a post-LN layer: (residual GEMM: y = a W^T + b + LN0(y0), bf16
+    copy, row partial sums) -> (folded GEMM: act(LN1(y) W1^T + b1) from the bf16 copy of RAW y).  Checked against float64
+    on the same bf16-rounded operands; the LayerNorms are never materialised on the device."""
+    import ctypes as C
+    from multimodal_sequencing_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + H)
+    eps = 1e-12
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    a = torch.randn(M, inter, generator=g).bfloat16()
+    W0 = (torch.randn(H, inter, generator=g) * 0.03).bfloat16()
+    b0 = torch.randn(H, generator=g) * 0.1
+    y0 = torch.randn(M, H, generator=g) * 1.5 + 0.2           # raw stream entering the layer
+    g0, be0 = torch.rand(H, generator=g) + 0.5, torch.randn(H, generator=g) * 0.1
+    g1, be1 = torch.rand(H, generator=g) + 0.5, torch.randn(H, generator=g) * 0.1
+    W1 = torch.randn(inter, H, generator=g) * 0.03
+    b1 = torch.randn(inter, generator=g) * 0.1
+
+    def partials(y, groups):   # [M, groups, 2] = (sum, sum of squares) over equal column groups (zero-padded to 128s)
+        pad = groups * 128 - y.shape[1]
+        yp = torch.nn.functional.pad(y.double(), (0, pad)).reshape(y.shape[0], groups, 128)
+        return torch.stack([yp.sum(-1), (yp * yp).sum(-1)], -1).float()
+
+    sp = 2 * math.ceil(H / 256)
+    st0 = partials(y0, sp)
+    # ---- reference (float64)
+    ln0 = torch.nn.functional.layer_norm(y0.double(), (H,), g0.double(), be0.double(), eps)
+    y_ref = a.double() @ W0.double().t() + b0.double() + ln0
+    # ---- device: residual GEMM with the pending LayerNorm 0 applied to its residual operand
+    y = y0.cuda().clone()
+    yt = torch.empty(M, H, device="cuda", dtype=torch.bfloat16)
+    st1 = torch.full((M, sp, 2), float("nan"), device="cuda")
+    ad, W0d, b0d, g0d, be0d, st0d = a.cuda(), W0.cuda(), b0.cuda(), g0.cuda(), be0.cuda(), st0.cuda()
+    _lib.check(lib.msq_gemm_deferred_ln(2, 0, ad.data_ptr(), W0d.data_ptr(), b0d.data_ptr(), y.data_ptr(), g0d.data_ptr(), be0d.data_ptr(),
+                                        st0d.data_ptr(), sp, H, eps, y.data_ptr(), yt.data_ptr(), st1.data_ptr(), M, H, inter, 0, st))
+    torch.cuda.synchronize()
+    _close(y, y_ref.float(), 3e-5, "residual GEMM, fp32 stream")
+    assert torch.equal(yt, y.bfloat16()), "bf16 copy is not the rounding of the fp32 stream"
+    _close(st1, partials(y.cpu(), sp), 2e-5, "row partial sums")
+    # ---- folded GEMM: LN1 of the RAW stream inside the epilogue
+    W1f = (g1[None, :] * W1).bfloat16()
+    svec = W1f.float().sum(1)
+    bias1 = b1 + W1 @ be1
+    out = torch.empty(M, inter, device="cuda", dtype=torch.bfloat16)
+    W1d, svd, b1d = W1f.cuda(), svec.cuda(), bias1.cuda()
+    _lib.check(lib.msq_gemm_deferred_ln(1, 1, yt.data_ptr(), W1d.data_ptr(), b1d.data_ptr(), None, svd.data_ptr(), None, st1.data_ptr(),
+                                        sp, H, eps, out.data_ptr(), None, None, M, inter, H, act, st))
+    torch.cuda.synchronize()
+    yd = y.cpu().double()
+    mu, var = yd.mean(-1, keepdim=True), yd.var(-1, unbiased=False, keepdim=True)
+    pre = ((yt.cpu().double() - mu) / torch.sqrt(var + eps)) @ W1f.double().t() + bias1.double()
+    ref = {0: lambda x: x, 1: O.gelu_erf, 2: O.quick_gelu}[act](pre)
+    _close(out, ref.float(), 8e-3, "folded GEMM")
+    # and the folded result is the LayerNorm'd linear up to bf16 operand rounding
+    full = torch.nn.functional.layer_norm(yd, (H,), g1.double(), be1.double(), eps) @ W1.double().t() + b1.double()
+    _close(out, {0: lambda x: x, 1: O.gelu_erf, 2: O.quick_gelu}[act](full).float(), 3e-2, "folded GEMM vs unfused LayerNorm + Linear")
+
+
 @pytest.mark.parametrize("H,eps", [(768, 1e-12), (128, 1e-5), (1024, 1e-6)])
 def test_layernorm(H, eps):
     import ctypes as C
