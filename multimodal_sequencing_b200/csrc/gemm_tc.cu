@@ -152,8 +152,8 @@ template <> __device__ __forceinline__ void epi_store8<bf16>(bf16* p, const floa
 template <typename TO, bool PAIR, int ACT, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_c2, TcEpi ep, int num_m, int num_n,
-               int num_k) {
+               const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_c2,
+               const __grid_constant__ CUtensorMap tma_r, TcEpi ep, int num_m, int num_n, int num_k) {
   using Cfg = TcCfg<PAIR, MODE>;
   static_assert(MODE != 2 || sizeof(TO) == 4, "EPI_RESLN writes the fp32 stream (+ its bf16 copy)");
   constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES;
@@ -178,6 +178,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
     if (Cfg::TMA_STORE) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_c) : "memory");
     if (Cfg::TMA_STORE && MODE == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_c2) : "memory");
+    if (Cfg::TMA_STORE && MODE == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_r) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, TC_EPI_WARPS * (PAIR ? 2 : 1)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -266,6 +267,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const uint32_t stg = staging0 + (warp - 2) * 8192;  // this warp's two staging boxes
     const uint32_t stg2 = staging0 + Cfg::STAGING_F32 + (warp - 2) * 2048;  // MODE 2: bf16 box (32 rows x 32 columns)
     int stg_use = 0;                                       // boxes handed to the TMA so far (parity selects the buffer)
+    // EPI_RESLN on CTA pairs: the residual chunk (32 rows x 32 fp32) is TMA-LOADED into the very staging box the output
+    // chunk is stored from: full 128-byte lines and no registers held across the latency, instead of 16 bytes per row
+    // per load instruction.  One chunk ahead; rk counts this warp's chunks (box rk&1, mbarrier parity (rk>>1)&1).
+    constexpr bool RES_TMA = MODE == 2 && Cfg::TMA_STORE;
+    const uint32_t rbar = bars + 128 + (warp - 2) * 16;   // two 8-byte mbarriers per epilogue warp
+    uint32_t rk = 0;
+    auto issue_res = [&](int t, int ch, uint32_t k) {      // lane 0
+      const int r0 = (t / num_n) * Cfg::TILE_M + (int)rank * TC_BM + q * 32;
+      const int c0 = (t % num_n) * TC_BN + half * 128 + ch * 32;
+      mbar_expect_tx(rbar + 8 * (k & 1), 4096);
+      tma_load_2d(stg + (k & 1) * 4096, &tma_r, c0, r0, rbar + 8 * (k & 1));
+    };
+    if (RES_TMA) {
+      if (lane == 0) {
+        mbar_init(rbar, 1); mbar_init(rbar + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (unit < num_tiles) issue_res(unit, 0, 0);
+      }
+      __syncwarp();
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
     TO* C = reinterpret_cast<TO*>(ep.C);
@@ -297,7 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int i = 0; i < 8; ++i)
           dst[i] = (row_ok && c0 + 4 * i < ep.N) ? __ldg(reinterpret_cast<const float4*>(rp + 4 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
       };
-      if (use_res) fetch_res(0, res);
+      if (use_res && !RES_TMA) fetch_res(0, res);
       {
         const int c = colw + lane * 4;
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -341,7 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int i = 0; i < 8; ++i) res[i] = res_next[i];
         if (ch + 1 < 4) {
           tmem_ld32_nowait(taddr + (ch + 1) * 32, raw_next);
-          if (use_res) fetch_res(ch + 1, res_next);
+          if (use_res && !RES_TMA) fetch_res(ch + 1, res_next);
         }
         const int col0 = colw + ch * 32;
         if (Cfg::TMA_STORE) {
@@ -349,19 +370,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           // (one chunk) or 64 bf16 columns (two chunks).  16-byte piece c of row r sits at r*128 + ((c ^ (r&7))<<4).
           constexpr bool F32 = sizeof(TO) == 4;
           const bool new_box = F32 || (ch & 1) == 0;
-          if (new_box) {
-            // the fp32 box used two chunks ago has been read out; MODE 2 commits the bf16 box of a chunk BEFORE its fp32 box,
-            // so "all but the newest group" also covers the single bf16 box of the previous chunk
+          if (RES_TMA) {
+            if (lane == 0) {
+              // every store issued so far has been read out of shared memory: the other fp32 box may receive the next
+              // residual chunk (of this tile or of this warp's next tile) and the bf16 box may be refilled
+              tma_store_wait_read<0>();
+              if (ch + 1 < 4) issue_res(tile, ch + 1, rk + 1);
+              else if (tile + num_units < num_tiles) issue_res(tile + num_units, 0, rk + 1);
+            }
+            __syncwarp();
+            mbar_wait(rbar + 8 * (rk & 1), (rk >> 1) & 1);   // residual chunk rk has landed in box rk&1
+          } else if (new_box) {
+            // the fp32 box used two chunks ago has been read out
             if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
           }
-          const uint32_t box = stg + (stg_use & 1) * 4096;
+          const uint32_t box = stg + ((RES_TMA ? rk : (uint32_t)stg_use) & 1) * 4096;
           const uint32_t rowp = box + lane * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float v[8];
-            epi_compute8<ACT, MODE>(v, raw + j * 8, bias_s + ch * 32 + j * 8, svec_s + ch * 32 + j * 8, beta_s + ch * 32 + j * 8, ra, rc,
-                                    has_ln, use_res, res[2 * j], res[2 * j + 1]);
+            if (RES_TMA) {
+              const float4 r0 = ld_shared_f4(rowp + (((2 * j) ^ (lane & 7)) << 4)), r1 = ld_shared_f4(rowp + (((2 * j + 1) ^ (lane & 7)) << 4));
+              epi_compute8<ACT, MODE>(v, raw + j * 8, bias_s + ch * 32 + j * 8, svec_s + ch * 32 + j * 8, beta_s + ch * 32 + j * 8, ra, rc,
+                                      has_ln, true, r0, r1);
+            } else {
+              epi_compute8<ACT, MODE>(v, raw + j * 8, bias_s + ch * 32 + j * 8, svec_s + ch * 32 + j * 8, beta_s + ch * 32 + j * 8, ra, rc,
+                                      has_ln, use_res, res[2 * j], res[2 * j + 1]);
+            }
             if (MODE == 2) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) { st_sum += v[i]; st_sq = fmaf(v[i], v[i], st_sq); }
@@ -394,6 +430,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               tma_store_commit();
             }
             ++stg_use;
+            ++rk;
           }
         } else if (row_ok && col0 < ep.N) {
 #pragma unroll
@@ -450,6 +487,8 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
   CUtensorMap mc2 = ma;
   if (Cfg::TMA_STORE) MSQ_TRY(make_map_2d(&mc, g.C, g.M, g.N, g.ldc, 128 / (int)sizeof(TO), 32, sizeof(TO) == 4));
   if (Cfg::TMA_STORE && MODE == 2) MSQ_TRY(make_map_2d(&mc2, g.C2bf, g.M, g.N, g.ldc, 32, 32, false, true));
+  CUtensorMap mr = ma;
+  if (Cfg::TMA_STORE && MODE == 2) MSQ_TRY(make_map_2d(&mr, g.resid, g.M, g.N, g.ldr, 32, 32, true));
   static bool configured = false;
   if (!configured) {
     MSQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TO, PAIR, ACT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -476,10 +515,10 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
     attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    MSQ_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<TO, PAIR, ACT, MODE>, ma, mb, mc, mc2, ep, num_m, num_n, num_k));
+    MSQ_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<TO, PAIR, ACT, MODE>, ma, mb, mc, mc2, mr, ep, num_m, num_n, num_k));
   } else {
     const int grid = (int)min((int64_t)sms, tiles);
-    MSQ_CUDA(launch_k(gemm_tc_kernel<TO, PAIR, ACT, MODE>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM, st, ma, mb, mc, mc2, ep, num_m, num_n, num_k));
+    MSQ_CUDA(launch_k(gemm_tc_kernel<TO, PAIR, ACT, MODE>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM, st, ma, mb, mc, mc2, mr, ep, num_m, num_n, num_k));
   }
   MSQ_LAUNCH_CHECK();
   profile_mark(st, true, 2.0 * (double)g.M * (double)g.N * (double)g.K);
