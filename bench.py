@@ -255,7 +255,7 @@ def main():
 
     pk = peaks()
     traffic = None  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
-    tp = os.path.join(ROOT, "profiles", "r1_gemm_tc_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r1h_gemm_tc_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("traffic_bytes_per_launch")
     total = world * B * args.steps
@@ -270,11 +270,11 @@ def main():
                     "api": "OrderingEngine.order_host -> msq_order_manuals_host (pinned host buffers)"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "msq::gemm_tc_kernel (tcgen05 bf16 GEMM, all encoder linears)",
+            "roofline": {"bound": "tensor", "kernel": "msq::gemm_tc_kernel (tcgen05 bf16 GEMM, all encoder linears; LayerNorms ride in its epilogues)",
                          "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                          "frac": (ach / pk["tf_sust"]) if ach else None, "traffic": traffic,
                          "traffic_note": "mean dram read+write bytes per launch over 8 BERT-layer GEMM launches at 640 pair rows, "
-                                         "ncu --set full (profiles/r1_gemm_tc_traffic.json); algorithmic bytes beside it there",
+                                         "ncu --set full (profiles/r1h_gemm_tc_traffic.json); algorithmic bytes beside it there",
                          "peak_source": pk["src"] + ", bf16_tflops_sustained (kernel timed inside a long step)",
                          "launches_timed": pl.value, "kernel_ms_per_step": pm.value / args.steps,
                          "kernel_share_of_step": (pm.value / args.steps) / (ms_total / args.steps),

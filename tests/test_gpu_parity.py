@@ -429,6 +429,55 @@ def test_full_size_vs_oracle(mm):
         torch.cuda.empty_cache()
 
 
+def test_full_size_long_manual_vs_oracle():
+    """BASELINE configs[4] shape on the full-size multimodal model: one 10-step manual (90 ordered pairs), beam 16."""
+    cfg = _full_cfg(True)
+    sd = synth.full_state_dict(cfg, cfg["vit"], seed=0)
+    N, W = 10, 16
+    ids, labels, images = O.synthetic_manuals(1, N, 64, image_px=224, seed=9)
+    torch.set_num_threads(os.cpu_count() or 1)
+    ocfg = dict(num_hidden_layers=12, num_attention_heads=12, vit=cfg["vit"], rn=None)
+    oenc = O.encode(sd, ocfg, O.prepare_inputs(ids, labels, N, images))
+    tr_o = []
+    operm = O.beam_search(sd, oenc, N, W, 0, tr_o)
+    eng = _engine(sd, cfg, True)
+    enc = eng.encode(eng.prepare(ids, labels, N, images))
+    for k in ENC:
+        _close(enc[k].reshape(oenc[k].shape), oenc[k], 1e-4, k)
+    perm, tr = eng.beam_search(enc, N, W, trace=True)
+    assert perm[0].tolist() == operm
+    for t, s_ in enumerate(tr_o):   # bit-exact beam indices at every step
+        k = s_["beam_ix"].numel()
+        assert torch.equal(tr["ix"][0, t, :k].cpu(), (s_["beam_ix"] * N + s_["tok_ix"]).int()), "step %d" % t
+    assert eng.order(ids, labels, N, W, images) == [operm]
+    del eng
+    torch.cuda.empty_cache()
+    eng = _engine(sd, cfg, False)   # bf16 tensor-core path: same decode given the same encoder outputs
+    assert eng.beam_search(oenc, N, W).cpu().tolist() == [operm]
+    p16 = eng.order(ids, labels, N, W, images)
+    assert sorted(p16[0]) == list(range(N))
+
+
+def test_config2_batch256_beam8_properties():
+    """BASELINE configs[2] shape (batch 256, beam 8) on one GPU: every output is a permutation, the batch result equals
+    the concatenation of its quarters (no cross-manual leakage across micro-batches), reruns are bit-identical, and the
+    host-buffer entry point agrees with the device-resident one."""
+    cfg = _full_cfg(True)
+    sd = synth.full_state_dict(cfg, cfg["vit"], seed=0)
+    eng = _engine(sd, cfg, precise=False)
+    N, W, B = 5, 8, 256
+    ids, labels, images = O.synthetic_manuals(B, N, 64, image_px=224, seed=11)
+    full = eng.order(ids, labels, N, W, images)
+    assert len(full) == B and all(sorted(p) == list(range(N)) for p in full)
+    assert eng.order(ids, labels, N, W, images) == full
+    for q in range(4):
+        sl = slice(64 * q, 64 * (q + 1))
+        assert eng.order(ids[sl], labels[sl], N, W, images[sl]) == full[sl]
+    assert eng.order_host(eng.prepare(ids, labels, N, images), W).tolist() == full
+    acc, pmr, tau = O.cal_result(labels.tolist(), full)
+    assert 0.0 <= acc <= 1.0 and -1.0 <= tau <= 1.0
+
+
 def test_full_size_batch_invariance_and_chunking():
     """Size-independent properties at the benchmark configuration: every output is a permutation;
     results do not depend on batch composition or on the micro-batch (chunk) boundaries; reruns are
