@@ -455,9 +455,9 @@ extern "C" int msq_model_create(const msq_config* cfg, msq_model** out) {
   MSQ_REQUIRE(cfg->heads * 64 == cfg->hidden, "head dim must be 64 (hidden=%d heads=%d)", cfg->hidden, cfg->heads);
   MSQ_REQUIRE(cfg->inter % 16 == 0 && cfg->layers >= 0, "bad inter/layers");
   if (cfg->rn_width) {
-    MSQ_REQUIRE(cfg->rn_width % 8 == 0 && cfg->rn_embed % 32 == 0 && cfg->vit_width == 2 * cfg->rn_embed && cfg->vit_layers == 0 &&
+    MSQ_REQUIRE(cfg->rn_width % 16 == 0 && cfg->rn_embed % 32 == 0 && cfg->vit_width == 2 * cfg->rn_embed && cfg->vit_layers == 0 &&
                     cfg->vit_patch == 32 && cfg->vit_res % 32 == 0,
-                "ResNet tower: need rn_width %% 8 == 0, vit_width == 2*rn_embed, vit_layers == 0, vit_patch == 32");
+                "ResNet tower: need rn_width %% 16 == 0, vit_width == 2*rn_embed, vit_layers == 0, vit_patch == 32");
     for (int i = 0; i < 4; ++i) MSQ_REQUIRE(cfg->rn_blocks[i] >= 1, "rn_blocks[%d]=%d", i, cfg->rn_blocks[i]);
   } else if (cfg->vit_width) {
     MSQ_REQUIRE(cfg->vit_width % 128 == 0 && cfg->vit_width <= 1024, "vit_width=%d unsupported", cfg->vit_width);
@@ -898,7 +898,7 @@ static int run_vit(msq_model* m, const int32_t* img_index, int64_t R, VitBufs& b
 }
 
 // ---- CLIP ModifiedResNet tower ---------------------------------------------------------------------
-constexpr int64_t RN_IMG_CHUNK = 64;  // images per trunk pass (bounds the im2col scratch: 8 MB / image in bf16 at width 64)
+constexpr int64_t RN_IMG_CHUNK = 256;  // images per trunk pass (bounds the im2col scratch: 8 MB / image in bf16 at width 64)
 
 struct RnDims { size_t a = 0, t = 0, f = 0; };  // per-image element counts: im2col rows, operand-type maps, fp32 maps
 static RnDims rn_dims(const msq_config& c) {

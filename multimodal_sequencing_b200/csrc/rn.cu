@@ -107,32 +107,47 @@ int rn_im2col_stem(const float* img, int64_t n, int S, int Kp, T* out, cudaStrea
 template int rn_im2col_stem<float>(const float*, int64_t, int, int, float*, cudaStream_t);
 template int rn_im2col_stem<bf16>(const float*, int64_t, int, int, bf16*, cudaStream_t);
 
-// ---- 3x3 / stride 1 / pad 1 over NHWC -> rows [n*H*W, Kp], col = (ky*3+kx)*C + c  (4 channels per thread)
+// ---- 3x3 / stride 1 / pad 1 over NHWC -> rows [n*H*W, Kp], col = (ky*3+kx)*C + c.  16 bytes per thread (8 bf16 or 4 fp32
+// channels), 32-bit index arithmetic (one launch covers at most RN_IMG_CHUNK images: < 2^31 vectors).
+template <typename T> struct VecIO;
+template <> struct VecIO<float> {
+  static constexpr int N = 4;
+  typedef float4 V;
+  static __device__ __forceinline__ V zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+};
+template <> struct VecIO<bf16> {
+  static constexpr int N = 8;
+  typedef uint4 V;
+  static __device__ __forceinline__ V zero() { return make_uint4(0u, 0u, 0u, 0u); }
+};
 template <typename T>
-__global__ void __launch_bounds__(256) rn_im2col3_kernel(const T* __restrict__ x, int64_t n, int H, int W, int C, int Kp,
-                                                         T* __restrict__ out) {
+__global__ void __launch_bounds__(256) rn_im2col3_kernel(const T* __restrict__ x, uint32_t n, uint32_t H, uint32_t W, uint32_t C,
+                                                         uint32_t Kp, T* __restrict__ out) {
   pdl_sync();
-  const int K4 = Kp / 4;
-  const int64_t total = n * H * W * (int64_t)K4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int col = (int)(i % K4) * 4;
-    const int64_t row = i / K4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (col < 9 * C) {
-      const int c = col % C, kk = col / C, ky = kk / 3, kx = kk % 3;
-      const int64_t im = row / (H * W);
-      const int oy = (int)(row % (H * W)) / W, ox = (int)(row % (H * W)) % W;
-      const int y = oy - 1 + ky, xx = ox - 1 + kx;
-      if (y >= 0 && y < H && xx >= 0 && xx < W) v = V4<T>::load(x + ((im * H + y) * W + xx) * (int64_t)C + c);
+  typedef typename VecIO<T>::V V;
+  constexpr uint32_t VN = VecIO<T>::N;
+  const uint32_t KV = Kp / VN, CV = C / VN, HW = H * W;
+  const uint32_t total = n * HW * KV;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t row = i / KV, cv = i - row * KV;
+    V v = VecIO<T>::zero();
+    if (cv < 9 * CV) {
+      const uint32_t kk = cv / CV, c = (cv - kk * CV) * VN, ky = kk / 3, kx = kk - ky * 3;
+      const uint32_t im = row / HW, pix = row - im * HW, oy = pix / W, ox = pix - oy * W;
+      const uint32_t y = oy + ky - 1, xx = ox + kx - 1;   // unsigned wrap-around makes -1 fail the range test
+      if (y < H && xx < W) v = *reinterpret_cast<const V*>(x + ((size_t)(im * H + y) * W + xx) * C + c);
     }
-    V4<T>::store(out + row * Kp + col, v);
+    *reinterpret_cast<V*>(out + (size_t)row * Kp + (size_t)cv * VN) = v;
   }
 }
 template <typename T>
 int rn_im2col3(const T* x, int64_t n, int H, int W, int C, int Kp, T* out, cudaStream_t st) {
-  MSQ_REQUIRE(C % 4 == 0 && Kp % 4 == 0 && Kp >= 9 * C, "rn_im2col3: C=%d Kp=%d", C, Kp);
+  constexpr int VN = VecIO<T>::N;
+  MSQ_REQUIRE(C % VN == 0 && Kp % VN == 0 && Kp >= 9 * C, "rn_im2col3: C=%d Kp=%d", C, Kp);
+  MSQ_REQUIRE(n * H * W * (int64_t)(Kp / VN) < ((int64_t)1 << 31), "rn_im2col3: launch too large");
   if (n == 0) return MSQ_OK;
-  MSQ_CUDA(launch_k(rn_im2col3_kernel<T>, grid_for(n * H * W * (int64_t)(Kp / 4)), dim3(256), 0, st, x, n, H, W, C, Kp, out));
+  MSQ_CUDA(launch_k(rn_im2col3_kernel<T>, grid_for(n * H * W * (int64_t)(Kp / VN)), dim3(256), 0, st, x, (uint32_t)n, (uint32_t)H,
+                    (uint32_t)W, (uint32_t)C, (uint32_t)Kp, out));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }

@@ -373,7 +373,7 @@ def test_mm_rn_tiny_golden(golden_dir, precise):
 @pytest.mark.parametrize("precise", [True, False])
 def test_resnet_tower_width64_vs_oracle(precise):
     """ModifiedResNet at RN50's channel widths (64..2048, one block per stage) so that every convolution GEMM takes the
-    shape class it has in the real tower (tcgen05 for K >= 64 in bf16 mode); 70 unique images span two trunk chunks."""
+    shape class it has in the real tower (tcgen05 for K >= 64 in bf16 mode)."""
     rn = dict(embed_dim=256, image_resolution=224, vision_layers=(1, 1, 1, 1), vision_width=64)
     pre = "bert.encoder.visual_model.visual."
     sd = synth.rn_weights(pre, rn, 5)
