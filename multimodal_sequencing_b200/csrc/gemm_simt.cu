@@ -72,7 +72,7 @@ template <typename TA, typename TO, int TILE>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A, const TA* __restrict__ W,
                                                         const float* __restrict__ bias, const float* __restrict__ resid,
                                                         TO* __restrict__ C, float* __restrict__ C2, int64_t M, int N, int K,
-                                                        int lda, int ldw, int ldc, int ldr, int act) {
+                                                        int lda, int ldw, int ldc, int ldr, int act, float* __restrict__ partial) {
   pdl_sync();
   constexpr int SG_BM = TILE, SG_BN = TILE, SG_LD = TILE + 4, TM = TILE / 16, HM = TM / 2;
   constexpr int KV = TILE == 128 ? 8 : 4;  // k elements each thread stages per tile row
@@ -83,8 +83,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
   const int n0 = blockIdx.x * SG_BN;
   const int lrow = tid % TILE, lk = (tid / TILE) * KV;
   const bool a_ok = (m0 + lrow) < M, b_ok = (n0 + lrow) < N;
-  const TA* ap = A + (m0 + lrow) * (int64_t)lda + lk;
-  const TA* bp = W + (int64_t)(n0 + lrow) * ldw + lk;
+  // split-K (partial != nullptr): block z accumulates k slabs [z*per, min(nk_all, (z+1)*per)) and stores the raw sums
+  const int nk_all = K / SG_BK, per = (nk_all + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int kbeg = (int)blockIdx.z * per, nk = max(0, min(per, nk_all - kbeg));
+  const TA* ap = A + (m0 + lrow) * (int64_t)lda + lk + (int64_t)kbeg * SG_BK;
+  const TA* bp = W + (int64_t)(n0 + lrow) * ldw + lk + (int64_t)kbeg * SG_BK;
   const int ty = tid >> 4, tx = tid & 15;
 
   float acc[TM][TM];
@@ -94,13 +97,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
     for (int j = 0; j < TM; ++j) acc[i][j] = 0.f;
 
   float ra[8], rb[8];
-  LoadK<TA, KV>::load(ap, a_ok, ra);
-  LoadK<TA, KV>::load(bp, b_ok, rb);
+  LoadK<TA, KV>::load(ap, a_ok && nk > 0, ra);
+  LoadK<TA, KV>::load(bp, b_ok && nk > 0, rb);
 #pragma unroll
   for (int i = 0; i < KV; ++i) { As[0][lk + i][lrow] = ra[i]; Bs[0][lk + i][lrow] = rb[i]; }
   __syncthreads();
 
-  const int nk = K / SG_BK;
   for (int kt = 0; kt < nk; ++kt) {
     const int cur = kt & 1;
     if (kt + 1 < nk) {
@@ -145,6 +147,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
       const int col = n0 + jh * 64 + tx * 4;
       if (col >= N) continue;  // N % 4 == 0
       float4 v = make_float4(acc[i][jh * 4 + 0], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
+      if (partial) {
+        *reinterpret_cast<float4*>(partial + ((int64_t)blockIdx.z * M + row) * N + col) = v;
+        continue;
+      }
       if (bias) {
         const float4 b = *reinterpret_cast<const float4*>(bias + col);
         v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
@@ -160,6 +166,49 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
   }
 }
 
+// second pass of the split-K path: C = act(sum_z partial[z] + bias) + resid, splits added in index order (deterministic)
+template <typename TO>
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int S, int64_t M, int N,
+                                                            const float* __restrict__ bias, const float* __restrict__ resid, int ldr,
+                                                            int act, TO* __restrict__ C, float* __restrict__ C2, int ldc) {
+  pdl_sync();
+  const int64_t total4 = M * (N / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / (N / 4);
+    const int col = (int)(i % (N / 4)) * 4;
+    float4 v = *reinterpret_cast<const float4*>(partial + row * N + col);
+    for (int z = 1; z < S; ++z) {
+      const float4 p = *reinterpret_cast<const float4*>(partial + ((int64_t)z * M + row) * N + col);
+      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+    if (bias) {
+      const float4 b = *reinterpret_cast<const float4*>(bias + col);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
+    if (resid) {
+      const float4 r = *reinterpret_cast<const float4*>(resid + row * ldr + col);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    store4<TO>(C + row * ldc + col, v);
+    if (C2) *reinterpret_cast<float4*>(C2 + row * ldc + col) = v;
+  }
+}
+
+// grow-only scratch for split-K partial sums (per host thread; reallocation synchronises the device)
+static int splitk_scratch(size_t floats, float** out) {
+  static thread_local float* buf = nullptr;
+  static thread_local size_t cap = 0;
+  if (floats > cap) {
+    if (buf) MSQ_CUDA(cudaFree(buf));
+    buf = nullptr; cap = 0;
+    MSQ_CUDA(cudaMalloc(&buf, floats * sizeof(float)));
+    cap = floats;
+  }
+  *out = buf;
+  return MSQ_OK;
+}
+
 template <typename TA, typename TO>
 int gemm_simt(const GemmArgs& g, cudaStream_t st) {
   MSQ_REQUIRE(g.K % SG_BK == 0 && g.N % 4 == 0 && g.lda % 8 == 0 && g.ldw % 8 == 0 && g.ldc % 4 == 0,
@@ -168,10 +217,25 @@ int gemm_simt(const GemmArgs& g, cudaStream_t st) {
   // small problems: 64x64 tiles give 4x the CTAs (fills the 148 SMs when M is a few hundred rows)
   if ((int64_t)ceil_div(g.N, 128) * ceil_div(g.M, 128) < 2 * 148) {
     dim3 grid(ceil_div(g.N, 64), ceil_div(g.M, 64));
-    MSQ_CUDA(launch_k(gemm_simt_kernel<TA, TO, 64>, dim3(grid), dim3(256), 0, st, (const TA*)g.A, (const TA*)g.W, g.bias, g.resid, (TO*)g.C, g.C2, g.M, g.N, g.K, g.lda, g.ldw, g.ldc, g.ldr, g.act));
+    // The fp32 heads (paragraph encoder, decoder pre-projections: M = B*N .. B*N^2 rows against 7-10 MB of weights) are a
+    // few dozen 64 x 64 tiles, each walking all of K on its own SM.  Split K (by a rule that depends on K only, so a
+    // row's summation order does not change with the batch) and add the partial sums in a second, ordered pass.
+    const int S = sizeof(TA) == 4 ? min(16, g.K / 256) : 1;
+    if (S > 1) {
+      float* part;
+      MSQ_TRY(splitk_scratch((size_t)S * g.M * g.N, &part));
+      grid.z = S;
+      MSQ_CUDA(launch_k(gemm_simt_kernel<TA, TO, 64>, dim3(grid), dim3(256), 0, st, (const TA*)g.A, (const TA*)g.W, g.bias, g.resid, (TO*)g.C, g.C2, g.M, g.N, g.K, g.lda, g.ldw, g.ldc, g.ldr, g.act, part));
+      MSQ_LAUNCH_CHECK();
+      const int64_t total4 = g.M * (g.N / 4);
+      MSQ_CUDA(launch_k(splitk_reduce_kernel<TO>, dim3((unsigned)min((int64_t)148 * 8, (total4 + 255) / 256)), dim3(256), 0, st, (const float*)part, S, g.M, g.N, g.bias, g.resid, g.ldr, g.act, (TO*)g.C, g.C2, g.ldc));
+      MSQ_LAUNCH_CHECK();
+      return MSQ_OK;
+    }
+    MSQ_CUDA(launch_k(gemm_simt_kernel<TA, TO, 64>, dim3(grid), dim3(256), 0, st, (const TA*)g.A, (const TA*)g.W, g.bias, g.resid, (TO*)g.C, g.C2, g.M, g.N, g.K, g.lda, g.ldw, g.ldc, g.ldr, g.act, (float*)nullptr));
   } else {
     dim3 grid(ceil_div(g.N, 128), ceil_div(g.M, 128));
-    MSQ_CUDA(launch_k(gemm_simt_kernel<TA, TO, 128>, dim3(grid), dim3(256), 0, st, (const TA*)g.A, (const TA*)g.W, g.bias, g.resid, (TO*)g.C, g.C2, g.M, g.N, g.K, g.lda, g.ldw, g.ldc, g.ldr, g.act));
+    MSQ_CUDA(launch_k(gemm_simt_kernel<TA, TO, 128>, dim3(grid), dim3(256), 0, st, (const TA*)g.A, (const TA*)g.W, g.bias, g.resid, (TO*)g.C, g.C2, g.M, g.N, g.K, g.lda, g.ldw, g.ldc, g.ldr, g.act, (float*)nullptr));
   }
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
