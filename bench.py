@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="manuals per step per GPU")
     ap.add_argument("--precise", action="store_true", help="fp32 FFMA parity mode instead of bf16 tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--text", default="bert-base", choices=["bert-base", "roberta-large"],
+                    help="joint encoder sizing: BERT-base (BASELINE configs, the headline) or the roberta-large config the "
+                         "reference's scripts pass (H=1024, 24 layers); secondary line")
     ap.add_argument("--backbone", default="vit", choices=["vit", "rn50"],
                     help="visual tower: ViT-B/32 (BASELINE configs[1], the headline) or the reference's wired default RN50")
     return ap.parse_args()
@@ -180,6 +183,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = dict(synth.BERT_BASE)
+    if args.text == "roberta-large":   # sizing only: ids stay BERT-style ([CLS]=101 ...), so keep two token types
+        cfg = dict(synth.ROBERTA_LARGE, type_vocab_size=2)
+        args.no_cpu_baseline = True
     vit, rn = _towers(args.backbone)
     cfg.update(vit=vit, rn=rn, para_ff=3072)
     sd = synth.full_state_dict(cfg, vit, seed=0, rn=rn)
@@ -265,7 +271,7 @@ def main():
     line = {"metric": "5-step manuals ordered/sec (beam=4)", "value": value, "unit": "manuals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precise else "bf16", "data": "synthetic",
-            "config": config_dict(B, world, args.backbone), "impl": "ours",
+            "config": dict(config_dict(B, world, args.backbone), text_encoder=args.text), "impl": "ours",
             "e2e": {"value": e2e, "unit": "manuals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "OrderingEngine.order_host -> msq_order_manuals_host (pinned host buffers)"},
             "gpu_launches": launches,
@@ -278,7 +284,8 @@ def main():
                          "peak_source": pk["src"] + ", bf16_tflops_sustained (kernel timed inside a long step)",
                          "launches_timed": pl.value, "kernel_ms_per_step": pm.value / args.steps,
                          "kernel_share_of_step": (pm.value / args.steps) / (ms_total / args.steps),
-                         "whole_step_tflops_per_gpu": FLOP_PER_MANUAL * B * args.steps / (ms_total / 1e3) / 1e12},
+                         "whole_step_tflops_per_gpu": (FLOP_PER_MANUAL * B * args.steps / (ms_total / 1e3) / 1e12
+                                                       if (args.text, args.backbone) == ("bert-base", "vit") else None)},
             }
     if not args.no_cpu_baseline and world == 1:
         times, cores = cpu_reference_run(3, budget_s=25.0, backbone=args.backbone)

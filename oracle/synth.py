@@ -78,7 +78,7 @@ def berson_head_weights(H, ff=3072, para_layers=2, seed=3):
     return sd
 
 
-def bert_weights(pre, H, layers, inter, vocab, max_pos, seed, lxrt=False):
+def bert_weights(pre, H, layers, inter, vocab, max_pos, seed, lxrt=False, type_vocab=2):
     """BERT embeddings + layer stack under prefix `pre` (keys of Appendix B)."""
     g = _g(seed)
     sd = {}
@@ -87,7 +87,7 @@ def bert_weights(pre, H, layers, inter, vocab, max_pos, seed, lxrt=False):
     e = pre + "embeddings."
     sd[e + "word_embeddings.weight"] = _normal(g, vocab, H)
     sd[e + "position_embeddings.weight"] = _normal(g, max_pos, H)
-    sd[e + "token_type_embeddings.weight"] = _normal(g, 2, H)
+    sd[e + "token_type_embeddings.weight"] = _normal(g, type_vocab, H)
     ln(e + "LayerNorm")
     for i in range(layers):
         l = pre + "encoder.layer.%d." % i
@@ -192,6 +192,9 @@ def rn_lxrt_extras(pre, rn, H, seed):
 RN50 = dict(embed_dim=1024, image_resolution=224, vision_layers=(3, 4, 6, 3), vision_width=64)
 BERT_BASE = dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
                  vocab_size=30522, max_position_embeddings=512)
+# scripts/wikihow_finetune.sh: --config_name roberta-large (the LXRT embeddings / layers are built from this config)
+ROBERTA_LARGE = dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096,
+                     vocab_size=50265, max_position_embeddings=514, type_vocab_size=1)
 VIT_B32 = dict(embed_dim=512, image_resolution=224, vision_layers=12, vision_width=768, vision_patch_size=32)
 
 
@@ -201,7 +204,8 @@ def full_state_dict(cfg=None, vit=None, seed=0, ff=3072, rn=None):
     H = cfg["hidden_size"]
     sd = berson_head_weights(H, ff=ff, seed=seed + 3)
     sd.update(bert_weights("bert.", H, cfg["num_hidden_layers"], cfg["intermediate_size"], cfg["vocab_size"],
-                           cfg["max_position_embeddings"], seed + 11, lxrt=vit is not None or rn is not None))
+                           cfg["max_position_embeddings"], seed + 11, lxrt=vit is not None or rn is not None,
+                           type_vocab=cfg.get("type_vocab_size", 2)))
     if rn is not None:
         sd.update(rn_weights("bert.encoder.visual_model.visual.", rn, seed + 23))
         sd.update(rn_lxrt_extras("bert.", rn, H, seed + 17))

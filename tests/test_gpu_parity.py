@@ -458,6 +458,44 @@ def test_full_size_long_manual_vs_oracle():
     assert sorted(p16[0]) == list(range(N))
 
 
+def test_wired_production_config_roberta_large_rn50_vs_oracle():
+    """The configuration the reference's own scripts run (scripts/wikihow_finetune.sh): LXRT built from the
+    roberta-large config (H=1024, 24 layers, 16 heads, type_vocab 1, <s>=0 </s>=2 <pad>=1 ids -> all-zero token types),
+    CLIP RN50 tower, 60 tokens per step."""
+    cfg = dict(synth.ROBERTA_LARGE)
+    cfg.update(vit=None, rn=dict(synth.RN50), para_ff=3072)
+    sd = synth.full_state_dict(cfg, None, seed=0, rn=cfg["rn"])
+    N, W, B = 5, 4, 1
+    g = torch.Generator().manual_seed(21)
+    body = torch.randint(1000, 50265, (B, N, 58), generator=g)
+    ids = torch.cat([torch.zeros(B, N, 1, dtype=torch.long), body, torch.full((B, N, 1), 2)], -1).reshape(B, N * 60)
+    labels = torch.stack([torch.randperm(N, generator=g) for _ in range(B)])
+    images = torch.randn(B, N, 3, 224, 224, generator=g)
+    torch.set_num_threads(os.cpu_count() or 1)
+    ocfg = dict(num_hidden_layers=24, num_attention_heads=16, vit=None, rn=cfg["rn"])
+    inp = O.prepare_inputs(ids, labels, N, images, cls_id=0, sep_id=2, pad_id=1)
+    assert int(inp["token_type_ids"].sum()) == 0
+    oenc = O.encode(sd, ocfg, inp)
+    operm = [O.beam_search(sd, oenc, N, W, 0)]
+    for precise in (True, False):
+        eng = _engine(sd, cfg, precise)
+        pb = eng.prepare(ids, labels, N, images, cls_id=0, sep_id=2, pad_id=1)
+        for k in ("input_ids", "token_type_ids", "attention_mask", "sep_positions"):
+            assert torch.equal(getattr(pb, k).reshape(inp[k].shape), inp[k]), k
+        enc = eng.encode(pb)
+        errs = {k: _close(enc[k].reshape(oenc[k].shape), oenc[k], (2e-4 if precise else 8e-2), k) for k in ENC}
+        print("roberta-large + RN50 %s max-abs errors: %s" % ("fp32" if precise else "bf16", {k: "%.2e" % v for k, v in errs.items()}))
+        assert eng.beam_search(oenc, N, W).cpu().tolist() == operm
+        perm = eng.order(ids, labels, N, W, images, cls_id=0, sep_id=2, pad_id=1)
+        if precise:
+            assert perm == operm
+        else:
+            assert sorted(perm[0]) == list(range(N))
+            print("bf16 end-to-end permutation equals oracle: %s" % (perm == operm))
+        del eng
+        torch.cuda.empty_cache()
+
+
 def test_config2_batch256_beam8_properties():
     """BASELINE configs[2] shape (batch 256, beam 8) on one GPU: every output is a permutation, the batch result equals
     the concatenation of its quarters (no cross-manual leakage across micro-batches), reruns are bit-identical, and the
