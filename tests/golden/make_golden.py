@@ -237,6 +237,108 @@ def gen_topo(ns, mm):
                 classifier={k: v.clone() for k, v in m.state_dict().items() if k.startswith("classifier.")})
 
 
+class TopoStubTokenizer:
+    """Stands in for the HF tokenizer inside topological_inference: a "text" is a string of space-separated token ids;
+    <s>=0 ... </s>=2, <pad>=1 (the function hard-codes the RoBERTa pad id, trainers/eval.py:466)."""
+
+    def __call__(self, texts, max_length=None, padding=None, truncation=None, **kw):
+        rows = []
+        for t in texts:
+            ids = ([0] + [int(x) for x in t.split()])[:max_length - 1] + [2]
+            rows.append(ids + [1] * (max_length - len(ids)))
+        return {"input_ids": rows}
+
+
+def gen_topo_inference(ns, mm, topo):
+    """trainers/eval.py::topological_inference (425-529) run on the REAL reference code: the function (and
+    debatch_stories) are compiled from the reference file's own source, without importing the module (its imports need
+    packages this image lacks), against the reference LXRTModel in classifier mode and the reference Graph."""
+    import ast
+    import contextlib
+    import io
+    import types
+    import numpy as np
+    from trainers.topological_sort import Graph
+    src = open(os.path.join(rh.REF if hasattr(rh, "REF") else "/root/reference", "trainers", "eval.py")).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("topological_inference", "debatch_stories")]
+    glb = dict(np=np, torch=torch, Graph=Graph)
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "reference:trainers/eval.py", "exec"), glb)
+    torch.manual_seed(123)
+    ns.fake_clip._vit_cfg = dict(TINY_VIT)
+    ns.param.VISUAL_CONFIG.set_visual_dims(TINY_VIT["vision_width"], 4)
+    ns.param.VISUAL_CONFIG.clip_model_name = "ViT-B/32"
+    cfg = ns.lxrt.BertConfig(**TINY)
+    cfg.classifier_dropout = None
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ns.lxrt.LXRTModel(cfg, multimodal_text_part=False, multimodal_img_part=False, cls_id=101, sep_id=102,
+                              max_story_length=5, clip_model_name="ViT-B/32", num_labels=2)
+    m.encoder.skip_last_layer = True
+    inner = {k[len("bert."):]: v for k, v in mm["sd"].items() if k.startswith("bert.")}
+    inner.update(topo["classifier"])
+    assert not m.load_state_dict(inner, strict=False).unexpected_keys
+    m.eval()
+    N, B = 5, 2
+    g = torch.Generator().manual_seed(77)
+    # seqs[j][b] = text of step j of story b (the DataLoader's collated layout, debatch_stories 1088-1097)
+    seqs = [[" ".join(str(int(t)) for t in torch.randint(10, 1000, (int(torch.randint(4, 12, (1,), generator=g)),), generator=g))
+             for _ in range(B)] for _ in range(N)]
+    images = torch.randn(B, N, 3, 224, 224, generator=g)
+    args = types.SimpleNamespace(multimodal=True, use_multimodal_model=False, use_cached=False, per_seq_max_length=16,
+                                 max_seq_length=40, device="cpu", multimodal_text_part=False,
+                                 include_num_img_regional_features=None, replace_token_type_embeddings=True,
+                                 multimodal_model_type="clip")
+    logits = []
+    fwd = m.forward
+
+    def spy(*a, **k):
+        out = fwd(*a, **k)
+        logits.append(out[0].detach().clone())
+        return out
+
+    m.forward = spy
+    glb["topological_inference"](args, m, seqs, TopoStubTokenizer(), images=images)
+    # a random-init classifier votes "ordered" for every pair; centre its decision boundary on the median margin so that
+    # the fixture exercises both edge directions (and a cyclic tournament or two)
+    d = torch.cat(logits)
+    with torch.no_grad():
+        ds = torch.sort(d[:, 1] - d[:, 0]).values
+        m.classifier.out_proj.bias[0] += 0.5 * (ds[len(ds) // 2 - 1] + ds[len(ds) // 2])   # midpoint: no zero margins
+    del logits[:]
+    preds, loss = glb["topological_inference"](args, m, seqs, TopoStubTokenizer(), images=images)
+    return dict(seqs=seqs, image_seed=77, image_checksum=float(images.double().sum()), preds=preds, loss=float(loss),
+                logits=torch.cat(logits), args=vars(args), N=N, B=B,
+                classifier={k: v.clone() for k, v in m.state_dict().items() if k.startswith("classifier.")})
+
+
+def gen_graph_cases():
+    """trainers/topological_sort.py::Graph on random tournaments (cycles included), with and without assert_head."""
+    import json
+    import random
+    from trainers.topological_sort import Graph
+    rnd = random.Random(5)
+    cases = []
+    for t in range(60):
+        n = rnd.randint(2, 10)
+        edges = []
+        for i in range(n):
+            for j in range(n):
+                if i < j:
+                    edges.append((i, j) if rnd.random() < 0.5 else (j, i))
+        head = rnd.randrange(n) if t % 3 == 0 else None
+        g = Graph(n)
+        for u, v in edges:
+            g.addEdge(u, v)
+        try:
+            order = g.topologicalSort(assert_head=head) if head is not None else g.topologicalSort()
+        except AssertionError:
+            order = "assert"
+        cases.append(dict(n=n, edges=edges, head=head, order=order))
+    with open(os.path.join(HERE, "graph_cases.json"), "w") as f:
+        json.dump(cases, f)
+    return cases
+
+
 def gen_pointer_p1(ns):
     """models/pointer_module.py::PointerOutput, p1 variant (dead code in the reference, SURVEY §0.4 / §3.5):
     LSTMPointerModule greedy decoding + CE loss on random hidden states."""
@@ -269,6 +371,15 @@ def gen_pointer_p1(ns):
 
 def main():
     ns = rh.load()
+    if "--only-graph" in sys.argv:
+        print(len(gen_graph_cases()), "graph cases")
+        return
+    if "--only-topo-inference" in sys.argv:
+        mm = torch.load(os.path.join(HERE, "mm_tiny.pt"), weights_only=False)
+        topo = torch.load(os.path.join(HERE, "topo_tiny.pt"), weights_only=False)
+        torch.save(gen_topo_inference(ns, mm, topo), os.path.join(HERE, "topo_inference_tiny.pt"))
+        print("topo_inference_tiny.pt", os.path.getsize(os.path.join(HERE, "topo_inference_tiny.pt")) // 1024, "KiB")
+        return
     if "--only-rn" in sys.argv:   # regenerate just the RN fixture (each generator seeds itself)
         torch.save(gen_mm_rn(ns), os.path.join(HERE, "mm_rn_tiny.pt"))
         print("mm_rn_tiny.pt", os.path.getsize(os.path.join(HERE, "mm_rn_tiny.pt")) // 1024, "KiB")
@@ -276,7 +387,11 @@ def main():
     torch.save(gen_text(ns), os.path.join(HERE, "text_tiny.pt"))
     mm = gen_mm(ns)
     torch.save(mm, os.path.join(HERE, "mm_tiny.pt"))
-    torch.save(gen_topo(ns, mm), os.path.join(HERE, "topo_tiny.pt"))
+    topo = gen_topo(ns, mm)
+    torch.save(topo, os.path.join(HERE, "topo_tiny.pt"))
+    torch.save(gen_topo_inference(ns, mm, topo), os.path.join(HERE, "topo_inference_tiny.pt"))
+    gen_graph_cases()
+    gen_graph_cases()
     torch.save(gen_mm_rn(ns), os.path.join(HERE, "mm_rn_tiny.pt"))
     torch.save(gen_decode_full(ns), os.path.join(HERE, "decode_full.pt"))
     torch.save(gen_pointer_p1(ns), os.path.join(HERE, "pointer_p1.pt"))

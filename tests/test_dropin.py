@@ -233,6 +233,78 @@ def test_dropin_reproduces_reference_fixtures(golden_dir, name):
             assert (pooled.cpu() - c["enc"]["cls"]).abs().max() < 4e-5
 
 
+def test_topological_sort_graph_matches_reference(golden_dir):
+    """models/topological.py::Graph against trainers/topological_sort.py::Graph outputs (random tournaments, cycles,
+    assert_head) recorded by tests/golden/make_golden.py --only-graph."""
+    import json
+    from models.topological import Graph, debatch_stories
+    cases = json.load(open(os.path.join(golden_dir, "graph_cases.json")))
+    assert len(cases) == 60
+    for c in cases:
+        g = Graph(c["n"])
+        for u, v in c["edges"]:
+            g.addEdge(u, v)
+        try:
+            order = g.topologicalSort(assert_head=c["head"]) if c["head"] is not None else g.topologicalSort()
+        except AssertionError:
+            order = "assert"
+        assert order == c["order"], c
+    assert debatch_stories([["a0", "b0"], ["a1", "b1"], ["a2", "b2"]]) == [["a0", "a1", "a2"], ["b0", "b1", "b2"]]
+
+
+class TopoStubTokenizer:
+    """Same stand-in as tests/golden/make_golden.py: a text is a string of token ids; <s>=0, </s>=2, <pad>=1."""
+
+    def __call__(self, texts, max_length=None, padding=None, truncation=None, **kw):
+        rows = []
+        for t in texts:
+            ids = ([0] + [int(x) for x in t.split()])[:max_length - 1] + [2]
+            rows.append(ids + [1] * (max_length - len(ids)))
+        return {"input_ids": rows}
+
+
+@pytest.mark.gpu
+def test_topological_inference_matches_reference(golden_dir):
+    """trainers/eval.py::topological_inference: predicted orders and every pairwise logit against what the reference's
+    own function produced with the reference LXRTModel (tests/golden/topo_inference_tiny.pt); here all C(N,2) pairs of a
+    story go through the device in one call."""
+    from models.topological import topological_inference
+    mm = torch.load(os.path.join(golden_dir, "mm_tiny.pt"), weights_only=False)
+    t = torch.load(os.path.join(golden_dir, "topo_inference_tiny.pt"), weights_only=False)
+    c = mm["cfg"]
+    model = LXRTModel(LxrtBertConfig(c["vocab_size_or_config_json_file"], hidden_size=c["hidden_size"],
+                                     num_hidden_layers=c["num_hidden_layers"], num_attention_heads=c["num_attention_heads"],
+                                     intermediate_size=c["intermediate_size"], max_position_embeddings=c["max_position_embeddings"]),
+                      clip_model_name="ViT-B/32", clip_config=mm["vit"], cls_id=101, sep_id=102, max_story_length=5, num_labels=2)
+    sd = {k[len("bert."):]: v for k, v in mm["sd"].items() if k.startswith("bert.")}
+    sd.update(t["classifier"])
+    assert not model.load_state_dict(sd, strict=False).unexpected_keys
+    model = model.cuda().eval()
+    model.precise = True
+    # the generator drew the texts from the same stream first; re-draw them to land on the same image bits
+    g = torch.Generator().manual_seed(t["image_seed"])
+    for _ in range(t["N"]):
+        for _ in range(t["B"]):
+            torch.randint(10, 1000, (int(torch.randint(4, 12, (1,), generator=g)),), generator=g)
+    images = torch.randn(t["B"], t["N"], 3, 224, 224, generator=g)
+    assert abs(float(images.double().sum()) - t["image_checksum"]) < 1e-6, "torch RNG drift"
+    args = types.SimpleNamespace(**t["args"])
+    args.device = "cuda"
+    logits = []
+    fwd = model.forward
+
+    def spy(*a, **k):
+        out = fwd(*a, **k)
+        logits.append(out[0].detach().float().cpu())
+        return out
+
+    model.forward = spy
+    preds, loss = topological_inference(args, model, t["seqs"], TopoStubTokenizer(), images=images)
+    assert len(logits) == t["B"], "one device call per story, not one per pair"
+    assert (torch.cat(logits) - t["logits"]).abs().max() < 8e-6
+    assert preds == t["preds"] and loss == t["loss"]
+
+
 @pytest.mark.gpu
 def test_lxrt_topo_sort_classifier_mode(golden_dir):
     """LXRTModel(..., num_labels=2) as the pairwise classifier of trainers/eval.py:topological_inference
