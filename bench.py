@@ -180,6 +180,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner to stdout when NCCL_DEBUG is set; stdout carries exactly one JSON line here
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = dict(synth.BERT_BASE)
