@@ -145,6 +145,35 @@ int msq_order_manuals_host(msq_model* m, const int64_t* ids_host, const int64_t*
                            const int64_t* sep_host, int64_t B, int32_t N, int32_t Lt, const float* images_host,
                            int64_t n_img, const int32_t* img_index_host, int32_t beam, int32_t* perm_host, void* stream);
 
+/* ---- fine-tuning of the inner encoder (BASELINE config 4) -------------------------------------
+ * What the reference gets from autograd + transformers.AdamW (trainers/train.py:172-190, 340-363) for the inner model
+ * LXRTModel / BertModel (lxrt/modeling.py:1513-1598, modeling_bert.py:563-663) and the CLIP ViT tower
+ * (clip/model.py:190-305).  Dropout is not applied (p = 0).  The BERSON heads have no backward pass yet: their
+ * parameters are not in the table below.
+ *
+ * Gradients live in ONE flat fp32 device buffer owned by the caller (msq_train_grad_numel elements, 256-byte aligned,
+ * zeroed by the caller before the first backward of an optimizer step; backward ACCUMULATES).  Parameter i occupies
+ * [offset, offset + numel) of it (msq_train_param_info; name = the reference state_dict key).  Data-parallel
+ * fine-tuning all-reduces that one buffer over NCCL and passes grad_scale = 1 / world_size to msq_adamw_step. */
+int64_t msq_train_param_count(msq_model* m, void* stream);   /* -1 on error */
+int64_t msq_train_grad_numel(msq_model* m, void* stream);    /* -1 on error */
+int msq_train_param_info(msq_model* m, int64_t i, const char** name, int64_t* offset, int64_t* numel, int32_t* decay);
+/* current fp32 master copy of a registered weight (what save_pretrained would write) */
+int msq_train_read_param(msq_model* m, const char* name, float* out_dev, int64_t numel, void* stream);
+/* msq_inner_forward in training mode: same outputs, and the activations the backward pass needs are recorded inside the
+ * model.  images_dev must stay valid until msq_inner_backward has been enqueued. */
+int msq_inner_forward_train(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev, int64_t R,
+                            int32_t Lt, const float* images_dev, int64_t n_img, const int32_t* img_index_dev, float* lang_dev,
+                            float* visn_dev, void* stream);
+/* Backward of the recorded forward: d_lang [R,Lt,H], d_visn [R,Lv,H] (either may be NULL = zero) -> grads_dev += dL/dparam. */
+int msq_inner_backward(msq_model* m, const float* d_lang_dev, const float* d_visn_dev, float* grads_dev, void* stream);
+/* torch.nn.utils.clip_grad_norm_(max_grad_norm) (<= 0: no clipping) over grad_scale * grads, then one step of
+ * transformers.AdamW (correct_bias=True; weight decay skipped for names containing "bias" or "LayerNorm.weight",
+ * train.py:172-181), then every packed copy of the weights is rebuilt.  norm_out_dev (2 floats or NULL) receives the
+ * gradient norm and the factor applied to the gradients. */
+int msq_adamw_step(msq_model* m, const float* grads_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   float max_grad_norm, float grad_scale, float* norm_out_dev, void* stream);
+
 /* ---- building blocks exposed for kernel-level parity tests and the bench's roofline lines ------ */
 /* C[M,N] = act(A[M,K] W[N,K]^T + bias) + resid.  dtype: 0 = fp32 in/out (FFMA), 1 = bf16 in / fp32 out
  * (tcgen05), 2 = bf16 in / bf16 out (tcgen05).  act: 0 none, 1 erf-GELU, 2 QuickGELU, 3 tanh, 4 tanh-GELU. */

@@ -13,7 +13,7 @@
 #include <vector>
 
 #include "../../include/msq_b200.h"
-#include "kernels.cuh"
+#include "model.cuh"
 
 namespace msq {
 
@@ -66,97 +66,11 @@ void profile_mark(cudaStream_t st, bool end, double flops) {
   }
 }
 
-struct Arena {
-  char* base = nullptr;
-  size_t cap = 0, off = 0;
-  int reserve(size_t bytes, cudaStream_t st) {
-    if (bytes <= cap) return MSQ_OK;
-    MSQ_CUDA(cudaStreamSynchronize(st));
-    if (base) MSQ_CUDA(cudaFree(base));
-    base = nullptr;
-    cap = 0;
-    MSQ_CUDA(cudaMalloc(&base, bytes));
-    cap = bytes;
-    return MSQ_OK;
-  }
-  void reset() { off = 0; }
-  template <typename T> T* take(size_t n) {
-    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
-    T* p = reinterpret_cast<T*>(base + off);
-    off += bytes;
-    return p;
-  }
-};
-// first pass with base == nullptr measures, second pass hands out pointers
-struct Planner {
-  Arena* a;
-  bool measure;
-  size_t need = 0;
-  template <typename T> T* take(size_t n) {
-    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
-    if (measure) { need += bytes; return nullptr; }
-    return a->take<T>(n);
-  }
-};
-
-struct Lin {           // y = x W^T + b
-  const float* w32 = nullptr;
-  const bf16* w16 = nullptr;
-  const float* b = nullptr;
-  int N = 0, K = 0, ld = 0;
-};
-struct LNp { const float* g = nullptr; const float* b = nullptr; };
-// a linear layer with the LayerNorm in front of it folded in: lin.w16 = bf16(gamma_k W[n,k]), lin.b = b + W beta,
-// svec[n] = sum_k lin.w16[n,k]  (GemmArgs EPI_LNFOLD)
-struct LinF { Lin lin; const float* svec = nullptr; };
-
-struct BertLayerW { Lin qkv, out, up, down; LNp ln1, ln2; LinF qkv_f, up_f; };   // qkv_f folds the PREVIOUS layer's ln2, up_f this layer's ln1
-struct VitLayerW { Lin qkv, out, fc, proj; LNp ln1, ln2; LinF qkv_f, fc_f; };    // qkv_f folds ln_1, fc_f ln_2
-struct ParaLayerW { Lin qkv, fin, w1, w2; LNp ln_in, ln_ff; };
-struct RnBlockW { Lin c1, c2, c3, ds; bool has_ds = false; int stride = 1, cin = 0, planes = 0; };
 
 }  // namespace msq
 
 using namespace msq;
 
-struct msq_model {
-  msq_config cfg;
-  std::unordered_map<std::string, std::pair<float*, int64_t>> raw;
-  std::vector<void*> owned;
-  bool packed = false, has_bert = false, has_vit = false, has_heads = false;
-  std::string prefix_inner = "bert.";
-  // packed
-  const float *word = nullptr, *pos = nullptr, *type = nullptr;
-  LNp emb_ln;
-  std::vector<BertLayerW> bert;
-  Lin pooler;
-  bool has_pooler = false;
-  // vit
-  Lin conv1, visn_fc;
-  LinF visn_fc_f;   // visn_fc with the ViT's ln_post folded in
-  bool folded = false;
-  const float *vit_cls = nullptr, *vit_pos = nullptr;
-  LNp ln_pre, ln_post, visn_ln;
-  std::vector<VitLayerW> vit;
-  // CLIP ModifiedResNet tower (cfg.rn_width != 0)
-  Lin rn_stem[3], rn_qkv, rn_cproj;
-  std::vector<RnBlockW> rn_blocks;
-  const float *rn_pos = nullptr, *rn_posadd = nullptr;
-  // berson heads
-  Lin sent_tran, key_lin, xg_lin, t4_lin, pwk_raw, wih_raw, whh_raw, wq_raw;
-  int Kp4 = 0;
-  const float *w2 = nullptr, *b2 = nullptr, *w_rel = nullptr, *b_rel = nullptr, *w_in2 = nullptr;
-  std::vector<ParaLayerW> para;
-  LNp para_ln;
-  DecodeWeights dec;
-  int Kp = 0;  // padded H+2
-  Arena ws;
-  ~msq_model() {
-    for (auto& kv : raw) cudaFree(kv.second.first);
-    for (void* p : owned) cudaFree(p);
-    if (ws.base) cudaFree(ws.base);
-  }
-};
 
 namespace msq {
 
@@ -175,10 +89,19 @@ static int get_raw(msq_model* m, const std::string& name, int64_t numel, const f
   return MSQ_OK;
 }
 
+// Packed copies are allocated once.  msq_model_pack runs again after every optimizer step (train.cu): the second and
+// later runs issue the same sequence of requests and are handed the same buffers back (m->repack_cursor).
 template <typename T> static int dev_alloc(msq_model* m, size_t n, T** out) {
+  if (m->repacking) {
+    MSQ_REQUIRE(m->repack_cursor < m->owned.size() && m->owned_bytes[m->repack_cursor] == n * sizeof(T),
+                "repack: allocation sequence changed");
+    *out = reinterpret_cast<T*>(m->owned[m->repack_cursor++]);
+    return MSQ_OK;
+  }
   void* p = nullptr;
   MSQ_CUDA(cudaMalloc(&p, n * sizeof(T)));
   m->owned.push_back(p);
+  m->owned_bytes.push_back(n * sizeof(T));
   *out = reinterpret_cast<T*>(p);
   return MSQ_OK;
 }
@@ -358,6 +281,8 @@ static int64_t slab_rows() {
   return v;
 }
 
+static bool use_tc(const msq_model* m);
+bool model_use_tc(const msq_model* m) { return use_tc(m); }
 static bool use_tc(const msq_model* m) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("MSQ_FORCE_SIMT"); forced = (e && e[0] == '1') ? 1 : 0; }
@@ -772,6 +697,19 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
   }
   MSQ_CUDA(cudaStreamSynchronize(st));
   m->packed = true;
+  return MSQ_OK;
+}
+
+// Re-derive every packed copy (fused QKV, bf16, folded LayerNorm, LSTM / pw_k repacks) from the fp32 masters after an
+// optimizer step has changed them.  Same buffers, no allocation (dev_alloc replays m->owned).
+int msq::model_repack(msq_model* m, cudaStream_t st) {
+  MSQ_REQUIRE(m && m->packed, "repack: model not packed");
+  m->packed = false; m->repacking = true; m->repack_cursor = 0;
+  m->rn_blocks.clear();
+  const int rc = msq_model_pack(m, (void*)st);
+  m->repacking = false;
+  if (rc != MSQ_OK) return rc;
+  MSQ_REQUIRE(m->repack_cursor == m->owned.size(), "repack: allocation sequence changed");
   return MSQ_OK;
 }
 

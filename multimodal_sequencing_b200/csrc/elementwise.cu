@@ -14,26 +14,6 @@ namespace msq {
 
 constexpr int LN_MAX_VEC = 8;  // H <= 8 * 128 = 1024
 
-template <typename T> struct Vec4;
-template <> struct Vec4<float> {
-  static __device__ __forceinline__ float4 load(const float* p) { return *reinterpret_cast<const float4*>(p); }
-  static __device__ __forceinline__ void store(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-};
-template <> struct Vec4<bf16> {
-  static __device__ __forceinline__ float4 load(const bf16* p) {
-    uint2 u = *reinterpret_cast<const uint2*>(p);
-    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x), b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
-    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
-  }
-  static __device__ __forceinline__ void store(bf16* p, float4 v) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&a);
-    u.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(p) = u;
-  }
-};
-
 // Normalise the row held in v[] (nv float4 per lane) and write fp32 and/or T copies.
 template <typename T>
 __device__ __forceinline__ void ln_finish(float4* v, int nv, int H, int lane, const float* __restrict__ gamma,

@@ -131,4 +131,31 @@ int pointer_p1(const float* enc, const float* cls, const int64_t* y, const float
                const float* Wih, const float* Whh, const float* bih, const float* bhh, int64_t B, int N, int H, int U, float* preds,
                float* ce_scratch, float* loss, cudaStream_t st);
 
+// ---- train_kernels.cu : backward / optimizer kernels of the fine-tuning path (train.cu orchestrates them)
+template <typename TI, typename TO>
+int transpose_pad(const TI* src, int64_t M, int N, int ld, int64_t Mp, TO* dst, int act, cudaStream_t st);
+template <typename T> int rowsum_accum(const T* a, int rows, int64_t ld, int64_t n, float* out, cudaStream_t st);
+template <typename T> int act_fwd(const T* u, int64_t n, int act, T* h, cudaStream_t st);
+template <typename T> int act_bwd(const T* dh, const T* u, int64_t n, int act, T* du, cudaStream_t st);
+size_t ln_bwd_scratch_floats(int H);
+template <typename T>
+int ln_bwd(const float* dy, const float* x, const float* add, int64_t rows, int H, const float* gamma, float eps, float* dx, T* dx_t,
+           float* dgamma, float* dbeta, float* scratch, int in_group, int out_group, int out_off, cudaStream_t st);
+int embed_ln_bwd(const float* dy, const int64_t* ids, const int64_t* tts, int64_t R, int Lt, int Lj, int H, const float* word,
+                 const float* pos, const float* type, const float* gamma, float eps, float* dword, float* dpos, float* dtype,
+                 float* dgamma, float* dbeta, float* scratch, int pad0, cudaStream_t st);
+int vit_assemble_bwd(const float* dy, const float* patch, const int32_t* img_index, int64_t R, int il, int g2, int W, const float* cls,
+                     const float* pos, const float* gamma, float eps, float* dpatch, float* dcls, float* dpos, float* dgamma,
+                     float* dbeta, float* scratch, cudaStream_t st);
+size_t attention_bwd_scratch_floats(int64_t R, int L, int heads);
+template <typename T>
+int attention_bwd(const T* qkv, const T* dctx, int64_t R, int L, int heads, float scale, const float* key_mask_add, int mask_ld,
+                  int mask_len, T* dqkv, float* scratch, cudaStream_t st);
+int mask_add_from_int(const int64_t* mask, int64_t n, float* out, cudaStream_t st);
+int scatter_rows(const float* src, int64_t rows, int H, int group, int dst_group, int off, float* dst, cudaStream_t st);
+size_t grad_norm_scratch_floats();
+int grad_norm_clip(const float* g, int64_t n, float max_norm, float grad_scale, float* scratch, cudaStream_t st);
+int adamw_update(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float wd, int64_t step,
+                 const float* coef, cudaStream_t st);
+
 }  // namespace msq

@@ -1,0 +1,529 @@
+// Fine-tuning path of the inner encoder (BASELINE config 4): training-mode forward that records the
+// activations the backward pass needs, the backward pass itself, and the optimizer step.
+//
+// Reference: autograd through LXRTModel.forward (models/CLIP/src/lxrt/modeling.py:1513-1598) = BertEmbeddings (342-370),
+// LXRTEncoder CLIP branch (838-1107: tower, visn_fc + LayerNorm, concat, BertLayer x L), BertLayer (373-507); the CLIP
+// VisualTransformer (models/CLIP/clip/model.py:190-305); optimizer trainers/train.py:172-190 (HF AdamW, no_decay =
+// bias / LayerNorm.weight), 353-363 (clip_grad_norm_ then step).  Dropout is NOT applied (p = 0 semantics, the
+// configuration SURVEY §8(d) cfg4 prescribes for parity runs).
+//
+// Design.  Every contraction of the backward pass is a call of the forward GEMM kernels (gemm_tc.cu on
+// tcgen05, gemm_simt.cu in the fp32 parity mode), which compute C = A W^T with K-major operands:
+//   dgrad: dX = dY (W^T)^T with W^T a packed [K,N] copy of every weight (refreshed after each optimizer step);
+//   wgrad: dW += (dY^T)(X^T)^T with M-contiguous, zero-padded transposes written by transpose_pad; the accumulation
+//          into the caller's flat gradient buffer happens in the GEMM epilogue (residual operand == output).
+// Gradients live in ONE flat fp32 buffer owned by the caller (a torch tensor): data-parallel fine-tuning all-reduces
+// that buffer with a single NCCL call and hands it to msq_adamw_step.
+#include <array>
+#include <math.h>
+
+#include "model.cuh"
+
+namespace msq {
+
+struct ParamSlot { std::string name; int64_t off = 0, numel = 0; float* master = nullptr; bool decay = true; };
+struct BertTape { void *x, *qkv, *ctx, *x1, *u; float *s1, *s2; };
+struct VitTape { float *x, *x1; void *y1, *qkv, *ctx, *y2, *u; };
+
+struct TrainState {
+  std::vector<ParamSlot> slots;
+  std::unordered_map<std::string, size_t> index;
+  int64_t total = 0;
+  float *adam_m = nullptr, *adam_v = nullptr, *opt_scratch = nullptr;
+  int64_t step = 0;
+  // W^T copies in the GEMM operand type: [qkv, out, up, down] per BERT layer, [qkv, out, fc, proj] per ViT layer
+  std::vector<std::array<void*, 4>> bertT, vitT;
+  void* visnT = nullptr;
+  std::vector<void*> owned;
+  Arena tape;
+  // ---- record of the last training forward
+  bool have_fwd = false, mm = false;
+  int64_t R = 0, n_img = 0;
+  int Lt = 0, Lv = 0, Lj = 0;
+  const float* images = nullptr;   // caller-owned; must stay valid until msq_inner_backward returns
+  int64_t *ids = nullptr, *tt = nullptr;
+  int32_t* img_index = nullptr;
+  float *mask_add = nullptr, *patch = nullptr, *vx_last = nullptr, *visn_pre = nullptr;
+  void *x_last = nullptr, *y_post = nullptr;
+  std::vector<BertTape> bt;
+  std::vector<VitTape> vt;
+};
+
+void train_state_free(TrainState* ts) {
+  if (!ts) return;
+  for (void* p : ts->owned) cudaFree(p);
+  if (ts->adam_m) cudaFree(ts->adam_m);
+  if (ts->adam_v) cudaFree(ts->adam_v);
+  if (ts->opt_scratch) cudaFree(ts->opt_scratch);
+  if (ts->tape.base) cudaFree(ts->tape.base);
+  delete ts;
+}
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+constexpr int64_t TRAIN_IMG_CHUNK = 1024;
+
+template <typename T> static const T* wptr(const Lin& l);
+template <> const float* wptr<float>(const Lin& l) { return l.w32; }
+template <> const bf16* wptr<bf16>(const Lin& l) { return l.w16; }
+
+// C[M,N] = act(A[M,K] W[N,K]^T + bias) + resid on the model's GEMM path (tcgen05 when available and aligned)
+template <typename T, typename TO>
+static int gemm_nt(const msq_model* m, const T* A, int lda, const T* W, int ldw, const float* bias, const float* resid, int ldr, TO* C,
+                   int ldc, int64_t M, int N, int K, int act, cudaStream_t st) {
+  GemmArgs g;
+  g.A = A; g.W = W; g.bias = bias; g.resid = resid; g.C = C; g.C2 = nullptr;
+  g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldc = ldc; g.ldr = ldr; g.act = act;
+  if constexpr (sizeof(T) == 4) {
+    static_assert(sizeof(TO) == 4, "fp32 mode has fp32 outputs");
+    return gemm_simt<float, float>(g, st);
+  } else {
+    if (model_use_tc(m) && K % 64 == 0 && N % 8 == 0 && ldc % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0) return gemm_tc<TO>(g, st);
+    return gemm_simt<bf16, TO>(g, st);
+  }
+}
+
+// ---- parameter table -------------------------------------------------------------------------------
+static int add_slot(msq_model* m, TrainState* ts, const std::string& name) {
+  auto it = m->raw.find(name);
+  MSQ_REQUIRE(it != m->raw.end(), "train: weight %s is not registered", name.c_str());
+  ParamSlot s;
+  s.name = name; s.off = ts->total; s.numel = it->second.second; s.master = it->second.first;
+  s.decay = name.find("bias") == std::string::npos && name.find("LayerNorm.weight") == std::string::npos;   // train.py:172
+  ts->index[name] = ts->slots.size();
+  ts->slots.push_back(s);
+  ts->total += round_up(s.numel, 64);   // 256-byte aligned slots (TMA / float4 access to the gradient blocks)
+  return MSQ_OK;
+}
+
+template <typename T> static int make_wT(TrainState* ts, const Lin& l, void** out) {
+  void* p = nullptr;
+  MSQ_CUDA(cudaMalloc(&p, (size_t)l.N * l.K * sizeof(T)));
+  ts->owned.push_back(p);
+  *out = p;
+  return MSQ_OK;
+}
+template <typename T> static int fill_wT(const Lin& l, void* wT, cudaStream_t st) {
+  // w32 [N, ld] (K columns used) -> [K, N]
+  return transpose_pad<float, T>(l.w32, l.N, l.K, l.ld, l.N, (T*)wT, ACT_NONE, st);
+}
+template <typename T> static int refresh_wT(msq_model* m, TrainState* ts, cudaStream_t st) {
+  for (size_t l = 0; l < m->bert.size(); ++l) {
+    const Lin* ls[4] = {&m->bert[l].qkv, &m->bert[l].out, &m->bert[l].up, &m->bert[l].down};
+    for (int i = 0; i < 4; ++i) MSQ_TRY(fill_wT<T>(*ls[i], ts->bertT[l][i], st));
+  }
+  for (size_t l = 0; l < m->vit.size(); ++l) {
+    const Lin* ls[4] = {&m->vit[l].qkv, &m->vit[l].out, &m->vit[l].fc, &m->vit[l].proj};
+    for (int i = 0; i < 4; ++i) MSQ_TRY(fill_wT<T>(*ls[i], ts->vitT[l][i], st));
+  }
+  if (ts->visnT) MSQ_TRY(fill_wT<T>(m->visn_fc, ts->visnT, st));
+  return MSQ_OK;
+}
+
+template <typename T> static int build_train_state(msq_model* m, cudaStream_t st) {
+  const msq_config& c = m->cfg;
+  MSQ_REQUIRE(m->packed && m->has_bert, "train: model not packed / no inner encoder weights");
+  MSQ_REQUIRE(c.rn_width == 0, "train: the ModifiedResNet tower has no backward pass in this build (ViT / text-only only)");
+  TrainState* ts = new TrainState();
+  m->train = ts;
+  const std::string P = m->prefix_inner;
+  for (const char* e : {"embeddings.word_embeddings.weight", "embeddings.position_embeddings.weight",
+                        "embeddings.token_type_embeddings.weight", "embeddings.LayerNorm.weight", "embeddings.LayerNorm.bias"})
+    MSQ_TRY(add_slot(m, ts, P + e));
+  for (int l = 0; l < c.layers; ++l) {
+    const std::string b = P + "encoder.layer." + std::to_string(l) + ".";
+    // q/k/v are adjacent so that the fused [3H,H] gradient block is contiguous
+    for (const char* e : {"attention.self.query.weight", "attention.self.key.weight", "attention.self.value.weight",
+                          "attention.self.query.bias", "attention.self.key.bias", "attention.self.value.bias",
+                          "attention.output.dense.weight", "attention.output.dense.bias", "attention.output.LayerNorm.weight",
+                          "attention.output.LayerNorm.bias", "intermediate.dense.weight", "intermediate.dense.bias",
+                          "output.dense.weight", "output.dense.bias", "output.LayerNorm.weight", "output.LayerNorm.bias"})
+      MSQ_TRY(add_slot(m, ts, b + e));
+  }
+  if (m->has_vit) {
+    const std::string v = P + "encoder.visual_model.visual.";
+    for (const char* e : {"conv1.weight", "class_embedding", "positional_embedding", "ln_pre.weight", "ln_pre.bias", "ln_post.weight",
+                          "ln_post.bias"})
+      MSQ_TRY(add_slot(m, ts, v + e));
+    for (int l = 0; l < c.vit_layers; ++l) {
+      const std::string b = v + "transformer.resblocks." + std::to_string(l) + ".";
+      for (const char* e : {"attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias", "ln_1.weight",
+                            "ln_1.bias", "mlp.c_fc.weight", "mlp.c_fc.bias", "mlp.c_proj.weight", "mlp.c_proj.bias", "ln_2.weight",
+                            "ln_2.bias"})
+        MSQ_TRY(add_slot(m, ts, b + e));
+    }
+    for (const char* e : {"encoder.visn_fc.visn_fc.weight", "encoder.visn_fc.visn_fc.bias", "encoder.visn_fc.visn_layer_norm.weight",
+                          "encoder.visn_fc.visn_layer_norm.bias"})
+      MSQ_TRY(add_slot(m, ts, P + e));
+  }
+  // the fused-QKV gradient block relies on adjacency without padding
+  MSQ_REQUIRE(((int64_t)c.hidden * c.hidden) % 64 == 0 && c.hidden % 64 == 0, "train: hidden size must be a multiple of 64");
+  ts->bertT.resize(m->bert.size());
+  for (size_t l = 0; l < m->bert.size(); ++l) {
+    const Lin* ls[4] = {&m->bert[l].qkv, &m->bert[l].out, &m->bert[l].up, &m->bert[l].down};
+    for (int i = 0; i < 4; ++i) MSQ_TRY(make_wT<T>(ts, *ls[i], &ts->bertT[l][i]));
+  }
+  ts->vitT.resize(m->vit.size());
+  for (size_t l = 0; l < m->vit.size(); ++l) {
+    const Lin* ls[4] = {&m->vit[l].qkv, &m->vit[l].out, &m->vit[l].fc, &m->vit[l].proj};
+    for (int i = 0; i < 4; ++i) MSQ_TRY(make_wT<T>(ts, *ls[i], &ts->vitT[l][i]));
+  }
+  if (m->has_vit) MSQ_TRY(make_wT<T>(ts, m->visn_fc, &ts->visnT));
+  MSQ_TRY(refresh_wT<T>(m, ts, st));
+  return MSQ_OK;
+}
+static int ensure_train(msq_model* m, cudaStream_t st) {
+  MSQ_REQUIRE(m, "null model");
+  if (m->train) return MSQ_OK;
+  const int rc = m->cfg.precise ? build_train_state<float>(m, st) : build_train_state<bf16>(m, st);
+  if (rc != MSQ_OK && m->train) { train_state_free(m->train); m->train = nullptr; }
+  return rc;
+}
+
+// ---- training forward ------------------------------------------------------------------------------
+template <typename T>
+static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, const int64_t* mask, int64_t R, int Lt, const float* images,
+                         int64_t n_img, const int32_t* img_index, float* lang, float* visn, cudaStream_t st) {
+  TrainState* ts = m->train;
+  const msq_config& c = m->cfg;
+  const int H = c.hidden, I = c.inter;
+  const bool mm = m->has_vit && images != nullptr;
+  MSQ_REQUIRE(!mm || img_index, "train: images without img_index");
+  MSQ_REQUIRE(Lt <= c.max_pos && R > 0, "train: bad R / Lt");
+  const int g = mm ? c.vit_res / c.vit_patch : 0, g2 = g * g;
+  const int Lv = mm ? 1 + 2 * g2 : 0, Lj = Lt + Lv, Wd = c.vit_width, Kc = 3 * c.vit_patch * c.vit_patch;
+  const int64_t Mj = R * Lj, Mv = R * Lv;
+  const size_t nb = m->bert.size(), nvl = mm ? m->vit.size() : 0;
+  ts->have_fwd = false;
+  ts->bt.assign(nb, BertTape{});
+  ts->vt.assign(nvl, VitTape{});
+  float *xf = nullptr, *x1f = nullptr;
+  T *hb = nullptr, *apatch = nullptr, *vhb = nullptr;
+  for (int pass = 0; pass < 2; ++pass) {
+    Planner p{&ts->tape, pass == 0};
+    if (pass == 1) ts->tape.reset();
+    ts->ids = p.take<int64_t>((size_t)R * Lt);
+    ts->tt = p.take<int64_t>((size_t)R * Lt);
+    ts->mask_add = p.take<float>((size_t)R * Lt);
+    if (mm) {
+      ts->img_index = p.take<int32_t>((size_t)R * 2);
+      ts->patch = p.take<float>((size_t)n_img * g2 * Wd);
+      for (auto& v : ts->vt) {
+        v.x = p.take<float>((size_t)Mv * Wd); v.y1 = p.take<T>((size_t)Mv * Wd); v.qkv = p.take<T>((size_t)Mv * 3 * Wd);
+        v.ctx = p.take<T>((size_t)Mv * Wd); v.x1 = p.take<float>((size_t)Mv * Wd); v.y2 = p.take<T>((size_t)Mv * Wd);
+        v.u = p.take<T>((size_t)Mv * 4 * Wd);
+      }
+      ts->vx_last = p.take<float>((size_t)Mv * Wd);
+      ts->y_post = p.take<T>((size_t)Mv * Wd);
+      ts->visn_pre = p.take<float>((size_t)Mv * H);
+    }
+    for (auto& b : ts->bt) {
+      b.x = p.take<T>((size_t)Mj * H); b.qkv = p.take<T>((size_t)Mj * 3 * H); b.ctx = p.take<T>((size_t)Mj * H);
+      b.s1 = p.take<float>((size_t)Mj * H); b.x1 = p.take<T>((size_t)Mj * H); b.u = p.take<T>((size_t)Mj * I);
+      b.s2 = p.take<float>((size_t)Mj * H);
+    }
+    ts->x_last = p.take<T>((size_t)Mj * H);
+    if (pass == 0) MSQ_TRY(ts->tape.reserve(p.need + 4096, st));
+  }
+  for (int pass = 0; pass < 2; ++pass) {   // transient buffers
+    Planner p{&m->ws, pass == 0};
+    if (pass == 1) m->ws.reset();
+    xf = p.take<float>((size_t)Mj * H);
+    x1f = p.take<float>((size_t)Mj * H);
+    hb = p.take<T>((size_t)Mj * I);
+    if (mm) {
+      apatch = p.take<T>((size_t)min(n_img, TRAIN_IMG_CHUNK) * g2 * Kc);
+      vhb = p.take<T>((size_t)Mv * 4 * Wd);
+    }
+    if (pass == 0) MSQ_TRY(m->ws.reserve(p.need + 4096, st));
+  }
+  MSQ_CUDA(cudaMemcpyAsync(ts->ids, ids, (size_t)R * Lt * 8, cudaMemcpyDeviceToDevice, st));
+  MSQ_CUDA(cudaMemcpyAsync(ts->tt, tt, (size_t)R * Lt * 8, cudaMemcpyDeviceToDevice, st));
+  if (mm) MSQ_CUDA(cudaMemcpyAsync(ts->img_index, img_index, (size_t)R * 2 * 4, cudaMemcpyDeviceToDevice, st));
+  MSQ_TRY(mask_add_from_int(mask, R * Lt, ts->mask_add, st));
+
+  // layer-0 input: embeddings (text rows) and visn_fc(LN) of the tower output (visual rows) -> xf (fp32) + X[0] (T)
+  T* x0 = nb ? (T*)ts->bt[0].x : (T*)ts->x_last;
+  MSQ_TRY(embed_ln<T>(ids, tt, R, Lt, Lj, H, m->word, m->pos, m->type, m->emb_ln.g, m->emb_ln.b, 1e-12f, xf, x0, st));
+  if (mm) {
+    // patch embedding per UNIQUE image
+    for (int64_t i0 = 0; i0 < n_img; i0 += TRAIN_IMG_CHUNK) {
+      const int64_t n = min(TRAIN_IMG_CHUNK, n_img - i0);
+      MSQ_TRY(im2col<T>(images + i0 * 3 * c.vit_res * c.vit_res, n, c.vit_res, c.vit_patch, apatch, st));
+      MSQ_TRY((gemm_nt<T, float>(m, apatch, Kc, wptr<T>(m->conv1), m->conv1.ld, nullptr, nullptr, 0, ts->patch + i0 * g2 * Wd, Wd, n * g2, Wd,
+                                 Kc, ACT_NONE, st)));
+    }
+    float* x = nvl ? ts->vt[0].x : ts->vx_last;
+    MSQ_TRY(vit_assemble(ts->patch, img_index, R, 2, g2, Wd, m->vit_cls, m->vit_pos, m->ln_pre.g, m->ln_pre.b, 1e-5f, x, st));
+    const int heads = Wd / 64;
+    for (size_t l = 0; l < nvl; ++l) {
+      VitLayerW& L = m->vit[l];
+      VitTape& t = ts->vt[l];
+      float* xn = l + 1 < nvl ? ts->vt[l + 1].x : ts->vx_last;
+      MSQ_TRY(layernorm<T>(t.x, Mv, Wd, L.ln1.g, L.ln1.b, 1e-5f, nullptr, (T*)t.y1, 0, 0, 0, st));
+      MSQ_TRY((gemm_nt<T, T>(m, (const T*)t.y1, Wd, wptr<T>(L.qkv), L.qkv.ld, L.qkv.b, nullptr, 0, (T*)t.qkv, 3 * Wd, Mv, 3 * Wd, Wd, ACT_NONE, st)));
+      MSQ_TRY(attention<T>((const T*)t.qkv, R, Lv, heads, 64, 0.125f, nullptr, 0, 0, (T*)t.ctx, st));
+      MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.ctx, Wd, wptr<T>(L.out), L.out.ld, L.out.b, t.x, Wd, t.x1, Wd, Mv, Wd, Wd, ACT_NONE, st)));
+      MSQ_TRY(layernorm<T>(t.x1, Mv, Wd, L.ln2.g, L.ln2.b, 1e-5f, nullptr, (T*)t.y2, 0, 0, 0, st));
+      MSQ_TRY((gemm_nt<T, T>(m, (const T*)t.y2, Wd, wptr<T>(L.fc), L.fc.ld, L.fc.b, nullptr, 0, (T*)t.u, 4 * Wd, Mv, 4 * Wd, Wd, ACT_NONE, st)));
+      MSQ_TRY(act_fwd<T>((const T*)t.u, Mv * 4 * Wd, ACT_QUICK_GELU, vhb, st));
+      MSQ_TRY((gemm_nt<T, float>(m, vhb, 4 * Wd, wptr<T>(L.proj), L.proj.ld, L.proj.b, t.x1, Wd, xn, Wd, Mv, Wd, 4 * Wd, ACT_NONE, st)));
+    }
+    MSQ_TRY(layernorm<T>(ts->vx_last, Mv, Wd, m->ln_post.g, m->ln_post.b, 1e-5f, nullptr, (T*)ts->y_post, 0, 0, 0, st));
+    MSQ_TRY((gemm_nt<T, float>(m, (const T*)ts->y_post, Wd, wptr<T>(m->visn_fc), m->visn_fc.ld, m->visn_fc.b, nullptr, 0, ts->visn_pre, H, Mv,
+                               H, Wd, ACT_NONE, st)));
+    MSQ_TRY(layernorm<T>(ts->visn_pre, Mv, H, m->visn_ln.g, m->visn_ln.b, 1e-12f, xf, x0, Lv, Lj, Lt, st));
+  }
+  for (size_t l = 0; l < nb; ++l) {
+    BertLayerW& L = m->bert[l];
+    BertTape& t = ts->bt[l];
+    T* xn = l + 1 < nb ? (T*)ts->bt[l + 1].x : (T*)ts->x_last;
+    MSQ_TRY((gemm_nt<T, T>(m, (const T*)t.x, H, wptr<T>(L.qkv), L.qkv.ld, L.qkv.b, nullptr, 0, (T*)t.qkv, 3 * H, Mj, 3 * H, H, ACT_NONE, st)));
+    MSQ_TRY(attention<T>((const T*)t.qkv, R, Lj, c.heads, 64, 0.125f, ts->mask_add, Lt, Lt, (T*)t.ctx, st));
+    MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.ctx, H, wptr<T>(L.out), L.out.ld, L.out.b, xf, H, t.s1, H, Mj, H, H, ACT_NONE, st)));
+    MSQ_TRY(layernorm<T>(t.s1, Mj, H, L.ln1.g, L.ln1.b, 1e-12f, x1f, (T*)t.x1, 0, 0, 0, st));
+    MSQ_TRY((gemm_nt<T, T>(m, (const T*)t.x1, H, wptr<T>(L.up), L.up.ld, L.up.b, nullptr, 0, (T*)t.u, I, Mj, I, H, ACT_NONE, st)));
+    MSQ_TRY(act_fwd<T>((const T*)t.u, Mj * I, ACT_GELU_ERF, hb, st));
+    MSQ_TRY((gemm_nt<T, float>(m, hb, I, wptr<T>(L.down), L.down.ld, L.down.b, x1f, H, t.s2, H, Mj, H, I, ACT_NONE, st)));
+    MSQ_TRY(layernorm<T>(t.s2, Mj, H, L.ln2.g, L.ln2.b, 1e-12f, xf, xn, 0, 0, 0, st));
+  }
+  if (lang) MSQ_TRY((gather_rows<float, float>(xf, R * Lt, H, Lt, Lj, 0, lang, st)));
+  if (visn && mm) MSQ_TRY((gather_rows<float, float>(xf, R * Lv, H, Lv, Lj, Lt, visn, st)));
+  ts->R = R; ts->n_img = n_img; ts->Lt = Lt; ts->Lv = Lv; ts->Lj = Lj; ts->mm = mm; ts->images = images;
+  ts->have_fwd = true;
+  return MSQ_OK;
+}
+
+// ---- backward --------------------------------------------------------------------------------------
+struct BwdBufs { float *gA, *gB, *ln_scr, *at_scr, *dpatch; void *gT, *gH, *gC, *gQ, *GT, *XT, *apatch; };
+
+// dW[Nout,Kin] += G^T X (act_x applied to X on the fly), db[Nout] += column sums of G
+template <typename T>
+static int wgrad(const msq_model* m, const T* G, int ldg, int Nout, const T* X, int ldx, int Kin, int act_x, int64_t M, float* dW, float* db,
+                 BwdBufs& b, cudaStream_t st) {
+  const int64_t Mp = round_up(M, 64);
+  MSQ_TRY((transpose_pad<T, T>(G, M, Nout, ldg, Mp, (T*)b.GT, ACT_NONE, st)));
+  MSQ_TRY((transpose_pad<T, T>(X, M, Kin, ldx, Mp, (T*)b.XT, act_x, st)));
+  MSQ_TRY((gemm_nt<T, float>(m, (const T*)b.GT, (int)Mp, (const T*)b.XT, (int)Mp, nullptr, dW, Kin, dW, Kin, Nout, Kin, (int)Mp, ACT_NONE, st)));
+  if (db) MSQ_TRY(rowsum_accum<T>((const T*)b.GT, Nout, Mp, Mp, db, st));
+  return MSQ_OK;
+}
+// dX[M,Kin] = G[M,Nout] W  (+ resid), W^T given as [Kin, Nout]
+template <typename T, typename TO>
+static int dgrad(const msq_model* m, const T* G, int Nout, const void* WT, int Kin, const float* resid, TO* dX, int64_t M, cudaStream_t st) {
+  return gemm_nt<T, TO>(m, G, Nout, (const T*)WT, Nout, nullptr, resid, Kin, dX, Kin, M, Kin, Nout, ACT_NONE, st);
+}
+
+template <typename T>
+static int backward_train(msq_model* m, const float* d_lang, const float* d_visn, float* grads, cudaStream_t st) {
+  TrainState* ts = m->train;
+  MSQ_REQUIRE(ts && ts->have_fwd, "msq_inner_backward: no recorded training forward");
+  const msq_config& c = m->cfg;
+  const int H = c.hidden, I = c.inter, Lt = ts->Lt, Lv = ts->Lv, Lj = ts->Lj;
+  const bool mm = ts->mm;
+  const int64_t R = ts->R, Mj = R * Lj, Mv = R * Lv, n_img = ts->n_img;
+  const int g = mm ? c.vit_res / c.vit_patch : 0, g2 = g * g, Wd = c.vit_width, Kc = 3 * c.vit_patch * c.vit_patch;
+  const size_t nb = m->bert.size(), nvl = ts->vt.size();
+  const std::string P = m->prefix_inner;
+  int err = MSQ_OK;
+  auto G = [&](const std::string& name) -> float* {
+    auto it = ts->index.find(name);
+    if (it == ts->index.end()) { set_error("train: no gradient slot for %s", name.c_str()); err = MSQ_ERR_STATE; return nullptr; }
+    return grads + ts->slots[it->second].off;
+  };
+  const int64_t MpJ = round_up(Mj, 64), MpV = round_up(max(Mv, (int64_t)1), 64);
+  const int64_t nchunk = mm ? min(n_img, TRAIN_IMG_CHUNK) * g2 : 0, Np = round_up(max(nchunk, (int64_t)1), 64);
+  BwdBufs b{};
+  for (int pass = 0; pass < 2; ++pass) {
+    Planner p{&m->ws, pass == 0};
+    if (pass == 1) m->ws.reset();
+    const size_t act = (size_t)max(Mj * H, Mv * (int64_t)Wd);
+    b.gA = p.take<float>(act);
+    b.gB = p.take<float>(max(act, (size_t)Mv * H));
+    b.gT = p.take<T>(max(act, (size_t)Mv * H));
+    b.gC = p.take<T>(act);
+    b.gH = p.take<T>((size_t)max(Mj * I, Mv * 4 * (int64_t)Wd));
+    b.gQ = p.take<T>(3 * act);
+    b.GT = p.take<T>((size_t)max(max((int64_t)max(3 * H, I) * MpJ, (int64_t)4 * Wd * MpV), (int64_t)Wd * Np));
+    b.XT = p.take<T>((size_t)max(max((int64_t)max(H, I) * MpJ, (int64_t)4 * Wd * MpV), (int64_t)Kc * Np));
+    b.ln_scr = p.take<float>(ln_bwd_scratch_floats(max(H, Wd)));
+    b.at_scr = p.take<float>(max(attention_bwd_scratch_floats(R, Lj, c.heads), attention_bwd_scratch_floats(R, max(Lv, 1), max(Wd / 64, 1))));
+    if (mm) {
+      b.dpatch = p.take<float>((size_t)n_img * g2 * Wd);
+      b.apatch = p.take<T>((size_t)nchunk * Kc);
+    }
+    if (pass == 0) MSQ_TRY(m->ws.reserve(p.need + 4096, st));
+  }
+  // gradient of the final joint stream
+  MSQ_CUDA(cudaMemsetAsync(b.gA, 0, (size_t)Mj * H * sizeof(float), st));
+  if (d_lang) MSQ_TRY(scatter_rows(d_lang, R * Lt, H, Lt, Lj, 0, b.gA, st));
+  if (d_visn && mm) MSQ_TRY(scatter_rows(d_visn, R * Lv, H, Lv, Lj, Lt, b.gA, st));
+
+  for (size_t li = nb; li-- > 0;) {
+    BertLayerW& L = m->bert[li];
+    BertTape& t = ts->bt[li];
+    auto& WT = ts->bertT[li];
+    const std::string bn = P + "encoder.layer." + std::to_string(li) + ".";
+    float *dWqkv = G(bn + "attention.self.query.weight"), *dbqkv = G(bn + "attention.self.query.bias");
+    float *dWo = G(bn + "attention.output.dense.weight"), *dbo = G(bn + "attention.output.dense.bias");
+    float *dg1 = G(bn + "attention.output.LayerNorm.weight"), *db1 = G(bn + "attention.output.LayerNorm.bias");
+    float *dWu = G(bn + "intermediate.dense.weight"), *dbu = G(bn + "intermediate.dense.bias");
+    float *dWd = G(bn + "output.dense.weight"), *dbd = G(bn + "output.dense.bias");
+    float *dg2 = G(bn + "output.LayerNorm.weight"), *db2 = G(bn + "output.LayerNorm.bias");
+    if (err) return err;
+    // output.LayerNorm -> ds2 (gB fp32, gT operand copy)
+    MSQ_TRY(ln_bwd<T>(b.gA, t.s2, nullptr, Mj, H, L.ln2.g, 1e-12f, b.gB, (T*)b.gT, dg2, db2, b.ln_scr, 0, 0, 0, st));
+    MSQ_TRY(wgrad<T>(m, (const T*)b.gT, H, H, (const T*)t.u, I, I, ACT_GELU_ERF, Mj, dWd, dbd, b, st));
+    MSQ_TRY((dgrad<T, T>(m, (const T*)b.gT, H, WT[3], I, nullptr, (T*)b.gH, Mj, st)));
+    MSQ_TRY(act_bwd<T>((const T*)b.gH, (const T*)t.u, Mj * I, ACT_GELU_ERF, (T*)b.gH, st));
+    MSQ_TRY(wgrad<T>(m, (const T*)b.gH, I, I, (const T*)t.x1, H, H, ACT_NONE, Mj, dWu, dbu, b, st));
+    MSQ_TRY((dgrad<T, float>(m, (const T*)b.gH, I, WT[2], H, b.gB, b.gA, Mj, st)));            // dX1 = du Wup + ds2
+    // attention.output.LayerNorm -> ds1
+    MSQ_TRY(ln_bwd<T>(b.gA, t.s1, nullptr, Mj, H, L.ln1.g, 1e-12f, b.gB, (T*)b.gT, dg1, db1, b.ln_scr, 0, 0, 0, st));
+    MSQ_TRY(wgrad<T>(m, (const T*)b.gT, H, H, (const T*)t.ctx, H, H, ACT_NONE, Mj, dWo, dbo, b, st));
+    MSQ_TRY((dgrad<T, T>(m, (const T*)b.gT, H, WT[1], H, nullptr, (T*)b.gC, Mj, st)));
+    MSQ_TRY(attention_bwd<T>((const T*)t.qkv, (const T*)b.gC, R, Lj, c.heads, 0.125f, ts->mask_add, Lt, Lt, (T*)b.gQ, b.at_scr, st));
+    MSQ_TRY(wgrad<T>(m, (const T*)b.gQ, 3 * H, 3 * H, (const T*)t.x, H, H, ACT_NONE, Mj, dWqkv, dbqkv, b, st));
+    MSQ_TRY((dgrad<T, float>(m, (const T*)b.gQ, 3 * H, WT[0], H, b.gB, b.gA, Mj, st)));        // dX0 = dqkv Wqkv + ds1
+  }
+  // gA = gradient of the layer-0 input (LayerNorm outputs of the embeddings / of visn_fc)
+  {
+    float *dword = G(P + "embeddings.word_embeddings.weight"), *dpos = G(P + "embeddings.position_embeddings.weight"),
+          *dtyp = G(P + "embeddings.token_type_embeddings.weight"), *dg = G(P + "embeddings.LayerNorm.weight"),
+          *db = G(P + "embeddings.LayerNorm.bias");
+    if (err) return err;
+    MSQ_TRY(embed_ln_bwd(b.gA, ts->ids, ts->tt, R, Lt, Lj, H, m->word, m->pos, m->type, m->emb_ln.g, 1e-12f, dword, dpos, dtyp, dg, db, b.ln_scr,
+                         c.vit_width != 0 ? 7 : 1, st));   // padding_idx=0 tables: LXRT all three, text-only BertModel the word table
+  }
+  if (!mm) return MSQ_OK;
+
+  const std::string v = P + "encoder.visual_model.visual.";
+  {
+    float *dWv = G(P + "encoder.visn_fc.visn_fc.weight"), *dbv = G(P + "encoder.visn_fc.visn_fc.bias"),
+          *dgv = G(P + "encoder.visn_fc.visn_layer_norm.weight"), *dbl = G(P + "encoder.visn_fc.visn_layer_norm.bias"),
+          *dgp = G(v + "ln_post.weight"), *dbp = G(v + "ln_post.bias");
+    if (err) return err;
+    // visn_layer_norm backward on the visual rows of the joint gradient -> d(visn_fc out) [Mv,H] (gB) + operand copy (gT)
+    MSQ_TRY(ln_bwd<T>(b.gA, ts->visn_pre, nullptr, Mv, H, m->visn_ln.g, 1e-12f, b.gB, (T*)b.gT, dgv, dbl, b.ln_scr, Lv, Lj, Lt, st));
+    MSQ_TRY(wgrad<T>(m, (const T*)b.gT, H, H, (const T*)ts->y_post, Wd, Wd, ACT_NONE, Mv, dWv, dbv, b, st));
+    // d(ln_post out) fp32 -> gA is free now: reuse it as [Mv, Wd]
+    MSQ_TRY((dgrad<T, float>(m, (const T*)b.gT, H, ts->visnT, Wd, nullptr, b.gA, Mv, st)));
+    MSQ_TRY(ln_bwd<T>(b.gA, ts->vx_last, nullptr, Mv, Wd, m->ln_post.g, 1e-5f, b.gB, (T*)b.gT, dgp, dbp, b.ln_scr, 0, 0, 0, st));
+  }
+  // ViT blocks: stream gradient dx in gB (fp32) + gT (operand copy)
+  const int vheads = Wd / 64;
+  for (size_t li = nvl; li-- > 0;) {
+    VitLayerW& L = m->vit[li];
+    VitTape& t = ts->vt[li];
+    auto& WT = ts->vitT[li];
+    const std::string bn = v + "transformer.resblocks." + std::to_string(li) + ".";
+    float *dWqkv = G(bn + "attn.in_proj_weight"), *dbqkv = G(bn + "attn.in_proj_bias");
+    float *dWo = G(bn + "attn.out_proj.weight"), *dbo = G(bn + "attn.out_proj.bias");
+    float *dg1 = G(bn + "ln_1.weight"), *db1 = G(bn + "ln_1.bias"), *dg2 = G(bn + "ln_2.weight"), *db2 = G(bn + "ln_2.bias");
+    float *dWf = G(bn + "mlp.c_fc.weight"), *dbf = G(bn + "mlp.c_fc.bias"), *dWp = G(bn + "mlp.c_proj.weight"), *dbp = G(bn + "mlp.c_proj.bias");
+    if (err) return err;
+    MSQ_TRY(wgrad<T>(m, (const T*)b.gT, Wd, Wd, (const T*)t.u, 4 * Wd, 4 * Wd, ACT_QUICK_GELU, Mv, dWp, dbp, b, st));
+    MSQ_TRY((dgrad<T, T>(m, (const T*)b.gT, Wd, WT[3], 4 * Wd, nullptr, (T*)b.gH, Mv, st)));
+    MSQ_TRY(act_bwd<T>((const T*)b.gH, (const T*)t.u, Mv * 4 * Wd, ACT_QUICK_GELU, (T*)b.gH, st));
+    MSQ_TRY(wgrad<T>(m, (const T*)b.gH, 4 * Wd, 4 * Wd, (const T*)t.y2, Wd, Wd, ACT_NONE, Mv, dWf, dbf, b, st));
+    MSQ_TRY((dgrad<T, float>(m, (const T*)b.gH, 4 * Wd, WT[2], Wd, nullptr, b.gA, Mv, st)));      // d(ln_2 out)
+    MSQ_TRY(ln_bwd<T>(b.gA, t.x1, b.gB, Mv, Wd, L.ln2.g, 1e-5f, b.gB, (T*)b.gT, dg2, db2, b.ln_scr, 0, 0, 0, st));   // dx1 = dx + LN'
+    MSQ_TRY(wgrad<T>(m, (const T*)b.gT, Wd, Wd, (const T*)t.ctx, Wd, Wd, ACT_NONE, Mv, dWo, dbo, b, st));
+    MSQ_TRY((dgrad<T, T>(m, (const T*)b.gT, Wd, WT[1], Wd, nullptr, (T*)b.gC, Mv, st)));
+    MSQ_TRY(attention_bwd<T>((const T*)t.qkv, (const T*)b.gC, R, Lv, vheads, 0.125f, nullptr, 0, 0, (T*)b.gQ, b.at_scr, st));
+    MSQ_TRY(wgrad<T>(m, (const T*)b.gQ, 3 * Wd, 3 * Wd, (const T*)t.y1, Wd, Wd, ACT_NONE, Mv, dWqkv, dbqkv, b, st));
+    MSQ_TRY((dgrad<T, float>(m, (const T*)b.gQ, 3 * Wd, WT[0], Wd, nullptr, b.gA, Mv, st)));      // d(ln_1 out)
+    MSQ_TRY(ln_bwd<T>(b.gA, t.x, b.gB, Mv, Wd, L.ln1.g, 1e-5f, b.gB, (T*)b.gT, dg1, db1, b.ln_scr, 0, 0, 0, st));    // dx = dx1 + LN'
+  }
+  // token assembly + ln_pre, then the patch-embedding weight gradient per image chunk
+  {
+    float *dcls = G(v + "class_embedding"), *dpos = G(v + "positional_embedding"), *dgp = G(v + "ln_pre.weight"), *dbp = G(v + "ln_pre.bias"),
+          *dWc = G(v + "conv1.weight");
+    if (err) return err;
+    MSQ_CUDA(cudaMemsetAsync(b.dpatch, 0, (size_t)n_img * g2 * Wd * sizeof(float), st));
+    MSQ_TRY(vit_assemble_bwd(b.gB, ts->patch, ts->img_index, R, 2, g2, Wd, m->vit_cls, m->vit_pos, m->ln_pre.g, 1e-5f, b.dpatch, dcls, dpos, dgp,
+                             dbp, b.ln_scr, st));
+    for (int64_t i0 = 0; i0 < n_img; i0 += TRAIN_IMG_CHUNK) {
+      const int64_t n = min(TRAIN_IMG_CHUNK, n_img - i0), rows = n * g2, Mp = round_up(rows, 64);
+      MSQ_TRY(im2col<T>(ts->images + i0 * 3 * c.vit_res * c.vit_res, n, c.vit_res, c.vit_patch, (T*)b.apatch, st));
+      MSQ_TRY((transpose_pad<float, T>(b.dpatch + i0 * g2 * Wd, rows, Wd, Wd, Mp, (T*)b.GT, ACT_NONE, st)));
+      MSQ_TRY((transpose_pad<T, T>((const T*)b.apatch, rows, Kc, Kc, Mp, (T*)b.XT, ACT_NONE, st)));
+      MSQ_TRY((gemm_nt<T, float>(m, (const T*)b.GT, (int)Mp, (const T*)b.XT, (int)Mp, nullptr, dWc, Kc, dWc, Kc, Wd, Kc, (int)Mp, ACT_NONE, st)));
+    }
+  }
+  return MSQ_OK;
+}
+
+}  // namespace msq
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" int64_t msq_train_param_count(msq_model* m, void* stream) {
+  if (ensure_train(m, (cudaStream_t)stream) != MSQ_OK) return -1;
+  return (int64_t)m->train->slots.size();
+}
+extern "C" int64_t msq_train_grad_numel(msq_model* m, void* stream) {
+  if (ensure_train(m, (cudaStream_t)stream) != MSQ_OK) return -1;
+  return m->train->total;
+}
+extern "C" int msq_train_param_info(msq_model* m, int64_t i, const char** name, int64_t* offset, int64_t* numel, int32_t* decay) {
+  MSQ_REQUIRE(m && m->train && i >= 0 && i < (int64_t)m->train->slots.size(), "msq_train_param_info: bad index / no training state");
+  const ParamSlot& s = m->train->slots[(size_t)i];
+  if (name) *name = s.name.c_str();
+  if (offset) *offset = s.off;
+  if (numel) *numel = s.numel;
+  if (decay) *decay = s.decay ? 1 : 0;
+  return MSQ_OK;
+}
+extern "C" int msq_train_read_param(msq_model* m, const char* name, float* out_dev, int64_t numel, void* stream) {
+  MSQ_REQUIRE(m && name && out_dev, "null argument");
+  auto it = m->raw.find(name);
+  MSQ_REQUIRE(it != m->raw.end() && it->second.second == numel, "msq_train_read_param: unknown weight %s or wrong size", name);
+  MSQ_CUDA(cudaMemcpyAsync(out_dev, it->second.first, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return MSQ_OK;
+}
+
+extern "C" int msq_inner_forward_train(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev, int64_t R,
+                                       int32_t Lt, const float* images_dev, int64_t n_img, const int32_t* img_index_dev, float* lang_dev,
+                                       float* visn_dev, void* stream) {
+  MSQ_REQUIRE(m && ids_dev && tt_dev && mask_dev, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  MSQ_TRY(ensure_train(m, st));
+  if (m->cfg.precise) return forward_train<float>(m, ids_dev, tt_dev, mask_dev, R, Lt, images_dev, n_img, img_index_dev, lang_dev, visn_dev, st);
+  return forward_train<bf16>(m, ids_dev, tt_dev, mask_dev, R, Lt, images_dev, n_img, img_index_dev, lang_dev, visn_dev, st);
+}
+
+extern "C" int msq_inner_backward(msq_model* m, const float* d_lang_dev, const float* d_visn_dev, float* grads_dev, void* stream) {
+  MSQ_REQUIRE(m && grads_dev, "null argument");
+  MSQ_REQUIRE(((uintptr_t)grads_dev & 255) == 0, "msq_inner_backward: the gradient buffer must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m->cfg.precise) return backward_train<float>(m, d_lang_dev, d_visn_dev, grads_dev, st);
+  return backward_train<bf16>(m, d_lang_dev, d_visn_dev, grads_dev, st);
+}
+
+extern "C" int msq_adamw_step(msq_model* m, const float* grads_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
+                              float max_grad_norm, float grad_scale, float* norm_out_dev, void* stream) {
+  MSQ_REQUIRE(m && grads_dev, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  MSQ_TRY(ensure_train(m, st));
+  TrainState* ts = m->train;
+  if (!ts->adam_m) {
+    MSQ_CUDA(cudaMalloc(&ts->adam_m, (size_t)ts->total * sizeof(float)));
+    MSQ_CUDA(cudaMalloc(&ts->adam_v, (size_t)ts->total * sizeof(float)));
+    MSQ_CUDA(cudaMalloc(&ts->opt_scratch, grad_norm_scratch_floats() * sizeof(float)));
+    MSQ_CUDA(cudaMemsetAsync(ts->adam_m, 0, (size_t)ts->total * sizeof(float), st));
+    MSQ_CUDA(cudaMemsetAsync(ts->adam_v, 0, (size_t)ts->total * sizeof(float), st));
+  }
+  ++ts->step;
+  // padding between slots is never written by the backward pass (the caller zeroes the buffer), so the norm over the
+  // whole flat buffer is the norm over the parameters' gradients
+  MSQ_TRY(grad_norm_clip(grads_dev, ts->total, max_grad_norm, grad_scale, ts->opt_scratch, st));
+  for (const ParamSlot& s : ts->slots)
+    MSQ_TRY(adamw_update(s.master, grads_dev + s.off, ts->adam_m + s.off, ts->adam_v + s.off, s.numel, lr, beta1, beta2, eps,
+                         s.decay ? weight_decay : 0.f, ts->step, ts->opt_scratch, st));
+  if (norm_out_dev) MSQ_CUDA(cudaMemcpyAsync(norm_out_dev, ts->opt_scratch, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // masters changed: rebuild the packed copies (fused QKV, bf16, folded LayerNorm, ...) and the W^T operands
+  MSQ_TRY(model_repack(m, st));
+  if (m->cfg.precise) return refresh_wT<float>(m, ts, st);
+  return refresh_wT<bf16>(m, ts, st);
+}

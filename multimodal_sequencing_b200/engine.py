@@ -256,6 +256,73 @@ class OrderingEngine:
         _lib.check(self.lib.msq_gemm(0, self._p(x), self._p(w), self._p(b), None, self._p(out), M, Np, Kp, act, self._stream()))
         return out[:, :N]
 
+    # ---- fine-tuning of the inner encoder (SURVEY 8(f).2): training forward / backward / AdamW -----------
+    def train_layout(self):
+        """[(state_dict key, offset, numel, decays)] of the flat gradient buffer (msq_train_param_info)."""
+        if getattr(self, "_layout", None) is None:
+            n = int(self.lib.msq_train_param_count(self._h, self._stream()))
+            if n < 0:
+                _lib.check(1)
+            out = []
+            name, off, numel, dec = C.c_char_p(), C.c_int64(), C.c_int64(), C.c_int32()
+            for i in range(n):
+                _lib.check(self.lib.msq_train_param_info(self._h, i, C.byref(name), C.byref(off), C.byref(numel), C.byref(dec)))
+                out.append((name.value.decode(), off.value, numel.value, bool(dec.value)))
+            self._layout = out
+            self._grad_numel = int(self.lib.msq_train_grad_numel(self._h, self._stream()))
+        return self._layout
+
+    def new_grad_buffer(self):
+        """Zeroed flat fp32 gradient buffer (one torch tensor: all-reduce it as a whole in data-parallel runs)."""
+        self.train_layout()
+        return torch.zeros(self._grad_numel, device=self.device, dtype=torch.float32)
+
+    def grads_by_name(self, flat):
+        """Views of the flat buffer keyed by the reference's state_dict names."""
+        return {n: flat[o:o + k] for n, o, k, _ in self.train_layout()}
+
+    def inner_forward_train(self, ids, tt, mask, images=None, img_index=None):
+        """LXRTModel.forward / BertModel.forward in training mode (activations recorded for inner_backward)."""
+        ids = ids.to(self.device, torch.long).contiguous()
+        tt = tt.to(self.device, torch.long).contiguous()
+        mask = mask.to(self.device, torch.long).contiguous()
+        R, Lt = ids.shape
+        lang = torch.empty(R, Lt, self.H, device=self.device)
+        visn, n_img = None, 0
+        if self.multimodal and images is not None:
+            images = images.to(self.device, torch.float32).contiguous()
+            img_index = img_index.to(self.device, torch.int32).contiguous()
+            g = self._grid
+            visn = torch.empty(R, 1 + 2 * g * g, self.H, device=self.device)
+            n_img = images.shape[0]
+        self._train_keep = (images, img_index)   # the backward pass re-reads the images (patch-embedding weight gradient)
+        _lib.check(self.lib.msq_inner_forward_train(self._h, self._p(ids), self._p(tt), self._p(mask), R, Lt,
+                                                    self._p(images if visn is not None else None), n_img,
+                                                    self._p(img_index if visn is not None else None), self._p(lang),
+                                                    self._p(visn), self._stream()))
+        return lang, visn
+
+    def inner_backward(self, d_lang, d_visn, grads):
+        """grads += dL/dparam for the recorded forward, given dL/d(lang), dL/d(visn)."""
+        d_lang = None if d_lang is None else d_lang.to(self.device, torch.float32).contiguous()
+        d_visn = None if d_visn is None else d_visn.to(self.device, torch.float32).contiguous()
+        _lib.check(self.lib.msq_inner_backward(self._h, self._p(d_lang), self._p(d_visn), self._p(grads), self._stream()))
+        return grads
+
+    def adamw_step(self, grads, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0, grad_scale=1.0):
+        """clip_grad_norm_ + transformers.AdamW step (trainers/train.py:185-190, 353-363) on the fp32 masters, then re-pack.
+        Returns a 2-element device tensor (gradient norm, factor applied to the gradients)."""
+        norm = torch.empty(2, device=self.device)
+        _lib.check(self.lib.msq_adamw_step(self._h, self._p(grads), lr, betas[0], betas[1], eps, weight_decay, max_grad_norm,
+                                           grad_scale, self._p(norm), self._stream()))
+        return norm
+
+    def read_param(self, name, shape):
+        """Current fp32 master of a registered weight (e.g. for save_pretrained)."""
+        out = torch.empty(*shape, device=self.device)
+        _lib.check(self.lib.msq_train_read_param(self._h, name.encode(), self._p(out), out.numel(), self._stream()))
+        return out
+
     def training_loss(self, batch: PairBatch, lam=0.6):
         """BertForOrdering._forward loss value (modeling_bert.py:943-1174), forward only -> 0-d device tensor."""
         b = batch.to(self.device)

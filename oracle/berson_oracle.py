@@ -484,7 +484,7 @@ def training_loss(sd, cfg, inp, lam=0.6):
             pm = pointed[-1].clone(); pm[ar, :, tar] = 1; pointed.append(pm)
         left1 = (hist * l1[..., None]).sum(1)
         left2 = (hist * l2[..., None]).sum(1)
-        rela.mul_(rela_mask[..., None])
+        rela = rela * rela_mask[..., None].clone()   # (the reference zeroes in place, 1385; out of place here so autograd can replay it)
         pw = torch.cat([left1, left2, rela.mean(2), rela.mean(1)], -1)
         pw_keys.append((pw @ sd["pw_k.weight"].t())[:, None])
         h, c = lstm_cell(sd, dec_in[:, t], h, c)

@@ -1,0 +1,82 @@
+"""Fine-tuning oracle (oracle/train_oracle.py) against gradients the REAL reference produced
+(tests/golden/make_golden_grads.py -> grads_tiny.pt), plus the optimizer restatement.  CPU only."""
+import os
+
+import torch
+
+from oracle import berson_oracle as O
+from oracle import train_oracle as TO
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def _cfg(g):
+    c = g["cfg"]
+    return dict(num_hidden_layers=c["num_hidden_layers"], num_attention_heads=c["num_attention_heads"], vit=g.get("vit"))
+
+
+def _check(grads, ref, loss, ref_loss):
+    assert abs(loss - ref_loss) < 2e-5
+    missing = [n for n in ref if n not in grads]
+    assert not missing, missing
+    for n, s in ref.items():
+        g = grads[n].double().reshape(-1)
+        assert g.numel() == s["numel"], n
+        scale = max(s["norm"], 1e-6)
+        assert abs(float(g.norm()) - s["norm"]) < 2e-4 * scale + 1e-7, n
+        assert (g[s["idx"]].float() - s["val"]).abs().max() < 2e-4 * scale / max(s["numel"], 1) ** 0.5 + 2e-6, n
+        assert abs(float(g.sum()) - s["sum"]) < 2e-4 * scale * max(s["numel"], 1) ** 0.5 + 1e-6, n
+
+
+def test_text_loss_gradients_match_reference(golden_dir):
+    g, r = _load(golden_dir, "text_tiny.pt"), _load(golden_dir, "grads_tiny.pt")["text"]
+    ids, labels, _ = O.synthetic_manuals(r["B"], r["N"], r["L"], vocab=1000, seed=r["seed"])
+    loss, grads = TO.loss_grads(g["sd"], _cfg(g), O.prepare_inputs(ids, labels, r["N"]))
+    _check(grads, r["grads"], loss, r["loss"])
+
+
+def test_multimodal_loss_gradients_match_reference(golden_dir):
+    g, r = _load(golden_dir, "mm_tiny.pt"), _load(golden_dir, "grads_tiny.pt")["mm"]
+    ids, labels, images = O.synthetic_manuals(r["B"], r["N"], r["L"], vocab=1000, image_px=224, seed=r["seed"])
+    assert abs(float(images.double().sum()) - r["image_checksum"]) < 1e-6, "torch RNG drift"
+    loss, grads = TO.loss_grads(g["sd"], _cfg(g), O.prepare_inputs(ids, labels, r["N"], images))
+    _check(grads, r["grads"], loss, r["loss"])
+
+
+def test_clip_matches_torch():
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(7, 5)), torch.nn.Parameter(torch.randn(11))]
+    for p in ps:
+        p.grad = torch.randn_like(p) * 3
+    gs = [p.grad.clone() for p in ps]
+    total, coef = TO.clip_coef(gs, 1.0)
+    ref_total = torch.nn.utils.clip_grad_norm_(ps, 1.0)
+    assert abs(total - float(ref_total)) < 1e-5
+    for p, g in zip(ps, gs):
+        assert (p.grad - g * coef).abs().max() < 1e-6
+
+
+def test_hf_adamw_known_answer():
+    """First step of Adam with bias correction moves every weight by lr * sign(g) (up to eps); a later step is
+    checked against torch.optim.Adam on the eps-free limit (HF and torch differ only in where eps enters)."""
+    p, g = torch.tensor([1.0, -2.0, 0.5]), torch.tensor([0.3, -0.1, 2.0])
+    m, v = torch.zeros(3), torch.zeros(3)
+    TO.hf_adamw_step(p, g, m, v, 1, lr=1e-2, eps=0.0)
+    assert torch.allclose(p, torch.tensor([1.0 - 1e-2, -2.0 + 1e-2, 0.5 - 1e-2]), atol=1e-7)
+    q = torch.nn.Parameter(torch.tensor([1.0, -2.0, 0.5]))
+    opt = torch.optim.Adam([q], lr=1e-2, eps=1e-30)
+    p2, m2, v2 = torch.tensor([1.0, -2.0, 0.5]), torch.zeros(3), torch.zeros(3)
+    for t in range(1, 4):
+        gt = torch.tensor([0.3, -0.1, 2.0]) * t
+        q.grad = gt.clone()
+        opt.step()
+        TO.hf_adamw_step(p2, gt, m2, v2, t, lr=1e-2, eps=0.0)
+    assert torch.allclose(p2, q.detach(), atol=1e-6)
+    # decoupled decay is applied after the Adam update, on the updated weight
+    p3, m3, v3 = torch.tensor([1.0]), torch.zeros(1), torch.zeros(1)
+    TO.hf_adamw_step(p3, torch.tensor([1.0]), m3, v3, 1, lr=0.1, eps=0.0, weight_decay=0.5)
+    assert abs(float(p3) - (0.9 - 0.1 * 0.5 * 0.9)) < 1e-7
+    assert TO.decays("bert.encoder.layer.0.output.dense.weight") and not TO.decays("bert.encoder.layer.0.output.dense.bias")
+    assert not TO.decays("bert.embeddings.LayerNorm.weight") and TO.decays("bert.encoder.visn_fc.visn_layer_norm.weight")
