@@ -148,8 +148,7 @@ int msq_order_manuals_host(msq_model* m, const int64_t* ids_host, const int64_t*
 /* ---- fine-tuning of the inner encoder (BASELINE config 4) -------------------------------------
  * What the reference gets from autograd + transformers.AdamW (trainers/train.py:172-190, 340-363) for the inner model
  * LXRTModel / BertModel (lxrt/modeling.py:1513-1598, modeling_bert.py:563-663) and the CLIP ViT tower
- * (clip/model.py:190-305).  Dropout is not applied (p = 0).  The BERSON heads have no backward pass yet: their
- * parameters are not in the table below.
+ * (clip/model.py:190-305), and for the BERSON heads + loss (msq_train_step).  Dropout is not applied (p = 0).
  *
  * Gradients live in ONE flat fp32 device buffer owned by the caller (msq_train_grad_numel elements, 256-byte aligned,
  * zeroed by the caller before the first backward of an optimizer step; backward ACCUMULATES).  Parameter i occupies
@@ -167,6 +166,15 @@ int msq_inner_forward_train(msq_model* m, const int64_t* ids_dev, const int64_t*
                             float* visn_dev, void* stream);
 /* Backward of the recorded forward: d_lang [R,Lt,H], d_visn [R,Lv,H] (either may be NULL = zero) -> grads_dev += dL/dparam. */
 int msq_inner_backward(msq_model* m, const float* d_lang_dev, const float* d_visn_dev, float* grads_dev, void* stream);
+/* One fine-tuning forward + backward of BertForOrdering.forward(inputs) -> (loss,) in train mode (modeling_bert.py:937-941,
+ * 943-1174, default objectives: teacher-forced pointer NLL / (N-1) + lam * pairwise NLL / P, batch mean) followed by
+ * loss.backward() (trainers/train.py:340-351): inputs as msq_training_loss; loss_dev (1 float, may be NULL) receives the
+ * loss, grads_dev += dL/dparam for every parameter of the path, encoder AND heads (the parameter table then also lists the
+ * head parameters the reference gives a gradient to). */
+int msq_train_step(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev, const int64_t* sep_dev,
+                   int64_t B, int32_t N, int32_t Lt, const float* images_dev, int64_t n_img, const int32_t* img_index_dev,
+                   const int32_t* ground_truth_dev, const int64_t* pairwise_labels_dev, float lam, float* grads_dev, float* loss_dev,
+                   void* stream);
 /* torch.nn.utils.clip_grad_norm_(max_grad_norm) (<= 0: no clipping) over grad_scale * grads, then one step of
  * transformers.AdamW (correct_bias=True; weight decay skipped for names containing "bias" or "LayerNorm.weight",
  * train.py:172-181), then every packed copy of the weights is rebuilt.  norm_out_dev (2 floats or NULL) receives the

@@ -48,6 +48,7 @@ SIGNATURES = {
     "msq_train_read_param": (C.c_int, [_P, C.c_char_p, _P, _I64, _P]),
     "msq_inner_forward_train": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _I64, _P, _P, _P, _P]),
     "msq_inner_backward": (C.c_int, [_P, _P, _P, _P, _P]),
+    "msq_train_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P, _P, _F, _P, _P, _P]),
     "msq_adamw_step": (C.c_int, [_P, _P, _F, _F, _F, _F, _F, _F, _F, _P, _P]),
     "msq_gemm": (C.c_int, [_I32, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P]),
     "msq_gemm_deferred_ln": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _F, _P, _P, _P, _I64, _I32, _I32, _I32, _P]),

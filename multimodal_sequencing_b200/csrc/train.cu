@@ -14,73 +14,11 @@
 //          into the caller's flat gradient buffer happens in the GEMM epilogue (residual operand == output).
 // Gradients live in ONE flat fp32 buffer owned by the caller (a torch tensor): data-parallel fine-tuning all-reduces
 // that buffer with a single NCCL call and hands it to msq_adamw_step.
-#include <array>
-#include <math.h>
-
-#include "model.cuh"
+#include "train_common.cuh"
 
 namespace msq {
 
-struct ParamSlot { std::string name; int64_t off = 0, numel = 0; float* master = nullptr; bool decay = true; };
-struct BertTape { void *x, *qkv, *ctx, *x1, *u; float *s1, *s2; };
-struct VitTape { float *x, *x1; void *y1, *qkv, *ctx, *y2, *u; };
-
-struct TrainState {
-  std::vector<ParamSlot> slots;
-  std::unordered_map<std::string, size_t> index;
-  int64_t total = 0;
-  float *adam_m = nullptr, *adam_v = nullptr, *opt_scratch = nullptr;
-  int64_t step = 0;
-  // W^T copies in the GEMM operand type: [qkv, out, up, down] per BERT layer, [qkv, out, fc, proj] per ViT layer
-  std::vector<std::array<void*, 4>> bertT, vitT;
-  void* visnT = nullptr;
-  std::vector<void*> owned;
-  Arena tape;
-  // ---- record of the last training forward
-  bool have_fwd = false, mm = false;
-  int64_t R = 0, n_img = 0;
-  int Lt = 0, Lv = 0, Lj = 0;
-  const float* images = nullptr;   // caller-owned; must stay valid until msq_inner_backward returns
-  int64_t *ids = nullptr, *tt = nullptr;
-  int32_t* img_index = nullptr;
-  float *mask_add = nullptr, *patch = nullptr, *vx_last = nullptr, *visn_pre = nullptr;
-  void *x_last = nullptr, *y_post = nullptr;
-  std::vector<BertTape> bt;
-  std::vector<VitTape> vt;
-};
-
-void train_state_free(TrainState* ts) {
-  if (!ts) return;
-  for (void* p : ts->owned) cudaFree(p);
-  if (ts->adam_m) cudaFree(ts->adam_m);
-  if (ts->adam_v) cudaFree(ts->adam_v);
-  if (ts->opt_scratch) cudaFree(ts->opt_scratch);
-  if (ts->tape.base) cudaFree(ts->tape.base);
-  delete ts;
-}
-
-static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
-constexpr int64_t TRAIN_IMG_CHUNK = 1024;
-
-template <typename T> static const T* wptr(const Lin& l);
-template <> const float* wptr<float>(const Lin& l) { return l.w32; }
-template <> const bf16* wptr<bf16>(const Lin& l) { return l.w16; }
-
-// C[M,N] = act(A[M,K] W[N,K]^T + bias) + resid on the model's GEMM path (tcgen05 when available and aligned)
-template <typename T, typename TO>
-static int gemm_nt(const msq_model* m, const T* A, int lda, const T* W, int ldw, const float* bias, const float* resid, int ldr, TO* C,
-                   int ldc, int64_t M, int N, int K, int act, cudaStream_t st) {
-  GemmArgs g;
-  g.A = A; g.W = W; g.bias = bias; g.resid = resid; g.C = C; g.C2 = nullptr;
-  g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldc = ldc; g.ldr = ldr; g.act = act;
-  if constexpr (sizeof(T) == 4) {
-    static_assert(sizeof(TO) == 4, "fp32 mode has fp32 outputs");
-    return gemm_simt<float, float>(g, st);
-  } else {
-    if (model_use_tc(m) && K % 64 == 0 && N % 8 == 0 && ldc % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0) return gemm_tc<TO>(g, st);
-    return gemm_simt<bf16, TO>(g, st);
-  }
-}
+void train_state_free(TrainState* ts) { train_state_free_impl(ts); }
 
 // ---- parameter table -------------------------------------------------------------------------------
 static int add_slot(msq_model* m, TrainState* ts, const std::string& name) {
@@ -169,6 +107,10 @@ template <typename T> static int build_train_state(msq_model* m, cudaStream_t st
   }
   if (m->has_vit) MSQ_TRY(make_wT<T>(ts, m->visn_fc, &ts->visnT));
   MSQ_TRY(refresh_wT<T>(m, ts, st));
+  if (m->has_heads) {
+    for (const std::string& n : heads_param_names(m)) MSQ_TRY(add_slot(m, ts, n));
+    MSQ_TRY(heads_train_setup(m, true, st));
+  }
   return MSQ_OK;
 }
 static int ensure_train(msq_model* m, cudaStream_t st) {
@@ -222,6 +164,7 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
       b.s2 = p.take<float>((size_t)Mj * H);
     }
     ts->x_last = p.take<T>((size_t)Mj * H);
+    ts->x_out = p.take<float>((size_t)Mj * H);
     if (pass == 0) MSQ_TRY(ts->tape.reserve(p.need + 4096, st));
   }
   for (int pass = 0; pass < 2; ++pass) {   // transient buffers
@@ -286,6 +229,7 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
     MSQ_TRY((gemm_nt<T, float>(m, hb, I, wptr<T>(L.down), L.down.ld, L.down.b, x1f, H, t.s2, H, Mj, H, I, ACT_NONE, st)));
     MSQ_TRY(layernorm<T>(t.s2, Mj, H, L.ln2.g, L.ln2.b, 1e-12f, xf, xn, 0, 0, 0, st));
   }
+  MSQ_CUDA(cudaMemcpyAsync(ts->x_out, xf, (size_t)Mj * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (lang) MSQ_TRY((gather_rows<float, float>(xf, R * Lt, H, Lt, Lj, 0, lang, st)));
   if (visn && mm) MSQ_TRY((gather_rows<float, float>(xf, R * Lv, H, Lv, Lj, Lt, visn, st)));
   ts->R = R; ts->n_img = n_img; ts->Lt = Lt; ts->Lv = Lv; ts->Lj = Lj; ts->mm = mm; ts->images = images;
@@ -294,25 +238,6 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
 }
 
 // ---- backward --------------------------------------------------------------------------------------
-struct BwdBufs { float *gA, *gB, *ln_scr, *at_scr, *dpatch; void *gT, *gH, *gC, *gQ, *GT, *XT, *apatch; };
-
-// dW[Nout,Kin] += G^T X (act_x applied to X on the fly), db[Nout] += column sums of G
-template <typename T>
-static int wgrad(const msq_model* m, const T* G, int ldg, int Nout, const T* X, int ldx, int Kin, int act_x, int64_t M, float* dW, float* db,
-                 BwdBufs& b, cudaStream_t st) {
-  const int64_t Mp = round_up(M, 64);
-  MSQ_TRY((transpose_pad<T, T>(G, M, Nout, ldg, Mp, (T*)b.GT, ACT_NONE, st)));
-  MSQ_TRY((transpose_pad<T, T>(X, M, Kin, ldx, Mp, (T*)b.XT, act_x, st)));
-  MSQ_TRY((gemm_nt<T, float>(m, (const T*)b.GT, (int)Mp, (const T*)b.XT, (int)Mp, nullptr, dW, Kin, dW, Kin, Nout, Kin, (int)Mp, ACT_NONE, st)));
-  if (db) MSQ_TRY(rowsum_accum<T>((const T*)b.GT, Nout, Mp, Mp, db, st));
-  return MSQ_OK;
-}
-// dX[M,Kin] = G[M,Nout] W  (+ resid), W^T given as [Kin, Nout]
-template <typename T, typename TO>
-static int dgrad(const msq_model* m, const T* G, int Nout, const void* WT, int Kin, const float* resid, TO* dX, int64_t M, cudaStream_t st) {
-  return gemm_nt<T, TO>(m, G, Nout, (const T*)WT, Nout, nullptr, resid, Kin, dX, Kin, M, Kin, Nout, ACT_NONE, st);
-}
-
 template <typename T>
 static int backward_train(msq_model* m, const float* d_lang, const float* d_visn, float* grads, cudaStream_t st) {
   TrainState* ts = m->train;
@@ -524,6 +449,29 @@ extern "C" int msq_adamw_step(msq_model* m, const float* grads_dev, float lr, fl
   if (norm_out_dev) MSQ_CUDA(cudaMemcpyAsync(norm_out_dev, ts->opt_scratch, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // masters changed: rebuild the packed copies (fused QKV, bf16, folded LayerNorm, ...) and the W^T operands
   MSQ_TRY(model_repack(m, st));
-  if (m->cfg.precise) return refresh_wT<float>(m, ts, st);
-  return refresh_wT<bf16>(m, ts, st);
+  if (m->cfg.precise) MSQ_TRY(refresh_wT<float>(m, ts, st));
+  else MSQ_TRY(refresh_wT<bf16>(m, ts, st));
+  return heads_train_setup(m, false, st);
+}
+
+extern "C" int msq_train_step(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev, const int64_t* sep_dev,
+                              int64_t B, int32_t N, int32_t Lt, const float* images_dev, int64_t n_img, const int32_t* img_index_dev,
+                              const int32_t* ground_truth_dev, const int64_t* pairwise_labels_dev, float lam, float* grads_dev, float* loss_dev,
+                              void* stream) {
+  MSQ_REQUIRE(m && ids_dev && tt_dev && mask_dev && sep_dev && ground_truth_dev && pairwise_labels_dev && grads_dev, "null argument");
+  MSQ_REQUIRE(((uintptr_t)grads_dev & 255) == 0, "msq_train_step: the gradient buffer must be 256-byte aligned");
+  MSQ_REQUIRE(B >= 1 && N >= 2 && N <= 16, "msq_train_step: B=%lld N=%d", (long long)B, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  MSQ_TRY(ensure_train(m, st));
+  MSQ_REQUIRE(m->train->heads, "msq_train_step: the model has no BERSON head weights");
+  MSQ_REQUIRE(m->cfg.vit_width == 0 || images_dev, "msq_train_step: multimodal model needs images");
+  const int64_t R = B * N * (N - 1);
+  if (m->cfg.precise) {
+    MSQ_TRY(forward_train<float>(m, ids_dev, tt_dev, mask_dev, R, Lt, images_dev, n_img, img_index_dev, nullptr, nullptr, st));
+    MSQ_TRY(heads_train<float>(m, sep_dev, B, N, ground_truth_dev, pairwise_labels_dev, lam, grads_dev, loss_dev, st));
+    return backward_train<float>(m, m->train->ht.d_lang, nullptr, grads_dev, st);
+  }
+  MSQ_TRY(forward_train<bf16>(m, ids_dev, tt_dev, mask_dev, R, Lt, images_dev, n_img, img_index_dev, nullptr, nullptr, st));
+  MSQ_TRY(heads_train<bf16>(m, sep_dev, B, N, ground_truth_dev, pairwise_labels_dev, lam, grads_dev, loss_dev, st));
+  return backward_train<bf16>(m, m->train->ht.d_lang, nullptr, grads_dev, st);
 }

@@ -1,0 +1,115 @@
+// Shared pieces of the fine-tuning path (train.cu: inner encoder; train_heads.cu: BERSON heads + loss).
+#pragma once
+#include <array>
+#include <math.h>
+
+#include "model.cuh"
+
+namespace msq {
+
+struct ParamSlot { std::string name; int64_t off = 0, numel = 0; float* master = nullptr; bool decay = true; };
+struct BertTape { void *x, *qkv, *ctx, *x1, *u; float *s1, *s2; };
+struct VitTape { float *x, *x1; void *y1, *qkv, *ctx, *y2, *u; };
+
+struct ParaTape { float *xin, *y, *qkv, *ctx, *out, *pn, *u, *xo; };
+struct HeadTape {
+  int64_t B = 0;
+  int N = 0;
+  void *topt = nullptr, *ttb = nullptr;                       // operand type [R*Lt, H]
+  float *mix, *rel6, *sents, *r0, *para, *h0, *keyin, *key, *sents_ext, *xg, *t4, *act, *c_all, *hs, *hprev, *query, *nll, *d_lang;
+  std::vector<ParaTape> pl;
+};
+
+struct TrainState {
+  std::vector<ParamSlot> slots;
+  std::unordered_map<std::string, size_t> index;
+  int64_t total = 0;
+  float *adam_m = nullptr, *adam_v = nullptr, *opt_scratch = nullptr;
+  int64_t step = 0;
+  // W^T copies in the GEMM operand type: [qkv, out, up, down] per BERT layer, [qkv, out, fc, proj] per ViT layer
+  std::vector<std::array<void*, 4>> bertT, vitT;
+  void* visnT = nullptr;
+  std::vector<void*> owned;
+  Arena tape;
+  // ---- record of the last training forward
+  bool have_fwd = false, mm = false;
+  int64_t R = 0, n_img = 0;
+  int Lt = 0, Lv = 0, Lj = 0;
+  const float* images = nullptr;   // caller-owned; must stay valid until msq_inner_backward returns
+  int64_t *ids = nullptr, *tt = nullptr;
+  int32_t* img_index = nullptr;
+  float *mask_add = nullptr, *patch = nullptr, *vx_last = nullptr, *visn_pre = nullptr;
+  void *x_last = nullptr, *y_post = nullptr;
+  std::vector<BertTape> bt;
+  std::vector<VitTape> vt;
+  float* x_out = nullptr;          // final joint stream [R*Lj, H] fp32 (what the heads read)
+  // ---- BERSON heads (train_heads.cu)
+  bool heads = false;                            // head parameters are part of the table
+  std::vector<std::array<float*, 4>> paraT;      // fp32 W^T of [qkv, fin, w1, w2] per paragraph layer
+  void* sentT = nullptr;                         // sentence_tran W^T (operand type)
+  float *keyT = nullptr, *wqT = nullptr, *whhT = nullptr, *wihT = nullptr, *pw4T = nullptr;
+  Arena htape;
+  HeadTape ht;
+};
+
+inline void train_state_free_impl(TrainState* ts) {
+  if (!ts) return;
+  for (void* p : ts->owned) cudaFree(p);
+  if (ts->adam_m) cudaFree(ts->adam_m);
+  if (ts->adam_v) cudaFree(ts->adam_v);
+  if (ts->opt_scratch) cudaFree(ts->opt_scratch);
+  if (ts->tape.base) cudaFree(ts->tape.base);
+  if (ts->htape.base) cudaFree(ts->htape.base);
+  delete ts;
+}
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+constexpr int64_t TRAIN_IMG_CHUNK = 1024;
+
+template <typename T> inline const T* wptr(const Lin& l);
+template <> inline const float* wptr<float>(const Lin& l) { return l.w32; }
+template <> inline const bf16* wptr<bf16>(const Lin& l) { return l.w16; }
+
+// C[M,N] = act(A[M,K] W[N,K]^T + bias) + resid on the model's GEMM path (tcgen05 when available and aligned)
+template <typename T, typename TO>
+static int gemm_nt(const msq_model* m, const T* A, int lda, const T* W, int ldw, const float* bias, const float* resid, int ldr, TO* C,
+                   int ldc, int64_t M, int N, int K, int act, cudaStream_t st) {
+  GemmArgs g;
+  g.A = A; g.W = W; g.bias = bias; g.resid = resid; g.C = C; g.C2 = nullptr;
+  g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldc = ldc; g.ldr = ldr; g.act = act;
+  if constexpr (sizeof(T) == 4) {
+    static_assert(sizeof(TO) == 4, "fp32 mode has fp32 outputs");
+    return gemm_simt<float, float>(g, st);
+  } else {
+    if (model_use_tc(m) && K % 64 == 0 && N % 8 == 0 && ldc % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0) return gemm_tc<TO>(g, st);
+    return gemm_simt<bf16, TO>(g, st);
+  }
+}
+
+struct BwdBufs { float *gA, *gB, *ln_scr, *at_scr, *dpatch; void *gT, *gH, *gC, *gQ, *GT, *XT, *apatch; };
+
+// dW[Nout,Kin] += G^T X (act_x applied to X on the fly), db[Nout] += column sums of G
+template <typename T>
+static int wgrad(const msq_model* m, const T* G, int ldg, int Nout, const T* X, int ldx, int Kin, int act_x, int64_t M, float* dW, float* db,
+                 BwdBufs& b, cudaStream_t st) {
+  const int64_t Mp = round_up(M, 64);
+  MSQ_TRY((transpose_pad<T, T>(G, M, Nout, ldg, Mp, (T*)b.GT, ACT_NONE, st)));
+  MSQ_TRY((transpose_pad<T, T>(X, M, Kin, ldx, Mp, (T*)b.XT, act_x, st)));
+  MSQ_TRY((gemm_nt<T, float>(m, (const T*)b.GT, (int)Mp, (const T*)b.XT, (int)Mp, nullptr, dW, Kin, dW, Kin, Nout, Kin, (int)Mp, ACT_NONE, st)));
+  if (db) MSQ_TRY(rowsum_accum<T>((const T*)b.GT, Nout, Mp, Mp, db, st));
+  return MSQ_OK;
+}
+// dX[M,Kin] = G[M,Nout] W  (+ resid), W^T given as [Kin, Nout]
+template <typename T, typename TO>
+static int dgrad(const msq_model* m, const T* G, int Nout, const void* WT, int Kin, const float* resid, TO* dX, int64_t M, cudaStream_t st) {
+  return gemm_nt<T, TO>(m, G, Nout, (const T*)WT, Nout, nullptr, resid, Kin, dX, Kin, M, Kin, Nout, ACT_NONE, st);
+}
+
+// ---- train_heads.cu
+int heads_train_setup(msq_model* m, bool alloc, cudaStream_t st);
+std::vector<std::string> heads_param_names(const msq_model* m);
+template <typename T>
+int heads_train(msq_model* m, const int64_t* sep, int64_t B, int N, const int32_t* target, const int64_t* pair_labels, float lam, float* grads,
+                float* loss_out, cudaStream_t st);
+
+}  // namespace msq

@@ -323,6 +323,22 @@ class OrderingEngine:
         _lib.check(self.lib.msq_train_read_param(self._h, name.encode(), self._p(out), out.numel(), self._stream()))
         return out
 
+    def train_step(self, batch: PairBatch, grads, lam=0.6):
+        """One fine-tuning forward + backward of BertForOrdering._forward's default objective (modeling_bert.py:943-1174:
+        pointer NLL / (N-1) + lam * pairwise NLL / P, batch mean): grads += dL/dparam for every parameter of the path
+        (encoder and heads).  Returns the loss as a 0-d device tensor.  Follow with adamw_step(grads, ...)."""
+        b = batch.to(self.device)
+        B, P, Lt = b.input_ids.shape
+        gt = b.ground_truth.to(torch.int32).contiguous()
+        loss = torch.zeros(1, device=self.device)
+        n_img = 0 if b.images is None else b.images.shape[0]
+        self._train_keep = (b, gt)
+        _lib.check(self.lib.msq_train_step(self._h, self._p(b.input_ids), self._p(b.token_type_ids), self._p(b.attention_mask),
+                                           self._p(b.sep_positions), B, b.n_steps, Lt, self._p(b.images), n_img, self._p(b.img_index),
+                                           self._p(gt), self._p(b.pairwise_labels.contiguous()), float(lam), self._p(grads),
+                                           self._p(loss), self._stream()))
+        return loss[0]
+
     def training_loss(self, batch: PairBatch, lam=0.6):
         """BertForOrdering._forward loss value (modeling_bert.py:943-1174), forward only -> 0-d device tensor."""
         b = batch.to(self.device)

@@ -51,17 +51,21 @@ def _case(g, multimodal, R, seed):
     return ids, labels, images
 
 
+# biases that only shift all logits of a softmax: attention key biases, the token-score bias, the pointer-score bias
+_ZERO_GRAD = ("attention.self.key.bias", "self_attn.linear_keys.bias", "tanh_linear.bias", "sentence_tran_2.bias")
+
+
 def _compare(got, ref, tol, skip=()):
     worst = ("", 0.0)
+    gmax = max(float(r.float().norm()) for r in ref.values())
     for n, r in ref.items():
         if n not in got or any(s in n for s in skip):
             continue
         a, b = got[n].detach().float().cpu().reshape(-1), r.float().reshape(-1)
-        if n.endswith("attention.self.key.bias"):
-            # softmax is invariant to a shift of every key score, so this gradient is exactly zero: both sides hold
-            # rounding noise only.  Bound it against the query bias gradient of the same layer.
-            q = ref[n.replace("key.bias", "query.bias")].float().norm()
-            assert float(a.norm()) <= 50 * tol * float(q) + 1e-6, "%s: %.3e vs |dq bias| %.3e" % (n, float(a.norm()), float(q))
+        if n.endswith(_ZERO_GRAD):
+            # softmax is invariant to a constant added to every score, so these gradients are exactly zero and both sides
+            # hold rounding noise only: bound the noise against the largest gradient of the model.
+            assert float(a.norm()) <= tol * gmax + 1e-6, "%s: %.3e vs largest gradient norm %.3e" % (n, float(a.norm()), gmax)
             continue
         err = float((a - b).norm() / (b.norm() + 1e-12)) if float(b.norm()) > 1e-9 else float((a - b).norm())
         if err > worst[1]:
@@ -95,7 +99,7 @@ def test_text_encoder_backward_vs_oracle_autograd(golden_dir, precise):
     eng, grads, lang, _, olang, _, ref, _ = _run(g, False, precise)
     tol_f, tol_g = (2e-5, 2e-4) if precise else (3e-2, 6e-2)
     assert (lang.cpu() - olang).abs().max() <= tol_f * max(1.0, float(olang.abs().max()))
-    got = eng.grads_by_name(grads)
+    got = {n: v for n, v in eng.grads_by_name(grads).items() if n.startswith("bert.")}   # the heads take no part here
     assert set(got) <= set(ref) | {"bert.pooler.dense.weight", "bert.pooler.dense.bias"}
     worst = _compare(got, ref, tol_g)
     print("text backward (%s): worst relative L2 %.2e at %s" % ("fp32" if precise else "bf16", worst[1], worst[0]))
@@ -111,7 +115,7 @@ def test_multimodal_encoder_backward_vs_oracle_autograd(golden_dir, precise):
     tol_f, tol_g = (4e-5, 3e-4) if precise else (3e-2, 8e-2)
     assert (lang.cpu() - olang).abs().max() <= tol_f * max(1.0, float(olang.abs().max()))
     assert (visn.cpu() - ovisn).abs().max() <= tol_f * max(1.0, float(ovisn.abs().max()))
-    got = eng.grads_by_name(grads)
+    got = {n: v for n, v in eng.grads_by_name(grads).items() if n.startswith("bert.")}   # the heads take no part here
     names = [n for n in got if n in ref]
     assert len(names) == len(got), sorted(set(got) - set(ref))
     worst = _compare(got, ref, tol_g)
@@ -183,3 +187,70 @@ def test_backward_without_forward_fails(golden_dir):
     grads = eng.new_grad_buffer()
     with pytest.raises(RuntimeError):
         eng.inner_backward(torch.zeros(1, 4, 128), None, grads)
+
+
+# ---- full fine-tuning step: loss + gradients of EVERY parameter (encoder and BERSON heads) -----------------------------
+def _full_step(g, multimodal, precise, B, N, L, seed):
+    eng = _engine(g["sd"], _cfg_from_golden(g), precise)
+    ids, labels, images = O.synthetic_manuals(B, N, L, vocab=1000, image_px=224 if multimodal else None, seed=seed)
+    pb = eng.prepare(ids, labels, N, images)
+    grads = eng.new_grad_buffer()
+    loss = eng.train_step(pb, grads)
+    torch.cuda.synchronize()
+    oloss, ref = TO.loss_grads(g["sd"], _ocfg(g), O.prepare_inputs(ids, labels, N, images))
+    return eng, pb, grads, float(loss), oloss, ref
+
+
+@pytest.mark.parametrize("precise", [True, False])
+def test_text_train_step_vs_reference_pinned_oracle(golden_dir, precise):
+    """Same batch as the reference-generated gradient fixture (grads_tiny.pt 'text': 3 five-step manuals)."""
+    g = torch.load(os.path.join(golden_dir, "text_tiny.pt"), weights_only=False)
+    r = torch.load(os.path.join(golden_dir, "grads_tiny.pt"), weights_only=False)["text"]
+    eng, pb, grads, loss, oloss, ref = _full_step(g, False, precise, r["B"], r["N"], r["L"], r["seed"])
+    assert abs(oloss - r["loss"]) < 2e-5                      # the oracle reproduces the reference's loss ...
+    assert abs(loss - r["loss"]) < (5e-5 if precise else 2e-2)     # ... and so does the CUDA path
+    got = eng.grads_by_name(grads)
+    assert set(got) == set(r["grads"]) - {"bert.pooler.dense.weight", "bert.pooler.dense.bias"}, sorted(set(got) ^ set(r["grads"]))
+    worst = _compare(got, ref, 5e-4 if precise else 1e-1)
+    print("text train step (%s): loss %.6f (reference %.6f), worst relative L2 %.2e at %s" %
+          ("fp32" if precise else "bf16", loss, r["loss"], worst[1], worst[0]))
+    if precise:   # directly against the reference's own numbers (norms + strided samples)
+        for n, s in r["grads"].items():
+            if n not in got:
+                continue
+            a = got[n].detach().double().cpu().reshape(-1)
+            assert abs(float(a.norm()) - s["norm"]) <= 1e-3 * s["norm"] + 1e-7, n
+            assert (a[s["idx"]].float() - s["val"]).abs().max() <= 1e-3 * s["norm"] / max(s["numel"], 1) ** 0.5 + 1e-5 * float(s["val"].abs().max()) + 1e-7, n
+
+
+@pytest.mark.parametrize("precise", [True, False])
+def test_multimodal_train_step_vs_reference_pinned_oracle(golden_dir, precise):
+    g = torch.load(os.path.join(golden_dir, "mm_tiny.pt"), weights_only=False)
+    r = torch.load(os.path.join(golden_dir, "grads_tiny.pt"), weights_only=False)["mm"]
+    eng, pb, grads, loss, oloss, ref = _full_step(g, True, precise, r["B"], r["N"], r["L"], r["seed"])
+    assert abs(oloss - r["loss"]) < 2e-5
+    assert abs(loss - r["loss"]) < (5e-5 if precise else 2e-2)
+    got = eng.grads_by_name(grads)
+    assert set(got) == set(r["grads"]) - {"bert.pooler.dense.weight", "bert.pooler.dense.bias"}, sorted(set(got) ^ set(r["grads"]))
+    worst = _compare(got, ref, 5e-4 if precise else 1e-1)
+    print("multimodal train step (%s): loss %.6f (reference %.6f), worst relative L2 %.2e at %s" %
+          ("fp32" if precise else "bf16", loss, r["loss"], worst[1], worst[0]))
+
+
+def test_fine_tuning_lowers_the_loss(golden_dir):
+    """Five optimizer steps on one batch: the loss the step reports must fall (end-to-end sign / wiring check), and the
+    eval-mode loss entry point must agree with the training one before and after."""
+    g = torch.load(os.path.join(golden_dir, "text_tiny.pt"), weights_only=False)
+    eng = _engine(g["sd"], _cfg_from_golden(g), True)
+    ids, labels, _ = O.synthetic_manuals(4, 5, 16, vocab=1000, seed=3)
+    pb = eng.prepare(ids, labels, 5, None)
+    losses = []
+    for step in range(5):
+        grads = eng.new_grad_buffer()
+        losses.append(float(eng.train_step(pb, grads)))
+        if step == 0:
+            assert abs(losses[0] - float(eng.training_loss(pb))) < 1e-5
+        eng.adamw_step(grads, 1e-3, max_grad_norm=1.0)
+    final = float(eng.training_loss(pb))
+    print("losses", losses, "final", final)
+    assert final < losses[0] - 0.05 and all(b < a + 1e-3 for a, b in zip(losses, losses[1:]))
