@@ -1,0 +1,269 @@
+// Attention backward on tensor cores for the bf16 fine-tuning path (autograd of BertAttention.forward,
+// models/CLIP/src/lxrt/modeling.py:398-425, and of nn.MultiheadAttention inside ResidualAttentionBlock,
+// models/CLIP/clip/model.py:204-226).  One CTA per (token group, head); Q, K, V and dO of the item (<= 256 tokens x 64)
+// live in shared memory as bf16; every contraction is mma.sync m16n8k16 (bf16 in, fp32 accumulate):
+//
+//   D_i   = dO_i . O_i                                  (row sums, computed while loading; O = saved context)
+//   pass A (a warp owns 16 query rows): S = scale Q K^T + mask twice -- once for the row log-sum-exp, once to form
+//          P = exp(S - lse), dP = dO V^T, dS = P (dP - D) in registers, fed straight back as the A operand of dQ += dS K
+//   pass B (a warp owns 16 key rows):   S^T, dP^T from (K, Q) and (V, dO), P^T / dS^T in registers,
+//          dV += P^T dO,  dK += dS^T Q
+// Nothing of size L x L touches shared or global memory.  (Not tcgen05: the item is 227 x 227 x 64 -- five small,
+// dependent GEMMs with a softmax between them -- and the accumulator-to-operand register reuse of mma.sync is what keeps
+// P and dS on chip without a TMEM round trip.  The fp32 parity mode keeps the CUDA-core kernels of train_kernels.cu.)
+#include "kernels.cuh"
+
+namespace msq {
+
+constexpr int ABM_LD = 72;      // bf16 elements per shared-memory row (64 + 8: conflict-free ldmatrix)
+constexpr int ABM_WARPS = 8;
+
+__device__ __forceinline__ void ldsm4(uint32_t* r, const bf16* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t* r, const bf16* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float dot8(uint4 a, uint4 b) {
+  const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 p = __bfloat1622float2(x[i]), q = __bfloat1622float2(y[i]);
+    s = fmaf(p.x, q.x, s);
+    s = fmaf(p.y, q.y, s);
+  }
+  return s;
+}
+
+// A operand (16 rows x 64) of row block rb: 4 k-steps x 4 registers
+__device__ __forceinline__ void load_a64(uint32_t (*a)[4], const bf16* M, int rb, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) ldsm4(a[ks], M + (rb * 16 + (lane & 15)) * ABM_LD + ks * 16 + (lane >> 4) * 8);
+}
+// acc[2][4] (16 x 16 tile) = A(16 x 64) * M[cb*16 .. +16][0..64)^T   (M rows are the n index, contiguous k)
+__device__ __forceinline__ void mma_nt16(float (*acc)[4], const uint32_t (*a)[4], const bf16* M, int cb, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[0][i] = acc[1][i] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t b[4];
+    ldsm4(b, M + (cb * 16 + (lane & 7) + ((lane >> 4) << 3)) * ABM_LD + ks * 16 + ((lane >> 3) & 1) * 8);
+    mma16816(acc[0], a[ks], b[0], b[1]);
+    mma16816(acc[1], a[ks], b[2], b[3]);
+  }
+}
+// acc[8][4] (16 x 64) += A(16 x 16, registers) * M[kb*16 .. +16][0..64)   (M rows are the k index)
+__device__ __forceinline__ void mma_nn64(float (*acc)[4], const uint32_t* a, const bf16* M, int kb, int lane) {
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) {
+    uint32_t b[4];
+    ldsm4t(b, M + (kb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ABM_LD + n2 * 16 + (lane >> 4) * 8);
+    mma16816(acc[2 * n2], a, b[0], b[1]);
+    mma16816(acc[2 * n2 + 1], a, b[2], b[3]);
+  }
+}
+
+__global__ void __launch_bounds__(ABM_WARPS * 32) attention_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ctx,
+                                                                           const bf16* __restrict__ dctx, int L, int Lp, int heads, float scale,
+                                                                           const float* __restrict__ mask_add, int mask_ld, int mask_len,
+                                                                           bf16* __restrict__ dqkv) {
+  pdl_sync();
+  extern __shared__ __align__(16) unsigned char smraw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smraw);
+  bf16* Ks = Qs + Lp * ABM_LD;
+  bf16* Vs = Ks + Lp * ABM_LD;
+  bf16* Gs = Vs + Lp * ABM_LD;                       // dO
+  float* Ms = reinterpret_cast<float*>(Gs + Lp * ABM_LD);   // additive key mask, -inf for the padded keys
+  float* Ds = Ms + Lp;                               // D_i
+  float* Ls = Ds + Lp;                               // row log-sum-exp
+  const int r = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int ld = 3 * heads * 64, ldc = heads * 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+
+  for (int base = 0; base < Lp * 8; base += ABM_WARPS * 32) {
+    const int idx = base + tid;
+    const bool in = idx < Lp * 8;
+    const int t = in ? idx >> 3 : 0, pc = idx & 7;
+    uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q, g = q;
+    float dpart = 0.f;
+    if (in && t < L) {
+      const bf16* src = qkv + ((int64_t)r * L + t) * ld + h * 64 + pc * 8;
+      q = *reinterpret_cast<const uint4*>(src);
+      k = *reinterpret_cast<const uint4*>(src + heads * 64);
+      v = *reinterpret_cast<const uint4*>(src + 2 * heads * 64);
+      const int64_t co = ((int64_t)r * L + t) * ldc + h * 64 + pc * 8;
+      g = *reinterpret_cast<const uint4*>(dctx + co);
+      dpart = dot8(g, *reinterpret_cast<const uint4*>(ctx + co));
+    }
+    if (in) {
+      const int so = t * ABM_LD + pc * 8;
+      *reinterpret_cast<uint4*>(Qs + so) = q;
+      *reinterpret_cast<uint4*>(Ks + so) = k;
+      *reinterpret_cast<uint4*>(Vs + so) = v;
+      *reinterpret_cast<uint4*>(Gs + so) = g;
+    }
+    dpart += __shfl_xor_sync(0xffffffffu, dpart, 1);
+    dpart += __shfl_xor_sync(0xffffffffu, dpart, 2);
+    dpart += __shfl_xor_sync(0xffffffffu, dpart, 4);
+    if (in && pc == 0) Ds[t] = dpart;
+  }
+  for (int t = tid; t < Lp; t += ABM_WARPS * 32)
+    Ms[t] = t < L ? ((mask_add && t < mask_len) ? mask_add[(int64_t)r * mask_ld + t] : 0.f) : -INFINITY;
+  __syncthreads();
+
+  const int nblk = Lp >> 4;
+  // ---------------- pass A: dQ, row statistics
+  for (int ib = warp; ib < nblk; ib += ABM_WARPS) {
+    uint32_t aq[4][4], ag[4][4];
+    load_a64(aq, Qs, ib, lane);
+    load_a64(ag, Gs, ib, lane);
+    float m[2] = {-INFINITY, -INFINITY}, s[2] = {0.f, 0.f};
+    for (int kb = 0; kb < nblk; ++kb) {
+      float acc[2][4];
+      mma_nt16(acc, aq, Ks, kb, lane);
+#pragma unroll
+      for (int hr = 0; hr < 2; ++hr) {          // hr: row gid (0) / gid + 8 (1)
+        float vals[4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) vals[nt * 2 + e] = fmaf(acc[nt][hr * 2 + e], scale, Ms[kb * 16 + nt * 8 + tig * 2 + e]);
+        const float um = fmaxf(fmaxf(vals[0], vals[1]), fmaxf(vals[2], vals[3]));
+        const float mn = fmaxf(m[hr], um);
+        if (mn > -INFINITY) {
+          s[hr] = s[hr] * __expf(m[hr] - mn) + (__expf(vals[0] - mn) + __expf(vals[1] - mn)) + (__expf(vals[2] - mn) + __expf(vals[3] - mn));
+          m[hr] = mn;
+        }
+      }
+    }
+    float lse[2], dd[2];
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m[hr], o), so = __shfl_xor_sync(0xffffffffu, s[hr], o);
+        const float mn = fmaxf(m[hr], mo);
+        if (mn > -INFINITY) {
+          s[hr] = s[hr] * __expf(m[hr] - mn) + so * __expf(mo - mn);
+          m[hr] = mn;
+        }
+      }
+      lse[hr] = m[hr] + __logf(s[hr]);
+      const int row = ib * 16 + gid + hr * 8;
+      dd[hr] = Ds[row];
+      if (tig == 0) Ls[row] = lse[hr];
+    }
+    float dq[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+    for (int kb = 0; kb < nblk; ++kb) {
+      float sa[2][4], dp[2][4];
+      mma_nt16(sa, aq, Ks, kb, lane);
+      mma_nt16(dp, ag, Vs, kb, lane);
+      uint32_t a[4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        float ds[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int hr = e >> 1;
+          const float p = __expf(fmaf(sa[nt][e], scale, Ms[kb * 16 + nt * 8 + tig * 2 + (e & 1)]) - lse[hr]);
+          ds[e] = p * (dp[nt][e] - dd[hr]);
+        }
+        a[nt * 2] = pack2(ds[0], ds[1]);
+        a[nt * 2 + 1] = pack2(ds[2], ds[3]);
+      }
+      mma_nn64(dq, a, Ks, kb, lane);
+    }
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int row = ib * 16 + gid + hr * 8;
+      if (row < L) {
+        bf16* op = dqkv + ((int64_t)r * L + row) * ld + h * 64 + tig * 2;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(op + nt * 8) = pack2(dq[nt][hr * 2] * scale, dq[nt][hr * 2 + 1] * scale);
+      }
+    }
+  }
+  __syncthreads();
+  // ---------------- pass B: dK, dV
+  for (int jb = warp; jb < nblk; jb += ABM_WARPS) {
+    uint32_t ak[4][4], av[4][4];
+    load_a64(ak, Ks, jb, lane);
+    load_a64(av, Vs, jb, lane);
+    const float mr[2] = {Ms[jb * 16 + gid], Ms[jb * 16 + gid + 8]};
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+    for (int qb = 0; qb < nblk; ++qb) {
+      float st[2][4], dp[2][4];
+      mma_nt16(st, ak, Qs, qb, lane);
+      mma_nt16(dp, av, Gs, qb, lane);
+      uint32_t pa[4], da[4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        float p[4], ds[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int qc = qb * 16 + nt * 8 + tig * 2 + (e & 1);
+          p[e] = __expf(fmaf(st[nt][e], scale, mr[e >> 1]) - Ls[qc]);
+          ds[e] = p[e] * (dp[nt][e] - Ds[qc]);
+        }
+        pa[nt * 2] = pack2(p[0], p[1]); pa[nt * 2 + 1] = pack2(p[2], p[3]);
+        da[nt * 2] = pack2(ds[0], ds[1]); da[nt * 2 + 1] = pack2(ds[2], ds[3]);
+      }
+      mma_nn64(dv, pa, Gs, qb, lane);
+      mma_nn64(dk, da, Qs, qb, lane);
+    }
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int row = jb * 16 + gid + hr * 8;
+      if (row < L) {
+        bf16* op = dqkv + ((int64_t)r * L + row) * ld + heads * 64 + h * 64 + tig * 2;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          *reinterpret_cast<uint32_t*>(op + nt * 8) = pack2(dk[nt][hr * 2] * scale, dk[nt][hr * 2 + 1] * scale);
+          *reinterpret_cast<uint32_t*>(op + heads * 64 + nt * 8) = pack2(dv[nt][hr * 2], dv[nt][hr * 2 + 1]);
+        }
+      }
+    }
+  }
+}
+
+bool attention_bwd_mma_supported(int L) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("MSQ_ATTN_BWD_SIMT"); off = (e && e[0] == '1') ? 1 : 0; }
+  return !off && L >= 1 && L <= 256;
+}
+
+int attention_bwd_mma(const bf16* qkv, const bf16* ctx, const bf16* dctx, int64_t R, int L, int heads, float scale, const float* key_mask_add,
+                      int mask_ld, int mask_len, bf16* dqkv, cudaStream_t st) {
+  MSQ_REQUIRE(L >= 1 && L <= 256, "attention_bwd_mma: sequence length %d out of range", L);
+  MSQ_REQUIRE((((uintptr_t)qkv | (uintptr_t)ctx | (uintptr_t)dctx | (uintptr_t)dqkv) & 15) == 0, "attention_bwd_mma: unaligned pointer");
+  if (R == 0) return MSQ_OK;
+  const int Lp = (L + 15) & ~15;
+  const size_t smem = (size_t)4 * Lp * ABM_LD * sizeof(bf16) + (size_t)3 * Lp * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    MSQ_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  MSQ_CUDA(launch_k(attention_bwd_mma_kernel, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem, st, qkv, ctx, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+
+}  // namespace msq

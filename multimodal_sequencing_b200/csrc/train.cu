@@ -238,6 +238,16 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
 }
 
 // ---- backward --------------------------------------------------------------------------------------
+// attention backward: tensor cores (mma.sync) on the bf16 path, fp32 CUDA cores in the parity mode
+template <typename T>
+static int attn_bwd(const T* qkv, const T* ctx, const T* dctx, int64_t R, int L, int heads, const float* mask, int mask_len, T* dqkv, float* scratch,
+                    cudaStream_t st) {
+  if constexpr (sizeof(T) == 2) {
+    if (attention_bwd_mma_supported(L)) return attention_bwd_mma(qkv, ctx, dctx, R, L, heads, 0.125f, mask, mask_len, mask_len, dqkv, st);
+  }
+  return attention_bwd<T>(qkv, dctx, R, L, heads, 0.125f, mask, mask_len, mask_len, dqkv, scratch, st);
+}
+
 template <typename T>
 static int backward_train(msq_model* m, const float* d_lang, const float* d_visn, float* grads, cudaStream_t st) {
   TrainState* ts = m->train;
@@ -306,7 +316,7 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
     MSQ_TRY(ln_bwd<T>(b.gA, t.s1, nullptr, Mj, H, L.ln1.g, 1e-12f, b.gB, (T*)b.gT, dg1, db1, b.ln_scr, 0, 0, 0, st));
     MSQ_TRY(wgrad<T>(m, (const T*)b.gT, H, H, (const T*)t.ctx, H, H, ACT_NONE, Mj, dWo, dbo, b, st));
     MSQ_TRY((dgrad<T, T>(m, (const T*)b.gT, H, WT[1], H, nullptr, (T*)b.gC, Mj, st)));
-    MSQ_TRY(attention_bwd<T>((const T*)t.qkv, (const T*)b.gC, R, Lj, c.heads, 0.125f, ts->mask_add, Lt, Lt, (T*)b.gQ, b.at_scr, st));
+    MSQ_TRY(attn_bwd<T>((const T*)t.qkv, (const T*)t.ctx, (const T*)b.gC, R, Lj, c.heads, ts->mask_add, Lt, (T*)b.gQ, b.at_scr, st));
     MSQ_TRY(wgrad<T>(m, (const T*)b.gQ, 3 * H, 3 * H, (const T*)t.x, H, H, ACT_NONE, Mj, dWqkv, dbqkv, b, st));
     MSQ_TRY((dgrad<T, float>(m, (const T*)b.gQ, 3 * H, WT[0], H, b.gB, b.gA, Mj, st)));        // dX0 = dqkv Wqkv + ds1
   }
@@ -354,7 +364,7 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
     MSQ_TRY(ln_bwd<T>(b.gA, t.x1, b.gB, Mv, Wd, L.ln2.g, 1e-5f, b.gB, (T*)b.gT, dg2, db2, b.ln_scr, 0, 0, 0, st));   // dx1 = dx + LN'
     MSQ_TRY(wgrad<T>(m, (const T*)b.gT, Wd, Wd, (const T*)t.ctx, Wd, Wd, ACT_NONE, Mv, dWo, dbo, b, st));
     MSQ_TRY((dgrad<T, T>(m, (const T*)b.gT, Wd, WT[1], Wd, nullptr, (T*)b.gC, Mv, st)));
-    MSQ_TRY(attention_bwd<T>((const T*)t.qkv, (const T*)b.gC, R, Lv, vheads, 0.125f, nullptr, 0, 0, (T*)b.gQ, b.at_scr, st));
+    MSQ_TRY(attn_bwd<T>((const T*)t.qkv, (const T*)t.ctx, (const T*)b.gC, R, Lv, vheads, nullptr, 0, (T*)b.gQ, b.at_scr, st));
     MSQ_TRY(wgrad<T>(m, (const T*)b.gQ, 3 * Wd, 3 * Wd, (const T*)t.y1, Wd, Wd, ACT_NONE, Mv, dWqkv, dbqkv, b, st));
     MSQ_TRY((dgrad<T, float>(m, (const T*)b.gQ, 3 * Wd, WT[0], Wd, nullptr, b.gA, Mv, st)));      // d(ln_1 out)
     MSQ_TRY(ln_bwd<T>(b.gA, t.x, b.gB, Mv, Wd, L.ln1.g, 1e-5f, b.gB, (T*)b.gT, dg1, db1, b.ln_scr, 0, 0, 0, st));    // dx = dx1 + LN'

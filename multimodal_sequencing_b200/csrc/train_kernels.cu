@@ -36,10 +36,48 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(const TI* __restrict
     if (n < N && m < Mp) dst[(int64_t)n * Mp + m] = from_f<TO>(tile[tx][j]);
   }
 }
+// bf16 -> bf16, 64 x 64 tiles: every global access of a warp is a full 128-byte line (bf16 pairs per lane both ways)
+__global__ void __launch_bounds__(256) transpose_pad_bf16_kernel(const bf16* __restrict__ src, int64_t M, int N, int ld, int64_t Mp,
+                                                                 bf16* __restrict__ dst, int act) {
+  pdl_sync();
+  __shared__ float tile[64][65];   // [n][m]
+  const int64_t m0 = (int64_t)blockIdx.x * 64;
+  const int n0 = blockIdx.y * 64;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int mi = i * 8 + w;
+    const int64_t m = m0 + mi;
+    const int n = n0 + 2 * lane;
+    float a = 0.f, b = 0.f;
+    if (m < M && n < N) {   // N is even: the pair is inside or outside as a whole
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + m * ld + n));
+      a = apply_act(v.x, act); b = apply_act(v.y, act);
+    }
+    tile[2 * lane][mi] = a;
+    tile[2 * lane + 1][mi] = b;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ni = i * 8 + w;
+    const int n = n0 + ni;
+    const int64_t m = m0 + 2 * lane;
+    if (n < N && m < Mp) *reinterpret_cast<__nv_bfloat162*>(dst + (int64_t)n * Mp + m) = __floats2bfloat162_rn(tile[ni][2 * lane], tile[ni][2 * lane + 1]);
+  }
+}
+
 template <typename TI, typename TO>
 int transpose_pad(const TI* src, int64_t M, int N, int ld, int64_t Mp, TO* dst, int act, cudaStream_t st) {
   MSQ_REQUIRE(Mp >= M && ceil_div(N, 32) <= 65535, "transpose_pad: bad shape");
   if (Mp == 0 || N == 0) return MSQ_OK;
+  if constexpr (sizeof(TI) == 2 && sizeof(TO) == 2) {
+    if (N % 2 == 0 && ld % 2 == 0 && Mp % 2 == 0 && (((uintptr_t)src | (uintptr_t)dst) & 3) == 0) {
+      MSQ_CUDA(launch_k(transpose_pad_bf16_kernel, dim3((unsigned)ceil_div(Mp, 64), (unsigned)ceil_div(N, 64)), dim3(256), 0, st, (const bf16*)src, M, N, ld, Mp, (bf16*)dst, act));
+      MSQ_LAUNCH_CHECK();
+      return MSQ_OK;
+    }
+  }
   MSQ_CUDA(launch_k(transpose_pad_kernel<TI, TO>, dim3((unsigned)ceil_div(Mp, 32), (unsigned)ceil_div(N, 32)), dim3(256), 0, st, src, M, N, ld, Mp, dst, act));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;

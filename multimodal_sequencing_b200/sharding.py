@@ -32,3 +32,14 @@ def merge_predictions(local_perm, local_idx, n_manuals, group=None):
         out[g[keep, 0].long()] = g[keep, 1:]
     assert (out >= 0).all(), "some manuals were not ordered by any rank"
     return out
+
+
+def allreduce_gradients(flat_grads, group=None):
+    """Data-parallel fine-tuning (BASELINE configs[3]): every rank holds the gradients of its own manuals in ONE flat fp32
+    buffer (OrderingEngine.new_grad_buffer), so the whole exchange is a single all-reduce (NCCL over NVLink on the GPU
+    box, gloo in the CPU tests).  Sums in place and returns the factor that turns the sum into the mean over ranks --
+    pass it to adamw_step(grad_scale=...), which folds it into the clip coefficient instead of spending a pass on it."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / world
