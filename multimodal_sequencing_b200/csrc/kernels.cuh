@@ -159,6 +159,9 @@ int mask_add_from_int(const int64_t* mask, int64_t n, float* out, cudaStream_t s
 int scatter_rows(const float* src, int64_t rows, int H, int group, int dst_group, int off, float* dst, cudaStream_t st);
 size_t grad_norm_scratch_floats();
 int grad_norm_clip(const float* g, int64_t n, float max_norm, float grad_scale, float* scratch, cudaStream_t st);
+struct AdamChunk { float* p; int64_t off; int32_t n; int32_t decay; };
+int adamw_update_multi(const AdamChunk* chunks_dev, int nchunks, const float* g, float* m, float* v, float lr, float b1, float b2, float eps, float wd,
+                       int64_t step, const float* coef, cudaStream_t st);
 int adamw_update(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float wd, int64_t step,
                  const float* coef, cudaStream_t st);
 

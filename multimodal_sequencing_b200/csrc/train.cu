@@ -448,14 +448,21 @@ extern "C" int msq_adamw_step(msq_model* m, const float* grads_dev, float lr, fl
     MSQ_CUDA(cudaMalloc(&ts->opt_scratch, grad_norm_scratch_floats() * sizeof(float)));
     MSQ_CUDA(cudaMemsetAsync(ts->adam_m, 0, (size_t)ts->total * sizeof(float), st));
     MSQ_CUDA(cudaMemsetAsync(ts->adam_v, 0, (size_t)ts->total * sizeof(float), st));
+    std::vector<AdamChunk> ch;
+    constexpr int64_t CH = 16384;
+    for (const ParamSlot& s : ts->slots)
+      for (int64_t o = 0; o < s.numel; o += CH) ch.push_back(AdamChunk{s.master + o, s.off + o, (int32_t)min(CH, s.numel - o), s.decay ? 1 : 0});
+    ts->n_chunks = (int)ch.size();
+    MSQ_CUDA(cudaMalloc(&ts->adam_chunks, ch.size() * sizeof(AdamChunk)));
+    MSQ_CUDA(cudaMemcpyAsync(ts->adam_chunks, ch.data(), ch.size() * sizeof(AdamChunk), cudaMemcpyHostToDevice, st));
+    MSQ_CUDA(cudaStreamSynchronize(st));   // `ch` is a host temporary
   }
   ++ts->step;
   // padding between slots is never written by the backward pass (the caller zeroes the buffer), so the norm over the
   // whole flat buffer is the norm over the parameters' gradients
   MSQ_TRY(grad_norm_clip(grads_dev, ts->total, max_grad_norm, grad_scale, ts->opt_scratch, st));
-  for (const ParamSlot& s : ts->slots)
-    MSQ_TRY(adamw_update(s.master, grads_dev + s.off, ts->adam_m + s.off, ts->adam_v + s.off, s.numel, lr, beta1, beta2, eps,
-                         s.decay ? weight_decay : 0.f, ts->step, ts->opt_scratch, st));
+  MSQ_TRY(adamw_update_multi(ts->adam_chunks, ts->n_chunks, grads_dev, ts->adam_m, ts->adam_v, lr, beta1, beta2, eps, weight_decay, ts->step,
+                             ts->opt_scratch, st));
   if (norm_out_dev) MSQ_CUDA(cudaMemcpyAsync(norm_out_dev, ts->opt_scratch, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // masters changed: rebuild the packed copies (fused QKV, bf16, folded LayerNorm, ...) and the W^T operands
   MSQ_TRY(model_repack(m, st));

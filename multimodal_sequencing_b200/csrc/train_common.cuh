@@ -25,6 +25,8 @@ struct TrainState {
   std::unordered_map<std::string, size_t> index;
   int64_t total = 0;
   float *adam_m = nullptr, *adam_v = nullptr, *opt_scratch = nullptr;
+  AdamChunk* adam_chunks = nullptr;   // device table for the single-launch update
+  int n_chunks = 0;
   int64_t step = 0;
   // W^T copies in the GEMM operand type: [qkv, out, up, down] per BERT layer, [qkv, out, fc, proj] per ViT layer
   std::vector<std::array<void*, 4>> bertT, vitT;
@@ -58,6 +60,7 @@ inline void train_state_free_impl(TrainState* ts) {
   if (ts->adam_m) cudaFree(ts->adam_m);
   if (ts->adam_v) cudaFree(ts->adam_v);
   if (ts->opt_scratch) cudaFree(ts->opt_scratch);
+  if (ts->adam_chunks) cudaFree(ts->adam_chunks);
   if (ts->tape.base) cudaFree(ts->tape.base);
   if (ts->htape.base) cudaFree(ts->htape.base);
   delete ts;

@@ -105,9 +105,38 @@ __global__ void __launch_bounds__(256) rowsum_accum_kernel(const T* __restrict__
     out[blockIdx.x] += t;
   }
 }
+// bf16 rows, 16-byte loads (the operand rows are 64-element aligned and zero padded)
+__global__ void __launch_bounds__(256) rowsum_accum_bf16v_kernel(const bf16* __restrict__ a, int64_t ld, int64_t n8, float* __restrict__ out) {
+  pdl_sync();
+  __shared__ float sh[8];
+  const uint4* r = reinterpret_cast<const uint4*>(a + (int64_t)blockIdx.x * ld);
+  float s0 = 0.f, s1 = 0.f;
+  for (int64_t i = threadIdx.x; i < n8; i += blockDim.x) {
+    const uint4 v = r[i];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+    const float2 a0 = __bfloat1622float2(h[0]), a1 = __bfloat1622float2(h[1]), a2 = __bfloat1622float2(h[2]), a3 = __bfloat1622float2(h[3]);
+    s0 += (a0.x + a0.y) + (a1.x + a1.y);
+    s1 += (a2.x + a2.y) + (a3.x + a3.y);
+  }
+  float s = warp_sum(s0 + s1);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    out[blockIdx.x] += t;
+  }
+}
 template <typename T>
 int rowsum_accum(const T* a, int rows, int64_t ld, int64_t n, float* out, cudaStream_t st) {
   if (rows == 0) return MSQ_OK;
+  if constexpr (sizeof(T) == 2) {
+    if (n % 8 == 0 && ld % 8 == 0 && ((uintptr_t)a & 15) == 0) {
+      MSQ_CUDA(launch_k(rowsum_accum_bf16v_kernel, dim3(rows), dim3(256), 0, st, (const bf16*)a, ld, n / 8, out));
+      MSQ_LAUNCH_CHECK();
+      return MSQ_OK;
+    }
+  }
   MSQ_CUDA(launch_k(rowsum_accum_kernel<T>, dim3(rows), dim3(256), 0, st, a, ld, n, out));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
@@ -281,14 +310,25 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) ln_bwd_kernel(const float* __r
   ln_bwd_flush(sh, ag, ab, nv, H, partial);
 }
 
+// block = 32 columns x 8 groups of partial blocks; the groups' sums are combined in index order (deterministic)
 __global__ void __launch_bounds__(256) ln_partial_reduce_kernel(const float* __restrict__ partial, int nblk, int H,
                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta) {
   pdl_sync();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * H) return;
+  __shared__ float sh[8][33];
+  const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += partial[(int64_t)b * 2 * H + c];
-  if (c < H) dgamma[c] += s; else dbeta[c - H] += s;
+  if (c < 2 * H) {
+    const int per = (nblk + 7) / 8, b0 = grp * per, b1 = min(nblk, b0 + per);
+    for (int b = b0; b < b1; ++b) s += partial[(int64_t)b * 2 * H + c];
+  }
+  sh[grp][cl] = s;
+  __syncthreads();
+  if (grp == 0 && c < 2 * H) {
+    float t = 0.f;
+    for (int g = 0; g < 8; ++g) t += sh[g][cl];
+    if (c < H) dgamma[c] += t; else dbeta[c - H] += t;
+  }
 }
 
 static inline int lnb_blocks(int64_t rows) { return (int)min((int64_t)148 * 4, (rows + LNB_WARPS - 1) / LNB_WARPS); }
@@ -302,7 +342,7 @@ int ln_bwd(const float* dy, const float* x, const float* add, int64_t rows, int 
   const int nblk = lnb_blocks(rows);
   MSQ_CUDA(launch_k(ln_bwd_kernel<T>, dim3(nblk), dim3(LNB_WARPS * 32), 0, st, dy, x, add, rows, H, gamma, eps, dx, dx_t, scratch, in_group, out_group, out_off));
   MSQ_LAUNCH_CHECK();
-  MSQ_CUDA(launch_k(ln_partial_reduce_kernel, dim3(ceil_div(2 * H, 256)), dim3(256), 0, st, (const float*)scratch, nblk, H, dgamma, dbeta));
+  MSQ_CUDA(launch_k(ln_partial_reduce_kernel, dim3(ceil_div(2 * H, 32)), dim3(256), 0, st, (const float*)scratch, nblk, H, dgamma, dbeta));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -368,7 +408,7 @@ int embed_ln_bwd(const float* dy, const int64_t* ids, const int64_t* tts, int64_
   const int nblk = lnb_blocks(R * Lt);
   MSQ_CUDA(launch_k(embed_ln_bwd_kernel, dim3(nblk), dim3(LNB_WARPS * 32), 0, st, dy, ids, tts, R, Lt, Lj, H, word, pos, type, gamma, eps, dword, dpos, dtype, scratch, pad0));
   MSQ_LAUNCH_CHECK();
-  MSQ_CUDA(launch_k(ln_partial_reduce_kernel, dim3(ceil_div(2 * H, 256)), dim3(256), 0, st, (const float*)scratch, nblk, H, dgamma, dbeta));
+  MSQ_CUDA(launch_k(ln_partial_reduce_kernel, dim3(ceil_div(2 * H, 32)), dim3(256), 0, st, (const float*)scratch, nblk, H, dgamma, dbeta));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -434,7 +474,7 @@ int vit_assemble_bwd(const float* dy, const float* patch, const int32_t* img_ind
   const int nblk = lnb_blocks(R * (1 + il * g2));
   MSQ_CUDA(launch_k(vit_assemble_bwd_kernel, dim3(nblk), dim3(LNB_WARPS * 32), 0, st, dy, patch, img_index, R, il, g2, W, cls, pos, gamma, eps, dpatch, dcls, dpos, scratch));
   MSQ_LAUNCH_CHECK();
-  MSQ_CUDA(launch_k(ln_partial_reduce_kernel, dim3(ceil_div(2 * W, 256)), dim3(256), 0, st, (const float*)scratch, nblk, W, dgamma, dbeta));
+  MSQ_CUDA(launch_k(ln_partial_reduce_kernel, dim3(ceil_div(2 * W, 32)), dim3(256), 0, st, (const float*)scratch, nblk, W, dgamma, dbeta));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -746,6 +786,35 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     p[i] = pi;
   }
 }
+// all parameters in ONE launch: block b owns chunk b = (master pointer, offset into the flat buffers, length, decays?)
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamChunk* __restrict__ chunks, const float* __restrict__ g, float* __restrict__ m,
+                                                          float* __restrict__ v, float lr, float b1, float b2, float eps, float wd, float step_size,
+                                                          const float* __restrict__ coef) {
+  pdl_sync();
+  const AdamChunk ch = chunks[blockIdx.x];
+  const float c = coef ? coef[1] : 1.f;
+  const float w = ch.decay ? wd : 0.f;
+  for (int i = threadIdx.x; i < ch.n; i += blockDim.x) {
+    const int64_t o = ch.off + i;
+    const float gi = g[o] * c;
+    const float mi = b1 * m[o] + (1.f - b1) * gi;
+    const float vi = b2 * v[o] + (1.f - b2) * gi * gi;
+    m[o] = mi; v[o] = vi;
+    float pi = ch.p[i] - step_size * (mi / (sqrtf(vi) + eps));
+    if (w != 0.f) pi -= lr * w * pi;
+    ch.p[i] = pi;
+  }
+}
+int adamw_update_multi(const AdamChunk* chunks_dev, int nchunks, const float* g, float* m, float* v, float lr, float b1, float b2, float eps, float wd,
+                       int64_t step, const float* coef, cudaStream_t st) {
+  if (nchunks == 0) return MSQ_OK;
+  const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+  const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
+  MSQ_CUDA(launch_k(adamw_multi_kernel, dim3(nchunks), dim3(256), 0, st, chunks_dev, g, m, v, lr, b1, b2, eps, wd, step_size, coef));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+
 int adamw_update(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float wd, int64_t step,
                  const float* coef, cudaStream_t st) {
   if (n == 0) return MSQ_OK;

@@ -3,8 +3,12 @@ HierarchicalAttention (parameter holder), BertForOrdering, berson_pointer_networ
 
 Same constructors, forward signatures and state_dict keys; the arithmetic runs in
 libmsq_b200.so through multimodal_sequencing_b200.OrderingEngine.  Reference lines are cited per method.
-Training (`forward` -> loss, modeling_bert.py:943-1237) is a later row of the scope table and raises."""
+Training: `forward(inputs)` in train() mode returns a loss whose .backward() fills p.grad of every nn.Parameter with the
+gradients the CUDA backward pass produced (msq_train_step), so trainers/train.py:340-363 (loss.backward();
+clip_grad_norm_(model.parameters()); optimizer.step(); model.zero_grad()) runs unchanged; `finetune_step` is the fused
+device-side alternative (clip + transformers.AdamW inside the library, no weight round trip).  Dropout is not applied."""
 import types
+import warnings
 
 import torch
 import torch.nn as nn
@@ -90,6 +94,23 @@ class _EngineOwner:
                                  precise=bool(getattr(self, "precise", False)))
             self.__dict__["_eng"], self.__dict__["_eng_sig"] = eng, sig
         return eng
+
+
+class _DeviceBackward(torch.autograd.Function):
+    """Bridge between the device-side backward pass and torch.autograd: forward passes the loss through, backward hands
+    every parameter its slice of the flat gradient buffer (scaled by the incoming gradient, e.g. 1 / accumulation steps)."""
+
+    @staticmethod
+    def forward(ctx, loss, flat, spans, *params):
+        ctx.flat, ctx.spans, ctx.shapes = flat, spans, [p.shape for p in params]
+        return loss.detach().clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        out = [None, None, None]
+        for span, shp in zip(ctx.spans, ctx.shapes):
+            out.append(None if span is None else ctx.flat[span[0]:span[0] + span[1]].reshape(shp) * g)
+        return tuple(out)
 
 
 class BertModel(nn.Module, _EngineOwner):
@@ -222,30 +243,85 @@ class BertForOrdering(nn.Module, _EngineOwner):
                 torch.cat((cls_output_matrix_nn, torch.softmax(cls_score_matrix_nn_his2, -1)), -1))
 
     def forward(self, inputs):
-        """modeling_bert.py:937-941 -> (loss,).  The loss VALUE (pointer NLL + lam * pairwise NLL, 943-1174) is
-        computed on the device, forward only: there is no backward in this build, so calling
-        it in train() mode raises instead of silently not learning."""
-        if self.training:
-            raise NotImplementedError("backward / fine-tuning is a later row of the scope table (SURVEY.md §8(f).2); "
-                                      "call model.eval() to obtain the validation loss")
+        """modeling_bert.py:937-941 -> (loss,): pointer NLL / (N-1) + lam * pairwise NLL / P (943-1174).  eval(): the loss
+        value only.  train(): the value AND the whole backward pass run on the device (msq_train_step); the returned tensor
+        carries an autograd node that hands those gradients to p.grad when the caller does loss.backward()."""
         berson_inputs = inputs
         if getattr(self, "tokenizer", None) is not None:
             berson_inputs = prepare_berson_inputs(berson_inputs, self.tokenizer, args=self.args)
         return self._forward(**berson_inputs)
 
+    def _pair_batch(self, input_ids, attention_mask, token_type_ids, pairs_list, passage_length, sep_positions, ground_truth,
+                    pairwise_labels, images, _pair_batch):
+        if _pair_batch is not None:
+            return _pair_batch
+        B, P, Lt = input_ids.shape
+        img = idx = None
+        if images is not None:
+            img = images.reshape(B * P * 2, *images.shape[3:])
+            idx = torch.arange(B * P * 2, dtype=torch.int32).reshape(B, P, 2)
+        return PairBatch(input_ids, attention_mask, token_type_ids, sep_positions, pairs_list, pairwise_labels, ground_truth,
+                         int(passage_length[0]), img, idx)
+
+    def _train_forward(self, pb):
+        drop = max(getattr(self.config, "hidden_dropout_prob", 0.0) or 0.0, getattr(self.args, "para_dropout", 0.0) or 0.0)
+        if drop > 0 and not self.__dict__.get("_warned_dropout"):
+            warnings.warn("multimodal_sequencing_b200: dropout is not applied in training (p = 0 semantics)")
+            self.__dict__["_warned_dropout"] = True
+        eng = self.engine()
+        flat = eng.new_grad_buffer()
+        with torch.no_grad():
+            loss = eng.train_step(pb, flat, self.pairwise_loss_lam)
+        lay = {n: (o, k) for n, o, k, _ in eng.train_layout()}
+        named = list(self.named_parameters())
+        spans = [lay.get(n) for n, _ in named]    # None: the reference gives this parameter no gradient either
+        with torch.enable_grad():
+            return _DeviceBackward.apply(loss, flat, spans, *[p for _, p in named])
+
+    def finetune_step(self, inputs, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0, grad_scale=None,
+                      allreduce=True):
+        """Fused alternative to loss.backward() + clip_grad_norm_ + AdamW.step() (trainers/train.py:340-363): one
+        msq_train_step, one all-reduce of the flat gradient buffer when torch.distributed is initialised, one
+        msq_adamw_step on the fp32 masters inside the library.  The nn.Parameters of this module go stale until
+        pull_weights() (call it before state_dict() / save_pretrained()).  Returns the loss (0-d device tensor)."""
+        from multimodal_sequencing_b200.sharding import allreduce_gradients
+        berson_inputs = inputs
+        if getattr(self, "tokenizer", None) is not None and "pairs_list" not in inputs:
+            berson_inputs = prepare_berson_inputs(inputs, self.tokenizer, args=self.args)
+        b = berson_inputs
+        pb = self._pair_batch(b["input_ids"], b.get("attention_mask"), b.get("token_type_ids"), b.get("pairs_list"),
+                              b["passage_length"], b.get("sep_positions"), b.get("ground_truth"), b.get("pairwise_labels"),
+                              b.get("images"), b.get("_pair_batch"))
+        eng = self.engine()
+        flat = self.__dict__.get("_flat")
+        if flat is None or flat.device != eng.device or flat.numel() != eng.new_grad_buffer().numel():
+            flat = self.__dict__["_flat"] = eng.new_grad_buffer()
+        flat.zero_()
+        with torch.no_grad():
+            loss = eng.train_step(pb, flat, self.pairwise_loss_lam)
+            scale = allreduce_gradients(flat) if allreduce else 1.0
+            eng.adamw_step(flat, lr, betas, eps, weight_decay, max_grad_norm, scale if grad_scale is None else grad_scale)
+        return loss
+
+    def pull_weights(self):
+        """Copy the library's fp32 masters back into this module's nn.Parameters (after finetune_step)."""
+        eng = self.engine()
+        with torch.no_grad():
+            for n, p in self.named_parameters():
+                if any(n == k for k, _, _, _ in eng.train_layout()):
+                    p.data.copy_(eng.read_param(n, tuple(p.shape)))
+        # the copies bumped the version counters: keep the packed model (it already holds these values)
+        tensors = list(self.parameters()) + list(self.buffers())
+        self.__dict__["_eng_sig"] = tuple(t._version for t in tensors) + (tuple(id(t) for t in tensors),
+                                                                          bool(getattr(self, "precise", False)))
+
     def _forward(self, input_ids, attention_mask=None, token_type_ids=None, pairs_list=None, passage_length=None,
                  pairs_num=None, sep_positions=None, ground_truth=None, mask_cls=None, pairwise_labels=None, cuda=None,
                  head_mask=None, images=None, _pair_batch=None):
-        B, P, Lt = input_ids.shape
-        N = int(passage_length[0])
-        pb = _pair_batch
-        if pb is None:
-            img = idx = None
-            if images is not None:
-                img = images.reshape(B * P * 2, *images.shape[3:])
-                idx = torch.arange(B * P * 2, dtype=torch.int32).reshape(B, P, 2)
-            pb = PairBatch(input_ids, attention_mask, token_type_ids, sep_positions, pairs_list, pairwise_labels,
-                           ground_truth, N, img, idx)
+        pb = self._pair_batch(input_ids, attention_mask, token_type_ids, pairs_list, passage_length, sep_positions, ground_truth,
+                              pairwise_labels, images, _pair_batch)
+        if self.training:
+            return (self._train_forward(pb),)
         with torch.no_grad():
             return (self.engine().training_loss(pb, self.pairwise_loss_lam),)
 

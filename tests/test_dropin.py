@@ -74,12 +74,50 @@ def test_beam_matches_generator_semantics():
     assert done == [] and remain == [0, 0, 0]
 
 
-def test_training_mode_is_declared_out_of_scope(golden_dir):
+@pytest.mark.gpu
+def test_reference_training_loop_runs_unchanged(golden_dir):
+    """trainers/train.py:340-363 against the drop-in module: loss = model(inputs)[0]; loss.backward();
+    clip_grad_norm_(model.parameters()); optimizer.step(); model.zero_grad().  p.grad must equal the gradients the real
+    reference produced (grads_tiny.pt), and the loop must lower the loss."""
     g = torch.load(os.path.join(golden_dir, "text_tiny.pt"), weights_only=False)
-    model, _ = _build(g, 5, 4)
-    model.train()
-    with pytest.raises(NotImplementedError):
-        model({"input_ids": None})
+    r = torch.load(os.path.join(golden_dir, "grads_tiny.pt"), weights_only=False)["text"]
+    from oracle import berson_oracle as O
+    ids, labels, _ = O.synthetic_manuals(r["B"], r["N"], r["L"], vocab=1000, seed=r["seed"])
+    model, args = _build(g, 5, 4, "cuda")
+    model.load_state_dict(g["sd"], strict=False)
+    model = model.cuda().train()
+    for mod in model.modules():
+        mod.precise = True
+    model.tokenizer = Tok()
+    inputs = {"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": labels}
+    opt = torch.optim.AdamW([p for p in model.parameters()], lr=1e-3, weight_decay=0.0)
+    losses = []
+    with torch.enable_grad():
+        for step in range(3):
+            loss = model(inputs)[0]
+            loss.backward()
+            if step == 0:
+                assert abs(loss.item() - r["loss"]) < 5e-5
+                named = dict(model.named_parameters())
+                for n, s_ in r["grads"].items():
+                    if n.startswith("bert.pooler"):
+                        continue
+                    a = named[n].grad.detach().double().cpu().reshape(-1)
+                    assert abs(float(a.norm()) - s_["norm"]) <= 1e-3 * s_["norm"] + 1e-7, n
+                for n in ("two_level_encoder.h1_relationship.weight", "classifier.weight", "encoder.transformer_inter.0.layer_norm.weight"):
+                    assert named[n].grad is None, n      # no gradient in the reference either
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
+            model.zero_grad()
+            losses.append(loss.item())
+    assert losses[-1] < losses[0] - 0.02, losses
+    # fused device-side step: same semantics without the weight round trip
+    l0 = model.finetune_step(inputs, 1e-3).item()
+    l1 = model.finetune_step(inputs, 1e-3).item()
+    assert l1 < l0
+    model.pull_weights()
+    model.eval()
+    assert abs(model(inputs)[0].item() - model.engine().training_loss(model.engine().prepare(ids, labels, 5, None)).item()) < 1e-6
 
 
 @pytest.mark.gpu
