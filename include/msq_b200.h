@@ -99,7 +99,7 @@ int msq_encode(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, cons
                const int32_t* img_index_dev, const msq_encode_out* out, void* stream);
 
 /* ---- BertForOrdering._forward loss VALUE (modeling_bert.py:943-1174: teacher-forced pointer NLL / (N-1) + lam *
- * pairwise NLL / P, batch mean), forward only (no gradients in this build).  ground_truth_dev [B,N] int32 =
+ * pairwise NLL / P, batch mean), value only (eval mode; msq_train_step below is the training twin).  ground_truth_dev [B,N] int32 =
  * the target order, pairwise_labels_dev [B,P] int64, perm_scratch_dev [B,N] int32 workspace, loss_dev 1 float. */
 int msq_training_loss(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev,
                       const int64_t* sep_dev, int64_t B, int32_t N, int32_t Lt, const float* images_dev, int64_t n_img,
