@@ -265,7 +265,7 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
     if (it == ts->index.end()) { set_error("train: no gradient slot for %s", name.c_str()); err = MSQ_ERR_STATE; return nullptr; }
     return grads + ts->slots[it->second].off;
   };
-  const int64_t MpJ = round_up(Mj, 64), MpV = round_up(max(Mv, (int64_t)1), 64);
+  const int64_t MpJ = wgrad_rows(Mj), MpV = wgrad_rows(max(Mv, (int64_t)1));
   const int64_t nchunk = mm ? min(n_img, TRAIN_IMG_CHUNK) * g2 : 0, Np = round_up(max(nchunk, (int64_t)1), 64);
   BwdBufs b{};
   for (int pass = 0; pass < 2; ++pass) {
@@ -286,8 +286,10 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
       b.dpatch = p.take<float>((size_t)n_img * g2 * Wd);
       b.apatch = p.take<T>((size_t)nchunk * Kc);
     }
+    if (sizeof(T) == 2) b.part = p.take<float>((size_t)SPLITK_MAX * max((int64_t)max(3 * H, I) * H, (int64_t)4 * Wd * Wd));
     if (pass == 0) MSQ_TRY(m->ws.reserve(p.need + 4096, st));
   }
+  if (sizeof(T) == 2) b.sk = &ts->splitk;
   // gradient of the final joint stream
   MSQ_CUDA(cudaMemsetAsync(b.gA, 0, (size_t)Mj * H * sizeof(float), st));
   if (d_lang) MSQ_TRY(scatter_rows(d_lang, R * Lt, H, Lt, Lj, 0, b.gA, st));

@@ -11,6 +11,27 @@ struct ParamSlot { std::string name; int64_t off = 0, numel = 0; float* master =
 struct BertTape { void *x, *qkv, *ctx, *x1, *u; float *s1, *s2; };
 struct VitTape { float *x, *x1; void *y1, *qkv, *ctx, *y2, *u; };
 
+// Split-K of the weight-gradient GEMMs: dW is only 9-72 output tiles (a fraction of the 148 SMs) against a contraction
+// of tens of thousands of rows, so the contraction is cut into S slices that run CONCURRENTLY as S launches of the same
+// GEMM kernel on S auxiliary streams (fork / join with events), each into its own partial buffer; an ordered pass adds
+// the partials into the gradient (deterministic).
+constexpr int SPLITK_MAX = 8;
+struct SplitK {
+  cudaStream_t aux[SPLITK_MAX] = {};
+  cudaEvent_t fork = nullptr, join[SPLITK_MAX] = {};
+  bool ready = false;
+  int init() {
+    if (ready) return MSQ_OK;
+    for (int i = 0; i < SPLITK_MAX; ++i) {
+      MSQ_CUDA(cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking));
+      MSQ_CUDA(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
+    }
+    MSQ_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    ready = true;
+    return MSQ_OK;
+  }
+};
+
 struct ParaTape { float *xin, *y, *qkv, *ctx, *out, *pn, *u, *xo; };
 struct HeadTape {
   int64_t B = 0;
@@ -52,6 +73,7 @@ struct TrainState {
   float *keyT = nullptr, *wqT = nullptr, *whhT = nullptr, *wihT = nullptr, *pw4T = nullptr;
   Arena htape;
   HeadTape ht;
+  SplitK splitk;
 };
 
 inline void train_state_free_impl(TrainState* ts) {
@@ -89,12 +111,52 @@ static int gemm_nt(const msq_model* m, const T* A, int lda, const T* W, int ldw,
   }
 }
 
-struct BwdBufs { float *gA, *gB, *ln_scr, *at_scr, *dpatch; void *gT, *gH, *gC, *gQ, *GT, *XT, *apatch; };
+int splitk_accumulate(const float* part, int S, int64_t n, float* dW, cudaStream_t st);   // train_kernels.cu
+
+struct BwdBufs {
+  float *gA, *gB, *ln_scr, *at_scr, *dpatch;
+  void *gT, *gH, *gC, *gQ, *GT, *XT, *apatch;
+  SplitK* sk = nullptr;     // non-null: split the wgrad contraction (bf16 tensor-core path)
+  float* part = nullptr;    // [SPLITK_MAX, max Nout*Kin] partial sums
+};
+static inline int wgrad_splits(int Nout, int Kin, int64_t M) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("MSQ_WGRAD_SPLITK"); off = (e && e[0] == '1') ? 0 : 1; }   // opt-in until measured on the GPU
+  if (off) return 1;
+  const int tiles = ceil_div(Nout, 128) * ceil_div(Kin, 256);
+  int S = 148 / (tiles > 0 ? tiles : 1);
+  if (S > SPLITK_MAX) S = SPLITK_MAX;
+  while (S > 1 && M / S < 2048) --S;     // keep every slice a long contraction
+  return S < 1 ? 1 : S;
+}
+// rows of the transposed operands: padded so that every split-K slice is a multiple of 64
+static inline int64_t wgrad_rows(int64_t M) { return round_up(M, 64 * SPLITK_MAX); }
 
 // dW[Nout,Kin] += G^T X (act_x applied to X on the fly), db[Nout] += column sums of G
 template <typename T>
 static int wgrad(const msq_model* m, const T* G, int ldg, int Nout, const T* X, int ldx, int Kin, int act_x, int64_t M, float* dW, float* db,
                  BwdBufs& b, cudaStream_t st) {
+  int S = 1;
+  if constexpr (sizeof(T) == 2) {
+    if (b.sk && b.part && model_use_tc(m)) S = wgrad_splits(Nout, Kin, M);
+  }
+  if (S > 1) {
+    const int64_t Mc = round_up((M + S - 1) / S, 64), Mp = Mc * S;
+    MSQ_TRY((transpose_pad<T, T>(G, M, Nout, ldg, Mp, (T*)b.GT, ACT_NONE, st)));
+    MSQ_TRY((transpose_pad<T, T>(X, M, Kin, ldx, Mp, (T*)b.XT, act_x, st)));
+    MSQ_TRY(b.sk->init());
+    MSQ_CUDA(cudaEventRecord(b.sk->fork, st));
+    for (int s = 0; s < S; ++s) {
+      MSQ_CUDA(cudaStreamWaitEvent(b.sk->aux[s], b.sk->fork, 0));
+      MSQ_TRY((gemm_nt<T, float>(m, (const T*)b.GT + s * Mc, (int)Mp, (const T*)b.XT + s * Mc, (int)Mp, nullptr, nullptr, 0,
+                                 b.part + (size_t)s * Nout * Kin, Kin, Nout, Kin, (int)Mc, ACT_NONE, b.sk->aux[s])));
+      MSQ_CUDA(cudaEventRecord(b.sk->join[s], b.sk->aux[s]));
+      MSQ_CUDA(cudaStreamWaitEvent(st, b.sk->join[s], 0));
+    }
+    MSQ_TRY(splitk_accumulate(b.part, S, (int64_t)Nout * Kin, dW, st));
+    if (db) MSQ_TRY(rowsum_accum<T>((const T*)b.GT, Nout, Mp, Mp, db, st));
+    return MSQ_OK;
+  }
   const int64_t Mp = round_up(M, 64);
   MSQ_TRY((transpose_pad<T, T>(G, M, Nout, ldg, Mp, (T*)b.GT, ACT_NONE, st)));
   MSQ_TRY((transpose_pad<T, T>(X, M, Kin, ldx, Mp, (T*)b.XT, act_x, st)));

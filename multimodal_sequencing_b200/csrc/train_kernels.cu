@@ -11,6 +11,8 @@
 
 namespace msq {
 
+int splitk_accumulate(const float* part, int S, int64_t n, float* dW, cudaStream_t st);
+
 // ---------------------------------------------------------------------------------------------------
 // dst[n, m] = act(src[m, n]) for m < M, 0 for M <= m < Mp   (dst row-major [N, Mp])
 // ---------------------------------------------------------------------------------------------------
@@ -693,6 +695,25 @@ int attention_bwd(const T* qkv, const T* dctx, int64_t R, int L, int heads, floa
 }
 template int attention_bwd<float>(const float*, const float*, int64_t, int, int, float, const float*, int, int, float*, float*, cudaStream_t);
 template int attention_bwd<bf16>(const bf16*, const bf16*, int64_t, int, int, float, const float*, int, int, bf16*, float*, cudaStream_t);
+
+// dW[i] += sum_s part[s, i]   (split-K partial sums of a weight gradient, added in slice order)
+__global__ void __launch_bounds__(256) splitk_accumulate_kernel(const float* __restrict__ part, int S, int64_t n4, float* __restrict__ dW) {
+  pdl_sync();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 a = *reinterpret_cast<const float4*>(dW + i * 4);
+    for (int s = 0; s < S; ++s) {
+      const float4 p = *reinterpret_cast<const float4*>(part + ((int64_t)s * n4 + i) * 4);
+      a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+    }
+    *reinterpret_cast<float4*>(dW + i * 4) = a;
+  }
+}
+int splitk_accumulate(const float* part, int S, int64_t n, float* dW, cudaStream_t st) {
+  MSQ_REQUIRE(n % 4 == 0, "splitk_accumulate: n %% 4");
+  MSQ_CUDA(launch_k(splitk_accumulate_kernel, ew_grid(n / 4), dim3(256), 0, st, part, S, n / 4, dW));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
 
 // additive key mask (1 - mask) * -10000 (lxrt/modeling.py:1537-1545)
 __global__ void __launch_bounds__(256) mask_add_train_kernel(const int64_t* __restrict__ mask, int64_t n, float* __restrict__ out) {
