@@ -197,6 +197,8 @@ def main():
                     "api": "OrderingEngine.train_step + sharding.allreduce_gradients + adamw_step from a pinned host PairBatch"},
             "gpu_launches": launches, "clocks": clocks, "loss_trajectory": losses,
             "roofline": {"bound": "tensor", "kernel": "msq::gemm_tc_kernel (forward, dgrad and wgrad GEMMs)", "achieved": ach,
+                         "note": "the split-K slices of a weight gradient run concurrently on auxiliary streams: their event durations overlap, so "
+                                 "the per-launch sum over-counts kernel time and `achieved` is a lower bound (MSQ_WGRAD_SPLITK=0 gives the clean figure)",
                          "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": (ach / pk["tf_sust"]) if ach else None, "traffic": None,
                          "peak_source": pk["src"] + ", bf16_tflops_sustained", "launches_timed": pl.value,
                          "kernel_ms_per_step": pm.value / args.steps,

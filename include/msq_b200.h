@@ -184,7 +184,8 @@ int msq_adamw_step(msq_model* m, const float* grads_dev, float lr, float beta1, 
 
 /* ---- building blocks exposed for kernel-level parity tests and the bench's roofline lines ------ */
 /* C[M,N] = act(A[M,K] W[N,K]^T + bias) + resid.  dtype: 0 = fp32 in/out (FFMA), 1 = bf16 in / fp32 out
- * (tcgen05), 2 = bf16 in / bf16 out (tcgen05).  act: 0 none, 1 erf-GELU, 2 QuickGELU, 3 tanh, 4 tanh-GELU. */
+ * (tcgen05), 2 = bf16 in / bf16 out (tcgen05), 3 / 4 = bf16 in on the FFMA kernel (fp32 / bf16 out), 5 = "TN" weight-gradient
+ * shape on tcgen05: A [K,M] and W [K,N] bf16 row-major (MN-major operands, no transposes), C [M,N] fp32 = A^T W + resid.  act: 0 none, 1 erf-GELU, 2 QuickGELU, 3 tanh, 4 tanh-GELU. */
 int msq_gemm(int32_t dtype, const void* A_dev, const void* W_dev, const float* bias_dev, const float* resid_dev,
              void* C_dev, int64_t M, int32_t N, int32_t K, int32_t act, void* stream);
 /* tcgen05 GEMM with a DEFERRED LayerNorm in its epilogue (bf16 operands; kernel-level entry used by tests and

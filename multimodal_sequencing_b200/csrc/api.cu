@@ -1470,6 +1470,9 @@ extern "C" int msq_gemm(int32_t dtype, const void* A_dev, const void* W_dev, con
     case 2: return gemm_tc<bf16>(g, st);
     case 3: return gemm_simt<bf16, float>(g, st);
     case 4: return gemm_simt<bf16, bf16>(g, st);
+    case 5:   // TN operands (weight-gradient shape): A [K, M], W [K, N] bf16 row-major -> C [M, N] fp32 = A^T W (+ resid)
+      g.tn = 1; g.lda = (int)M; g.ldw = N;
+      return gemm_tc<float>(g, st);
   }
   set_error("msq_gemm: unknown dtype %d", dtype);
   return MSQ_ERR_ARG;

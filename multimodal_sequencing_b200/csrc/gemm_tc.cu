@@ -60,6 +60,7 @@ struct TcEpi {
   bf16* C2;
   int sp_in;
   float inv_dim, eps;
+  int tn;   // GemmArgs::tn: MN-major operands (single-CTA path)
 };
 
 // 8 consecutive output columns of one row: accumulator -> value to store (see GemmArgs for the modes)
@@ -215,6 +216,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * STAGE_BYTES);
             tma_load_2d_pair(sa, &tma_a, kb * TC_BK, a_row, lead_full);
             tma_load_2d_pair(sb, &tma_b, kb * TC_BK, b_row, lead_full);
+          } else if (ep.tn) {
+            // MN-major operands: boxes of 64 contraction rows x 64 columns, one per 64-wide slice of the tile
+            mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
+#pragma unroll
+            for (int i = 0; i < TC_BM / 64; ++i) tma_load_2d(sa + i * 8192, &tma_a, a_row + i * 64, kb * TC_BK, full0 + 8 * stage);
+#pragma unroll
+            for (int i = 0; i < Cfg::B_ROWS / 64; ++i) tma_load_2d(sb + i * 8192, &tma_b, b_row + i * 64, kb * TC_BK, full0 + 8 * stage);
           } else {
             mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
             tma_load_2d(sa, &tma_a, kb * TC_BK, a_row, full0 + 8 * stage);
@@ -228,7 +236,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && rank == 0) {
       // instruction descriptor: D=F32 [4,6), A=BF16 [7,10), B=BF16 [10,13), K-major A/B, N>>3 [17,23), M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(Cfg::TILE_M >> 4) << 24);
+      // TN mode: A and B MN-major (bits 15, 16)
+      const bool tn = !PAIR && ep.tn;
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(Cfg::TILE_M >> 4) << 24) |
+                             (tn ? ((1u << 15) | (1u << 16)) : 0u);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = unit; tile < num_tiles; tile += num_units) {
@@ -241,7 +252,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + TC_A_BYTES;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t da = umma_desc_sw128(sa + k * 32), db = umma_desc_sw128(sb + k * 32);
+            // K-major: 16 elements = 32 B further along the swizzled row; MN-major: 16 contraction rows = 2048 B further down
+            const uint64_t da = tn ? umma_desc_sw128_mn(sa + k * 2048) : umma_desc_sw128(sa + k * 32);
+            const uint64_t db = tn ? umma_desc_sw128_mn(sb + k * 2048) : umma_desc_sw128(sb + k * 32);
             if (PAIR) umma_bf16_pair(tmem_d, da, db, idesc, (kb | k) != 0);
             else umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0);
           }
@@ -481,8 +494,13 @@ template <typename TO, bool PAIR, int ACT, int MODE>
 static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
   using Cfg = TcCfg<PAIR, MODE>;
   CUtensorMap ma, mb;
-  MSQ_TRY(make_map_bf16(&ma, g.A, g.M, g.K, g.lda, TC_BK, TC_BM));
-  MSQ_TRY(make_map_bf16(&mb, g.W, g.N, g.K, g.ldw, TC_BK, Cfg::B_ROWS));
+  if (g.tn) {   // [K rows, M or N columns], boxes of 64 x 64
+    MSQ_TRY(make_map_bf16(&ma, g.A, g.K, (int)g.M, g.lda, 64, 64));
+    MSQ_TRY(make_map_bf16(&mb, g.W, g.K, g.N, g.ldw, 64, 64));
+  } else {
+    MSQ_TRY(make_map_bf16(&ma, g.A, g.M, g.K, g.lda, TC_BK, TC_BM));
+    MSQ_TRY(make_map_bf16(&mb, g.W, g.N, g.K, g.ldw, TC_BK, Cfg::B_ROWS));
+  }
   CUtensorMap mc = ma;
   CUtensorMap mc2 = ma;
   if (Cfg::TMA_STORE) MSQ_TRY(make_map_2d(&mc, g.C, g.M, g.N, g.ldc, 128 / (int)sizeof(TO), 32, sizeof(TO) == 4));
@@ -497,8 +515,8 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
   TcEpi ep;
   ep.bias = g.bias; ep.resid = g.resid; ep.C = g.C; ep.M = g.M; ep.N = g.N; ep.ldc = g.ldc; ep.ldr = g.ldr; ep.act = g.act;
   ep.svec = g.svec; ep.beta = g.beta; ep.stats_in = g.stats_in; ep.stats_out = g.stats_out; ep.C2 = (bf16*)g.C2bf; ep.sp_in = g.sp_in;
-  ep.inv_dim = g.ln_inv_dim; ep.eps = g.ln_eps;
-  const int num_m = ceil_div(g.M, Cfg::TILE_M), num_n = ceil_div(g.N, TC_BN), num_k = g.K / TC_BK;
+  ep.inv_dim = g.ln_inv_dim; ep.eps = g.ln_eps; ep.tn = g.tn;
+  const int num_m = ceil_div(g.M, Cfg::TILE_M), num_n = ceil_div(g.N, TC_BN), num_k = ceil_div(g.K, TC_BK);
   const int64_t tiles = (int64_t)num_m * num_n;
   profile_mark(st, false, 0.0);
   if (PAIR) {
@@ -560,8 +578,9 @@ static int launch_gemm_tc(const GemmArgs& g, int sms, cudaStream_t st) {
 template <typename TO>
 int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   MSQ_REQUIRE(gemm_tc_selftest_supported(), "gemm_tc: tcgen05 path needs an sm_100 device and cuTensorMapEncodeTiled");
-  MSQ_REQUIRE(g.K % TC_BK == 0 && g.N % 8 == 0 && g.lda % 8 == 0 && g.ldw % 8 == 0 && g.ldc % 8 == 0,
+  MSQ_REQUIRE((g.tn || g.K % TC_BK == 0) && g.N % 8 == 0 && g.lda % 8 == 0 && g.ldw % 8 == 0 && g.ldc % 8 == 0,
               "gemm_tc: K=%d N=%d lda=%d ldw=%d ldc=%d not supported", g.K, g.N, g.lda, g.ldw, g.ldc);
+  MSQ_REQUIRE(!g.tn || (g.mode == EPI_PLAIN && g.M % 8 == 0 && g.K >= 1), "gemm_tc: TN operands need the plain epilogue and M %% 8 == 0");
   MSQ_REQUIRE(((uintptr_t)g.A & 15) == 0 && ((uintptr_t)g.W & 15) == 0 && ((uintptr_t)g.C & 15) == 0, "gemm_tc: unaligned pointer");
   MSQ_REQUIRE(g.C2 == nullptr, "gemm_tc: second output unsupported");
   if (g.M == 0) return MSQ_OK;
@@ -574,7 +593,7 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   if (force_single < 0) { const char* e = getenv("MSQ_GEMM_1CTA"); force_single = (e && e[0] == '1') ? 1 : 0; }
   // CTA pairs pay off once there are enough 256 x 256 tiles to occupy most SM pairs
   const int64_t pair_tiles = (int64_t)ceil_div(g.M, 256) * ceil_div(g.N, TC_BN);
-  if (!force_single && pair_tiles >= sms / 4) return launch_gemm_tc<TO, true>(g, sms, st);
+  if (!g.tn && !force_single && pair_tiles >= sms / 4) return launch_gemm_tc<TO, true>(g, sms, st);
   return launch_gemm_tc<TO, false>(g, sms, st);
 }
 template int gemm_tc<float>(const GemmArgs&, cudaStream_t);

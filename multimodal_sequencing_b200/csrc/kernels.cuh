@@ -55,6 +55,12 @@ struct GemmArgs {
   //   EPI_RESLN   C = acc + bias + LN_pending(resid) (raw resid when stats_in is null); also writes the bf16 copy C2bf
   //               and the partial statistics of the rows it produced (stats_out [M, 2*ceil(N/256), 2]), i.e. the
   //               NEXT pending LayerNorm's input.  svec/beta hold gamma/beta of the LayerNorm pending on resid.
+  // gemm_tc only, single-CTA path: "TN" operands for weight gradients.  A is [K, M] (row = contraction index, lda) and
+  // W is [K, N] (ldw), both row-major, i.e. MN-major for the tensor core: C[M,N] = A^T W.  TMA boxes of 64 contraction
+  // rows x 64 columns land in shared memory as the canonical MN-major SWIZZLE_128B atoms and are consumed through
+  // MN-major UMMA descriptors -- no transposed copy of the activations / gradients is ever made.  K need not be a
+  // multiple of 64 (out-of-range rows are zero-filled by the TMA unit).
+  int tn = 0;
   int mode = EPI_PLAIN;
   const float* svec = nullptr;
   const float* beta = nullptr;
@@ -135,6 +141,8 @@ int pointer_p1(const float* enc, const float* cls, const int64_t* y, const float
 template <typename TI, typename TO>
 int transpose_pad(const TI* src, int64_t M, int N, int ld, int64_t Mp, TO* dst, int act, cudaStream_t st);
 template <typename T> int rowsum_accum(const T* a, int rows, int64_t ld, int64_t n, float* out, cudaStream_t st);
+size_t colsum_scratch_floats(int N);
+int colsum_accum_bf16(const bf16* G, int64_t M, int N, int ld, float* out, float* scratch, cudaStream_t st);
 template <typename T> int act_fwd(const T* u, int64_t n, int act, T* h, cudaStream_t st);
 template <typename T> int act_bwd(const T* dh, const T* u, int64_t n, int act, T* du, cudaStream_t st);
 size_t ln_bwd_scratch_floats(int H);

@@ -79,6 +79,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
   return d;
 }
+// MN-major, 128-byte swizzle: atoms of 64 MN elements (128 B, contiguous) x 8 K rows; SBO = distance between 8-row groups
+// along K (1024 B inside a TMA box of 64 rows), LBO = distance between 64-element atoms along MN (one 64 x 64 box = 8192 B)
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"

@@ -280,7 +280,8 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
     b.gQ = p.take<T>(3 * act);
     b.GT = p.take<T>((size_t)max(max((int64_t)max(3 * H, I) * MpJ, (int64_t)4 * Wd * MpV), (int64_t)Wd * Np));
     b.XT = p.take<T>((size_t)max(max((int64_t)max(H, I) * MpJ, (int64_t)4 * Wd * MpV), (int64_t)Kc * Np));
-    b.ln_scr = p.take<float>(ln_bwd_scratch_floats(max(H, Wd)));
+    b.scr_floats = max(ln_bwd_scratch_floats(max(H, Wd)), colsum_scratch_floats(max(max(3 * H, I), 4 * Wd)));
+    b.ln_scr = p.take<float>(b.scr_floats);
     b.at_scr = p.take<float>(max(attention_bwd_scratch_floats(R, Lj, c.heads), attention_bwd_scratch_floats(R, max(Lv, 1), max(Wd / 64, 1))));
     if (mm) {
       b.dpatch = p.take<float>((size_t)n_img * g2 * Wd);

@@ -116,12 +116,18 @@ int splitk_accumulate(const float* part, int S, int64_t n, float* dW, cudaStream
 struct BwdBufs {
   float *gA, *gB, *ln_scr, *at_scr, *dpatch;
   void *gT, *gH, *gC, *gQ, *GT, *XT, *apatch;
+  size_t scr_floats = 0;    // capacity of ln_scr (also the column-sum scratch of the TN weight-gradient path)
   SplitK* sk = nullptr;     // non-null: split the wgrad contraction (bf16 tensor-core path)
   float* part = nullptr;    // [SPLITK_MAX, max Nout*Kin] partial sums
 };
+static inline bool wgrad_tn_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MSQ_WGRAD_TN"); on = (e && e[0] == '0') ? 0 : 1; }   // MSQ_WGRAD_TN=0: transposed copies instead
+  return on != 0;
+}
 static inline int wgrad_splits(int Nout, int Kin, int64_t M) {
   static int off = -1;
-  if (off < 0) { const char* e = getenv("MSQ_WGRAD_SPLITK"); off = (e && e[0] == '1') ? 0 : 1; }   // opt-in until measured on the GPU
+  if (off < 0) { const char* e = getenv("MSQ_WGRAD_SPLITK"); off = (e && e[0] == '0') ? 1 : 0; }   // MSQ_WGRAD_SPLITK=0: one launch per weight
   if (off) return 1;
   const int tiles = ceil_div(Nout, 128) * ceil_div(Kin, 256);
   int S = 148 / (tiles > 0 ? tiles : 1);
@@ -139,6 +145,40 @@ static int wgrad(const msq_model* m, const T* G, int ldg, int Nout, const T* X, 
   int S = 1;
   if constexpr (sizeof(T) == 2) {
     if (b.sk && b.part && model_use_tc(m)) S = wgrad_splits(Nout, Kin, M);
+    // TN path: the GEMM reads dY [M, Nout] and X [M, Kin] as MN-major operands straight from HBM (GemmArgs::tn) -- no
+    // transposed copies; act(X) is materialised once into the XT scratch when the operand is a recomputed activation.
+    if (wgrad_tn_enabled() && b.ln_scr && model_use_tc(m) && Nout % 8 == 0 && Kin % 8 == 0 && ldg % 8 == 0 && ldx % 8 == 0 &&
+        colsum_scratch_floats(Nout) <= b.scr_floats) {
+      const T* Xo = X;
+      int ldxo = ldx;
+      if (act_x != ACT_NONE) {
+        MSQ_REQUIRE(ldx == Kin, "wgrad: strided activation operand");
+        MSQ_TRY(act_fwd<T>(X, M * (int64_t)Kin, act_x, (T*)b.XT, st));
+        Xo = (const T*)b.XT; ldxo = Kin;
+      }
+      GemmArgs g;
+      g.tn = 1; g.bias = nullptr; g.C2 = nullptr; g.N = Kin; g.M = Nout; g.lda = ldg; g.ldw = ldxo; g.ldc = Kin; g.ldr = Kin; g.act = ACT_NONE;
+      if (S > 1) {
+        const int64_t Mc = round_up((M + S - 1) / S, 64);
+        MSQ_TRY(b.sk->init());
+        MSQ_CUDA(cudaEventRecord(b.sk->fork, st));
+        int used = 0;
+        for (int s = 0; s < S && s * Mc < M; ++s, ++used) {
+          MSQ_CUDA(cudaStreamWaitEvent(b.sk->aux[s], b.sk->fork, 0));
+          g.A = G + s * Mc * ldg; g.W = Xo + s * Mc * ldxo; g.K = (int)min(Mc, M - s * Mc); g.resid = nullptr;
+          g.C = b.part + (size_t)s * Nout * Kin;
+          MSQ_TRY(gemm_tc<float>(g, b.sk->aux[s]));
+          MSQ_CUDA(cudaEventRecord(b.sk->join[s], b.sk->aux[s]));
+          MSQ_CUDA(cudaStreamWaitEvent(st, b.sk->join[s], 0));
+        }
+        MSQ_TRY(splitk_accumulate(b.part, used, (int64_t)Nout * Kin, dW, st));
+      } else {
+        g.A = G; g.W = Xo; g.K = (int)M; g.resid = dW; g.C = dW;
+        MSQ_TRY(gemm_tc<float>(g, st));
+      }
+      if (db) MSQ_TRY(colsum_accum_bf16((const bf16*)G, M, Nout, ldg, db, b.ln_scr, st));
+      return MSQ_OK;
+    }
   }
   if (S > 1) {
     const int64_t Mc = round_up((M + S - 1) / S, 64), Mp = Mc * S;

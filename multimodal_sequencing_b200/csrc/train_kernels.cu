@@ -146,6 +146,48 @@ int rowsum_accum(const T* a, int rows, int64_t ld, int64_t n, float* out, cudaSt
 template int rowsum_accum<float>(const float*, int, int64_t, int64_t, float*, cudaStream_t);
 template int rowsum_accum<bf16>(const bf16*, int, int64_t, int64_t, float*, cudaStream_t);
 
+// out[n] += sum_m G[m, n] for a row-major bf16 [M, N] matrix (bias gradients without a transposed copy): 64 row chunks x
+// 64-column groups write partial sums, an ordered second pass adds the chunks (deterministic).
+constexpr int CS_CHUNKS = 64;
+__global__ void __launch_bounds__(256) colsum_partial_bf16_kernel(const bf16* __restrict__ G, int64_t M, int N, int ld, float* __restrict__ partial) {
+  pdl_sync();
+  __shared__ float sh[8][65];
+  const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int n = blockIdx.x * 64 + 2 * lane;
+  const int64_t per = (M + CS_CHUNKS - 1) / CS_CHUNKS, r0 = blockIdx.y * per, r1 = min(M, r0 + per);
+  float a = 0.f, b = 0.f;
+  if (n < N)
+    for (int64_t r = r0 + rl; r < r1; r += 8) {
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(G + r * ld + n));
+      a += v.x; b += v.y;
+    }
+  sh[rl][2 * lane] = a; sh[rl][2 * lane + 1] = b;
+  __syncthreads();
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < N) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    partial[(int64_t)blockIdx.y * N + blockIdx.x * 64 + threadIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ partial, int N, float* __restrict__ out) {
+  pdl_sync();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int c = 0; c < CS_CHUNKS; ++c) s += partial[(int64_t)c * N + n];
+  out[n] += s;
+}
+size_t colsum_scratch_floats(int N) { return (size_t)CS_CHUNKS * N; }
+int colsum_accum_bf16(const bf16* G, int64_t M, int N, int ld, float* out, float* scratch, cudaStream_t st) {
+  MSQ_REQUIRE(N % 2 == 0 && ld % 2 == 0 && ((uintptr_t)G & 3) == 0, "colsum_accum_bf16: N=%d ld=%d", N, ld);
+  if (M == 0) return MSQ_OK;
+  MSQ_CUDA(launch_k(colsum_partial_bf16_kernel, dim3(ceil_div(N, 64), CS_CHUNKS), dim3(256), 0, st, G, M, N, ld, scratch));
+  MSQ_LAUNCH_CHECK();
+  MSQ_CUDA(launch_k(colsum_reduce_kernel, dim3(ceil_div(N, 256)), dim3(256), 0, st, (const float*)scratch, N, out));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // activations, forward (training keeps the pre-activation u) and backward:  h = act(u);  du = dh * act'(u)
 // ---------------------------------------------------------------------------------------------------

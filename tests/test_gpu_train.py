@@ -284,3 +284,28 @@ def test_full_size_train_step_vs_oracle_autograd():
               ("fp32" if precise else "bf16", loss, oloss, worst[1], worst[0]))
         del eng, grads, got
         torch.cuda.empty_cache()
+
+
+# ---- kernel level: tcgen05 GEMM with MN-major ("TN") operands, the weight-gradient shape -------------------------------
+@pytest.mark.parametrize("shape", [(768, 768, 6810), (3072, 768, 1000), (128, 512, 77), (2304, 768, 54480)])
+def test_gemm_tn_operands_vs_float64(shape):
+    """C[M,N] = A^T W + resid with A [K,M], W [K,N] bf16 row-major read as MN-major UMMA operands (no transposes);
+    K is deliberately not a multiple of 64 (TMA zero-fills the tail rows)."""
+    import ctypes as C
+    from multimodal_sequencing_b200 import _lib
+    lib = _lib.load()
+    if not lib.msq_tc_available():
+        pytest.skip("no tcgen05 device")
+    M, N, K = shape
+    gen = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(K, M, generator=gen).to(torch.bfloat16).cuda()
+    W = torch.randn(K, N, generator=gen).to(torch.bfloat16).cuda()
+    R = torch.randn(M, N, generator=gen).cuda()
+    out = R.clone()
+    p = lambda t: C.c_void_p(t.data_ptr())
+    _lib.check(lib.msq_gemm(5, p(A), p(W), None, p(out), p(out), M, N, K, 0, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    ref = A.double().t() @ W.double() + R.double()
+    err = (out.double() - ref).abs().max().item()
+    bound = 2e-5 * (K ** 0.5) * 4 + 1e-3      # fp32 accumulation of K bf16 x bf16 products of O(1) magnitude
+    assert err <= bound * max(1.0, ref.abs().max().item() / (K ** 0.5)), (err, bound)
