@@ -139,7 +139,7 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
   ts->bt.assign(nb, BertTape{});
   ts->vt.assign(nvl, VitTape{});
   float *xf = nullptr, *x1f = nullptr;
-  T *hb = nullptr, *apatch = nullptr, *vhb = nullptr;
+  T* apatch = nullptr;
   for (int pass = 0; pass < 2; ++pass) {
     Planner p{&ts->tape, pass == 0};
     if (pass == 1) ts->tape.reset();
@@ -152,7 +152,7 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
       for (auto& v : ts->vt) {
         v.x = p.take<float>((size_t)Mv * Wd); v.y1 = p.take<T>((size_t)Mv * Wd); v.qkv = p.take<T>((size_t)Mv * 3 * Wd);
         v.ctx = p.take<T>((size_t)Mv * Wd); v.x1 = p.take<float>((size_t)Mv * Wd); v.y2 = p.take<T>((size_t)Mv * Wd);
-        v.u = p.take<T>((size_t)Mv * 4 * Wd);
+        v.u = p.take<T>((size_t)Mv * 4 * Wd); v.hb = p.take<T>((size_t)Mv * 4 * Wd);
       }
       ts->vx_last = p.take<float>((size_t)Mv * Wd);
       ts->y_post = p.take<T>((size_t)Mv * Wd);
@@ -161,7 +161,7 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
     for (auto& b : ts->bt) {
       b.x = p.take<T>((size_t)Mj * H); b.qkv = p.take<T>((size_t)Mj * 3 * H); b.ctx = p.take<T>((size_t)Mj * H);
       b.s1 = p.take<float>((size_t)Mj * H); b.x1 = p.take<T>((size_t)Mj * H); b.u = p.take<T>((size_t)Mj * I);
-      b.s2 = p.take<float>((size_t)Mj * H);
+      b.s2 = p.take<float>((size_t)Mj * H); b.hb = p.take<T>((size_t)Mj * I);
     }
     ts->x_last = p.take<T>((size_t)Mj * H);
     ts->x_out = p.take<float>((size_t)Mj * H);
@@ -172,10 +172,8 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
     if (pass == 1) m->ws.reset();
     xf = p.take<float>((size_t)Mj * H);
     x1f = p.take<float>((size_t)Mj * H);
-    hb = p.take<T>((size_t)Mj * I);
     if (mm) {
       apatch = p.take<T>((size_t)min(n_img, TRAIN_IMG_CHUNK) * g2 * Kc);
-      vhb = p.take<T>((size_t)Mv * 4 * Wd);
     }
     if (pass == 0) MSQ_TRY(m->ws.reserve(p.need + 4096, st));
   }
@@ -208,8 +206,8 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
       MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.ctx, Wd, wptr<T>(L.out), L.out.ld, L.out.b, t.x, Wd, t.x1, Wd, Mv, Wd, Wd, ACT_NONE, st)));
       MSQ_TRY(layernorm<T>(t.x1, Mv, Wd, L.ln2.g, L.ln2.b, 1e-5f, nullptr, (T*)t.y2, 0, 0, 0, st));
       MSQ_TRY((gemm_nt<T, T>(m, (const T*)t.y2, Wd, wptr<T>(L.fc), L.fc.ld, L.fc.b, nullptr, 0, (T*)t.u, 4 * Wd, Mv, 4 * Wd, Wd, ACT_NONE, st)));
-      MSQ_TRY(act_fwd<T>((const T*)t.u, Mv * 4 * Wd, ACT_QUICK_GELU, vhb, st));
-      MSQ_TRY((gemm_nt<T, float>(m, vhb, 4 * Wd, wptr<T>(L.proj), L.proj.ld, L.proj.b, t.x1, Wd, xn, Wd, Mv, Wd, 4 * Wd, ACT_NONE, st)));
+      MSQ_TRY(act_fwd<T>((const T*)t.u, Mv * 4 * Wd, ACT_QUICK_GELU, (T*)t.hb, st));
+      MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.hb, 4 * Wd, wptr<T>(L.proj), L.proj.ld, L.proj.b, t.x1, Wd, xn, Wd, Mv, Wd, 4 * Wd, ACT_NONE, st)));
     }
     MSQ_TRY(layernorm<T>(ts->vx_last, Mv, Wd, m->ln_post.g, m->ln_post.b, 1e-5f, nullptr, (T*)ts->y_post, 0, 0, 0, st));
     MSQ_TRY((gemm_nt<T, float>(m, (const T*)ts->y_post, Wd, wptr<T>(m->visn_fc), m->visn_fc.ld, m->visn_fc.b, nullptr, 0, ts->visn_pre, H, Mv,
@@ -225,8 +223,8 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
     MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.ctx, H, wptr<T>(L.out), L.out.ld, L.out.b, xf, H, t.s1, H, Mj, H, H, ACT_NONE, st)));
     MSQ_TRY(layernorm<T>(t.s1, Mj, H, L.ln1.g, L.ln1.b, 1e-12f, x1f, (T*)t.x1, 0, 0, 0, st));
     MSQ_TRY((gemm_nt<T, T>(m, (const T*)t.x1, H, wptr<T>(L.up), L.up.ld, L.up.b, nullptr, 0, (T*)t.u, I, Mj, I, H, ACT_NONE, st)));
-    MSQ_TRY(act_fwd<T>((const T*)t.u, Mj * I, ACT_GELU_ERF, hb, st));
-    MSQ_TRY((gemm_nt<T, float>(m, hb, I, wptr<T>(L.down), L.down.ld, L.down.b, x1f, H, t.s2, H, Mj, H, I, ACT_NONE, st)));
+    MSQ_TRY(act_fwd<T>((const T*)t.u, Mj * I, ACT_GELU_ERF, (T*)t.hb, st));
+    MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.hb, I, wptr<T>(L.down), L.down.ld, L.down.b, x1f, H, t.s2, H, Mj, H, I, ACT_NONE, st)));
     MSQ_TRY(layernorm<T>(t.s2, Mj, H, L.ln2.g, L.ln2.b, 1e-12f, xf, xn, 0, 0, 0, st));
   }
   MSQ_CUDA(cudaMemcpyAsync(ts->x_out, xf, (size_t)Mj * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -310,7 +308,7 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
     if (err) return err;
     // output.LayerNorm -> ds2 (gB fp32, gT operand copy)
     MSQ_TRY(ln_bwd<T>(b.gA, t.s2, nullptr, Mj, H, L.ln2.g, 1e-12f, b.gB, (T*)b.gT, dg2, db2, b.ln_scr, 0, 0, 0, st));
-    MSQ_TRY(wgrad<T>(m, (const T*)b.gT, H, H, (const T*)t.u, I, I, ACT_GELU_ERF, Mj, dWd, dbd, b, st));
+    MSQ_TRY(wgrad<T>(m, (const T*)b.gT, H, H, (const T*)t.hb, I, I, ACT_NONE, Mj, dWd, dbd, b, st));
     MSQ_TRY((dgrad<T, T>(m, (const T*)b.gT, H, WT[3], I, nullptr, (T*)b.gH, Mj, st)));
     MSQ_TRY(act_bwd<T>((const T*)b.gH, (const T*)t.u, Mj * I, ACT_GELU_ERF, (T*)b.gH, st));
     MSQ_TRY(wgrad<T>(m, (const T*)b.gH, I, I, (const T*)t.x1, H, H, ACT_NONE, Mj, dWu, dbu, b, st));
@@ -359,7 +357,7 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
     float *dg1 = G(bn + "ln_1.weight"), *db1 = G(bn + "ln_1.bias"), *dg2 = G(bn + "ln_2.weight"), *db2 = G(bn + "ln_2.bias");
     float *dWf = G(bn + "mlp.c_fc.weight"), *dbf = G(bn + "mlp.c_fc.bias"), *dWp = G(bn + "mlp.c_proj.weight"), *dbp = G(bn + "mlp.c_proj.bias");
     if (err) return err;
-    MSQ_TRY(wgrad<T>(m, (const T*)b.gT, Wd, Wd, (const T*)t.u, 4 * Wd, 4 * Wd, ACT_QUICK_GELU, Mv, dWp, dbp, b, st));
+    MSQ_TRY(wgrad<T>(m, (const T*)b.gT, Wd, Wd, (const T*)t.hb, 4 * Wd, 4 * Wd, ACT_NONE, Mv, dWp, dbp, b, st));
     MSQ_TRY((dgrad<T, T>(m, (const T*)b.gT, Wd, WT[3], 4 * Wd, nullptr, (T*)b.gH, Mv, st)));
     MSQ_TRY(act_bwd<T>((const T*)b.gH, (const T*)t.u, Mv * 4 * Wd, ACT_QUICK_GELU, (T*)b.gH, st));
     MSQ_TRY(wgrad<T>(m, (const T*)b.gH, 4 * Wd, 4 * Wd, (const T*)t.y2, Wd, Wd, ACT_NONE, Mv, dWf, dbf, b, st));

@@ -8,8 +8,8 @@
 namespace msq {
 
 struct ParamSlot { std::string name; int64_t off = 0, numel = 0; float* master = nullptr; bool decay = true; };
-struct BertTape { void *x, *qkv, *ctx, *x1, *u; float *s1, *s2; };
-struct VitTape { float *x, *x1; void *y1, *qkv, *ctx, *y2, *u; };
+struct BertTape { void *x, *qkv, *ctx, *x1, *u, *hb; float *s1, *s2; };   // hb = act(u): operand of the down-projection wgrad
+struct VitTape { float *x, *x1; void *y1, *qkv, *ctx, *y2, *u, *hb; };
 
 // Split-K of the weight-gradient GEMMs: dW is only 9-72 output tiles (a fraction of the 148 SMs) against a contraction
 // of tens of thousands of rows, so the contraction is cut into S slices that run CONCURRENTLY as S launches of the same
