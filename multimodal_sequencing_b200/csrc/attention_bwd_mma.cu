@@ -243,6 +243,228 @@ __global__ void __launch_bounds__(ABM_WARPS * 32) attention_bwd_mma_kernel(const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Two-kernel variant (default): the fused kernel above keeps all four matrices resident (138 KB at L = 227) and needs 167
+// registers, i.e. ONE CTA of 8 warps per SM (ncu: warps_active 12 %, tensor pipe 37 %).  Here pass A keeps only K and V in
+// shared memory and pass B only Q and dO (69 KB each); the 16-row operand a warp owns (Q_i / dO_i, K_j / V_j) is loaded
+// straight from global memory into the mma A-fragment layout, D_i = dO_i . O_i is formed from the fragments, and the row
+// statistics (lse, D) travel through a small global scratch.  Two to three CTAs fit per SM.
+// ---------------------------------------------------------------------------------------------------
+// A operand (16 rows x 64) of row block rb read from global memory (row stride ld elements); rows >= L are zero
+__device__ __forceinline__ void load_a64_global(uint32_t (*a)[4], const bf16* M, int64_t ld, int rb, int L, int lane) {
+  const int gid = lane >> 2, tig = lane & 3;
+  const int r0 = rb * 16 + gid, r1 = r0 + 8;
+  const bf16* p0 = M + (int64_t)r0 * ld + tig * 2;
+  const bf16* p1 = M + (int64_t)r1 * ld + tig * 2;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    a[ks][0] = r0 < L ? *reinterpret_cast<const uint32_t*>(p0 + ks * 16) : 0u;
+    a[ks][1] = r1 < L ? *reinterpret_cast<const uint32_t*>(p1 + ks * 16) : 0u;
+    a[ks][2] = r0 < L ? *reinterpret_cast<const uint32_t*>(p0 + ks * 16 + 8) : 0u;
+    a[ks][3] = r1 < L ? *reinterpret_cast<const uint32_t*>(p1 + ks * 16 + 8) : 0u;
+  }
+}
+__device__ __forceinline__ float dot2(uint32_t x, uint32_t y) {
+  const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&x));
+  const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&y));
+  return fmaf(p.x, q.x, p.y * q.y);
+}
+// cooperative load of two [L, 64] matrices (row stride ld) into padded shared memory, rows >= L zeroed
+__device__ __forceinline__ void load_two(bf16* S0, bf16* S1, const bf16* G0, int64_t ld0, const bf16* G1, int64_t ld1, int L, int Lp) {
+  for (int idx = threadIdx.x; idx < Lp * 8; idx += blockDim.x) {
+    const int t = idx >> 3, pc = idx & 7;
+    uint4 a = make_uint4(0, 0, 0, 0), b = a;
+    if (t < L) {
+      a = *reinterpret_cast<const uint4*>(G0 + (int64_t)t * ld0 + pc * 8);
+      b = *reinterpret_cast<const uint4*>(G1 + (int64_t)t * ld1 + pc * 8);
+    }
+    *reinterpret_cast<uint4*>(S0 + t * ABM_LD + pc * 8) = a;
+    *reinterpret_cast<uint4*>(S1 + t * ABM_LD + pc * 8) = b;
+  }
+}
+
+__global__ void __launch_bounds__(ABM_WARPS * 32, 2) attention_bwd_dq_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ctx,
+                                                                                 const bf16* __restrict__ dctx, int L, int Lp, int heads, float scale,
+                                                                                 const float* __restrict__ mask_add, int mask_ld, int mask_len,
+                                                                                 bf16* __restrict__ dqkv, float* __restrict__ lse_out,
+                                                                                 float* __restrict__ dsum_out) {
+  pdl_sync();
+  extern __shared__ __align__(16) unsigned char smraw[];
+  bf16* Ks = reinterpret_cast<bf16*>(smraw);
+  bf16* Vs = Ks + Lp * ABM_LD;
+  float* Ms = reinterpret_cast<float*>(Vs + Lp * ABM_LD);
+  const int r = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int ld = 3 * heads * 64, ldc = heads * 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+  const bf16* qbase = qkv + (int64_t)r * L * ld + h * 64;
+  const bf16* gbase = dctx + (int64_t)r * L * ldc + h * 64;
+  const bf16* obase = ctx + (int64_t)r * L * ldc + h * 64;
+  load_two(Ks, Vs, qbase + heads * 64, ld, qbase + 2 * heads * 64, ld, L, Lp);
+  for (int t = tid; t < Lp; t += ABM_WARPS * 32)
+    Ms[t] = t < L ? ((mask_add && t < mask_len) ? mask_add[(int64_t)r * mask_ld + t] : 0.f) : -INFINITY;
+  __syncthreads();
+  const int nblk = Lp >> 4;
+  for (int ib = warp; ib < nblk; ib += ABM_WARPS) {
+    uint32_t aq[4][4], ag[4][4];
+    load_a64_global(aq, qbase, ld, ib, L, lane);
+    load_a64_global(ag, gbase, ldc, ib, L, lane);
+    float dd[2] = {0.f, 0.f};
+    {
+      uint32_t ao[4][4];
+      load_a64_global(ao, obase, ldc, ib, L, lane);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        dd[0] += dot2(ag[ks][0], ao[ks][0]) + dot2(ag[ks][2], ao[ks][2]);
+        dd[1] += dot2(ag[ks][1], ao[ks][1]) + dot2(ag[ks][3], ao[ks][3]);
+      }
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        dd[0] += __shfl_xor_sync(0xffffffffu, dd[0], o);
+        dd[1] += __shfl_xor_sync(0xffffffffu, dd[1], o);
+      }
+    }
+    float m[2] = {-INFINITY, -INFINITY}, s[2] = {0.f, 0.f};
+    for (int kb = 0; kb < nblk; ++kb) {
+      float acc[2][4];
+      mma_nt16(acc, aq, Ks, kb, lane);
+#pragma unroll
+      for (int hr = 0; hr < 2; ++hr) {
+        float vals[4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) vals[nt * 2 + e] = fmaf(acc[nt][hr * 2 + e], scale, Ms[kb * 16 + nt * 8 + tig * 2 + e]);
+        const float um = fmaxf(fmaxf(vals[0], vals[1]), fmaxf(vals[2], vals[3]));
+        const float mn = fmaxf(m[hr], um);
+        if (mn > -INFINITY) {
+          s[hr] = s[hr] * __expf(m[hr] - mn) + (__expf(vals[0] - mn) + __expf(vals[1] - mn)) + (__expf(vals[2] - mn) + __expf(vals[3] - mn));
+          m[hr] = mn;
+        }
+      }
+    }
+    float lse[2];
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m[hr], o), so = __shfl_xor_sync(0xffffffffu, s[hr], o);
+        const float mn = fmaxf(m[hr], mo);
+        if (mn > -INFINITY) {
+          s[hr] = s[hr] * __expf(m[hr] - mn) + so * __expf(mo - mn);
+          m[hr] = mn;
+        }
+      }
+      lse[hr] = m[hr] + __logf(s[hr]);
+      const int row = ib * 16 + gid + hr * 8;
+      if (tig == 0 && row < L) {
+        lse_out[(int64_t)blockIdx.x * L + row] = lse[hr];
+        dsum_out[(int64_t)blockIdx.x * L + row] = dd[hr];
+      }
+    }
+    float dq[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+    for (int kb = 0; kb < nblk; ++kb) {
+      float sa[2][4], dp[2][4];
+      mma_nt16(sa, aq, Ks, kb, lane);
+      mma_nt16(dp, ag, Vs, kb, lane);
+      uint32_t a[4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        float ds[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int hr = e >> 1;
+          const float p = __expf(fmaf(sa[nt][e], scale, Ms[kb * 16 + nt * 8 + tig * 2 + (e & 1)]) - lse[hr]);
+          ds[e] = p * (dp[nt][e] - dd[hr]);
+        }
+        a[nt * 2] = pack2(ds[0], ds[1]);
+        a[nt * 2 + 1] = pack2(ds[2], ds[3]);
+      }
+      mma_nn64(dq, a, Ks, kb, lane);
+    }
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int row = ib * 16 + gid + hr * 8;
+      if (row < L) {
+        bf16* op = dqkv + ((int64_t)r * L + row) * ld + h * 64 + tig * 2;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(op + nt * 8) = pack2(dq[nt][hr * 2] * scale, dq[nt][hr * 2 + 1] * scale);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(ABM_WARPS * 32, 2) attention_bwd_dkv_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dctx, int L,
+                                                                                  int Lp, int heads, float scale, const float* __restrict__ mask_add,
+                                                                                  int mask_ld, int mask_len, bf16* __restrict__ dqkv,
+                                                                                  const float* __restrict__ lse_in, const float* __restrict__ dsum_in) {
+  pdl_sync();
+  extern __shared__ __align__(16) unsigned char smraw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smraw);
+  bf16* Gs = Qs + Lp * ABM_LD;
+  float* Ls = reinterpret_cast<float*>(Gs + Lp * ABM_LD);
+  float* Ds = Ls + Lp;
+  const int r = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int ld = 3 * heads * 64, ldc = heads * 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+  const bf16* qbase = qkv + (int64_t)r * L * ld + h * 64;
+  const bf16* gbase = dctx + (int64_t)r * L * ldc + h * 64;
+  load_two(Qs, Gs, qbase, ld, gbase, ldc, L, Lp);
+  for (int t = tid; t < Lp; t += ABM_WARPS * 32) {
+    Ls[t] = t < L ? lse_in[(int64_t)blockIdx.x * L + t] : 0.f;
+    Ds[t] = t < L ? dsum_in[(int64_t)blockIdx.x * L + t] : 0.f;
+  }
+  __syncthreads();
+  const int nblk = Lp >> 4;
+  for (int jb = warp; jb < nblk; jb += ABM_WARPS) {
+    uint32_t ak[4][4], av[4][4];
+    load_a64_global(ak, qbase + heads * 64, ld, jb, L, lane);
+    load_a64_global(av, qbase + 2 * heads * 64, ld, jb, L, lane);
+    float mr[2];
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int j = jb * 16 + gid + hr * 8;
+      mr[hr] = j < L ? ((mask_add && j < mask_len) ? mask_add[(int64_t)r * mask_ld + j] : 0.f) : -INFINITY;
+    }
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+    for (int qb = 0; qb < nblk; ++qb) {
+      float st[2][4], dp[2][4];
+      mma_nt16(st, ak, Qs, qb, lane);
+      mma_nt16(dp, av, Gs, qb, lane);
+      uint32_t pa[4], da[4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        float p[4], ds[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int qc = qb * 16 + nt * 8 + tig * 2 + (e & 1);
+          p[e] = __expf(fmaf(st[nt][e], scale, mr[e >> 1]) - Ls[qc]);
+          ds[e] = p[e] * (dp[nt][e] - Ds[qc]);
+        }
+        pa[nt * 2] = pack2(p[0], p[1]); pa[nt * 2 + 1] = pack2(p[2], p[3]);
+        da[nt * 2] = pack2(ds[0], ds[1]); da[nt * 2 + 1] = pack2(ds[2], ds[3]);
+      }
+      mma_nn64(dv, pa, Gs, qb, lane);
+      mma_nn64(dk, da, Qs, qb, lane);
+    }
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int row = jb * 16 + gid + hr * 8;
+      if (row < L) {
+        bf16* op = dqkv + ((int64_t)r * L + row) * ld + heads * 64 + h * 64 + tig * 2;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          *reinterpret_cast<uint32_t*>(op + nt * 8) = pack2(dk[nt][hr * 2] * scale, dk[nt][hr * 2 + 1] * scale);
+          *reinterpret_cast<uint32_t*>(op + heads * 64 + nt * 8) = pack2(dv[nt][hr * 2], dv[nt][hr * 2 + 1]);
+        }
+      }
+    }
+  }
+}
+
 bool attention_bwd_mma_supported(int L) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("MSQ_ATTN_BWD_SIMT"); off = (e && e[0] == '1') ? 1 : 0; }
@@ -250,18 +472,40 @@ bool attention_bwd_mma_supported(int L) {
 }
 
 int attention_bwd_mma(const bf16* qkv, const bf16* ctx, const bf16* dctx, int64_t R, int L, int heads, float scale, const float* key_mask_add,
-                      int mask_ld, int mask_len, bf16* dqkv, cudaStream_t st) {
+                      int mask_ld, int mask_len, bf16* dqkv, float* scratch, cudaStream_t st) {
   MSQ_REQUIRE(L >= 1 && L <= 256, "attention_bwd_mma: sequence length %d out of range", L);
   MSQ_REQUIRE((((uintptr_t)qkv | (uintptr_t)ctx | (uintptr_t)dctx | (uintptr_t)dqkv) & 15) == 0, "attention_bwd_mma: unaligned pointer");
   if (R == 0) return MSQ_OK;
   const int Lp = (L + 15) & ~15;
-  const size_t smem = (size_t)4 * Lp * ABM_LD * sizeof(bf16) + (size_t)3 * Lp * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
-    MSQ_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  static int fused = -1;
+  if (fused < 0) { const char* e = getenv("MSQ_ATTN_BWD_FUSED"); fused = (e && e[0] == '1') ? 1 : 0; }
+  if (fused || !scratch) {
+    const size_t smem = (size_t)4 * Lp * ABM_LD * sizeof(bf16) + (size_t)3 * Lp * sizeof(float);
+    static size_t configured = 0;
+    if (smem > configured) {
+      MSQ_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    MSQ_CUDA(launch_k(attention_bwd_mma_kernel, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem, st, qkv, ctx, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv));
+    MSQ_LAUNCH_CHECK();
+    return MSQ_OK;
   }
-  MSQ_CUDA(launch_k(attention_bwd_mma_kernel, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem, st, qkv, ctx, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv));
+  float* lse = scratch;
+  float* dsum = scratch + (size_t)R * heads * L;
+  const size_t smem_a = (size_t)2 * Lp * ABM_LD * sizeof(bf16) + (size_t)Lp * sizeof(float);
+  const size_t smem_b = (size_t)2 * Lp * ABM_LD * sizeof(bf16) + (size_t)2 * Lp * sizeof(float);
+  static size_t conf_a = 0, conf_b = 0;
+  if (smem_a > conf_a) {
+    MSQ_CUDA(cudaFuncSetAttribute(attention_bwd_dq_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    conf_a = smem_a;
+  }
+  if (smem_b > conf_b) {
+    MSQ_CUDA(cudaFuncSetAttribute(attention_bwd_dkv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    conf_b = smem_b;
+  }
+  MSQ_CUDA(launch_k(attention_bwd_dq_mma_kernel, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem_a, st, qkv, ctx, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, lse, dsum));
+  MSQ_LAUNCH_CHECK();
+  MSQ_CUDA(launch_k(attention_bwd_dkv_mma_kernel, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem_b, st, qkv, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, (const float*)lse, (const float*)dsum));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }

@@ -241,7 +241,7 @@ template <typename T>
 static int attn_bwd(const T* qkv, const T* ctx, const T* dctx, int64_t R, int L, int heads, const float* mask, int mask_len, T* dqkv, float* scratch,
                     cudaStream_t st) {
   if constexpr (sizeof(T) == 2) {
-    if (attention_bwd_mma_supported(L)) return attention_bwd_mma(qkv, ctx, dctx, R, L, heads, 0.125f, mask, mask_len, mask_len, dqkv, st);
+    if (attention_bwd_mma_supported(L)) return attention_bwd_mma(qkv, ctx, dctx, R, L, heads, 0.125f, mask, mask_len, mask_len, dqkv, scratch, st);
   }
   return attention_bwd<T>(qkv, dctx, R, L, heads, 0.125f, mask, mask_len, mask_len, dqkv, scratch, st);
 }
