@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=8, help="manuals per optimizer step per GPU (scripts/recipeqa_finetune.sh: 1-8)")
     ap.add_argument("--precise", action="store_true")
     ap.add_argument("--lr", type=float, default=5e-6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
@@ -53,9 +54,8 @@ def config_dict(batch, world):
             "l2": "activations recorded for the backward pass (GBs) exceed the 126 MB L2"}
 
 
-def run_reference(args, rank):
-    if rank != 0:
-        return
+def cpu_reference_steps(n, budget_s):
+    """Oracle port of one fine-tuning step (forward + autograd backward + gradient norm) of ONE manual on the host cores."""
     import torch
     from oracle import berson_oracle as O
     from oracle import synth
@@ -68,14 +68,20 @@ def run_reference(args, rank):
     ids, labels, images = O.synthetic_manuals(1, N_STEPS, TOKENS, image_px=IMG, seed=1)
     inp = O.prepare_inputs(ids, labels, N_STEPS, images)
     times = []
-    n = min(args.steps + args.warmup, 3)
     for _ in range(n):
         t0 = time.time()
         loss, grads = TO.loss_grads(sd, cfg, inp)
         total, coef = TO.clip_coef(list(grads.values()), 1.0)
         times.append(time.time() - t0)
-        if sum(times) > 150:
+        if sum(times) > budget_s:
             break
+    return times, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    times, cores = cpu_reference_steps(min(args.steps + args.warmup, 3), 150)
     timed = times[1:] if len(times) > 1 else times
     ms = 1e3 * sum(timed) / len(timed)
     val = 1e3 / ms
@@ -204,6 +210,14 @@ def main():
                          "kernel_ms_per_step": pm.value / args.steps,
                          "kernel_share_of_step": (pm.value / args.steps) / (ms_total / args.steps),
                          "whole_step_tflops_per_gpu": 3 * FWD_FLOP_PER_MANUAL * B * args.steps / (ms_total / 1e3) / 1e12}}
+    if not args.no_cpu_baseline and world == 1:
+        with torch.enable_grad():
+            times, cores = cpu_reference_steps(2, 25.0)
+        timed = times[1:] if len(times) > 1 else times
+        line["cpu_baseline"] = {"value": len(timed) / sum(timed), "unit": "manuals/s", "cores": cores, "kind": "port",
+                                "sample": "%d optimizer step(s) of ONE manual of the same workload (forward + autograd backward + gradient "
+                                          "norm, no AdamW update) after %d warm-up, oracle port (torch fp32) on %d host threads" %
+                                          (len(timed), len(times) - len(timed), cores)}
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

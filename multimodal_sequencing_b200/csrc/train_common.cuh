@@ -85,6 +85,10 @@ inline void train_state_free_impl(TrainState* ts) {
   if (ts->adam_chunks) cudaFree(ts->adam_chunks);
   if (ts->tape.base) cudaFree(ts->tape.base);
   if (ts->htape.base) cudaFree(ts->htape.base);
+  if (ts->splitk.ready) {
+    for (int i = 0; i < SPLITK_MAX; ++i) { cudaStreamDestroy(ts->splitk.aux[i]); cudaEventDestroy(ts->splitk.join[i]); }
+    cudaEventDestroy(ts->splitk.fork);
+  }
   delete ts;
 }
 
