@@ -400,3 +400,51 @@ def test_pointer_module_p1_matches_reference(golden_dir):
     assert abs(loss.item() - g["loss"].item()) < 1e-5 * max(1.0, abs(g["loss"].item()))
     (out2,) = m({"input_ids": g["ids"].cuda()}, g["seq"].cuda())
     assert torch.equal(out2.cpu(), g["outputs"])
+
+
+def test_train_mode_autograd_bridge_host_logic(golden_dir):
+    """BertForOrdering.forward in train() mode, host side only (a stand-in engine supplies a known flat gradient buffer):
+    loss.backward() must hand every parameter its slice, scaled by the upstream gradient, leave parameters without a slot
+    at grad None, and accumulate over two backward passes like autograd does."""
+    g = torch.load(os.path.join(golden_dir, "text_tiny.pt"), weights_only=False)
+    model, _ = _build(g, 5, 4)
+    model.train()
+    named = [(n, p) for n, p in model.named_parameters()]
+    skip = {"classifier.weight", "classifier.bias", "two_level_encoder.h1_relationship.weight"}
+    layout, off = [], 0
+    for n, p in named:
+        if n in skip:
+            continue
+        layout.append((n, off, p.numel(), True))
+        off += (p.numel() + 63) // 64 * 64
+
+    class FakeEngine:
+        device = torch.device("cpu")
+
+        def train_layout(self):
+            return layout
+
+        def new_grad_buffer(self):
+            return torch.zeros(off)
+
+        def train_step(self, pb, flat, lam):
+            for i, (n, o, k, _) in enumerate(layout):
+                flat[o:o + k] += float(i + 1)
+            return torch.tensor(2.5)
+
+    model.engine = lambda: FakeEngine()
+    from oracle import berson_oracle as O
+    ids, labels, _ = O.synthetic_manuals(1, 5, 8, vocab=1000, seed=2)
+    bi = O.prepare_inputs(ids, labels, 5)
+    with torch.enable_grad(), pytest.warns(UserWarning, match="dropout"):
+        loss = model._forward(**bi)[0]
+        assert loss.requires_grad and abs(loss.item() - 2.5) < 1e-6
+        (loss * 0.5).backward()
+        loss2 = model._forward(**bi)[0]
+        loss2.backward()
+    idx = {n: i for i, (n, _, _, _) in enumerate(layout)}
+    for n, p in named:
+        if n in skip:
+            assert p.grad is None, n
+        else:
+            assert p.grad.shape == p.shape and torch.all(p.grad == 1.5 * (idx[n] + 1)), n
