@@ -547,23 +547,29 @@ def synthetic_manuals(B, n_steps, tokens_per_step=64, vocab=30522, image_px=None
 # --------------------------------------------------------------------------------------------
 
 
-def _bn(sd, name, x):
-    """eval-mode BatchNorm2d (running statistics, eps 1e-5)."""
-    w, b, m, v = sd[name + ".weight"], sd[name + ".bias"], sd[name + ".running_mean"], sd[name + ".running_var"]
+def _bn(sd, name, x, train=False):
+    """BatchNorm2d, eps 1e-5.  eval: running statistics.  train=True (the mode the reference fine-tunes in): statistics
+    of the batch itself -- mean and BIASED variance over (N, H, W), torch.nn.functional.batch_norm(training=True)."""
+    w, b = sd[name + ".weight"], sd[name + ".bias"]
+    if train:
+        m = x.mean(dim=(0, 2, 3))
+        v = ((x - m[None, :, None, None]) ** 2).mean(dim=(0, 2, 3))
+    else:
+        m, v = sd[name + ".running_mean"], sd[name + ".running_var"]
     return (x - m[None, :, None, None]) / torch.sqrt(v[None, :, None, None] + 1e-5) * w[None, :, None, None] + b[None, :, None, None]
 
 
-def _bottleneck(sd, pre, x, stride):
+def _bottleneck(sd, pre, x, stride, bn_train=False):
     """models/CLIP/clip/model.py:10-53: 1x1 -> 3x3 -> (avgpool) -> 1x1, anti-aliased down-sampling branch."""
-    out = torch.relu(_bn(sd, pre + "bn1", F.conv2d(x, sd[pre + "conv1.weight"])))
-    out = torch.relu(_bn(sd, pre + "bn2", F.conv2d(out, sd[pre + "conv2.weight"], padding=1)))
+    out = torch.relu(_bn(sd, pre + "bn1", F.conv2d(x, sd[pre + "conv1.weight"]), bn_train))
+    out = torch.relu(_bn(sd, pre + "bn2", F.conv2d(out, sd[pre + "conv2.weight"], padding=1), bn_train))
     if stride > 1:
         out = F.avg_pool2d(out, stride)
-    out = _bn(sd, pre + "bn3", F.conv2d(out, sd[pre + "conv3.weight"]))
+    out = _bn(sd, pre + "bn3", F.conv2d(out, sd[pre + "conv3.weight"]), bn_train)
     identity = x
     if (pre + "downsample.0.weight") in sd:
         identity = F.avg_pool2d(x, stride) if stride > 1 else x
-        identity = _bn(sd, pre + "downsample.1", F.conv2d(identity, sd[pre + "downsample.0.weight"]))
+        identity = _bn(sd, pre + "downsample.1", F.conv2d(identity, sd[pre + "downsample.0.weight"]), bn_train)
     return torch.relu(out + identity)
 
 
@@ -574,12 +580,14 @@ def rn_pair_tower(sd, pre, images, rn, img_len=2):
     Quirk reproduced (model.py:76): the NCHW feature maps of a pair are reshaped [R, C, g*g*img_len] WITHOUT moving the
     image axis, so token t / channel c' reads flat element c'*(g*g*img_len) + t of the pair's [img, C, g*g] block."""
     x = images
+    bn_train = bool(rn.get("bn_train", False))   # fine-tuning: BatchNorm over the batch of MATERIALISED pair images
     for i in (1, 2, 3):
-        x = torch.relu(_bn(sd, pre + "bn%d" % i, F.conv2d(x, sd[pre + "conv%d.weight" % i], stride=2 if i == 1 else 1, padding=1)))
+        x = torch.relu(_bn(sd, pre + "bn%d" % i, F.conv2d(x, sd[pre + "conv%d.weight" % i], stride=2 if i == 1 else 1, padding=1),
+                           bn_train))
     x = F.avg_pool2d(x, 2)
     for li, nblk in enumerate(rn["vision_layers"], start=1):
         for bi in range(nblk):
-            x = _bottleneck(sd, pre + "layer%d.%d." % (li, bi), x, 2 if (li > 1 and bi == 0) else 1)
+            x = _bottleneck(sd, pre + "layer%d.%d." % (li, bi), x, 2 if (li > 1 and bi == 0) else 1, bn_train)
     a = pre + "attnpool."
     R = x.shape[0] // img_len
     C, g2 = x.shape[1], x.shape[2] * x.shape[3]

@@ -64,6 +64,7 @@ def loss_grads(sd, cfg, inp, lam=0.6):
         loss.backward()
     grads = {k: v.grad for k, v in leaf.items() if torch.is_tensor(v) and v.is_floating_point() and v.grad is not None}
     lxrt = (cfg.get("vit") is not None or cfg.get("rn") is not None) and inp.get("images") is not None
+    grads = {k: v for k, v in grads.items() if "running_" not in k}   # BatchNorm buffers are not parameters
     return float(loss.detach()), _padding_idx_rows(grads, "bert.", lxrt)
 
 

@@ -6,6 +6,10 @@ BertForOrdering._forward (modeling_bert.py:943-1174) -> loss.backward() through 
 eval() mode (dropout off == the p = 0 semantics of the parity runs), for
   text  : the tiny text-only model / batch of text_tiny.pt's loss_case (3 five-step manuals)
   mm    : the tiny LXRT + CLIP-ViT model of mm_tiny.pt, one five-step manual (seed 45, 16 tokens per step)
+  mm_rn / mm_rn_bntrain : the tiny LXRT + ModifiedResNet ("RN50" wiring) model of mm_rn_tiny.pt, one five-step manual (seed 65);
+          first with the tower's BatchNorm in eval mode (running statistics), then with the WHOLE model in train() mode and every
+          dropout probability set to 0 -- the mode the reference actually fine-tunes in (BatchNorm uses the statistics of the
+          batch of materialised pair images).  Pins the oracle for the next scope row (backward through the RN50 tower).
 Per parameter the fixture keeps a compact summary (numel, float64 sum, float64 L2 norm, 32 strided samples): enough
 to pin the oracle's autograd (tests/test_oracle_golden.py) without committing two more copies of the weights.
 """
@@ -62,6 +66,19 @@ def main():
     ids, labels, images = O.synthetic_manuals(1, 5, 16, vocab=1000, image_px=224, seed=45)
     loss, g = grads_of(ns, model, args, ids, labels, images)
     res["mm"] = dict(loss=loss, grads=g, seed=45, B=1, N=5, L=16, image_checksum=float(images.double().sum()))
+    # RN50 wiring: eval-mode BatchNorm, then train() with all dropouts at 0
+    args = rh.make_args(5, 4, multimodal=True)
+    args.ff_size = 256
+    args.para_dropout = 0.0
+    tiny0 = dict(mg.TINY, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    ids, labels, images = O.synthetic_manuals(1, 5, 16, vocab=1000, image_px=224, seed=65)
+    for key, train in (("mm_rn", False), ("mm_rn_bntrain", True)):
+        model = rh.build_multimodal_model(ns, tiny0, args, seed=0, rn_cfg=mg.TINY_RN)
+        if train:
+            model.train()
+            assert all(m.p == 0.0 for m in model.modules() if isinstance(m, torch.nn.Dropout)), "a dropout is still active"
+        loss, g = grads_of(ns, model, args, ids, labels, images)
+        res[key] = dict(loss=loss, grads=g, seed=65, B=1, N=5, L=16, image_checksum=float(images.double().sum()))
     torch.save(res, os.path.join(HERE, "grads_tiny.pt"))
     for k, v in res.items():
         print(k, "loss", v["loss"], "params with grad", len(v["grads"]))
