@@ -309,3 +309,15 @@ def test_gemm_tn_operands_vs_float64(shape):
     err = (out.double() - ref).abs().max().item()
     bound = 2e-5 * (K ** 0.5) * 4 + 1e-3      # fp32 accumulation of K bf16 x bf16 products of O(1) magnitude
     assert err <= bound * max(1.0, ref.abs().max().item() / (K ** 0.5)), (err, bound)
+
+
+@pytest.mark.parametrize("precise", [True, False])
+def test_multimodal_train_step_two_manuals(golden_dir, precise):
+    """B = 2 multimodal manuals of 4 steps (unique-image table shared across the batch, pair rows of both manuals in one
+    encoder pass) against oracle autograd."""
+    g = torch.load(os.path.join(golden_dir, "mm_tiny.pt"), weights_only=False)
+    eng, pb, grads, loss, oloss, ref = _full_step(g, True, precise, 2, 4, 12, 91)
+    assert abs(loss - oloss) < (5e-5 if precise else 2e-2)
+    worst = _compare(eng.grads_by_name(grads), ref, 5e-4 if precise else 1e-1)
+    print("multimodal B=2 train step (%s): loss %.6f (oracle %.6f), worst relative L2 %.2e at %s" %
+          ("fp32" if precise else "bf16", loss, oloss, worst[1], worst[0]))
