@@ -321,3 +321,33 @@ def test_multimodal_train_step_two_manuals(golden_dir, precise):
     worst = _compare(eng.grads_by_name(grads), ref, 5e-4 if precise else 1e-1)
     print("multimodal B=2 train step (%s): loss %.6f (oracle %.6f), worst relative L2 %.2e at %s" %
           ("fp32" if precise else "bf16", loss, oloss, worst[1], worst[0]))
+
+
+def test_full_size_gradient_additivity_over_the_batch():
+    """Size-independent property at BASELINE configs[3] size (BERT-base + ViT-B/32, six-step manuals, bf16 tensor-core path):
+    the loss is a batch mean, so one step on {a, b} must equal the two single-manual steps accumulated into one buffer and
+    halved -- loss exactly so up to fp32 rounding, gradients up to the summation order of the weight-gradient GEMMs."""
+    from oracle import synth
+    cfg = dict(synth.BERT_BASE)
+    vit = dict(synth.VIT_B32)
+    cfg.update(vit=vit, rn=None, para_ff=3072)
+    eng = _engine(synth.full_state_dict(cfg, vit, seed=0), cfg, False)
+    ids, labels, images = O.synthetic_manuals(2, 6, 64, image_px=224, seed=12)
+    both = eng.new_grad_buffer()
+    loss_ab = float(eng.train_step(eng.prepare(ids, labels, 6, images), both))
+    acc = eng.new_grad_buffer()
+    la = float(eng.train_step(eng.prepare(ids[:1], labels[:1], 6, images[:1]), acc))
+    lb = float(eng.train_step(eng.prepare(ids[1:], labels[1:], 6, images[1:]), acc))   # accumulates
+    torch.cuda.synchronize()
+    assert abs(loss_ab - 0.5 * (la + lb)) < 2e-5
+    worst = ("", 0.0)
+    for n, o, k, _ in eng.train_layout():
+        a, b = both[o:o + k], 0.5 * acc[o:o + k]
+        ref = float(b.norm())
+        if ref < 1e-7:
+            continue
+        err = float((a - b).norm()) / ref
+        if err > worst[1]:
+            worst = (n, err)
+        assert err < 2e-2 or n.endswith(_ZERO_GRAD), "%s: %.3e" % (n, err)
+    print("batch additivity at full size: loss %.6f vs %.6f, worst relative L2 %.2e at %s" % (loss_ab, 0.5 * (la + lb), worst[1], worst[0]))
