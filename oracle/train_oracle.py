@@ -6,14 +6,14 @@ models/CLIP/src/lxrt/modeling.py:1513-1598.  PIN: tests/golden/grads_tiny.pt hol
 reference produced (tests/golden/make_golden_grads.py); tests/test_oracle_golden.py checks `loss_grads` against them.
 
 Optimizer: the reference uses transformers.AdamW (trainers/train.py:36,185; transformers==3.4.0 per requirements.txt),
-which the installed transformers 5.5 no longer ships.  `hf_adamw_step` restates its published algorithm
-(transformers/optimization.py, class AdamW, correct_bias=True):
+which the installed transformers 5.5 no longer ships -- but the reference tree vendors the same class in
+models/berson/optimization.py:107-189.  `hf_adamw_step` restates it (correct_bias=True):
     exp_avg    = b1 exp_avg + (1 - b1) g
     exp_avg_sq = b2 exp_avg_sq + (1 - b2) g^2
     p -= lr sqrt(1 - b2^t) / (1 - b1^t) * exp_avg / (sqrt(exp_avg_sq) + eps)
     p -= lr * weight_decay * p                      (decoupled, after the Adam update)
-PARITY UNPINNED for this one function (no copy of transformers 3.4 in the image); the clip is
-torch.nn.utils.clip_grad_norm_ (train.py:358) and is checked against torch itself.
+PIN: tests/test_train_oracle.py runs the vendored class itself (loaded from /root/reference) against this function; the
+clip is torch.nn.utils.clip_grad_norm_ (train.py:358) and is checked against torch itself.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
 """

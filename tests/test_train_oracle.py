@@ -105,3 +105,30 @@ def test_hf_adamw_known_answer():
     assert abs(float(p3) - (0.9 - 0.1 * 0.5 * 0.9)) < 1e-7
     assert TO.decays("bert.encoder.layer.0.output.dense.weight") and not TO.decays("bert.encoder.layer.0.output.dense.bias")
     assert not TO.decays("bert.embeddings.LayerNorm.weight") and TO.decays("bert.encoder.visn_fc.visn_layer_norm.weight")
+
+
+def test_hf_adamw_matches_the_reference_vendored_class():
+    """trainers/train.py imports AdamW from transformers 3.4; the reference tree vendors the same class in
+    models/berson/optimization.py:107-189.  Run THAT code (loaded from /root/reference, skipped where the checkout is absent)
+    against the oracle's restatement: five steps, weight decay on, fp32."""
+    import importlib.util
+    import warnings
+    path = "/root/reference/models/berson/optimization.py"
+    if not os.path.exists(path):
+        import pytest
+        pytest.skip("reference checkout not present")
+    spec = importlib.util.spec_from_file_location("ref_berson_optimization", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gen = torch.Generator().manual_seed(5)
+    p_ref = torch.nn.Parameter(torch.randn(37, 11, generator=gen))
+    p, m, v = p_ref.detach().clone(), torch.zeros(37, 11), torch.zeros(37, 11)
+    opt = mod.AdamW([p_ref], lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05, correct_bias=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")     # deprecated add_/addcdiv_ overloads of torch 1.x, same arithmetic
+        for step in range(1, 6):
+            g = torch.randn(37, 11, generator=gen) * (0.1 * step)
+            p_ref.grad = g.clone()
+            opt.step()
+            TO.hf_adamw_step(p, g, m, v, step, lr=3e-3, eps=1e-8, weight_decay=0.05)
+            assert (p - p_ref.detach()).abs().max() <= 1e-7 * max(1.0, float(p.abs().max())), step
