@@ -7,6 +7,9 @@ Training: `forward(inputs)` in train() mode returns a loss whose .backward() fil
 gradients the CUDA backward pass produced (msq_train_step), so trainers/train.py:340-363 (loss.backward();
 clip_grad_norm_(model.parameters()); optimizer.step(); model.zero_grad()) runs unchanged; `finetune_step` is the fused
 device-side alternative (clip + transformers.AdamW inside the library, no weight round trip).  Dropout is not applied."""
+import copy
+import json
+import os
 import types
 import warnings
 
@@ -113,7 +116,80 @@ class _DeviceBackward(torch.autograd.Function):
         return tuple(out)
 
 
-class BertModel(nn.Module, _EngineOwner):
+WEIGHTS_NAME, CONFIG_NAME = "pytorch_model.bin", "config.json"   # models/berson/file_utils / modeling_utils constants
+
+
+class _Pretrained:
+    """save_pretrained / from_pretrained of the reference's PreTrainedModel (models/berson/modeling_utils.py:190-400) for local
+    directories and files -- the forms trainers/train.py uses (404, 2030-2035, 2194-2199).  No hub downloads, no TF checkpoints."""
+
+    base_model_prefix = "bert"
+
+    def save_pretrained(self, save_directory):
+        assert os.path.isdir(save_directory), "Saving path should be a directory where the model and configuration can be saved"
+        model_to_save = self.module if hasattr(self, "module") else self
+        if model_to_save.__dict__.get("_flat") is not None:     # fused finetune_step ran: the fp32 masters live in the library
+            model_to_save.pull_weights()
+        cfg = {k: v for k, v in vars(model_to_save.config).items() if isinstance(v, (int, float, str, bool, list, dict, type(None)))}
+        with open(os.path.join(save_directory, CONFIG_NAME), "w", encoding="utf-8") as fh:
+            json.dump(cfg, fh, indent=2, sort_keys=True)
+        torch.save(model_to_save.state_dict(), os.path.join(save_directory, WEIGHTS_NAME))
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, *model_args, **kwargs):
+        config = kwargs.pop("config", None)
+        state_dict = kwargs.pop("state_dict", None)
+        output_loading_info = kwargs.pop("output_loading_info", False)
+        for k in ("cache_dir", "force_download", "proxies"):
+            kwargs.pop(k, None)
+        if kwargs.pop("from_tf", False):
+            raise NotImplementedError("TensorFlow checkpoints are not supported by the B200 drop-in")
+        path = pretrained_model_name_or_path
+        if config is None:
+            cfg_file = os.path.join(path, CONFIG_NAME) if os.path.isdir(path) else path
+            with open(cfg_file, "r", encoding="utf-8") as fh:
+                d = json.load(fh)
+            vocab = d.pop("vocab_size", d.pop("vocab_size_or_config_json_file", 30522))
+            config = BertConfig(vocab, **d)
+        if state_dict is None and path is not None:
+            if os.path.isdir(path):
+                archive = os.path.join(path, WEIGHTS_NAME)
+                if not os.path.isfile(archive):
+                    raise EnvironmentError("Error no file named {} found in directory {}".format(WEIGHTS_NAME, path))
+            elif os.path.isfile(path):
+                archive = path
+            else:
+                raise EnvironmentError("Model name '{}' was not found: only local directories / files are supported".format(path))
+            state_dict = torch.load(archive, map_location="cpu")
+        model = cls(config, *model_args, **kwargs)
+        missing, unexpected, errors = [], [], []
+        if state_dict is not None:
+            # old TF-style LayerNorm names (modeling_utils.py: gamma -> weight, beta -> bias)
+            state_dict = {k.replace("gamma", "weight").replace("beta", "bias") if ("gamma" in k or "beta" in k) else k: v
+                          for k, v in state_dict.items()}
+            pre = cls.base_model_prefix
+            has_base, ckpt_has_base = hasattr(model, pre), any(k.startswith(pre + ".") for k in state_dict)
+            target = model
+            if not has_base and ckpt_has_base:          # bare inner model <- checkpoint of a model with heads
+                state_dict = {k[len(pre) + 1:]: v for k, v in state_dict.items() if k.startswith(pre + ".")}
+            elif has_base and not ckpt_has_base:        # model with heads <- checkpoint of the bare inner model
+                target = getattr(model, pre)
+            own = target.state_dict()
+            for k, v in state_dict.items():
+                if k in own and tuple(own[k].shape) != tuple(v.shape):
+                    errors.append("size mismatch for {}: copying a param with shape {} from checkpoint, the shape in current model "
+                                  "is {}.".format(k, tuple(v.shape), tuple(own[k].shape)))
+            if errors:
+                raise RuntimeError("Error(s) in loading state_dict for {}:\n\t{}".format(model.__class__.__name__, "\n\t".join(errors)))
+            res = target.load_state_dict(state_dict, strict=False)
+            missing, unexpected = list(res.missing_keys), list(res.unexpected_keys)
+        model.eval()
+        if output_loading_info:
+            return model, {"missing_keys": missing, "unexpected_keys": unexpected, "error_msgs": errors}
+        return model
+
+
+class BertModel(nn.Module, _EngineOwner, _Pretrained):
     """Text-only inner encoder (modeling_bert.py:563-663): forward -> (sequence_output, sequence_output[:, 0])."""
 
     def __init__(self, config):
@@ -185,7 +261,7 @@ class TransformerInterEncoder(nn.Module):
         self.layer_norm = nn.LayerNorm(d_model, eps=1e-6)
 
 
-class BertForOrdering(nn.Module, _EngineOwner):
+class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
     """models/berson/modeling_bert.py:825-1402."""
 
     def __init__(self, config, args, inner_model=None, tokenizer=None, load_inner_model=False, **kwargs):

@@ -448,3 +448,37 @@ def test_train_mode_autograd_bridge_host_logic(golden_dir):
             assert p.grad is None, n
         else:
             assert p.grad.shape == p.shape and torch.all(p.grad == 1.5 * (idx[n] + 1)), n
+
+
+def test_save_and_from_pretrained_round_trip(golden_dir, tmp_path):
+    """trainers/train.py:404 save_pretrained(dir) and 2030-2035 from_pretrained(dir, inner_model=, tokenizer=, config=,
+    load_inner_model=True, args=): weights and configuration survive the round trip, a bare-BertModel checkpoint loads into
+    the model with heads (base_model_prefix rule), a shape mismatch raises like torch's loader does."""
+    from models.berson.modeling_bert import BertModel
+    g = torch.load(os.path.join(golden_dir, "text_tiny.pt"), weights_only=False)
+    model, args = _build(g, 5, 4)
+    model.load_state_dict(g["sd"], strict=False)
+    d = tmp_path / "ckpt"
+    d.mkdir()
+    model.save_pretrained(str(d))
+    assert (d / "pytorch_model.bin").exists() and (d / "config.json").exists()
+    again = BertForOrdering.from_pretrained(str(d), args=args)              # config read back from config.json
+    assert not again.training and again.config.hidden_size == model.config.hidden_size
+    for k, v in model.state_dict().items():
+        assert torch.equal(again.state_dict()[k], v), k
+    again2, info = BertForOrdering.from_pretrained(str(d), config=model.config, args=args, output_loading_info=True)
+    assert info["missing_keys"] == [] and info["unexpected_keys"] == []
+    # bare inner model checkpoint -> model with heads, and the other way round
+    inner_dir = tmp_path / "inner"
+    inner_dir.mkdir()
+    model.bert.save_pretrained(str(inner_dir))
+    fresh = BertForOrdering.from_pretrained(str(inner_dir), config=model.config, args=args)
+    assert torch.equal(fresh.bert.state_dict()["embeddings.word_embeddings.weight"], model.bert.state_dict()["embeddings.word_embeddings.weight"])
+    bare = BertModel.from_pretrained(str(d), config=model.config)
+    assert torch.equal(bare.state_dict()["encoder.layer.1.output.dense.weight"], model.state_dict()["bert.encoder.layer.1.output.dense.weight"])
+    bad = dict(model.state_dict())
+    bad["key_linear.weight"] = torch.zeros(3, 3)
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        BertForOrdering.from_pretrained(None, config=model.config, state_dict=bad, args=args)
+    with pytest.raises(EnvironmentError):
+        BertForOrdering.from_pretrained(str(tmp_path / "nowhere"), config=model.config, args=args)
