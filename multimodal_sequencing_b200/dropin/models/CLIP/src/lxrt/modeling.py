@@ -2,6 +2,9 @@
 (1456-1598) in CLIP / visualbert-style mode.  Same constructor kwargs, forward signature and state_dict
 keys; the forward is msq_inner_forward (ViT or ResNet pair tower -> [+ visual_pos +
 visual_token_type for the ResNet] -> visn_fc -> joint BERT)."""
+import json
+import os
+
 import torch
 import torch.nn as nn
 
@@ -77,6 +80,51 @@ class LXRTModel(nn.Module):
         if self.topo_sort:
             self.classifier = _holder(dense=nn.Linear(H, H), out_proj=nn.Linear(H, self.num_labels))
         self.apply(lambda m: _init_bert_weights(m, config.initializer_range))  # 1464: re-initialises the tower's Linears too
+
+    # ---- checkpoints (lxrt/modeling.py:1257-1450): local directories only -- no downloads, no tar archives, no TF
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, state_dict=None, cache_dir=None, from_tf=False, *inputs, **kwargs):
+        """Directory with config.json + pytorch_model.bin (what save_pretrained writes).  As in the reference, a checkpoint whose
+        keys carry a `bert.` or `roberta.` prefix is loaded into this (prefix-less) body, old gamma/beta LayerNorm names are
+        renamed, missing / unexpected keys are tolerated and a shape mismatch raises RuntimeError."""
+        if from_tf:
+            raise NotImplementedError("TensorFlow checkpoints are not supported by the B200 drop-in")
+        path = pretrained_model_name_or_path
+        if not os.path.isdir(path):
+            raise EnvironmentError("Model name '{}' was not found: only local checkpoint directories are supported".format(path))
+        with open(os.path.join(path, "config.json"), "r", encoding="utf-8") as fh:
+            d = json.load(fh)
+        vocab = d.pop("vocab_size", d.pop("vocab_size_or_config_json_file", 30522))
+        known = ("hidden_size", "num_hidden_layers", "num_attention_heads", "intermediate_size", "hidden_act", "hidden_dropout_prob",
+                 "attention_probs_dropout_prob", "max_position_embeddings", "type_vocab_size", "initializer_range")
+        config = BertConfig(vocab, **{k: d[k] for k in known if k in d})
+        model = cls(config, *inputs, **kwargs)
+        if state_dict is None:
+            state_dict = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu")
+        sd = {}
+        for k, v in state_dict.items():
+            k = k.replace("gamma", "weight") if "gamma" in k else k
+            k = k.replace("beta", "bias") if "beta" in k else k
+            sd[k] = v
+        for pre in ("bert.", "roberta."):
+            if any(k.startswith(pre) for k in sd):
+                sd = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+                break
+        own = model.state_dict()
+        errors = ["size mismatch for {}: copying a param with shape {} from checkpoint, the shape in current model is {}.".format(
+            k, tuple(v.shape), tuple(own[k].shape)) for k, v in sd.items() if k in own and tuple(own[k].shape) != tuple(v.shape)]
+        if errors:
+            raise RuntimeError("Error(s) in loading state_dict for {}:\n\t{}".format(cls.__name__, "\n\t".join(errors)))
+        model.load_state_dict(sd, strict=False)
+        return model
+
+    def save_pretrained(self, save_directory):
+        assert os.path.isdir(save_directory), "Saving path should be a directory where the model and configuration can be saved"
+        model_to_save = self.module if hasattr(self, "module") else self
+        cfg = {k: v for k, v in vars(model_to_save.config).items() if isinstance(v, (int, float, str, bool, list, dict, type(None)))}
+        with open(os.path.join(save_directory, "config.json"), "w", encoding="utf-8") as fh:
+            json.dump(cfg, fh, indent=2, sort_keys=True)
+        torch.save(model_to_save.state_dict(), os.path.join(save_directory, "pytorch_model.bin"))
 
     def _engine(self):
         sig = tuple(t._version for t in list(self.parameters()) + list(self.buffers())) + (bool(getattr(self, "precise", False)),)

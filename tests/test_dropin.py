@@ -482,3 +482,27 @@ def test_save_and_from_pretrained_round_trip(golden_dir, tmp_path):
         BertForOrdering.from_pretrained(None, config=model.config, state_dict=bad, args=args)
     with pytest.raises(EnvironmentError):
         BertForOrdering.from_pretrained(str(tmp_path / "nowhere"), config=model.config, args=args)
+
+
+def test_lxrt_from_pretrained_prefix_rules(golden_dir, tmp_path):
+    """LXRTModel.from_pretrained(path, **kwargs) (train.py:1869-1880; lxrt/modeling.py:1257-1430): config.json +
+    pytorch_model.bin from a directory; `bert.`-prefixed checkpoints load into the prefix-less body."""
+    g = torch.load(os.path.join(golden_dir, "mm_tiny.pt"), weights_only=False)
+    model, _ = _build(g, 5, 4)
+    model.load_state_dict(g["sd"], strict=False)
+    kw = dict(clip_model_name="ViT-B/32", clip_config=g["vit"], cls_id=101, sep_id=102, max_story_length=5)
+    d = tmp_path / "lxrt"
+    d.mkdir()
+    model.bert.save_pretrained(str(d))
+    a = LXRTModel.from_pretrained(str(d), **kw)
+    for k, v in model.bert.state_dict().items():
+        assert torch.equal(a.state_dict()[k], v), k
+    # a checkpoint written by the wrapper (keys "bert.*" + heads) loads into the bare body as well
+    d2 = tmp_path / "wrapper"
+    d2.mkdir()
+    model.bert.save_pretrained(str(d2))
+    torch.save(model.state_dict(), str(d2 / "pytorch_model.bin"))
+    b = LXRTModel.from_pretrained(str(d2), **kw)
+    assert torch.equal(b.state_dict()["encoder.layer.0.output.dense.weight"], model.state_dict()["bert.encoder.layer.0.output.dense.weight"])
+    with pytest.raises(EnvironmentError):
+        LXRTModel.from_pretrained(str(tmp_path / "missing"), **kw)
