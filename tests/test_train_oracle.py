@@ -132,3 +132,17 @@ def test_hf_adamw_matches_the_reference_vendored_class():
             opt.step()
             TO.hf_adamw_step(p, g, m, v, step, lr=3e-3, eps=1e-8, weight_decay=0.05)
             assert (p - p_ref.detach()).abs().max() <= 1e-7 * max(1.0, float(p.abs().max())), step
+
+
+def test_linear_schedule_matches_transformers():
+    """trainers/train.py:187 get_linear_schedule_with_warmup: the fused path's pure-function schedule against the library's
+    LambdaLR over a dummy optimizer, step by step."""
+    from transformers import get_linear_schedule_with_warmup
+    from multimodal_sequencing_b200.schedule import linear_schedule_with_warmup
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=5e-6)
+    sch = get_linear_schedule_with_warmup(opt, num_warmup_steps=7, num_training_steps=40)
+    for step in range(45):
+        assert abs(sch.get_last_lr()[0] - linear_schedule_with_warmup(5e-6, step, 7, 40)) < 1e-18, step
+        opt.step()
+        sch.step()
