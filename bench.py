@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="manuals per step per GPU")
     ap.add_argument("--precise", action="store_true", help="fp32 FFMA parity mode instead of bf16 tcgen05")
+    ap.add_argument("--precision", default=None, choices=["bf16", "bf16x3", "fp32"],
+                    help="encoder arithmetic: bf16 tcgen05 operands, bf16x3 (hi+lo bf16 operands, 3 MMAs per product) or fp32 FFMA")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--text", default="bert-base", choices=["bert-base", "roberta-large"],
                     help="joint encoder sizing: BERT-base (BASELINE configs, the headline) or the roberta-large config the "
@@ -191,7 +193,8 @@ def main():
     vit, rn = _towers(args.backbone)
     cfg.update(vit=vit, rn=rn, para_ff=3072)
     sd = synth.full_state_dict(cfg, vit, seed=0, rn=rn)
-    eng = OrderingEngine(sd, cfg, precise=args.precise, device=dev)
+    precision = args.precision or ("fp32" if args.precise else "bf16")
+    eng = OrderingEngine(sd, cfg, precise=precision, device=dev)
     del sd
     lib = _lib.load()
 
@@ -272,7 +275,7 @@ def main():
     ach = (pf.value / 1e12) / (pm.value / 1e3) if pm.value > 0 else None
     line = {"metric": "5-step manuals ordered/sec (beam=4)", "value": value, "unit": "manuals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precise else "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32"}.get(precision, precision), "data": "synthetic",
             "config": dict(config_dict(B, world, args.backbone), text_encoder=args.text), "impl": "ours",
             "e2e": {"value": e2e, "unit": "manuals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "OrderingEngine.order_host -> msq_order_manuals_host (pinned host buffers)"},

@@ -38,7 +38,12 @@ typedef struct msq_config {
   int32_t para_heads;    /* 8 */
   int32_t para_ff;       /* 3072 */
   int32_t para_layers;   /* 2 */
-  int32_t precise;       /* 0: bf16 tcgen05 tensor-core encoder; 1: fp32 FFMA encoder (parity mode) */
+  int32_t precise;       /* 0: bf16 tcgen05 tensor-core encoder (fastest, ~1e-2 of fp32);
+                          * 1: fp32 FFMA encoder (CUDA cores; 1e-5 parity mode, slow);
+                          * 2: "bf16x3" tcgen05 encoder: every operand is carried as hi + lo bf16 (16 significand bits),
+                          *    every product is a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with fp32 accumulation, activations
+                          *    are exact (erff / tanhf): outputs within ~1e-5 of fp32 at tensor-core speed.  Evaluation
+                          *    only; ViT / text-only models (not the ModifiedResNet tower). */
   int32_t reserved;
   /* CLIP ModifiedResNet backbone ("RN50", models/CLIP/clip/model.py:128-187), the reference's wired default
    * (param.py VISUAL_CONFIG.clip_model_name).  rn_width != 0 selects it; then vit_width must hold the tower's
@@ -212,6 +217,10 @@ int msq_layernorm(int32_t dtype, const float* x_dev, int64_t rows, int32_t H, co
 int msq_attention(int32_t dtype, const void* qkv_dev, int64_t R, int32_t L, int32_t heads, float scale,
                   const float* mask_add_dev, int32_t mask_len, void* ctx_dev, void* stream);
 int msq_f32_to_bf16(const float* src_dev, void* dst_dev, int64_t n, void* stream);
+/* fp32 [rows,K] -> split-bf16 rows [hi(K) | lo(K)] (bf16 x 2K per row): the operand layout of the bf16x3 mode, accepted by
+ * msq_gemm dtype 6 (fp32 out) / 7 (split-bf16 out [M, hi(N)|lo(N)]), msq_attention dtype 2 (qkv rows
+ * [hi(3*heads*64) | lo(..)], ctx rows [hi(heads*64) | lo(..)]) and produced by msq_layernorm dtype 2. */
+int msq_f32_to_bf16_split(const float* src_dev, void* dst_dev, int64_t rows, int32_t K, void* stream);
 
 #ifdef __cplusplus
 }

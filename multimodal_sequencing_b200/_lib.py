@@ -56,6 +56,7 @@ SIGNATURES = {
     "msq_layernorm": (C.c_int, [_I32, _P, _I64, _I32, _P, _P, _F, _P, _P]),
     "msq_attention": (C.c_int, [_I32, _P, _I64, _I32, _I32, _F, _P, _I32, _P, _P]),
     "msq_f32_to_bf16": (C.c_int, [_P, _P, _I64, _P]),
+    "msq_f32_to_bf16_split": (C.c_int, [_P, _P, _I64, _I32, _P]),
 }
 
 _lib = None

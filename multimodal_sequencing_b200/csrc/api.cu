@@ -118,7 +118,12 @@ static int make_lin(msq_model* m, const float* w, const float* b, int N, int K, 
   } else {
     out->w32 = w;
   }
-  if (want16) {
+  if (want16 && m->cfg.precise == 2) {   // bf16x3 mode: rows [hi(Kp) | lo(Kp)]
+    bf16s* w16;
+    MSQ_TRY(dev_alloc(m, (size_t)N * Kp, &w16));
+    MSQ_TRY(pack_pad<bf16s>(w, N, K, Kp, w16, st));
+    out->w16 = reinterpret_cast<const bf16*>(w16);
+  } else if (want16) {
     bf16* w16;
     MSQ_TRY(dev_alloc(m, (size_t)N * Kp, &w16));
     MSQ_TRY(pack_pad<bf16>(w, N, K, Kp, w16, st));
@@ -286,7 +291,7 @@ bool model_use_tc(const msq_model* m) { return use_tc(m); }
 static bool use_tc(const msq_model* m) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("MSQ_FORCE_SIMT"); forced = (e && e[0] == '1') ? 1 : 0; }
-  return !m->cfg.precise && !forced && gemm_tc_selftest_supported();
+  return m->cfg.precise != 1 && !forced && gemm_tc_selftest_supported();
 }
 
 // C = act(A W^T + b) + resid, A in T, output in TO
@@ -296,9 +301,15 @@ static int run_gemm(const msq_model* m, const T* A, int lda, const Lin& w, const
   GemmArgs g;
   g.A = A; g.bias = with_bias ? w.b : nullptr; g.resid = resid; g.C = C; g.C2 = nullptr;
   g.M = M; g.N = w.N; g.K = w.K; g.lda = lda; g.ldw = w.ld; g.ldc = ldc; g.ldr = ldr; g.act = act;
-  if constexpr (sizeof(T) == 4) {
+  if constexpr (same_type<T, float>::value) {
     g.W = w.w32;
     return gemm_simt<float, TO>(g, st);
+  } else if constexpr (is_split<T>::value) {
+    // bf16x3 mode: tensor cores only (split operands have no FFMA twin; the fp32 parity mode is the CUDA-core path)
+    g.W = w.w16; g.split = 1;
+    MSQ_REQUIRE(w.w16 != nullptr, "split-bf16 weight copy missing");
+    MSQ_REQUIRE(use_tc(m) && g.K % 64 == 0 && g.N % 8 == 0 && ldc % 8 == 0, "bf16x3 mode: GEMM N=%d K=%d not supported by the tcgen05 kernel", g.N, g.K);
+    return gemm_tc<TO>(g, st);
   } else {
     g.W = w.w16;
     MSQ_REQUIRE(w.w16 != nullptr, "bf16 weight copy missing");
@@ -389,6 +400,9 @@ extern "C" int msq_model_create(const msq_config* cfg, msq_model** out) {
     MSQ_REQUIRE(cfg->vit_res % cfg->vit_patch == 0 && cfg->vit_patch % 4 == 0, "vit patch/res");
   }
   MSQ_REQUIRE(cfg->para_heads >= 1 && cfg->hidden % cfg->para_heads == 0 && cfg->para_ff % 16 == 0, "bad paragraph config");
+  MSQ_REQUIRE(cfg->precise >= 0 && cfg->precise <= 2, "precise=%d: 0 bf16, 1 fp32, 2 bf16x3", cfg->precise);
+  MSQ_REQUIRE(!(cfg->precise == 2 && cfg->rn_width), "the bf16x3 mode does not cover the ModifiedResNet tower (use precise 0 or 1)");
+  MSQ_REQUIRE(!(cfg->precise == 2 && (cfg->inter % 64 || cfg->vit_width % 64)), "the bf16x3 mode needs inter and vit_width to be multiples of 64");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     set_error("no CUDA device: this library has no CPU fallback");
@@ -419,7 +433,8 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const msq_config& c = m->cfg;
   const int H = c.hidden;
-  const bool w16 = !c.precise;
+  const bool w16 = c.precise != 1;
+  const bool fold = c.precise == 0;   // deferred-LayerNorm copies: plain bf16 tensor-core path only
   std::string miss;
   const std::string P = m->prefix_inner;
   auto W = [&](const std::string& n, int64_t numel) {
@@ -522,7 +537,7 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
                      w16, &L.down, st));
     L.ln1 = {W(b + "attention.output.LayerNorm.weight", H), W(b + "attention.output.LayerNorm.bias", H)};
     L.ln2 = {W(b + "output.LayerNorm.weight", H), W(b + "output.LayerNorm.bias", H)};
-    if (w16 && miss.empty()) {   // deferred-LayerNorm copies (tensor-core path only)
+    if (fold && miss.empty()) {   // deferred-LayerNorm copies (tensor-core path only)
       MSQ_TRY(make_folded(m, L.up, L.ln1, &L.up_f, st));
       if (l >= 1) MSQ_TRY(make_folded(m, L.qkv, m->bert[l - 1].ln2, &L.qkv_f, st));
       m->folded = true;
@@ -615,7 +630,7 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
                        &L.proj, st));
       L.ln1 = {W(b + "ln_1.weight", Wd), W(b + "ln_1.bias", Wd)};
       L.ln2 = {W(b + "ln_2.weight", Wd), W(b + "ln_2.bias", Wd)};
-      if (w16 && miss.empty()) {
+      if (fold && miss.empty()) {
         MSQ_TRY(make_folded(m, L.qkv, L.ln1, &L.qkv_f, st));
         MSQ_TRY(make_folded(m, L.fc, L.ln2, &L.fc_f, st));
         m->folded = true;
@@ -625,7 +640,7 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
       MSQ_TRY(make_lin(m, W(P + "encoder.visn_fc.visn_fc.weight", (int64_t)H * Wd), W(P + "encoder.visn_fc.visn_fc.bias", H), H, Wd, Wd,
                        w16, &m->visn_fc, st));
       m->visn_ln = {W(P + "encoder.visn_fc.visn_layer_norm.weight", H), W(P + "encoder.visn_fc.visn_layer_norm.bias", H)};
-      if (w16 && miss.empty()) MSQ_TRY(make_folded(m, m->visn_fc, m->ln_post, &m->visn_fc_f, st));
+      if (fold && miss.empty()) MSQ_TRY(make_folded(m, m->visn_fc, m->ln_post, &m->visn_fc_f, st));
     }
   }
   // ---- BERSON heads
@@ -769,7 +784,7 @@ static int run_vit(msq_model* m, const int32_t* img_index, int64_t R, VitBufs& b
   const int64_t Mv = R * Lv;
   MSQ_TRY(vit_assemble(b.patch, img_index, R, 2, g2, Wd, m->vit_cls, m->vit_pos, m->ln_pre.g, m->ln_pre.b, 1e-5f, b.xv, st));
   b.post_pending = false;
-  if constexpr (sizeof(T) == 2) {
+  if constexpr (same_type<T, bf16>::value) {
     if (ln_fold_enabled(m) && m->folded && !m->vit.empty() && !gemm_ln_enabled()) {
       // Deferred LayerNorm: the residual stream x stays raw (fp32 b.xv + bf16 copy b.y + per-row partial sums written by
       // the residual GEMMs); ln_2 / the next ln_1 / ln_post are applied inside the consuming GEMMs' epilogues.
@@ -935,16 +950,27 @@ static int run_rn_pool(msq_model* m, const int32_t* img_index, int64_t R, VitBuf
 // backbone dispatch: per-image part (patch embedding / ResNet trunk) and per-pair part (transformer / attention pool)
 template <typename T>
 static void plan_visual(const msq_config& c, Planner& p, int64_t n_img, int64_t R, VitBufs* b) {
-  if (c.rn_width) plan_rn<T>(c, p, n_img, R, b); else plan_vit<T>(c, p, n_img, R, b);
+  if constexpr (!is_split<T>::value) { if (c.rn_width) { plan_rn<T>(c, p, n_img, R, b); return; } }
+  plan_vit<T>(c, p, n_img, R, b);
 }
 template <typename T>
 static int run_visual_images(msq_model* m, const float* images, int64_t n_img, VitBufs& b, cudaStream_t st, int64_t first = 0) {
-  return m->cfg.rn_width ? run_rn_trunk<T>(m, images, n_img, b, st, first) : run_patch_embed<T>(m, images, n_img, b, st, first);
+  if constexpr (!is_split<T>::value) { if (m->cfg.rn_width) return run_rn_trunk<T>(m, images, n_img, b, st, first); }
+  return run_patch_embed<T>(m, images, n_img, b, st, first);
 }
 template <typename T>
 static int run_visual_pairs(msq_model* m, const int32_t* img_index, int64_t R, VitBufs& b, cudaStream_t st) {
-  return m->cfg.rn_width ? run_rn_pool<T>(m, img_index, R, b, st) : run_vit<T>(m, img_index, R, b, st);
+  if constexpr (!is_split<T>::value) { if (m->cfg.rn_width) return run_rn_pool<T>(m, img_index, R, b, st); }
+  return run_vit<T>(m, img_index, R, b, st);
 }
+
+// precision dispatch: msq_config.precise 0 = bf16 operands, 1 = fp32 FFMA, 2 = bf16x3 (split bf16 operands)
+#define MSQ_DISPATCH_T(m, CALL)                                  \
+  do {                                                           \
+    if ((m)->cfg.precise == 1) { using T = float; return CALL; } \
+    if ((m)->cfg.precise == 2) { using T = bf16s; return CALL; } \
+    { using T = bf16; return CALL; }                             \
+  } while (0)
 
 struct JointBufs {
   float* x; void* xt; float* tmp; void* qkv; void* ctx; void* hbuf; float* mask_add; float* vtmp;
@@ -991,8 +1017,8 @@ static int run_inner(msq_model* m, const int64_t* ids, const int64_t* tt, const 
     MSQ_TRY(layernorm<T>(jb.tmp, Mv, H, m->visn_ln.g, m->visn_ln.b, 1e-12f, jb.x, (T*)jb.xt, Lv, Lj, Lt, st));
   }
   bool fused = false;
-  if constexpr (sizeof(T) == 2) fused = use_tc(m) && gemm_ln_enabled() && gemm_ln_supported(H, H) && gemm_ln_supported(H, c.inter);
-  if constexpr (sizeof(T) == 2) {
+  if constexpr (same_type<T, bf16>::value) fused = use_tc(m) && gemm_ln_enabled() && gemm_ln_supported(H, H) && gemm_ln_supported(H, c.inter);
+  if constexpr (same_type<T, bf16>::value) {
     if (ln_fold_enabled(m) && m->folded && !fused && !m->bert.empty()) {
       // Deferred LayerNorm through the post-LN BERT stack: jb.x / jb.xt hold the RAW sums (dense(...) + residual), the
       // LayerNorm after each sub-layer lives in the consumers: folded into the next QKV / intermediate GEMM and applied
@@ -1178,9 +1204,15 @@ static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const i
     MSQ_TRY((run_inner<T>(m, ids + r0 * Lt, tt + r0 * Lt, mask + r0 * Lt, rc, Lt, mm ? img_index + r0 * 2 : nullptr, vb, jb, st)));
     // ---- pooling for this chunk
     MSQ_TRY((gather_rows<float, T>(jb.x, rc * Lt, H, Lt, Lj, 0, (T*)hb.topt, st)));
+    if constexpr (is_split<T>::value) {   // tanh(sentence_tran(.)) stays fp32 (hb.ttb holds 4 bytes per element)
+      MSQ_TRY((run_gemm<T, float>(m, (const T*)hb.topt, H, m->sent_tran, nullptr, 0, (float*)hb.ttb, H, rc * Lt, ACT_TANH, st)));
+      MSQ_TRY(token_pool<float>((const float*)hb.ttb, jb.x, rc, Lt, Lj, H, m->w2, m->b2, sep + r0 * 2, m->w_rel, m->b_rel,
+                                hb.mix + r0 * 2 * H, hb.rel6 + r0 * 6, st));
+    } else {
     MSQ_TRY((run_gemm<T, T>(m, (const T*)hb.topt, H, m->sent_tran, nullptr, 0, (T*)hb.ttb, H, rc * Lt, ACT_TANH, st)));
     MSQ_TRY(token_pool<T>((const T*)hb.ttb, jb.x, rc, Lt, Lj, H, m->w2, m->b2, sep + r0 * 2, m->w_rel, m->b_rel, hb.mix + r0 * 2 * H,
                           hb.rel6 + r0 * 6, st));
+    }
     const int64_t cell0 = b0 * N * N;
     MSQ_TRY(edge_pool(hb.mix + r0 * 2 * H, jb.x, hb.rel6 + r0 * 6, bc, N, Lj, H, m->w_in2, hb.sents + b0 * N * H,
                       hb.r0 + cell0 * m->Kp, m->Kp, out && out->cls_mat ? out->cls_mat + cell0 * H : nullptr,
@@ -1240,7 +1272,7 @@ extern "C" int msq_vit_forward(msq_model* m, const float* images_dev, int64_t n_
     if (c.rn_width) return rn_finish<float>(vb.xv, R * Lv, Lv, c.rn_embed, nullptr, out_dev, st);  // cat([x, x]) (model.py:106)
     return layernorm<float>(vb.xv, R * Lv, c.vit_width, m->ln_post.g, m->ln_post.b, 1e-5f, out_dev, nullptr, 0, 0, 0, st);
   };
-  return c.precise ? go(float()) : go(bf16());
+  return c.precise == 1 ? go(float()) : (c.precise == 2 ? go(bf16s()) : go(bf16()));
 }
 
 extern "C" int msq_inner_forward(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev, int64_t R,
@@ -1272,7 +1304,7 @@ extern "C" int msq_inner_forward(msq_model* m, const int64_t* ids_dev, const int
     }
     return MSQ_OK;
   };
-  return c.precise ? go(float()) : go(bf16());
+  return c.precise == 1 ? go(float()) : (c.precise == 2 ? go(bf16s()) : go(bf16()));
 }
 
 extern "C" int msq_encode(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev,
@@ -1280,9 +1312,7 @@ extern "C" int msq_encode(msq_model* m, const int64_t* ids_dev, const int64_t* t
                           const int32_t* img_index_dev, const msq_encode_out* out, void* stream) {
   MSQ_REQUIRE(m && out, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (m->cfg.precise)
-    return run_path<float>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, out, 0, nullptr, st);
-  return run_path<bf16>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, out, 0, nullptr, st);
+  MSQ_DISPATCH_T(m, run_path<T>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, out, 0, nullptr, st));
 }
 
 extern "C" int msq_order_manuals_dev(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev,
@@ -1290,9 +1320,7 @@ extern "C" int msq_order_manuals_dev(msq_model* m, const int64_t* ids_dev, const
                                      int64_t n_img, const int32_t* img_index_dev, int32_t beam, int32_t* perm_dev, void* stream) {
   MSQ_REQUIRE(m && perm_dev, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (m->cfg.precise)
-    return run_path<float>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, nullptr, beam, perm_dev, st);
-  return run_path<bf16>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, nullptr, beam, perm_dev, st);
+  MSQ_DISPATCH_T(m, run_path<T>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, nullptr, beam, perm_dev, st));
 }
 
 // BertForOrdering._forward loss VALUE (modeling_bert.py:943-1174, default objectives), forward only
@@ -1302,11 +1330,8 @@ extern "C" int msq_training_loss(msq_model* m, const int64_t* ids_dev, const int
                                  float lam, int32_t* perm_scratch_dev, float* loss_dev, void* stream) {
   MSQ_REQUIRE(m && ground_truth_dev && pairwise_labels_dev && perm_scratch_dev && loss_dev, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (m->cfg.precise)
-    return run_path<float>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, nullptr, 1,
-                           perm_scratch_dev, st, ground_truth_dev, pairwise_labels_dev, lam, loss_dev);
-  return run_path<bf16>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, nullptr, 1, perm_scratch_dev,
-                        st, ground_truth_dev, pairwise_labels_dev, lam, loss_dev);
+  MSQ_DISPATCH_T(m, run_path<T>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, nullptr, 1,
+                                perm_scratch_dev, st, ground_truth_dev, pairwise_labels_dev, lam, loss_dev));
 }
 
 extern "C" int msq_beam_search(msq_model* m, const float* sents_dev, const float* key_dev, const float* h0_dev,
@@ -1443,12 +1468,11 @@ extern "C" int msq_order_manuals_host(msq_model* m, const int64_t* ids_host, con
       MSQ_CUDA(cudaMemcpyAsync(img, images_host, img_elems * 4, cudaMemcpyHostToDevice, st));
     }
   }
-  if (m->cfg.precise)
-    MSQ_TRY(run_path<float>(m, ids, tt, mask, sep, B, N, Lt, images_host ? img : nullptr, n_img, images_host ? idx : nullptr, nullptr, beam,
-                            perm, st, nullptr, nullptr, 0.f, nullptr, ready));
-  else
-    MSQ_TRY(run_path<bf16>(m, ids, tt, mask, sep, B, N, Lt, images_host ? img : nullptr, n_img, images_host ? idx : nullptr, nullptr, beam,
-                           perm, st, nullptr, nullptr, 0.f, nullptr, ready));
+  auto go = [&]() -> int {
+    MSQ_DISPATCH_T(m, run_path<T>(m, ids, tt, mask, sep, B, N, Lt, images_host ? img : nullptr, n_img, images_host ? idx : nullptr, nullptr,
+                                  beam, perm, st, nullptr, nullptr, 0.f, nullptr, ready));
+  };
+  MSQ_TRY(go());
   MSQ_CUDA(cudaMemcpyAsync(perm_host, perm, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
   MSQ_CUDA(cudaStreamSynchronize(st));
   return MSQ_OK;
@@ -1473,6 +1497,8 @@ extern "C" int msq_gemm(int32_t dtype, const void* A_dev, const void* W_dev, con
     case 5:   // TN operands (weight-gradient shape): A [K, M], W [K, N] bf16 row-major -> C [M, N] fp32 = A^T W (+ resid)
       g.tn = 1; g.lda = (int)M; g.ldw = N;
       return gemm_tc<float>(g, st);
+    case 6: g.split = 1; return gemm_tc<float>(g, st);   // bf16x3: split-bf16 A [M, hi(K)|lo(K)] and W, fp32 out
+    case 7: g.split = 1; return gemm_tc<bf16s>(g, st);   // bf16x3: split-bf16 out [M, hi(N)|lo(N)]
   }
   set_error("msq_gemm: unknown dtype %d", dtype);
   return MSQ_ERR_ARG;
@@ -1502,6 +1528,7 @@ extern "C" int msq_layernorm(int32_t dtype, const float* x_dev, int64_t rows, in
                              const float* beta_dev, float eps, void* out_dev, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == 0) return layernorm<float>(x_dev, rows, H, gamma_dev, beta_dev, eps, (float*)out_dev, nullptr, 0, 0, 0, st);
+  if (dtype == 2) return layernorm<bf16s>(x_dev, rows, H, gamma_dev, beta_dev, eps, nullptr, (bf16s*)out_dev, 0, 0, 0, st);
   return layernorm<bf16>(x_dev, rows, H, gamma_dev, beta_dev, eps, nullptr, (bf16*)out_dev, 0, 0, 0, st);
 }
 
@@ -1510,6 +1537,8 @@ extern "C" int msq_attention(int32_t dtype, const void* qkv_dev, int64_t R, int3
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == 0)
     return attention<float>((const float*)qkv_dev, R, L, heads, 64, scale, mask_add_dev, mask_len, mask_len, (float*)ctx_dev, st);
+  if (dtype == 2)
+    return attention<bf16s>((const bf16s*)qkv_dev, R, L, heads, 64, scale, mask_add_dev, mask_len, mask_len, (bf16s*)ctx_dev, st);
   return attention<bf16>((const bf16*)qkv_dev, R, L, heads, 64, scale, mask_add_dev, mask_len, mask_len, (bf16*)ctx_dev, st);
 }
 
@@ -1518,4 +1547,10 @@ extern "C" int msq_f32_to_bf16(const float* src_dev, void* dst_dev, int64_t n, v
   MSQ_CUDA(launch_k(f32_to_bf16_kernel, dim3((int)min((int64_t)148 * 8, (n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, src_dev, (bf16*)dst_dev, n));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
+}
+
+// fp32 [rows, K] -> split bf16 rows [hi(K) | lo(K)] (the operand layout of the bf16x3 mode; msq_gemm dtype 6 / 7)
+extern "C" int msq_f32_to_bf16_split(const float* src_dev, void* dst_dev, int64_t rows, int32_t K, void* stream) {
+  MSQ_REQUIRE(K % 4 == 0, "msq_f32_to_bf16_split: K=%d", K);
+  return gather_rows<float, bf16s>(src_dev, rows, K, 0, 0, 0, (bf16s*)dst_dev, (cudaStream_t)stream);
 }

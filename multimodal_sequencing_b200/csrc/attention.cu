@@ -121,21 +121,36 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
       : "memory");
 }
 
-template <int KP>
+// SPL (bf16x3 mode): q, k, v and the probabilities are carried as hi + lo bf16 pairs.  qkv rows are
+// [hi(3*heads*64) | lo(3*heads*64)], ctx rows [hi(heads*64) | lo(heads*64)]; every contraction is three MMA chains
+// (hi*lo, lo*hi, hi*hi) into the same fp32 accumulator; P_lo lives in its own TMEM columns [KP, KP + KP/2).
+template <int KP, bool SPL> struct AttnCfg {
+  static constexpr int Q_BYTES = 128 * 64 * 2, KV_BYTES = KP * 64 * 2;
+  static constexpr int QT = (SPL && KP == 128) ? 1 : 2;           // query tiles resident (L <= 128 needs one)
+  static constexpr int PLANES = SPL ? 2 : 1;
+  static constexpr int OPER_BYTES = PLANES * (QT * Q_BYTES + 2 * KV_BYTES);
+  static constexpr int SMEM = OPER_BYTES + KP * 4 + 2048 + 64 + 1024;
+  static constexpr int TMEM_COLS = SPL ? 2 * KP : KP;
+};
+
+template <int KP, bool SPL>
 __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant__ CUtensorMap map_q,
                                                            const __grid_constant__ CUtensorMap map_kv, int L, int heads,
                                                            float scale_l2e, const float* __restrict__ mask_add, int mask_ld,
                                                            int mask_len, bf16* __restrict__ ctx, int n_items) {
-  constexpr int Q_BYTES = 128 * 64 * 2, KV_BYTES = KP * 64 * 2;
+  using Cfg = AttnCfg<KP, SPL>;
+  constexpr int Q_BYTES = Cfg::Q_BYTES, KV_BYTES = Cfg::KV_BYTES, QT = Cfg::QT, OPER = Cfg::OPER_BYTES;
   constexpr int CH = KP / 64;  // 32-column chunks per thread: two threads share a query row, half the keys each
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sQ = base, sK = base + 2 * Q_BYTES, sV = sK + KV_BYTES;
-  float* maskf = reinterpret_cast<float*>(gen + 2 * Q_BYTES + 2 * KV_BYTES);  // [KP] additive mask * log2(e), -inf beyond L
+  const uint32_t sQ = base, sK = base + QT * Q_BYTES, sV = sK + KV_BYTES;
+  // lo planes (SPL): same order behind the hi planes
+  const uint32_t sQl = sV + KV_BYTES, sKl = sQl + QT * Q_BYTES, sVl = sKl + KV_BYTES;
+  float* maskf = reinterpret_cast<float*>(gen + OPER);                         // [KP] additive mask * log2(e), -inf beyond L
   float* red = maskf + KP;                                                     // [2 (max|sum)][2 halves][128 rows]
-  const uint32_t bars = base + 2 * Q_BYTES + 2 * KV_BYTES + KP * 4 + 2048;     // bar_qk | bar_s | bar_o | bar_v | tmem slot
-  volatile uint32_t* tslot_gen = reinterpret_cast<volatile uint32_t*>(gen + 2 * Q_BYTES + 2 * KV_BYTES + KP * 4 + 2048 + 32);
+  const uint32_t bars = base + OPER + KP * 4 + 2048;                           // bar_qk | bar_s | bar_o | bar_v | tmem slot
+  volatile uint32_t* tslot_gen = reinterpret_cast<volatile uint32_t*>(gen + OPER + KP * 4 + 2048 + 32);
   const uint32_t bar_qk = bars, bar_s = bars + 8, bar_o = bars + 16, bar_v = bars + 24, tslot = bars + 32;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -153,7 +168,7 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(KP) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(Cfg::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   pdl_sync();  // barrier init / TMEM allocation above overlap the previous kernel's tail
@@ -167,14 +182,20 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
   // per CTA, not once per item.
   auto load_qk = [&](int item) {   // tid 0
     const int row0 = (item / heads) * L, hh = item % heads;
-    mbar_expect_tx(bar_qk, (uint32_t)(nqt * Q_BYTES + KV_BYTES));
+    mbar_expect_tx(bar_qk, (uint32_t)(Cfg::PLANES * (nqt * Q_BYTES + KV_BYTES)));
     tma_load_2d(sK, &map_kv, heads * AT_D + hh * AT_D, row0, bar_qk);
     for (int qt = 0; qt < nqt; ++qt) tma_load_2d(sQ + qt * Q_BYTES, &map_q, hh * AT_D, row0 + qt * 128, bar_qk);
+    if (SPL) {
+      const int lo = 3 * heads * AT_D;   // the lo plane of a qkv row starts here
+      tma_load_2d(sKl, &map_kv, lo + heads * AT_D + hh * AT_D, row0, bar_qk);
+      for (int qt = 0; qt < nqt; ++qt) tma_load_2d(sQl + qt * Q_BYTES, &map_q, lo + hh * AT_D, row0 + qt * 128, bar_qk);
+    }
   };
   auto load_v = [&](int item) {    // tid 0
     const int row0 = (item / heads) * L, hh = item % heads;
-    mbar_expect_tx(bar_v, (uint32_t)KV_BYTES);
+    mbar_expect_tx(bar_v, (uint32_t)(Cfg::PLANES * KV_BYTES));
     tma_load_2d(sV, &map_kv, 2 * heads * AT_D + hh * AT_D, row0, bar_v);
+    if (SPL) tma_load_2d(sVl, &map_kv, 5 * heads * AT_D + hh * AT_D, row0, bar_v);
   };
   if (tid == 0 && (int)blockIdx.x < n_items) { load_qk(blockIdx.x); load_v(blockIdx.x); }
 
@@ -203,9 +224,17 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
   for (int qt = 0; qt < nqt; ++qt, mma_phase ^= 1) {
     if (tid == 0) {
       tc_fence_after();
+      if (SPL) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem, umma_desc_sw128(sQ + qt * Q_BYTES + k * 32), umma_desc_sw128(sKl + k * 32), idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem, umma_desc_sw128(sQl + qt * Q_BYTES + k * 32), umma_desc_sw128(sK + k * 32), idesc_s, 1);
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        umma_bf16(tmem, umma_desc_sw128(sQ + qt * Q_BYTES + k * 32), umma_desc_sw128(sK + k * 32), idesc_s, k != 0);
+        umma_bf16(tmem, umma_desc_sw128(sQ + qt * Q_BYTES + k * 32), umma_desc_sw128(sK + k * 32), idesc_s, SPL || k != 0);
       umma_commit(bar_s);
     }
     mbar_wait(bar_s, mma_phase);
@@ -240,6 +269,7 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       uint32_t raw[32];
+      uint32_t pl[16];
       tmem_ld32(lane_addr + col0 + j * 32, raw);
       const int k0 = col0 + j * 32;
       if (masked || k0 + 32 > L) {
@@ -250,6 +280,10 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
           sum += p0 + p1;
           __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);  // .x (low half) = even key
           pk[j][i] = *reinterpret_cast<uint32_t*>(&b);
+          if (SPL) {
+            __nv_bfloat162 c = __floats2bfloat162_rn(p0 - __low2float(b), p1 - __high2float(b));
+            pl[i] = *reinterpret_cast<uint32_t*>(&c);
+          }
         }
       } else {
 #pragma unroll
@@ -259,8 +293,14 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
           sum += p0 + p1;
           __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
           pk[j][i] = *reinterpret_cast<uint32_t*>(&b);
+          if (SPL) {
+            __nv_bfloat162 c = __floats2bfloat162_rn(p0 - __low2float(b), p1 - __high2float(b));
+            pl[i] = *reinterpret_cast<uint32_t*>(&c);
+          }
         }
       }
+      // P_lo has TMEM columns of its own (free since the previous tile's P V completed): written chunk by chunk
+      if (SPL) tmem_st16(lane_addr + KP + half * (KP / 4) + j * 16, pl);
     }
     red[256 + half * 128 + trow] = sum;
     tc_fence_before();
@@ -276,9 +316,17 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
     if (tid == 0) {
       if (qt == 0) mbar_wait(bar_v, n_done & 1);
       tc_fence_after();
+      if (SPL) {
+#pragma unroll
+        for (int kk = 0; kk < KP / 16; ++kk)
+          umma_bf16_ts(tmem + KP / 2, tmem + kk * 8, umma_desc_sw128(sVl + kk * 2048), idesc_o, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < KP / 16; ++kk)
+          umma_bf16_ts(tmem + KP / 2, tmem + KP + kk * 8, umma_desc_sw128(sV + kk * 2048), idesc_o, 1);
+      }
 #pragma unroll
       for (int kk = 0; kk < KP / 16; ++kk)
-        umma_bf16_ts(tmem + KP / 2, tmem + kk * 8, umma_desc_sw128(sV + kk * 2048), idesc_o, kk != 0);
+        umma_bf16_ts(tmem + KP / 2, tmem + kk * 8, umma_desc_sw128(sV + kk * 2048), idesc_o, SPL || kk != 0);
       umma_commit(bar_o);
     }
     mbar_wait(bar_o, mma_phase);
@@ -292,7 +340,19 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
     {
       uint32_t raw[32];
       tmem_ld32(lane_addr + KP / 2 + half * 32, raw);
-      if (q < L) {
+      if (SPL) {
+        if (q < L) {   // ctx row = [hi(heads*64) | lo(heads*64)]
+          bf16* op = ctx + ((int64_t)r * L + q) * (2 * heads * AT_D) + h * AT_D + half * 32;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint2 hi, lo;
+            split4(make_float4(__uint_as_float(raw[4 * i]) * inv, __uint_as_float(raw[4 * i + 1]) * inv,
+                               __uint_as_float(raw[4 * i + 2]) * inv, __uint_as_float(raw[4 * i + 3]) * inv), hi, lo);
+            *reinterpret_cast<uint2*>(op + 4 * i) = hi;
+            *reinterpret_cast<uint2*>(op + heads * AT_D + 4 * i) = lo;
+          }
+        }
+      } else if (q < L) {
         bf16* op = ctx + ((int64_t)r * L + q) * (heads * AT_D) + h * AT_D + half * 32;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -313,21 +373,21 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
   }
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(KP) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(Cfg::TMEM_COLS) : "memory");
   }
 }
 
-template <int KP>
+template <int KP, bool SPL>
 static int launch_attention_tc(const bf16* qkv, int64_t R, int L, int heads, float scale, const float* mask_add, int mask_ld,
                                int mask_len, bf16* ctx, cudaStream_t st) {
   CUtensorMap mq, mkv;
-  const int ld = 3 * heads * AT_D;
+  const int ld = (SPL ? 2 : 1) * 3 * heads * AT_D;   // bf16 elements per qkv row
   MSQ_TRY(make_map_bf16(&mq, qkv, R * L, ld, ld, AT_D, 128));
   MSQ_TRY(make_map_bf16(&mkv, qkv, R * L, ld, ld, AT_D, KP));
-  constexpr int SMEM = 2 * 128 * 64 * 2 + 2 * KP * 64 * 2 + KP * 4 + 2048 + 64 + 1024;
+  constexpr int SMEM = AttnCfg<KP, SPL>::SMEM;
   static bool configured = false;
   if (!configured) {
-    MSQ_CUDA(cudaFuncSetAttribute(attention_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    MSQ_CUDA(cudaFuncSetAttribute(attention_tc_kernel<KP, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
   // Persistent grid = the CTAs that are resident at once: 2 per SM at KP = 256 (256 TMEM columns and 100 KB of shared
@@ -338,12 +398,12 @@ static int launch_attention_tc(const bf16* qkv, int64_t R, int L, int heads, flo
     int dev = 0, sms = 0;
     MSQ_CUDA(cudaGetDevice(&dev));
     MSQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    resident = (KP == 256 ? 2 : 3) * sms;
+    resident = (SPL ? (KP == 256 ? 1 : 2) : (KP == 256 ? 2 : 3)) * sms;   // SPL: 197 KB / 100 KB of shared memory, 512 / 256 TMEM columns
   }
   const int64_t n_items = R * heads;
   MSQ_REQUIRE(n_items < ((int64_t)1 << 31), "attention: too many (row, head) items");
 
-  MSQ_CUDA(launch_k(attention_tc_kernel<KP>, dim3((unsigned)min((int64_t)resident, n_items)), dim3(256), SMEM, st, mq, mkv, L, heads, scale * 1.4426950408889634f, mask_add, mask_ld, mask_len, ctx, (int)n_items));
+  MSQ_CUDA(launch_k(attention_tc_kernel<KP, SPL>, dim3((unsigned)min((int64_t)resident, n_items)), dim3(256), SMEM, st, mq, mkv, L, heads, scale * 1.4426950408889634f, mask_add, mask_ld, mask_len, ctx, (int)n_items));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -360,11 +420,17 @@ int attention(const T* qkv, int64_t R, int L, int heads, int dhead, float scale,
   MSQ_REQUIRE(dhead == AT_D, "attention: head dim %d != 64", dhead);
   MSQ_REQUIRE(L >= 1 && L <= 320, "attention: sequence length %d out of range", L);
   if (R == 0) return MSQ_OK;
+  if constexpr (is_split<T>::value) {
+    MSQ_REQUIRE(tc_supported_impl() && L <= 256 && (((uintptr_t)qkv) & 15) == 0, "attention: the bf16x3 mode needs the tcgen05 path (sm_100, L <= 256)");
+    if (L <= 128)
+      return launch_attention_tc<128, true>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
+    return launch_attention_tc<256, true>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
+  } else {
   if constexpr (sizeof(T) == 2) {
     if (attention_use_tc() && L <= 256 && (((uintptr_t)qkv) & 15) == 0) {
       if (L <= 128)
-        return launch_attention_tc<128>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
-      return launch_attention_tc<256>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
+        return launch_attention_tc<128, false>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
+      return launch_attention_tc<256, false>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
     }
   }
   const int Lpad = (L + 31) & ~31;
@@ -378,7 +444,9 @@ int attention(const T* qkv, int64_t R, int L, int heads, int dhead, float scale,
   MSQ_CUDA(launch_k(attention_simt_kernel<T>, dim3((unsigned)(R * heads)), dim3(AT_WARPS * 32), smem, st, qkv, L, heads, scale, key_mask_add, mask_ld, mask_len, ctx));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
+  }
 }
+template int attention<bf16s>(const bf16s*, int64_t, int, int, int, float, const float*, int, int, bf16s*, cudaStream_t);
 template int attention<float>(const float*, int64_t, int, int, int, float, const float*, int, int, float*, cudaStream_t);
 template int attention<bf16>(const bf16*, int64_t, int, int, int, float, const float*, int, int, bf16*, cudaStream_t);
 

@@ -15,6 +15,17 @@ namespace msq {
 
 typedef __nv_bfloat16 bf16;
 
+// "Split bf16" operand type of the bf16x3 precision mode (msq_config.precise == 2): a value x is carried as
+// hi = bf16(x) and lo = bf16(x - hi), i.e. 16 significand bits, and a product a*w is formed on the tensor cores as
+// a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with fp32 accumulation (the dropped lo*lo term is 2^-18 relative).
+// Storage: a row of K logical elements is [hi(K) | lo(K)] bf16 = K * 4 bytes, so sizeof(bf16s) == 4 keeps all row
+// arithmetic (r * K, buffer sizes) in units of T; only kernels look inside a row.
+struct bf16s { bf16 hi, lo; };
+template <typename T> struct is_split { static constexpr bool value = false; };
+template <> struct is_split<bf16s> { static constexpr bool value = true; };
+template <typename A, typename B> struct same_type { static constexpr bool value = false; };
+template <typename A> struct same_type<A, A> { static constexpr bool value = true; };
+
 void set_error(const char* fmt, ...);
 
 #define MSQ_CUDA(...)                                                                              \
@@ -174,6 +185,36 @@ template <> struct Vec4<bf16> {
     *reinterpret_cast<uint2*>(p) = u;
   }
 };
+
+// hi / lo parts of four values, packed as bf16 pairs
+__device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - __low2float(h0), v.y - __high2float(h0));
+  const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - __low2float(h1), v.w - __high2float(h1));
+  hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+  lo.x = *reinterpret_cast<const uint32_t*>(&l0); lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+}
+// store / load four consecutive logical elements at column `col` of a row of K logical elements
+template <typename T> __device__ __forceinline__ void store_row4(T* row, int col, int K, const float4& v) {
+  (void)K;
+  Vec4<T>::store(row + col, v);
+}
+template <> __device__ __forceinline__ void store_row4<bf16s>(bf16s* row, int col, int K, const float4& v) {
+  bf16* p = reinterpret_cast<bf16*>(row);
+  uint2 hi, lo;
+  split4(v, hi, lo);
+  *reinterpret_cast<uint2*>(p + col) = hi;
+  *reinterpret_cast<uint2*>(p + K + col) = lo;
+}
+template <typename T> __device__ __forceinline__ float4 load_row4(const T* row, int col, int K) {
+  (void)K;
+  return Vec4<T>::load(row + col);
+}
+template <> __device__ __forceinline__ float4 load_row4<bf16s>(const bf16s* row, int col, int K) {
+  const bf16* p = reinterpret_cast<const bf16*>(row);
+  const float4 a = Vec4<bf16>::load(p + col), b = Vec4<bf16>::load(p + K + col);
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -39,7 +39,7 @@ __device__ __forceinline__ void ln_finish(float4* v, int nv, int H, int lane, co
       float4 o = make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
                              (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
       if (out_f) Vec4<float>::store(out_f + col, o);
-      if (out_t) Vec4<T>::store(out_t + col, o);
+      if (out_t) store_row4<T>(out_t, col, H, o);
     }
 }
 
@@ -80,6 +80,8 @@ template int layernorm<float>(const float*, int64_t, int, const float*, const fl
                               cudaStream_t);
 template int layernorm<bf16>(const float*, int64_t, int, const float*, const float*, float, float*, bf16*, int, int, int,
                              cudaStream_t);
+template int layernorm<bf16s>(const float*, int64_t, int, const float*, const float*, float, float*, bf16s*, int, int, int,
+                              cudaStream_t);
 
 // word[ids] + pos[t] + type[tt] -> LN -> joint rows r*Lj + t
 template <typename T>
@@ -123,6 +125,8 @@ template int embed_ln<float>(const int64_t*, const int64_t*, int64_t, int, int, 
                              const float*, const float*, const float*, float, float*, float*, cudaStream_t);
 template int embed_ln<bf16>(const int64_t*, const int64_t*, int64_t, int, int, int, const float*, const float*,
                             const float*, const float*, const float*, float, float*, bf16*, cudaStream_t);
+template int embed_ln<bf16s>(const int64_t*, const int64_t*, int64_t, int, int, int, const float*, const float*,
+                             const float*, const float*, const float*, float, float*, bf16s*, cudaStream_t);
 
 // ViT pair token sequence: row (r, t), t in [0, 1 + il*g2): t==0 class token, else patch (t-1)%g2 of
 // image slot (t-1)/g2; positional row = t (t <= g2) else (t-1-g2) % g2 [clip/model.py:271-275]; ln_pre.
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ i
     const int64_t im = row / (g * g);
     const int py = (int)(row % (g * g)) / g, px = (int)(row % (g * g)) % g;
     const float4 v = *reinterpret_cast<const float4*>(img + ((im * 3 + c) * S + (py * P + ky)) * (int64_t)S + px * P + kx);
-    Vec4<T>::store(out + row * K + col, v);
+    store_row4<T>(out + row * K, col, K, v);
   }
 }
 
@@ -201,6 +205,7 @@ int im2col(const float* img, int64_t n, int S, int P, T* out, cudaStream_t st) {
 }
 template int im2col<float>(const float*, int64_t, int, int, float*, cudaStream_t);
 template int im2col<bf16>(const float*, int64_t, int, int, bf16*, cudaStream_t);
+template int im2col<bf16s>(const float*, int64_t, int, int, bf16s*, cudaStream_t);
 
 // dst[r, c] = src[(r / group) * src_group + off + r % group, c]  (row gather with dtype conversion)
 template <typename TI, typename TO>
@@ -212,7 +217,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const TI* __restrict__
     const int64_t r = i / (H / 4);
     const int c = (int)(i % (H / 4)) * 4;
     const int64_t sr = group ? (r / group) * (int64_t)src_group + off + r % group : r;
-    Vec4<TO>::store(dst + r * H + c, Vec4<TI>::load(src + sr * H + c));
+    store_row4<TO>(dst + r * H, c, H, Vec4<TI>::load(src + sr * H + c));
   }
 }
 
@@ -227,6 +232,7 @@ int gather_rows(const TI* src, int64_t rows, int H, int group, int src_group, in
 }
 template int gather_rows<float, float>(const float*, int64_t, int, int, int, int, float*, cudaStream_t);
 template int gather_rows<float, bf16>(const float*, int64_t, int, int, int, int, bf16*, cudaStream_t);
+template int gather_rows<float, bf16s>(const float*, int64_t, int, int, int, int, bf16s*, cudaStream_t);
 template int gather_rows<bf16, bf16>(const bf16*, int64_t, int, int, int, int, bf16*, cudaStream_t);
 
 // weight packing: dst[r, 0..Kp) = src[r, 0..K) zero padded, with dtype conversion (row-major [rows, K])
@@ -237,7 +243,15 @@ __global__ void pack_pad_kernel(const float* __restrict__ src, int64_t rows, int
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / Kp;
     const int c = (int)(i % Kp);
-    dst[i] = from_f<TO>(c < K ? src[r * K + c] : 0.f);
+    const float v = c < K ? src[r * K + c] : 0.f;
+    if constexpr (is_split<TO>::value) {   // row = [hi(Kp) | lo(Kp)]
+      bf16* d = reinterpret_cast<bf16*>(dst) + r * 2 * Kp;
+      const bf16 h = __float2bfloat16_rn(v);
+      d[c] = h;
+      d[Kp + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+    } else {
+      dst[i] = from_f<TO>(v);
+    }
   }
 }
 template <typename TO>
@@ -249,5 +263,6 @@ int pack_pad(const float* src, int64_t rows, int K, int Kp, TO* dst, cudaStream_
 }
 template int pack_pad<float>(const float*, int64_t, int, int, float*, cudaStream_t);
 template int pack_pad<bf16>(const float*, int64_t, int, int, bf16*, cudaStream_t);
+template int pack_pad<bf16s>(const float*, int64_t, int, int, bf16s*, cudaStream_t);
 
 }  // namespace msq

@@ -61,12 +61,14 @@ struct TcEpi {
   int sp_in;
   float inv_dim, eps;
   int tn;   // GemmArgs::tn: MN-major operands (single-CTA path)
+  int split_k;  // GemmArgs::split: logical K (A and W rows are [hi(K) | lo(K)]); 0 = plain bf16 operands
 };
 
 // 8 consecutive output columns of one row: accumulator -> value to store (see GemmArgs for the modes)
 template <int ACT, int MODE>
 __device__ __forceinline__ void epi_compute8(float* v, const uint32_t* raw, const float* bias8, const float* s8, const float* beta8,
-                                             float ra, float rc, bool has_ln, bool use_res, const float4& r0, const float4& r1) {
+                                             float ra, float rc, bool has_ln, bool use_res, const float4& r0, const float4& r1,
+                                             bool exact_act = false) {
   const float4 b0 = *reinterpret_cast<const float4*>(bias8), b1 = *reinterpret_cast<const float4*>(bias8 + 4);
   const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   if (MODE == 1) {
@@ -79,8 +81,13 @@ __device__ __forceinline__ void epi_compute8(float* v, const uint32_t* raw, cons
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[i]) + b[i];
   }
   if (ACT != ACT_NONE) {
+    if (exact_act) {   // bf16x3 mode: erff / tanhf / expf as in the fp32 parity mode
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = apply_act_fast(v[i], ACT);
+      for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], ACT);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = apply_act_fast(v[i], ACT);
+    }
   }
   if (use_res) {
     float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
@@ -141,6 +148,14 @@ template <> __device__ __forceinline__ void epi_store8<float>(float* p, const fl
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
+// split output: hi at p, lo at p + plane
+__device__ __forceinline__ void epi_pack8_split(const float* v, uint4& hi, uint4& lo) {
+  uint2 h0, l0, h1, l1;
+  split4(make_float4(v[0], v[1], v[2], v[3]), h0, l0);
+  split4(make_float4(v[4], v[5], v[6], v[7]), h1, l1);
+  hi = make_uint4(h0.x, h0.y, h1.x, h1.y);
+  lo = make_uint4(l0.x, l0.y, l1.x, l1.y);
+}
 template <> __device__ __forceinline__ void epi_store8<bf16>(bf16* p, const float* v) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
   __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
@@ -156,7 +171,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_c2,
                const __grid_constant__ CUtensorMap tma_r, TcEpi ep, int num_m, int num_n, int num_k) {
   using Cfg = TcCfg<PAIR, MODE>;
-  static_assert(MODE != 2 || sizeof(TO) == 4, "EPI_RESLN writes the fp32 stream (+ its bf16 copy)");
+  constexpr bool F32 = same_type<TO, float>::value, SPL = is_split<TO>::value;
+  static_assert(MODE != 2 || F32, "EPI_RESLN writes the fp32 stream (+ its bf16 copy)");
+  static_assert(!SPL || MODE == 0, "split-bf16 output: plain epilogue only");
   constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -208,14 +225,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       for (int tile = unit; tile < num_tiles; tile += num_units) {
         const int n_blk = tile % num_n, m_blk = tile / num_n;
         const int a_row = m_blk * Cfg::TILE_M + (int)rank * TC_BM, b_row = n_blk * TC_BN + (int)rank * Cfg::B_ROWS;
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kq = 0; kq < num_k; ++kq) {
+          // bf16x3: the K loop runs three times over every 64-column slab: a_hi*w_lo, a_lo*w_hi, a_hi*w_hi (the hi and
+          // lo planes of a row are K columns apart); the MMA warp just sees a contraction of length 3K
+          int kb = kq, ka = 0, kw = 0;
+          if (ep.split_k) { kb = kq / 3; const int t = kq - 3 * kb; ka = t == 1 ? ep.split_k : 0; kw = t == 0 ? ep.split_k : 0; }
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + TC_A_BYTES;
           if (PAIR) {
             const uint32_t lead_full = mapa_rank(full0 + 8 * stage, 0);
             if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * STAGE_BYTES);
-            tma_load_2d_pair(sa, &tma_a, kb * TC_BK, a_row, lead_full);
-            tma_load_2d_pair(sb, &tma_b, kb * TC_BK, b_row, lead_full);
+            tma_load_2d_pair(sa, &tma_a, ka + kb * TC_BK, a_row, lead_full);
+            tma_load_2d_pair(sb, &tma_b, kw + kb * TC_BK, b_row, lead_full);
           } else if (ep.tn) {
             // MN-major operands: boxes of 64 contraction rows x 64 columns, one per 64-wide slice of the tile
             mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
@@ -225,8 +246,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             for (int i = 0; i < Cfg::B_ROWS / 64; ++i) tma_load_2d(sb + i * 8192, &tma_b, b_row + i * 64, kb * TC_BK, full0 + 8 * stage);
           } else {
             mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
-            tma_load_2d(sa, &tma_a, kb * TC_BK, a_row, full0 + 8 * stage);
-            tma_load_2d(sb, &tma_b, kb * TC_BK, b_row, full0 + 8 * stage);
+            tma_load_2d(sa, &tma_a, ka + kb * TC_BK, a_row, full0 + 8 * stage);
+            tma_load_2d(sb, &tma_b, kw + kb * TC_BK, b_row, full0 + 8 * stage);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -304,6 +325,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint32_t acc_phase = 0;
     TO* C = reinterpret_cast<TO*>(ep.C);
     const bool use_res = ep.resid != nullptr;
+    const bool exact_act = SPL || ep.split_k != 0;
     // residual rows are pulled into L2 one tile ahead (no registers held): the epilogue of a K=768 residual GEMM is
     // HBM-latency bound otherwise, with only one 32-column chunk of loads in flight per thread
     auto prefetch_res = [&](int t) {
@@ -381,7 +403,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (Cfg::TMA_STORE) {
           // ---- registers -> swizzled staging box -> TMA store.  A box is 32 rows x 128 B: 32 fp32 columns
           // (one chunk) or 64 bf16 columns (two chunks).  16-byte piece c of row r sits at r*128 + ((c ^ (r&7))<<4).
-          constexpr bool F32 = sizeof(TO) == 4;
           const bool new_box = F32 || (ch & 1) == 0;
           if (RES_TMA) {
             if (lane == 0) {
@@ -394,11 +415,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             __syncwarp();
             mbar_wait(rbar + 8 * (rk & 1), (rk >> 1) & 1);   // residual chunk rk has landed in box rk&1
           } else if (new_box) {
-            // the fp32 box used two chunks ago has been read out
-            if (lane == 0) tma_store_wait_read<1>();
+            // the fp32 box used two chunks ago has been read out (split output: box 0 = hi, box 1 = lo, both reused)
+            if (lane == 0) { if (SPL) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
             __syncwarp();
           }
-          const uint32_t box = stg + ((RES_TMA ? rk : (uint32_t)stg_use) & 1) * 4096;
+          const uint32_t box = SPL ? stg : stg + ((RES_TMA ? rk : (uint32_t)stg_use) & 1) * 4096;
           const uint32_t rowp = box + lane * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -406,10 +427,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (RES_TMA) {
               const float4 r0 = ld_shared_f4(rowp + (((2 * j) ^ (lane & 7)) << 4)), r1 = ld_shared_f4(rowp + (((2 * j + 1) ^ (lane & 7)) << 4));
               epi_compute8<ACT, MODE>(v, raw + j * 8, bias_s + ch * 32 + j * 8, svec_s + ch * 32 + j * 8, beta_s + ch * 32 + j * 8, ra, rc,
-                                      has_ln, true, r0, r1);
+                                      has_ln, true, r0, r1, exact_act);
             } else {
               epi_compute8<ACT, MODE>(v, raw + j * 8, bias_s + ch * 32 + j * 8, svec_s + ch * 32 + j * 8, beta_s + ch * 32 + j * 8, ra, rc,
-                                      has_ln, use_res, res[2 * j], res[2 * j + 1]);
+                                      has_ln, use_res, res[2 * j], res[2 * j + 1], exact_act);
             }
             if (MODE == 2) {
 #pragma unroll
@@ -423,6 +444,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (F32) {
               st_shared_v4(rowp + (((2 * j) ^ (lane & 7)) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
               st_shared_v4(rowp + (((2 * j + 1) ^ (lane & 7)) << 4), __float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+            } else if (SPL) {
+              uint4 hi, lo;
+              epi_pack8_split(v, hi, lo);
+              const uint32_t o = rowp + ((((ch & 1) * 4 + j) ^ (lane & 7)) << 4);
+              st_shared_v4(o, hi.x, hi.y, hi.z, hi.w);
+              st_shared_v4(o + 4096, lo.x, lo.y, lo.z, lo.w);
             } else {
               __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
               __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
@@ -439,7 +466,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 if (col0 < ep.N) tma_store_2d(&tma_c2, stg2, col0, (int)(row - lane));
                 tma_store_commit();
               }
-              if (box_col < ep.N) tma_store_2d(&tma_c, box, box_col, (int)(row - lane));
+              if (box_col < ep.N) {
+                tma_store_2d(&tma_c, box, box_col, (int)(row - lane));
+                if (SPL) tma_store_2d(&tma_c, box + 4096, ep.ldc + box_col, (int)(row - lane));   // lo plane (N % 64 == 0)
+              }
               tma_store_commit();
             }
             ++stg_use;
@@ -452,13 +482,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (col < ep.N) {  // N % 8 == 0
               float v[8];
               epi_compute8<ACT, MODE>(v, raw + j * 8, bias_s + ch * 32 + j * 8, svec_s + ch * 32 + j * 8, beta_s + ch * 32 + j * 8, ra, rc,
-                                      has_ln, use_res, res[2 * j], res[2 * j + 1]);
+                                      has_ln, use_res, res[2 * j], res[2 * j + 1], exact_act);
               if (MODE == 2) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { st_sum += v[i]; st_sq = fmaf(v[i], v[i], st_sq); }
                 epi_store8<bf16>(ep.C2 + row * ep.ldc + col, v);
               }
-              epi_store8<TO>(C + row * ep.ldc + col, v);
+              if constexpr (SPL) {   // row of C = [hi(ldc) | lo(ldc)]
+                bf16* cb = reinterpret_cast<bf16*>(ep.C) + row * (2 * (int64_t)ep.ldc) + col;
+                uint4 hi, lo;
+                epi_pack8_split(v, hi, lo);
+                *reinterpret_cast<uint4*>(cb) = hi;
+                *reinterpret_cast<uint4*>(cb + ep.ldc) = lo;
+              } else {
+                epi_store8<TO>(C + row * ep.ldc + col, v);
+              }
             }
           }
         }
@@ -497,13 +535,18 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
   if (g.tn) {   // [K rows, M or N columns], boxes of 64 x 64
     MSQ_TRY(make_map_bf16(&ma, g.A, g.K, (int)g.M, g.lda, 64, 64));
     MSQ_TRY(make_map_bf16(&mb, g.W, g.K, g.N, g.ldw, 64, 64));
+  } else if (g.split) {   // rows are [hi(K) | lo(K)]; lda / ldw count logical elements
+    MSQ_TRY(make_map_bf16(&ma, g.A, g.M, 2 * g.K, 2 * g.lda, TC_BK, TC_BM));
+    MSQ_TRY(make_map_bf16(&mb, g.W, g.N, 2 * g.K, 2 * g.ldw, TC_BK, Cfg::B_ROWS));
   } else {
     MSQ_TRY(make_map_bf16(&ma, g.A, g.M, g.K, g.lda, TC_BK, TC_BM));
     MSQ_TRY(make_map_bf16(&mb, g.W, g.N, g.K, g.ldw, TC_BK, Cfg::B_ROWS));
   }
   CUtensorMap mc = ma;
   CUtensorMap mc2 = ma;
-  if (Cfg::TMA_STORE) MSQ_TRY(make_map_2d(&mc, g.C, g.M, g.N, g.ldc, 128 / (int)sizeof(TO), 32, sizeof(TO) == 4));
+  constexpr bool F32 = same_type<TO, float>::value, SPL = is_split<TO>::value;
+  if (Cfg::TMA_STORE && SPL) MSQ_TRY(make_map_2d(&mc, g.C, g.M, g.ldc + g.N, 2 * g.ldc, 64, 32, false));   // lo plane at column ldc
+  else if (Cfg::TMA_STORE) MSQ_TRY(make_map_2d(&mc, g.C, g.M, g.N, g.ldc, F32 ? 32 : 64, 32, F32));
   if (Cfg::TMA_STORE && MODE == 2) MSQ_TRY(make_map_2d(&mc2, g.C2bf, g.M, g.N, g.ldc, 32, 32, false, true));
   CUtensorMap mr = ma;
   if (Cfg::TMA_STORE && MODE == 2) MSQ_TRY(make_map_2d(&mr, g.resid, g.M, g.N, g.ldr, 32, 32, true));
@@ -515,8 +558,8 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
   TcEpi ep;
   ep.bias = g.bias; ep.resid = g.resid; ep.C = g.C; ep.M = g.M; ep.N = g.N; ep.ldc = g.ldc; ep.ldr = g.ldr; ep.act = g.act;
   ep.svec = g.svec; ep.beta = g.beta; ep.stats_in = g.stats_in; ep.stats_out = g.stats_out; ep.C2 = (bf16*)g.C2bf; ep.sp_in = g.sp_in;
-  ep.inv_dim = g.ln_inv_dim; ep.eps = g.ln_eps; ep.tn = g.tn;
-  const int num_m = ceil_div(g.M, Cfg::TILE_M), num_n = ceil_div(g.N, TC_BN), num_k = ceil_div(g.K, TC_BK);
+  ep.inv_dim = g.ln_inv_dim; ep.eps = g.ln_eps; ep.tn = g.tn; ep.split_k = g.split ? g.K : 0;
+  const int num_m = ceil_div(g.M, Cfg::TILE_M), num_n = ceil_div(g.N, TC_BN), num_k = ceil_div(g.K, TC_BK) * (g.split ? 3 : 1);
   const int64_t tiles = (int64_t)num_m * num_n;
   profile_mark(st, false, 0.0);
   if (PAIR) {
@@ -546,7 +589,7 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
 template <typename TO, bool PAIR>
 static int launch_gemm_tc(const GemmArgs& g, int sms, cudaStream_t st) {
   if (g.mode == EPI_RESLN) {
-    if constexpr (sizeof(TO) == 4) {
+    if constexpr (same_type<TO, float>::value) {
       MSQ_REQUIRE(g.act == ACT_NONE && g.C2bf && g.stats_out && g.resid, "gemm_tc: EPI_RESLN needs resid, C2bf, stats_out and no activation");
       return launch_gemm_tc_act<TO, PAIR, ACT_NONE, 2>(g, sms, st);
     } else {
@@ -554,6 +597,17 @@ static int launch_gemm_tc(const GemmArgs& g, int sms, cudaStream_t st) {
       return MSQ_ERR_ARG;
     }
   }
+  if constexpr (is_split<TO>::value) {
+    MSQ_REQUIRE(g.mode == EPI_PLAIN, "gemm_tc: split-bf16 output supports the plain epilogue only");
+    switch (g.act) {
+      case ACT_NONE: return launch_gemm_tc_act<TO, PAIR, ACT_NONE, 0>(g, sms, st);
+      case ACT_GELU_ERF: return launch_gemm_tc_act<TO, PAIR, ACT_GELU_ERF, 0>(g, sms, st);
+      case ACT_QUICK_GELU: return launch_gemm_tc_act<TO, PAIR, ACT_QUICK_GELU, 0>(g, sms, st);
+      case ACT_RELU: return launch_gemm_tc_act<TO, PAIR, ACT_RELU, 0>(g, sms, st);
+    }
+    set_error("gemm_tc: activation %d not instantiated for split-bf16 output", g.act);
+    return MSQ_ERR_ARG;
+  } else {
   if (g.mode == EPI_LNFOLD) {
     MSQ_REQUIRE(g.svec && g.stats_in && g.sp_in > 0, "gemm_tc: EPI_LNFOLD needs svec and stats_in");
     switch (g.act) {
@@ -573,6 +627,7 @@ static int launch_gemm_tc(const GemmArgs& g, int sms, cudaStream_t st) {
   }
   set_error("gemm_tc: activation %d not supported on the tensor-core path", g.act);
   return MSQ_ERR_ARG;
+  }
 }
 
 template <typename TO>
@@ -583,6 +638,8 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   MSQ_REQUIRE(!g.tn || (g.mode == EPI_PLAIN && g.M % 8 == 0 && g.K >= 1), "gemm_tc: TN operands need the plain epilogue and M %% 8 == 0");
   MSQ_REQUIRE(((uintptr_t)g.A & 15) == 0 && ((uintptr_t)g.W & 15) == 0 && ((uintptr_t)g.C & 15) == 0, "gemm_tc: unaligned pointer");
   MSQ_REQUIRE(g.C2 == nullptr, "gemm_tc: second output unsupported");
+  MSQ_REQUIRE(!g.split || (!g.tn && g.mode == EPI_PLAIN && g.K % TC_BK == 0), "gemm_tc: split-bf16 operands need K-major layout, the plain epilogue and K %% 64 == 0");
+  MSQ_REQUIRE(!is_split<TO>::value || (g.split && g.N % 64 == 0), "gemm_tc: split-bf16 output needs split operands and N %% 64 == 0");
   if (g.M == 0) return MSQ_OK;
   static int sms = 0, force_single = -1;
   if (!sms) {
@@ -598,5 +655,6 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
 }
 template int gemm_tc<float>(const GemmArgs&, cudaStream_t);
 template int gemm_tc<bf16>(const GemmArgs&, cudaStream_t);
+template int gemm_tc<bf16s>(const GemmArgs&, cudaStream_t);
 
 }  // namespace msq

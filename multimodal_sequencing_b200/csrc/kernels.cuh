@@ -61,6 +61,10 @@ struct GemmArgs {
   // MN-major UMMA descriptors -- no transposed copy of the activations / gradients is ever made.  K need not be a
   // multiple of 64 (out-of-range rows are zero-filled by the TMA unit).
   int tn = 0;
+  // gemm_tc only: bf16x3 precision mode.  A and W rows are [hi(K) | lo(K)] bf16 (type bf16s; lda / ldw / ldc count logical
+  // elements); C = A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T with fp32 accumulation, exact activations in the epilogue.
+  // Output type float or bf16s (a split row [hi(ldc) | lo(ldc)]).  Plain epilogue only.
+  int split = 0;
   int mode = EPI_PLAIN;
   const float* svec = nullptr;
   const float* beta = nullptr;

@@ -61,7 +61,7 @@ class VisualTransformer(nn.Module):
                     vision_width=self.width, vision_patch_size=self.patch_size)
 
     def _engine(self):
-        sig = tuple(p._version for p in self.parameters()) + (bool(getattr(self, "precise", False)),)
+        sig = tuple(p._version for p in self.parameters()) + (getattr(self, "precise", False),)
         if self.__dict__.get("_eng") is None or self.__dict__.get("_eng_sig") != sig:
             dev = self.conv1.weight.device
             if dev.type != "cuda":
@@ -69,7 +69,7 @@ class VisualTransformer(nn.Module):
             cfg = dict(hidden_size=self.width, num_hidden_layers=0, num_attention_heads=self.width // 64,
                        intermediate_size=4 * self.width, vocab_size=1, max_position_embeddings=1, vit=self.vit_config())
             sd = {"bert.encoder.visual_model.visual." + k: v for k, v in self.state_dict().items()}
-            self.__dict__["_eng"] = OrderingEngine(sd, cfg, device=dev, precise=bool(getattr(self, "precise", False)))
+            self.__dict__["_eng"] = OrderingEngine(sd, cfg, device=dev, precise=getattr(self, "precise", False))
             self.__dict__["_eng_sig"] = sig
         return self.__dict__["_eng"]
 
@@ -150,7 +150,7 @@ class ModifiedResNet(nn.Module):
 
     def _engine(self):
         tensors = list(self.parameters()) + list(self.buffers())
-        sig = tuple(t._version for t in tensors) + (bool(getattr(self, "precise", False)),)
+        sig = tuple(t._version for t in tensors) + (getattr(self, "precise", False),)
         if self.__dict__.get("_eng") is None or self.__dict__.get("_eng_sig") != sig:
             dev = self.conv1.weight.device
             if dev.type != "cuda":
@@ -158,7 +158,7 @@ class ModifiedResNet(nn.Module):
             cfg = dict(hidden_size=128, num_hidden_layers=0, num_attention_heads=2, intermediate_size=512, vocab_size=1,
                        max_position_embeddings=1, rn=self.rn_config())
             sd = {"bert.encoder.visual_model.visual." + k: v for k, v in self.state_dict().items()}
-            self.__dict__["_eng"] = OrderingEngine(sd, cfg, device=dev, precise=bool(getattr(self, "precise", False)))
+            self.__dict__["_eng"] = OrderingEngine(sd, cfg, device=dev, precise=getattr(self, "precise", False))
             self.__dict__["_eng_sig"] = sig
         return self.__dict__["_eng"]
 

@@ -127,7 +127,7 @@ class LXRTModel(nn.Module):
         torch.save(model_to_save.state_dict(), os.path.join(save_directory, "pytorch_model.bin"))
 
     def _engine(self):
-        sig = tuple(t._version for t in list(self.parameters()) + list(self.buffers())) + (bool(getattr(self, "precise", False)),)
+        sig = tuple(t._version for t in list(self.parameters()) + list(self.buffers())) + (getattr(self, "precise", False),)
         if self.__dict__.get("_eng") is None or self.__dict__.get("_eng_sig") != sig:
             dev = self.pooler.dense.weight.device
             if dev.type != "cuda":
@@ -138,7 +138,7 @@ class LXRTModel(nn.Module):
                        max_position_embeddings=c.max_position_embeddings, type_vocab_size=c.type_vocab_size)
             cfg["rn" if self.is_resnet else "vit"] = self.vit_config
             sd = {"bert." + k: v for k, v in self.state_dict().items()}
-            self.__dict__["_eng"] = OrderingEngine(sd, cfg, device=dev, precise=bool(getattr(self, "precise", False)))
+            self.__dict__["_eng"] = OrderingEngine(sd, cfg, device=dev, precise=getattr(self, "precise", False))
             self.__dict__["_eng_sig"] = sig
         return self.__dict__["_eng"]
 

@@ -87,14 +87,14 @@ class _EngineOwner:
 
     def engine(self):
         tensors = list(self.parameters()) + list(self.buffers())   # buffers: BatchNorm statistics of the ResNet tower
-        sig = tuple(t._version for t in tensors) + (tuple(id(t) for t in tensors), bool(getattr(self, "precise", False)))
+        sig = tuple(t._version for t in tensors) + (tuple(id(t) for t in tensors), getattr(self, "precise", False))
         eng = self.__dict__.get("_eng")
         if eng is None or self.__dict__.get("_eng_sig") != sig:
             dev = next(self.parameters()).device
             if dev.type != "cuda":
                 raise RuntimeError("the B200 path has no CPU fallback: move the model to a CUDA device first")
             eng = OrderingEngine(self._engine_state(), self._engine_config(), device=dev,
-                                 precise=bool(getattr(self, "precise", False)))
+                                 precise=getattr(self, "precise", False))
             self.__dict__["_eng"], self.__dict__["_eng_sig"] = eng, sig
         return eng
 
@@ -389,7 +389,7 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
         # the copies bumped the version counters: keep the packed model (it already holds these values)
         tensors = list(self.parameters()) + list(self.buffers())
         self.__dict__["_eng_sig"] = tuple(t._version for t in tensors) + (tuple(id(t) for t in tensors),
-                                                                          bool(getattr(self, "precise", False)))
+                                                                          getattr(self, "precise", False))
 
     def _forward(self, input_ids, attention_mask=None, token_type_ids=None, pairs_list=None, passage_length=None,
                  pairs_num=None, sep_positions=None, ground_truth=None, mask_cls=None, pairwise_labels=None, cuda=None,

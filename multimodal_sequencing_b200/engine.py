@@ -115,8 +115,23 @@ def prepare_pairs(input_ids, labels, n_steps, images=None, cls_id=101, sep_id=10
                      pi[None].expand(B, P, 2).contiguous(), plab, labels.clone(), N, img, idx)
 
 
+# msq_config.precise: 0 = bf16 operands (fastest), 1 = fp32 FFMA (CUDA cores), 2 = bf16x3 (hi + lo bf16 operands,
+# three tcgen05 MMAs per product: fp32-grade results at tensor-core speed)
+PRECISION = {False: 0, True: 1, 2: 2, "bf16": 0, "fp32": 1, "bf16x3": 2}
+
+
+def precision_code(precise):
+    try:
+        return PRECISION[precise]
+    except (KeyError, TypeError):
+        raise ValueError("precise=%r: expected False/'bf16', True/'fp32' or 2/'bf16x3'" % (precise,))
+
+
 class OrderingEngine:
-    """Owns one packed device model (msq_model) and runs the path through the C ABI."""
+    """Owns one packed device model (msq_model) and runs the path through the C ABI.
+
+    precise: False / "bf16" (bf16 tensor-core operands), True / "fp32" (CUDA-core fp32 parity mode) or
+    2 / "bf16x3" (split-bf16 operands on the tensor cores; evaluation only, ViT or text-only models)."""
 
     def __init__(self, state_dict, config, precise=False, device="cuda:0", inner_prefix="bert."):
         if not torch.cuda.is_available():
@@ -134,7 +149,7 @@ class OrderingEngine:
             type_vocab=config.get("type_vocab_size", 2), vit_width=vit["vision_width"] if vit else 0,
             vit_layers=vit["vision_layers"] if vit else 0, vit_patch=vit["vision_patch_size"] if vit else 0,
             vit_res=vit["image_resolution"] if vit else 0, para_heads=config.get("para_heads", 8),
-            para_ff=config.get("para_ff", 3072), para_layers=config.get("para_layers", 2), precise=int(bool(precise)),
+            para_ff=config.get("para_ff", 3072), para_layers=config.get("para_layers", 2), precise=precision_code(precise),
             reserved=0)
         if rn:
             # CLIP ModifiedResNet (clip/model.py:128-187): the tower hands 2*embed_dim features per token to visn_fc
@@ -147,7 +162,8 @@ class OrderingEngine:
         # visual tokens per pair row and their feature width as the tower returns them
         self._grid = (vit["image_resolution"] // vit["vision_patch_size"]) if vit else (rn["image_resolution"] // 32 if rn else 0)
         self._vis_width = vit["vision_width"] if vit else (2 * rn["embed_dim"] if rn else 0)
-        self.precise = bool(precise)
+        self.precise = precision_code(precise) == 1
+        self.precision = ("bf16", "fp32", "bf16x3")[precision_code(precise)]
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.msq_model_create(C.byref(c), C.byref(self._h)))
