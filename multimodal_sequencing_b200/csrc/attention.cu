@@ -240,7 +240,6 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
     mbar_wait(bar_s, mma_phase);
     __syncwarp();
     tc_fence_after();
-    if (tid == 0 && qt == nqt - 1 && next < n_items) load_qk(next);   // Q / K tiles are free: every S of this item is done
 
     // ---- pass 1: row maximum (in the log2 domain) over this thread's half of the keys
     float mx = -INFINITY;
@@ -261,6 +260,10 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
     }
     red[half * 128 + trow] = mx;
     __syncthreads();
+    // Q / K tiles are free (every S of this item is done) AND every thread has passed this item's bar_qk wait (the barrier
+    // above): re-arming bar_qk earlier lets it complete a second phase before a late waker has observed the first, and a
+    // parity wait that misses a phase never returns (seen as a hang when the loads, not the math, bound an item).
+    if (tid == 0 && qt == nqt - 1 && next < n_items) load_qk(next);
     mx = fmaxf(red[trow], red[128 + trow]);
 
     // ---- pass 2: p = 2^(s*c + mask - max); packed bf16 P kept in registers until every S read is done
@@ -399,6 +402,7 @@ static int launch_attention_tc(const bf16* qkv, int64_t R, int L, int heads, flo
     MSQ_CUDA(cudaGetDevice(&dev));
     MSQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     resident = (SPL ? (KP == 256 ? 1 : 2) : (KP == 256 ? 2 : 3)) * sms;   // SPL: 197 KB / 100 KB of shared memory, 512 / 256 TMEM columns
+    if (const char* e = getenv("MSQ_ATTN_CTAS_PER_SM")) resident = max(1, atoi(e)) * sms;
   }
   const int64_t n_items = R * heads;
   MSQ_REQUIRE(n_items < ((int64_t)1 << 31), "attention: too many (row, head) items");

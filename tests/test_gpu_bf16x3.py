@@ -159,24 +159,56 @@ def _assert_enc(enc, ref, what):
     return worst
 
 
+def _fixture_margin(steps, N):
+    """Smallest decision gap of the REFERENCE's own beam search (fixture trace): last kept vs best dropped candidate at every
+    step, best vs second-best hypothesis at the last one, and the gaps between neighbouring kept candidates (their order
+    decides ties further down).  candidate = parent score + log-prob."""
+    margin = float("inf")
+    parent = torch.zeros(1)
+    for t, s in enumerate(steps):
+        cand = (parent[:, None] + s["logp"][:parent.numel()]).reshape(-1)
+        cand = cand[cand > -1e8].sort(descending=True).values
+        k = s["beam_ix"].numel()
+        upto = min(k + 1, cand.numel())
+        if upto > 1:
+            margin = min(margin, float((cand[:upto - 1] - cand[1:upto]).min()))
+        parent = s["score"]
+    return margin
+
+
 @pytest.mark.parametrize("name", ["text_tiny.pt", "mm_tiny.pt"])
 def test_tiny_goldens_bf16x3(golden_dir, name):
-    """fixtures the REAL reference produced: encode tensors within the bf16 gate, permutations and beam traces bit-exact."""
+    """fixtures the REAL reference produced: encode tensors within the bf16 gate; permutations and beam indices bit-exact
+    wherever the reference's own decision gaps exceed GAP_EPS (the N=10 / W=16 fixtures hold exact ties)."""
     g = torch.load(os.path.join(golden_dir, name), weights_only=False)
     eng = _engine(g["sd"], _cfg_from_golden(g), "bf16x3")
+    n_exact = 0
     for c in g["cases"]:
         if name.startswith("mm"):
             ids, labels, images = O.synthetic_manuals(1, c["N"], c["L"], vocab=1000, image_px=224, seed=c["seed"])
         else:
             ids, labels, images = c["ids"], c["labels"], None
         enc = eng.encode(eng.prepare(ids, labels, c["N"], images))
-        worst = _assert_enc(enc, c["enc"], name)
-        perm, tr = eng.beam_search(enc, c["N"], c["W"], trace=True)
-        assert perm[0].tolist() == c["perm"], (perm[0].tolist(), c["perm"], worst)
+        _assert_enc(enc, c["enc"], name)
+        # the decode kernel itself: the reference's encoder outputs in -> the reference's indices out, bit-exact
+        perm, tr = eng.beam_search(c["enc"], c["N"], c["W"], trace=True)
+        assert perm[0].tolist() == c["perm"]
         for t, s in enumerate(c["steps"]):
             k = s["beam_ix"].numel()
             assert torch.equal(tr["ix"][0, t, :k].cpu(), (s["beam_ix"] * c["N"] + s["tok_ix"]).int()), "step %d beam indices" % t
-        assert eng.order(ids, labels, c["N"], c["W"], images) == [c["perm"]]
+        # end to end through the bf16x3 encoder
+        margin = _fixture_margin(c["steps"], c["N"])
+        perm, tr = eng.beam_search(enc, c["N"], c["W"], trace=True)
+        same = perm[0].tolist() == c["perm"] and all(
+            torch.equal(tr["ix"][0, t, :s["beam_ix"].numel()].cpu(), (s["beam_ix"] * c["N"] + s["tok_ix"]).int())
+            for t, s in enumerate(c["steps"]))
+        n_exact += same
+        assert same or margin < GAP_EPS, "N=%d W=%d: trace differs although the reference's smallest gap is %.3e" % (c["N"], c["W"], margin)
+        assert sorted(perm[0].tolist()) == list(range(c["N"]))
+        if margin >= GAP_EPS:
+            assert eng.order(ids, labels, c["N"], c["W"], images) == [c["perm"]]
+    print("%s: %d / %d cases bit-exact end to end (the others have a reference decision gap < %.0e)" % (name, n_exact, len(g["cases"]), GAP_EPS))
+    assert n_exact >= len(g["cases"]) // 2
 
 
 def _full_cfg(mm):
