@@ -152,7 +152,7 @@ static int concat3(msq_model* m, const float* a, const float* b, const float* c,
 // LSTM / pw_k repacks
 __global__ void pack_lstm_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b_ih,
                                  const float* __restrict__ b_hh, int H, float* __restrict__ wih_perm,
-                                 float* __restrict__ bias_perm, float* __restrict__ whh_t) {
+                                 float* __restrict__ bias_perm, float* __restrict__ whh_t, float* __restrict__ whh_perm) {
   pdl_sync();
   const int64_t total = (int64_t)4 * H * H;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -160,6 +160,7 @@ __global__ void pack_lstm_kernel(const float* __restrict__ w_ih, const float* __
     const int g = row / H, u = row % H, col = 4 * u + g;
     wih_perm[(int64_t)col * H + k] = w_ih[i];
     whh_t[(int64_t)k * 4 * H + col] = w_hh[i];
+    whh_perm[(int64_t)col * H + k] = w_hh[i];
     if (k == 0) bias_perm[col] = b_ih[row] + b_hh[row];
   }
 }
@@ -677,14 +678,15 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
   MSQ_TRY(make_lin(m, W("key_linear.weight", (int64_t)2 * H * H), W("key_linear.bias", H), H, 2 * H, 2 * H, false, &m->key_lin, st));
   // decoder repacks
   {
-    float *wih_perm, *bias_perm, *whh_t, *wq_t, *wpw4;
-    m->Kp = ((H + 2) + 15) / 16 * 16;
+    float *wih_perm, *bias_perm, *whh_t, *wq_t, *wpw4, *whh_perm;
+    m->Kp = ((H + 2) + 63) / 64 * 64;   // padded H+2: a multiple of 64 so that the T4 projection can run on the tcgen05 kernel
+    MSQ_TRY(dev_alloc(m, (size_t)4 * H * H, &whh_perm));
     MSQ_TRY(dev_alloc(m, (size_t)4 * H * H, &wih_perm));
     MSQ_TRY(dev_alloc(m, (size_t)4 * H, &bias_perm));
     MSQ_TRY(dev_alloc(m, (size_t)4 * H * H, &whh_t));
     MSQ_TRY(dev_alloc(m, (size_t)H * H, &wq_t));
     MSQ_TRY(dev_alloc(m, (size_t)4 * H * m->Kp, &wpw4));
-    MSQ_CUDA(launch_k(pack_lstm_kernel, dim3(512), dim3(256), 0, st, W("decoder.weight_ih_l0", (int64_t)4 * H * H), W("decoder.weight_hh_l0", (int64_t)4 * H * H), W("decoder.bias_ih_l0", 4 * H), W("decoder.bias_hh_l0", 4 * H), H, wih_perm, bias_perm, whh_t));
+    MSQ_CUDA(launch_k(pack_lstm_kernel, dim3(512), dim3(256), 0, st, W("decoder.weight_ih_l0", (int64_t)4 * H * H), W("decoder.weight_hh_l0", (int64_t)4 * H * H), W("decoder.bias_ih_l0", 4 * H), W("decoder.bias_hh_l0", 4 * H), H, wih_perm, bias_perm, whh_t, whh_perm));
     MSQ_LAUNCH_CHECK();
     MSQ_CUDA(launch_k(transpose_kernel, dim3(256), dim3(256), 0, st, W("query_linear.weight", (int64_t)H * H), H, H, wq_t));
     MSQ_LAUNCH_CHECK();
@@ -698,6 +700,23 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
     MSQ_CUDA(cudaMemcpyAsync(&bt, W("tanh_linear.bias", 1), sizeof(float), cudaMemcpyDeviceToHost, st));
     MSQ_CUDA(cudaStreamSynchronize(st));
     m->dec.bt = bt;
+    if (c.precise != 1) {
+      // tensor-core decode (bf16x6): three-plane bf16 copies of the decoder's weights; products are formed from all plane
+      // pairs (i, j) with i + j <= 2, i.e. to ~2^-24 relative -- fp32-grade results at tcgen05 speed
+      bf16 *wih3, *wpw3, *wcat3;
+      float* bcat;
+      MSQ_TRY(dev_alloc(m, (size_t)4 * H * 3 * H, &wih3));
+      MSQ_TRY(dev_alloc(m, (size_t)4 * H * 3 * m->Kp, &wpw3));
+      MSQ_TRY(dev_alloc(m, (size_t)5 * H * 3 * H, &wcat3));
+      MSQ_TRY(dev_alloc(m, (size_t)5 * H, &bcat));
+      MSQ_TRY(pack_split3(wih_perm, 4 * H, H, H, H, wih3, st));
+      MSQ_TRY(pack_split3(wpw4, 4 * H, m->Kp, m->Kp, m->Kp, wpw3, st));
+      MSQ_TRY(pack_split3(W("query_linear.weight", (int64_t)H * H), H, H, H, H, wcat3, st));
+      MSQ_TRY(pack_split3(whh_perm, 4 * H, H, H, H, wcat3 + (size_t)H * 3 * H, st));
+      MSQ_CUDA(cudaMemsetAsync(bcat, 0, (size_t)5 * H * sizeof(float), st));
+      MSQ_CUDA(cudaMemcpyAsync(bcat, W("query_linear.bias", H), (size_t)H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      m->wih3 = wih3; m->wpw3 = wpw3; m->dec.wcat3 = wcat3; m->dec.bcat = bcat;
+    }
     // raw-layout copies for the step-by-step API (msq_decode_step): pw_k padded to a multiple of 16 columns
     m->Kp4 = (4 * (H + 2) + 15) / 16 * 16;
     MSQ_TRY(make_lin(m, W("pw_k.weight", (int64_t)H * 4 * (H + 2)), nullptr, H, 4 * (H + 2), m->Kp4, false, &m->pwk_raw, st));
@@ -1075,11 +1094,11 @@ static int run_inner(msq_model* m, const int64_t* ids, const int64_t* tt, const 
 
 struct HeadBufs {   // whole batch, fp32
   float *mix, *rel6, *sents, *r0, *para, *pa, *pb, *pn, *pqkv, *pctx, *pff, *h0, *keyin, *key, *sents_ext, *xg, *t4;
-  void *topt, *ttb;
+  void *topt, *ttb, *dec;
 };
 
 template <typename T>
-static void plan_heads(const msq_config& c, Planner& p, int64_t B, int N, int64_t Rc, int Lt, int Kp, HeadBufs* h) {
+static void plan_heads(const msq_config& c, Planner& p, int64_t B, int N, int64_t Rc, int Lt, int Kp, HeadBufs* h, int beam = 16) {
   const int H = c.hidden;
   const int64_t R = B * N * (N - 1);
   h->topt = p.take<T>((size_t)Rc * Lt * H);
@@ -1101,6 +1120,7 @@ static void plan_heads(const msq_config& c, Planner& p, int64_t B, int N, int64_
   h->sents_ext = p.take<float>((size_t)B * (N + 1) * H);
   h->xg = p.take<float>((size_t)B * (N + 1) * 4 * H);
   h->t4 = p.take<float>((size_t)B * N * N * 4 * H);
+  h->dec = p.take<char>(beam_search_scratch_bytes(B, N, beam, H));
 }
 
 static int run_gemm32(const float* A, int lda, const Lin& w, const float* resid, int ldr, float* C, int ldc, int64_t M, int act,
@@ -1142,17 +1162,35 @@ static int run_paragraph(msq_model* m, HeadBufs& h, int64_t B, int N, cudaStream
 // decode pre-projections + beam search from (sents, key, h0, r0)
 static int run_decode(msq_model* m, const float* sents, const float* key, const float* h0, const float* r0, float* sents_ext,
                       float* xg, float* t4, int64_t B, int N, int beam, int32_t* perm, int32_t* tr_ix, float* tr_cost,
-                      float* tr_logp, cudaStream_t st, const int32_t* forced = nullptr, float* final_cost = nullptr) {
+                      float* tr_logp, cudaStream_t st, const int32_t* forced = nullptr, float* final_cost = nullptr,
+                      void* scratch = nullptr) {
   const int H = m->cfg.hidden;
   MSQ_CUDA(launch_k(sents_ext_kernel, dim3(ceil_div(B * (N + 1) * (int64_t)H, 256)), dim3(256), 0, st, sents, B, N, H, sents_ext));
   MSQ_LAUNCH_CHECK();
-  MSQ_TRY(run_gemm32(sents_ext, H, m->xg_lin, nullptr, 0, xg, 4 * H, B * (N + 1), ACT_NONE, st));
-  MSQ_TRY(run_gemm32(r0, m->Kp, m->t4_lin, nullptr, 0, t4, 4 * H, B * N * N, ACT_NONE, st));
+  const bool tc = use_tc(m) && m->dec.wcat3 != nullptr && scratch != nullptr && H % 64 == 0 && decode_tc_enabled();
+  if (tc) {
+    // pre-projections on the tensor cores: three-plane operands (bf16x6).  The plane copies of sents_ext / r0 live in the
+    // tail of the decode scratch buffer (beam_search_scratch_bytes reserves them).
+    char* tail = reinterpret_cast<char*>(scratch) + beam_search_state_bytes(B, beam, H);
+    bf16* s3 = reinterpret_cast<bf16*>(tail);
+    bf16* r3 = s3 + (((size_t)B * (N + 1) * 3 * H + 127) & ~size_t(127));
+    MSQ_TRY(pack_split3(sents_ext, B * (N + 1), H, H, H, s3, st));
+    MSQ_TRY(pack_split3(r0, B * N * N, m->Kp, m->Kp, m->Kp, r3, st));
+    GemmArgs g;
+    g.A = s3; g.W = m->wih3; g.bias = m->xg_lin.b; g.resid = nullptr; g.C = xg; g.C2 = nullptr;
+    g.M = B * (N + 1); g.N = 4 * H; g.K = H; g.lda = H; g.ldw = H; g.ldc = 4 * H; g.ldr = 0; g.act = ACT_NONE; g.split = 2;
+    MSQ_TRY(gemm_tc<float>(g, st));
+    g.A = r3; g.W = m->wpw3; g.bias = nullptr; g.C = t4; g.M = B * N * N; g.K = m->Kp; g.lda = m->Kp; g.ldw = m->Kp;
+    MSQ_TRY(gemm_tc<float>(g, st));
+  } else {
+    MSQ_TRY(run_gemm32(sents_ext, H, m->xg_lin, nullptr, 0, xg, 4 * H, B * (N + 1), ACT_NONE, st));
+    MSQ_TRY(run_gemm32(r0, m->Kp, m->t4_lin, nullptr, 0, t4, 4 * H, B * N * N, ACT_NONE, st));
+  }
   if (tr_ix) MSQ_CUDA(cudaMemsetAsync(tr_ix, 0xff, (size_t)B * (N - 1) * beam * sizeof(int32_t), st));
   DecodeIO io;
   io.xg = xg; io.t4 = t4; io.key0 = key; io.h0 = h0; io.B = B; io.N = N; io.W = beam; io.H = H;
   io.perm = perm; io.trace_ix = tr_ix; io.trace_cost = tr_cost; io.trace_logp = tr_logp;
-  io.forced = forced; io.final_cost = final_cost;
+  io.forced = forced; io.final_cost = final_cost; io.scratch = scratch; io.tc = tc ? 1 : 0;
   return beam_search(m->dec, io, st);
 }
 
@@ -1174,6 +1212,7 @@ static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const i
   MSQ_REQUIRE(c.vit_width == 0 || m->has_vit, "model lacks the visual tower weights");
   MSQ_REQUIRE(N >= 2 && N <= 16, "N=%d out of range [2,16]", N);
   MSQ_REQUIRE(!(c.vit_width != 0 && images == nullptr), "multimodal model needs images");
+  MSQ_REQUIRE(beam >= 0 && beam <= 16, "beam width %d out of range [1,16]", beam);
   const int H = c.hidden, P = N * (N - 1);
   const bool mm = c.vit_width != 0;
   const int g2 = mm ? (c.vit_res / c.vit_patch) * (c.vit_res / c.vit_patch) : 0;
@@ -1187,7 +1226,7 @@ static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const i
     if (pass == 1) m->ws.reset();
     if (mm) plan_visual<T>(c, p, n_img, Rc, &vb);
     plan_joint<T>(c, p, Rc, Lt, Lj, &jb);
-    plan_heads<T>(c, p, B, N, Rc, Lt, m->Kp, &hb);
+    plan_heads<T>(c, p, B, N, Rc, Lt, m->Kp, &hb, beam > 0 ? beam : 1);
     if (pass == 0) MSQ_TRY(m->ws.reserve(p.need + 4096, st));
   }
   // patch embedding once per UNIQUE image, not per pair slot.  When the caller streams the images in manual order
@@ -1234,12 +1273,13 @@ static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const i
                                                    (size_t)R, cudaMemcpyDeviceToDevice, st));
   }
   if (perm && !forced)
-    MSQ_TRY(run_decode(m, hb.sents, hb.key, hb.h0, hb.r0, hb.sents_ext, hb.xg, hb.t4, B, N, beam, perm, nullptr, nullptr, nullptr, st));
+    MSQ_TRY(run_decode(m, hb.sents, hb.key, hb.h0, hb.r0, hb.sents_ext, hb.xg, hb.t4, B, N, beam, perm, nullptr, nullptr, nullptr, st, nullptr,
+                       nullptr, hb.dec));
   if (forced) {
     // teacher-forced NLL of the ground-truth order + lam * pairwise NLL (modeling_bert.py:1098-1174), forward only
     float* nll = hb.pn;  // [B] scratch (paragraph buffers are free again)
     MSQ_TRY(run_decode(m, hb.sents, hb.key, hb.h0, hb.r0, hb.sents_ext, hb.xg, hb.t4, B, N, 1, perm, nullptr, nullptr, nullptr, st, forced,
-                       nll));
+                       nll, hb.dec));
     MSQ_CUDA(launch_k(training_loss_kernel, dim3(1), dim3(256), 0, st, nll, hb.rel6, pair_labels, B, N, lam, loss_out));
     MSQ_LAUNCH_CHECK();
   }
@@ -1342,6 +1382,8 @@ extern "C" int msq_beam_search(msq_model* m, const float* sents_dev, const float
   cudaStream_t st = (cudaStream_t)stream;
   const int H = m->cfg.hidden;
   float *r0 = nullptr, *sents_ext = nullptr, *xg = nullptr, *t4 = nullptr;
+  void* dscr = nullptr;
+  MSQ_REQUIRE(beam >= 1 && beam <= 16, "beam width %d out of range [1,16]", beam);
   for (int pass = 0; pass < 2; ++pass) {
     Planner p{&m->ws, pass == 0};
     if (pass == 1) m->ws.reset();
@@ -1349,13 +1391,14 @@ extern "C" int msq_beam_search(msq_model* m, const float* sents_dev, const float
     sents_ext = p.take<float>((size_t)B * (N + 1) * H);
     xg = p.take<float>((size_t)B * (N + 1) * 4 * H);
     t4 = p.take<float>((size_t)B * N * N * 4 * H);
+    dscr = p.take<char>(beam_search_scratch_bytes(B, N, beam, H));
     if (pass == 0) MSQ_TRY(m->ws.reserve(p.need + 4096, st));
   }
   if (B == 0) return MSQ_OK;
   MSQ_CUDA(launch_k(build_r0_kernel, dim3((unsigned)(B * N * N)), dim3(128), 0, st, cls_mat_dev, score_mat_dev, B * N * N, H, m->Kp, r0));
   MSQ_LAUNCH_CHECK();
   return run_decode(m, sents_dev, key_dev, h0_dev, r0, sents_ext, xg, t4, B, N, beam, perm_dev, trace_ix_dev, trace_cost_dev,
-                    trace_logp_dev, st);
+                    trace_logp_dev, st, nullptr, nullptr, dscr);
 }
 
 // BertForOrdering.step with the reference's materialised tensors (modeling_bert.py:1368-1402)

@@ -17,6 +17,8 @@
 // Per-beam state is just (picked sequence, h, c, cost).  Likewise W_ih x_t is a row gather of
 // XG = sents W_ih^T + b_ih + b_hh.  All arithmetic is fp32 with a fixed summation order.
 // Ties in the top-k are broken by the lowest flat index beam*N+step.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace msq {
@@ -281,13 +283,9 @@ static int launch_beam(const DecodeWeights& w, const DecodeIO& io, int G, cudaSt
   return MSQ_OK;
 }
 
-int beam_search(const DecodeWeights& w, const DecodeIO& io, cudaStream_t st) {
-  MSQ_REQUIRE(io.N >= 2 && io.N <= DC_MAXN, "beam_search: N=%d out of range [2,%d]", io.N, DC_MAXN);
-  MSQ_REQUIRE(io.W >= 1 && io.W <= 16, "beam_search: beam width %d out of range [1,16]", io.W);
-  MSQ_REQUIRE(io.H % 8 == 0 && io.H <= 1024, "beam_search: H=%d unsupported", io.H);
-  if (io.B == 0) return MSQ_OK;
-  // rows per CTA: enough manuals to reuse each weight row across ~16 beams, but never fewer CTAs than
-  // needed to give every SM work when B is large.
+// The single-kernel form above (round 1) keeps the whole search of a few manuals inside one CTA: every CTA streams the full
+// W_hh / W_q (11.8 MB) from L2 at every step for at most 16 rows.  It is kept for B*W <= 16 rows only when MSQ_DECODE_FUSED=1.
+static int beam_search_fused(const DecodeWeights& w, const DecodeIO& io, cudaStream_t st) {
   int G = 16 / io.W;
   if (G < 1) G = 1;
   while (G > 1 && ceil_div(io.B, G) < 148) G /= 2;
@@ -295,6 +293,524 @@ int beam_search(const DecodeWeights& w, const DecodeIO& io, cudaStream_t st) {
   if (rows <= 4) return launch_beam<4>(w, io, G, st);
   if (rows <= 8) return launch_beam<8>(w, io, G, st);
   return launch_beam<16>(w, io, G, st);
+}
+
+// ===================================================================================================
+// Tiled decode (round 2): the search is a sequence of three kernels per decode step over ALL B*live rows
+//   1. dec_gemm_kernel<.., 0>  gates = XG[prev] + h W_hh^T as a rows x 4H fp32 GEMM tiled over (rows, gate columns): a weight
+//                              tile is read once per 64/128 rows (not once per <= 16 rows), h rows are gathered through the
+//                              parent table (the beam re-gather costs nothing), the LSTM cell is the epilogue;
+//   2. dec_gemm_kernel<.., 1>  q = h' W_q^T + b_q, same kernel;
+//   3. dec_select_kernel       one CTA per manual: F / G rows of T4 staged in shared memory once per candidate step k and
+//                              shared by all beams, pointer scores, log-softmax, rank-counting top-k, new (sequence, cost,
+//                              parent) tables -- and the permutation after the last step.
+// Arithmetic is the fused kernel's, operation for operation: accumulators start from XG / b_q and add w*h in ascending k
+// with fmaf; F / G sums ascend in j; the score dot product is lane-strided with an xor-tree warp sum.  Results are therefore
+// bit-identical to the fused kernel (and to what the golden beam traces pin).
+// ===================================================================================================
+struct DecState {
+  float* h[2];        // [B*W, H] h' of the previous / current step
+  float* c[2];        // [B*W, H]
+  const float* q;     // query rows: row (b * q_rows + beam), leading dimension q_ld
+  int q_ld, q_rows;
+  uint8_t* seq[2];    // [B*W, 16] picked steps so far (ping-pong)
+  float* cost[2];     // [B*W]
+  int32_t* parent;    // [B*W] beam slot (of the previous step) a row descends from
+};
+
+// FFMA form: h[2], c[2], q (5 x rows*H fp32).  Tensor-core form: h' planes (rows * 3H bf16), c[2], [q | h W_hh^T][2]
+// (rows * 5H fp32 each), h0 planes.  One size covers both.
+size_t beam_search_state_bytes(int64_t B, int W, int H) {
+  const size_t rows = (size_t)B * W, al = 255;
+  const size_t tc = ((rows * 3 * H * 2 + al) & ~al) + 2 * ((rows * H * 4 + al) & ~al) + 2 * ((rows * 5 * H * 4 + al) & ~al) +
+                    (((size_t)B * 3 * H * 2 + al) & ~al);
+  return tc + 2 * ((rows * 16 + al) & ~al) + 3 * ((rows * 4 + al) & ~al) + 1024;
+}
+size_t beam_search_scratch_bytes(int64_t B, int N, int W, int H) {
+  const size_t Kp = ((size_t)(H + 2) + 63) / 64 * 64;
+  return beam_search_state_bytes(B, W, H) + ((((size_t)B * (N + 1) * 3 * H + 127) & ~size_t(127)) + (size_t)B * N * N * 3 * Kp) * 2 + 1024;
+}
+bool decode_tc_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MSQ_DECODE_TC"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
+struct DecGemm {
+  const float* Wt;      // [H][ldw] k-major (whh_t: ldw = 4H gate-interleaved; wq_t: ldw = H)
+  int ldw, Ncols;
+  const float* h_src;   // MODE 0: h' of the previous step (rows gathered by parent), t == 0: h0 [B, H];  MODE 1: h' of this step
+  const float* c_src;   // MODE 0: c of the previous step (t == 0: null -> 0)
+  const int32_t* parent;
+  const uint8_t* seq;   // current sequences (token t-1 selects the XG row)
+  const float* xg;      // [B, N+1, 4H]
+  const float* bq;
+  float* h_out;         // MODE 0: h' ; MODE 1: q
+  float* c_out;
+  int64_t M;            // B * live
+  int live, W, N, H, t;
+};
+
+// TILE x TILE x 16 fp32 tiles, 256 threads, (TILE/16)^2 register micro-tile, register-prefetch double buffering
+template <int TILE, int MODE>
+__global__ void __launch_bounds__(256) dec_gemm_kernel(DecGemm a) {
+  pdl_sync();
+  constexpr int BK = 16, LD = TILE + 4, TM = TILE / 16, KV = TILE == 128 ? 8 : 4, BV = TILE == 128 ? 2 : 1;
+  __shared__ __align__(16) float As[2][BK][LD];
+  __shared__ __align__(16) float Bs[2][BK][LD];
+  const int tid = threadIdx.x, H = a.H;
+  const int64_t m0 = (int64_t)blockIdx.y * TILE;
+  const int n0 = blockIdx.x * TILE;
+  // A staging: thread owns row lrow, KV consecutive k
+  const int lrow = tid % TILE, lk = (tid / TILE) * KV;
+  const int64_t am = m0 + lrow;
+  const bool a_ok = am < a.M;
+  const float* ap = nullptr;
+  if (a_ok) {
+    const int64_t b = am / a.live;
+    const int wslot = (int)(am % a.live);
+    if (MODE == 0) ap = a.t == 0 ? a.h_src + b * H : a.h_src + (b * a.W + a.parent[b * a.W + wslot]) * H;
+    else ap = a.h_src + (b * a.W + wslot) * H;
+    ap += lk;
+  }
+  // B staging: BV float4 per thread; element e = tid + 256 * i covers k = e / (TILE/4), columns 4 * (e % (TILE/4))
+  const int ty = tid >> 4, tx = tid & 15;
+
+  auto row_of = [&](int i) -> int64_t { return m0 + (TILE == 128 ? (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4)) : ty * 4 + i); };
+  auto col_of = [&](int jh) -> int { return n0 + jh * 64 + tx * 4; };
+
+  float acc[TM][TM];
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int64_t row = row_of(i);
+    const bool ok = row < a.M;
+    const float* init = nullptr;
+    if (ok) {
+      if (MODE == 0) {
+        const int64_t b = row / a.live;
+        const int wslot = (int)(row % a.live);
+        const int prev = a.t == 0 ? a.N : a.seq[(b * a.W + wslot) * DC_MAXN + a.t - 1];
+        init = a.xg + (b * (a.N + 1) + prev) * (int64_t)(4 * H);
+      } else {
+        init = a.bq;
+      }
+    }
+#pragma unroll
+    for (int jh = 0; jh < TM / 4; ++jh) {
+      const int col = col_of(jh);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok && col < a.Ncols) v = *reinterpret_cast<const float4*>(init + col);
+      acc[i][jh * 4 + 0] = v.x; acc[i][jh * 4 + 1] = v.y; acc[i][jh * 4 + 2] = v.z; acc[i][jh * 4 + 3] = v.w;
+    }
+  }
+
+  float ra[KV];
+  float4 rb[BV];
+  auto load_a = [&](int kt) {
+    if (a_ok) {
+      const float4 x = *reinterpret_cast<const float4*>(ap + kt * BK);
+      ra[0] = x.x; ra[1] = x.y; ra[2] = x.z; ra[3] = x.w;
+      if (KV == 8) { const float4 y = *reinterpret_cast<const float4*>(ap + kt * BK + 4); ra[4] = y.x; ra[5] = y.y; ra[6] = y.z; ra[7] = y.w; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < KV; ++i) ra[i] = 0.f;
+    }
+  };
+  auto load_b = [&](int kt) {
+#pragma unroll
+    for (int i = 0; i < BV; ++i) {
+      const int e = tid + 256 * i, k = e / (TILE / 4), c = 4 * (e % (TILE / 4));
+      rb[i] = (n0 + c < a.Ncols) ? __ldg(reinterpret_cast<const float4*>(a.Wt + (int64_t)(kt * BK + k) * a.ldw + n0 + c))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto stage = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < KV; ++i) As[buf][lk + i][lrow] = ra[i];
+#pragma unroll
+    for (int i = 0; i < BV; ++i) {
+      const int e = tid + 256 * i, k = e / (TILE / 4), c = 4 * (e % (TILE / 4));
+      *reinterpret_cast<float4*>(&Bs[buf][k][c]) = rb[i];
+    }
+  };
+  const int nk = H / BK;
+  load_a(0); load_b(0); stage(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) { load_a(kt + 1); load_b(kt + 1); }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float av[TM], bv[TM];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+      av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
+      bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+      if (TILE == 128) {
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
+        av[TM - 4] = a1.x; av[TM - 3] = a1.y; av[TM - 2] = a1.z; av[TM - 1] = a1.w;
+        bv[TM - 4] = b1.x; bv[TM - 3] = b1.y; bv[TM - 2] = b1.z; bv[TM - 1] = b1.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TM; ++j) acc[i][j] = fmaf(bv[j], av[i], acc[i][j]);
+    }
+    if (kt + 1 < nk) stage(cur ^ 1);
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int64_t row = row_of(i);
+    if (row >= a.M) continue;
+    const int64_t b = row / a.live;
+    const int wslot = (int)(row % a.live);
+    const int64_t orow = b * a.W + wslot;
+#pragma unroll
+    for (int jh = 0; jh < TM / 4; ++jh) {
+      const int col = col_of(jh);
+      if (col >= a.Ncols) continue;
+      if (MODE == 0) {
+        // columns 4u .. 4u+3 are the (i, f, g, o) pre-activations of hidden unit u
+        const int u = col >> 2;
+        const float gi = acc[i][jh * 4 + 0], gf = acc[i][jh * 4 + 1], gc = acc[i][jh * 4 + 2], go = acc[i][jh * 4 + 3];
+        const float ig = 1.f / (1.f + expf(-gi)), fg = 1.f / (1.f + expf(-gf));
+        const float gg = tanhf(gc), og = 1.f / (1.f + expf(-go));
+        const float cin = a.c_src ? a.c_src[(b * a.W + a.parent[orow]) * H + u] : 0.f;
+        const float c2 = fg * cin + ig * gg;
+        a.c_out[orow * H + u] = c2;
+        a.h_out[orow * H + u] = og * tanhf(c2);
+      } else {
+        *reinterpret_cast<float4*>(a.h_out + orow * H + col) =
+            make_float4(acc[i][jh * 4 + 0], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
+      }
+    }
+  }
+}
+
+template <int MODE>
+static int launch_dec_gemm(const DecGemm& a, cudaStream_t st) {
+  // 64 x 64 tiles until there are enough 128 x 128 tiles for two per SM
+  if ((int64_t)ceil_div(a.Ncols, 128) * ceil_div(a.M, 128) < 2 * 148) {
+    MSQ_CUDA(launch_k(dec_gemm_kernel<64, MODE>, dim3(ceil_div(a.Ncols, 64), ceil_div(a.M, 64)), dim3(256), 0, st, a));
+  } else {
+    MSQ_CUDA(launch_k(dec_gemm_kernel<128, MODE>, dim3(ceil_div(a.Ncols, 128), ceil_div(a.M, 128)), dim3(256), 0, st, a));
+  }
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+
+// One CTA per manual: pointer scores of every live beam over the N candidate steps, log-softmax, top-k, new tables.
+__global__ void __launch_bounds__(512, 1) dec_select_kernel(DecodeWeights w, DecodeIO io, DecState s, int t, int live, int cur, int nbuf) {
+  pdl_sync();
+  extern __shared__ __align__(16) float fg_s[];   // 2 x (F rows [N][H] | G rows [N][H]): candidate step being scored + the next
+  const int H = io.H, N = io.N, W = io.W, H4 = 4 * H;
+  __shared__ float e[16][DC_MAXN];
+  __shared__ float cost[16];
+  __shared__ uint8_t seq[16][DC_MAXN];
+  __shared__ uint32_t pickm[16];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x;
+  const int64_t b = blockIdx.x;
+  // x / N as a correctly rounded quotient without the division subroutine: q0 = RN(x rN), r = x - q0 N (exact, fma),
+  // q = RN(q0 + r rN) (Markstein; rN = RN(1/N); operands are O(1), far from under/overflow): bit-identical to x / (float)N
+  const float fN = (float)N, rN = 1.0f / fN;
+  auto div_n = [&](float x) { const float q0 = x * rN; return fmaf(fmaf(-q0, fN, x), rN, q0); };
+  const uint8_t* seq_g = s.seq[cur] + b * W * DC_MAXN;
+  if (tid < live) {
+    uint32_t picked = 0;
+    for (int i = 0; i < t; ++i) { const uint8_t v = seq_g[tid * DC_MAXN + i]; seq[tid][i] = v; picked |= 1u << v; }
+    pickm[tid] = picked;
+    cost[tid] = t == 0 ? 0.f : s.cost[cur][b * W + tid];
+  }
+  __syncthreads();
+  const float* t4 = io.t4 + b * (int64_t)N * N * H4;
+  uint32_t any_rem = 0;   // steps still unpicked in at least one live beam
+  for (int i = 0; i < live; ++i) any_rem |= ~pickm[i];
+
+  // ---- F[k, j, :] and G[j, k, :] for every j some beam still needs are staged with cp.async, one candidate step ahead
+  // (double buffer): read once per manual and step, shared by all beams
+  auto stage = [&](int k, int buf) {
+    float* F = fg_s + (size_t)buf * 2 * N * H;
+    float* G = F + (size_t)N * H;
+    for (int idx = tid; idx < N * (H / 4); idx += nthr) {
+      const int j = idx / (H / 4), d4 = idx % (H / 4);
+      if (j == k || !(any_rem >> j & 1u)) continue;
+      const uint32_t df = (uint32_t)__cvta_generic_to_shared(F + (size_t)j * H + 4 * d4);
+      const uint32_t dg = (uint32_t)__cvta_generic_to_shared(G + (size_t)j * H + 4 * d4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(df), "l"(t4 + ((int64_t)k * N + j) * H4 + 2 * H + 4 * d4) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dg), "l"(t4 + ((int64_t)j * N + k) * H4 + 3 * H + 4 * d4) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // nbuf == 2: candidate step k+1 is staged while k is scored (few CTAs: latency matters); nbuf == 1: half the shared memory,
+  // more CTAs per SM hide the staging instead (many manuals: throughput matters)
+  if (nbuf == 2) stage(0, 0);
+  for (int k = 0; k < N; ++k) {
+    if (nbuf == 2 && k + 1 < N) {
+      stage(k + 1, (k + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      if (nbuf == 1) stage(k, 0);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* Fs = fg_s + (size_t)(nbuf == 2 ? (k & 1) : 0) * 2 * N * H;
+    const float* Gs = Fs + (size_t)N * H;
+    // A warp scores candidate step k for one beam.  Lane-strided over d in batches of 4 (the global operands of a batch are
+    // loaded before any is used); the summation order is the reference order: j ascending inside fs / gs, d ascending
+    // inside the dot product, xor-tree over lanes.
+    for (int wslot = warp; wslot < live; wslot += nthr >> 5) {
+      const uint32_t picked = pickm[wslot];
+      if (picked >> k & 1u) {
+        if (lane == 0) e[wslot][k] = -1e9f;
+        continue;
+      }
+      const uint32_t need = ~picked & ~(1u << k) & ((1u << N) - 1u);
+      const float* qp = s.q + (b * s.q_rows + wslot) * (int64_t)s.q_ld;
+      const float* a1 = t >= 1 ? t4 + ((int64_t)seq[wslot][t - 1] * N + k) * H4 : nullptr;
+      const float* a2 = t >= 2 ? t4 + ((int64_t)seq[wslot][t - 2] * N + k) * H4 + H : nullptr;
+      const float* k0 = io.key0 + (b * N + k) * (int64_t)H;
+      float part = 0.f;
+      for (int d0 = lane; d0 < H; d0 += 32 * 4) {
+        float qv[4], a1v[4], a2v[4], kv[4], wv[4], fs[4], gs[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int d = d0 + 32 * u;
+          const bool ok = d < H;
+          kv[u] = ok ? __ldg(k0 + d) : 0.f;
+          wv[u] = ok ? __ldg(w.wt + d) : 0.f;
+          qv[u] = ok ? qp[d] : 0.f;
+          a1v[u] = (ok && a1) ? __ldg(a1 + d) : 0.f;
+          a2v[u] = (ok && a2) ? __ldg(a2 + d) : 0.f;
+          fs[u] = 0.f; gs[u] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < DC_MAXN; ++j) {
+          if (j < N && (need >> j & 1u)) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int d = d0 + 32 * u;
+              if (d < H) { fs[u] += Fs[(size_t)j * H + d]; gs[u] += Gs[(size_t)j * H + d]; }
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (d0 + 32 * u < H) {
+            float key = div_n(fs[u]) + div_n(gs[u]);
+            if (a1) key += a1v[u];
+            if (a2) key += a2v[u];
+            part = fmaf(wv[u], tanhf(qv[u] + key + kv[u]), part);
+          }
+      }
+      part = warp_sum(part);
+      if (lane == 0) e[wslot][k] = part + w.bt;
+    }
+    __syncthreads();
+  }
+
+  // ---- log-softmax per live beam; e <- candidate cost
+  if (tid < live) {
+    float mx = -INFINITY, sum = 0.f;
+    for (int k = 0; k < N; ++k) mx = fmaxf(mx, e[tid][k]);
+    for (int k = 0; k < N; ++k) sum += expf(e[tid][k] - mx);
+    const float lse = logf(sum);
+    for (int k = 0; k < N; ++k) {
+      const float logp = (e[tid][k] - mx) - lse;
+      if (io.trace_logp) io.trace_logp[((b * (N - 1) + t) * W + tid) * N + k] = logp;
+      e[tid][k] = -logp + cost[tid];
+    }
+  }
+  __syncthreads();
+
+  // ---- top-k by rank counting (ascending cost, ties -> lowest flat index beam*N+step)
+  const int nxt = cur ^ 1;
+  const int numel = live * N;
+  const bool last = t == N - 2;
+  for (int flat = tid; flat < numel; flat += nthr) {
+    const int wslot = flat / N, k = flat % N;
+    int kk = min(W, numel);
+    const float mine = e[wslot][k];
+    int rank = 0;
+    if (io.forced) {
+      kk = 1;   // teacher forcing (modeling_bert.py:998-1078): the single hypothesis follows the target order
+      rank = (wslot == 0 && k == io.forced[b * N + t]) ? 0 : 1;
+    } else {
+      for (int o = 0; o < numel; ++o) {
+        const float v = e[o / N][o % N];
+        rank += (v < mine) || (v == mine && o < flat);
+      }
+    }
+    if (rank < kk) {
+      const int64_t nr = b * W + rank;
+      if (io.trace_ix) io.trace_ix[(b * (N - 1) + t) * W + rank] = flat;
+      if (io.trace_cost) io.trace_cost[(b * (N - 1) + t) * W + rank] = mine;
+      if (!last) {
+        s.parent[nr] = wslot;
+        s.cost[nxt][nr] = mine;
+        uint8_t* ns = s.seq[nxt] + nr * DC_MAXN;
+        for (int i = 0; i < t; ++i) ns[i] = seq[wslot][i];
+        ns[t] = (uint8_t)k;
+      } else if (rank == 0) {
+        // best hypothesis; the one unused index goes last (modeling_bert.py:1549-1550)
+        uint32_t picked = pickm[wslot] | (1u << k);
+        for (int i = 0; i < t; ++i) io.perm[b * N + i] = seq[wslot][i];
+        io.perm[b * N + t] = k;
+        int rest = 0;
+        while (rest < N - 1 && (picked >> rest & 1u)) ++rest;
+        io.perm[b * N + N - 1] = rest;
+        if (io.final_cost) io.final_cost[b] = mine;
+      }
+    }
+  }
+}
+
+static int next_live(int live, int N, int W) { return min(W, live * N); }
+
+static int beam_search_tiled(const DecodeWeights& w, const DecodeIO& io, cudaStream_t st) {
+  MSQ_REQUIRE(io.scratch != nullptr, "beam_search: scratch buffer missing");
+  const int H = io.H, N = io.N, W = io.W;
+  const size_t rows = (size_t)io.B * W;
+  char* p = reinterpret_cast<char*>(io.scratch);
+  auto carve = [&](size_t bytes) { char* r = p; p += (bytes + 255) & ~size_t(255); return r; };
+  DecState s;
+  for (int i = 0; i < 2; ++i) s.h[i] = (float*)carve(rows * H * 4);
+  for (int i = 0; i < 2; ++i) s.c[i] = (float*)carve(rows * H * 4);
+  float* qbuf = (float*)carve(rows * H * 4);
+  s.q = qbuf; s.q_ld = H; s.q_rows = W;
+  for (int i = 0; i < 2; ++i) s.seq[i] = (uint8_t*)carve(rows * 16);
+  for (int i = 0; i < 2; ++i) s.cost[i] = (float*)carve(rows * 4);
+  s.parent = (int32_t*)carve(rows * 4);
+  const size_t smem = (size_t)4 * N * H * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    MSQ_CUDA(cudaFuncSetAttribute(dec_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int live = 1;
+  for (int t = 0; t < N - 1; ++t) {
+    const int cur = t & 1;   // tables (seq, cost) of step t live in slot cur; h'/c of step t are written to slot cur
+    DecGemm g;
+    g.Wt = w.whh_t; g.ldw = 4 * H; g.Ncols = 4 * H;
+    g.h_src = t == 0 ? io.h0 : s.h[cur ^ 1]; g.c_src = t == 0 ? nullptr : s.c[cur ^ 1];
+    g.parent = s.parent; g.seq = s.seq[cur]; g.xg = io.xg; g.bq = nullptr;
+    g.h_out = s.h[cur]; g.c_out = s.c[cur];
+    g.M = io.B * live; g.live = live; g.W = W; g.N = N; g.H = H; g.t = t;
+    MSQ_TRY(launch_dec_gemm<0>(g, st));
+    DecGemm q = g;
+    q.Wt = w.wq_t; q.ldw = H; q.Ncols = H; q.h_src = s.h[cur]; q.c_src = nullptr; q.bq = w.bq; q.h_out = qbuf; q.c_out = nullptr;
+    MSQ_TRY(launch_dec_gemm<1>(q, st));
+    {
+      // throughput form (every SM has CTAs to interleave): 256 threads, single staging buffer; latency form otherwise
+      static int force = -2;
+      if (force == -2) { const char* e = getenv("MSQ_DEC_MANY"); force = e ? atoi(e) : -1; }
+      const bool many = force >= 0 ? force != 0 : io.B > 148;
+      const int nbuf = many ? 1 : 2;
+      MSQ_CUDA(launch_k(dec_select_kernel, dim3((unsigned)io.B), dim3((!many && live > 8) ? 512 : 256), smem / (many ? 2 : 1), st, w, io, s, t, live, cur, nbuf));
+    }
+    MSQ_LAUNCH_CHECK();
+    live = io.forced ? 1 : next_live(live, N, W);
+  }
+  return MSQ_OK;
+}
+
+// ---- tensor-core form: per step  cell (elementwise)  ->  [q | h' W_hh^T] = h' [W_q ; W_hh]^T + [b_q ; 0] as ONE tcgen05 GEMM on
+// three-plane bf16 operands (bf16x6)  ->  dec_select.  h W_hh^T is computed once per PARENT row; the children gather it in
+// the cell kernel together with their own XG row, so the beam re-gather costs nothing and no GEMM operand is permuted.
+__global__ void __launch_bounds__(256) dec_cell_kernel(const float* __restrict__ xg, const float* __restrict__ hw_prev, int hw_ld,
+                                                       const float* __restrict__ c_prev, const int32_t* __restrict__ parent,
+                                                       const uint8_t* __restrict__ seq, int t, int live, int live_prev, int W, int N,
+                                                       int H, int64_t rows, float* __restrict__ c_out, bf16* __restrict__ hp) {
+  pdl_sync();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * H) return;
+  const int64_t m = i / H;
+  const int u = (int)(i % H);
+  const int64_t b = m / live;
+  const int wslot = (int)(m % live);
+  const int prev = t == 0 ? N : seq[(b * W + wslot) * DC_MAXN + t - 1];
+  const int p = t == 0 ? 0 : parent[b * W + wslot];
+  const float4 x = *reinterpret_cast<const float4*>(xg + (b * (N + 1) + prev) * (int64_t)(4 * H) + 4 * u);
+  const float4 g = *reinterpret_cast<const float4*>(hw_prev + (b * live_prev + p) * (int64_t)hw_ld + 4 * u);
+  const float gi = x.x + g.x, gf = x.y + g.y, gc = x.z + g.z, go = x.w + g.w;
+  const float ig = 1.f / (1.f + expf(-gi)), fg = 1.f / (1.f + expf(-gf));
+  const float gg = tanhf(gc), og = 1.f / (1.f + expf(-go));
+  const float cin = t == 0 ? 0.f : c_prev[(b * live_prev + p) * (int64_t)H + u];
+  const float c2 = fg * cin + ig * gg;
+  const float h2 = og * tanhf(c2);
+  c_out[m * H + u] = c2;
+  const bf16 p0 = __float2bfloat16_rn(h2);
+  const float r1 = h2 - __bfloat162float(p0);
+  const bf16 p1 = __float2bfloat16_rn(r1);
+  bf16* d = hp + m * 3 * H + u;
+  d[0] = p0; d[H] = p1; d[2 * H] = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+}
+
+static int beam_search_tc(const DecodeWeights& w, const DecodeIO& io, cudaStream_t st) {
+  const int H = io.H, N = io.N, W = io.W;
+  const size_t rows = (size_t)io.B * W;
+  char* p = reinterpret_cast<char*>(io.scratch);
+  auto carve = [&](size_t bytes) { char* r = p; p += (bytes + 255) & ~size_t(255); return r; };
+  bf16* hp = (bf16*)carve(rows * 3 * H * 2);
+  float* cb[2]; float* qh[2];
+  for (int i = 0; i < 2; ++i) cb[i] = (float*)carve(rows * H * 4);
+  for (int i = 0; i < 2; ++i) qh[i] = (float*)carve(rows * 5 * H * 4);
+  bf16* h0p = (bf16*)carve((size_t)io.B * 3 * H * 2);
+  DecState s;
+  s.h[0] = s.h[1] = nullptr; s.c[0] = cb[0]; s.c[1] = cb[1];
+  for (int i = 0; i < 2; ++i) s.seq[i] = (uint8_t*)carve(rows * 16);
+  for (int i = 0; i < 2; ++i) s.cost[i] = (float*)carve(rows * 4);
+  s.parent = (int32_t*)carve(rows * 4);
+  const size_t smem = (size_t)4 * N * H * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    MSQ_CUDA(cudaFuncSetAttribute(dec_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  GemmArgs g;
+  g.bias = nullptr; g.resid = nullptr; g.C2 = nullptr; g.K = H; g.lda = H; g.ldw = H; g.ldc = 5 * H; g.ldr = 0; g.act = ACT_NONE; g.split = 2;
+  // h0 W_hh^T -> columns [H, 5H) of qh[1] (read by the first cell as "previous step")
+  MSQ_TRY(pack_split3(io.h0, io.B, H, H, H, h0p, st));
+  g.A = h0p; g.W = w.wcat3 + (size_t)H * 3 * H; g.C = qh[1] + H; g.M = io.B; g.N = 4 * H;
+  MSQ_TRY(gemm_tc<float>(g, st));
+  int live = 1, live_prev = 1;
+  for (int t = 0; t < N - 1; ++t) {
+    const int cur = t & 1;
+    const int64_t M = io.B * live;
+    MSQ_CUDA(launch_k(dec_cell_kernel, dim3((unsigned)ceil_div(M * H, 256)), dim3(256), 0, st, io.xg, (const float*)(qh[cur ^ 1] + H), 5 * H,
+                      (const float*)cb[cur ^ 1], (const int32_t*)s.parent, (const uint8_t*)s.seq[cur], t, live, live_prev, W, N, H, M, cb[cur], hp));
+    MSQ_LAUNCH_CHECK();
+    const bool last = t == N - 2;
+    g.A = hp; g.W = w.wcat3; g.bias = w.bcat; g.C = qh[cur]; g.M = M; g.N = last ? H : 5 * H;   // the last step needs q only
+    MSQ_TRY(gemm_tc<float>(g, st));
+    s.q = qh[cur]; s.q_ld = 5 * H; s.q_rows = live;
+    {
+      // throughput form (every SM has CTAs to interleave): 256 threads, single staging buffer; latency form otherwise
+      static int force = -2;
+      if (force == -2) { const char* e = getenv("MSQ_DEC_MANY"); force = e ? atoi(e) : -1; }
+      const bool many = force >= 0 ? force != 0 : io.B > 148;
+      const int nbuf = many ? 1 : 2;
+      MSQ_CUDA(launch_k(dec_select_kernel, dim3((unsigned)io.B), dim3((!many && live > 8) ? 512 : 256), smem / (many ? 2 : 1), st, w, io, s, t, live, cur, nbuf));
+    }
+    MSQ_LAUNCH_CHECK();
+    live_prev = live;
+    live = io.forced ? 1 : next_live(live, N, W);
+  }
+  return MSQ_OK;
+}
+
+int beam_search(const DecodeWeights& w, const DecodeIO& io, cudaStream_t st) {
+  MSQ_REQUIRE(io.N >= 2 && io.N <= DC_MAXN, "beam_search: N=%d out of range [2,%d]", io.N, DC_MAXN);
+  MSQ_REQUIRE(io.W >= 1 && io.W <= 16, "beam_search: beam width %d out of range [1,16]", io.W);
+  MSQ_REQUIRE(io.H % 16 == 0 && io.H <= 1024, "beam_search: H=%d unsupported", io.H);
+  if (io.B == 0) return MSQ_OK;
+  static int fused = -1;
+  if (fused < 0) { const char* e = getenv("MSQ_DECODE_FUSED"); fused = (e && e[0] == '1') ? 1 : 0; }
+  if (fused || !io.scratch) return beam_search_fused(w, io, st);
+  if (io.tc && w.wcat3 && io.H % 64 == 0) return beam_search_tc(w, io, st);
+  return beam_search_tiled(w, io, st);
 }
 
 

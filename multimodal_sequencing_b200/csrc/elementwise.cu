@@ -254,6 +254,28 @@ __global__ void pack_pad_kernel(const float* __restrict__ src, int64_t rows, int
     }
   }
 }
+__global__ void pack_split3_kernel(const float* __restrict__ src, int64_t rows, int K, int ld, int Kp, bf16* __restrict__ dst) {
+  pdl_sync();
+  const int64_t total = rows * Kp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / Kp;
+    const int c = (int)(i % Kp);
+    const float v = c < K ? src[r * ld + c] : 0.f;
+    const bf16 p0 = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(p0);
+    const bf16 p1 = __float2bfloat16_rn(r1);
+    const bf16 p2 = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+    bf16* d = dst + r * 3 * Kp + c;
+    d[0] = p0; d[Kp] = p1; d[2 * Kp] = p2;
+  }
+}
+int pack_split3(const float* src, int64_t rows, int K, int ld, int Kp, bf16* dst, cudaStream_t st) {
+  if (rows == 0) return MSQ_OK;
+  MSQ_CUDA(launch_k(pack_split3_kernel, dim3((int)min((int64_t)148 * 8, (rows * Kp + 255) / 256)), dim3(256), 0, st, src, rows, K, ld, Kp, dst));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+
 template <typename TO>
 int pack_pad(const float* src, int64_t rows, int K, int Kp, TO* dst, cudaStream_t st) {
   if (rows == 0) return MSQ_OK;

@@ -61,7 +61,8 @@ struct TcEpi {
   int sp_in;
   float inv_dim, eps;
   int tn;   // GemmArgs::tn: MN-major operands (single-CTA path)
-  int split_k;  // GemmArgs::split: logical K (A and W rows are [hi(K) | lo(K)]); 0 = plain bf16 operands
+  int split_k;  // GemmArgs::split: logical K (A and W rows are planes of K columns: [hi | lo] or [hi | mid | lo]); 0 = plain bf16
+  int split_passes;  // 3 (two planes: bf16x3) or 6 (three planes: bf16x6, fp32-grade products)
 };
 
 // 8 consecutive output columns of one row: accumulator -> value to store (see GemmArgs for the modes)
@@ -229,7 +230,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           // bf16x3: the K loop runs three times over every 64-column slab: a_hi*w_lo, a_lo*w_hi, a_hi*w_hi (the hi and
           // lo planes of a row are K columns apart); the MMA warp just sees a contraction of length 3K
           int kb = kq, ka = 0, kw = 0;
-          if (ep.split_k) { kb = kq / 3; const int t = kq - 3 * kb; ka = t == 1 ? ep.split_k : 0; kw = t == 0 ? ep.split_k : 0; }
+          if (ep.split_k) {
+            // (plane of A, plane of W) per pass, smallest products first.  two planes: (0,1) (1,0) (0,0);
+            // three planes: (0,2) (1,1) (2,0) (0,1) (1,0) (0,0) -- every product a_i w_j with i + j <= 2
+            kb = kq / ep.split_passes;
+            const int t = kq - ep.split_passes * kb;
+            const uint32_t pa = ep.split_passes == 3 ? 0x010u : 0x010210u, pw = ep.split_passes == 3 ? 0x001u : 0x001012u;
+            ka = (int)((pa >> (4 * t)) & 0xFu) * ep.split_k;
+            kw = (int)((pw >> (4 * t)) & 0xFu) * ep.split_k;
+          }
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + TC_A_BYTES;
           if (PAIR) {
@@ -535,9 +544,10 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
   if (g.tn) {   // [K rows, M or N columns], boxes of 64 x 64
     MSQ_TRY(make_map_bf16(&ma, g.A, g.K, (int)g.M, g.lda, 64, 64));
     MSQ_TRY(make_map_bf16(&mb, g.W, g.K, g.N, g.ldw, 64, 64));
-  } else if (g.split) {   // rows are [hi(K) | lo(K)]; lda / ldw count logical elements
-    MSQ_TRY(make_map_bf16(&ma, g.A, g.M, 2 * g.K, 2 * g.lda, TC_BK, TC_BM));
-    MSQ_TRY(make_map_bf16(&mb, g.W, g.N, 2 * g.K, 2 * g.ldw, TC_BK, Cfg::B_ROWS));
+  } else if (g.split) {   // rows are planes of K columns ([hi | lo] or [hi | mid | lo]); lda / ldw count logical elements
+    const int P = g.split + 1;
+    MSQ_TRY(make_map_bf16(&ma, g.A, g.M, P * g.K, P * g.lda, TC_BK, TC_BM));
+    MSQ_TRY(make_map_bf16(&mb, g.W, g.N, P * g.K, P * g.ldw, TC_BK, Cfg::B_ROWS));
   } else {
     MSQ_TRY(make_map_bf16(&ma, g.A, g.M, g.K, g.lda, TC_BK, TC_BM));
     MSQ_TRY(make_map_bf16(&mb, g.W, g.N, g.K, g.ldw, TC_BK, Cfg::B_ROWS));
@@ -559,7 +569,8 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
   ep.bias = g.bias; ep.resid = g.resid; ep.C = g.C; ep.M = g.M; ep.N = g.N; ep.ldc = g.ldc; ep.ldr = g.ldr; ep.act = g.act;
   ep.svec = g.svec; ep.beta = g.beta; ep.stats_in = g.stats_in; ep.stats_out = g.stats_out; ep.C2 = (bf16*)g.C2bf; ep.sp_in = g.sp_in;
   ep.inv_dim = g.ln_inv_dim; ep.eps = g.ln_eps; ep.tn = g.tn; ep.split_k = g.split ? g.K : 0;
-  const int num_m = ceil_div(g.M, Cfg::TILE_M), num_n = ceil_div(g.N, TC_BN), num_k = ceil_div(g.K, TC_BK) * (g.split ? 3 : 1);
+  ep.split_passes = g.split == 2 ? 6 : 3;
+  const int num_m = ceil_div(g.M, Cfg::TILE_M), num_n = ceil_div(g.N, TC_BN), num_k = ceil_div(g.K, TC_BK) * (g.split ? ep.split_passes : 1);
   const int64_t tiles = (int64_t)num_m * num_n;
   profile_mark(st, false, 0.0);
   if (PAIR) {
@@ -639,7 +650,8 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   MSQ_REQUIRE(((uintptr_t)g.A & 15) == 0 && ((uintptr_t)g.W & 15) == 0 && ((uintptr_t)g.C & 15) == 0, "gemm_tc: unaligned pointer");
   MSQ_REQUIRE(g.C2 == nullptr, "gemm_tc: second output unsupported");
   MSQ_REQUIRE(!g.split || (!g.tn && g.mode == EPI_PLAIN && g.K % TC_BK == 0), "gemm_tc: split-bf16 operands need K-major layout, the plain epilogue and K %% 64 == 0");
-  MSQ_REQUIRE(!is_split<TO>::value || (g.split && g.N % 64 == 0), "gemm_tc: split-bf16 output needs split operands and N %% 64 == 0");
+  MSQ_REQUIRE(g.split >= 0 && g.split <= 2 && (!g.split || (g.K == g.lda && g.K == g.ldw)), "gemm_tc: split=%d operands need lda == ldw == K (planes are K columns apart)", g.split);
+  MSQ_REQUIRE(!is_split<TO>::value || (g.split == 1 && g.N % 64 == 0), "gemm_tc: split-bf16 output needs split operands and N %% 64 == 0");
   if (g.M == 0) return MSQ_OK;
   static int sms = 0, force_single = -1;
   if (!sms) {

@@ -21,6 +21,8 @@ template <typename T> int im2col(const float* img, int64_t n, int S, int P, T* o
 template <typename TI, typename TO>
 int gather_rows(const TI* src, int64_t rows, int H, int group, int src_group, int off, TO* dst, cudaStream_t st);
 template <typename TO> int pack_pad(const float* src, int64_t rows, int K, int Kp, TO* dst, cudaStream_t st);
+// fp32 [rows, K] (leading dimension ld) -> three bf16 planes per row [hi(Kp) | mid(Kp) | lo(Kp)], zero padded to Kp columns
+int pack_split3(const float* src, int64_t rows, int K, int ld, int Kp, bf16* dst, cudaStream_t st);
 
 // ---- rn.cu : CLIP ModifiedResNet helpers (NHWC activations; convolutions run as im2col + GEMM)
 int rn_fold(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, int Cout, int Cin, int k,
@@ -64,6 +66,8 @@ struct GemmArgs {
   // gemm_tc only: bf16x3 precision mode.  A and W rows are [hi(K) | lo(K)] bf16 (type bf16s; lda / ldw / ldc count logical
   // elements); C = A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T with fp32 accumulation, exact activations in the epilogue.
   // Output type float or bf16s (a split row [hi(ldc) | lo(ldc)]).  Plain epilogue only.
+  // split = 2: THREE planes [hi | mid | lo] (24 significand bits = every fp32 value exactly) and six MMAs per product
+  // (all a_i w_j with i + j <= 2): fp32-grade products on the tensor cores ("bf16x6"; the decoder's GEMMs).  fp32 out.
   int split = 0;
   int mode = EPI_PLAIN;
   const float* svec = nullptr;
@@ -108,6 +112,9 @@ struct DecodeWeights {
   const float* bq;      // [H]
   const float* wt;      // [H] tanh_linear.weight
   float bt;             // tanh_linear.bias
+  // tensor-core decode (bf16x6): [W_q ; W_hh gate-interleaved] as [5H rows][3 planes x H] bf16, and [b_q ; 0] (5H)
+  const bf16* wcat3 = nullptr;
+  const float* bcat = nullptr;
 };
 struct DecodeIO {
   const float* xg;     // [B, N+1, 4H] gate-interleaved input projections; row N = bias only (t = 0)
@@ -122,7 +129,12 @@ struct DecodeIO {
   float* trace_logp;   // optional [B, N-1, W, N]
   const int32_t* forced;  // optional [B, N]: teacher-forced picks (W must be 1)
   float* final_cost;      // optional [B]: cost of the best hypothesis
+  void* scratch = nullptr;  // beam_search_scratch_bytes(B, N, W, H) bytes of device memory (tiled decode; null -> fused kernel)
+  int tc = 0;               // 1: recurrent GEMMs on the tensor cores (bf16x6, needs DecodeWeights::wcat3); 0: fp32 FFMA
 };
+size_t beam_search_state_bytes(int64_t B, int W, int H);             // search state (either decode form)
+size_t beam_search_scratch_bytes(int64_t B, int N, int W, int H);    // state + three-plane copies of sents_ext / r0 (tensor-core form)
+bool decode_tc_enabled();                                             // MSQ_DECODE_TC=0 keeps the fp32 FFMA GEMMs in every mode
 int beam_search(const DecodeWeights& w, const DecodeIO& io, cudaStream_t st);
 struct StepIO {
   float* rela;                 // [Wb,N,N,H+2] zeroed in place where rela_mask == 0

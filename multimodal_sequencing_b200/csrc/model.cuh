@@ -96,6 +96,7 @@ struct msq_model {
   const float *rn_pos = nullptr, *rn_posadd = nullptr;
   // berson heads
   Lin sent_tran, key_lin, xg_lin, t4_lin, pwk_raw, wih_raw, whh_raw, wq_raw;
+  const bf16 *wih3 = nullptr, *wpw3 = nullptr;   // three-plane (bf16x6) copies of xg_lin / t4_lin weights (tensor-core decode)
   int Kp4 = 0;
   const float *w2 = nullptr, *b2 = nullptr, *w_rel = nullptr, *b_rel = nullptr, *w_in2 = nullptr;
   std::vector<ParaLayerW> para;

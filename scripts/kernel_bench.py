@@ -126,16 +126,23 @@ def bench_decode():
     H = 768
     cfg = dict(hidden_size=H, num_hidden_layers=1, num_attention_heads=12, intermediate_size=64, vocab_size=64,
                max_position_embeddings=8, vit=None, para_ff=64)
-    eng = OrderingEngine(synth.full_state_dict(cfg, None, seed=0, ff=64), cfg, precise=True)
+    eng = OrderingEngine(synth.full_state_dict(cfg, None, seed=0, ff=64), cfg, precise=(os.environ.get("MSQ_BENCH_PRECISE", "0") == "1"))
     for N, W in ((5, 4), (10, 16)):
         for B in (1, 8, 64, 256):
             enc = {k: v.to(dev) for k, v in synth.synthetic_encode(N, H, seed=3, B=B).items()}
             ms = timed(lambda: eng.beam_search(enc, N, W), iters=5, do_flush=False)
             per_step = N * N * 770 * 4 + N * 768 * 4 + W * (4 * 768 * 4 + 2 * N * 4)
             byt = B * per_step * (N - 1)
-            print(json.dumps(dict(kernel="decode (2 pre-projection GEMMs + beam_search_kernel)", N=N, W=W, B=B, ms=ms,
-                                  manuals_per_s=B / ms * 1e3, algorithmic_gbs=byt / ms / 1e6,
-                                  frac_hbm=byt / ms / 1e6 / PK["hbm_gbs"], bound="fp32 FMA / L2 (see DESIGN.md §3)")))
+            live, fma = 1, 0
+            for t in range(N - 1):       # recurrent GEMMs: gates (4H columns) + query (H columns) for every live row
+                fma += B * live * 5 * H * H
+                live = min(W, live * N)
+            peak32 = 148 * 128 * 2 * 1.965e9 / 1e12   # fp32 FFMA peak at the maximum SM clock (TFLOP/s)
+            print(json.dumps(dict(kernel="decode (2 pre-projection GEMMs + %s)" % ("beam_search_kernel" if os.environ.get("MSQ_DECODE_FUSED") == "1"
+                                                                                  else "per step: dec_gemm x2 + dec_select"),
+                                  N=N, W=W, B=B, ms=ms, manuals_per_s=B / ms * 1e3, algorithmic_gbs=byt / ms / 1e6,
+                                  frac_hbm=byt / ms / 1e6 / PK["hbm_gbs"], recurrent_fp32_tflops=2 * fma / ms / 1e9,
+                                  frac_fp32_peak=2 * fma / ms / 1e9 / peak32, bound="fp32 FMA (recurrent GEMMs) + HBM (T4 rows)")))
 
 
 if __name__ == "__main__":

@@ -246,16 +246,19 @@ def test_attention(L, heads, masked):
 # golden fixtures produced by the REAL reference
 # ---------------------------------------------------------------------------------------------
 
-def test_decode_full_width_golden(golden_dir):
+@pytest.mark.parametrize("precise", [True, False])
+def test_decode_full_width_golden(golden_dir, precise):
     """H=768 decode stage fed with identical (seeded) encode outputs: bit-exact beam indices and
-    permutations for N in {5,6,10} x W in {1,4,8,16} against the reference's beam_search_pointer."""
+    permutations for N in {5,6,10} x W in {1,4,8,16} against the reference's beam_search_pointer.
+    precise=True: fp32 FFMA decode (tiled SGEMM); precise=False: the tensor-core decode (three-plane bf16 operands, six MMAs
+    per product) the bf16 / bf16x3 modes run -- held to the same bit-exact indices and the same cost tolerance."""
     g = torch.load(os.path.join(golden_dir, "decode_full.pt"), weights_only=False)
     H = g["H"]
     cfg = dict(hidden_size=H, num_hidden_layers=1, num_attention_heads=12, intermediate_size=64, vocab_size=64,
                max_position_embeddings=8, vit=None, para_ff=64)
     sd = synth.full_state_dict(cfg, None, seed=0, ff=64)
     sd.update(synth.decode_head_weights(H, 7))
-    eng = _engine(sd, cfg, precise=True)
+    eng = _engine(sd, cfg, precise=precise)
     for c in g["cases"]:
         enc = synth.synthetic_encode(c["N"], H, c["enc_seed"])
         perm, tr = eng.beam_search(enc, c["N"], c["W"], trace=True)
@@ -264,13 +267,14 @@ def test_decode_full_width_golden(golden_dir):
         _check_trace(tr, 0, c["steps"], c["W"], c["N"])
 
 
-def test_decode_batched_equals_single(golden_dir):
+@pytest.mark.parametrize("precise", [True, False])
+def test_decode_batched_equals_single(golden_dir, precise):
     """batched beam search (a new capability) must reproduce the per-manual results exactly."""
     H = 768
     cfg = dict(hidden_size=H, num_hidden_layers=1, num_attention_heads=12, intermediate_size=64, vocab_size=64,
                max_position_embeddings=8, vit=None, para_ff=64)
     sd = synth.full_state_dict(cfg, None, seed=0, ff=64)
-    eng = _engine(sd, cfg, precise=True)
+    eng = _engine(sd, cfg, precise=precise)
     for N, W, B in ((5, 4, 37), (10, 16, 9), (6, 8, 20), (5, 1, 300)):
         enc = synth.synthetic_encode(N, H, seed=500 + N, B=B)
         perm = eng.beam_search(enc, N, W).cpu()
@@ -538,18 +542,19 @@ def test_full_size_batch_invariance_and_chunking():
 # edge cases of the decode / host boundary
 # ---------------------------------------------------------------------------------------------
 
-def _decode_engine(H=768):
+def _decode_engine(H=768, precise=True):
     cfg = dict(hidden_size=H, num_hidden_layers=1, num_attention_heads=H // 64, intermediate_size=64, vocab_size=64,
                max_position_embeddings=8, vit=None, para_ff=64)
     sd = synth.full_state_dict(cfg, None, seed=0, ff=64)
-    return _engine(sd, cfg, precise=True), sd
+    return _engine(sd, cfg, precise=precise), sd
 
 
+@pytest.mark.parametrize("precise", [True, False])
 @pytest.mark.parametrize("N,W", [(2, 1), (2, 16), (3, 16), (4, 16), (16, 1), (16, 16), (9, 3)])
-def test_decode_edge_sizes_vs_oracle(N, W):
+def test_decode_edge_sizes_vs_oracle(N, W, precise):
     """smallest / largest manuals and beams wider than the number of valid candidates (the reference then
     selects masked candidates with cost ~1e9, generator.py:19-22): final permutation equals the oracle's."""
-    eng, sd = _decode_engine()
+    eng, sd = _decode_engine(precise=precise)
     for seed in (1, 2, 3):
         enc = synth.synthetic_encode(N, 768, seed=900 + seed + N, B=3)
         perm = eng.beam_search(enc, N, W).cpu().tolist()
