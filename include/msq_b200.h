@@ -55,6 +55,13 @@ typedef struct msq_config {
   int32_t reserved2[2];
 } msq_config;
 
+/* Hard limits of this build (violations fail with a message, nothing is silently truncated):
+ *   manual length N in [2,16]; beam width W in [1,16]; hidden size H a multiple of 128, <= 1024; head dim = 64
+ *   (heads * 64 == hidden); vit_width a multiple of 128, <= 1024; inter % 16 == 0 (bf16x3: % 64); joint sequence
+ *   length per pair (text + visual tokens) <= 320 (tcgen05 attention: <= 256); text tokens per pair Lt <= max_pos;
+ *   manuals are encoded in micro-batches of MSQ_CHUNK_MANUALS (environment, default 32); the ModifiedResNet tower needs
+ *   rn_width % 16 == 0, rn_embed % 32 == 0, image size a multiple of 32; fine-tuning (msq_train_*) covers the ViT-B/32 and
+ *   text-only models in precise 0 / 1. */
 const char* msq_last_error(void);
 int msq_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
@@ -150,6 +157,25 @@ int msq_order_manuals_host(msq_model* m, const int64_t* ids_host, const int64_t*
                            const int64_t* sep_host, int64_t B, int32_t N, int32_t Lt, const float* images_host,
                            int64_t n_img, const int32_t* img_index_host, int32_t beam, int32_t* perm_host, void* stream);
 
+/* ---- device-side pair expansion (models/berson/process_inputs_for_berson.py:113-368, 246-261, 82-97) -------------------
+ * msq_scan_steps: positions of the N [CLS] / [SEP] tokens of every manual row ids_dev [B,L] -> starts_dev / lens_dev (int32
+ *   [B,N]); meta_dev = 2 int32 of scratch; *lt_out = padded pair length max_{i!=j}(len_i + len_j), read back with one 8-byte
+ *   device->host copy (the only synchronisation).  Fails when a manual does not hold exactly N [CLS]..[SEP] steps (the
+ *   reference asserts the same).
+ * msq_expand_pairs: writes the P = N(N-1) ordered pair rows of every manual: out_ids / out_mask / out_tt [B,P,Lt] int64,
+ *   out_sep [B,P,2] int64, img_index [B,P,2] int32 (manual-order images, may be NULL).  Bit-identical to the reference's host
+ *   code, quirks included (mask of a padded position = pad_id; token types all zero when cls_id == 0).
+ * msq_order_manuals_raw_host: berson_pointer_network from the DataLoader tuple: token rows ids_host [B,L] int64 and step
+ *   images images_host [B*N,3,S,S] fp32 in host memory -> perm_host [B,N]; expansion happens on the device. */
+int msq_scan_steps(const int64_t* ids_dev, int64_t B, int32_t L, int32_t N, int64_t cls_id, int64_t sep_id, int32_t* starts_dev,
+                   int32_t* lens_dev, int32_t* meta_dev, int32_t* lt_out, void* stream);
+int msq_expand_pairs(const int64_t* ids_dev, int64_t B, int32_t L, int32_t N, int32_t Lt, int64_t cls_id, int64_t pad_id,
+                     const int32_t* starts_dev, const int32_t* lens_dev, int64_t* out_ids_dev, int64_t* out_mask_dev,
+                     int64_t* out_tt_dev, int64_t* out_sep_dev, int32_t* img_index_dev, void* stream);
+int msq_order_manuals_raw_host(msq_model* m, const int64_t* ids_host, int64_t B, int32_t L, int32_t N, int64_t cls_id,
+                               int64_t sep_id, int64_t pad_id, const float* images_host, int32_t beam, int32_t* perm_host,
+                               void* stream);
+
 /* ---- fine-tuning of the inner encoder (BASELINE config 4) -------------------------------------
  * What the reference gets from autograd + transformers.AdamW (trainers/train.py:172-190, 340-363) for the inner model
  * LXRTModel / BertModel (lxrt/modeling.py:1513-1598, modeling_bert.py:563-663) and the CLIP ViT tower
@@ -180,6 +206,15 @@ int msq_train_step(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, 
                    int64_t B, int32_t N, int32_t Lt, const float* images_dev, int64_t n_img, const int32_t* img_index_dev,
                    const int32_t* ground_truth_dev, const int64_t* pairwise_labels_dev, float lam, float* grads_dev, float* loss_dev,
                    void* stream);
+/* Data-parallel overlap: msq_train_step records one CUDA event per REGION of the flat gradient buffer at the moment that
+ * region is final (BERSON heads, BERT layers top -> bottom, embeddings, visn_fc, ViT blocks top -> bottom, ViT stem).
+ * msq_train_ready_count = regions of the last step, in completion order; msq_train_ready_info = element range [begin, end)
+ * of region i (regions are disjoint and cover every parameter); msq_train_ready_wait makes `stream` wait for region i, so
+ * the caller can all-reduce it on a side stream while the backward pass of the earlier layers is still running
+ * (what DistributedDataParallel's bucketing does for trainers/train.py:217-221). */
+int64_t msq_train_ready_count(msq_model* m);
+int msq_train_ready_info(msq_model* m, int64_t i, int64_t* begin, int64_t* end);
+int msq_train_ready_wait(msq_model* m, int64_t i, void* stream);
 /* torch.nn.utils.clip_grad_norm_(max_grad_norm) (<= 0: no clipping) over grad_scale * grads, then one step of
  * transformers.AdamW (correct_bias=True; weight decay skipped for names containing "bias" or "LayerNorm.weight",
  * train.py:172-181), then every packed copy of the weights is rebuilt.  norm_out_dev (2 floats or NULL) receives the

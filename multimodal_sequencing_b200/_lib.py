@@ -42,6 +42,9 @@ SIGNATURES = {
     "msq_pointer_p1": (C.c_int, [_P] * 10 + [_I64, _I32, _I32, _I32, _P, _P, _P, _P]),
     "msq_order_manuals_dev": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _I32, _P, _P]),
     "msq_order_manuals_host": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _I32, _P, _P]),
+    "msq_scan_steps": (C.c_int, [_P, _I64, _I32, _I32, _I64, _I64, _P, _P, _P, C.POINTER(_I32), _P]),
+    "msq_expand_pairs": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "msq_order_manuals_raw_host": (C.c_int, [_P, _P, _I64, _I32, _I32, _I64, _I64, _I64, _P, _I32, _P, _P]),
     "msq_train_param_count": (_I64, [_P, _P]),
     "msq_train_grad_numel": (_I64, [_P, _P]),
     "msq_train_param_info": (C.c_int, [_P, _I64, C.POINTER(C.c_char_p), C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I32)]),
@@ -49,6 +52,9 @@ SIGNATURES = {
     "msq_inner_forward_train": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _I64, _P, _P, _P, _P]),
     "msq_inner_backward": (C.c_int, [_P, _P, _P, _P, _P]),
     "msq_train_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P, _P, _F, _P, _P, _P]),
+    "msq_train_ready_count": (_I64, [_P]),
+    "msq_train_ready_info": (C.c_int, [_P, _I64, C.POINTER(_I64), C.POINTER(_I64)]),
+    "msq_train_ready_wait": (C.c_int, [_P, _I64, _P]),
     "msq_adamw_step": (C.c_int, [_P, _P, _F, _F, _F, _F, _F, _F, _F, _P, _P]),
     "msq_gemm": (C.c_int, [_I32, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P]),
     "msq_gemm_deferred_ln": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _F, _P, _P, _P, _I64, _I32, _I32, _I32, _P]),

@@ -411,13 +411,18 @@ extern "C" int msq_model_create(const msq_config* cfg, msq_model** out) {
   }
   msq_model* m = new msq_model();
   m->cfg = *cfg;
+  MSQ_CUDA(cudaGetDevice(&m->device));
   *out = m;
   return MSQ_OK;
 }
 
-extern "C" void msq_model_destroy(msq_model* m) { delete m; }
+extern "C" void msq_model_destroy(msq_model* m) {
+  DevGuard dev_guard__(m);
+  delete m;
+}
 
 extern "C" int msq_model_set_weight(msq_model* m, const char* name, const float* data_dev, int64_t numel, void* stream) {
+  DevGuard dev_guard__(m);
   MSQ_REQUIRE(m && name && data_dev && numel > 0, "bad argument");
   MSQ_REQUIRE(!m->packed, "model already packed");
   float* p = nullptr;
@@ -430,6 +435,7 @@ extern "C" int msq_model_set_weight(msq_model* m, const char* name, const float*
 }
 
 extern "C" int msq_model_pack(msq_model* m, void* stream) {
+  DevGuard dev_guard__(m);
   MSQ_REQUIRE(m && !m->packed, "bad state");
   cudaStream_t st = (cudaStream_t)stream;
   const msq_config& c = m->cfg;
@@ -1294,6 +1300,7 @@ static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const i
 
 extern "C" int msq_vit_forward(msq_model* m, const float* images_dev, int64_t n_img, const int32_t* img_index_dev, int64_t R,
                                float* out_dev, void* stream) {
+  DevGuard dev_guard__(m);
   MSQ_REQUIRE(m && m->packed && m->has_vit, "model has no visual tower / not packed");
   cudaStream_t st = (cudaStream_t)stream;
   const msq_config& c = m->cfg;
@@ -1318,6 +1325,7 @@ extern "C" int msq_vit_forward(msq_model* m, const float* images_dev, int64_t n_
 extern "C" int msq_inner_forward(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev, int64_t R,
                                  int32_t Lt, const float* images_dev, int64_t n_img, const int32_t* img_index_dev, float* lang_dev,
                                  float* visn_dev, float* pooled_dev, void* stream) {
+  DevGuard dev_guard__(m);
   MSQ_REQUIRE(m && m->packed && m->has_bert, "model not packed / no inner encoder weights");
   cudaStream_t st = (cudaStream_t)stream;
   const msq_config& c = m->cfg;
@@ -1350,6 +1358,7 @@ extern "C" int msq_inner_forward(msq_model* m, const int64_t* ids_dev, const int
 extern "C" int msq_encode(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev,
                           const int64_t* sep_dev, int64_t B, int32_t N, int32_t Lt, const float* images_dev, int64_t n_img,
                           const int32_t* img_index_dev, const msq_encode_out* out, void* stream) {
+  DevGuard dev_guard__(m);
   MSQ_REQUIRE(m && out, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   MSQ_DISPATCH_T(m, run_path<T>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, out, 0, nullptr, st));
@@ -1358,6 +1367,7 @@ extern "C" int msq_encode(msq_model* m, const int64_t* ids_dev, const int64_t* t
 extern "C" int msq_order_manuals_dev(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev,
                                      const int64_t* sep_dev, int64_t B, int32_t N, int32_t Lt, const float* images_dev,
                                      int64_t n_img, const int32_t* img_index_dev, int32_t beam, int32_t* perm_dev, void* stream) {
+  DevGuard dev_guard__(m);
   MSQ_REQUIRE(m && perm_dev, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   MSQ_DISPATCH_T(m, run_path<T>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, nullptr, beam, perm_dev, st));
@@ -1368,6 +1378,7 @@ extern "C" int msq_training_loss(msq_model* m, const int64_t* ids_dev, const int
                                  const int64_t* sep_dev, int64_t B, int32_t N, int32_t Lt, const float* images_dev, int64_t n_img,
                                  const int32_t* img_index_dev, const int32_t* ground_truth_dev, const int64_t* pairwise_labels_dev,
                                  float lam, int32_t* perm_scratch_dev, float* loss_dev, void* stream) {
+  DevGuard dev_guard__(m);
   MSQ_REQUIRE(m && ground_truth_dev && pairwise_labels_dev && perm_scratch_dev && loss_dev, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   MSQ_DISPATCH_T(m, run_path<T>(m, ids_dev, tt_dev, mask_dev, sep_dev, B, N, Lt, images_dev, n_img, img_index_dev, nullptr, 1,
@@ -1377,6 +1388,7 @@ extern "C" int msq_training_loss(msq_model* m, const int64_t* ids_dev, const int
 extern "C" int msq_beam_search(msq_model* m, const float* sents_dev, const float* key_dev, const float* h0_dev,
                                const float* cls_mat_dev, const float* score_mat_dev, int64_t B, int32_t N, int32_t beam,
                                int32_t* perm_dev, int32_t* trace_ix_dev, float* trace_cost_dev, float* trace_logp_dev, void* stream) {
+  DevGuard dev_guard__(m);
   MSQ_REQUIRE(m && m->packed && m->has_heads, "model not packed / no BERSON head weights");
   MSQ_REQUIRE(N >= 2 && N <= 16, "N=%d out of range", N);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1407,6 +1419,7 @@ extern "C" int msq_decode_step(msq_model* m, const float* prev_y_dev, const floa
                                const float* hist1_dev, const float* hist2_dev, const uint8_t* l1_mask_dev,
                                const uint8_t* l2_mask_dev, int32_t Wb, int32_t N, float* h_out_dev, float* c_out_dev,
                                float* logp_out_dev, void* stream) {
+  DevGuard dev_guard__(m);
   MSQ_REQUIRE(m && m->packed && m->has_heads, "model not packed / no BERSON head weights");
   MSQ_REQUIRE(Wb >= 1 && N >= 2 && N <= 16, "bad Wb/N");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1447,24 +1460,28 @@ extern "C" int msq_pointer_p1(const float* enc_dev, const float* cls_dev, const 
                     ce_scratch_dev, loss_dev, (cudaStream_t)stream);
 }
 
+static int stage_reserve(msq_model* m, size_t need, cudaStream_t st) {
+  if (need <= m->stage_cap) return MSQ_OK;
+  MSQ_CUDA(cudaStreamSynchronize(st));
+  if (m->stage) MSQ_CUDA(cudaFree(m->stage));
+  m->stage = nullptr; m->stage_cap = 0;
+  MSQ_CUDA(cudaMalloc(&m->stage, need));
+  m->stage_cap = need;
+  return MSQ_OK;
+}
+
 extern "C" int msq_order_manuals_host(msq_model* m, const int64_t* ids_host, const int64_t* tt_host, const int64_t* mask_host,
                                       const int64_t* sep_host, int64_t B, int32_t N, int32_t Lt, const float* images_host,
                                       int64_t n_img, const int32_t* img_index_host, int32_t beam, int32_t* perm_host, void* stream) {
+  DevGuard dev_guard__(m);
   MSQ_REQUIRE(m && m->packed && perm_host, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t R = B * N * (N - 1);
   const size_t n_tok = (size_t)R * Lt, img_elems = images_host ? (size_t)n_img * 3 * m->cfg.vit_res * m->cfg.vit_res : 0;
-  // staging buffers live outside the workspace arena (which run_path re-plans)
-  static thread_local char* stage = nullptr;
-  static thread_local size_t stage_cap = 0;
+  // staging buffer: owned by the model, outside the workspace arena (which run_path re-plans)
   const size_t need = 3 * n_tok * 8 + (size_t)R * 2 * 8 + img_elems * 4 + (size_t)R * 2 * 4 + (size_t)B * N * 4 + 8 * 256;
-  if (need > stage_cap) {
-    MSQ_CUDA(cudaStreamSynchronize(st));
-    if (stage) MSQ_CUDA(cudaFree(stage));
-    stage = nullptr; stage_cap = 0;
-    MSQ_CUDA(cudaMalloc(&stage, need));
-    stage_cap = need;
-  }
+  MSQ_TRY(stage_reserve(m, need, st));
+  char* stage = m->stage;
   size_t off = 0;
   auto carve = [&](size_t bytes) { char* p = stage + off; off += (bytes + 255) & ~size_t(255); return p; };
   int64_t* ids = (int64_t*)carve(n_tok * 8);
@@ -1489,8 +1506,8 @@ extern "C" int msq_order_manuals_host(msq_model* m, const int64_t* ids_host, con
       const int64_t b = i / P2;
       local = img_index_host[i] >= b * N && img_index_host[i] < (b + 1) * N;
     }
-    static thread_local cudaStream_t copy_st = nullptr;
-    static thread_local std::vector<cudaEvent_t> evs;
+    cudaStream_t& copy_st = m->copy_st;
+    std::vector<cudaEvent_t>& evs = m->copy_evs;
     const int64_t Bc = min((int64_t)chunk_manuals(), B);
     const int64_t nchunks = (B + Bc - 1) / Bc;
     if (local && nchunks > 1) {
@@ -1511,6 +1528,104 @@ extern "C" int msq_order_manuals_host(msq_model* m, const int64_t* ids_host, con
       MSQ_CUDA(cudaMemcpyAsync(img, images_host, img_elems * 4, cudaMemcpyHostToDevice, st));
     }
   }
+  auto go = [&]() -> int {
+    MSQ_DISPATCH_T(m, run_path<T>(m, ids, tt, mask, sep, B, N, Lt, images_host ? img : nullptr, n_img, images_host ? idx : nullptr, nullptr,
+                                  beam, perm, st, nullptr, nullptr, 0.f, nullptr, ready));
+  };
+  MSQ_TRY(go());
+  MSQ_CUDA(cudaMemcpyAsync(perm_host, perm, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
+  MSQ_CUDA(cudaStreamSynchronize(st));
+  return MSQ_OK;
+}
+
+// ---- device-side pair expansion (process_inputs_for_berson.py:113-368) ------------------------------------------------
+// msq_scan_steps: [CLS] / [SEP] positions of every manual -> starts / lens tables (device, int32 [B,N]) and, after ONE
+// 8-byte device->host read, the padded pair length Lt = max_{i != j}(len_i + len_j).  Fails (like the reference's
+// assertion) when a manual does not hold exactly N [CLS] .. [SEP] steps.
+extern "C" int msq_scan_steps(const int64_t* ids_dev, int64_t B, int32_t L, int32_t N, int64_t cls_id, int64_t sep_id,
+                              int32_t* starts_dev, int32_t* lens_dev, int32_t* meta_dev, int32_t* lt_out, void* stream) {
+  MSQ_REQUIRE(ids_dev && starts_dev && lens_dev && meta_dev && lt_out, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  MSQ_TRY(scan_steps(ids_dev, B, L, N, cls_id, sep_id, starts_dev, lens_dev, meta_dev, st));
+  int32_t meta[2] = {0, 0};
+  if (B > 0) {
+    MSQ_CUDA(cudaMemcpyAsync(meta, meta_dev, sizeof(meta), cudaMemcpyDeviceToHost, st));
+    MSQ_CUDA(cudaStreamSynchronize(st));
+  }
+  MSQ_REQUIRE(meta[1] == 0, "every manual must hold exactly max_story_length [CLS]..[SEP] steps");
+  *lt_out = meta[0];
+  return MSQ_OK;
+}
+extern "C" int msq_expand_pairs(const int64_t* ids_dev, int64_t B, int32_t L, int32_t N, int32_t Lt, int64_t cls_id, int64_t pad_id,
+                                const int32_t* starts_dev, const int32_t* lens_dev, int64_t* out_ids_dev, int64_t* out_mask_dev,
+                                int64_t* out_tt_dev, int64_t* out_sep_dev, int32_t* img_index_dev, void* stream) {
+  MSQ_REQUIRE(ids_dev && starts_dev && lens_dev && out_ids_dev && out_mask_dev && out_tt_dev && out_sep_dev, "null argument");
+  return expand_pairs(ids_dev, B, L, N, Lt, cls_id, pad_id, starts_dev, lens_dev, out_ids_dev, out_mask_dev, out_tt_dev, out_sep_dev,
+                      img_index_dev, (cudaStream_t)stream);
+}
+
+// berson_pointer_network from the DataLoader tuple (modeling_bert.py:1405-1408 + process_inputs_for_berson.py): token rows
+// [B, L] and step images [B*N, 3, S, S] in HOST memory (ideally pinned) -> predicted orders [B, N] in host memory.  The token
+// rows are uploaded as they are (B*L*8 bytes), pairs are expanded on the device, images stream in micro-batch by
+// micro-batch behind the compute.  Synchronous.
+extern "C" int msq_order_manuals_raw_host(msq_model* m, const int64_t* ids_host, int64_t B, int32_t L, int32_t N, int64_t cls_id,
+                                          int64_t sep_id, int64_t pad_id, const float* images_host, int32_t beam, int32_t* perm_host,
+                                          void* stream) {
+  DevGuard dev_guard__(m);
+  MSQ_REQUIRE(m && m->packed && ids_host && perm_host, "bad argument");
+  MSQ_REQUIRE(N >= 2 && N <= 16 && B >= 0, "N=%d out of range [2,16]", N);
+  MSQ_REQUIRE(!(m->cfg.vit_width != 0 && images_host == nullptr), "multimodal model needs images");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) return MSQ_OK;
+  const int64_t R = B * N * (N - 1), n_img = images_host ? B * N : 0;
+  const size_t per_img = (size_t)3 * m->cfg.vit_res * m->cfg.vit_res, img_elems = images_host ? (size_t)n_img * per_img : 0;
+  const int Lt_cap = 2 * L;   // upper bound of the padded pair length (the true Lt is known after the scan)
+  const size_t need = (size_t)B * L * 8 + 2 * (size_t)B * N * 4 + 256 + 3 * (size_t)R * Lt_cap * 8 + (size_t)R * 2 * 8 + img_elems * 4 +
+                      (size_t)R * 2 * 4 + (size_t)B * N * 4 + 12 * 256;
+  MSQ_TRY(stage_reserve(m, need, st));
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { char* p = m->stage + off; off += (bytes + 255) & ~size_t(255); return p; };
+  int64_t* raw = (int64_t*)carve((size_t)B * L * 8);
+  int32_t* starts = (int32_t*)carve((size_t)B * N * 4);
+  int32_t* lens = (int32_t*)carve((size_t)B * N * 4);
+  int32_t* meta = (int32_t*)carve(256);
+  float* img = (float*)carve(img_elems * 4);
+  int32_t* idx = (int32_t*)carve((size_t)R * 2 * 4);
+  int32_t* perm = (int32_t*)carve((size_t)B * N * 4);
+  int64_t* sep = (int64_t*)carve((size_t)R * 2 * 8);
+  char* toks = carve(3 * (size_t)R * Lt_cap * 8);
+  // images first on the copy stream (they are the bulk of the bytes), one event per micro-batch
+  const cudaEvent_t* ready = nullptr;
+  const int64_t Bc = min((int64_t)chunk_manuals(), B), nchunks = (B + Bc - 1) / Bc;
+  if (images_host) {
+    if (nchunks > 1) {
+      if (!m->copy_st) MSQ_CUDA(cudaStreamCreateWithFlags(&m->copy_st, cudaStreamNonBlocking));
+      while ((int64_t)m->copy_evs.size() < nchunks + 1) {
+        cudaEvent_t e;
+        MSQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        m->copy_evs.push_back(e);
+      }
+      // the staging buffer may still be read by work enqueued on `st` by a previous call
+      MSQ_CUDA(cudaEventRecord(m->copy_evs[nchunks], st));
+      MSQ_CUDA(cudaStreamWaitEvent(m->copy_st, m->copy_evs[nchunks], 0));
+      for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t i0 = c * Bc * N, n = min(Bc, B - c * Bc) * N;
+        MSQ_CUDA(cudaMemcpyAsync(img + i0 * per_img, images_host + i0 * per_img, n * per_img * 4, cudaMemcpyHostToDevice, m->copy_st));
+        MSQ_CUDA(cudaEventRecord(m->copy_evs[c], m->copy_st));
+      }
+      ready = m->copy_evs.data();
+    } else {
+      MSQ_CUDA(cudaMemcpyAsync(img, images_host, img_elems * 4, cudaMemcpyHostToDevice, st));
+    }
+  }
+  MSQ_CUDA(cudaMemcpyAsync(raw, ids_host, (size_t)B * L * 8, cudaMemcpyHostToDevice, st));
+  int32_t Lt = 0;
+  MSQ_TRY(msq_scan_steps(raw, B, L, N, cls_id, sep_id, starts, lens, meta, &Lt, stream));
+  MSQ_REQUIRE(Lt >= 2 && Lt <= Lt_cap, "pair length %d out of range", Lt);
+  int64_t* ids = (int64_t*)toks;
+  int64_t* mask = ids + (size_t)R * Lt;
+  int64_t* tt = mask + (size_t)R * Lt;
+  MSQ_TRY(expand_pairs(raw, B, L, N, Lt, cls_id, pad_id, starts, lens, ids, mask, tt, sep, images_host ? idx : nullptr, st));
   auto go = [&]() -> int {
     MSQ_DISPATCH_T(m, run_path<T>(m, ids, tt, mask, sep, B, N, Lt, images_host ? img : nullptr, n_img, images_host ? idx : nullptr, nullptr,
                                   beam, perm, st, nullptr, nullptr, 0.f, nullptr, ready));

@@ -388,11 +388,7 @@ static int launch_attention_tc(const bf16* qkv, int64_t R, int L, int heads, flo
   MSQ_TRY(make_map_bf16(&mq, qkv, R * L, ld, ld, AT_D, 128));
   MSQ_TRY(make_map_bf16(&mkv, qkv, R * L, ld, ld, AT_D, KP));
   constexpr int SMEM = AttnCfg<KP, SPL>::SMEM;
-  static bool configured = false;
-  if (!configured) {
-    MSQ_CUDA(cudaFuncSetAttribute(attention_tc_kernel<KP, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured = true;
-  }
+  MSQ_SMEM_ATTR(SMEM, attention_tc_kernel<KP, SPL>);
   // Persistent grid = the CTAs that are resident at once: 2 per SM at KP = 256 (256 TMEM columns and 100 KB of shared
   // memory each), 3 per SM at KP = 128 (68 KB, 80 registers).  Measured (640 x 12 items): 296 CTAs 0.289 ms, 444 CTAs 0.365 ms
   // (a wave and a half), one CTA per item 0.335 ms; L = 99: 444 CTAs 0.101 ms vs 0.116 ms.
@@ -439,12 +435,7 @@ int attention(const T* qkv, int64_t R, int L, int heads, int dhead, float scale,
   }
   const int Lpad = (L + 31) & ~31;
   const size_t smem = sizeof(float) * ((size_t)L * 65 + (size_t)L * AT_D + ((L + 3) & ~3) + AT_WARPS * AT_D + AT_WARPS * Lpad);
-  static size_t configured_f = 0, configured_b = 0;
-  size_t& configured = sizeof(T) == 4 ? configured_f : configured_b;
-  if (smem > configured) {
-    MSQ_CUDA(cudaFuncSetAttribute(attention_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  MSQ_SMEM_ATTR(smem, attention_simt_kernel<T>);
   MSQ_CUDA(launch_k(attention_simt_kernel<T>, dim3((unsigned)(R * heads)), dim3(AT_WARPS * 32), smem, st, qkv, L, heads, scale, key_mask_add, mask_ld, mask_len, ctx));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;

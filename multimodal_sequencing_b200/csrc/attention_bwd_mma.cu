@@ -481,11 +481,7 @@ int attention_bwd_mma(const bf16* qkv, const bf16* ctx, const bf16* dctx, int64_
   if (fused < 0) { const char* e = getenv("MSQ_ATTN_BWD_FUSED"); fused = (e && e[0] == '1') ? 1 : 0; }
   if (fused || !scratch) {
     const size_t smem = (size_t)4 * Lp * ABM_LD * sizeof(bf16) + (size_t)3 * Lp * sizeof(float);
-    static size_t configured = 0;
-    if (smem > configured) {
-      MSQ_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
+    MSQ_SMEM_ATTR(smem, attention_bwd_mma_kernel);
     MSQ_CUDA(launch_k(attention_bwd_mma_kernel, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem, st, qkv, ctx, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv));
     MSQ_LAUNCH_CHECK();
     return MSQ_OK;
@@ -494,15 +490,8 @@ int attention_bwd_mma(const bf16* qkv, const bf16* ctx, const bf16* dctx, int64_
   float* dsum = scratch + (size_t)R * heads * L;
   const size_t smem_a = (size_t)2 * Lp * ABM_LD * sizeof(bf16) + (size_t)Lp * sizeof(float);
   const size_t smem_b = (size_t)2 * Lp * ABM_LD * sizeof(bf16) + (size_t)2 * Lp * sizeof(float);
-  static size_t conf_a = 0, conf_b = 0;
-  if (smem_a > conf_a) {
-    MSQ_CUDA(cudaFuncSetAttribute(attention_bwd_dq_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
-    conf_a = smem_a;
-  }
-  if (smem_b > conf_b) {
-    MSQ_CUDA(cudaFuncSetAttribute(attention_bwd_dkv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-    conf_b = smem_b;
-  }
+  MSQ_SMEM_ATTR(smem_a, attention_bwd_dq_mma_kernel);
+  MSQ_SMEM_ATTR(smem_b, attention_bwd_dkv_mma_kernel);
   MSQ_CUDA(launch_k(attention_bwd_dq_mma_kernel, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem_a, st, qkv, ctx, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, lse, dsum));
   MSQ_LAUNCH_CHECK();
   MSQ_CUDA(launch_k(attention_bwd_dkv_mma_kernel, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem_b, st, qkv, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, (const float*)lse, (const float*)dsum));

@@ -61,6 +61,19 @@ void set_error(const char* fmt, ...);
     if (rc__ != MSQ_OK) return rc__; \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remember per device what has been requested
+// (a process may hold models on several GPUs).  Usage: MSQ_SMEM_ATTR(bytes, kernel<template, args>);
+#define MSQ_SMEM_ATTR(bytes, ...)                                                                              \
+  do {                                                                                                         \
+    static size_t cfg__[64] = {0};                                                                             \
+    int dev__ = 0;                                                                                             \
+    MSQ_CUDA(cudaGetDevice(&dev__));                                                                           \
+    if ((size_t)(bytes) > cfg__[dev__ & 63]) {                                                                 \
+      MSQ_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      cfg__[dev__ & 63] = (size_t)(bytes);                                                                     \
+    }                                                                                                          \
+  } while (0)
+
 void count_launch();
 int pdl_enabled();
 

@@ -273,11 +273,7 @@ __global__ void __launch_bounds__(DC_THREADS) beam_search_kernel(DecodeWeights w
 template <int ROWS>
 static int launch_beam(const DecodeWeights& w, const DecodeIO& io, int G, cudaStream_t st) {
   const size_t smem = (size_t)3 * ROWS * io.H * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
-    MSQ_CUDA(cudaFuncSetAttribute(beam_search_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  MSQ_SMEM_ATTR(smem, beam_search_kernel<ROWS>);
   MSQ_CUDA(launch_k(beam_search_kernel<ROWS>, dim3(ceil_div(io.B, G)), dim3(DC_THREADS), smem, st, w, io, G));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
@@ -684,11 +680,7 @@ static int beam_search_tiled(const DecodeWeights& w, const DecodeIO& io, cudaStr
   for (int i = 0; i < 2; ++i) s.cost[i] = (float*)carve(rows * 4);
   s.parent = (int32_t*)carve(rows * 4);
   const size_t smem = (size_t)4 * N * H * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
-    MSQ_CUDA(cudaFuncSetAttribute(dec_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  MSQ_SMEM_ATTR(smem, dec_select_kernel);
   int live = 1;
   for (int t = 0; t < N - 1; ++t) {
     const int cur = t & 1;   // tables (seq, cost) of step t live in slot cur; h'/c of step t are written to slot cur
@@ -764,11 +756,7 @@ static int beam_search_tc(const DecodeWeights& w, const DecodeIO& io, cudaStream
   for (int i = 0; i < 2; ++i) s.cost[i] = (float*)carve(rows * 4);
   s.parent = (int32_t*)carve(rows * 4);
   const size_t smem = (size_t)4 * N * H * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
-    MSQ_CUDA(cudaFuncSetAttribute(dec_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  MSQ_SMEM_ATTR(smem, dec_select_kernel);
   GemmArgs g;
   g.bias = nullptr; g.resid = nullptr; g.C2 = nullptr; g.K = H; g.lda = H; g.ldw = H; g.ldc = 5 * H; g.ldr = 0; g.act = ACT_NONE; g.split = 2;
   // h0 W_hh^T -> columns [H, 5H) of qh[1] (read by the first cell as "previous step")
@@ -1023,11 +1011,7 @@ int pointer_p1(const float* enc, const float* cls, const int64_t* y, const float
   MSQ_REQUIRE(N >= 1 && N <= PM_MAXN && U >= 1 && U <= PM_MAXU && H <= 2048, "pointer_p1: N=%d U=%d H=%d out of range", N, U, H);
   if (B == 0) return MSQ_OK;
   const size_t smem = (size_t)8 * H * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
-    MSQ_CUDA(cudaFuncSetAttribute(pointer_p1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  MSQ_SMEM_ATTR(smem, pointer_p1_kernel);
   MSQ_CUDA(launch_k(pointer_p1_kernel, dim3((unsigned)B), dim3(256), smem, st, enc, cls, y, W1, W2, V, Wih, Whh, bih, bhh, N, H, U, preds,
                     ce_scratch));
   MSQ_LAUNCH_CHECK();

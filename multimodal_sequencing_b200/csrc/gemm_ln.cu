@@ -336,17 +336,13 @@ int gemm_ln(const bf16* A, int lda, const bf16* W, int ldw, const float* bias, c
   MSQ_TRY(make_map_2d(&mc, C, M, N, N, 32, 32, true));
   MSQ_TRY(make_map_2d(&mc2, C2, M, N, N, 64, 32, false));
   static int sms = 0;
-  static bool configured[2] = {false, false};
   if (!sms) {
     int dev = 0;
     MSQ_CUDA(cudaGetDevice(&dev));
     MSQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  if (!configured[raw32]) {
-    if (raw32) MSQ_CUDA(cudaFuncSetAttribute(gemm_ln_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LSMEM));
-    else MSQ_CUDA(cudaFuncSetAttribute(gemm_ln_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LSMEM));
-    configured[raw32] = true;
-  }
+  if (raw32) MSQ_SMEM_ATTR(LSMEM, gemm_ln_kernel<true>);
+  else MSQ_SMEM_ATTR(LSMEM, gemm_ln_kernel<false>);
   LnEpi ep;
   ep.bias = bias; ep.resid = resid; ep.gamma = gamma; ep.beta = beta; ep.M = M; ep.N = N; ep.ldr = ldr; ep.eps = eps;
   const int csize = N / LBN, num_m = ceil_div(M, LBM), num_k = K / LBK;

@@ -560,11 +560,7 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
   if (Cfg::TMA_STORE && MODE == 2) MSQ_TRY(make_map_2d(&mc2, g.C2bf, g.M, g.N, g.ldc, 32, 32, false, true));
   CUtensorMap mr = ma;
   if (Cfg::TMA_STORE && MODE == 2) MSQ_TRY(make_map_2d(&mr, g.resid, g.M, g.N, g.ldr, 32, 32, true));
-  static bool configured = false;
-  if (!configured) {
-    MSQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TO, PAIR, ACT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    configured = true;
-  }
+  MSQ_SMEM_ATTR(Cfg::SMEM, gemm_tc_kernel<TO, PAIR, ACT, MODE>);
   TcEpi ep;
   ep.bias = g.bias; ep.resid = g.resid; ep.C = g.C; ep.M = g.M; ep.N = g.N; ep.ldc = g.ldc; ep.ldr = g.ldr; ep.act = g.act;
   ep.svec = g.svec; ep.beta = g.beta; ep.stats_in = g.stats_in; ep.stats_out = g.stats_out; ep.C2 = (bf16*)g.C2bf; ep.sp_in = g.sp_in;

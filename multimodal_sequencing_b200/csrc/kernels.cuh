@@ -24,6 +24,13 @@ template <typename TO> int pack_pad(const float* src, int64_t rows, int K, int K
 // fp32 [rows, K] (leading dimension ld) -> three bf16 planes per row [hi(Kp) | mid(Kp) | lo(Kp)], zero padded to Kp columns
 int pack_split3(const float* src, int64_t rows, int K, int ld, int Kp, bf16* dst, cudaStream_t st);
 
+// ---- expand.cu : device-side pair expansion (process_inputs_for_berson.py:113-368)
+int scan_steps(const int64_t* ids, int64_t B, int L, int N, int64_t cls_id, int64_t sep_id, int32_t* starts, int32_t* lens, int32_t* meta,
+               cudaStream_t st);
+int expand_pairs(const int64_t* ids, int64_t B, int L, int N, int Lt, int64_t cls_id, int64_t pad_id, const int32_t* starts,
+                 const int32_t* lens, int64_t* out_ids, int64_t* out_mask, int64_t* out_tt, int64_t* out_sep, int32_t* img_index,
+                 cudaStream_t st);
+
 // ---- rn.cu : CLIP ModifiedResNet helpers (NHWC activations; convolutions run as im2col + GEMM)
 int rn_fold(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, int Cout, int Cin, int k,
             float* wf, float* bf, cudaStream_t st);

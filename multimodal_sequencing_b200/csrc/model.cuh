@@ -69,6 +69,12 @@ using namespace msq;
 
 struct msq_model {
   msq_config cfg;
+  int device = 0;   // CUDA device the model lives on (recorded by msq_model_create); every C ABI entry switches to it
+  // host-buffer entry points: staging buffer, copy stream and per-micro-batch events (owned by the model, freed with it)
+  char* stage = nullptr;
+  size_t stage_cap = 0;
+  cudaStream_t copy_st = nullptr;
+  std::vector<cudaEvent_t> copy_evs;
   std::unordered_map<std::string, std::pair<float*, int64_t>> raw;
   std::vector<void*> owned;
   std::vector<size_t> owned_bytes;
@@ -108,11 +114,23 @@ struct msq_model {
     for (auto& kv : raw) cudaFree(kv.second.first);
     for (void* p : owned) cudaFree(p);
     if (ws.base) cudaFree(ws.base);
+    if (stage) cudaFree(stage);
+    if (copy_st) cudaStreamDestroy(copy_st);
+    for (cudaEvent_t e : copy_evs) cudaEventDestroy(e);
     if (train) train_state_free(train);
   }
 };
 
 namespace msq {
+// switches the calling thread to the model's device for the duration of a C ABI call (restored on return)
+struct DevGuard {
+  int prev = -1;
+  bool sw = false;
+  explicit DevGuard(const msq_model* m) {
+    if (m && cudaGetDevice(&prev) == cudaSuccess && prev != m->device) sw = cudaSetDevice(m->device) == cudaSuccess;
+  }
+  ~DevGuard() { if (sw) cudaSetDevice(prev); }
+};
 int model_repack(msq_model* m, cudaStream_t st);   // api.cu
 bool model_use_tc(const msq_model* m);             // api.cu: tcgen05 path selected for this model / device
 }  // namespace msq

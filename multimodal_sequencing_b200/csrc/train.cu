@@ -122,6 +122,23 @@ static int ensure_train(msq_model* m, cudaStream_t st) {
   return rc;
 }
 
+// mark the slots [first, last] (by name) final: one event on the compute stream, recorded in completion order
+static int mark_ready(TrainState* ts, const std::string& first, const std::string& last, cudaStream_t st) {
+  auto a = ts->index.find(first), b = ts->index.find(last);
+  if (a == ts->index.end() || b == ts->index.end()) return MSQ_OK;   // group absent from this model
+  if (ts->ready_used == ts->ready_ev.size()) {
+    cudaEvent_t e;
+    MSQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ts->ready_ev.push_back(e);
+    ts->ready_rng.push_back({0, 0});
+  }
+  const ParamSlot &sa = ts->slots[a->second], &sb = ts->slots[b->second];
+  ts->ready_rng[ts->ready_used] = {sa.off, sb.off + sb.numel};
+  MSQ_CUDA(cudaEventRecord(ts->ready_ev[ts->ready_used], st));
+  ++ts->ready_used;
+  return MSQ_OK;
+}
+
 // ---- training forward ------------------------------------------------------------------------------
 template <typename T>
 static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, const int64_t* mask, int64_t R, int Lt, const float* images,
@@ -321,6 +338,7 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
     MSQ_TRY(attn_bwd<T>((const T*)t.qkv, (const T*)t.ctx, (const T*)b.gC, R, Lj, c.heads, ts->mask_add, Lt, (T*)b.gQ, b.at_scr, st));
     MSQ_TRY(wgrad<T>(m, (const T*)b.gQ, 3 * H, 3 * H, (const T*)t.x, H, H, ACT_NONE, Mj, dWqkv, dbqkv, b, st));
     MSQ_TRY((dgrad<T, float>(m, (const T*)b.gQ, 3 * H, WT[0], H, b.gB, b.gA, Mj, st)));        // dX0 = dqkv Wqkv + ds1
+    MSQ_TRY(mark_ready(ts, bn + "attention.self.query.weight", bn + "output.LayerNorm.bias", st));
   }
   // gA = gradient of the layer-0 input (LayerNorm outputs of the embeddings / of visn_fc)
   {
@@ -330,6 +348,7 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
     if (err) return err;
     MSQ_TRY(embed_ln_bwd(b.gA, ts->ids, ts->tt, R, Lt, Lj, H, m->word, m->pos, m->type, m->emb_ln.g, 1e-12f, dword, dpos, dtyp, dg, db, b.ln_scr,
                          c.vit_width != 0 ? 7 : 1, st));   // padding_idx=0 tables: LXRT all three, text-only BertModel the word table
+    MSQ_TRY(mark_ready(ts, P + "embeddings.word_embeddings.weight", P + "embeddings.LayerNorm.bias", st));
   }
   if (!mm) return MSQ_OK;
 
@@ -345,6 +364,7 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
     // d(ln_post out) fp32 -> gA is free now: reuse it as [Mv, Wd]
     MSQ_TRY((dgrad<T, float>(m, (const T*)b.gT, H, ts->visnT, Wd, nullptr, b.gA, Mv, st)));
     MSQ_TRY(ln_bwd<T>(b.gA, ts->vx_last, nullptr, Mv, Wd, m->ln_post.g, 1e-5f, b.gB, (T*)b.gT, dgp, dbp, b.ln_scr, 0, 0, 0, st));
+    MSQ_TRY(mark_ready(ts, P + "encoder.visn_fc.visn_fc.weight", P + "encoder.visn_fc.visn_layer_norm.bias", st));
   }
   // ViT blocks: stream gradient dx in gB (fp32) + gT (operand copy)
   const int vheads = Wd / 64;
@@ -370,6 +390,7 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
     MSQ_TRY(wgrad<T>(m, (const T*)b.gQ, 3 * Wd, 3 * Wd, (const T*)t.y1, Wd, Wd, ACT_NONE, Mv, dWqkv, dbqkv, b, st));
     MSQ_TRY((dgrad<T, float>(m, (const T*)b.gQ, 3 * Wd, WT[0], Wd, nullptr, b.gA, Mv, st)));      // d(ln_1 out)
     MSQ_TRY(ln_bwd<T>(b.gA, t.x, b.gB, Mv, Wd, L.ln1.g, 1e-5f, b.gB, (T*)b.gT, dg1, db1, b.ln_scr, 0, 0, 0, st));    // dx = dx1 + LN'
+    MSQ_TRY(mark_ready(ts, bn + "attn.in_proj_weight", bn + "ln_2.bias", st));
   }
   // token assembly + ln_pre, then the patch-embedding weight gradient per image chunk
   {
@@ -386,6 +407,7 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
       MSQ_TRY((transpose_pad<T, T>((const T*)b.apatch, rows, Kc, Kc, Mp, (T*)b.XT, ACT_NONE, st)));
       MSQ_TRY((gemm_nt<T, float>(m, (const T*)b.GT, (int)Mp, (const T*)b.XT, (int)Mp, nullptr, dWc, Kc, dWc, Kc, Wd, Kc, (int)Mp, ACT_NONE, st)));
     }
+    MSQ_TRY(mark_ready(ts, v + "conv1.weight", v + "ln_post.bias", st));
   }
   return MSQ_OK;
 }
@@ -396,14 +418,17 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
 // C ABI
 // =====================================================================================================
 extern "C" int64_t msq_train_param_count(msq_model* m, void* stream) {
+  DevGuard dev_guard__(m);
   if (ensure_train(m, (cudaStream_t)stream) != MSQ_OK) return -1;
   return (int64_t)m->train->slots.size();
 }
 extern "C" int64_t msq_train_grad_numel(msq_model* m, void* stream) {
+  DevGuard dev_guard__(m);
   if (ensure_train(m, (cudaStream_t)stream) != MSQ_OK) return -1;
   return m->train->total;
 }
 extern "C" int msq_train_param_info(msq_model* m, int64_t i, const char** name, int64_t* offset, int64_t* numel, int32_t* decay) {
+  DevGuard dev_guard__(m);
   MSQ_REQUIRE(m && m->train && i >= 0 && i < (int64_t)m->train->slots.size(), "msq_train_param_info: bad index / no training state");
   const ParamSlot& s = m->train->slots[(size_t)i];
   if (name) *name = s.name.c_str();
@@ -413,6 +438,7 @@ extern "C" int msq_train_param_info(msq_model* m, int64_t i, const char** name, 
   return MSQ_OK;
 }
 extern "C" int msq_train_read_param(msq_model* m, const char* name, float* out_dev, int64_t numel, void* stream) {
+  DevGuard dev_guard__(m);
   MSQ_REQUIRE(m && name && out_dev, "null argument");
   auto it = m->raw.find(name);
   MSQ_REQUIRE(it != m->raw.end() && it->second.second == numel, "msq_train_read_param: unknown weight %s or wrong size", name);
@@ -423,6 +449,7 @@ extern "C" int msq_train_read_param(msq_model* m, const char* name, float* out_d
 extern "C" int msq_inner_forward_train(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev, int64_t R,
                                        int32_t Lt, const float* images_dev, int64_t n_img, const int32_t* img_index_dev, float* lang_dev,
                                        float* visn_dev, void* stream) {
+  DevGuard dev_guard__(m);
   MSQ_REQUIRE(m && ids_dev && tt_dev && mask_dev, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   MSQ_TRY(ensure_train(m, st));
@@ -431,6 +458,7 @@ extern "C" int msq_inner_forward_train(msq_model* m, const int64_t* ids_dev, con
 }
 
 extern "C" int msq_inner_backward(msq_model* m, const float* d_lang_dev, const float* d_visn_dev, float* grads_dev, void* stream) {
+  DevGuard dev_guard__(m);
   MSQ_REQUIRE(m && grads_dev, "null argument");
   MSQ_REQUIRE(((uintptr_t)grads_dev & 255) == 0, "msq_inner_backward: the gradient buffer must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -440,6 +468,7 @@ extern "C" int msq_inner_backward(msq_model* m, const float* d_lang_dev, const f
 
 extern "C" int msq_adamw_step(msq_model* m, const float* grads_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
                               float max_grad_norm, float grad_scale, float* norm_out_dev, void* stream) {
+  DevGuard dev_guard__(m);
   MSQ_REQUIRE(m && grads_dev, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   MSQ_TRY(ensure_train(m, st));
@@ -473,10 +502,36 @@ extern "C" int msq_adamw_step(msq_model* m, const float* grads_dev, float lr, fl
   return heads_train_setup(m, false, st);
 }
 
+// head parameters are the tail of the slot table (added after the encoder's); their gradients are final once heads_train returns
+static int mark_heads_ready(msq_model* m, cudaStream_t st) {
+  TrainState* ts = m->train;
+  ts->ready_used = 0;
+  const std::vector<std::string> names = heads_param_names(m);
+  if (names.empty()) return MSQ_OK;
+  return mark_ready(ts, names.front(), names.back(), st);   // slots were added in this order: first .. last are contiguous
+}
+
+/* Gradient-ready regions of the last msq_train_step, in completion order (see TrainState::ready_ev): count, the element
+ * range of region i, and "make `stream` wait until region i is final". */
+extern "C" int64_t msq_train_ready_count(msq_model* m) { return (m && m->train) ? (int64_t)m->train->ready_used : 0; }
+extern "C" int msq_train_ready_info(msq_model* m, int64_t i, int64_t* begin, int64_t* end) {
+  MSQ_REQUIRE(m && m->train && i >= 0 && (size_t)i < m->train->ready_used && begin && end, "msq_train_ready_info: bad index");
+  *begin = m->train->ready_rng[i].first;
+  *end = m->train->ready_rng[i].second;
+  return MSQ_OK;
+}
+extern "C" int msq_train_ready_wait(msq_model* m, int64_t i, void* stream) {
+  DevGuard dev_guard__(m);
+  MSQ_REQUIRE(m && m->train && i >= 0 && (size_t)i < m->train->ready_used, "msq_train_ready_wait: bad index");
+  MSQ_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, m->train->ready_ev[i], 0));
+  return MSQ_OK;
+}
+
 extern "C" int msq_train_step(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, const int64_t* mask_dev, const int64_t* sep_dev,
                               int64_t B, int32_t N, int32_t Lt, const float* images_dev, int64_t n_img, const int32_t* img_index_dev,
                               const int32_t* ground_truth_dev, const int64_t* pairwise_labels_dev, float lam, float* grads_dev, float* loss_dev,
                               void* stream) {
+  DevGuard dev_guard__(m);
   MSQ_REQUIRE(m && ids_dev && tt_dev && mask_dev && sep_dev && ground_truth_dev && pairwise_labels_dev && grads_dev, "null argument");
   MSQ_REQUIRE(((uintptr_t)grads_dev & 255) == 0, "msq_train_step: the gradient buffer must be 256-byte aligned");
   MSQ_REQUIRE(B >= 1 && N >= 2 && N <= 16, "msq_train_step: B=%lld N=%d", (long long)B, N);
@@ -488,9 +543,11 @@ extern "C" int msq_train_step(msq_model* m, const int64_t* ids_dev, const int64_
   if (m->cfg.precise) {
     MSQ_TRY(forward_train<float>(m, ids_dev, tt_dev, mask_dev, R, Lt, images_dev, n_img, img_index_dev, nullptr, nullptr, st));
     MSQ_TRY(heads_train<float>(m, sep_dev, B, N, ground_truth_dev, pairwise_labels_dev, lam, grads_dev, loss_dev, st));
+    MSQ_TRY(mark_heads_ready(m, st));
     return backward_train<float>(m, m->train->ht.d_lang, nullptr, grads_dev, st);
   }
   MSQ_TRY(forward_train<bf16>(m, ids_dev, tt_dev, mask_dev, R, Lt, images_dev, n_img, img_index_dev, nullptr, nullptr, st));
   MSQ_TRY(heads_train<bf16>(m, sep_dev, B, N, ground_truth_dev, pairwise_labels_dev, lam, grads_dev, loss_dev, st));
+  MSQ_TRY(mark_heads_ready(m, st));
   return backward_train<bf16>(m, m->train->ht.d_lang, nullptr, grads_dev, st);
 }

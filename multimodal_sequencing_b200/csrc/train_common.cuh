@@ -74,11 +74,18 @@ struct TrainState {
   Arena htape;
   HeadTape ht;
   SplitK splitk;
+  // ---- gradient-ready events of the last backward pass, in the order the regions of the flat buffer become final
+  // (heads, BERT layers top -> bottom, embeddings, visn_fc, ViT blocks top -> bottom, ViT stem): a data-parallel caller
+  // all-reduces region i on a side stream as soon as event i has fired, overlapping the rest of the backward pass
+  std::vector<cudaEvent_t> ready_ev;
+  std::vector<std::pair<int64_t, int64_t>> ready_rng;   // [begin, end) element offsets
+  size_t ready_used = 0;
 };
 
 inline void train_state_free_impl(TrainState* ts) {
   if (!ts) return;
   for (void* p : ts->owned) cudaFree(p);
+  for (cudaEvent_t e : ts->ready_ev) cudaEventDestroy(e);
   if (ts->adam_m) cudaFree(ts->adam_m);
   if (ts->adam_v) cudaFree(ts->adam_v);
   if (ts->opt_scratch) cudaFree(ts->opt_scratch);

@@ -732,11 +732,7 @@ int heads_train(msq_model* m, const int64_t* sep, int64_t B, int N, const int32_
   MSQ_CUDA(cudaMemsetAsync(dkey0, 0, (size_t)M * H * sizeof(float), st));
   MSQ_CUDA(cudaMemsetAsync(dt4, 0, (size_t)C2 * 4 * H * sizeof(float), st));
   const float scale = 1.0f / (((float)N + 1e-20f - 1.f) * (float)B);
-  static bool tf_configured = false;
-  if (!tf_configured) {
-    MSQ_CUDA(cudaFuncSetAttribute(tf_pointer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)TH_MAXN * 1024 * sizeof(float))));
-    tf_configured = true;
-  }
+  MSQ_SMEM_ATTR((int)((size_t)TH_MAXN * 1024 * sizeof(float)), tf_pointer_kernel);
   MSQ_CUDA(launch_k(tf_pointer_kernel, dim3((unsigned)B), dim3(256), (size_t)N * H * sizeof(float), st, (const float*)h.query, (const float*)h.t4,
                     (const float*)h.key, target, m->dec.wt, m->dec.bt, N, H, scale, h.nll, dquery, dkey0, dt4, part));
   MSQ_LAUNCH_CHECK();

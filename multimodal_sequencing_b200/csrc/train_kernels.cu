@@ -719,16 +719,8 @@ int attention_bwd(const T* qkv, const T* dctx, int64_t R, int L, int heads, floa
   float* dsum = scratch + (size_t)R * heads * L;
   const size_t smem1 = sizeof(float) * ((size_t)2 * L * 65 + Lpad + 2 * AB_WARPS * AB_D + (size_t)AB_WARPS * Lpad);
   const size_t smem2 = sizeof(float) * ((size_t)2 * L * 65 + 2 * Lpad + 2 * AB_WARPS * AB_D + (size_t)2 * AB_WARPS * Lpad);
-  static size_t conf1[2] = {0, 0}, conf2[2] = {0, 0};
-  const int ti = sizeof(T) == 4 ? 0 : 1;
-  if (smem1 > conf1[ti]) {
-    MSQ_CUDA(cudaFuncSetAttribute(attention_bwd_dq_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    conf1[ti] = smem1;
-  }
-  if (smem2 > conf2[ti]) {
-    MSQ_CUDA(cudaFuncSetAttribute(attention_bwd_dkv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    conf2[ti] = smem2;
-  }
+  MSQ_SMEM_ATTR(smem1, attention_bwd_dq_kernel<T>);
+  MSQ_SMEM_ATTR(smem2, attention_bwd_dkv_kernel<T>);
   MSQ_CUDA(launch_k(attention_bwd_dq_kernel<T>, dim3((unsigned)(R * heads)), dim3(AB_WARPS * 32), smem1, st, qkv, dctx, L, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, lse, dsum));
   MSQ_LAUNCH_CHECK();
   MSQ_CUDA(launch_k(attention_bwd_dkv_kernel<T>, dim3((unsigned)(R * heads)), dim3(AB_WARPS * 32), smem2, st, qkv, dctx, L, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, (const float*)lse, (const float*)dsum));

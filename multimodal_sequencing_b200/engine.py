@@ -435,6 +435,49 @@ class OrderingEngine:
                                                        self._p(perm_out), self._stream()))
         return perm_out
 
+    def expand_pairs_device(self, input_ids, n_steps, cls_id=101, sep_id=102, pad_id=0, with_images=True):
+        """prepare_berson_inputs' pair expansion on the DEVICE (msq_scan_steps + msq_expand_pairs): token rows [B,L] ->
+        (input_ids, attention_mask, token_type_ids [B,P,Lt], sep_positions [B,P,2], img_index [B,P,2] int32), all on device.
+        Bit-identical to prepare_pairs (process_inputs_for_berson.py:113-368)."""
+        ids = torch.as_tensor(input_ids).to(self.device, torch.long).contiguous()
+        B, L = ids.shape
+        N, P = n_steps, n_steps * (n_steps - 1)
+        starts = torch.empty(B, N, dtype=torch.int32, device=self.device)
+        lens = torch.empty(B, N, dtype=torch.int32, device=self.device)
+        meta = torch.empty(2, dtype=torch.int32, device=self.device)
+        lt = C.c_int32(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.msq_scan_steps(self._p(ids), B, L, N, cls_id, sep_id, self._p(starts), self._p(lens), self._p(meta),
+                                               C.byref(lt), self._stream()))
+            Lt = int(lt.value)
+            out = [torch.empty(B, P, Lt, dtype=torch.long, device=self.device) for _ in range(3)]
+            sep = torch.empty(B, P, 2, dtype=torch.long, device=self.device)
+            idx = torch.empty(B, P, 2, dtype=torch.int32, device=self.device) if with_images else None
+            _lib.check(self.lib.msq_expand_pairs(self._p(ids), B, L, N, Lt, cls_id, pad_id, self._p(starts), self._p(lens),
+                                                 self._p(out[0]), self._p(out[1]), self._p(out[2]), self._p(sep), self._p(idx),
+                                                 self._stream()))
+        return out[0], out[1], out[2], sep, idx
+
+    def order_raw_host(self, input_ids, images, n_steps, beam, perm_out=None, cls_id=101, sep_id=102, pad_id=0):
+        """berson_pointer_network from the DataLoader tuple: token rows [B,L] int64 and step images [B,N,3,S,S] fp32 in HOST
+        memory (pinned for full H2D bandwidth) -> permutations [B,N] int32 (host).  Pair expansion, H2D and D2H all happen
+        inside this call (msq_order_manuals_raw_host); synchronous."""
+        ids = torch.as_tensor(input_ids)
+        if ids.dtype != torch.long or not ids.is_contiguous() or ids.is_cuda:
+            ids = ids.cpu().to(torch.long).contiguous()
+        B, L = ids.shape
+        if images is not None:
+            if images.dtype != torch.float32 or not images.is_contiguous() or images.is_cuda:
+                images = images.cpu().float().contiguous()
+            if images.shape[0] * (images.shape[1] if images.dim() == 5 else 1) != B * n_steps:
+                raise ValueError("images must hold one image per step: [B,N,3,S,S] or [B*N,3,S,S]")
+        if perm_out is None:
+            perm_out = torch.empty(B, n_steps, dtype=torch.int32).pin_memory()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.msq_order_manuals_raw_host(self._h, self._p(ids), B, L, n_steps, cls_id, sep_id, pad_id,
+                                                           self._p(images), beam, self._p(perm_out), self._stream()))
+        return perm_out
+
     def order(self, input_ids, labels, n_steps, beam, images=None, cls_id=101, sep_id=102, pad_id=0):
         """berson_pointer_network for a batch of manuals: list of permutations (python ints)."""
         batch = prepare_pairs(input_ids, labels, n_steps, images, cls_id, sep_id, pad_id).to(self.device)

@@ -43,3 +43,76 @@ def allreduce_gradients(flat_grads, group=None):
     if world > 1:
         dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
     return 1.0 / world
+
+
+class GradientReducer:
+    """Bucketed gradient all-reduce overlapped with the backward pass (what DistributedDataParallel does for the reference,
+    trainers/train.py:217-221).  msq_train_step records a CUDA event per region of the flat gradient buffer when that region
+    is final (heads, BERT layers top -> bottom, embeddings, visn_fc, ViT blocks top -> bottom, ViT stem); regions are merged
+    into buckets of >= bucket_mb, and each bucket is all-reduced (NCCL, SUM) on a side stream that waits for the bucket's
+    last event only -- the host has enqueued the whole step long before the GPU has executed it, so the collectives run
+    under the rest of the backward pass.  `allreduce()` returns 1 / world for adamw_step(grad_scale=...).
+
+    Falls back to one all-reduce of the whole buffer if the regions do not cover every parameter slot."""
+
+    def __init__(self, engine, flat_grads, bucket_mb=64, group=None):
+        self.eng, self.flat, self.group = engine, flat_grads, group
+        self.bucket_elems = int(bucket_mb * (1 << 20) // 4)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.side = torch.cuda.Stream(device=flat_grads.device) if flat_grads.is_cuda else None
+        self.n_buckets = 1
+        self._plan = None
+
+    def _regions(self):
+        import ctypes as C
+        lib, h = self.eng.lib, self.eng._h
+        out = []
+        for i in range(int(lib.msq_train_ready_count(h))):
+            b, e = C.c_int64(), C.c_int64()
+            if lib.msq_train_ready_info(h, i, C.byref(b), C.byref(e)) != 0:
+                return None
+            out.append((int(b.value), int(e.value)))
+        return out
+
+    def _make_plan(self):
+        regions = self._regions()
+        if not regions:
+            return None
+        # every parameter slot must lie inside a region
+        for _, off, numel, _ in self.eng.train_layout():
+            if not any(b <= off and off + numel <= e for b, e in regions):
+                return None
+        plan, cur = [], None   # bucket = [begin, end, index of its last region]
+        for i, (b, e) in enumerate(regions):
+            if cur is not None and (b == cur[1] or e == cur[0] or abs(b - cur[1]) < 1024 or abs(cur[0] - e) < 1024):
+                cur = [min(cur[0], b), max(cur[1], e), i]
+            else:
+                if cur is not None:
+                    plan.append(tuple(cur))
+                cur = [b, e, i]
+            if cur[1] - cur[0] >= self.bucket_elems:
+                plan.append(tuple(cur))
+                cur = None
+        if cur is not None:
+            plan.append(tuple(cur))
+        return plan
+
+    def allreduce(self):
+        if self.world == 1:
+            return 1.0
+        if self._plan is None:
+            self._plan = self._make_plan() or False
+            self.n_buckets = len(self._plan) if self._plan else 1
+        if not self._plan or self.side is None:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            return 1.0 / self.world
+        import ctypes as C
+        lib, h = self.eng.lib, self.eng._h
+        works = []
+        for b, e, last in self._plan:
+            lib.msq_train_ready_wait(h, last, C.c_void_p(self.side.cuda_stream))
+            with torch.cuda.stream(self.side):
+                works.append(dist.all_reduce(self.flat[b:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for w in works:
+            w.wait()     # the compute stream waits for the collectives; the host does not block
+        return 1.0 / self.world

@@ -597,3 +597,60 @@ def test_roberta_style_token_types_and_ragged_batch():
     rob = ids.clone().masked_fill(ids == 0, 1).masked_fill(ids == 101, 0)   # <s> = 0, <pad> = 1
     pb = eng.prepare(rob, labels, 5, cls_id=0, sep_id=102, pad_id=1)
     assert int(pb.token_type_ids.sum()) == 0 and int((pb.input_ids == 0).sum()) == 2 * 20 * len(labels)
+
+
+# ---------------------------------------------------------------------------------------------
+# device-side pair expansion and the DataLoader-tuple entry point
+# ---------------------------------------------------------------------------------------------
+
+def test_device_pair_expansion_bit_exact_vs_host(golden_dir):
+    """msq_scan_steps + msq_expand_pairs against prepare_pairs (itself pinned bit-exactly to the reference's dict in
+    tests/test_host_cpu.py): ragged manuals, N in {2..10}, BERT and RoBERTa special ids."""
+    from multimodal_sequencing_b200.engine import prepare_pairs
+    g = torch.load(os.path.join(golden_dir, "text_tiny.pt"), weights_only=False)
+    eng = _engine(g["sd"], _cfg_from_golden(g), True)
+    gen = torch.Generator().manual_seed(5)
+    cases = [(c["ids"], c["labels"], c["N"], 101, 102, 0) for c in g["cases"]]
+    for N in (2, 3, 7, 10, 16):
+        B = 5
+        rows, L = [], 0
+        for b in range(B):
+            toks = []
+            for i in range(N):
+                n = int(torch.randint(1, 30, (1,), generator=gen))
+                toks += [0] + torch.randint(1000, 2000, (n,), generator=gen).tolist() + [2]
+            rows.append(toks)
+            L = max(L, len(toks))
+        ids = torch.tensor([r + [1] * (L + 3 - len(r)) for r in rows])      # RoBERTa: <s>=0 </s>=2 <pad>=1
+        labels = torch.stack([torch.randperm(N, generator=gen) for _ in range(B)])
+        cases.append((ids, labels, N, 0, 2, 1))
+    for ids, labels, N, cls_id, sep_id, pad_id in cases:
+        want = prepare_pairs(ids, labels, N, None, cls_id, sep_id, pad_id)
+        got = eng.expand_pairs_device(ids, N, cls_id, sep_id, pad_id)
+        assert torch.equal(got[0].cpu(), want.input_ids)
+        assert torch.equal(got[1].cpu(), want.attention_mask)
+        assert torch.equal(got[2].cpu(), want.token_type_ids)
+        assert torch.equal(got[3].cpu(), want.sep_positions)
+        B, P = want.input_ids.shape[:2]
+        pi = want.pairs_list[0]
+        assert torch.equal(got[4].cpu().long(), torch.arange(B)[:, None, None] * N + pi[None])
+    bad = cases[0][0].clone()
+    bad[0, 0] = 7   # drop a [CLS]
+    with pytest.raises(RuntimeError):
+        eng.expand_pairs_device(bad, cases[0][2])
+
+
+@pytest.mark.parametrize("precise", [True, "bf16x3"])
+def test_order_raw_host_equals_prepared_path(precise):
+    """the DataLoader-tuple entry point (raw token rows + step images from host memory, expansion on the device, images streamed
+    per micro-batch) returns exactly what the prepared-batch paths return, across a micro-batch boundary."""
+    cfg = _full_cfg(True)
+    sd = synth.full_state_dict(cfg, cfg["vit"], seed=0)
+    eng = _engine(sd, cfg, precise)
+    N, W, B = 5, 4, 35
+    ids, labels, images = O.synthetic_manuals(B, N, 64, image_px=224, seed=12)
+    want = eng.order(ids, labels, N, W, images)
+    got = eng.order_raw_host(ids.pin_memory(), images.pin_memory(), N, W)
+    assert got.tolist() == want
+    assert eng.order_raw_host(ids, images, N, W).tolist() == want          # pageable buffers work too
+    assert eng.order_raw_host(ids[:1], images[:1], N, W).tolist() == want[:1]
