@@ -85,6 +85,13 @@ int msq_model_set_weight(msq_model* m, const char* name, const float* data_dev, 
  * Fails with the list of missing keys if the state_dict was incomplete. */
 int msq_model_pack(msq_model* m, void* stream);
 
+/* In-place refresh for callers that keep the fp32 masters themselves (the reference trainer's optimizer updates
+ * nn.Parameter.data, which no version counter sees): overwrite the registered copy of `name` (same element count; no
+ * allocation), then msq_model_refresh re-derives every packed copy (fused QKV, bf16 / split-bf16, folded LayerNorm, LSTM
+ * repacks, and the training state's W^T operands).  ~1 GB of device-to-device copies + the pack kernels: a few ms. */
+int msq_model_update_weight(msq_model* m, const char* name, const float* data_dev, int64_t numel, void* stream);
+int msq_model_refresh(msq_model* m, void* stream);
+
 /* ---- encoders -------------------------------------------------------------------------------
  * msq_vit_forward       CLIP VisualTransformer.forward, pair-joint variant, skip_last_layer=True
  *                       (models/CLIP/clip/model.py:262-305).  images_dev [n_img,3,S,S] fp32 are UNIQUE

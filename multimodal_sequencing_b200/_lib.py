@@ -33,6 +33,8 @@ SIGNATURES = {
     "msq_model_destroy": (None, [_P]),
     "msq_model_set_weight": (C.c_int, [_P, C.c_char_p, _P, _I64, _P]),
     "msq_model_pack": (C.c_int, [_P, _P]),
+    "msq_model_update_weight": (C.c_int, [_P, C.c_char_p, _P, _I64, _P]),
+    "msq_model_refresh": (C.c_int, [_P, _P]),
     "msq_vit_forward": (C.c_int, [_P, _P, _I64, _P, _I64, _P, _P]),
     "msq_inner_forward": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _I64, _P, _P, _P, _P, _P]),
     "msq_encode": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, C.POINTER(MsqEncodeOut), _P]),

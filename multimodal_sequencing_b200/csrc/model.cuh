@@ -132,5 +132,6 @@ struct DevGuard {
   ~DevGuard() { if (sw) cudaSetDevice(prev); }
 };
 int model_repack(msq_model* m, cudaStream_t st);   // api.cu
+int model_weights_changed(msq_model* m, cudaStream_t st);   // train.cu: repack + training-state operand copies
 bool model_use_tc(const msq_model* m);             // api.cu: tcgen05 path selected for this model / device
 }  // namespace msq

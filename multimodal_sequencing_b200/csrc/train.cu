@@ -496,10 +496,36 @@ extern "C" int msq_adamw_step(msq_model* m, const float* grads_dev, float lr, fl
                              ts->opt_scratch, st));
   if (norm_out_dev) MSQ_CUDA(cudaMemcpyAsync(norm_out_dev, ts->opt_scratch, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // masters changed: rebuild the packed copies (fused QKV, bf16, folded LayerNorm, ...) and the W^T operands
+  return msq::model_weights_changed(m, st);
+}
+
+// every derived copy of the fp32 masters: packed inference weights, and (when a training state exists) the W^T operands
+int msq::model_weights_changed(msq_model* m, cudaStream_t st) {
   MSQ_TRY(model_repack(m, st));
+  TrainState* ts = m->train;
+  if (!ts) return MSQ_OK;
   if (m->cfg.precise) MSQ_TRY(refresh_wT<float>(m, ts, st));
   else MSQ_TRY(refresh_wT<bf16>(m, ts, st));
-  return heads_train_setup(m, false, st);
+  return ts->heads ? heads_train_setup(m, false, st) : MSQ_OK;
+}
+
+/* In-place weight refresh for callers that own the fp32 masters themselves (the unchanged reference trainer: its optimizer
+ * updates nn.Parameter.data): msq_model_update_weight overwrites the registered copy of `name` (same element count, device
+ * -> device, no allocation), msq_model_refresh re-derives every packed copy afterwards.  Nothing is rebuilt or reallocated. */
+extern "C" int msq_model_update_weight(msq_model* m, const char* name, const float* data_dev, int64_t numel, void* stream) {
+  DevGuard dev_guard__(m);
+  MSQ_REQUIRE(m && name && data_dev, "bad argument");
+  auto it = m->raw.find(name);
+  MSQ_REQUIRE(it != m->raw.end(), "msq_model_update_weight: %s was never registered", name);
+  MSQ_REQUIRE(it->second.second == numel, "msq_model_update_weight: %s has %lld elements, got %lld", name,
+              (long long)it->second.second, (long long)numel);
+  MSQ_CUDA(cudaMemcpyAsync(it->second.first, data_dev, numel * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return MSQ_OK;
+}
+extern "C" int msq_model_refresh(msq_model* m, void* stream) {
+  DevGuard dev_guard__(m);
+  MSQ_REQUIRE(m && m->packed, "msq_model_refresh: model not packed");
+  return msq::model_weights_changed(m, (cudaStream_t)stream);
 }
 
 // head parameters are the tail of the slot table (added after the encoder's); their gradients are final once heads_train returns

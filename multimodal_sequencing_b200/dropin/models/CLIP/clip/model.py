@@ -8,6 +8,7 @@ import torch
 import torch.nn as nn
 
 from multimodal_sequencing_b200.engine import OrderingEngine
+from multimodal_sequencing_b200.dropin._owner import owned_engine
 
 
 class LayerNorm(nn.LayerNorm):
@@ -61,17 +62,11 @@ class VisualTransformer(nn.Module):
                     vision_width=self.width, vision_patch_size=self.patch_size)
 
     def _engine(self):
-        sig = tuple(p._version for p in self.parameters()) + (getattr(self, "precise", False),)
-        if self.__dict__.get("_eng") is None or self.__dict__.get("_eng_sig") != sig:
-            dev = self.conv1.weight.device
-            if dev.type != "cuda":
-                raise RuntimeError("the B200 path has no CPU fallback: move the model to a CUDA device first")
-            cfg = dict(hidden_size=self.width, num_hidden_layers=0, num_attention_heads=self.width // 64,
-                       intermediate_size=4 * self.width, vocab_size=1, max_position_embeddings=1, vit=self.vit_config())
-            sd = {"bert.encoder.visual_model.visual." + k: v for k, v in self.state_dict().items()}
-            self.__dict__["_eng"] = OrderingEngine(sd, cfg, device=dev, precise=getattr(self, "precise", False))
-            self.__dict__["_eng_sig"] = sig
-        return self.__dict__["_eng"]
+        return owned_engine(self, lambda: dict(hidden_size=self.width, num_hidden_layers=0, num_attention_heads=self.width // 64,
+                                               intermediate_size=4 * self.width, vocab_size=1, max_position_embeddings=1,
+                                               vit=self.vit_config()),
+                            lambda: {"bert.encoder.visual_model.visual." + k: v for k, v in self.state_dict().items()},
+                            self.conv1.weight.device)
 
     def forward(self, x, skip_last_layer=False, text_embedding=None, text_mask=None, img_len=None):
         if not skip_last_layer or text_embedding is not None:
@@ -149,18 +144,10 @@ class ModifiedResNet(nn.Module):
                     vision_width=self.width)
 
     def _engine(self):
-        tensors = list(self.parameters()) + list(self.buffers())
-        sig = tuple(t._version for t in tensors) + (getattr(self, "precise", False),)
-        if self.__dict__.get("_eng") is None or self.__dict__.get("_eng_sig") != sig:
-            dev = self.conv1.weight.device
-            if dev.type != "cuda":
-                raise RuntimeError("the B200 path has no CPU fallback: move the model to a CUDA device first")
-            cfg = dict(hidden_size=128, num_hidden_layers=0, num_attention_heads=2, intermediate_size=512, vocab_size=1,
-                       max_position_embeddings=1, rn=self.rn_config())
-            sd = {"bert.encoder.visual_model.visual." + k: v for k, v in self.state_dict().items()}
-            self.__dict__["_eng"] = OrderingEngine(sd, cfg, device=dev, precise=getattr(self, "precise", False))
-            self.__dict__["_eng_sig"] = sig
-        return self.__dict__["_eng"]
+        return owned_engine(self, lambda: dict(hidden_size=128, num_hidden_layers=0, num_attention_heads=2, intermediate_size=512,
+                                               vocab_size=1, max_position_embeddings=1, rn=self.rn_config()),
+                            lambda: {"bert.encoder.visual_model.visual." + k: v for k, v in self.state_dict().items()},
+                            self.conv1.weight.device)
 
     def forward(self, x, skip_last_layer=False, text_embedding=None, text_mask=None, img_len=None):
         if skip_last_layer or text_embedding is not None:

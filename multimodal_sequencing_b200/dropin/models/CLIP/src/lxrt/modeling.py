@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 
 from multimodal_sequencing_b200.engine import OrderingEngine
+from multimodal_sequencing_b200.dropin._owner import owned_engine
 from models.berson.modeling_bert import _bert_layer, _holder, _init_bert_weights
 from models.CLIP.clip.model import CLIP
 
@@ -127,20 +128,16 @@ class LXRTModel(nn.Module):
         torch.save(model_to_save.state_dict(), os.path.join(save_directory, "pytorch_model.bin"))
 
     def _engine(self):
-        sig = tuple(t._version for t in list(self.parameters()) + list(self.buffers())) + (getattr(self, "precise", False),)
-        if self.__dict__.get("_eng") is None or self.__dict__.get("_eng_sig") != sig:
-            dev = self.pooler.dense.weight.device
-            if dev.type != "cuda":
-                raise RuntimeError("the B200 path has no CPU fallback: move the model to a CUDA device first")
+        def make_config():
             c = self.config
             cfg = dict(hidden_size=c.hidden_size, num_hidden_layers=c.num_hidden_layers, num_attention_heads=c.num_attention_heads,
                        intermediate_size=c.intermediate_size, vocab_size=c.vocab_size,
                        max_position_embeddings=c.max_position_embeddings, type_vocab_size=c.type_vocab_size)
             cfg["rn" if self.is_resnet else "vit"] = self.vit_config
-            sd = {"bert." + k: v for k, v in self.state_dict().items()}
-            self.__dict__["_eng"] = OrderingEngine(sd, cfg, device=dev, precise=getattr(self, "precise", False))
-            self.__dict__["_eng_sig"] = sig
-        return self.__dict__["_eng"]
+            return cfg
+        # built once; parameter values are pushed in place (dropin/_owner.py)
+        return owned_engine(self, make_config, lambda: {"bert." + k: v for k, v in self.state_dict().items()},
+                            self.pooler.dense.weight.device)
 
     def forward(self, input_ids, token_type_ids=None, attention_mask=None, visual_feats=None, visual_attention_mask=None,
                 pretraining_objective=None, labels=None):

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from multimodal_sequencing_b200.engine import OrderingEngine, PairBatch
+from multimodal_sequencing_b200.dropin._owner import mark_dirty, owned_engine
 from .process_inputs_for_berson import prepare_berson_inputs
 from .generator import Beam
 
@@ -77,7 +78,7 @@ def _init_bert_weights(module, std):
 
 
 class _EngineOwner:
-    """Lazily (re)builds the packed device model whenever a parameter changed (version counters)."""
+    """Owns the packed device model: built once, its weights refreshed in place (never rebuilt because values changed)."""
 
     def _engine_config(self):
         raise NotImplementedError
@@ -86,17 +87,12 @@ class _EngineOwner:
         return self.state_dict()
 
     def engine(self):
-        tensors = list(self.parameters()) + list(self.buffers())   # buffers: BatchNorm statistics of the ResNet tower
-        sig = tuple(t._version for t in tensors) + (tuple(id(t) for t in tensors), getattr(self, "precise", False))
-        eng = self.__dict__.get("_eng")
-        if eng is None or self.__dict__.get("_eng_sig") != sig:
-            dev = next(self.parameters()).device
-            if dev.type != "cuda":
-                raise RuntimeError("the B200 path has no CPU fallback: move the model to a CUDA device first")
-            eng = OrderingEngine(self._engine_state(), self._engine_config(), device=dev,
-                                 precise=getattr(self, "precise", False))
-            self.__dict__["_eng"], self.__dict__["_eng_sig"] = eng, sig
-        return eng
+        # built once; parameter VALUES are pushed in place (see dropin/_owner.py for when)
+        return owned_engine(self, self._engine_config, self._engine_state, next(self.parameters()).device)
+
+    def mark_dirty(self):
+        """parameter values were changed behind the module's back in eval mode (`p.data` edits): re-upload before the next call"""
+        mark_dirty(self)
 
 
 class _DeviceBackward(torch.autograd.Function):
@@ -373,6 +369,7 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
         if flat is None or flat.device != eng.device or flat.numel() != eng.new_grad_buffer().numel():
             flat = self.__dict__["_flat"] = eng.new_grad_buffer()
         flat.zero_()
+        self.__dict__["_lib_masters"] = True   # from here on the library's fp32 masters are the truth (until pull_weights)
         with torch.no_grad():
             loss = eng.train_step(pb, flat, self.pairwise_loss_lam)
             scale = allreduce_gradients(flat) if allreduce else 1.0
@@ -386,10 +383,10 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
             for n, p in self.named_parameters():
                 if any(n == k for k, _, _, _ in eng.train_layout()):
                     p.data.copy_(eng.read_param(n, tuple(p.shape)))
-        # the copies bumped the version counters: keep the packed model (it already holds these values)
+        # both sides hold the same values again: the nn.Parameters are the masters from here on
         tensors = list(self.parameters()) + list(self.buffers())
-        self.__dict__["_eng_sig"] = tuple(t._version for t in tensors) + (tuple(id(t) for t in tensors),
-                                                                          getattr(self, "precise", False))
+        self.__dict__["_eng_vers"] = tuple((t._version, t.data_ptr()) for t in tensors)
+        self.__dict__["_lib_masters"], self.__dict__["_eng_dirty"] = False, False
 
     def _forward(self, input_ids, attention_mask=None, token_type_ids=None, pairs_list=None, passage_length=None,
                  pairs_num=None, sep_positions=None, ground_truth=None, mask_cls=None, pairwise_labels=None, cuda=None,

@@ -51,10 +51,18 @@ class PairBatch:
     def Lt(self):
         return self.input_ids.shape[2]
 
-    def to(self, device, non_blocking=False):
+    _DTYPES = dict(images=torch.float32, img_index=torch.int32)
+
+    def to(self, device=None, non_blocking=False):
+        """Move to `device` (None: stay) AND canonicalise what the kernels read through raw pointers: int64 ids / masks /
+        token types / sep positions / labels, int32 img_index, fp32 images, all contiguous (a sliced or transposed view or an
+        int32 id tensor would otherwise be misread silently).  Tensors already in that form are passed through untouched."""
         kw = {}
         for k, v in self.__dict__.items():
-            kw[k] = v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v
+            if torch.is_tensor(v):
+                v = v.to(device=device if device is not None else v.device, dtype=self._DTYPES.get(k, torch.long),
+                         non_blocking=non_blocking).contiguous()
+            kw[k] = v
         return PairBatch(**kw)
 
     def reference_dict(self, materialize_images=True):
@@ -177,6 +185,27 @@ class OrderingEngine:
                 _lib.check(self.lib.msq_model_set_weight(self._h, k.encode(), t.data_ptr(), t.numel(), st))
             torch.cuda.synchronize(self.device)
             _lib.check(self.lib.msq_model_pack(self._h, st))
+
+    def refresh_weights(self, state_dict, inner_prefix="bert."):
+        """Overwrite the registered fp32 masters IN PLACE with the tensors of `state_dict` (same keys / shapes as at
+        construction) and re-derive every packed copy -- no model rebuild, no allocation.  For trainers that update
+        nn.Parameter.data themselves (transformers.AdamW 3.4 / models/berson/optimization.py do): call it before the next
+        forward.  Returns the number of tensors uploaded."""
+        n = 0
+        with torch.cuda.device(self.device):
+            st = self._stream()
+            for k, v in state_dict.items():
+                if not torch.is_tensor(v) or not v.is_floating_point() or any(d in k for d in _DEAD):
+                    continue
+                if inner_prefix != "bert." and k.startswith(inner_prefix):
+                    k = "bert." + k[len(inner_prefix):]
+                t = v.detach()
+                if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                    t = t.to(self.device, torch.float32).contiguous()
+                _lib.check(self.lib.msq_model_update_weight(self._h, k.encode(), t.data_ptr(), t.numel(), st))
+                n += 1
+            _lib.check(self.lib.msq_model_refresh(self._h, st))
+        return n
 
     def __del__(self):
         try:
@@ -411,7 +440,7 @@ class OrderingEngine:
 
     def order_device(self, batch: PairBatch, beam):
         """encode + beam search on device-resident inputs; returns perm [B,N] int32 (device, async)."""
-        b = batch
+        b = batch.to(self.device)
         B, P, Lt = b.input_ids.shape
         perm = torch.empty(B, b.n_steps, dtype=torch.int32, device=self.device)
         n_img = 0 if b.images is None else b.images.shape[0]
@@ -423,7 +452,9 @@ class OrderingEngine:
 
     def order_host(self, batch: PairBatch, beam, perm_out=None):
         """Whole path from HOST (ideally pinned) buffers, H2D and D2H included; synchronous."""
-        b = batch
+        b = batch.to(None)       # canonical dtypes / contiguity, stays in host memory
+        if b.input_ids.is_cuda:
+            raise ValueError("order_host takes HOST buffers (use order_device for a device-resident batch)")
         B, P, Lt = b.input_ids.shape
         if perm_out is None:
             perm_out = torch.empty(B, b.n_steps, dtype=torch.int32).pin_memory()

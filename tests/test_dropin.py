@@ -121,6 +121,75 @@ def test_reference_training_loop_runs_unchanged(golden_dir):
 
 
 @pytest.mark.gpu
+def test_training_loop_with_data_updating_optimizer(golden_dir):
+    """The reference's optimizers (transformers.AdamW 3.4, trainers/train.py:185; models/berson/optimization.py:176,187) update
+    weights through `p.data.addcdiv_` / `p.data.add_`, which does NOT bump `p._version`.  The drop-in must still see every
+    update (it refreshes its packed model in place on each train-mode forward) -- and must not rebuild the model per step."""
+    import time
+    g = torch.load(os.path.join(golden_dir, "text_tiny.pt"), weights_only=False)
+    r = torch.load(os.path.join(golden_dir, "grads_tiny.pt"), weights_only=False)["text"]
+    from oracle import berson_oracle as O
+    ids, labels, _ = O.synthetic_manuals(r["B"], r["N"], r["L"], vocab=1000, seed=r["seed"])
+    model, args = _build(g, 5, 4, "cuda")
+    model.load_state_dict(g["sd"], strict=False)
+    model = model.cuda().train()
+    for mod in model.modules():
+        mod.precise = True
+    model.tokenizer = Tok()
+    inputs = {"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": labels}
+    params = [p for p in model.parameters()]
+    state = {id(p): (torch.zeros_like(p), torch.zeros_like(p)) for p in params}
+
+    def data_adamw_step(step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-6):
+        # the update rule of the vendored AdamW, written as that file writes it: in place on p.data
+        for p in params:
+            if p.grad is None:
+                continue
+            m, v = state[id(p)]
+            m.mul_(b1).add_(p.grad.data, alpha=1 - b1)
+            v.mul_(b2).addcmul_(p.grad.data, p.grad.data, value=1 - b2)
+            step_size = lr * (1 - b2 ** step) ** 0.5 / (1 - b1 ** step)
+            p.data.addcdiv_(m, v.sqrt().add_(eps), value=-step_size)
+
+    versions = [p._version for p in params]
+    losses = []
+    with torch.enable_grad():
+        for step in range(1, 5):
+            loss = model(inputs)[0]
+            loss.backward()
+            data_adamw_step(step)
+            model.zero_grad()
+            losses.append(loss.item())
+    assert [p._version for p in params] == versions, "the test optimizer must not bump version counters"
+    assert losses[-1] < losses[0] - 0.02, "stale packed weights: the loss does not move (%s)" % losses
+    assert all(abs(a - b) > 1e-7 for a, b in zip(losses, losses[1:])), losses
+    assert model.__dict__["_eng_builds"] == 1, "the packed model was rebuilt %d times" % model.__dict__["_eng_builds"]
+    assert model.__dict__["_eng_uploads"] >= 3
+    # eval after the last optimizer step: the first eval-mode call must see that step too
+    model.eval()
+    ev = model(inputs)[0].item()
+    eng = model.engine()
+    named = dict(model.named_parameters())
+    for n, _, _, _ in eng.train_layout()[:40:7]:
+        assert torch.equal(eng.read_param(n, tuple(named[n].shape)), named[n].data), n
+    assert abs(ev - eng.training_loss(eng.prepare(ids, labels, 5, None)).item()) < 1e-6
+    ups = model.__dict__["_eng_uploads"]
+    model(inputs)
+    model(inputs)
+    assert model.__dict__["_eng_uploads"] == ups, "an eval-only model must not re-upload its weights"
+    # cost of the in-place refresh on this (tiny) model: it must be a refresh, not a rebuild
+    model.train()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        model.engine()
+    torch.cuda.synchronize()
+    per = (time.perf_counter() - t0) / 5
+    print("in-place weight refresh (tiny model): %.2f ms per train-mode forward" % (per * 1e3))
+    assert model.__dict__["_eng_builds"] == 1
+
+
+@pytest.mark.gpu
 def test_validation_loss_matches_reference(golden_dir):
     """BertForOrdering._forward loss value (modeling_bert.py:943-1174) against the reference's own number."""
     g = torch.load(os.path.join(golden_dir, "text_tiny.pt"), weights_only=False)
