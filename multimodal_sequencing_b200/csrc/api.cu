@@ -1200,10 +1200,13 @@ static int run_decode(msq_model* m, const float* sents, const float* key, const 
   return beam_search(m->dec, io, st);
 }
 
-static int chunk_manuals() {
+// manuals encoded per micro-batch: MSQ_CHUNK_MANUALS, else 32 (bf16 / fp32) or 64 (bf16x3: its GEMMs are tensor-bound, so larger
+// micro-batches only shrink the tile-quantisation tails: 260 -> 270 manuals/s measured)
+static int chunk_manuals(const msq_model* m = nullptr) {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MSQ_CHUNK_MANUALS"); v = e ? atoi(e) : 32; if (v < 1) v = 1; }
-  return v;
+  if (v < 0) { const char* e = getenv("MSQ_CHUNK_MANUALS"); v = e ? atoi(e) : 0; if (v < 0) v = 0; }
+  if (v > 0) return v;
+  return (m && m->cfg.precise == 2) ? 64 : 32;
 }
 
 // Full path for B manuals.  images are UNIQUE images [n_img,3,S,S]; img_index [B*P*2] indexes them.
@@ -1211,7 +1214,7 @@ template <typename T>
 static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const int64_t* mask, const int64_t* sep, int64_t B, int N,
                     int Lt, const float* images, int64_t n_img, const int32_t* img_index, const msq_encode_out* out, int beam,
                     int32_t* perm, cudaStream_t st, const int32_t* forced = nullptr, const int64_t* pair_labels = nullptr,
-                    float lam = 0.f, float* loss_out = nullptr, const cudaEvent_t* img_ready = nullptr) {
+                    float lam = 0.f, float* loss_out = nullptr, const cudaEvent_t* img_ready = nullptr, int64_t img_chunk = 0) {
   const msq_config& c = m->cfg;
   MSQ_REQUIRE(m->packed, "msq_model_pack() has not been called");
   MSQ_REQUIRE(m->has_bert && m->has_heads, "model lacks the inner encoder or the BERSON head weights");
@@ -1224,7 +1227,7 @@ static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const i
   const int g2 = mm ? (c.vit_res / c.vit_patch) * (c.vit_res / c.vit_patch) : 0;
   const int Lv = mm ? 1 + 2 * g2 : 0, Lj = Lt + Lv;
   const int64_t R = B * P;
-  const int64_t Bc = min((int64_t)chunk_manuals(), B), Rc = Bc * P;
+  const int64_t Bc = min((int64_t)chunk_manuals(m), B), Rc = Bc * P;
 
   VitBufs vb{}; JointBufs jb{}; HeadBufs hb{};
   for (int pass = 0; pass < 2; ++pass) {
@@ -1243,8 +1246,13 @@ static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const i
   for (int64_t b0 = 0; b0 < B; b0 += Bc) {
     const int64_t bc = min(Bc, B - b0), rc = bc * P, r0 = b0 * P;
     if (mm && img_ready) {
-      MSQ_CUDA(cudaStreamWaitEvent(st, img_ready[b0 / Bc], 0));
-      MSQ_TRY(run_visual_images<T>(m, images, bc * N, vb, st, b0 * N));
+      // images arrive in upload chunks of img_chunk manuals (one event each; img_chunk divides Bc): embed each as it lands
+      const int64_t ic = img_chunk > 0 ? img_chunk : Bc;
+      for (int64_t u0 = b0; u0 < b0 + bc; u0 += ic) {
+        const int64_t uc = min(ic, b0 + bc - u0);
+        MSQ_CUDA(cudaStreamWaitEvent(st, img_ready[u0 / ic], 0));
+        MSQ_TRY(run_visual_images<T>(m, images, uc * N, vb, st, u0 * N));
+      }
     }
     MSQ_TRY((run_inner<T>(m, ids + r0 * Lt, tt + r0 * Lt, mask + r0 * Lt, rc, Lt, mm ? img_index + r0 * 2 : nullptr, vb, jb, st)));
     // ---- pooling for this chunk
@@ -1496,6 +1504,7 @@ extern "C" int msq_order_manuals_host(msq_model* m, const int64_t* ids_host, con
   MSQ_CUDA(cudaMemcpyAsync(mask, mask_host, n_tok * 8, cudaMemcpyHostToDevice, st));
   MSQ_CUDA(cudaMemcpyAsync(sep, sep_host, (size_t)R * 2 * 8, cudaMemcpyHostToDevice, st));
   const cudaEvent_t* ready = nullptr;
+  int64_t up_chunk = 0;
   if (images_host) {
     MSQ_CUDA(cudaMemcpyAsync(idx, img_index_host, (size_t)R * 2 * 4, cudaMemcpyHostToDevice, st));
     // images in manual order (row b*N+i, every pair of manual b points into [b*N, (b+1)*N)): upload them micro-batch by
@@ -1508,7 +1517,9 @@ extern "C" int msq_order_manuals_host(msq_model* m, const int64_t* ids_host, con
     }
     cudaStream_t& copy_st = m->copy_st;
     std::vector<cudaEvent_t>& evs = m->copy_evs;
-    const int64_t Bc = min((int64_t)chunk_manuals(), B);
+    const int64_t Bcm = min((int64_t)chunk_manuals(m), B);
+    const int64_t Bc = (Bcm % 16 == 0 && B > 16) ? 16 : Bcm;   // upload granularity: 16 manuals when that divides the compute micro-batch
+    up_chunk = Bc;
     const int64_t nchunks = (B + Bc - 1) / Bc;
     if (local && nchunks > 1) {
       if (!copy_st) MSQ_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
@@ -1530,7 +1541,7 @@ extern "C" int msq_order_manuals_host(msq_model* m, const int64_t* ids_host, con
   }
   auto go = [&]() -> int {
     MSQ_DISPATCH_T(m, run_path<T>(m, ids, tt, mask, sep, B, N, Lt, images_host ? img : nullptr, n_img, images_host ? idx : nullptr, nullptr,
-                                  beam, perm, st, nullptr, nullptr, 0.f, nullptr, ready));
+                                  beam, perm, st, nullptr, nullptr, 0.f, nullptr, ready, up_chunk));
   };
   MSQ_TRY(go());
   MSQ_CUDA(cudaMemcpyAsync(perm_host, perm, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
@@ -1596,7 +1607,9 @@ extern "C" int msq_order_manuals_raw_host(msq_model* m, const int64_t* ids_host,
   char* toks = carve(3 * (size_t)R * Lt_cap * 8);
   // images first on the copy stream (they are the bulk of the bytes), one event per micro-batch
   const cudaEvent_t* ready = nullptr;
-  const int64_t Bc = min((int64_t)chunk_manuals(), B), nchunks = (B + Bc - 1) / Bc;
+  const int64_t Bcm = min((int64_t)chunk_manuals(m), B);
+  const int64_t Bc = (Bcm % 16 == 0 && B > 16) ? 16 : Bcm;   // upload granularity (divides the compute micro-batch)
+  const int64_t nchunks = (B + Bc - 1) / Bc, up_chunk = Bc;
   if (images_host) {
     if (nchunks > 1) {
       if (!m->copy_st) MSQ_CUDA(cudaStreamCreateWithFlags(&m->copy_st, cudaStreamNonBlocking));
@@ -1628,7 +1641,7 @@ extern "C" int msq_order_manuals_raw_host(msq_model* m, const int64_t* ids_host,
   MSQ_TRY(expand_pairs(raw, B, L, N, Lt, cls_id, pad_id, starts, lens, ids, mask, tt, sep, images_host ? idx : nullptr, st));
   auto go = [&]() -> int {
     MSQ_DISPATCH_T(m, run_path<T>(m, ids, tt, mask, sep, B, N, Lt, images_host ? img : nullptr, n_img, images_host ? idx : nullptr, nullptr,
-                                  beam, perm, st, nullptr, nullptr, 0.f, nullptr, ready));
+                                  beam, perm, st, nullptr, nullptr, 0.f, nullptr, ready, up_chunk));
   };
   MSQ_TRY(go());
   MSQ_CUDA(cudaMemcpyAsync(perm_host, perm, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
