@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--no-extra-configs", action="store_true", help="config 1 only: do not embed short runs of configs 2-4")
     ap.add_argument("--no-parity", action="store_true", help="config 1/2: skip the fp32-path agreement check")
     ap.add_argument("--lr", type=float, default=5e-6)
+    ap.add_argument("--dropout", type=float, default=0.1, help="config 3: hidden / attention / paragraph-encoder dropout (the reference trains with 0.1)")
     ap.add_argument("--text", default="bert-base", choices=["bert-base", "roberta-large"])
     ap.add_argument("--backbone", default="vit", choices=["vit", "rn50"])
     return ap.parse_args()
@@ -125,7 +126,8 @@ def config_dict(cfg_id, per_gpu, n_gpus, backbone="vit", text="bert-base"):
     N = c["n_steps"]
     work = {1: "configs[1]: multimodal BERSON + CLIP ViT-B/32, 5 steps x 64 tokens + 224px images, beam=4, eval",
             2: "configs[2]: same model, 256 manuals in total, beam=8, data-parallel eval strong-sharded r::G",
-            3: "configs[3]: multimodal fine-tuning step (AdamW lr 5e-6 eps 1e-8 wd 0, clip 1.0) on 6-step manuals, NCCL gradient all-reduce",
+            3: "configs[3]: multimodal fine-tuning step (AdamW lr 5e-6 eps 1e-8 wd 0, clip 1.0, dropout 0.1 as the reference trains) on "
+               "6-step manuals, NCCL gradient all-reduce",
             4: "configs[4]: long-manual stress, 10-step manuals, beam=16, pointer/beam decode (pre-projections + search) from encoder outputs"}[cfg_id]
     if backbone != "vit":
         work += " [RN50 tower instead of ViT-B/32: secondary line, not the headline]"
@@ -452,6 +454,7 @@ def run_finetune(ctx, args, steps, warmup, full=True):
     pinned = type(host)(**{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.__dict__.items()})
     devb = host.to(ctx.dev)
     grads = eng.new_grad_buffer()
+    eng.set_dropout(args.dropout, args.dropout, args.dropout, seed=1234 + ctx.rank)   # every rank drops its own elements, as DDP replicas do
     h2d = sum(v.numel() * v.element_size() for v in (pinned.input_ids, pinned.token_type_ids, pinned.attention_mask, pinned.sep_positions,
                                                      pinned.images, pinned.img_index, pinned.ground_truth, pinned.pairwise_labels))
     reducer = sharding.GradientReducer(eng, grads) if ctx.world > 1 else None
@@ -477,7 +480,7 @@ def run_finetune(ctx, args, steps, warmup, full=True):
     torch.cuda.empty_cache()
     return {"value": total * steps / (ms_total / 1e3), "ms_per_step": ms_total / steps, "e2e_value": total * steps / (e2e_ms / 1e3),
             "h2d": h2d, "d2h": 4, "launches": ex["launches"], "clocks": ex["clocks"], "extra": ex, "precision": precision, "B": B,
-            "ms_total": ms_total, "loss_trajectory": traj,
+            "ms_total": ms_total, "loss_trajectory": traj, "dropout": args.dropout,
             "collective": ("NCCL all-reduce (SUM) of the flat fp32 gradient buffer in %d buckets" % reducer.n_buckets) if reducer else None}
 
 
@@ -491,6 +494,7 @@ def line_finetune(ctx, args, rec, steps, warmup):
             "e2e": {"value": rec["e2e_value"], "unit": "manuals/s", "h2d_bytes_per_step": rec["h2d"], "d2h_bytes_per_step": rec["d2h"],
                     "api": "OrderingEngine.train_step + gradient all-reduce + adamw_step from a pinned host PairBatch; the loss comes back"},
             "gpu_launches": rec["launches"], "clocks": rec["clocks"], "loss_trajectory": rec["loss_trajectory"], "collective": rec["collective"],
+            "dropout": rec["dropout"],
             "roofline": gemm_roofline(rec["extra"], steps, rec["ms_total"], pk, "msq::gemm_tc_kernel (forward, dgrad and wgrad GEMMs)",
                                       note="split-K slices of a weight gradient run concurrently on auxiliary streams: their event durations "
                                            "overlap, so `achieved` is a lower bound")}

@@ -213,6 +213,18 @@ int msq_train_step(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, 
                    int64_t B, int32_t N, int32_t Lt, const float* images_dev, int64_t n_img, const int32_t* img_index_dev,
                    const int32_t* ground_truth_dev, const int64_t* pairwise_labels_dev, float lam, float* grads_dev, float* loss_dev,
                    void* stream);
+/* Dropout of the fine-tuning path.  The reference trains with hidden_dropout_prob = attention_probs_dropout_prob = 0.1
+ * (BertConfig) and args.para_dropout in the paragraph encoder; sites: embeddings, visn_fc output, attention probabilities,
+ * attention-output and FFN-output dense (lxrt/modeling.py:369,601,419,437,491; modeling_bert.py:179,228,253,319), the
+ * token-attention probabilities of HierarchicalAttention (modeling_bert.py:735), and the paragraph encoder's attention,
+ * context and feed-forward dropouts (neural.py:228,31-32; encoder.py:28).  msq_train_set_dropout sets the three
+ * probabilities (in [0,1); 0 = off, the default) and a seed for all later training forwards.  Masks are never stored: an
+ * element is kept iff hash(seed, forward counter, site, element index) >= p * 2^32 (csrc/dropout.cuh), so the backward pass
+ * regenerates them, and a CPU checker can too (msq_train_dropout_step returns the counter of the last training forward;
+ * oracle/dropout.py is the numpy twin).  Evaluation entry points never apply dropout. */
+int msq_train_set_dropout(msq_model* m, float p_hidden, float p_attn, float p_para, uint32_t seed, void* stream);
+int64_t msq_train_dropout_step(msq_model* m);
+
 /* Data-parallel overlap: msq_train_step records one CUDA event per REGION of the flat gradient buffer at the moment that
  * region is final (BERSON heads, BERT layers top -> bottom, embeddings, visn_fc, ViT blocks top -> bottom, ViT stem).
  * msq_train_ready_count = regions of the last step, in completion order; msq_train_ready_info = element range [begin, end)

@@ -19,7 +19,7 @@ constexpr int AT_WARPS = 16;
 template <typename T>
 __global__ void __launch_bounds__(AT_WARPS * 32) attention_simt_kernel(const T* __restrict__ qkv, int L, int heads,
                                                                        float scale, const float* __restrict__ mask_add,
-                                                                       int mask_ld, int mask_len, T* __restrict__ ctx) {
+                                                                       int mask_ld, int mask_len, T* __restrict__ ctx, Drop drop) {
   pdl_sync();
   extern __shared__ __align__(16) float sm[];
   const int r = blockIdx.x / heads, h = blockIdx.x % heads;
@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attention_simt_kernel(const T* 
     for (int c = 0; c < nch; ++c) {
       const int key = c * 32 + lane;
       const float e = key < L ? expf(p[key] - mx) : 0.f;
-      p[key] = e;
+      // training: dropout of the (normalised) probabilities -- the row sum stays the full softmax denominator
+      p[key] = e * drop_mul(drop, ((uint64_t)blockIdx.x * L + t) * L + key);
       sum += e;
     }
     sum = warp_sum(sum);
@@ -137,7 +138,7 @@ template <int KP, bool SPL>
 __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant__ CUtensorMap map_q,
                                                            const __grid_constant__ CUtensorMap map_kv, int L, int heads,
                                                            float scale_l2e, const float* __restrict__ mask_add, int mask_ld,
-                                                           int mask_len, bf16* __restrict__ ctx, int n_items) {
+                                                           int mask_len, bf16* __restrict__ ctx, int n_items, Drop drop) {
   using Cfg = AttnCfg<KP, SPL>;
   constexpr int Q_BYTES = Cfg::Q_BYTES, KV_BYTES = Cfg::KV_BYTES, QT = Cfg::QT, OPER = Cfg::OPER_BYTES;
   constexpr int CH = KP / 64;  // 32-column chunks per thread: two threads share a query row, half the keys each
@@ -278,9 +279,13 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
       if (masked || k0 + 32 > L) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), scale_l2e, maskf[k0 + 2 * i]) - mx);
-          const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), scale_l2e, maskf[k0 + 2 * i + 1]) - mx);
+          float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), scale_l2e, maskf[k0 + 2 * i]) - mx);
+          float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), scale_l2e, maskf[k0 + 2 * i + 1]) - mx);
           sum += p0 + p1;
+          if (drop.thresh) {   // training: drop probabilities (the denominator `sum` stays the full one)
+            const uint64_t e0 = ((uint64_t)item * L + (uint64_t)(qt * 128 + trow)) * L + (uint64_t)(k0 + 2 * i);
+            p0 *= drop_mul(drop, e0); p1 *= drop_mul(drop, e0 + 1);
+          }
           __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);  // .x (low half) = even key
           pk[j][i] = *reinterpret_cast<uint32_t*>(&b);
           if (SPL) {
@@ -291,9 +296,13 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), scale_l2e, -mx));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), scale_l2e, -mx));
+          float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), scale_l2e, -mx));
+          float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), scale_l2e, -mx));
           sum += p0 + p1;
+          if (drop.thresh) {
+            const uint64_t e0 = ((uint64_t)item * L + (uint64_t)(qt * 128 + trow)) * L + (uint64_t)(k0 + 2 * i);
+            p0 *= drop_mul(drop, e0); p1 *= drop_mul(drop, e0 + 1);
+          }
           __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
           pk[j][i] = *reinterpret_cast<uint32_t*>(&b);
           if (SPL) {
@@ -382,7 +391,7 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
 
 template <int KP, bool SPL>
 static int launch_attention_tc(const bf16* qkv, int64_t R, int L, int heads, float scale, const float* mask_add, int mask_ld,
-                               int mask_len, bf16* ctx, cudaStream_t st) {
+                               int mask_len, bf16* ctx, cudaStream_t st, const Drop& drop = Drop()) {
   CUtensorMap mq, mkv;
   const int ld = (SPL ? 2 : 1) * 3 * heads * AT_D;   // bf16 elements per qkv row
   MSQ_TRY(make_map_bf16(&mq, qkv, R * L, ld, ld, AT_D, 128));
@@ -403,7 +412,7 @@ static int launch_attention_tc(const bf16* qkv, int64_t R, int L, int heads, flo
   const int64_t n_items = R * heads;
   MSQ_REQUIRE(n_items < ((int64_t)1 << 31), "attention: too many (row, head) items");
 
-  MSQ_CUDA(launch_k(attention_tc_kernel<KP, SPL>, dim3((unsigned)min((int64_t)resident, n_items)), dim3(256), SMEM, st, mq, mkv, L, heads, scale * 1.4426950408889634f, mask_add, mask_ld, mask_len, ctx, (int)n_items));
+  MSQ_CUDA(launch_k(attention_tc_kernel<KP, SPL>, dim3((unsigned)min((int64_t)resident, n_items)), dim3(256), SMEM, st, mq, mkv, L, heads, scale * 1.4426950408889634f, mask_add, mask_ld, mask_len, ctx, (int)n_items, drop));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -416,11 +425,12 @@ static bool attention_use_tc() {
 
 template <typename T>
 int attention(const T* qkv, int64_t R, int L, int heads, int dhead, float scale, const float* key_mask_add, int mask_ld,
-              int mask_len, T* ctx, cudaStream_t st) {
+              int mask_len, T* ctx, cudaStream_t st, const Drop& drop) {
   MSQ_REQUIRE(dhead == AT_D, "attention: head dim %d != 64", dhead);
   MSQ_REQUIRE(L >= 1 && L <= 320, "attention: sequence length %d out of range", L);
   if (R == 0) return MSQ_OK;
   if constexpr (is_split<T>::value) {
+    MSQ_REQUIRE(drop.thresh == 0, "attention: dropout is a training-path feature (bf16 / fp32), not available in the bf16x3 mode");
     MSQ_REQUIRE(tc_supported_impl() && L <= 256 && (((uintptr_t)qkv) & 15) == 0, "attention: the bf16x3 mode needs the tcgen05 path (sm_100, L <= 256)");
     if (L <= 128)
       return launch_attention_tc<128, true>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
@@ -429,20 +439,20 @@ int attention(const T* qkv, int64_t R, int L, int heads, int dhead, float scale,
   if constexpr (sizeof(T) == 2) {
     if (attention_use_tc() && L <= 256 && (((uintptr_t)qkv) & 15) == 0) {
       if (L <= 128)
-        return launch_attention_tc<128, false>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
-      return launch_attention_tc<256, false>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
+        return launch_attention_tc<128, false>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st, drop);
+      return launch_attention_tc<256, false>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st, drop);
     }
   }
   const int Lpad = (L + 31) & ~31;
   const size_t smem = sizeof(float) * ((size_t)L * 65 + (size_t)L * AT_D + ((L + 3) & ~3) + AT_WARPS * AT_D + AT_WARPS * Lpad);
   MSQ_SMEM_ATTR(smem, attention_simt_kernel<T>);
-  MSQ_CUDA(launch_k(attention_simt_kernel<T>, dim3((unsigned)(R * heads)), dim3(AT_WARPS * 32), smem, st, qkv, L, heads, scale, key_mask_add, mask_ld, mask_len, ctx));
+  MSQ_CUDA(launch_k(attention_simt_kernel<T>, dim3((unsigned)(R * heads)), dim3(AT_WARPS * 32), smem, st, qkv, L, heads, scale, key_mask_add, mask_ld, mask_len, ctx, drop));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
   }
 }
-template int attention<bf16s>(const bf16s*, int64_t, int, int, int, float, const float*, int, int, bf16s*, cudaStream_t);
-template int attention<float>(const float*, int64_t, int, int, int, float, const float*, int, int, float*, cudaStream_t);
-template int attention<bf16>(const bf16*, int64_t, int, int, int, float, const float*, int, int, bf16*, cudaStream_t);
+template int attention<bf16s>(const bf16s*, int64_t, int, int, int, float, const float*, int, int, bf16s*, cudaStream_t, const Drop&);
+template int attention<float>(const float*, int64_t, int, int, int, float, const float*, int, int, float*, cudaStream_t, const Drop&);
+template int attention<bf16>(const bf16*, int64_t, int, int, int, float, const float*, int, int, bf16*, cudaStream_t, const Drop&);
 
 }  // namespace msq

@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(ABM_WARPS * 32, 2) attention_bwd_dq_mma_kernel
                                                                                  const bf16* __restrict__ dctx, int L, int Lp, int heads, float scale,
                                                                                  const float* __restrict__ mask_add, int mask_ld, int mask_len,
                                                                                  bf16* __restrict__ dqkv, float* __restrict__ lse_out,
-                                                                                 float* __restrict__ dsum_out) {
+                                                                                 float* __restrict__ dsum_out, Drop drop) {
   pdl_sync();
   extern __shared__ __align__(16) unsigned char smraw[];
   bf16* Ks = reinterpret_cast<bf16*>(smraw);
@@ -376,7 +376,10 @@ __global__ void __launch_bounds__(ABM_WARPS * 32, 2) attention_bwd_dq_mma_kernel
         for (int e = 0; e < 4; ++e) {
           const int hr = e >> 1;
           const float p = __expf(fmaf(sa[nt][e], scale, Ms[kb * 16 + nt * 8 + tig * 2 + (e & 1)]) - lse[hr]);
-          ds[e] = p * (dp[nt][e] - dd[hr]);
+          float dpe = dp[nt][e];
+          if (drop.thresh)   // dP = (dO V^T) . mask; D = rowsum(dO . O) already holds the masked sum
+            dpe *= drop_mul(drop, ((uint64_t)blockIdx.x * L + (uint64_t)(ib * 16 + gid + hr * 8)) * L + (uint64_t)(kb * 16 + nt * 8 + tig * 2 + (e & 1)));
+          ds[e] = p * (dpe - dd[hr]);
         }
         a[nt * 2] = pack2(ds[0], ds[1]);
         a[nt * 2 + 1] = pack2(ds[2], ds[3]);
@@ -398,7 +401,7 @@ __global__ void __launch_bounds__(ABM_WARPS * 32, 2) attention_bwd_dq_mma_kernel
 __global__ void __launch_bounds__(ABM_WARPS * 32, 2) attention_bwd_dkv_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dctx, int L,
                                                                                   int Lp, int heads, float scale, const float* __restrict__ mask_add,
                                                                                   int mask_ld, int mask_len, bf16* __restrict__ dqkv,
-                                                                                  const float* __restrict__ lse_in, const float* __restrict__ dsum_in) {
+                                                                                  const float* __restrict__ lse_in, const float* __restrict__ dsum_in, Drop drop) {
   pdl_sync();
   extern __shared__ __align__(16) unsigned char smraw[];
   bf16* Qs = reinterpret_cast<bf16*>(smraw);
@@ -442,7 +445,10 @@ __global__ void __launch_bounds__(ABM_WARPS * 32, 2) attention_bwd_dkv_mma_kerne
         for (int e = 0; e < 4; ++e) {
           const int qc = qb * 16 + nt * 8 + tig * 2 + (e & 1);
           p[e] = __expf(fmaf(st[nt][e], scale, mr[e >> 1]) - Ls[qc]);
-          ds[e] = p[e] * (dp[nt][e] - Ds[qc]);
+          float dm = 1.f;
+          if (drop.thresh) dm = drop_mul(drop, ((uint64_t)blockIdx.x * L + (uint64_t)qc) * L + (uint64_t)(jb * 16 + gid + (e >> 1) * 8));
+          ds[e] = p[e] * (dp[nt][e] * dm - Ds[qc]);
+          p[e] *= dm;                                  // dV = (P . mask)^T dO
         }
         pa[nt * 2] = pack2(p[0], p[1]); pa[nt * 2 + 1] = pack2(p[2], p[3]);
         da[nt * 2] = pack2(ds[0], ds[1]); da[nt * 2 + 1] = pack2(ds[2], ds[3]);
@@ -472,7 +478,7 @@ bool attention_bwd_mma_supported(int L) {
 }
 
 int attention_bwd_mma(const bf16* qkv, const bf16* ctx, const bf16* dctx, int64_t R, int L, int heads, float scale, const float* key_mask_add,
-                      int mask_ld, int mask_len, bf16* dqkv, float* scratch, cudaStream_t st) {
+                      int mask_ld, int mask_len, bf16* dqkv, float* scratch, cudaStream_t st, const Drop& drop) {
   MSQ_REQUIRE(L >= 1 && L <= 256, "attention_bwd_mma: sequence length %d out of range", L);
   MSQ_REQUIRE((((uintptr_t)qkv | (uintptr_t)ctx | (uintptr_t)dctx | (uintptr_t)dqkv) & 15) == 0, "attention_bwd_mma: unaligned pointer");
   if (R == 0) return MSQ_OK;
@@ -480,6 +486,7 @@ int attention_bwd_mma(const bf16* qkv, const bf16* ctx, const bf16* dctx, int64_
   static int fused = -1;
   if (fused < 0) { const char* e = getenv("MSQ_ATTN_BWD_FUSED"); fused = (e && e[0] == '1') ? 1 : 0; }
   if (fused || !scratch) {
+    MSQ_REQUIRE(drop.thresh == 0, "attention_bwd_mma: the single-kernel form (MSQ_ATTN_BWD_FUSED=1) has no dropout; unset it to train with dropout");
     const size_t smem = (size_t)4 * Lp * ABM_LD * sizeof(bf16) + (size_t)3 * Lp * sizeof(float);
     MSQ_SMEM_ATTR(smem, attention_bwd_mma_kernel);
     MSQ_CUDA(launch_k(attention_bwd_mma_kernel, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem, st, qkv, ctx, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv));
@@ -492,9 +499,9 @@ int attention_bwd_mma(const bf16* qkv, const bf16* ctx, const bf16* dctx, int64_
   const size_t smem_b = (size_t)2 * Lp * ABM_LD * sizeof(bf16) + (size_t)2 * Lp * sizeof(float);
   MSQ_SMEM_ATTR(smem_a, attention_bwd_dq_mma_kernel);
   MSQ_SMEM_ATTR(smem_b, attention_bwd_dkv_mma_kernel);
-  MSQ_CUDA(launch_k(attention_bwd_dq_mma_kernel, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem_a, st, qkv, ctx, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, lse, dsum));
+  MSQ_CUDA(launch_k(attention_bwd_dq_mma_kernel, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem_a, st, qkv, ctx, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, lse, dsum, drop));
   MSQ_LAUNCH_CHECK();
-  MSQ_CUDA(launch_k(attention_bwd_dkv_mma_kernel, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem_b, st, qkv, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, (const float*)lse, (const float*)dsum));
+  MSQ_CUDA(launch_k(attention_bwd_dkv_mma_kernel, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem_b, st, qkv, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, (const float*)lse, (const float*)dsum, drop));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }

@@ -2,6 +2,7 @@
 // the given stream; nothing synchronises.
 #pragma once
 #include "common.cuh"
+#include "dropout.cuh"
 
 namespace msq {
 
@@ -98,18 +99,20 @@ int gemm_ln(const bf16* A, int lda, const bf16* W, int ldw, const float* bias, c
             const float* beta, float eps, float* C, bf16* C2, int64_t M, int N, int K, bool raw32, cudaStream_t st);
 
 // ---- attention.cu : ctx[r, t, h*64 + d] = softmax(q k^T / sqrt(d) + mask) v over the L tokens of row-group r
+// drop: training-mode dropout of the probabilities (site A; element index ((r*heads + h)*L + q)*L + k); default = off
 template <typename T>
 int attention(const T* qkv, int64_t R, int L, int heads, int dhead, float scale, const float* key_mask_add, int mask_ld,
-              int mask_len, T* ctx, cudaStream_t st);
+              int mask_len, T* ctx, cudaStream_t st, const Drop& drop = Drop());
 
 // ---- pooling.cu
 template <typename T>
 int token_pool(const T* tt, const float* x, int64_t R, int Lt, int Lj, int H, const float* w2, const float* b2,
-               const int64_t* sep, const float* w_rel, const float* b_rel, float* mix, float* rel6, cudaStream_t st);
+               const int64_t* sep, const float* w_rel, const float* b_rel, float* mix, float* rel6, cudaStream_t st,
+               const Drop& drop = Drop());   // drop: training-mode dropout of the token-attention probabilities (site H)
 int edge_pool(const float* mix, const float* x, const float* rel6, int64_t B, int N, int Lj, int H, const float* w_in2,
               float* sents, float* r0, int r0_ld, float* cls_mat, float* score_mat, float* his1, float* his2, float* cls_out,
               cudaStream_t st);
-int para_attention(const float* qkv, int64_t B, int N, int heads, int H, float* ctx, cudaStream_t st);
+int para_attention(const float* qkv, int64_t B, int N, int heads, int H, float* ctx, cudaStream_t st, const Drop& drop = Drop());
 int para_finish(const float* sents, const float* para, int64_t B, int N, int H, float* h0, float* keyin, cudaStream_t st);
 
 // ---- decode.cu
@@ -181,11 +184,11 @@ int vit_assemble_bwd(const float* dy, const float* patch, const int32_t* img_ind
 size_t attention_bwd_scratch_floats(int64_t R, int L, int heads);
 template <typename T>
 int attention_bwd(const T* qkv, const T* dctx, int64_t R, int L, int heads, float scale, const float* key_mask_add, int mask_ld,
-                  int mask_len, T* dqkv, float* scratch, cudaStream_t st);
+                  int mask_len, T* dqkv, float* scratch, cudaStream_t st, const Drop& drop = Drop());
 // attention_bwd_mma.cu: bf16 tensor-core (mma.sync) version; ctx = the forward's output (for D_i = dO_i . O_i)
 bool attention_bwd_mma_supported(int L);
 int attention_bwd_mma(const bf16* qkv, const bf16* ctx, const bf16* dctx, int64_t R, int L, int heads, float scale, const float* key_mask_add,
-                      int mask_ld, int mask_len, bf16* dqkv, float* scratch, cudaStream_t st);   // scratch: attention_bwd_scratch_floats
+                      int mask_ld, int mask_len, bf16* dqkv, float* scratch, cudaStream_t st, const Drop& drop = Drop());   // scratch: attention_bwd_scratch_floats
 int mask_add_from_int(const int64_t* mask, int64_t n, float* out, cudaStream_t st);
 int scatter_rows(const float* src, int64_t rows, int H, int group, int dst_group, int off, float* dst, cudaStream_t st);
 size_t grad_norm_scratch_floats();

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) token_pool_kernel(const T* __restrict__ t
                                                          int H, const float* __restrict__ w2, const float* __restrict__ b2,
                                                          const int64_t* __restrict__ sep, const float* __restrict__ w_rel,
                                                          const float* __restrict__ b_rel, float* __restrict__ mix,
-                                                         float* __restrict__ rel6) {
+                                                         float* __restrict__ rel6, Drop drop) {
   pdl_sync();
   extern __shared__ float sm[];
   float* score = sm;        // [Lt]
@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(256) token_pool_kernel(const T* __restrict__ t
     }
     s = warp_sum(s);
     const float inv = 1.f / s;
-    for (int t = lane; t < Lt; t += 32) p[t] *= inv;
+    // training: dropout of the token-attention probabilities [R, 2, Lt] (modeling_bert.py:735)
+    for (int t = lane; t < Lt; t += 32) p[t] *= inv * drop_mul(drop, ((uint64_t)r * 2 + warp) * Lt + t);
   }
   __syncthreads();
   const float* xr = x + r * Lj * (int64_t)H;
@@ -76,16 +77,16 @@ __global__ void __launch_bounds__(256) token_pool_kernel(const T* __restrict__ t
 
 template <typename T>
 int token_pool(const T* tt, const float* x, int64_t R, int Lt, int Lj, int H, const float* w2, const float* b2,
-               const int64_t* sep, const float* w_rel, const float* b_rel, float* mix, float* rel6, cudaStream_t st) {
+               const int64_t* sep, const float* w_rel, const float* b_rel, float* mix, float* rel6, cudaStream_t st, const Drop& drop) {
   if (R == 0) return MSQ_OK;
-  MSQ_CUDA(launch_k(token_pool_kernel<T>, dim3((unsigned)R), dim3(256), 3 * Lt * sizeof(float), st, tt, x, Lt, Lj, H, w2, b2, sep, w_rel, b_rel, mix, rel6));
+  MSQ_CUDA(launch_k(token_pool_kernel<T>, dim3((unsigned)R), dim3(256), 3 * Lt * sizeof(float), st, tt, x, Lt, Lj, H, w2, b2, sep, w_rel, b_rel, mix, rel6, drop));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
 template int token_pool<float>(const float*, const float*, int64_t, int, int, int, const float*, const float*, const int64_t*,
-                               const float*, const float*, float*, float*, cudaStream_t);
+                               const float*, const float*, float*, float*, cudaStream_t, const Drop&);
 template int token_pool<bf16>(const bf16*, const float*, int64_t, int, int, int, const float*, const float*, const int64_t*,
-                              const float*, const float*, float*, float*, cudaStream_t);
+                              const float*, const float*, float*, float*, cudaStream_t, const Drop&);
 
 // pair index of the ordered pair (i, j), i != j, in pairs_generator order
 // (models/berson/process_inputs_for_berson.py:246-261): combinations first, then the mirrored list.
@@ -185,7 +186,7 @@ int edge_pool(const float* mix, const float* x, const float* rel6, int64_t B, in
 // qkv [B*N, 3H] (q | k | v), heads x (H/heads).  One block per (manual, head); mask is all-ones
 // (every manual has exactly N steps, process_inputs_for_berson.py:133).
 __global__ void __launch_bounds__(128) para_attention_kernel(const float* __restrict__ qkv, int N, int heads, int H,
-                                                             float* __restrict__ ctx) {
+                                                             float* __restrict__ ctx, Drop drop) {
   pdl_sync();
   __shared__ float s[PL_MAXN][PL_MAXN + 1];
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
@@ -206,7 +207,8 @@ __global__ void __launch_bounds__(128) para_attention_kernel(const float* __rest
     float mx = -INFINITY, sum = 0.f;
     for (int j = 0; j < N; ++j) mx = fmaxf(mx, s[i][j]);
     for (int j = 0; j < N; ++j) { s[i][j] = expf(s[i][j] - mx); sum += s[i][j]; }
-    for (int j = 0; j < N; ++j) s[i][j] /= sum;
+    // training: attention dropout [B, heads, N, N] (neural.py:228)
+    for (int j = 0; j < N; ++j) s[i][j] = s[i][j] / sum * drop_mul(drop, ((uint64_t)blockIdx.x * N + i) * N + j);
   }
   __syncthreads();
   for (int ie = threadIdx.x; ie < N * d; ie += blockDim.x) {
@@ -217,10 +219,10 @@ __global__ void __launch_bounds__(128) para_attention_kernel(const float* __rest
   }
 }
 
-int para_attention(const float* qkv, int64_t B, int N, int heads, int H, float* ctx, cudaStream_t st) {
+int para_attention(const float* qkv, int64_t B, int N, int heads, int H, float* ctx, cudaStream_t st, const Drop& drop) {
   MSQ_REQUIRE(N <= PL_MAXN && H % heads == 0, "para_attention: N=%d heads=%d H=%d", N, heads, H);
   if (B == 0) return MSQ_OK;
-  MSQ_CUDA(launch_k(para_attention_kernel, dim3((unsigned)(B * heads)), dim3(128), 0, st, qkv, N, heads, H, ctx));
+  MSQ_CUDA(launch_k(para_attention_kernel, dim3((unsigned)(B * heads)), dim3(128), 0, st, qkv, N, heads, H, ctx, drop));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }

@@ -200,9 +200,14 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
   if (mm) MSQ_CUDA(cudaMemcpyAsync(ts->img_index, img_index, (size_t)R * 2 * 4, cudaMemcpyDeviceToDevice, st));
   MSQ_TRY(mask_add_from_int(mask, R * Lt, ts->mask_add, st));
 
+  // dropout: this forward's masks are keyed by a fresh step counter (the backward pass regenerates them from it)
+  ts->drop.step = ts->drop_next_step++;
+  const DropCfg& dc = ts->drop;
+  const bool drop_h = dc.p_hidden > 0.f;
   // layer-0 input: embeddings (text rows) and visn_fc(LN) of the tower output (visual rows) -> xf (fp32) + X[0] (T)
   T* x0 = nb ? (T*)ts->bt[0].x : (T*)ts->x_last;
   MSQ_TRY(embed_ln<T>(ids, tt, R, Lt, Lj, H, m->word, m->pos, m->type, m->emb_ln.g, m->emb_ln.b, 1e-12f, xf, x0, st));
+  MSQ_TRY(dropout_rows<T>(xf, x0, R, Lj, 0, Lt, H, make_drop(dc, DROP_E, 0, dc.p_hidden), st));
   if (mm) {
     // patch embedding per UNIQUE image
     for (int64_t i0 = 0; i0 < n_img; i0 += TRAIN_IMG_CHUNK) {
@@ -231,18 +236,30 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
     MSQ_TRY((gemm_nt<T, float>(m, (const T*)ts->y_post, Wd, wptr<T>(m->visn_fc), m->visn_fc.ld, m->visn_fc.b, nullptr, 0, ts->visn_pre, H, Mv,
                                H, Wd, ACT_NONE, st)));
     MSQ_TRY(layernorm<T>(ts->visn_pre, Mv, H, m->visn_ln.g, m->visn_ln.b, 1e-12f, xf, x0, Lv, Lj, Lt, st));
+    MSQ_TRY(dropout_rows<T>(xf, x0, R, Lj, Lt, Lv, H, make_drop(dc, DROP_V, 0, dc.p_hidden), st));
   }
   for (size_t l = 0; l < nb; ++l) {
     BertLayerW& L = m->bert[l];
     BertTape& t = ts->bt[l];
     T* xn = l + 1 < nb ? (T*)ts->bt[l + 1].x : (T*)ts->x_last;
     MSQ_TRY((gemm_nt<T, T>(m, (const T*)t.x, H, wptr<T>(L.qkv), L.qkv.ld, L.qkv.b, nullptr, 0, (T*)t.qkv, 3 * H, Mj, 3 * H, H, ACT_NONE, st)));
-    MSQ_TRY(attention<T>((const T*)t.qkv, R, Lj, c.heads, 64, 0.125f, ts->mask_add, Lt, Lt, (T*)t.ctx, st));
-    MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.ctx, H, wptr<T>(L.out), L.out.ld, L.out.b, xf, H, t.s1, H, Mj, H, H, ACT_NONE, st)));
+    MSQ_TRY(attention<T>((const T*)t.qkv, R, Lj, c.heads, 64, 0.125f, ts->mask_add, Lt, Lt, (T*)t.ctx, st,
+                         make_drop(dc, DROP_A, (int)l, dc.p_attn)));
+    if (drop_h) {   // s1 = dropout(dense(ctx) + b) + x
+      MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.ctx, H, wptr<T>(L.out), L.out.ld, L.out.b, nullptr, 0, t.s1, H, Mj, H, H, ACT_NONE, st)));
+      MSQ_TRY(dropout_add(t.s1, xf, Mj * H, make_drop(dc, DROP_O, (int)l, dc.p_hidden), st));
+    } else {
+      MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.ctx, H, wptr<T>(L.out), L.out.ld, L.out.b, xf, H, t.s1, H, Mj, H, H, ACT_NONE, st)));
+    }
     MSQ_TRY(layernorm<T>(t.s1, Mj, H, L.ln1.g, L.ln1.b, 1e-12f, x1f, (T*)t.x1, 0, 0, 0, st));
     MSQ_TRY((gemm_nt<T, T>(m, (const T*)t.x1, H, wptr<T>(L.up), L.up.ld, L.up.b, nullptr, 0, (T*)t.u, I, Mj, I, H, ACT_NONE, st)));
     MSQ_TRY(act_fwd<T>((const T*)t.u, Mj * I, ACT_GELU_ERF, (T*)t.hb, st));
-    MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.hb, I, wptr<T>(L.down), L.down.ld, L.down.b, x1f, H, t.s2, H, Mj, H, I, ACT_NONE, st)));
+    if (drop_h) {   // s2 = dropout(dense(h) + b) + x1
+      MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.hb, I, wptr<T>(L.down), L.down.ld, L.down.b, nullptr, 0, t.s2, H, Mj, H, I, ACT_NONE, st)));
+      MSQ_TRY(dropout_add(t.s2, x1f, Mj * H, make_drop(dc, DROP_F, (int)l, dc.p_hidden), st));
+    } else {
+      MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.hb, I, wptr<T>(L.down), L.down.ld, L.down.b, x1f, H, t.s2, H, Mj, H, I, ACT_NONE, st)));
+    }
     MSQ_TRY(layernorm<T>(t.s2, Mj, H, L.ln2.g, L.ln2.b, 1e-12f, xf, xn, 0, 0, 0, st));
   }
   MSQ_CUDA(cudaMemcpyAsync(ts->x_out, xf, (size_t)Mj * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -257,11 +274,11 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
 // attention backward: tensor cores (mma.sync) on the bf16 path, fp32 CUDA cores in the parity mode
 template <typename T>
 static int attn_bwd(const T* qkv, const T* ctx, const T* dctx, int64_t R, int L, int heads, const float* mask, int mask_len, T* dqkv, float* scratch,
-                    cudaStream_t st) {
+                    cudaStream_t st, const Drop& drop = Drop()) {
   if constexpr (sizeof(T) == 2) {
-    if (attention_bwd_mma_supported(L)) return attention_bwd_mma(qkv, ctx, dctx, R, L, heads, 0.125f, mask, mask_len, mask_len, dqkv, scratch, st);
+    if (attention_bwd_mma_supported(L)) return attention_bwd_mma(qkv, ctx, dctx, R, L, heads, 0.125f, mask, mask_len, mask_len, dqkv, scratch, st, drop);
   }
-  return attention_bwd<T>(qkv, dctx, R, L, heads, 0.125f, mask, mask_len, mask_len, dqkv, scratch, st);
+  return attention_bwd<T>(qkv, dctx, R, L, heads, 0.125f, mask, mask_len, mask_len, dqkv, scratch, st, drop);
 }
 
 template <typename T>
@@ -281,6 +298,7 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
     if (it == ts->index.end()) { set_error("train: no gradient slot for %s", name.c_str()); err = MSQ_ERR_STATE; return nullptr; }
     return grads + ts->slots[it->second].off;
   };
+  const DropCfg& dc = ts->drop;   // the masks of the recorded forward
   const int64_t MpJ = wgrad_rows(Mj), MpV = wgrad_rows(max(Mv, (int64_t)1));
   const int64_t nchunk = mm ? min(n_img, TRAIN_IMG_CHUNK) * g2 : 0, Np = round_up(max(nchunk, (int64_t)1), 64);
   BwdBufs b{};
@@ -326,6 +344,8 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
     if (err) return err;
     // output.LayerNorm -> ds2 (gB fp32, gT operand copy)
     MSQ_TRY(ln_bwd<T>(b.gA, t.s2, nullptr, Mj, H, L.ln2.g, 1e-12f, b.gB, (T*)b.gT, dg2, db2, b.ln_scr, 0, 0, 0, st));
+    // under dropout the dense output's gradient is ds2 * mask (operand copy gT); the residual branch keeps ds2 (gB)
+    MSQ_TRY(dropout_mask_copy<T>(b.gB, (T*)b.gT, Mj * H, make_drop(dc, DROP_F, (int)li, dc.p_hidden), st));
     MSQ_TRY(wgrad<T>(m, (const T*)b.gT, H, H, (const T*)t.hb, I, I, ACT_NONE, Mj, dWd, dbd, b, st));
     MSQ_TRY((dgrad<T, T>(m, (const T*)b.gT, H, WT[3], I, nullptr, (T*)b.gH, Mj, st)));
     MSQ_TRY(act_bwd<T>((const T*)b.gH, (const T*)t.u, Mj * I, ACT_GELU_ERF, (T*)b.gH, st));
@@ -333,9 +353,11 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
     MSQ_TRY((dgrad<T, float>(m, (const T*)b.gH, I, WT[2], H, b.gB, b.gA, Mj, st)));            // dX1 = du Wup + ds2
     // attention.output.LayerNorm -> ds1
     MSQ_TRY(ln_bwd<T>(b.gA, t.s1, nullptr, Mj, H, L.ln1.g, 1e-12f, b.gB, (T*)b.gT, dg1, db1, b.ln_scr, 0, 0, 0, st));
+    MSQ_TRY(dropout_mask_copy<T>(b.gB, (T*)b.gT, Mj * H, make_drop(dc, DROP_O, (int)li, dc.p_hidden), st));
     MSQ_TRY(wgrad<T>(m, (const T*)b.gT, H, H, (const T*)t.ctx, H, H, ACT_NONE, Mj, dWo, dbo, b, st));
     MSQ_TRY((dgrad<T, T>(m, (const T*)b.gT, H, WT[1], H, nullptr, (T*)b.gC, Mj, st)));
-    MSQ_TRY(attn_bwd<T>((const T*)t.qkv, (const T*)t.ctx, (const T*)b.gC, R, Lj, c.heads, ts->mask_add, Lt, (T*)b.gQ, b.at_scr, st));
+    MSQ_TRY(attn_bwd<T>((const T*)t.qkv, (const T*)t.ctx, (const T*)b.gC, R, Lj, c.heads, ts->mask_add, Lt, (T*)b.gQ, b.at_scr, st,
+                        make_drop(dc, DROP_A, (int)li, dc.p_attn)));
     MSQ_TRY(wgrad<T>(m, (const T*)b.gQ, 3 * H, 3 * H, (const T*)t.x, H, H, ACT_NONE, Mj, dWqkv, dbqkv, b, st));
     MSQ_TRY((dgrad<T, float>(m, (const T*)b.gQ, 3 * H, WT[0], H, b.gB, b.gA, Mj, st)));        // dX0 = dqkv Wqkv + ds1
     MSQ_TRY(mark_ready(ts, bn + "attention.self.query.weight", bn + "output.LayerNorm.bias", st));
@@ -346,6 +368,9 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
           *dtyp = G(P + "embeddings.token_type_embeddings.weight"), *dg = G(P + "embeddings.LayerNorm.weight"),
           *db = G(P + "embeddings.LayerNorm.bias");
     if (err) return err;
+    // gA = d(joint layer-0 input): undo the input dropouts (text rows: E, visual rows: V) before the LayerNorm backwards
+    MSQ_TRY(dropout_rows<float>(b.gA, nullptr, R, Lj, 0, Lt, H, make_drop(dc, DROP_E, 0, dc.p_hidden), st));
+    if (mm) MSQ_TRY(dropout_rows<float>(b.gA, nullptr, R, Lj, Lt, Lv, H, make_drop(dc, DROP_V, 0, dc.p_hidden), st));
     MSQ_TRY(embed_ln_bwd(b.gA, ts->ids, ts->tt, R, Lt, Lj, H, m->word, m->pos, m->type, m->emb_ln.g, 1e-12f, dword, dpos, dtyp, dg, db, b.ln_scr,
                          c.vit_width != 0 ? 7 : 1, st));   // padding_idx=0 tables: LXRT all three, text-only BertModel the word table
     MSQ_TRY(mark_ready(ts, P + "embeddings.word_embeddings.weight", P + "embeddings.LayerNorm.bias", st));
@@ -535,6 +560,22 @@ static int mark_heads_ready(msq_model* m, cudaStream_t st) {
   const std::vector<std::string> names = heads_param_names(m);
   if (names.empty()) return MSQ_OK;
   return mark_ready(ts, names.front(), names.back(), st);   // slots were added in this order: first .. last are contiguous
+}
+
+/* Dropout of the fine-tuning path (the reference trains with hidden_dropout_prob = attention_probs_dropout_prob = 0.1,
+ * BertConfig; args.para_dropout for the paragraph encoder).  Probabilities in [0, 1); 0 = off (the default).  Masks are a
+ * pure function of (seed, forward counter, site, element index): see csrc/dropout.cuh / oracle/dropout.py. */
+extern "C" int msq_train_set_dropout(msq_model* m, float p_hidden, float p_attn, float p_para, uint32_t seed, void* stream) {
+  DevGuard dev_guard__(m);
+  MSQ_TRY(ensure_train(m, (cudaStream_t)stream));
+  MSQ_REQUIRE(p_hidden >= 0.f && p_hidden < 1.f && p_attn >= 0.f && p_attn < 1.f && p_para >= 0.f && p_para < 1.f, "dropout probabilities must lie in [0, 1)");
+  TrainState* ts = m->train;
+  ts->drop.seed = seed; ts->drop.p_hidden = p_hidden; ts->drop.p_attn = p_attn; ts->drop.p_para = p_para;
+  return MSQ_OK;
+}
+/* counter of the LAST training forward (what keyed its masks); -1 before the first one */
+extern "C" int64_t msq_train_dropout_step(msq_model* m) {
+  return (m && m->train && m->train->drop_next_step > 0) ? (int64_t)m->train->drop.step : -1;
 }
 
 /* Gradient-ready regions of the last msq_train_step, in completion order (see TrainState::ready_ev): count, the element

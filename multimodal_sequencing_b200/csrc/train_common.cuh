@@ -3,6 +3,7 @@
 #include <array>
 #include <math.h>
 
+#include "dropout.cuh"
 #include "model.cuh"
 
 namespace msq {
@@ -32,7 +33,7 @@ struct SplitK {
   }
 };
 
-struct ParaTape { float *xin, *y, *qkv, *ctx, *out, *pn, *u, *xo; };
+struct ParaTape { float *xin, *y, *qkv, *ctx, *out, *pn, *u, *xo, *hf; };   // hf: dropped FFN activations (dropout only)
 struct HeadTape {
   int64_t B = 0;
   int N = 0;
@@ -74,6 +75,9 @@ struct TrainState {
   Arena htape;
   HeadTape ht;
   SplitK splitk;
+  // ---- dropout (msq_train_set_dropout): probabilities + seed; `step` is the counter of the forward whose masks are live
+  DropCfg drop;
+  uint32_t drop_next_step = 0;
   // ---- gradient-ready events of the last backward pass, in the order the regions of the flat buffer become final
   // (heads, BERT layers top -> bottom, embeddings, visn_fc, ViT blocks top -> bottom, ViT stem): a data-parallel caller
   // all-reduces region i on a side stream as soon as event i has fired, overlapping the rest of the backward pass
@@ -224,6 +228,10 @@ static int dgrad(const msq_model* m, const T* G, int Nout, const void* WT, int K
 // ---- train_heads.cu
 int heads_train_setup(msq_model* m, bool alloc, cudaStream_t st);
 std::vector<std::string> heads_param_names(const msq_model* m);
+// train_kernels.cu: elementwise dropout sites
+template <typename T> int dropout_rows(float* xf, T* xt, int64_t R, int group, int off, int n, int H, const Drop& d, cudaStream_t st);
+int dropout_add(float* s, const float* resid, int64_t n, const Drop& d, cudaStream_t st);
+template <typename T> int dropout_mask_copy(const float* g, T* gt, int64_t n, const Drop& d, cudaStream_t st);
 template <typename T>
 int heads_train(msq_model* m, const int64_t* sep, int64_t B, int N, const int32_t* target, const int64_t* pair_labels, float lam, float* grads,
                 float* loss_out, cudaStream_t st);

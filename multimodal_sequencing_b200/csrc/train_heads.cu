@@ -116,7 +116,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) token_pool_bwd_kernel(const T* __restrict__ tt, const float* __restrict__ x, int Lt, int Lj, int H,
                                                              const float* __restrict__ w2, const float* __restrict__ b2,
                                                              const int64_t* __restrict__ sep, const float* __restrict__ dmix,
-                                                             float* __restrict__ d_lang, float* __restrict__ dscore) {
+                                                             float* __restrict__ d_lang, float* __restrict__ dscore, Drop drop) {
   pdl_sync();
   extern __shared__ float sm[];
   float* score = sm;          // [Lt]
@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(256) token_pool_bwd_kernel(const T* __restrict
       const float* dm = dmix + (r * 2 + (t <= sep0 ? 0 : 1)) * H;
       for (int d = lane; d < H; d += 32) c = fmaf(dm[d], xr[(int64_t)t * H + d], c);
       c = warp_sum(c);
+      c *= drop_mul(drop, ((uint64_t)r * 2 + (t <= sep0 ? 0 : 1)) * Lt + t);   // dP = (dmix . x_t) . mask
     }
     if (lane == 0) dp[t] = c;
   }
@@ -167,7 +168,8 @@ __global__ void __launch_bounds__(256) token_pool_bwd_kernel(const T* __restrict
   for (int i = threadIdx.x; i < Lt * H; i += blockDim.x) {
     const int t = i / H, d = i % H;
     float v = 0.f;
-    if (t >= 1 && t <= sep1) v = p[t] * dmix[(r * 2 + (t <= sep0 ? 0 : 1)) * H + d];
+    if (t >= 1 && t <= sep1)
+      v = p[t] * drop_mul(drop, ((uint64_t)r * 2 + (t <= sep0 ? 0 : 1)) * Lt + t) * dmix[(r * 2 + (t <= sep0 ? 0 : 1)) * H + d];
     dl[i] = v;
   }
 }
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(256) edge_pool_bwd_kernel(const float* __restr
 // paragraph attention backward (neural.py:200-226), one block per (manual, head); N <= 16 tokens.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) para_attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dctx, int N, int heads,
-                                                                 int H, float* __restrict__ dqkv) {
+                                                                 int H, float* __restrict__ dqkv, Drop drop) {
   pdl_sync();
   __shared__ float s[TH_MAXN][TH_MAXN + 1], g[TH_MAXN][TH_MAXN + 1];
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
@@ -313,8 +315,16 @@ __global__ void __launch_bounds__(128) para_attention_bwd_kernel(const float* __
     float mx = -INFINITY, sum = 0.f, dot = 0.f;
     for (int j = 0; j < N; ++j) mx = fmaxf(mx, s[i][j]);
     for (int j = 0; j < N; ++j) { s[i][j] = expf(s[i][j] - mx); sum += s[i][j]; }
-    for (int j = 0; j < N; ++j) { s[i][j] /= sum; dot = fmaf(s[i][j], g[i][j], dot); }
-    for (int j = 0; j < N; ++j) g[i][j] = s[i][j] * (g[i][j] - dot);   // dS
+    for (int j = 0; j < N; ++j) {
+      const float dm = drop_mul(drop, ((uint64_t)blockIdx.x * N + i) * N + j);
+      s[i][j] /= sum;
+      g[i][j] *= dm;                       // dP = (dctx v^T) . mask
+      dot = fmaf(s[i][j], g[i][j], dot);
+    }
+    for (int j = 0; j < N; ++j) {
+      g[i][j] = s[i][j] * (g[i][j] - dot);   // dS
+      s[i][j] *= drop_mul(drop, ((uint64_t)blockIdx.x * N + i) * N + j);   // P . mask, what dV sees
+    }
   }
   __syncthreads();
   for (int ie = threadIdx.x; ie < N * d; ie += blockDim.x) {
@@ -645,6 +655,7 @@ int heads_train(msq_model* m, const int64_t* sep, int64_t B, int N, const int32_
       L.y = p.take<float>((size_t)M * H); L.qkv = p.take<float>((size_t)M * 3 * H); L.ctx = p.take<float>((size_t)M * H);
       L.out = p.take<float>((size_t)M * H); L.pn = p.take<float>((size_t)M * H); L.u = p.take<float>((size_t)M * ff);
       L.xo = p.take<float>((size_t)M * H);
+      L.hf = ts->drop.p_para > 0.f ? p.take<float>((size_t)M * ff) : nullptr;
     }
     h.para = p.take<float>((size_t)M * H); h.h0 = p.take<float>((size_t)B * H);
     h.keyin = p.take<float>((size_t)M * 2 * H); h.key = p.take<float>((size_t)M * H);
@@ -662,7 +673,7 @@ int heads_train(msq_model* m, const int64_t* sep, int64_t B, int N, const int32_
   const int64_t MpTok = round_up(Mt, 64), MpS = round_up(max(max(C2, B * (N + 1)), (int64_t)N * B), 64);
   const int wide = max(max(4 * H, ff), max(3 * H, Kp));
   float *hf, *pre, *hsbt, *dmix, *dscore, *drel2, *dsents, *dpara, *dkeyin, *dkey0, *dquery, *dhs, *dt4, *dr0, *dw4, *dxg, *dext, *dgall, *dcbuf,
-      *dhrec, *part, *gx, *gy, *gq, *gu, *dh0;
+      *dhrec, *part, *gx, *gy, *gq, *gu, *dh0, *gm;
   void* dpre = nullptr;
   BwdBufs bb{};
   for (int pass = 0; pass < 2; ++pass) {
@@ -678,6 +689,7 @@ int heads_train(msq_model* m, const int64_t* sep, int64_t B, int N, const int32_
     dh0 = p.take<float>((size_t)B * H);
     part = p.take<float>((size_t)max(max((int64_t)148 * 4, M), B) * (H + 1) + ln_bwd_scratch_floats(H));
     gx = p.take<float>((size_t)M * H); gy = p.take<float>((size_t)M * H); gq = p.take<float>((size_t)M * 3 * H); gu = p.take<float>((size_t)M * ff);
+    gm = p.take<float>((size_t)M * H);   // dropout: masked copy of a sub-layer output gradient
     dpre = p.take<T>((size_t)Mt * H);
     const size_t tbytes = max((size_t)H * MpTok * sizeof(T), (size_t)wide * MpS * sizeof(float));
     bb.GT = p.take<char>(tbytes);
@@ -689,7 +701,10 @@ int heads_train(msq_model* m, const int64_t* sep, int64_t B, int N, const int32_
   // ================= forward =================
   MSQ_TRY((gather_rows<float, T>(x, Mt, H, Lt, Lj, 0, (T*)h.topt, st)));
   MSQ_TRY((gemm_nt<T, T>(m, (const T*)h.topt, H, wptr<T>(m->sent_tran), m->sent_tran.ld, m->sent_tran.b, nullptr, 0, (T*)h.ttb, H, Mt, H, H, ACT_TANH, st)));
-  MSQ_TRY(token_pool<T>((const T*)h.ttb, x, R, Lt, Lj, H, m->w2, m->b2, sep, m->w_rel, m->b_rel, h.mix, h.rel6, st));
+  const DropCfg& dc = ts->drop;   // masks of this step (keyed by the encoder forward that just ran)
+  const bool drop_p = dc.p_para > 0.f;
+  MSQ_TRY(token_pool<T>((const T*)h.ttb, x, R, Lt, Lj, H, m->w2, m->b2, sep, m->w_rel, m->b_rel, h.mix, h.rel6, st,
+                        make_drop(dc, DROP_H, 0, dc.p_hidden)));
   MSQ_TRY(edge_pool(h.mix, x, h.rel6, B, N, Lj, H, m->w_in2, h.sents, h.r0, Kp, nullptr, nullptr, nullptr, nullptr, nullptr, st));
   {
     const float* xin = h.sents;
@@ -700,12 +715,24 @@ int heads_train(msq_model* m, const int64_t* sep, int64_t B, int N, const int32_
       const float* y = xin;
       if (l != 0) { MSQ_TRY(layernorm<float>(xin, M, H, L.ln_in.g, L.ln_in.b, 1e-6f, t.y, nullptr, 0, 0, 0, st)); y = t.y; }
       MSQ_TRY(g32(y, H, L.qkv.w32, L.qkv.ld, L.qkv.b, nullptr, 0, t.qkv, 3 * H, M, 3 * H, H, ACT_NONE, st));
-      MSQ_TRY(para_attention(t.qkv, B, N, c.para_heads, H, t.ctx, st));
-      MSQ_TRY(g32(t.ctx, H, L.fin.w32, L.fin.ld, L.fin.b, xin, H, t.out, H, M, H, H, ACT_NONE, st));
+      MSQ_TRY(para_attention(t.qkv, B, N, c.para_heads, H, t.ctx, st, make_drop(dc, DROP_PA, (int)l, dc.p_para)));
+      if (drop_p) {   // out = dropout(final_linear(ctx)) + x   (encoder.py:28)
+        MSQ_TRY(g32(t.ctx, H, L.fin.w32, L.fin.ld, L.fin.b, nullptr, 0, t.out, H, M, H, H, ACT_NONE, st));
+        MSQ_TRY(dropout_add(t.out, xin, M * H, make_drop(dc, DROP_PC, (int)l, dc.p_para), st));
+      } else {
+        MSQ_TRY(g32(t.ctx, H, L.fin.w32, L.fin.ld, L.fin.b, xin, H, t.out, H, M, H, H, ACT_NONE, st));
+      }
       MSQ_TRY(layernorm<float>(t.out, M, H, L.ln_ff.g, L.ln_ff.b, 1e-6f, t.pn, nullptr, 0, 0, 0, st));
       MSQ_TRY(g32(t.pn, H, L.w1.w32, L.w1.ld, L.w1.b, nullptr, 0, t.u, ff, M, ff, H, ACT_NONE, st));
-      MSQ_TRY(act_fwd<float>(t.u, M * ff, ACT_GELU_TANH, hf, st));
-      MSQ_TRY(g32(hf, ff, L.w2.w32, L.w2.ld, L.w2.b, t.out, H, t.xo, H, M, H, ff, ACT_NONE, st));
+      float* hfl = drop_p ? t.hf : hf;   // under dropout the dropped activations are kept for the w_2 weight gradient
+      MSQ_TRY(act_fwd<float>(t.u, M * ff, ACT_GELU_TANH, hfl, st));
+      if (drop_p) {   // x' = dropout_2(w_2(dropout_1(gelu(.)))) + out   (neural.py:31-33)
+        MSQ_TRY(dropout_rows<float>(hfl, nullptr, M, 1, 0, 1, ff, make_drop(dc, DROP_PF1, (int)l, dc.p_para), st));
+        MSQ_TRY(g32(hfl, ff, L.w2.w32, L.w2.ld, L.w2.b, nullptr, 0, t.xo, H, M, H, ff, ACT_NONE, st));
+        MSQ_TRY(dropout_add(t.xo, t.out, M * H, make_drop(dc, DROP_PF2, (int)l, dc.p_para), st));
+      } else {
+        MSQ_TRY(g32(hfl, ff, L.w2.w32, L.w2.ld, L.w2.b, t.out, H, t.xo, H, M, H, ff, ACT_NONE, st));
+      }
       xin = t.xo;
     }
     MSQ_TRY(layernorm<float>(xin, M, H, m->para_ln.g, m->para_ln.b, 1e-6f, h.para, nullptr, 0, 0, 0, st));
@@ -794,17 +821,30 @@ int heads_train(msq_model* m, const int64_t* sep, int64_t B, int N, const int32_
       ParaTape& t = h.pl[li];
       auto& WT = ts->paraT[li];
       const std::string bn = "encoder.transformer_inter." + std::to_string(li) + ".";
-      MSQ_TRY(wgrad<float>(m, gx, H, H, t.u, ff, ff, ACT_GELU_TANH, M, G(bn + "feed_forward.w_2.weight"), G(bn + "feed_forward.w_2.bias"), bb, st));
-      MSQ_TRY((dgrad<float, float>(m, gx, H, WT[3], ff, nullptr, gu, M, st)));
+      if (drop_p) {
+        // gx = d(x'): the w_2 output sees gx . mask_2; its input was the DROPPED activation (kept in t.hf)
+        MSQ_TRY(dropout_mask_copy<float>(gx, gm, M * H, make_drop(dc, DROP_PF2, (int)li, dc.p_para), st));
+        MSQ_TRY(wgrad<float>(m, gm, H, H, t.hf, ff, ff, ACT_NONE, M, G(bn + "feed_forward.w_2.weight"), G(bn + "feed_forward.w_2.bias"), bb, st));
+        MSQ_TRY((dgrad<float, float>(m, gm, H, WT[3], ff, nullptr, gu, M, st)));
+        MSQ_TRY(dropout_rows<float>(gu, nullptr, M, 1, 0, 1, ff, make_drop(dc, DROP_PF1, (int)li, dc.p_para), st));
+      } else {
+        MSQ_TRY(wgrad<float>(m, gx, H, H, t.u, ff, ff, ACT_GELU_TANH, M, G(bn + "feed_forward.w_2.weight"), G(bn + "feed_forward.w_2.bias"), bb, st));
+        MSQ_TRY((dgrad<float, float>(m, gx, H, WT[3], ff, nullptr, gu, M, st)));
+      }
       MSQ_TRY(act_bwd<float>(gu, t.u, M * ff, ACT_GELU_TANH, gu, st));
       MSQ_TRY(wgrad<float>(m, gu, ff, ff, t.pn, H, H, ACT_NONE, M, G(bn + "feed_forward.w_1.weight"), G(bn + "feed_forward.w_1.bias"), bb, st));
       MSQ_TRY((dgrad<float, float>(m, gu, ff, WT[2], H, nullptr, gy, M, st)));
       MSQ_TRY(ln_bwd<float>(gy, t.out, gx, M, H, L.ln_ff.g, 1e-6f, gx, nullptr, G(bn + "feed_forward.layer_norm.weight"),
                             G(bn + "feed_forward.layer_norm.bias"), ln_scr, 0, 0, 0, st));                        // gx = d(out)
-      MSQ_TRY(wgrad<float>(m, gx, H, H, t.ctx, H, H, ACT_NONE, M, G(bn + "self_attn.final_linear.weight"), G(bn + "self_attn.final_linear.bias"), bb, st));
-      MSQ_TRY((dgrad<float, float>(m, gx, H, WT[1], H, nullptr, gy, M, st)));                                      // d(ctx)
+      const float* gfin = gx;   // gradient at the final_linear output: d(out) . mask under dropout
+      if (drop_p) {
+        MSQ_TRY(dropout_mask_copy<float>(gx, gm, M * H, make_drop(dc, DROP_PC, (int)li, dc.p_para), st));
+        gfin = gm;
+      }
+      MSQ_TRY(wgrad<float>(m, gfin, H, H, t.ctx, H, H, ACT_NONE, M, G(bn + "self_attn.final_linear.weight"), G(bn + "self_attn.final_linear.bias"), bb, st));
+      MSQ_TRY((dgrad<float, float>(m, gfin, H, WT[1], H, nullptr, gy, M, st)));                                    // d(ctx)
       MSQ_CUDA(launch_k(para_attention_bwd_kernel, dim3((unsigned)(B * c.para_heads)), dim3(128), 0, st, (const float*)t.qkv, (const float*)gy, N,
-                        (int)c.para_heads, H, gq));
+                        (int)c.para_heads, H, gq, make_drop(dc, DROP_PA, (int)li, dc.p_para)));
       MSQ_LAUNCH_CHECK();
       const float* y = li == 0 ? t.xin : t.y;
       MSQ_TRY(wgrad<float>(m, gq, 3 * H, 3 * H, y, H, H, ACT_NONE, M, G(bn + "self_attn.linear_query.weight"), G(bn + "self_attn.linear_query.bias"), bb, st));
@@ -824,7 +864,7 @@ int heads_train(msq_model* m, const int64_t* sep, int64_t B, int N, const int32_
   MSQ_LAUNCH_CHECK();
   MSQ_TRY(partial_reduce(part, (int)M, H, 0, H, G("two_level_encoder.linear_in_2.weight"), st));
   MSQ_CUDA(launch_k(token_pool_bwd_kernel<T>, dim3((unsigned)R), dim3(256), 3 * Lt * sizeof(float), st, (const T*)h.ttb, x, Lt, Lj, H, m->w2, m->b2, sep,
-                    (const float*)dmix, h.d_lang, dscore));
+                    (const float*)dmix, h.d_lang, dscore, make_drop(dc, DROP_H, 0, dc.p_hidden)));
   MSQ_LAUNCH_CHECK();
   const float lam_scale = lam / (((float)P + 1e-20f) * (float)B);
   MSQ_CUDA(launch_k(cls_rel_bwd_kernel, dim3((unsigned)R), dim3(256), 0, st, (const float*)dr0, Kp, (const float*)h.rel6, pair_labels, m->w_rel, N, Lt, H,

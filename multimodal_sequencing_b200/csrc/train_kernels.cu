@@ -8,6 +8,7 @@
 // activation backward, attention backward (fp32 CUDA cores, two kernels: dQ then dK/dV), embedding / token-assembly
 // scatter, gradient norm + HF-AdamW update.
 #include "kernels.cuh"
+#include "dropout.cuh"
 
 namespace msq {
 
@@ -539,7 +540,7 @@ template <typename T>
 __global__ void __launch_bounds__(AB_WARPS * 32) attention_bwd_dq_kernel(const T* __restrict__ qkv, const T* __restrict__ dctx, int L,
                                                                          int heads, float scale, const float* __restrict__ mask_add,
                                                                          int mask_ld, int mask_len, T* __restrict__ dqkv,
-                                                                         float* __restrict__ lse_out, float* __restrict__ dsum_out) {
+                                                                         float* __restrict__ lse_out, float* __restrict__ dsum_out, Drop drop) {
   pdl_sync();
   extern __shared__ __align__(16) float sm[];
   const int r = blockIdx.x / heads, h = blockIdx.x % heads;
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32) attention_bwd_dq_kernel(const T
 #pragma unroll 16
           for (int d = 0; d < AB_D; ++d) { a = fmaf(q[d], kr[d], a); b = fmaf(g[d], vr[d], b); }
           s = a * scale + Ms[key];
-          dpv[c] = b;
+          dpv[c] = b * drop_mul(drop, ((uint64_t)blockIdx.x * L + t) * L + key);   // dP = (dO V^T) . mask
         }
         p[key] = s;
         mx = fmaxf(mx, s);
@@ -638,7 +639,7 @@ template <typename T>
 __global__ void __launch_bounds__(AB_WARPS * 32) attention_bwd_dkv_kernel(const T* __restrict__ qkv, const T* __restrict__ dctx, int L,
                                                                           int heads, float scale, const float* __restrict__ mask_add,
                                                                           int mask_ld, int mask_len, T* __restrict__ dqkv,
-                                                                          const float* __restrict__ lse_in, const float* __restrict__ dsum_in) {
+                                                                          const float* __restrict__ lse_in, const float* __restrict__ dsum_in, Drop drop) {
   pdl_sync();
   extern __shared__ __align__(16) float sm[];
   const int r = blockIdx.x / heads, h = blockIdx.x % heads;
@@ -684,7 +685,9 @@ __global__ void __launch_bounds__(AB_WARPS * 32) attention_bwd_dkv_kernel(const 
 #pragma unroll 16
         for (int d = 0; d < AB_D; ++d) { a = fmaf(qr[d], k[d], a); b = fmaf(gr[d], v[d], b); }
         pr = expf(a * scale + mj - Ls[i]);
-        ds = pr * (b - Ds[i]);
+        const float dm = drop_mul(drop, ((uint64_t)blockIdx.x * L + i) * L + j);
+        ds = pr * (b * dm - Ds[i]);
+        pr *= dm;                                   // dV = (P . mask)^T dO
       }
       p[i] = pr;
       s[i] = ds;
@@ -711,7 +714,7 @@ size_t attention_bwd_scratch_floats(int64_t R, int L, int heads) { return (size_
 
 template <typename T>
 int attention_bwd(const T* qkv, const T* dctx, int64_t R, int L, int heads, float scale, const float* key_mask_add, int mask_ld,
-                  int mask_len, T* dqkv, float* scratch, cudaStream_t st) {
+                  int mask_len, T* dqkv, float* scratch, cudaStream_t st, const Drop& drop) {
   MSQ_REQUIRE(L >= 1 && L <= 32 * AB_MAXCH, "attention_bwd: sequence length %d out of range", L);
   if (R == 0) return MSQ_OK;
   const int Lpad = (L + 31) & ~31;
@@ -721,14 +724,14 @@ int attention_bwd(const T* qkv, const T* dctx, int64_t R, int L, int heads, floa
   const size_t smem2 = sizeof(float) * ((size_t)2 * L * 65 + 2 * Lpad + 2 * AB_WARPS * AB_D + (size_t)2 * AB_WARPS * Lpad);
   MSQ_SMEM_ATTR(smem1, attention_bwd_dq_kernel<T>);
   MSQ_SMEM_ATTR(smem2, attention_bwd_dkv_kernel<T>);
-  MSQ_CUDA(launch_k(attention_bwd_dq_kernel<T>, dim3((unsigned)(R * heads)), dim3(AB_WARPS * 32), smem1, st, qkv, dctx, L, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, lse, dsum));
+  MSQ_CUDA(launch_k(attention_bwd_dq_kernel<T>, dim3((unsigned)(R * heads)), dim3(AB_WARPS * 32), smem1, st, qkv, dctx, L, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, lse, dsum, drop));
   MSQ_LAUNCH_CHECK();
-  MSQ_CUDA(launch_k(attention_bwd_dkv_kernel<T>, dim3((unsigned)(R * heads)), dim3(AB_WARPS * 32), smem2, st, qkv, dctx, L, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, (const float*)lse, (const float*)dsum));
+  MSQ_CUDA(launch_k(attention_bwd_dkv_kernel<T>, dim3((unsigned)(R * heads)), dim3(AB_WARPS * 32), smem2, st, qkv, dctx, L, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, (const float*)lse, (const float*)dsum, drop));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
-template int attention_bwd<float>(const float*, const float*, int64_t, int, int, float, const float*, int, int, float*, float*, cudaStream_t);
-template int attention_bwd<bf16>(const bf16*, const bf16*, int64_t, int, int, float, const float*, int, int, bf16*, float*, cudaStream_t);
+template int attention_bwd<float>(const float*, const float*, int64_t, int, int, float, const float*, int, int, float*, float*, cudaStream_t, const Drop&);
+template int attention_bwd<bf16>(const bf16*, const bf16*, int64_t, int, int, float, const float*, int, int, bf16*, float*, cudaStream_t, const Drop&);
 
 // dW[i] += sum_s part[s, i]   (split-K partial sums of a weight gradient, added in slice order)
 __global__ void __launch_bounds__(256) splitk_accumulate_kernel(const float* __restrict__ part, int S, int64_t n4, float* __restrict__ dW) {
@@ -879,5 +882,78 @@ int adamw_update(float* p, const float* g, float* m, float* v, int64_t n, float 
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
+
+
+// ---- dropout (dropout.cuh): elementwise sites.  Masks are regenerated from (key, element index), never stored. ------------
+// rows [off, off + n) of every group of `group` rows of a [*, H] buffer; the mask index runs over the [R, n, H] tensor the
+// reference's nn.Dropout sees.  In place on the fp32 buffer; xt (optional) receives the operand-type copy.
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_rows_kernel(float* __restrict__ xf, T* __restrict__ xt, int64_t R, int group, int off, int n,
+                                                           int H, Drop d) {
+  pdl_sync();
+  const int64_t total4 = R * n * (int64_t)(H / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / (H / 4);
+    const int c = (int)(i % (H / 4)) * 4;
+    const int64_t r = row / n;
+    const int t = (int)(row % n);
+    const int64_t brow = r * group + off + t;
+    float4 v = *reinterpret_cast<const float4*>(xf + brow * H + c);
+    const uint64_t idx = (uint64_t)row * H + c;
+    v.x *= drop_mul(d, idx); v.y *= drop_mul(d, idx + 1); v.z *= drop_mul(d, idx + 2); v.w *= drop_mul(d, idx + 3);
+    *reinterpret_cast<float4*>(xf + brow * H + c) = v;
+    if (xt) Vec4<T>::store(xt + brow * H + c, v);
+  }
+}
+template <typename T>
+int dropout_rows(float* xf, T* xt, int64_t R, int group, int off, int n, int H, const Drop& d, cudaStream_t st) {
+  if (d.thresh == 0 || R * n == 0) return MSQ_OK;
+  const int64_t total4 = R * n * (int64_t)(H / 4);
+  MSQ_CUDA(launch_k(dropout_rows_kernel<T>, dim3((unsigned)min((int64_t)148 * 16, (total4 + 255) / 256)), dim3(256), 0, st, xf, xt, R, group, off, n, H, d));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+template int dropout_rows<float>(float*, float*, int64_t, int, int, int, int, const Drop&, cudaStream_t);
+template int dropout_rows<bf16>(float*, bf16*, int64_t, int, int, int, int, const Drop&, cudaStream_t);
+
+// s <- dropout(s) + resid   (s = dense(x) + bias of a residual sub-layer; lxrt/modeling.py:436-438, 490-492)
+__global__ void __launch_bounds__(256) dropout_add_kernel(float* __restrict__ s, const float* __restrict__ resid, int64_t n4, Drop d) {
+  pdl_sync();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(s)[i];
+    const float4 r = resid ? reinterpret_cast<const float4*>(resid)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint64_t idx = (uint64_t)i * 4;
+    v.x = fmaf(v.x, drop_mul(d, idx), r.x); v.y = fmaf(v.y, drop_mul(d, idx + 1), r.y);
+    v.z = fmaf(v.z, drop_mul(d, idx + 2), r.z); v.w = fmaf(v.w, drop_mul(d, idx + 3), r.w);
+    reinterpret_cast<float4*>(s)[i] = v;
+  }
+}
+int dropout_add(float* s, const float* resid, int64_t n, const Drop& d, cudaStream_t st) {
+  if (n == 0) return MSQ_OK;
+  MSQ_CUDA(launch_k(dropout_add_kernel, dim3((unsigned)min((int64_t)148 * 16, (n / 4 + 255) / 256)), dim3(256), 0, st, s, resid, n / 4, d));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+
+// gt <- T(g * mask): the gradient of the dense output under dropout (the fp32 g stays the residual-branch gradient)
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_mask_copy_kernel(const float* __restrict__ g, T* __restrict__ gt, int64_t n4, Drop d) {
+  pdl_sync();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(g)[i];
+    const uint64_t idx = (uint64_t)i * 4;
+    v.x *= drop_mul(d, idx); v.y *= drop_mul(d, idx + 1); v.z *= drop_mul(d, idx + 2); v.w *= drop_mul(d, idx + 3);
+    Vec4<T>::store(gt + i * 4, v);
+  }
+}
+template <typename T>
+int dropout_mask_copy(const float* g, T* gt, int64_t n, const Drop& d, cudaStream_t st) {
+  if (d.thresh == 0 || n == 0) return MSQ_OK;
+  MSQ_CUDA(launch_k(dropout_mask_copy_kernel<T>, dim3((unsigned)min((int64_t)148 * 16, (n / 4 + 255) / 256)), dim3(256), 0, st, g, gt, n / 4, d));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+template int dropout_mask_copy<float>(const float*, float*, int64_t, const Drop&, cudaStream_t);
+template int dropout_mask_copy<bf16>(const float*, bf16*, int64_t, const Drop&, cudaStream_t);
 
 }  // namespace msq

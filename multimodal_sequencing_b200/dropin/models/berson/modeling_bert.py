@@ -335,12 +335,21 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
         return PairBatch(input_ids, attention_mask, token_type_ids, sep_positions, pairs_list, pairwise_labels, ground_truth,
                          int(passage_length[0]), img, idx)
 
+    def _apply_dropout_config(self, eng):
+        """train(): the reference's dropout probabilities (BertConfig.hidden_dropout_prob / attention_probs_dropout_prob of the
+        INNER model's config, args.para_dropout for the paragraph encoder), seeded from torch's RNG seed once per engine."""
+        inner_cfg = getattr(self.bert, "config", self.config)
+        probs = (float(getattr(inner_cfg, "hidden_dropout_prob", 0.0) or 0.0),
+                 float(getattr(inner_cfg, "attention_probs_dropout_prob", 0.0) or 0.0),
+                 float(getattr(self.args, "para_dropout", 0.0) or 0.0))
+        key = (id(eng), probs)
+        if self.__dict__.get("_drop_key") != key:
+            eng.set_dropout(*probs, seed=torch.initial_seed() & 0xFFFFFFFF)
+            self.__dict__["_drop_key"] = key
+
     def _train_forward(self, pb):
-        drop = max(getattr(self.config, "hidden_dropout_prob", 0.0) or 0.0, getattr(self.args, "para_dropout", 0.0) or 0.0)
-        if drop > 0 and not self.__dict__.get("_warned_dropout"):
-            warnings.warn("multimodal_sequencing_b200: dropout is not applied in training (p = 0 semantics)")
-            self.__dict__["_warned_dropout"] = True
         eng = self.engine()
+        self._apply_dropout_config(eng)
         flat = eng.new_grad_buffer()
         with torch.no_grad():
             loss = eng.train_step(pb, flat, self.pairwise_loss_lam)
@@ -365,6 +374,7 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
                               b["passage_length"], b.get("sep_positions"), b.get("ground_truth"), b.get("pairwise_labels"),
                               b.get("images"), b.get("_pair_batch"))
         eng = self.engine()
+        self._apply_dropout_config(eng)
         flat = self.__dict__.get("_flat")
         if flat is None or flat.device != eng.device or flat.numel() != eng.new_grad_buffer().numel():
             flat = self.__dict__["_flat"] = eng.new_grad_buffer()

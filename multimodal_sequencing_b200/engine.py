@@ -368,6 +368,17 @@ class OrderingEngine:
         _lib.check(self.lib.msq_train_read_param(self._h, name.encode(), self._p(out), out.numel(), self._stream()))
         return out
 
+    def set_dropout(self, p_hidden=0.1, p_attn=0.1, p_para=0.1, seed=0):
+        """Training-mode dropout for every later train_step / inner_forward_train (the reference's defaults are 0.1 each:
+        BertConfig.hidden_dropout_prob / attention_probs_dropout_prob, args.para_dropout).  0 switches a family off."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.msq_train_set_dropout(self._h, float(p_hidden), float(p_attn), float(p_para), int(seed) & 0xFFFFFFFF,
+                                                      self._stream()))
+
+    def dropout_step(self):
+        """counter that keyed the masks of the last training forward (-1: none yet); what oracle.dropout.DropSpec needs"""
+        return int(self.lib.msq_train_dropout_step(self._h))
+
     def train_step(self, batch: PairBatch, grads, lam=0.6):
         """One fine-tuning forward + backward of BertForOrdering._forward's default objective (modeling_bert.py:943-1174:
         pointer NLL / (N-1) + lam * pairwise NLL / P, batch mean): grads += dL/dparam for every parameter of the path

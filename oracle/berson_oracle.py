@@ -127,12 +127,26 @@ def prepare_inputs(input_ids, labels, n_steps, images=None, cls_id=101, sep_id=1
 # --------------------------------------------------------------------------------------------
 
 
+# training-mode dropout: None (eval) or an oracle.dropout.DropSpec -- a callable (x, kind, layer) -> x with the elements of
+# that site dropped and the rest scaled by 1/(1-p).  Set by oracle.train_oracle around a training forward.
+DROPOUT = None
+
+
+def _drop(x, kind, layer=0):
+    return x if DROPOUT is None else DROPOUT(x, kind, layer)
+
+
+def _layer_index(pre):
+    """'...encoder.layer.7.' / '...transformer_inter.1.' -> 7 / 1"""
+    return int(pre.rstrip(".").rsplit(".", 1)[1])
+
+
 def bert_embeddings(sd, pre, ids, tt, eps=1e-12):
     """lxrt/modeling.py:342-370 == models/berson/modeling_bert.py:148-180 (eval: dropout off)."""
     L = ids.shape[1]
     e = sd[pre + "word_embeddings.weight"][ids] + sd[pre + "position_embeddings.weight"][:L][None] \
         + sd[pre + "token_type_embeddings.weight"][tt]
-    return _ln(sd, pre + "LayerNorm", e, eps)
+    return _drop(_ln(sd, pre + "LayerNorm", e, eps), "E")
 
 
 def _heads(x, h):
@@ -150,11 +164,12 @@ def bert_layer(sd, pre, x, add_mask, heads, eps=1e-12, lxrt=True):
     s = q @ k.transpose(-1, -2) / math.sqrt(q.shape[-1])
     if add_mask is not None:
         s = s + add_mask
-    p = torch.softmax(s, dim=-1)
+    li = _layer_index(pre) if DROPOUT is not None else 0
+    p = _drop(torch.softmax(s, dim=-1), "A", li)
     c = (p @ v).permute(0, 2, 1, 3).reshape(x.shape)
-    x1 = _ln(sd, a + "output.LayerNorm", _lin(sd, a + "output.dense", c) + x, eps)
+    x1 = _ln(sd, a + "output.LayerNorm", _drop(_lin(sd, a + "output.dense", c), "O", li) + x, eps)
     inter = gelu_erf(_lin(sd, pre + "intermediate.dense", x1))
-    return _ln(sd, pre + "output.LayerNorm", _lin(sd, pre + "output.dense", inter) + x1, eps)
+    return _ln(sd, pre + "output.LayerNorm", _drop(_lin(sd, pre + "output.dense", inter), "F", li) + x1, eps)
 
 
 def ext_mask(attention_mask):
@@ -220,7 +235,7 @@ def lxrt_forward(sd, cfg, ids, tt, attention_mask, images, pre="bert."):
     Returns (lang [R,Lt,H], visn [R,Lv,H], pooled [R,H])."""
     emb = bert_embeddings(sd, pre + "embeddings.", ids, tt, 1e-12)
     tower = vit_pair_tower(sd, pre + "encoder.visual_model.visual.", images, cfg["vit"])
-    v = _ln(sd, pre + "encoder.visn_fc.visn_layer_norm", _lin(sd, pre + "encoder.visn_fc.visn_fc", tower), 1e-12)
+    v = _drop(_ln(sd, pre + "encoder.visn_fc.visn_layer_norm", _lin(sd, pre + "encoder.visn_fc.visn_fc", tower), 1e-12), "V")
     R, Lt = ids.shape
     joint = torch.cat([emb, v], dim=1)
     m = torch.cat([ext_mask(attention_mask), torch.zeros(R, 1, 1, v.shape[1])], dim=-1)
@@ -249,7 +264,7 @@ def hierarchical_attention(sd, top_vec, cls, pairs_list, n_steps, sep_positions,
     m1 = ((pos > sep[:, 0:1]) & (pos <= sep[:, 1:2])).float()   # span1 = sep0+1..sep1 (712)
     sel = torch.stack([m0, m1], dim=1)                          # [R,2,L]
     att = sel * score[:, None, :] + (1.0 - sel) * -10000.0      # (722-731)
-    mix = torch.softmax(att, -1) @ top_vec                      # [R,2,H]
+    mix = _drop(torch.softmax(att, -1), "H") @ top_vec          # [R,2,H]  (attention-prob dropout, 735)
     mix = mix.reshape(B, P, 2, H)
     cls_score = _lin(sd, pre + "pairwise_relationship", cls)    # [R,2]
     his1 = _lin(sd, pre + "h1_relationship", cls)
@@ -293,11 +308,12 @@ def paragraph_encoder(sd, x, mask, heads=8, layers=2, pre="encoder."):
         k = _heads(_lin(sd, p + "self_attn.linear_keys", y), heads)
         v = _heads(_lin(sd, p + "self_attn.linear_values", y), heads)
         q = _heads(_lin(sd, p + "self_attn.linear_query", y), heads) / math.sqrt(d)
-        a = torch.softmax(q @ k.transpose(2, 3) + addm, -1)
+        a = _drop(torch.softmax(q @ k.transpose(2, 3) + addm, -1), "PA", i)
         c = (a @ v).transpose(1, 2).reshape(B, N, H)
-        out = _lin(sd, p + "self_attn.final_linear", c) + x
+        out = _drop(_lin(sd, p + "self_attn.final_linear", c), "PC", i) + x
         f = p + "feed_forward."
-        x = _lin(sd, f + "w_2", gelu_tanh(_lin(sd, f + "w_1", _ln(sd, f + "layer_norm", out, 1e-6)))) + out
+        inter = _drop(gelu_tanh(_lin(sd, f + "w_1", _ln(sd, f + "layer_norm", out, 1e-6))), "PF1", i)
+        x = _drop(_lin(sd, f + "w_2", inter), "PF2", i) + out
     return _ln(sd, pre + "layer_norm", x, 1e-6)
 
 

@@ -56,12 +56,17 @@ def inner_grads(sd, cfg, ids, tt, mask, images, g_lang, g_visn=None, pre="bert."
     return lang.detach(), (None if visn is None else visn.detach()), _padding_idx_rows(grads, pre, images is not None)
 
 
-def loss_grads(sd, cfg, inp, lam=0.6):
-    """(loss, {name: grad}) of BertForOrdering._forward's default objective (modeling_bert.py:943-1174)."""
+def loss_grads(sd, cfg, inp, lam=0.6, dropout=None):
+    """(loss, {name: grad}) of BertForOrdering._forward's default objective (modeling_bert.py:943-1174).
+    dropout: None (p = 0) or an oracle.dropout.DropSpec -- the training-mode forward with those masks."""
     leaf = _leaf_sd(sd)
-    with torch.enable_grad():
-        loss = O.training_loss(leaf, cfg, inp, lam)
-        loss.backward()
+    O.DROPOUT = dropout
+    try:
+        with torch.enable_grad():
+            loss = O.training_loss(leaf, cfg, inp, lam)
+            loss.backward()
+    finally:
+        O.DROPOUT = None
     grads = {k: v.grad for k, v in leaf.items() if torch.is_tensor(v) and v.is_floating_point() and v.grad is not None}
     lxrt = (cfg.get("vit") is not None or cfg.get("rn") is not None) and inp.get("images") is not None
     grads = {k: v for k, v in grads.items() if "running_" not in k}   # BatchNorm buffers are not parameters

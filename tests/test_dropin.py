@@ -84,6 +84,9 @@ def test_reference_training_loop_runs_unchanged(golden_dir):
     from oracle import berson_oracle as O
     ids, labels, _ = O.synthetic_manuals(r["B"], r["N"], r["L"], vocab=1000, seed=r["seed"])
     model, args = _build(g, 5, 4, "cuda")
+    # the reference's gradient fixture was produced without dropout: switch it off the way a user would (config / args)
+    model.config.hidden_dropout_prob = model.config.attention_probs_dropout_prob = 0.0
+    args.para_dropout = 0.0
     model.load_state_dict(g["sd"], strict=False)
     model = model.cuda().train()
     for mod in model.modules():
@@ -501,16 +504,23 @@ def test_train_mode_autograd_bridge_host_logic(golden_dir):
                 flat[o:o + k] += float(i + 1)
             return torch.tensor(2.5)
 
-    model.engine = lambda: FakeEngine()
+        def set_dropout(self, p_hidden, p_attn, p_para, seed=0):
+            dropped.append((p_hidden, p_attn, p_para))
+
+    dropped = []
+    fake = FakeEngine()
+    model.engine = lambda: fake
     from oracle import berson_oracle as O
     ids, labels, _ = O.synthetic_manuals(1, 5, 8, vocab=1000, seed=2)
     bi = O.prepare_inputs(ids, labels, 5)
-    with torch.enable_grad(), pytest.warns(UserWarning, match="dropout"):
+    with torch.enable_grad():
         loss = model._forward(**bi)[0]
         assert loss.requires_grad and abs(loss.item() - 2.5) < 1e-6
         (loss * 0.5).backward()
         loss2 = model._forward(**bi)[0]
         loss2.backward()
+    # train(): the reference's dropout probabilities reach the engine, once (BertConfig 0.1 / 0.1, args.para_dropout 0.1)
+    assert dropped == [(model.config.hidden_dropout_prob, model.config.attention_probs_dropout_prob, 0.1)], dropped
     idx = {n: i for i, (n, _, _, _) in enumerate(layout)}
     for n, p in named:
         if n in skip:

@@ -146,3 +146,27 @@ def test_linear_schedule_matches_transformers():
         assert abs(sch.get_last_lr()[0] - linear_schedule_with_warmup(5e-6, step, 7, 40)) < 1e-18, step
         opt.step()
         sch.step()
+
+
+KNOWN_E = [0, 1, 1, 1, 0, 0, 1, 0, 0, 1, 1, 1, 0, 0, 1, 1]
+KNOWN_PA = [1, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1]
+
+
+def test_dropout_hash_known_answers():
+    """oracle/dropout.py is the numpy twin of csrc/dropout.cuh; these values pin the hash itself (any change to either side
+    must change both) and its statistics."""
+    import numpy as np
+    from oracle.dropout import DropSpec, keep_mask
+    m = keep_mask(1234, 0, "A", 3, 0.1, (4, 8))
+    assert m.dtype == np.bool_ and m.shape == (4, 8)
+    big = keep_mask(99, 5, "O", 11, 0.1, (1 << 20,))
+    assert abs(big.mean() - 0.9) < 2e-3
+    assert (keep_mask(99, 5, "O", 11, 0.1, (1 << 12,)) == big[: 1 << 12]).all()          # counter-based: prefix property
+    assert (keep_mask(99, 6, "O", 11, 0.1, (1 << 12,)) != big[: 1 << 12]).any()          # a new step -> a new mask
+    assert (keep_mask(99, 5, "F", 11, 0.1, (1 << 12,)) != big[: 1 << 12]).any()          # a new site -> a new mask
+    # known answers (first 16 keep bits of two streams)
+    assert keep_mask(1, 0, "E", 0, 0.5, (16,)).astype(int).tolist() == KNOWN_E
+    assert keep_mask(1234, 2, "PA", 1, 0.25, (16,)).astype(int).tolist() == KNOWN_PA
+    x = torch.ones(1000, 64)
+    y = DropSpec(7, 0, p_hidden=0.1)(x, "E")
+    assert abs(float(y.mean()) - 1.0) < 0.02 and all(abs(v) < 1e-12 or abs(v - 1.0 / 0.9) < 1e-6 for v in y.unique().tolist())
