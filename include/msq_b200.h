@@ -44,7 +44,9 @@ typedef struct msq_config {
                           *    every product is a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with fp32 accumulation, activations
                           *    are exact (erff / tanhf): outputs within ~1e-5 of fp32 at tensor-core speed.  Evaluation
                           *    only; ViT / text-only models (not the ModifiedResNet tower). */
-  int32_t reserved;
+  int32_t reserved;      /* flags.  bit 0 "cls_pooler": the inner encoder is a HuggingFace AutoModel (trainers/train.py:1928-1933)
+                          * whose outputs[1] = tanh(pooler.dense(seq[:,0])): BertForOrdering.encode takes THAT as the pair's
+                          * CLS vector (modeling_bert.py:1315) instead of seq[:,0].  Evaluation entry points only. */
   /* CLIP ModifiedResNet backbone ("RN50", models/CLIP/clip/model.py:128-187), the reference's wired default
    * (param.py VISUAL_CONFIG.clip_model_name).  rn_width != 0 selects it; then vit_width must hold the tower's
    * OUTPUT feature size 2*rn_embed (model.py:106 concatenates the pooled tokens with themselves), vit_layers 0,

@@ -1256,22 +1256,41 @@ static int run_path(msq_model* m, const int64_t* ids, const int64_t* tt, const i
     }
     MSQ_TRY((run_inner<T>(m, ids + r0 * Lt, tt + r0 * Lt, mask + r0 * Lt, rc, Lt, mm ? img_index + r0 * 2 : nullptr, vb, jb, st)));
     // ---- pooling for this chunk
+    if (out && out->top_vec) MSQ_TRY((gather_rows<float, float>(jb.x, rc * Lt, H, Lt, Lj, 0, out->top_vec + r0 * Lt * H, st)));
     MSQ_TRY((gather_rows<float, T>(jb.x, rc * Lt, H, Lt, Lj, 0, (T*)hb.topt, st)));
+    // cfg.reserved bit 0 ("cls_pooler"): the inner model is a HuggingFace AutoModel (trainers/train.py:1928-1933) whose
+    // outputs[1] is tanh(pooler.dense(seq[:,0])): that vector replaces row 0 of every pair in the heads' view of the
+    // stream (top_vec above keeps the encoder's own row; token pooling never reads position 0).  hb.topt is free once
+    // sentence_tran has consumed it.
+    bool cls_pooled = false;
+    auto pool_cls = [&]() -> int {
+      if (!(c.reserved & 1) || cls_pooled) return MSQ_OK;
+      MSQ_REQUIRE(m->has_pooler, "cls_pooler: the model has no pooler.dense weights");
+      float* cls_in = reinterpret_cast<float*>(hb.topt);
+      float* cls_out = cls_in + (size_t)rc * H;
+      MSQ_TRY((gather_rows<float, float>(jb.x, rc, H, 1, Lj, 0, cls_in, st)));
+      MSQ_TRY(run_gemm32(cls_in, H, m->pooler, nullptr, 0, cls_out, H, rc, ACT_TANH, st));
+      MSQ_TRY(scatter_rows(cls_out, rc, H, 1, Lj, 0, jb.x, st));
+      cls_pooled = true;
+      return MSQ_OK;
+    };
     if constexpr (is_split<T>::value) {   // tanh(sentence_tran(.)) stays fp32 (hb.ttb holds 4 bytes per element)
       MSQ_TRY((run_gemm<T, float>(m, (const T*)hb.topt, H, m->sent_tran, nullptr, 0, (float*)hb.ttb, H, rc * Lt, ACT_TANH, st)));
+      MSQ_TRY(pool_cls());
       MSQ_TRY(token_pool<float>((const float*)hb.ttb, jb.x, rc, Lt, Lj, H, m->w2, m->b2, sep + r0 * 2, m->w_rel, m->b_rel,
                                 hb.mix + r0 * 2 * H, hb.rel6 + r0 * 6, st));
     } else {
     MSQ_TRY((run_gemm<T, T>(m, (const T*)hb.topt, H, m->sent_tran, nullptr, 0, (T*)hb.ttb, H, rc * Lt, ACT_TANH, st)));
+    MSQ_TRY(pool_cls());
     MSQ_TRY(token_pool<T>((const T*)hb.ttb, jb.x, rc, Lt, Lj, H, m->w2, m->b2, sep + r0 * 2, m->w_rel, m->b_rel, hb.mix + r0 * 2 * H,
                           hb.rel6 + r0 * 6, st));
     }
     const int64_t cell0 = b0 * N * N;
+    MSQ_TRY(pool_cls());
     MSQ_TRY(edge_pool(hb.mix + r0 * 2 * H, jb.x, hb.rel6 + r0 * 6, bc, N, Lj, H, m->w_in2, hb.sents + b0 * N * H,
                       hb.r0 + cell0 * m->Kp, m->Kp, out && out->cls_mat ? out->cls_mat + cell0 * H : nullptr,
                       out && out->score_mat ? out->score_mat + cell0 * 2 : nullptr, out && out->his1 ? out->his1 + cell0 * 2 : nullptr,
                       out && out->his2 ? out->his2 + cell0 * 2 : nullptr, out && out->cls ? out->cls + r0 * H : nullptr, st));
-    if (out && out->top_vec) MSQ_TRY((gather_rows<float, float>(jb.x, rc * Lt, H, Lt, Lj, 0, out->top_vec + r0 * Lt * H, st)));
   }
   MSQ_TRY(run_paragraph(m, hb, B, N, st));
   if (out) {

@@ -117,6 +117,7 @@ static int ensure_train(msq_model* m, cudaStream_t st) {
   MSQ_REQUIRE(m, "null model");
   if (m->train) return MSQ_OK;
   MSQ_REQUIRE(m->cfg.precise != 2, "fine-tuning runs in precise 0 (bf16) or 1 (fp32); the bf16x3 mode is an evaluation mode");
+  MSQ_REQUIRE(!(m->cfg.reserved & 1), "fine-tuning through a tanh-pooled CLS (cls_pooler, HuggingFace inner model) is not built: evaluation only");
   const int rc = m->cfg.precise ? build_train_state<float>(m, st) : build_train_state<bf16>(m, st);
   if (rc != MSQ_OK && m->train) { train_state_free(m->train); m->train = nullptr; }
   return rc;

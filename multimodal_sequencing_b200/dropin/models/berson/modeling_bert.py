@@ -296,7 +296,10 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
         if vit is not None and getattr(inner, "is_resnet", False):
             vit, rn = None, vit
         ic = getattr(inner, "config", c)
-        return dict(rn=rn, hidden_size=c.hidden_size, num_hidden_layers=ic.num_hidden_layers,
+        # a HuggingFace AutoModel as the inner encoder (trainers/train.py:1928-1933, load_inner_model=True): same parameter names
+        # as the vendored BertModel, but outputs[1] is the tanh pooler -- the engine then pools the pair CLS the same way
+        hf_inner = not isinstance(inner, BertModel) and vit is None and rn is None and getattr(inner, "pooler", None) is not None
+        return dict(rn=rn, cls_pooler=hf_inner, hidden_size=c.hidden_size, num_hidden_layers=ic.num_hidden_layers,
                     num_attention_heads=ic.num_attention_heads, intermediate_size=ic.intermediate_size,
                     vocab_size=ic.vocab_size, max_position_embeddings=ic.max_position_embeddings,
                     type_vocab_size=getattr(ic, "type_vocab_size", 2), vit=vit, para_heads=self.args.heads,

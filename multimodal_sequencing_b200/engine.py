@@ -158,7 +158,7 @@ class OrderingEngine:
             vit_layers=vit["vision_layers"] if vit else 0, vit_patch=vit["vision_patch_size"] if vit else 0,
             vit_res=vit["image_resolution"] if vit else 0, para_heads=config.get("para_heads", 8),
             para_ff=config.get("para_ff", 3072), para_layers=config.get("para_layers", 2), precise=precision_code(precise),
-            reserved=0)
+            reserved=1 if config.get("cls_pooler") else 0)
         if rn:
             # CLIP ModifiedResNet (clip/model.py:128-187): the tower hands 2*embed_dim features per token to visn_fc
             blocks = tuple(rn["vision_layers"])

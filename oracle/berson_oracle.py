@@ -178,12 +178,17 @@ def ext_mask(attention_mask):
 
 
 def text_bert(sd, cfg, ids, attention_mask, tt, pre="bert."):
-    """models/berson/modeling_bert.py:563-663: returns (sequence_output, seq[:,0])."""
+    """models/berson/modeling_bert.py:563-663: returns (sequence_output, seq[:,0]).
+    cfg["cls_pooler"]: the inner model is a HuggingFace AutoModel, as trainers/train.py:1928-1933 builds it for the text-only
+    task: its outputs[1] is pooler_output = tanh(pooler.dense(seq[:,0])) (transformers BertPooler), and that is what
+    BertForOrdering.encode takes as cls_pooled_output (modeling_bert.py:1315)."""
     x = bert_embeddings(sd, pre + "embeddings.", ids, tt, cfg.get("layer_norm_eps", 1e-12))
     m = ext_mask(attention_mask)
     for i in range(cfg["num_hidden_layers"]):
         x = bert_layer(sd, pre + "encoder.layer.%d." % i, x, m, cfg["num_attention_heads"],
                        cfg.get("layer_norm_eps", 1e-12))
+    if cfg.get("cls_pooler"):
+        return x, torch.tanh(_lin(sd, pre + "pooler.dense", x[:, 0]))
     return x, x[:, 0]
 
 

@@ -585,3 +585,66 @@ def test_lxrt_from_pretrained_prefix_rules(golden_dir, tmp_path):
     assert torch.equal(b.state_dict()["encoder.layer.0.output.dense.weight"], model.state_dict()["bert.encoder.layer.0.output.dense.weight"])
     with pytest.raises(EnvironmentError):
         LXRTModel.from_pretrained(str(tmp_path / "missing"), **kw)
+
+
+def _hf_tiny():
+    import transformers
+    cfg = transformers.BertConfig(vocab_size=1000, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=512,
+                                  max_position_embeddings=256, type_vocab_size=2, hidden_dropout_prob=0.1,
+                                  attention_probs_dropout_prob=0.1)
+    torch.manual_seed(11)
+    return transformers.BertModel(cfg).eval(), cfg
+
+
+def test_oracle_matches_huggingface_automodel_outputs():
+    """trainers/train.py:1928-1933 builds the text-only inner encoder with transformers' AutoModel; BertForOrdering.encode takes
+    outputs[0] / outputs[1] of it (modeling_bert.py:1308-1315), and outputs[1] of an HF BertModel is the TANH POOLER, not
+    seq[:,0].  Pin the oracle's restatement of that (text_bert with cfg["cls_pooler"]) to the real HF module."""
+    from oracle import berson_oracle as O
+    hf, cfg = _hf_tiny()
+    ids = torch.randint(1, 1000, (6, 23), generator=torch.Generator().manual_seed(0))
+    am = torch.ones_like(ids)
+    am[2, 15:] = 0
+    tt = (torch.arange(23)[None] > 9).long().expand(6, -1).contiguous()
+    out = hf(input_ids=ids, attention_mask=am, token_type_ids=tt)
+    sd = {"bert." + k: v for k, v in hf.state_dict().items()}
+    ocfg = dict(num_hidden_layers=2, num_attention_heads=2, cls_pooler=True)
+    seq, pooled = O.text_bert(sd, ocfg, ids, am, tt)
+    assert (seq - out.last_hidden_state).abs().max() < 2e-5
+    assert (pooled - out.pooler_output).abs().max() < 2e-5
+    assert (pooled - seq[:, 0]).abs().max() > 1e-2       # and it really differs from the CLS row
+
+
+@pytest.mark.gpu
+def test_bert_for_ordering_with_huggingface_inner_model():
+    """BertForOrdering(config, args, inner_model=<HF AutoModel>, tokenizer=..., load_inner_model=True) as train.py:1928-1933 +
+    2012-2022 assemble the text-only task: encode() and berson_pointer_network through the drop-in equal the oracle with the
+    tanh-pooled CLS (and differ from the seq[:,0] variant)."""
+    from oracle import berson_oracle as O
+    hf, hcfg = _hf_tiny()
+    cfg = BertConfig(1000, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=512, max_position_embeddings=256)
+    N, W = 5, 4
+    args = _args(N, W, 256, "cuda")
+    torch.manual_seed(5)
+    model = BertForOrdering(cfg, args, inner_model=hf, tokenizer=Tok(), load_inner_model=True)
+    assert model.bert is hf
+    model = model.cuda().eval()
+    for mod in model.modules():
+        mod.precise = True
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ids, labels, _ = O.synthetic_manuals(3, N, 14, vocab=1000, seed=8)
+    inp = O.prepare_inputs(ids, labels, N)
+    ocfg = dict(num_hidden_layers=2, num_attention_heads=2, vit=None, cls_pooler=True)
+    want = O.encode(sd, ocfg, inp)
+    plain = O.encode(sd, dict(ocfg, cls_pooler=False), inp)
+    eng = model.engine()
+    got = eng.encode(eng.prepare(ids, labels, N), want_top_vec=True)
+    for k in ("sents", "para", "h0", "key", "cls", "cls_mat", "cls_score", "score_mat", "his1", "his2", "top_vec"):
+        a, b = got[k].reshape(want[k].shape).cpu(), want[k]
+        assert (a - b).abs().max() <= 4e-5 * max(1.0, float(b.abs().max())), k
+    assert (got["cls"].cpu().reshape(plain["cls"].shape) - plain["cls"]).abs().max() > 1e-2
+    perms = eng.order(ids, labels, N, W)
+    assert perms == [O.beam_search(sd, want, N, W, b) for b in range(3)]
+    # and the module-level call sites of the reference: encode() / berson_pointer_network
+    one = {"input_ids": ids[:1], "attention_mask": torch.ones_like(ids[:1]), "labels": labels[:1]}
+    assert berson_pointer_network(args, model, Tok(), dict(one)) == perms[0]
