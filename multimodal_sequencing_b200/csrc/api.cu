@@ -268,12 +268,42 @@ __global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ 
     bf[n] = (b ? b[n] : 0.f) + c;
   }
 }
+// split-bf16 twin (bf16x3 mode): wf row = [hi(K) | lo(K)] of gamma_k w[n,k]; svec[n] = sum_k (hi + lo)
+__global__ void __launch_bounds__(256) fold_ln_split_kernel(const float* __restrict__ w, int ldw, const float* __restrict__ b,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta, int K,
+                                                            bf16* __restrict__ wf, float* __restrict__ svec, float* __restrict__ bf) {
+  pdl_sync();
+  __shared__ float sh[2][8];
+  const int n = blockIdx.x;
+  float s = 0.f, t = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float wv = w[(int64_t)n * ldw + k];
+    const float gw = gamma[k] * wv;
+    const bf16 hi = __float2bfloat16_rn(gw);
+    const bf16 lo = __float2bfloat16_rn(gw - __bfloat162float(hi));
+    wf[(int64_t)n * 2 * K + k] = hi;
+    wf[(int64_t)n * 2 * K + K + k] = lo;
+    s += __bfloat162float(hi) + __bfloat162float(lo);
+    t = fmaf(beta[k], wv, t);
+  }
+  s = warp_sum(s); t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = t; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int i = 0; i < 8; ++i) { a += sh[0][i]; c += sh[1][i]; }
+    svec[n] = a;
+    bf[n] = (b ? b[n] : 0.f) + c;
+  }
+}
 static int make_folded(msq_model* m, const Lin& src, const LNp& ln, LinF* out, cudaStream_t st) {
   bf16* wf; float *sv, *bf;
-  MSQ_TRY(dev_alloc(m, (size_t)src.N * src.K, &wf));
+  const bool split = m->cfg.precise == 2;
+  MSQ_TRY(dev_alloc(m, (size_t)src.N * src.K * (split ? 2 : 1), &wf));
   MSQ_TRY(dev_alloc(m, (size_t)src.N, &sv));
   MSQ_TRY(dev_alloc(m, (size_t)src.N, &bf));
-  MSQ_CUDA(launch_k(fold_ln_kernel, dim3(src.N), dim3(256), 0, st, src.w32, src.ld, src.b, ln.g, ln.b, src.K, wf, sv, bf));
+  if (split) MSQ_CUDA(launch_k(fold_ln_split_kernel, dim3(src.N), dim3(256), 0, st, src.w32, src.ld, src.b, ln.g, ln.b, src.K, wf, sv, bf));
+  else MSQ_CUDA(launch_k(fold_ln_kernel, dim3(src.N), dim3(256), 0, st, src.w32, src.ld, src.b, ln.g, ln.b, src.K, wf, sv, bf));
   MSQ_LAUNCH_CHECK();
   out->lin = src; out->lin.w32 = nullptr; out->lin.w16 = wf; out->lin.b = bf; out->lin.ld = src.K; out->svec = sv;
   return MSQ_OK;
@@ -330,18 +360,22 @@ static bool ln_fold_enabled(const msq_model* m) {
 struct LnPending { const float* stats = nullptr; int sp = 0; LNp ln; float eps = 0.f; int dim = 0; };
 
 // C = act(LN_pending(Y) W^T + b) computed from the bf16 copy of the raw stream
+// (split: Yt and the folded weight are split-bf16 rows, bf16x3 mode)
 template <typename TO>
-static int run_gemm_fold(const bf16* Yt, int lda, const LinF& w, const LnPending& ln, TO* C, int ldc, int64_t M, int act, cudaStream_t st) {
+static int run_gemm_fold(const void* Yt, int lda, const LinF& w, const LnPending& ln, TO* C, int ldc, int64_t M, int act, cudaStream_t st,
+                         bool split = false) {
   GemmArgs g;
+  g.split = split ? 1 : 0;
   g.A = Yt; g.W = w.lin.w16; g.bias = w.lin.b; g.resid = nullptr; g.C = C; g.C2 = nullptr;
   g.M = M; g.N = w.lin.N; g.K = w.lin.K; g.lda = lda; g.ldw = w.lin.ld; g.ldc = ldc; g.ldr = 0; g.act = act;
   g.mode = EPI_LNFOLD; g.svec = w.svec; g.stats_in = ln.stats; g.sp_in = ln.sp; g.ln_inv_dim = 1.0f / (float)ln.dim; g.ln_eps = ln.eps;
   return gemm_tc<TO>(g, st);
 }
 // Y <- A W^T + b + (ln ? LN_pending(Y) : Y) in place, plus its bf16 copy Yt and the partial row sums of the new Y
-static int run_gemm_resln(const bf16* A, int lda, const Lin& w, float* Y, bf16* Yt, const LnPending* ln, float* stats_out, int64_t M,
-                          cudaStream_t st) {
+static int run_gemm_resln(const void* A, int lda, const Lin& w, float* Y, void* Yt, const LnPending* ln, float* stats_out, int64_t M,
+                          cudaStream_t st, bool split = false) {
   GemmArgs g;
+  g.split = split ? 1 : 0;
   g.A = A; g.W = w.w16; g.bias = w.b; g.resid = Y; g.C = Y; g.C2 = nullptr;
   g.M = M; g.N = w.N; g.K = w.K; g.lda = lda; g.ldw = w.ld; g.ldc = w.N; g.ldr = w.N; g.act = ACT_NONE;
   g.mode = EPI_RESLN; g.C2bf = Yt; g.stats_out = stats_out;
@@ -441,7 +475,7 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
   const msq_config& c = m->cfg;
   const int H = c.hidden;
   const bool w16 = c.precise != 1;
-  const bool fold = c.precise == 0;   // deferred-LayerNorm copies: plain bf16 tensor-core path only
+  const bool fold = c.precise != 1;   // deferred-LayerNorm copies: the tensor-core paths (bf16 and split-bf16)
   std::string miss;
   const std::string P = m->prefix_inner;
   auto W = [&](const std::string& n, int64_t numel) {
@@ -809,8 +843,9 @@ static int run_vit(msq_model* m, const int32_t* img_index, int64_t R, VitBufs& b
   const int64_t Mv = R * Lv;
   MSQ_TRY(vit_assemble(b.patch, img_index, R, 2, g2, Wd, m->vit_cls, m->vit_pos, m->ln_pre.g, m->ln_pre.b, 1e-5f, b.xv, st));
   b.post_pending = false;
-  if constexpr (same_type<T, bf16>::value) {
-    if (ln_fold_enabled(m) && m->folded && !m->vit.empty() && !gemm_ln_enabled()) {
+  if constexpr (!same_type<T, float>::value) {
+    constexpr bool SP = is_split<T>::value;
+    if (ln_fold_enabled(m) && m->folded && !m->vit.empty() && (SP || !gemm_ln_enabled())) {
       // Deferred LayerNorm: the residual stream x stays raw (fp32 b.xv + bf16 copy b.y + per-row partial sums written by
       // the residual GEMMs); ln_2 / the next ln_1 / ln_post are applied inside the consuming GEMMs' epilogues.
       const int sp = 2 * ceil_div(Wd, 256);
@@ -821,18 +856,20 @@ static int run_vit(msq_model* m, const int32_t* img_index, int64_t R, VitBufs& b
       for (size_t l = 0; l < nl; ++l) {
         VitLayerW& L = m->vit[l];
         if (l == 0) MSQ_TRY((run_gemm<T, T>(m, (const T*)b.y, Wd, L.qkv, nullptr, 0, (T*)b.qkv, 3 * Wd, Mv, ACT_NONE, st)));
-        else MSQ_TRY(run_gemm_fold<bf16>((const bf16*)b.y, Wd, L.qkv_f, pend, (bf16*)b.qkv, 3 * Wd, Mv, ACT_NONE, st));
+        else MSQ_TRY(run_gemm_fold<T>(b.y, Wd, L.qkv_f, pend, (T*)b.qkv, 3 * Wd, Mv, ACT_NONE, st, SP));
         MSQ_TRY(attention<T>((const T*)b.qkv, R, Lv, heads, 64, 0.125f, nullptr, 0, 0, (T*)b.ctx, st));
-        MSQ_TRY(run_gemm_resln((const bf16*)b.ctx, Wd, L.out, b.xv, (bf16*)b.y, nullptr, b.st[0], Mv, st));
+        MSQ_TRY(run_gemm_resln(b.ctx, Wd, L.out, b.xv, b.y, nullptr, b.st[0], Mv, st, SP));
         pend.stats = b.st[0]; pend.ln = L.ln2;
-        MSQ_TRY(run_gemm_fold<bf16>((const bf16*)b.y, Wd, L.fc_f, pend, (bf16*)b.hbuf, 4 * Wd, Mv, ACT_QUICK_GELU, st));
-        MSQ_TRY(run_gemm_resln((const bf16*)b.hbuf, 4 * Wd, L.proj, b.xv, (bf16*)b.y, nullptr, b.st[1], Mv, st));
+        MSQ_TRY(run_gemm_fold<T>(b.y, Wd, L.fc_f, pend, (T*)b.hbuf, 4 * Wd, Mv, ACT_QUICK_GELU, st, SP));
+        MSQ_TRY(run_gemm_resln(b.hbuf, 4 * Wd, L.proj, b.xv, b.y, nullptr, b.st[1], Mv, st, SP));
         pend.stats = b.st[1]; pend.ln = l + 1 < nl ? m->vit[l + 1].ln1 : m->ln_post;
       }
       b.post = pend;           // b.y is the RAW stream; ln_post is folded into visn_fc by the caller
       b.post_pending = true;
       return MSQ_OK;
     }
+  }
+  if constexpr (same_type<T, bf16>::value) {
     if (use_tc(m) && gemm_ln_enabled() && gemm_ln_supported(Wd, Wd) && gemm_ln_supported(Wd, 4 * Wd)) {
       // fused path: every residual GEMM also emits LayerNorm(x) (bf16) for the NEXT GEMM -- ln_2 after out_proj,
       // the next block's ln_1 (ln_post after the last block) after c_proj.  b.y ends up holding ln_post(x).
@@ -1037,13 +1074,14 @@ static int run_inner(msq_model* m, const int64_t* ids, const int64_t* tt, const 
     const int Wd = c.vit_width;
     const int64_t Mv = R * Lv;
     // vb.y == ln_post(x); visn_fc output reuses the (now free) fp32 tmp buffer of the joint stream
-    if (vb.post_pending) MSQ_TRY(run_gemm_fold<float>((const bf16*)vb.y, Wd, m->visn_fc_f, vb.post, jb.tmp, H, Mv, ACT_NONE, st));
+    if (vb.post_pending) MSQ_TRY(run_gemm_fold<float>(vb.y, Wd, m->visn_fc_f, vb.post, jb.tmp, H, Mv, ACT_NONE, st, is_split<T>::value));
     else MSQ_TRY((run_gemm<T, float>(m, (const T*)vb.y, Wd, m->visn_fc, nullptr, 0, jb.tmp, H, Mv, ACT_NONE, st)));
     MSQ_TRY(layernorm<T>(jb.tmp, Mv, H, m->visn_ln.g, m->visn_ln.b, 1e-12f, jb.x, (T*)jb.xt, Lv, Lj, Lt, st));
   }
   bool fused = false;
   if constexpr (same_type<T, bf16>::value) fused = use_tc(m) && gemm_ln_enabled() && gemm_ln_supported(H, H) && gemm_ln_supported(H, c.inter);
-  if constexpr (same_type<T, bf16>::value) {
+  if constexpr (!same_type<T, float>::value) {
+    constexpr bool SP = is_split<T>::value;
     if (ln_fold_enabled(m) && m->folded && !fused && !m->bert.empty()) {
       // Deferred LayerNorm through the post-LN BERT stack: jb.x / jb.xt hold the RAW sums (dense(...) + residual), the
       // LayerNorm after each sub-layer lives in the consumers: folded into the next QKV / intermediate GEMM and applied
@@ -1054,13 +1092,13 @@ static int run_inner(msq_model* m, const int64_t* ids, const int64_t* tt, const 
       bool have = false;
       int cur = 0;
       for (auto& L : m->bert) {
-        if (have) MSQ_TRY(run_gemm_fold<bf16>((const bf16*)jb.xt, H, L.qkv_f, pend, (bf16*)jb.qkv, 3 * H, Mj, ACT_NONE, st));
+        if (have) MSQ_TRY(run_gemm_fold<T>(jb.xt, H, L.qkv_f, pend, (T*)jb.qkv, 3 * H, Mj, ACT_NONE, st, SP));
         else MSQ_TRY((run_gemm<T, T>(m, (const T*)jb.xt, H, L.qkv, nullptr, 0, (T*)jb.qkv, 3 * H, Mj, ACT_NONE, st)));
         MSQ_TRY(attention<T>((const T*)jb.qkv, R, Lj, c.heads, 64, 0.125f, jb.mask_add, Lt, Lt, (T*)jb.ctx, st));
-        MSQ_TRY(run_gemm_resln((const bf16*)jb.ctx, H, L.out, jb.x, (bf16*)jb.xt, have ? &pend : nullptr, jb.st[cur ^ 1], Mj, st));
+        MSQ_TRY(run_gemm_resln(jb.ctx, H, L.out, jb.x, jb.xt, have ? &pend : nullptr, jb.st[cur ^ 1], Mj, st, SP));
         cur ^= 1; pend.stats = jb.st[cur]; pend.ln = L.ln1; have = true;
-        MSQ_TRY(run_gemm_fold<bf16>((const bf16*)jb.xt, H, L.up_f, pend, (bf16*)jb.hbuf, c.inter, Mj, ACT_GELU_ERF, st));
-        MSQ_TRY(run_gemm_resln((const bf16*)jb.hbuf, c.inter, L.down, jb.x, (bf16*)jb.xt, &pend, jb.st[cur ^ 1], Mj, st));
+        MSQ_TRY(run_gemm_fold<T>(jb.xt, H, L.up_f, pend, (T*)jb.hbuf, c.inter, Mj, ACT_GELU_ERF, st, SP));
+        MSQ_TRY(run_gemm_resln(jb.hbuf, c.inter, L.down, jb.x, jb.xt, &pend, jb.st[cur ^ 1], Mj, st, SP));
         cur ^= 1; pend.stats = jb.st[cur]; pend.ln = L.ln2;
       }
       MSQ_TRY(layernorm<T>(jb.x, Mj, H, pend.ln.g, pend.ln.b, 1e-12f, jb.tmp, (T*)jb.xt, 0, 0, 0, st));

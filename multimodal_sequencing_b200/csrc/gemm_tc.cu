@@ -30,14 +30,15 @@ constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_EPI_WARPS = 8, TC_THREADS = (2 + TC_EPI_WARPS) * 32;
 
+// MODE: 0 plain, 1 EPI_LNFOLD, 2 EPI_RESLN (bf16 copy), 3 EPI_RESLN with a SPLIT-bf16 copy (bf16x3 mode: hi and lo boxes)
 template <bool PAIR, int MODE = 0> struct TcCfg {
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = (PAIR && MODE == 3) ? 3 : 4;   // the second copy box costs 16 KB: one pipeline stage less
   // PAIR: the epilogue stages 32-row x 128-byte output boxes in shared memory (2 per warp) and writes
   // them with TMA bulk tensor stores (full-line, asynchronous) instead of per-thread 16-byte stores.
   static constexpr bool TMA_STORE = PAIR;
   static constexpr int STAGING_F32 = TMA_STORE ? TC_EPI_WARPS * 2 * 4096 : 0;
   // EPI_RESLN: one more box per warp for the bf16 copy, 32 rows x 32 columns (64-byte rows, 64B swizzle), stored every chunk
-  static constexpr int STAGING_BYTES = STAGING_F32 + ((TMA_STORE && MODE == 2) ? TC_EPI_WARPS * 2048 : 0);
+  static constexpr int STAGING_BYTES = STAGING_F32 + ((TMA_STORE && MODE >= 2) ? (MODE == 3 ? 2 : 1) * TC_EPI_WARPS * 2048 : 0);
   static constexpr int VECS = MODE == 0 ? 1 : (MODE == 1 ? 2 : 3);   // per-column vectors held per warp: bias | svec/gamma | beta
   static constexpr int B_ROWS = PAIR ? 128 : 256;            // rows of W staged per CTA and stage
   static constexpr int B_BYTES = B_ROWS * TC_BK * 2;
@@ -92,7 +93,7 @@ __device__ __forceinline__ void epi_compute8(float* v, const uint32_t* raw, cons
   }
   if (use_res) {
     float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-    if (MODE == 2 && has_ln) {
+    if (MODE >= 2 && has_ln) {
       const float4 g0 = *reinterpret_cast<const float4*>(s8), g1 = *reinterpret_cast<const float4*>(s8 + 4);
       const float4 e0 = *reinterpret_cast<const float4*>(beta8), e1 = *reinterpret_cast<const float4*>(beta8 + 4);
       const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bt[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
@@ -173,8 +174,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                const __grid_constant__ CUtensorMap tma_r, TcEpi ep, int num_m, int num_n, int num_k) {
   using Cfg = TcCfg<PAIR, MODE>;
   constexpr bool F32 = same_type<TO, float>::value, SPL = is_split<TO>::value;
-  static_assert(MODE != 2 || F32, "EPI_RESLN writes the fp32 stream (+ its bf16 copy)");
-  static_assert(!SPL || MODE == 0, "split-bf16 output: plain epilogue only");
+  static_assert(MODE < 2 || F32, "EPI_RESLN writes the fp32 stream (+ its bf16 / split-bf16 copy)");
+  static_assert(!SPL || MODE <= 1, "split-bf16 output: plain or LayerNorm-folded epilogue");
+  constexpr bool RESLN = MODE >= 2, C2SPL = MODE == 3;
   constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -196,8 +198,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
     if (Cfg::TMA_STORE) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_c) : "memory");
-    if (Cfg::TMA_STORE && MODE == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_c2) : "memory");
-    if (Cfg::TMA_STORE && MODE == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_r) : "memory");
+    if (Cfg::TMA_STORE && RESLN) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_c2) : "memory");
+    if (Cfg::TMA_STORE && RESLN) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_r) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, TC_EPI_WARPS * (PAIR ? 2 : 1)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -308,12 +310,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     float* svec_s = bias_s + TC_EPI_WARPS * 128;   // MODE 1: s_n; MODE 2: gamma of the LayerNorm pending on the residual
     float* beta_s = svec_s + TC_EPI_WARPS * 128;   // MODE 2: its beta
     const uint32_t stg = staging0 + (warp - 2) * 8192;  // this warp's two staging boxes
-    const uint32_t stg2 = staging0 + Cfg::STAGING_F32 + (warp - 2) * 2048;  // MODE 2: bf16 box (32 rows x 32 columns)
+    const uint32_t stg2 = staging0 + Cfg::STAGING_F32 + (warp - 2) * 2048;  // MODE 2 / 3: bf16 (hi) box (32 rows x 32 columns)
+    const uint32_t stg3 = stg2 + TC_EPI_WARPS * 2048;                        // MODE 3: lo box
     int stg_use = 0;                                       // boxes handed to the TMA so far (parity selects the buffer)
     // EPI_RESLN on CTA pairs: the residual chunk (32 rows x 32 fp32) is TMA-LOADED into the very staging box the output
     // chunk is stored from: full 128-byte lines and no registers held across the latency, instead of 16 bytes per row
     // per load instruction.  One chunk ahead; rk counts this warp's chunks (box rk&1, mbarrier parity (rk>>1)&1).
-    constexpr bool RES_TMA = MODE == 2 && Cfg::TMA_STORE;
+    constexpr bool RES_TMA = RESLN && Cfg::TMA_STORE;
     const uint32_t rbar = bars + 128 + (warp - 2) * 16;   // two 8-byte mbarriers per epilogue warp
     uint32_t rk = 0;
     auto issue_res = [&](int t, int ch, uint32_t k) {      // lane 0
@@ -369,11 +372,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (ep.bias && c < ep.N) b = __ldg(reinterpret_cast<const float4*>(ep.bias + c));
         float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), bt = sv;
         if (MODE >= 1 && ep.svec && c < ep.N) sv = __ldg(reinterpret_cast<const float4*>(ep.svec + c));
-        if (MODE == 2 && ep.beta && c < ep.N) bt = __ldg(reinterpret_cast<const float4*>(ep.beta + c));
+        if (RESLN && ep.beta && c < ep.N) bt = __ldg(reinterpret_cast<const float4*>(ep.beta + c));
         __syncwarp();
         *reinterpret_cast<float4*>(bias_s + lane * 4) = b;
         if (MODE >= 1) *reinterpret_cast<float4*>(svec_s + lane * 4) = sv;
-        if (MODE == 2) *reinterpret_cast<float4*>(beta_s + lane * 4) = bt;
+        if (RESLN) *reinterpret_cast<float4*>(beta_s + lane * 4) = bt;
         __syncwarp();
       }
       // pending LayerNorm of this row: ra = rstd, rc = -rstd * mean, from the partial sums of the producer
@@ -441,14 +444,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               epi_compute8<ACT, MODE>(v, raw + j * 8, bias_s + ch * 32 + j * 8, svec_s + ch * 32 + j * 8, beta_s + ch * 32 + j * 8, ra, rc,
                                       has_ln, use_res, res[2 * j], res[2 * j + 1], exact_act);
             }
-            if (MODE == 2) {
+            if (RESLN) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) { st_sum += v[i]; st_sq = fmaf(v[i], v[i], st_sq); }
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
               // 64-byte rows, 64B swizzle: 16-byte piece j of row r sits at r*64 + ((j ^ ((r >> 1) & 3)) << 4)
-              st_shared_v4(stg2 + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), *reinterpret_cast<uint32_t*>(&p0),
-                           *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+              const uint32_t o2 = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+              if (C2SPL) {
+                uint4 hi, lo;
+                epi_pack8_split(v, hi, lo);
+                st_shared_v4(stg2 + o2, hi.x, hi.y, hi.z, hi.w);
+                st_shared_v4(stg3 + o2, lo.x, lo.y, lo.z, lo.w);
+              } else {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+                st_shared_v4(stg2 + o2, *reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                             *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+              }
             }
             if (F32) {
               st_shared_v4(rowp + (((2 * j) ^ (lane & 7)) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
@@ -471,8 +482,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             __syncwarp();
             if (lane == 0) {
               const int box_col = F32 ? col0 : col0 - 32;
-              if (MODE == 2) {
-                if (col0 < ep.N) tma_store_2d(&tma_c2, stg2, col0, (int)(row - lane));
+              if (RESLN) {
+                if (col0 < ep.N) {
+                  tma_store_2d(&tma_c2, stg2, col0, (int)(row - lane));
+                  if (C2SPL) tma_store_2d(&tma_c2, stg3, ep.ldc + col0, (int)(row - lane));   // lo plane of the split copy
+                }
                 tma_store_commit();
               }
               if (box_col < ep.N) {
@@ -492,10 +506,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               float v[8];
               epi_compute8<ACT, MODE>(v, raw + j * 8, bias_s + ch * 32 + j * 8, svec_s + ch * 32 + j * 8, beta_s + ch * 32 + j * 8, ra, rc,
                                       has_ln, use_res, res[2 * j], res[2 * j + 1], exact_act);
-              if (MODE == 2) {
+              if (RESLN) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { st_sum += v[i]; st_sq = fmaf(v[i], v[i], st_sq); }
-                epi_store8<bf16>(ep.C2 + row * ep.ldc + col, v);
+                if (C2SPL) {   // row of the copy = [hi(ldc) | lo(ldc)]
+                  bf16* cb = ep.C2 + row * (2 * (int64_t)ep.ldc) + col;
+                  uint4 hi, lo;
+                  epi_pack8_split(v, hi, lo);
+                  *reinterpret_cast<uint4*>(cb) = hi;
+                  *reinterpret_cast<uint4*>(cb + ep.ldc) = lo;
+                } else {
+                  epi_store8<bf16>(ep.C2 + row * ep.ldc + col, v);
+                }
               }
               if constexpr (SPL) {   // row of C = [hi(ldc) | lo(ldc)]
                 bf16* cb = reinterpret_cast<bf16*>(ep.C) + row * (2 * (int64_t)ep.ldc) + col;
@@ -510,7 +532,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         }
       }
-      if (MODE == 2 && ep.stats_out && row_ok)
+      if (RESLN && ep.stats_out && row_ok)
         reinterpret_cast<float2*>(ep.stats_out)[row * (2 * num_n) + n_blk * 2 + half] = make_float2(st_sum, st_sq);
       tc_fence_before();
       __syncwarp();
@@ -558,8 +580,9 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
   if (Cfg::TMA_STORE && SPL) MSQ_TRY(make_map_2d(&mc, g.C, g.M, g.ldc + g.N, 2 * g.ldc, 64, 32, false));   // lo plane at column ldc
   else if (Cfg::TMA_STORE) MSQ_TRY(make_map_2d(&mc, g.C, g.M, g.N, g.ldc, F32 ? 32 : 64, 32, F32));
   if (Cfg::TMA_STORE && MODE == 2) MSQ_TRY(make_map_2d(&mc2, g.C2bf, g.M, g.N, g.ldc, 32, 32, false, true));
+  if (Cfg::TMA_STORE && MODE == 3) MSQ_TRY(make_map_2d(&mc2, g.C2bf, g.M, g.ldc + g.N, 2 * g.ldc, 32, 32, false, true));   // [hi(ldc) | lo(ldc)]
   CUtensorMap mr = ma;
-  if (Cfg::TMA_STORE && MODE == 2) MSQ_TRY(make_map_2d(&mr, g.resid, g.M, g.N, g.ldr, 32, 32, true));
+  if (Cfg::TMA_STORE && MODE >= 2) MSQ_TRY(make_map_2d(&mr, g.resid, g.M, g.N, g.ldr, 32, 32, true));
   MSQ_SMEM_ATTR(Cfg::SMEM, gemm_tc_kernel<TO, PAIR, ACT, MODE>);
   TcEpi ep;
   ep.bias = g.bias; ep.resid = g.resid; ep.C = g.C; ep.M = g.M; ep.N = g.N; ep.ldc = g.ldc; ep.ldr = g.ldr; ep.act = g.act;
@@ -598,6 +621,7 @@ static int launch_gemm_tc(const GemmArgs& g, int sms, cudaStream_t st) {
   if (g.mode == EPI_RESLN) {
     if constexpr (same_type<TO, float>::value) {
       MSQ_REQUIRE(g.act == ACT_NONE && g.C2bf && g.stats_out && g.resid, "gemm_tc: EPI_RESLN needs resid, C2bf, stats_out and no activation");
+      if (g.split) return launch_gemm_tc_act<TO, PAIR, ACT_NONE, 3>(g, sms, st);   // split operands -> split copy
       return launch_gemm_tc_act<TO, PAIR, ACT_NONE, 2>(g, sms, st);
     } else {
       set_error("gemm_tc: EPI_RESLN writes an fp32 stream");
@@ -605,7 +629,17 @@ static int launch_gemm_tc(const GemmArgs& g, int sms, cudaStream_t st) {
     }
   }
   if constexpr (is_split<TO>::value) {
-    MSQ_REQUIRE(g.mode == EPI_PLAIN, "gemm_tc: split-bf16 output supports the plain epilogue only");
+    MSQ_REQUIRE(g.mode == EPI_PLAIN || g.mode == EPI_LNFOLD, "gemm_tc: split-bf16 output supports the plain and LayerNorm-folded epilogues");
+    if (g.mode == EPI_LNFOLD) {
+      MSQ_REQUIRE(g.svec && g.stats_in && g.sp_in > 0, "gemm_tc: EPI_LNFOLD needs svec and stats_in");
+      switch (g.act) {
+        case ACT_NONE: return launch_gemm_tc_act<TO, PAIR, ACT_NONE, 1>(g, sms, st);
+        case ACT_GELU_ERF: return launch_gemm_tc_act<TO, PAIR, ACT_GELU_ERF, 1>(g, sms, st);
+        case ACT_QUICK_GELU: return launch_gemm_tc_act<TO, PAIR, ACT_QUICK_GELU, 1>(g, sms, st);
+      }
+      set_error("gemm_tc: activation %d not instantiated for EPI_LNFOLD", g.act);
+      return MSQ_ERR_ARG;
+    }
     switch (g.act) {
       case ACT_NONE: return launch_gemm_tc_act<TO, PAIR, ACT_NONE, 0>(g, sms, st);
       case ACT_GELU_ERF: return launch_gemm_tc_act<TO, PAIR, ACT_GELU_ERF, 0>(g, sms, st);
@@ -645,7 +679,7 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   MSQ_REQUIRE(!g.tn || (g.mode == EPI_PLAIN && g.M % 8 == 0 && g.K >= 1), "gemm_tc: TN operands need the plain epilogue and M %% 8 == 0");
   MSQ_REQUIRE(((uintptr_t)g.A & 15) == 0 && ((uintptr_t)g.W & 15) == 0 && ((uintptr_t)g.C & 15) == 0, "gemm_tc: unaligned pointer");
   MSQ_REQUIRE(g.C2 == nullptr, "gemm_tc: second output unsupported");
-  MSQ_REQUIRE(!g.split || (!g.tn && g.mode == EPI_PLAIN && g.K % TC_BK == 0), "gemm_tc: split-bf16 operands need K-major layout, the plain epilogue and K %% 64 == 0");
+  MSQ_REQUIRE(!g.split || (!g.tn && g.K % TC_BK == 0 && (g.mode == EPI_PLAIN || g.split == 1)), "gemm_tc: split-bf16 operands need K-major layout and K %% 64 == 0 (three planes: plain epilogue)");
   MSQ_REQUIRE(g.split >= 0 && g.split <= 2 && (!g.split || (g.K == g.lda && g.K == g.ldw)), "gemm_tc: split=%d operands need lda == ldw == K (planes are K columns apart)", g.split);
   MSQ_REQUIRE(!is_split<TO>::value || (g.split == 1 && g.N % 64 == 0), "gemm_tc: split-bf16 output needs split operands and N %% 64 == 0");
   if (g.M == 0) return MSQ_OK;
