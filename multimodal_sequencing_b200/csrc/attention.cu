@@ -134,7 +134,7 @@ template <int KP, bool SPL> struct AttnCfg {
   static constexpr int TMEM_COLS = SPL ? 2 * KP : KP;
 };
 
-template <int KP, bool SPL>
+template <int KP, bool SPL, bool DROP>
 __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant__ CUtensorMap map_q,
                                                            const __grid_constant__ CUtensorMap map_kv, int L, int heads,
                                                            float scale_l2e, const float* __restrict__ mask_add, int mask_ld,
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
           float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), scale_l2e, maskf[k0 + 2 * i]) - mx);
           float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), scale_l2e, maskf[k0 + 2 * i + 1]) - mx);
           sum += p0 + p1;
-          if (drop.thresh) {   // training: drop probabilities (the denominator `sum` stays the full one)
+          if (DROP) {   // training: drop probabilities (the denominator `sum` stays the full one)
             const uint64_t e0 = ((uint64_t)item * L + (uint64_t)(qt * 128 + trow)) * L + (uint64_t)(k0 + 2 * i);
             p0 *= drop_mul(drop, e0); p1 *= drop_mul(drop, e0 + 1);
           }
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
           float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), scale_l2e, -mx));
           float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), scale_l2e, -mx));
           sum += p0 + p1;
-          if (drop.thresh) {
+          if (DROP) {
             const uint64_t e0 = ((uint64_t)item * L + (uint64_t)(qt * 128 + trow)) * L + (uint64_t)(k0 + 2 * i);
             p0 *= drop_mul(drop, e0); p1 *= drop_mul(drop, e0 + 1);
           }
@@ -397,7 +397,11 @@ static int launch_attention_tc(const bf16* qkv, int64_t R, int L, int heads, flo
   MSQ_TRY(make_map_bf16(&mq, qkv, R * L, ld, ld, AT_D, 128));
   MSQ_TRY(make_map_bf16(&mkv, qkv, R * L, ld, ld, AT_D, KP));
   constexpr int SMEM = AttnCfg<KP, SPL>::SMEM;
-  MSQ_SMEM_ATTR(SMEM, attention_tc_kernel<KP, SPL>);
+  // dropout is a compile-time variant: its hash code inside the unrolled exp loops doubled the evaluation kernel's time
+  // (instruction footprint) when it was a run-time branch
+  const bool dropping = !SPL && drop.thresh != 0;
+  if (dropping) MSQ_SMEM_ATTR(SMEM, (attention_tc_kernel<KP, SPL, !SPL>));
+  else MSQ_SMEM_ATTR(SMEM, (attention_tc_kernel<KP, SPL, false>));
   // Persistent grid = the CTAs that are resident at once: 2 per SM at KP = 256 (256 TMEM columns and 100 KB of shared
   // memory each), 3 per SM at KP = 128 (68 KB, 80 registers).  Measured (640 x 12 items): 296 CTAs 0.289 ms, 444 CTAs 0.365 ms
   // (a wave and a half), one CTA per item 0.335 ms; L = 99: 444 CTAs 0.101 ms vs 0.116 ms.
@@ -412,7 +416,9 @@ static int launch_attention_tc(const bf16* qkv, int64_t R, int L, int heads, flo
   const int64_t n_items = R * heads;
   MSQ_REQUIRE(n_items < ((int64_t)1 << 31), "attention: too many (row, head) items");
 
-  MSQ_CUDA(launch_k(attention_tc_kernel<KP, SPL>, dim3((unsigned)min((int64_t)resident, n_items)), dim3(256), SMEM, st, mq, mkv, L, heads, scale * 1.4426950408889634f, mask_add, mask_ld, mask_len, ctx, (int)n_items, drop));
+  const dim3 grid((unsigned)min((int64_t)resident, n_items));
+  if (dropping) MSQ_CUDA(launch_k(attention_tc_kernel<KP, SPL, !SPL>, grid, dim3(256), SMEM, st, mq, mkv, L, heads, scale * 1.4426950408889634f, mask_add, mask_ld, mask_len, ctx, (int)n_items, drop));
+  else MSQ_CUDA(launch_k(attention_tc_kernel<KP, SPL, false>, grid, dim3(256), SMEM, st, mq, mkv, L, heads, scale * 1.4426950408889634f, mask_add, mask_ld, mask_len, ctx, (int)n_items, drop));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }

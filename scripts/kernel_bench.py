@@ -109,17 +109,22 @@ def bench_deferred():
 
 
 def bench_attn():
-    for L, masked in ((227, True), (99, False)):
-        R, heads = 640, 12
-        qkv = torch.randn(R * L, 3 * heads * 64, device=dev).bfloat16()
-        mask = torch.zeros(R, 128, device=dev)
-        ctx = torch.empty(R * L, heads * 64, device=dev, dtype=torch.bfloat16)
-        ms = timed(lambda: lib.msq_attention(1, qkv.data_ptr(), R, L, heads, 0.125, mask.data_ptr() if masked else None, 128 if masked else 0,
-                                             ctx.data_ptr(), st()))
-        fl = 4.0 * L * L * 64 * heads * R
-        byt = R * L * heads * 64 * 2 * 4
-        print(json.dumps(dict(kernel="attention_tc_kernel", L=L, R=R, ms=ms, tflops=fl / ms / 1e9, gbs=byt / ms / 1e6,
-                              frac_hbm=byt / ms / 1e6 / PK["hbm_gbs"], bound="hbm+sfu")))
+    for split in (False, True):
+        for L, masked in ((227, True), (99, False)):
+            R, heads = 640, 12
+            pl = 2 if split else 1
+            qkv = torch.randn(R * L, pl * 3 * heads * 64, device=dev).bfloat16()
+            if split:
+                qkv[:, 3 * heads * 64:] *= 2.0 ** -9
+            mask = torch.zeros(R, 128, device=dev)
+            ctx = torch.empty(R * L, pl * heads * 64, device=dev, dtype=torch.bfloat16)
+            ms = timed(lambda: lib.msq_attention(2 if split else 1, qkv.data_ptr(), R, L, heads, 0.125, mask.data_ptr() if masked else None,
+                                                 128 if masked else 0, ctx.data_ptr(), st()))
+            fl = 4.0 * L * L * 64 * heads * R
+            byt = R * L * heads * 64 * 2 * 4 * pl
+            print(json.dumps(dict(kernel="attention (bf16x3)" if split else "attention (bf16)", L=L, R=R, ms=ms, tflops=fl / ms / 1e9,
+                                  executed_tflops=fl * (3 if split else 1) / ms / 1e9, gbs=byt / ms / 1e6,
+                                  frac_hbm=byt / ms / 1e6 / PK["hbm_gbs"], bound="tensor+sfu")))
 
 
 def bench_decode():
