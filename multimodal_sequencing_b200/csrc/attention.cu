@@ -389,6 +389,430 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Warp-specialised form for split (bf16x3) operands: one persistent CTA per SM, 14 warps.
+//   warp 0      TMA producer: Q / K / V tiles (hi and lo planes) of the NEXT item as soon as their slots are released
+//   warp 1      MMA issuer (one thread) + TMEM allocation
+//   warps 2-5   softmax group 0, warps 6-9 softmax group 1 (one thread per query row, a 128-key block each)
+//   warps 10-13 epilogue group: combines the key blocks of a query tile and stores the context rows (hi | lo)
+// The work of a CTA is a sequence of BLOCKS (item, query tile of 128 rows, key block of 128 keys).  S of block n lives in
+// TMEM buffer n & 1 (128 fp32 columns); group n & 1 turns it into P (hi and lo bf16 planes written over the S columns of
+// the same 32-key chunk, so nothing is held in registers) with the block's OWN row maximum; O_kb = P_kb V_kb accumulates
+// into its own 64 TMEM columns and the epilogue forms (O_0 2^(m_0-m) + O_1 2^(m_1-m)) / (l_0 2^(m_0-m) + l_1 2^(m_1-m)) --
+// the exact softmax, with no rescaling pass over TMEM.  The issue order S(n+2) after PV(n) (tcgen05.mma executes in issue
+// order) is what frees an S buffer, so the tensor pipe runs S(n+1) / PV(n-1) while group n & 1 is in its exponentials:
+// the serial chain S -> softmax -> PV of attention_tc_kernel (one tile in flight, 20 % tensor pipe) becomes a pipeline.
+// TMEM columns: S0 [0,128) | S1 [128,256) | O[tile parity][key block] 4 x 64 at [256,512).
+// ---------------------------------------------------------------------------------------------------
+template <int KP> struct AttnWsCfg {
+  static constexpr int NKB = KP / 128;                 // key blocks per item
+  static constexpr int QT = KP / 128;                  // query tiles resident per item
+  static constexpr int STAGES = 256 / KP;              // items resident in shared memory
+  static constexpr int TILE = 128 * 64 * 2;            // 128 rows x 64 dims of bf16, 128B swizzle
+  static constexpr int PLANE = (QT + 2 * NKB) * TILE;  // Q tiles | K blocks | V blocks of one plane
+  static constexpr int STAGE_BYTES = 2 * PLANE;        // hi plane, lo plane
+  static constexpr int OPER = STAGES * STAGE_BYTES;    // 192 KB
+  static constexpr int STG_OFF = OPER;                 // epilogue staging: one 32-row x 128-byte box per epilogue warp (1024-aligned)
+  static constexpr int MASK_OFF = STG_OFF + 4 * 4096, STATS_OFF = MASK_OFF + 2 * 128 * 4, BAR_OFF = STATS_OFF + 4 * 2 * 128 * 8;
+  static constexpr int SMEM = BAR_OFF + 256 + 1024;
+  static constexpr int THREADS = 14 * 32;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ bool named_bar_or(int id, int n, bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 q, %3, 0;\n\t"
+      "bar.red.or.pred p, %1, %2, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "r"(id), "r"(n), "r"((uint32_t)pred)
+      : "memory");
+  return r != 0;
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// tcgen05.mma with a compile-time-foldable accumulate flag; TS: A operand in TMEM (address in the low word of `a`)
+template <bool TS>
+__device__ __forceinline__ void umma_bf16_acc(uint32_t tmem_d, uint64_t a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  if (TS) {
+    if (accumulate)
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"((uint32_t)a), "l"(desc_b), "r"(idesc) : "memory");
+    else
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"((uint32_t)a), "l"(desc_b), "r"(idesc) : "memory");
+  } else {
+    if (accumulate)
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(a), "l"(desc_b), "r"(idesc) : "memory");
+    else
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(a), "l"(desc_b), "r"(idesc) : "memory");
+  }
+}
+
+template <int KP>
+__global__ void __launch_bounds__(AttnWsCfg<KP>::THREADS, 1)
+attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                    const __grid_constant__ CUtensorMap map_ctx, int L, int heads,
+                    float scale_l2e, const float* __restrict__ mask_add, int mask_ld, int mask_len, bf16* __restrict__ ctx,
+                    int n_items, long long* trace) {
+  using Cfg = AttnWsCfg<KP>;
+#ifdef MSQ_ATTN_TRACE
+  // event trace of CTA 0 (development aid): trace[role][n][k] = clock64 at event k of block / tile n
+#define TR(role, n, k) do { if (blockIdx.x == 0 && (n) < 64) trace[((role) * 64 + (n)) * 8 + (k)] = clock64(); } while (0)
+#else
+#define TR(role, n, k) do { } while (0)
+#endif
+  constexpr int NKB = Cfg::NKB, QT = Cfg::QT, STAGES = Cfg::STAGES, TILE = Cfg::TILE, PLANE = Cfg::PLANE;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  float* maskf = reinterpret_cast<float*>(gen + Cfg::MASK_OFF);          // [2 groups][128]
+  float2* stats = reinterpret_cast<float2*>(gen + Cfg::STATS_OFF);       // [4 tile slots][2 key blocks][128 rows] (max, sum)
+  const uint32_t bars = base + Cfg::BAR_OFF;
+  // 8-byte barriers: qk_full[2] | qk_empty[2] | v_full[2] | v_empty[2] | s_full[2] | p_ready[2] | o_full[2] | o_empty[2] | slot
+  const uint32_t qk_full = bars, qk_empty = bars + 16, v_full = bars + 32, v_empty = bars + 48, s_full = bars + 64,
+                 p_ready = bars + 80, o_full = bars + 96, o_empty = bars + 112, tslot = bars + 128;
+  volatile uint32_t* tslot_gen = reinterpret_cast<volatile uint32_t*>(gen + Cfg::BAR_OFF + 128);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nqt = (L + 127) >> 7;
+  const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int NT = my_items * nqt, NB = NT * NKB;   // query tiles / blocks of this CTA
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ctx) : "memory");
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(qk_full + 8 * i, 1); mbar_init(qk_empty + 8 * i, 1); mbar_init(v_full + 8 * i, 1); mbar_init(v_empty + 8 * i, 1);
+      mbar_init(s_full + 8 * i, 1); mbar_init(p_ready + 8 * i, 4); mbar_init(o_full + 8 * i, 1); mbar_init(o_empty + 8 * i, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_sync();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot_gen;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int lo = 3 * heads * AT_D;   // the lo plane of a qkv row starts here
+      int item = blockIdx.x;
+      for (int li = 0; li < my_items; ++li, item += gridDim.x) {
+        const int s = li % STAGES, u = li / STAGES;
+        const int row0 = (item / heads) * L, hh = item % heads;
+        const uint32_t st0 = base + s * Cfg::STAGE_BYTES;
+        mbar_wait(qk_empty + 8 * s, (u & 1) ^ 1);
+        mbar_expect_tx(qk_full + 8 * s, (uint32_t)(2 * (nqt + NKB) * TILE));
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          tma_load_2d(st0 + pl * PLANE + QT * TILE, &map_kv, pl * lo + heads * AT_D + hh * AT_D, row0, qk_full + 8 * s);
+          for (int qt = 0; qt < nqt; ++qt)
+            tma_load_2d(st0 + pl * PLANE + qt * TILE, &map_q, pl * lo + hh * AT_D, row0 + qt * 128, qk_full + 8 * s);
+        }
+        mbar_wait(v_empty + 8 * s, (u & 1) ^ 1);
+        mbar_expect_tx(v_full + 8 * s, (uint32_t)(2 * NKB * TILE));
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl)
+          tma_load_2d(st0 + pl * PLANE + (QT + NKB) * TILE, &map_kv, pl * lo + 2 * heads * AT_D + hh * AT_D, row0, v_full + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // The whole warp walks the block sequence (uniform control flow, every lane waits on the barriers); ONE elected lane
+    // issues.  elect.sync (instead of `lane == 0`) lets ptxas keep descriptors in uniform registers without a per-MMA
+    // waterfall loop, and descriptors are advanced by adding to their low word: at ~70 cycles of issue overhead per
+    // tcgen05.mma the 32-cycle N = 64 MMAs of P V were issue-bound.
+    {
+      // instruction descriptors: D=F32, A=B=BF16; S: N=128, A/B K-major; PV: N=64, B MN-major (bit 16)
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | (8u << 24);
+      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | (8u << 24);
+      const uint64_t dk0 = umma_desc_sw128(base), dv0 = umma_desc_sw128_mn(base);   // descriptors of the stage base
+      auto issue_s = [&](int n) {
+        const int t = n / NKB, kb = n % NKB, li = t / nqt, qt = t - li * nqt, s = li % STAGES, u = li / STAGES;
+        if (qt == 0 && kb == 0) { mbar_wait(qk_full + 8 * s, u & 1); tc_fence_after(); }
+        const uint32_t d = tmem + (n & 1) * 128;
+        // byte offsets >> 4 from the stage base: Q tile qt, K block kb (hi planes; lo planes PLANE further)
+        const uint64_t qh = dk0 + (uint64_t)((s * Cfg::STAGE_BYTES + qt * TILE) >> 4), ql = qh + (PLANE >> 4);
+        const uint64_t kh = dk0 + (uint64_t)((s * Cfg::STAGE_BYTES + (QT + kb) * TILE) >> 4), kl = kh + (PLANE >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_acc<false>(d, qh + 2 * k, kl + 2 * k, idesc_s, k != 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_acc<false>(d, ql + 2 * k, kh + 2 * k, idesc_s, true);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_acc<false>(d, qh + 2 * k, kh + 2 * k, idesc_s, true);
+          umma_commit(s_full + 8 * (n & 1));
+          if (qt == nqt - 1 && kb == NKB - 1) umma_commit(qk_empty + 8 * s);   // Q / K of this item have been read
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int n) {
+        const int t = n / NKB, kb = n % NKB, li = t / nqt, qt = t - li * nqt, s = li % STAGES, u = li / STAGES;
+        if (qt == 0 && kb == 0) mbar_wait(v_full + 8 * s, u & 1);
+        if (kb == 0) mbar_wait(o_empty + 8 * (t & 1), ((t >> 1) & 1) ^ 1);   // the epilogue has drained this O buffer
+        if (lane == 0) TR(0, n, 0);
+        mbar_wait(p_ready + 8 * (n & 1), (n >> 1) & 1);
+        if (lane == 0) TR(0, n, 1);
+        tc_fence_after();
+        const uint32_t p = tmem + (n & 1) * 128, d = tmem + 256 + ((t & 1) * 2 + kb) * 64;
+        const uint64_t vh = dv0 + (uint64_t)((s * Cfg::STAGE_BYTES + (QT + NKB + kb) * TILE) >> 4), vl = vh + (PLANE >> 4);
+        // P of 32-key chunk j: hi plane in columns [32 j, 32 j + 16), lo plane in [32 j + 16, 32 j + 32); 16 keys = 8 columns;
+        // 16 keys of V (MN-major) = 2048 bytes
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16_acc<true>(d, (uint64_t)(p + 32 * (kk >> 1) + 8 * (kk & 1)), vl + 128 * kk, idesc_o, kk != 0);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16_acc<true>(d, (uint64_t)(p + 32 * (kk >> 1) + 16 + 8 * (kk & 1)), vh + 128 * kk, idesc_o, true);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16_acc<true>(d, (uint64_t)(p + 32 * (kk >> 1) + 8 * (kk & 1)), vh + 128 * kk, idesc_o, true);
+          if (kb == NKB - 1) umma_commit(o_full + 8 * (t & 1));
+          if (qt == nqt - 1 && kb == NKB - 1) umma_commit(v_empty + 8 * s);    // V of this item has been read
+        }
+        __syncwarp();
+        if (lane == 0) TR(0, n, 2);
+      };
+      issue_s(0);
+      if (NB > 1) issue_s(1);
+      for (int n = 0; n < NB; ++n) {
+        issue_pv(n);
+        if (n + 2 < NB) issue_s(n + 2);   // after PV(n) in issue order: S buffer n & 1 (and its P) is free by then
+        if (lane == 0) TR(0, n, 3);
+      }
+    }
+  } else if (warp < 10) {
+    // ===================== softmax groups =====================
+    const int w = (warp - 2) >> 2;                       // group: blocks with n & 1 == w
+    const int quarter = warp & 3, row = quarter * 32 + lane, gtid = ((warp - 2) & 3) * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    float* mk = maskf + w * 128;
+    const float LOG2E = 1.4426950408889634f;
+    int have_item = -1, have_kb = -1;
+    bool masked = false;
+    for (int n = w; n < NB; n += 2) {
+      const int t = n / NKB, kb = n % NKB, li = t / nqt;
+      const int item = (int)blockIdx.x + li * (int)gridDim.x, r = item / heads;
+      const int key0 = kb * 128;
+      if (item != have_item || kb != have_kb) {
+        // additive key mask of this block (log2 domain), -inf beyond the sequence; the all-visible case skips the reads
+        named_bar_sync(1 + w, 128);   // the previous block's readers are done
+        const int key = key0 + gtid;
+        float m = -INFINITY;
+        bool nz = false;
+        if (key < L) {
+          m = (mask_add != nullptr && key < mask_len) ? mask_add[(int64_t)r * mask_ld + key] * LOG2E : 0.f;
+          nz = m != 0.f;
+        }
+        mk[gtid] = m;
+        masked = named_bar_or(1 + w, 128, nz);
+        have_item = item; have_kb = kb;
+      }
+      const uint32_t sb = lane_addr + (n & 1) * 128;
+      if (gtid == 0) TR(1, n, 0);
+      mbar_wait(s_full + 8 * (n & 1), (n >> 1) & 1);
+      if (gtid == 0) TR(1, n, 1);
+      tc_fence_after();
+      // ---- pass 1: row maximum of the block (log2 domain)
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        uint32_t raw[32];
+        tmem_ld32(sb + j * 32, raw);
+        if (masked || key0 + j * 32 + 32 > L) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(raw[i]), scale_l2e, mk[j * 32 + i]));
+        } else {
+          float m2 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m2 = fmaxf(m2, __uint_as_float(raw[i]));
+          mx = fmaxf(mx, m2 * scale_l2e);
+        }
+      }
+      if (gtid == 0) TR(1, n, 2);
+      // ---- pass 2: p = 2^(s c + mask - max), hi / lo planes written over the chunk's own S columns
+      float sum = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        uint32_t raw[32], ph[16], pl[16];
+        tmem_ld32(sb + j * 32, raw);
+        if (masked || key0 + j * 32 + 32 > L) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), scale_l2e, mk[j * 32 + 2 * i]) - mx);
+            const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), scale_l2e, mk[j * 32 + 2 * i + 1]) - mx);
+            sum += p0 + p1;
+            const __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);  // .x (low half) = even key
+            const __nv_bfloat162 c = __floats2bfloat162_rn(p0 - __low2float(b), p1 - __high2float(b));
+            ph[i] = *reinterpret_cast<const uint32_t*>(&b);
+            pl[i] = *reinterpret_cast<const uint32_t*>(&c);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), scale_l2e, -mx));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), scale_l2e, -mx));
+            sum += p0 + p1;
+            const __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
+            const __nv_bfloat162 c = __floats2bfloat162_rn(p0 - __low2float(b), p1 - __high2float(b));
+            ph[i] = *reinterpret_cast<const uint32_t*>(&b);
+            pl[i] = *reinterpret_cast<const uint32_t*>(&c);
+          }
+        }
+        tmem_st16(sb + j * 32, ph);
+        tmem_st16(sb + j * 32 + 16, pl);
+      }
+      stats[((t & 3) * 2 + kb) * 128 + row] = make_float2(mx, sum);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready + 8 * (n & 1));
+      if (gtid == 0) TR(1, n, 3);
+    }
+  } else {
+    // ===================== epilogue group =====================
+    const int quarter = warp & 3, row = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    for (int t = 0; t < NT; ++t) {
+      const int li = t / nqt, qt = t % nqt;
+      const int item = (int)blockIdx.x + li * (int)gridDim.x, r = item / heads, h = item % heads;
+      if (tid == 320) TR(2, t, 0);
+      mbar_wait(o_full + 8 * (t & 1), (t >> 1) & 1);
+      if (tid == 320) TR(2, t, 1);
+      tc_fence_after();
+      const float2 s0 = stats[((t & 3) * 2 + 0) * 128 + row];
+      float w0 = 1.f, w1 = 0.f, den = s0.y;
+      if (NKB == 2) {
+        const float2 s1 = stats[((t & 3) * 2 + 1) * 128 + row];
+        const float m = fmaxf(s0.x, s1.x);
+        w0 = ex2_approx(s0.x - m); w1 = ex2_approx(s1.x - m);
+        den = fmaf(s0.y, w0, s1.y * w1);
+      }
+      const float inv = 1.0f / den;
+      w0 *= inv; w1 *= inv;
+      const uint32_t ob = lane_addr + 256 + (t & 1) * 128;
+      float o[64];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t a[32];
+        tmem_ld32(ob + hf * 32, a);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[hf * 32 + i] = __uint_as_float(a[i]) * w0;
+        if (NKB == 2) {
+          tmem_ld32(ob + 64 + hf * 32, a);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[hf * 32 + i] = fmaf(__uint_as_float(a[i]), w1, o[hf * 32 + i]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty + 8 * (t & 1));   // O buffer drained: the tile after next may accumulate into it
+      // ctx rows = [hi(heads*64) | lo(heads*64)]: this warp's 32 rows x 64 columns go out as two TMA boxes (hi plane, lo plane)
+      // staged in shared memory (128B swizzle; piece j of row r at r*128 + ((j ^ (r & 7)) << 4)).  Per-thread 16-byte stores
+      // of whole rows (32 different lines per instruction) had flooded the memory pipeline the softmax warps' TMEM loads and
+      // the barrier polls share.  The 3-D map clips the box at the end of the token group (rows >= L are not written).
+      const int q0 = qt * 128 + quarter * 32;
+      const uint32_t stg = base + Cfg::STG_OFF + (warp - 10) * 4096 + lane * 128;
+      if (lane == 0) tma_store_wait_read<0>();   // the previous tile's lo box has been read out of the staging buffer
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {   // hi plane: round-to-nearest bf16 of the normalised outputs
+        const __nv_bfloat162 a0 = __floats2bfloat162_rn(o[8 * i], o[8 * i + 1]), a1 = __floats2bfloat162_rn(o[8 * i + 2], o[8 * i + 3]);
+        const __nv_bfloat162 a2 = __floats2bfloat162_rn(o[8 * i + 4], o[8 * i + 5]), a3 = __floats2bfloat162_rn(o[8 * i + 6], o[8 * i + 7]);
+        st_shared_v4(stg + ((i ^ (lane & 7)) << 4), *reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1),
+                     *reinterpret_cast<const uint32_t*>(&a2), *reinterpret_cast<const uint32_t*>(&a3));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && q0 < L) { tma_store_3d(&map_ctx, stg, h * AT_D, q0, r); tma_store_commit(); }
+      // lo plane: computed while the TMA reads the hi box
+      uint4 lo4[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint2 h0, l0, h1, l1;
+        split4(make_float4(o[8 * i], o[8 * i + 1], o[8 * i + 2], o[8 * i + 3]), h0, l0);
+        split4(make_float4(o[8 * i + 4], o[8 * i + 5], o[8 * i + 6], o[8 * i + 7]), h1, l1);
+        lo4[i] = make_uint4(l0.x, l0.y, l1.x, l1.y);
+      }
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) st_shared_v4(stg + ((i ^ (lane & 7)) << 4), lo4[i].x, lo4[i].y, lo4[i].z, lo4[i].w);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && q0 < L) { tma_store_3d(&map_ctx, stg, heads * AT_D + h * AT_D, q0, r); tma_store_commit(); }
+      if (tid == 320) TR(2, t, 2);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last boxes are in global memory
+  }
+#undef TR
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  }
+}
+
+template <int KP>
+static int launch_attention_ws(const bf16* qkv, int64_t R, int L, int heads, float scale, const float* mask_add, int mask_ld,
+                               int mask_len, bf16* ctx, cudaStream_t st) {
+  using Cfg = AttnWsCfg<KP>;
+  CUtensorMap mq, mkv;
+  const int ld = 2 * 3 * heads * AT_D;   // bf16 elements per qkv row (hi | lo)
+  MSQ_TRY(make_map_bf16(&mq, qkv, R * L, ld, ld, AT_D, 128));
+  MSQ_TRY(make_map_bf16(&mkv, qkv, R * L, ld, ld, AT_D, KP));
+  CUtensorMap mctx;
+  MSQ_TRY(make_map_3d_bf16(&mctx, ctx, R, L, 2 * heads * AT_D, 2 * heads * AT_D, AT_D, 32));
+  MSQ_SMEM_ATTR(Cfg::SMEM, attention_ws_kernel<KP>);
+  int dev = 0, sms = 0;
+  MSQ_CUDA(cudaGetDevice(&dev));
+  MSQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t n_items = R * heads;
+  MSQ_REQUIRE(n_items < ((int64_t)1 << 28), "attention: too many (row, head) items");
+  long long* trace = nullptr;
+#ifdef MSQ_ATTN_TRACE
+  static long long* trace_dev = nullptr;
+  if (!trace_dev) MSQ_CUDA(cudaMalloc(&trace_dev, 3 * 64 * 8 * sizeof(long long)));
+  MSQ_CUDA(cudaMemsetAsync(trace_dev, 0, 3 * 64 * 8 * sizeof(long long), st));
+  trace = trace_dev;
+#endif
+  MSQ_CUDA(launch_k(attention_ws_kernel<KP>, dim3((unsigned)min((int64_t)sms, n_items)), dim3(Cfg::THREADS), Cfg::SMEM, st, mq, mkv, mctx, L,
+                    heads, scale * 1.4426950408889634f, mask_add, mask_ld, mask_len, ctx, (int)n_items, trace));
+  MSQ_LAUNCH_CHECK();
+#ifdef MSQ_ATTN_TRACE
+  {
+    static long long host[3 * 64 * 8];
+    MSQ_CUDA(cudaStreamSynchronize(st));
+    MSQ_CUDA(cudaMemcpy(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen("gpurun_out/attn_trace.bin", "wb")) { fwrite(host, 1, sizeof(host), f); fclose(f); }
+  }
+#endif
+  return MSQ_OK;
+}
+static bool attention_use_ws() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MSQ_ATTN_WS"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 template <int KP, bool SPL>
 static int launch_attention_tc(const bf16* qkv, int64_t R, int L, int heads, float scale, const float* mask_add, int mask_ld,
                                int mask_len, bf16* ctx, cudaStream_t st, const Drop& drop = Drop()) {
@@ -438,6 +862,11 @@ int attention(const T* qkv, int64_t R, int L, int heads, int dhead, float scale,
   if constexpr (is_split<T>::value) {
     MSQ_REQUIRE(drop.thresh == 0, "attention: dropout is a training-path feature (bf16 / fp32), not available in the bf16x3 mode");
     MSQ_REQUIRE(tc_supported_impl() && L <= 256 && (((uintptr_t)qkv) & 15) == 0, "attention: the bf16x3 mode needs the tcgen05 path (sm_100, L <= 256)");
+    if (attention_use_ws()) {   // warp-specialised pipeline (MSQ_ATTN_WS=0: the one-tile-at-a-time kernel)
+      if (L <= 128)
+        return launch_attention_ws<128>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
+      return launch_attention_ws<256>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
+    }
     if (L <= 128)
       return launch_attention_tc<128, true>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
     return launch_attention_tc<256, true>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);

@@ -50,6 +50,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1),
+               "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
@@ -178,5 +183,22 @@ inline int make_map_2d(CUtensorMap* map, const void* ptr, int64_t rows, int K, i
   return MSQ_OK;
 }
 
+// 3-D bf16 tensor map over [groups, rows_per_group, cols] (row-major, leading dimension ld): a box of box_cols x box_rows x 1
+// is clipped at the END OF ITS GROUP, so a tile of rows may be stored without touching the next group (128-byte swizzle).
+inline int make_map_3d_bf16(CUtensorMap* map, const void* ptr, int64_t groups, int rows_per_group, int cols, int ld, int box_cols,
+                            int box_rows) {
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows_per_group, (cuuint64_t)groups};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)rows_per_group};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D) failed (%d) groups=%lld rows=%d cols=%d ld=%d", (int)r, (long long)groups, rows_per_group, cols, ld);
+    return MSQ_ERR_CUDA;
+  }
+  return MSQ_OK;
+}
 
 }  // namespace msq

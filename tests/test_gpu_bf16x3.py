@@ -85,7 +85,8 @@ def test_gemm_bf16x3(M, N, K, act, split_out):
 
 
 @pytest.mark.parametrize("R,L,heads,mask_len", [(3, 227, 12, 128), (5, 99, 12, 0), (2, 128, 2, 128), (4, 60, 4, 60), (1, 256, 12, 100),
-                                                (300, 227, 12, 128)])
+                                                (300, 227, 12, 128), (1, 129, 1, 0), (2, 1, 1, 0), (200, 99, 12, 0), (37, 200, 3, 128),
+                                                (149, 130, 1, 64)])
 def test_attention_bf16x3(R, L, heads, mask_len):
     _lib, lib, st = _lib_and_stream()
     g = torch.Generator().manual_seed(R * 1000 + L)
