@@ -32,11 +32,15 @@ constexpr int TC_EPI_WARPS = 8, TC_THREADS = (2 + TC_EPI_WARPS) * 32;
 
 // MODE: 0 plain, 1 EPI_LNFOLD, 2 EPI_RESLN (bf16 copy), 3 EPI_RESLN with a SPLIT-bf16 copy (bf16x3 mode: hi and lo boxes)
 template <bool PAIR, int MODE = 0> struct TcCfg {
-  static constexpr int STAGES = (PAIR && MODE == 3) ? 3 : 4;   // the second copy box costs 16 KB: one pipeline stage less
+  static constexpr int STAGES = 4;
+  // MODE 3 (split copy: two more boxes per warp) keeps ONE fp32 box per warp instead of two, so that the operand ring stays at
+  // four stages: the residual chunk is loaded when the box has been stored (no chunk-ahead prefetch); at three MMAs per
+  // product the mainloop of a tile is long enough to hide that latency, a three-stage ring was not (+26 % per launch).
+  static constexpr int F32_BOXES = (PAIR && MODE == 3) ? 1 : 2;
   // PAIR: the epilogue stages 32-row x 128-byte output boxes in shared memory (2 per warp) and writes
   // them with TMA bulk tensor stores (full-line, asynchronous) instead of per-thread 16-byte stores.
   static constexpr bool TMA_STORE = PAIR;
-  static constexpr int STAGING_F32 = TMA_STORE ? TC_EPI_WARPS * 2 * 4096 : 0;
+  static constexpr int STAGING_F32 = TMA_STORE ? TC_EPI_WARPS * F32_BOXES * 4096 : 0;
   // EPI_RESLN: one more box per warp for the bf16 copy, 32 rows x 32 columns (64-byte rows, 64B swizzle), stored every chunk
   static constexpr int STAGING_BYTES = STAGING_F32 + ((TMA_STORE && MODE >= 2) ? (MODE == 3 ? 2 : 1) * TC_EPI_WARPS * 2048 : 0);
   static constexpr int VECS = MODE == 0 ? 1 : (MODE == 1 ? 2 : 3);   // per-column vectors held per warp: bias | svec/gamma | beta
@@ -64,6 +68,9 @@ struct TcEpi {
   int tn;   // GemmArgs::tn: MN-major operands (single-CTA path)
   int split_k;  // GemmArgs::split: logical K (A and W rows are planes of K columns: [hi | lo] or [hi | mid | lo]); 0 = plain bf16
   int split_passes;  // 3 (two planes: bf16x3) or 6 (three planes: bf16x6, fp32-grade products)
+  // bf16x3 on CTA pairs: a K slab is staged ONCE as two stages ([a_hi | w_hi], [a_lo | w_lo]) and the three MMA passes
+  // read them crosswise, instead of three stages that fetch a_hi and w_hi twice: L2 -> shared-memory traffic -1/3
+  int share;
 };
 
 // 8 consecutive output columns of one row: accumulator -> value to store (see GemmArgs for the modes)
@@ -232,7 +239,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           // bf16x3: the K loop runs three times over every 64-column slab: a_hi*w_lo, a_lo*w_hi, a_hi*w_hi (the hi and
           // lo planes of a row are K columns apart); the MMA warp just sees a contraction of length 3K
           int kb = kq, ka = 0, kw = 0;
-          if (ep.split_k) {
+          if (PAIR && ep.share) {
+            kb = kq >> 1;
+            ka = kw = (kq & 1) * ep.split_k;   // even stage: hi planes, odd stage: lo planes
+          } else if (ep.split_k) {
             // (plane of A, plane of W) per pass, smallest products first.  two planes: (0,1) (1,0) (0,0);
             // three planes: (0,2) (1,1) (2,0) (0,1) (1,0) (0,0) -- every product a_i w_j with i + j <= 2
             kb = kq / ep.split_passes;
@@ -278,6 +288,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * TC_BN;
+        if (PAIR && ep.share) {
+          for (int kb = 0; kb < num_k; kb += 2) {
+            mbar_wait(full0 + 8 * stage, phase);
+            mbar_wait(full0 + 8 * (stage + 1), phase);
+            tc_fence_after();
+            const uint32_t ah = base + stage * STAGE_BYTES, wh = ah + TC_A_BYTES, al = ah + STAGE_BYTES, wl = al + TC_A_BYTES;
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k)   // smallest products first
+              umma_bf16_pair(tmem_d, umma_desc_sw128(ah + k * 32), umma_desc_sw128(wl + k * 32), idesc, (kb | k) != 0);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) umma_bf16_pair(tmem_d, umma_desc_sw128(al + k * 32), umma_desc_sw128(wh + k * 32), idesc, 1);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) umma_bf16_pair(tmem_d, umma_desc_sw128(ah + k * 32), umma_desc_sw128(wh + k * 32), idesc, 1);
+            umma_commit_pair(empty0 + 8 * stage);
+            umma_commit_pair(empty0 + 8 * (stage + 1));
+            stage += 2;
+            if (stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        } else
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
@@ -309,7 +338,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     float* bias_s = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + Cfg::STAGING_BYTES + 256) + (warp - 2) * 128;
     float* svec_s = bias_s + TC_EPI_WARPS * 128;   // MODE 1: s_n; MODE 2: gamma of the LayerNorm pending on the residual
     float* beta_s = svec_s + TC_EPI_WARPS * 128;   // MODE 2: its beta
-    const uint32_t stg = staging0 + (warp - 2) * 8192;  // this warp's two staging boxes
+    constexpr bool RES_DB = Cfg::F32_BOXES == 2;           // residual chunk prefetched one chunk ahead into the other box
+    const uint32_t stg = staging0 + (warp - 2) * (Cfg::F32_BOXES * 4096);  // this warp's staging box(es)
     const uint32_t stg2 = staging0 + Cfg::STAGING_F32 + (warp - 2) * 2048;  // MODE 2 / 3: bf16 (hi) box (32 rows x 32 columns)
     const uint32_t stg3 = stg2 + TC_EPI_WARPS * 2048;                        // MODE 3: lo box
     int stg_use = 0;                                       // boxes handed to the TMA so far (parity selects the buffer)
@@ -323,13 +353,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int r0 = (t / num_n) * Cfg::TILE_M + (int)rank * TC_BM + q * 32;
       const int c0 = (t % num_n) * TC_BN + half * 128 + ch * 32;
       mbar_expect_tx(rbar + 8 * (k & 1), 4096);
-      tma_load_2d(stg + (k & 1) * 4096, &tma_r, c0, r0, rbar + 8 * (k & 1));
+      tma_load_2d(stg + (RES_DB ? (k & 1) * 4096 : 0), &tma_r, c0, r0, rbar + 8 * (k & 1));
     };
     if (RES_TMA) {
       if (lane == 0) {
         mbar_init(rbar, 1); mbar_init(rbar + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (unit < num_tiles) issue_res(unit, 0, 0);
+        if (RES_DB && unit < num_tiles) issue_res(unit, 0, 0);
       }
       __syncwarp();
     }
@@ -421,7 +451,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               // every store issued so far has been read out of shared memory: the other fp32 box may receive the next
               // residual chunk (of this tile or of this warp's next tile) and the bf16 box may be refilled
               tma_store_wait_read<0>();
-              if (ch + 1 < 4) issue_res(tile, ch + 1, rk + 1);
+              if (!RES_DB) issue_res(tile, ch, rk);   // single box: it has just been read out by the previous chunk's store
+              else if (ch + 1 < 4) issue_res(tile, ch + 1, rk + 1);
               else if (tile + num_units < num_tiles) issue_res(tile + num_units, 0, rk + 1);
             }
             __syncwarp();
@@ -431,7 +462,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (lane == 0) { if (SPL) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
             __syncwarp();
           }
-          const uint32_t box = SPL ? stg : stg + ((RES_TMA ? rk : (uint32_t)stg_use) & 1) * 4096;
+          const uint32_t box = (SPL || !RES_DB) ? stg : stg + ((RES_TMA ? rk : (uint32_t)stg_use) & 1) * 4096;
           const uint32_t rowp = box + lane * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -589,7 +620,12 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
   ep.svec = g.svec; ep.beta = g.beta; ep.stats_in = g.stats_in; ep.stats_out = g.stats_out; ep.C2 = (bf16*)g.C2bf; ep.sp_in = g.sp_in;
   ep.inv_dim = g.ln_inv_dim; ep.eps = g.ln_eps; ep.tn = g.tn; ep.split_k = g.split ? g.K : 0;
   ep.split_passes = g.split == 2 ? 6 : 3;
-  const int num_m = ceil_div(g.M, Cfg::TILE_M), num_n = ceil_div(g.N, TC_BN), num_k = ceil_div(g.K, TC_BK) * (g.split ? ep.split_passes : 1);
+  static int share_env = -1;
+  if (share_env < 0) { const char* e = getenv("MSQ_X3_SHARE"); share_env = (e && e[0] == '0') ? 0 : 1; }
+  ep.share = (PAIR && g.split == 1 && !g.tn && share_env) ? 1 : 0;
+  static_assert(Cfg::STAGES % 2 == 0, "the shared bf16x3 slab occupies two consecutive stages");
+  const int num_m = ceil_div(g.M, Cfg::TILE_M), num_n = ceil_div(g.N, TC_BN),
+            num_k = ceil_div(g.K, TC_BK) * (ep.share ? 2 : (g.split ? ep.split_passes : 1));
   const int64_t tiles = (int64_t)num_m * num_n;
   profile_mark(st, false, 0.0);
   if (PAIR) {
