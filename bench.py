@@ -446,7 +446,7 @@ def run_finetune(ctx, args, steps, warmup, full=True):
     B = args.batch or CFG[3]["batch"]
     precision = args.precision or ("fp32" if args.precise else "bf16")
     mcfg, vit, rn = _model_cfg(args)
-    sd = synth.full_state_dict(mcfg, vit, seed=0)
+    sd = synth.full_state_dict(mcfg, vit, seed=0, rn=rn)
     eng = OrderingEngine(sd, mcfg, precise=precision, device=ctx.dev)
     del sd
     ids, labels, images = O.synthetic_manuals(B, N, TOKENS, image_px=IMG, seed=1 + ctx.rank)

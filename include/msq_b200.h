@@ -226,6 +226,13 @@ int msq_train_step(msq_model* m, const int64_t* ids_dev, const int64_t* tt_dev, 
  * oracle/dropout.py is the numpy twin).  Evaluation entry points never apply dropout. */
 int msq_train_set_dropout(msq_model* m, float p_hidden, float p_attn, float p_para, uint32_t seed, void* stream);
 int64_t msq_train_dropout_step(msq_model* m);
+/* BatchNorm of the ModifiedResNet tower inside a training step (models/CLIP/clip/model.py:10-53, 128-187).  Default
+ * (use_running_stats = 0): nn.BatchNorm2d in train() mode, the mode trainers/train.py fine-tunes in -- statistics of the
+ * batch of MATERIALISED pair images (mean and biased variance over N, H, W; the tower itself runs on the unique images with
+ * their pair multiplicities as weights), gradients flow through the statistics.  use_running_stats = 1: eval() semantics
+ * (frozen running statistics) with the same backward pass otherwise.  Running statistics are never modified by this
+ * library: a caller that needs the reference's momentum update applies it to its own buffers.  No-op for other backbones. */
+int msq_train_set_bn_mode(msq_model* m, int32_t use_running_stats, void* stream);
 
 /* Data-parallel overlap: msq_train_step records one CUDA event per REGION of the flat gradient buffer at the moment that
  * region is final (BERSON heads, BERT layers top -> bottom, embeddings, visn_fc, ViT blocks top -> bottom, ViT stem).

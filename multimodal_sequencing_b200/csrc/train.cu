@@ -54,13 +54,13 @@ template <typename T> static int refresh_wT(msq_model* m, TrainState* ts, cudaSt
     for (int i = 0; i < 4; ++i) MSQ_TRY(fill_wT<T>(*ls[i], ts->vitT[l][i], st));
   }
   if (ts->visnT) MSQ_TRY(fill_wT<T>(m->visn_fc, ts->visnT, st));
+  if (ts->rn) MSQ_TRY(rn_train_refresh<T>(m, st));
   return MSQ_OK;
 }
 
 template <typename T> static int build_train_state(msq_model* m, cudaStream_t st) {
   const msq_config& c = m->cfg;
   MSQ_REQUIRE(m->packed && m->has_bert, "train: model not packed / no inner encoder weights");
-  MSQ_REQUIRE(c.rn_width == 0, "train: the ModifiedResNet tower has no backward pass in this build (ViT / text-only only)");
   TrainState* ts = new TrainState();
   m->train = ts;
   const std::string P = m->prefix_inner;
@@ -77,7 +77,9 @@ template <typename T> static int build_train_state(msq_model* m, cudaStream_t st
                           "output.dense.weight", "output.dense.bias", "output.LayerNorm.weight", "output.LayerNorm.bias"})
       MSQ_TRY(add_slot(m, ts, b + e));
   }
-  if (m->has_vit) {
+  if (m->has_vit && c.rn_width) {
+    for (const std::string& n : rn_param_names(m)) MSQ_TRY(add_slot(m, ts, n));
+  } else if (m->has_vit) {
     const std::string v = P + "encoder.visual_model.visual.";
     for (const char* e : {"conv1.weight", "class_embedding", "positional_embedding", "ln_pre.weight", "ln_pre.bias", "ln_post.weight",
                           "ln_post.bias"})
@@ -106,6 +108,7 @@ template <typename T> static int build_train_state(msq_model* m, cudaStream_t st
     for (int i = 0; i < 4; ++i) MSQ_TRY(make_wT<T>(ts, *ls[i], &ts->vitT[l][i]));
   }
   if (m->has_vit) MSQ_TRY(make_wT<T>(ts, m->visn_fc, &ts->visnT));
+  if (m->has_vit && c.rn_width) MSQ_TRY(rn_train_build<T>(m, st));
   MSQ_TRY(refresh_wT<T>(m, ts, st));
   if (m->has_heads) {
     for (const std::string& n : heads_param_names(m)) MSQ_TRY(add_slot(m, ts, n));
@@ -124,7 +127,7 @@ static int ensure_train(msq_model* m, cudaStream_t st) {
 }
 
 // mark the slots [first, last] (by name) final: one event on the compute stream, recorded in completion order
-static int mark_ready(TrainState* ts, const std::string& first, const std::string& last, cudaStream_t st) {
+int mark_ready(TrainState* ts, const std::string& first, const std::string& last, cudaStream_t st) {
   auto a = ts->index.find(first), b = ts->index.find(last);
   if (a == ts->index.end() || b == ts->index.end()) return MSQ_OK;   // group absent from this model
   if (ts->ready_used == ts->ready_ev.size()) {
@@ -210,6 +213,9 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
   MSQ_TRY(embed_ln<T>(ids, tt, R, Lt, Lj, H, m->word, m->pos, m->type, m->emb_ln.g, m->emb_ln.b, 1e-12f, xf, x0, st));
   MSQ_TRY(dropout_rows<T>(xf, x0, R, Lj, 0, Lt, H, make_drop(dc, DROP_E, 0, dc.p_hidden), st));
   if (mm) {
+    if (c.rn_width) {
+      MSQ_TRY(rn_forward_train<T>(m, images, n_img, img_index, R, st));   // -> ts->y_post = cat(o, o) + position / type embeddings
+    } else {
     // patch embedding per UNIQUE image
     for (int64_t i0 = 0; i0 < n_img; i0 += TRAIN_IMG_CHUNK) {
       const int64_t n = min(TRAIN_IMG_CHUNK, n_img - i0);
@@ -234,6 +240,7 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
       MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.hb, 4 * Wd, wptr<T>(L.proj), L.proj.ld, L.proj.b, t.x1, Wd, xn, Wd, Mv, Wd, 4 * Wd, ACT_NONE, st)));
     }
     MSQ_TRY(layernorm<T>(ts->vx_last, Mv, Wd, m->ln_post.g, m->ln_post.b, 1e-5f, nullptr, (T*)ts->y_post, 0, 0, 0, st));
+    }
     MSQ_TRY((gemm_nt<T, float>(m, (const T*)ts->y_post, Wd, wptr<T>(m->visn_fc), m->visn_fc.ld, m->visn_fc.b, nullptr, 0, ts->visn_pre, H, Mv,
                                H, Wd, ACT_NONE, st)));
     MSQ_TRY(layernorm<T>(ts->visn_pre, Mv, H, m->visn_ln.g, m->visn_ln.b, 1e-12f, xf, x0, Lv, Lj, Lt, st));
@@ -272,16 +279,6 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
 }
 
 // ---- backward --------------------------------------------------------------------------------------
-// attention backward: tensor cores (mma.sync) on the bf16 path, fp32 CUDA cores in the parity mode
-template <typename T>
-static int attn_bwd(const T* qkv, const T* ctx, const T* dctx, int64_t R, int L, int heads, const float* mask, int mask_len, T* dqkv, float* scratch,
-                    cudaStream_t st, const Drop& drop = Drop()) {
-  if constexpr (sizeof(T) == 2) {
-    if (attention_bwd_mma_supported(L)) return attention_bwd_mma(qkv, ctx, dctx, R, L, heads, 0.125f, mask, mask_len, mask_len, dqkv, scratch, st, drop);
-  }
-  return attention_bwd<T>(qkv, dctx, R, L, heads, 0.125f, mask, mask_len, mask_len, dqkv, scratch, st, drop);
-}
-
 template <typename T>
 static int backward_train(msq_model* m, const float* d_lang, const float* d_visn, float* grads, cudaStream_t st) {
   TrainState* ts = m->train;
@@ -380,17 +377,19 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
 
   const std::string v = P + "encoder.visual_model.visual.";
   {
+    const bool rn = c.rn_width != 0;
     float *dWv = G(P + "encoder.visn_fc.visn_fc.weight"), *dbv = G(P + "encoder.visn_fc.visn_fc.bias"),
           *dgv = G(P + "encoder.visn_fc.visn_layer_norm.weight"), *dbl = G(P + "encoder.visn_fc.visn_layer_norm.bias"),
-          *dgp = G(v + "ln_post.weight"), *dbp = G(v + "ln_post.bias");
+          *dgp = rn ? nullptr : G(v + "ln_post.weight"), *dbp = rn ? nullptr : G(v + "ln_post.bias");
     if (err) return err;
     // visn_layer_norm backward on the visual rows of the joint gradient -> d(visn_fc out) [Mv,H] (gB) + operand copy (gT)
     MSQ_TRY(ln_bwd<T>(b.gA, ts->visn_pre, nullptr, Mv, H, m->visn_ln.g, 1e-12f, b.gB, (T*)b.gT, dgv, dbl, b.ln_scr, Lv, Lj, Lt, st));
     MSQ_TRY(wgrad<T>(m, (const T*)b.gT, H, H, (const T*)ts->y_post, Wd, Wd, ACT_NONE, Mv, dWv, dbv, b, st));
     // d(ln_post out) fp32 -> gA is free now: reuse it as [Mv, Wd]
     MSQ_TRY((dgrad<T, float>(m, (const T*)b.gT, H, ts->visnT, Wd, nullptr, b.gA, Mv, st)));
-    MSQ_TRY(ln_bwd<T>(b.gA, ts->vx_last, nullptr, Mv, Wd, m->ln_post.g, 1e-5f, b.gB, (T*)b.gT, dgp, dbp, b.ln_scr, 0, 0, 0, st));
     MSQ_TRY(mark_ready(ts, P + "encoder.visn_fc.visn_fc.weight", P + "encoder.visn_fc.visn_layer_norm.bias", st));
+    if (rn) return rn_backward_train<T>(m, b.gA, grads, st);   // ModifiedResNet tower: attention pool, blocks, stem (train_rn.cu)
+    MSQ_TRY(ln_bwd<T>(b.gA, ts->vx_last, nullptr, Mv, Wd, m->ln_post.g, 1e-5f, b.gB, (T*)b.gT, dgp, dbp, b.ln_scr, 0, 0, 0, st));
   }
   // ViT blocks: stream gradient dx in gB (fp32) + gT (operand copy)
   const int vheads = Wd / 64;
@@ -552,6 +551,13 @@ extern "C" int msq_model_refresh(msq_model* m, void* stream) {
   DevGuard dev_guard__(m);
   MSQ_REQUIRE(m && m->packed, "msq_model_refresh: model not packed");
   return msq::model_weights_changed(m, (cudaStream_t)stream);
+}
+
+extern "C" int msq_train_set_bn_mode(msq_model* m, int32_t use_running_stats, void* stream) {
+  DevGuard dev_guard__(m);
+  MSQ_TRY(ensure_train(m, (cudaStream_t)stream));
+  if (m->train->rn) m->train->rn->bn_eval = use_running_stats != 0;
+  return MSQ_OK;
 }
 
 // head parameters are the tail of the slot table (added after the encoder's); their gradients are final once heads_train returns

@@ -33,6 +33,32 @@ struct SplitK {
   }
 };
 
+// ---- ModifiedResNet tower (train_rn.cu)
+struct RnConvT {     // one convolution + its BatchNorm
+  std::string wname, bn;
+  int cin = 0, cout = 0, k = 1, K = 0, Kp = 0;
+  const float *w = nullptr, *gamma = nullptr, *beta = nullptr, *rmean = nullptr, *rvar = nullptr;   // fp32 masters
+  void *wg = nullptr, *wgT = nullptr;   // GEMM layouts in the operand type: [Cout, Kp] and [Kp, Cout]
+  float* Y = nullptr;                   // tape: pre-BatchNorm output [M, Cout], fp32 in every mode
+  float *mean = nullptr, *rstd = nullptr, *S1 = nullptr, *S2 = nullptr;
+  int64_t M = 0;
+  int HW = 0;
+  float Wtot = 0.f;                     // weighted element count per channel of the materialised batch
+};
+struct RnBlockTape { const void* x; void *o1, *o2, *o2p, *xs, *out; int H, Ho; };
+struct RnTrain {
+  std::vector<RnConvT> convs;           // stem 0..2, then per block conv1, conv2, conv3, [downsample]
+  std::vector<RnBlockTape> blk;
+  std::vector<void*> owned;
+  Arena tape, ws;
+  void *qkvT = nullptr, *cprojT = nullptr;
+  float *wimg = nullptr, *partial = nullptr, *feat = nullptr, *o = nullptr;
+  void *a[3] = {nullptr, nullptr, nullptr}, *x0 = nullptr, *tok = nullptr, *qkv = nullptr, *ctx = nullptr;
+  int64_t n_img = 0, R = 0;
+  bool bn_eval = false;                 // BatchNorm from the running statistics (model.eval() semantics inside a training step)
+};
+void rn_train_free(RnTrain* r);
+
 struct ParaTape { float *xin, *y, *qkv, *ctx, *out, *pn, *u, *xo, *hf; };   // hf: dropped FFN activations (dropout only)
 struct HeadTape {
   int64_t B = 0;
@@ -75,6 +101,7 @@ struct TrainState {
   Arena htape;
   HeadTape ht;
   SplitK splitk;
+  RnTrain* rn = nullptr;                 // ModifiedResNet tower state (cfg.rn_width != 0)
   // ---- dropout (msq_train_set_dropout): probabilities + seed; `step` is the counter of the forward whose masks are live
   DropCfg drop;
   uint32_t drop_next_step = 0;
@@ -89,6 +116,7 @@ struct TrainState {
 inline void train_state_free_impl(TrainState* ts) {
   if (!ts) return;
   for (void* p : ts->owned) cudaFree(p);
+  rn_train_free(ts->rn);
   for (cudaEvent_t e : ts->ready_ev) cudaEventDestroy(e);
   if (ts->adam_m) cudaFree(ts->adam_m);
   if (ts->adam_v) cudaFree(ts->adam_v);
@@ -224,6 +252,24 @@ template <typename T, typename TO>
 static int dgrad(const msq_model* m, const T* G, int Nout, const void* WT, int Kin, const float* resid, TO* dX, int64_t M, cudaStream_t st) {
   return gemm_nt<T, TO>(m, G, Nout, (const T*)WT, Nout, nullptr, resid, Kin, dX, Kin, M, Kin, Nout, ACT_NONE, st);
 }
+
+// attention backward: tensor cores (mma.sync) on the bf16 path, fp32 CUDA cores in the parity mode
+template <typename T>
+static int attn_bwd(const T* qkv, const T* ctx, const T* dctx, int64_t R, int L, int heads, const float* mask, int mask_len, T* dqkv, float* scratch,
+                    cudaStream_t st, const Drop& drop = Drop()) {
+  if constexpr (sizeof(T) == 2) {
+    if (attention_bwd_mma_supported(L)) return attention_bwd_mma(qkv, ctx, dctx, R, L, heads, 0.125f, mask, mask_len, mask_len, dqkv, scratch, st, drop);
+  }
+  return attention_bwd<T>(qkv, dctx, R, L, heads, 0.125f, mask, mask_len, mask_len, dqkv, scratch, st, drop);
+}
+// mark the slots [first, last] (by name) final (train.cu)
+int mark_ready(TrainState* ts, const std::string& first, const std::string& last, cudaStream_t st);
+// ---- train_rn.cu
+std::vector<std::string> rn_param_names(const msq_model* m);
+template <typename T> int rn_train_build(msq_model* m, cudaStream_t st);
+template <typename T> int rn_train_refresh(msq_model* m, cudaStream_t st);
+template <typename T> int rn_forward_train(msq_model* m, const float* images, int64_t n_img, const int32_t* img_index, int64_t R, cudaStream_t st);
+template <typename T> int rn_backward_train(msq_model* m, const float* dyp, float* grads, cudaStream_t st);
 
 // ---- train_heads.cu
 int heads_train_setup(msq_model* m, bool alloc, cudaStream_t st);

@@ -375,6 +375,12 @@ class OrderingEngine:
             _lib.check(self.lib.msq_train_set_dropout(self._h, float(p_hidden), float(p_attn), float(p_para), int(seed) & 0xFFFFFFFF,
                                                       self._stream()))
 
+    def set_bn_mode(self, use_running_stats=False):
+        """BatchNorm of the ModifiedResNet tower inside training steps: batch statistics (False, nn.BatchNorm2d.train(), what the
+        reference fine-tunes with) or the frozen running statistics (True, eval() semantics)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.msq_train_set_bn_mode(self._h, 1 if use_running_stats else 0, self._stream()))
+
     def dropout_step(self):
         """counter that keyed the masks of the last training forward (-1: none yet); what oracle.dropout.DropSpec needs"""
         return int(self.lib.msq_train_dropout_step(self._h))

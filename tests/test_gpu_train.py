@@ -30,9 +30,12 @@ def _cfg_from_golden(g):
                 vit=g.get("vit"), rn=g.get("rn"), para_ff=g["ff_size"])
 
 
-def _ocfg(g):
+def _ocfg(g, bn_train=None):
     c = g["cfg"]
-    return dict(num_hidden_layers=c["num_hidden_layers"], num_attention_heads=c["num_attention_heads"], vit=g.get("vit"))
+    rn = g.get("rn")
+    if rn is not None and bn_train is not None:
+        rn = dict(rn, bn_train=bn_train)
+    return dict(num_hidden_layers=c["num_hidden_layers"], num_attention_heads=c["num_attention_heads"], vit=g.get("vit"), rn=rn)
 
 
 def _ragged(n_steps, vocab, seed):
@@ -235,6 +238,51 @@ def test_multimodal_train_step_vs_reference_pinned_oracle(golden_dir, precise):
     worst = _compare(got, ref, 5e-4 if precise else 1e-1)
     print("multimodal train step (%s): loss %.6f (reference %.6f), worst relative L2 %.2e at %s" %
           ("fp32" if precise else "bf16", loss, r["loss"], worst[1], worst[0]))
+
+
+@pytest.mark.parametrize("bn_train", [True, False])
+@pytest.mark.parametrize("precise", [True, False])
+def test_resnet_train_step_vs_reference_pinned_oracle(golden_dir, precise, bn_train):
+    """Fine-tuning step through the ModifiedResNet tower (the reference's wired backbone): loss and EVERY parameter gradient
+    against torch autograd through the oracle, on the batch of the reference-generated fixtures (grads_tiny.pt 'mm_rn_bntrain':
+    nn.BatchNorm2d in train() mode, the mode the reference fine-tunes in; 'mm_rn': frozen running statistics)."""
+    g = torch.load(os.path.join(golden_dir, "mm_rn_tiny.pt"), weights_only=False)
+    r = torch.load(os.path.join(golden_dir, "grads_tiny.pt"), weights_only=False)["mm_rn_bntrain" if bn_train else "mm_rn"]
+    eng = _engine(g["sd"], _cfg_from_golden(g), precise)
+    eng.set_bn_mode(use_running_stats=not bn_train)
+    ids, labels, images = O.synthetic_manuals(r["B"], r["N"], r["L"], vocab=1000, image_px=224, seed=r["seed"])
+    pb = eng.prepare(ids, labels, r["N"], images)
+    grads = eng.new_grad_buffer()
+    loss = float(eng.train_step(pb, grads))
+    torch.cuda.synchronize()
+    oloss, ref = TO.loss_grads(g["sd"], _ocfg(g, bn_train), O.prepare_inputs(ids, labels, r["N"], images))
+    assert abs(oloss - r["loss"]) < 2e-5                            # the oracle reproduces the reference's loss ...
+    assert abs(loss - r["loss"]) < (5e-5 if precise else 2e-2)     # ... and so does the CUDA path
+    got = eng.grads_by_name(grads)
+    assert set(got) == set(r["grads"]) - {"bert.pooler.dense.weight", "bert.pooler.dense.bias"}, sorted(set(got) ^ set(r["grads"]))
+    # fp32, batch statistics: the BatchNorm backward subtracts the mean and the xhat-projection of the incoming gradient, so the
+    # convolution gradients in front of it are small differences of large fp32 sums -- against a float64 run BOTH the fp32
+    # oracle and the fp32 reference are 2-4e-3 away on the tower's early layers (tests/test_train_oracle.py), hence 1e-2 here;
+    # frozen statistics have no such cancellation: 5e-4.  bf16, frozen statistics: 1e-1 (13 convolutions deep).
+    # bf16 + batch statistics ON THIS FIXTURE (one manual, 5 images, 8-128 channels, random init): the fp32 run above shows a
+    # condition number of ~5e4 (6e-8 -> 7e-3) for everything in front of the last BatchNorm, i.e. bf16's 4e-3 per operand
+    # leaves those gradients noise-dominated in ANY bf16 implementation; they are bounded loosely (0.75: no blow-up, no
+    # sign flip of the bulk), while the loss and every gradient behind the tower stay within 1.5e-1.
+    tower = "visual_model.visual."
+    if precise or not bn_train:
+        worst = _compare(got, ref, (1e-2 if bn_train else 5e-4) if precise else 1e-1)
+    else:
+        worst = _compare({n: v for n, v in got.items() if tower not in n or "attnpool" in n}, ref, 1.5e-1)
+        worst_t = _compare({n: v for n, v in got.items() if tower in n and "attnpool" not in n}, ref, 0.75)
+        print("  tower convolutions / BatchNorms (noise-dominated in bf16, see above): worst %.2e at %s" % (worst_t[1], worst_t[0]))
+    print("ResNet train step (%s, BatchNorm %s): loss %.6f (reference %.6f), worst relative L2 %.2e at %s" %
+          ("fp32" if precise else "bf16", "batch statistics" if bn_train else "running statistics", loss, r["loss"], worst[1], worst[0]))
+    if precise:   # directly against the reference's own numbers (norms + strided samples)
+        for n, s_ in r["grads"].items():
+            if n not in got:
+                continue
+            a = got[n].detach().double().cpu().reshape(-1)
+            assert abs(float(a.norm()) - s_["norm"]) <= (1e-2 if bn_train else 1e-3) * s_["norm"] + 1e-7, n
 
 
 def test_fine_tuning_lowers_the_loss(golden_dir):
