@@ -230,8 +230,10 @@ int64_t msq_train_dropout_step(msq_model* m);
  * (use_running_stats = 0): nn.BatchNorm2d in train() mode, the mode trainers/train.py fine-tunes in -- statistics of the
  * batch of MATERIALISED pair images (mean and biased variance over N, H, W; the tower itself runs on the unique images with
  * their pair multiplicities as weights), gradients flow through the statistics.  use_running_stats = 1: eval() semantics
- * (frozen running statistics) with the same backward pass otherwise.  Running statistics are never modified by this
- * library: a caller that needs the reference's momentum update applies it to its own buffers.  No-op for other backbones. */
+ * (frozen running statistics) with the same backward pass otherwise.  In batch-statistics mode every training forward also
+ * moves the registered running_mean / running_var masters (momentum 0.1, unbiased batch variance, as nn.BatchNorm2d does);
+ * msq_train_read_param returns them, the packed evaluation weights pick them up at the next re-pack (msq_adamw_step /
+ * msq_model_refresh).  No-op for other backbones. */
 int msq_train_set_bn_mode(msq_model* m, int32_t use_running_stats, void* stream);
 
 /* Data-parallel overlap: msq_train_step records one CUDA event per REGION of the flat gradient buffer at the moment that

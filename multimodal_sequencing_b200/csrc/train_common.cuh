@@ -56,6 +56,7 @@ struct RnTrain {
   void *a[3] = {nullptr, nullptr, nullptr}, *x0 = nullptr, *tok = nullptr, *qkv = nullptr, *ctx = nullptr;
   int64_t n_img = 0, R = 0;
   bool bn_eval = false;                 // BatchNorm from the running statistics (model.eval() semantics inside a training step)
+  float bn_momentum = 0.1f;             // running-statistics update of a training forward (nn.BatchNorm2d default); 0 = frozen
 };
 void rn_train_free(RnTrain* r);
 

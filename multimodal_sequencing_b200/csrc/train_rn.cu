@@ -15,7 +15,7 @@
 // w-weighted ones and, because the upstream gradient of a unique image already is the sum over its copies,
 //     dY_u = gamma rstd (dz_u - (w_u / W) (S1 + xhat_u S2)),   S1 = sum dz, S2 = sum dz xhat (plain sums),  W = sum_i w_i H W
 // is exactly the sum of the materialised copies' gradients.  Column reductions are two-stage with a fixed order (deterministic).
-// BatchNorm running statistics are NOT updated (they do not enter the training-mode forward; the drop-in documents it).
+// BatchNorm running statistics follow every training forward (momentum 0.1, unbiased batch variance) like nn.BatchNorm2d.train().
 #include <type_traits>
 
 #include "train_common.cuh"
@@ -140,6 +140,17 @@ __global__ void rn_running_stats_kernel(const float* __restrict__ rm, const floa
   pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) { mean[c] = rm[c]; rstd[c] = rsqrtf(rv[c] + eps); }
+}
+
+// nn.BatchNorm2d train() bookkeeping: running = (1 - momentum) running + momentum batch (UNBIASED batch variance, n = W)
+__global__ void rn_running_update_kernel(const float* __restrict__ mean, const float* __restrict__ rstd, int C, float eps, float Wtot, float mom,
+                                         float* __restrict__ rm, float* __restrict__ rv) {
+  pdl_sync();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float var = 1.0f / (rstd[c] * rstd[c]) - eps;
+  rm[c] = (1.f - mom) * rm[c] + mom * mean[c];
+  rv[c] = (1.f - mom) * rv[c] + mom * var * (Wtot / fmaxf(Wtot - 1.f, 1.f));
 }
 
 // ---- out = act( bn_a(ya) + [bn_b(yb) | xres] ), four channels per thread
@@ -506,6 +517,12 @@ int conv_stats(msq_model* m, RnTrain* r, RnConvT& cv, const T* A, int64_t M, int
   }
   MSQ_TRY((colred<T, 0>((const float*)cv.Y, nullptr, nullptr, nullptr, nullptr, r->wimg, HW, M, cv.cout, Wtot, r->partial, cv.mean, nullptr, nullptr, nullptr, st)));
   MSQ_TRY((colred<T, 1>((const float*)cv.Y, nullptr, nullptr, cv.mean, nullptr, r->wimg, HW, M, cv.cout, Wtot, r->partial, cv.rstd, nullptr, nullptr, nullptr, st)));
+  if (r->bn_momentum > 0.f) {   // the module's running statistics follow the batch, as nn.BatchNorm2d.train() does (the fp32 masters are updated
+                                // in place; the packed evaluation weights pick them up at the next re-pack)
+    MSQ_CUDA(launch_k(rn_running_update_kernel, dim3(ceil_div(cv.cout, 128)), dim3(128), 0, st, (const float*)cv.mean, (const float*)cv.rstd, cv.cout,
+                      1e-5f, Wtot, r->bn_momentum, const_cast<float*>(cv.rmean), const_cast<float*>(cv.rvar)));
+    MSQ_LAUNCH_CHECK();
+  }
   return MSQ_OK;
 }
 template <typename T>

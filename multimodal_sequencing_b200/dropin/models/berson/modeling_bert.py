@@ -350,12 +350,24 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
             eng.set_dropout(*probs, seed=torch.initial_seed() & 0xFFFFFFFF)
             self.__dict__["_drop_key"] = key
 
+    def _pull_bn_buffers(self, eng, count=True):
+        """ModifiedResNet tower: a training forward moved the library's running_mean / running_var (nn.BatchNorm2d.train()
+        bookkeeping, clip/model.py:10-53); mirror them in this module's buffers so that state_dict() / the next weight refresh
+        carry them, and advance num_batches_tracked as torch does."""
+        with torch.no_grad():
+            for n, b in self.named_buffers():
+                if n.endswith("running_mean") or n.endswith("running_var"):
+                    b.copy_(eng.read_param(n, tuple(b.shape)))
+                elif count and n.endswith("num_batches_tracked"):
+                    b += 1
+
     def _train_forward(self, pb):
         eng = self.engine()
         self._apply_dropout_config(eng)
         flat = eng.new_grad_buffer()
         with torch.no_grad():
             loss = eng.train_step(pb, flat, self.pairwise_loss_lam)
+        self._pull_bn_buffers(eng)
         lay = {n: (o, k) for n, o, k, _ in eng.train_layout()}
         named = list(self.named_parameters())
         spans = [lay.get(n) for n, _ in named]    # None: the reference gives this parameter no gradient either
@@ -387,6 +399,9 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
             loss = eng.train_step(pb, flat, self.pairwise_loss_lam)
             scale = allreduce_gradients(flat) if allreduce else 1.0
             eng.adamw_step(flat, lr, betas, eps, weight_decay, max_grad_norm, scale if grad_scale is None else grad_scale)
+        for n, b in self.named_buffers():
+            if n.endswith("num_batches_tracked"):
+                b += 1
         return loss
 
     def pull_weights(self):
@@ -396,6 +411,7 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
             for n, p in self.named_parameters():
                 if any(n == k for k, _, _, _ in eng.train_layout()):
                     p.data.copy_(eng.read_param(n, tuple(p.shape)))
+        self._pull_bn_buffers(eng, count=False)
         # both sides hold the same values again: the nn.Parameters are the masters from here on
         tensors = list(self.parameters()) + list(self.buffers())
         self.__dict__["_eng_vers"] = tuple((t._version, t.data_ptr()) for t in tensors)

@@ -266,15 +266,20 @@ def test_resnet_train_step_vs_reference_pinned_oracle(golden_dir, precise, bn_tr
     # frozen statistics have no such cancellation: 5e-4.  bf16, frozen statistics: 1e-1 (13 convolutions deep).
     # bf16 + batch statistics ON THIS FIXTURE (one manual, 5 images, 8-128 channels, random init): the fp32 run above shows a
     # condition number of ~5e4 (6e-8 -> 7e-3) for everything in front of the last BatchNorm, i.e. bf16's 4e-3 per operand
-    # leaves those gradients noise-dominated in ANY bf16 implementation; they are bounded loosely (0.75: no blow-up, no
-    # sign flip of the bulk), while the loss and every gradient behind the tower stay within 1.5e-1.
+    # leaves those gradients noise-dominated in ANY bf16 implementation; their concatenation is bounded loosely (0.6: no
+    # blow-up, no sign flip of the bulk), while the loss and every gradient behind the tower stay within 1.5e-1.
     tower = "visual_model.visual."
     if precise or not bn_train:
         worst = _compare(got, ref, (1e-2 if bn_train else 5e-4) if precise else 1e-1)
     else:
         worst = _compare({n: v for n, v in got.items() if tower not in n or "attnpool" in n}, ref, 1.5e-1)
-        worst_t = _compare({n: v for n, v in got.items() if tower in n and "attnpool" not in n}, ref, 0.75)
-        print("  tower convolutions / BatchNorms (noise-dominated in bf16, see above): worst %.2e at %s" % (worst_t[1], worst_t[0]))
+        names = [n for n in got if tower in n and "attnpool" not in n]
+        a = torch.cat([got[n].detach().float().cpu().reshape(-1) for n in names])
+        b = torch.cat([ref[n].float().reshape(-1) for n in names])
+        assert bool(torch.isfinite(a).all())
+        rel = float((a - b).norm() / b.norm())
+        print("  tower convolutions / BatchNorms (noise-dominated in bf16, see above): relative L2 of the concatenated gradient %.2e" % rel)
+        assert rel <= 0.6, rel
     print("ResNet train step (%s, BatchNorm %s): loss %.6f (reference %.6f), worst relative L2 %.2e at %s" %
           ("fp32" if precise else "bf16", "batch statistics" if bn_train else "running statistics", loss, r["loss"], worst[1], worst[0]))
     if precise:   # directly against the reference's own numbers (norms + strided samples)
@@ -283,6 +288,36 @@ def test_resnet_train_step_vs_reference_pinned_oracle(golden_dir, precise, bn_tr
                 continue
             a = got[n].detach().double().cpu().reshape(-1)
             assert abs(float(a.norm()) - s_["norm"]) <= (1e-2 if bn_train else 1e-3) * s_["norm"] + 1e-7, n
+
+
+def test_resnet_running_statistics_follow_the_batch(golden_dir):
+    """nn.BatchNorm2d.train() bookkeeping: after one training forward the registered running_mean / running_var of the stem's
+    first two BatchNorms equal torch's own update (momentum 0.1, unbiased batch variance) over the MATERIALISED pair images."""
+    import torch.nn.functional as F
+    g = torch.load(os.path.join(golden_dir, "mm_rn_tiny.pt"), weights_only=False)
+    sd = g["sd"]
+    eng = _engine(sd, _cfg_from_golden(g), True)
+    ids, labels, images = O.synthetic_manuals(1, 5, 16, vocab=1000, image_px=224, seed=65)
+    pb = eng.prepare(ids, labels, 5, images)
+    eng.train_step(pb, eng.new_grad_buffer())
+    torch.cuda.synchronize()
+    v = "bert.encoder.visual_model.visual."
+    x = pb.images[pb.img_index.reshape(-1).long()].cpu()                      # every image once per pair slot
+    for i, stride in ((1, 2), (2, 1)):
+        y = F.conv2d(x, sd[v + "conv%d.weight" % i], stride=stride, padding=1)
+        rm, rv = sd[v + "bn%d.running_mean" % i].clone(), sd[v + "bn%d.running_var" % i].clone()
+        x = torch.relu(F.batch_norm(y, rm, rv, sd[v + "bn%d.weight" % i], sd[v + "bn%d.bias" % i], training=True, momentum=0.1, eps=1e-5))
+        got_m = eng.read_param(v + "bn%d.running_mean" % i, tuple(rm.shape)).cpu()
+        got_v = eng.read_param(v + "bn%d.running_var" % i, tuple(rv.shape)).cpu()
+        assert (got_m - rm).abs().max() <= 1e-5 * max(1.0, float(rm.abs().max())), (i, got_m, rm)
+        assert (got_v - rv).abs().max() <= 1e-5 * max(1.0, float(rv.abs().max())), (i, got_v, rv)
+        assert (got_m - sd[v + "bn%d.running_mean" % i]).abs().max() > 1e-4      # they did move
+    # frozen statistics: nothing moves
+    eng2 = _engine(sd, _cfg_from_golden(g), True)
+    eng2.set_bn_mode(use_running_stats=True)
+    eng2.train_step(pb, eng2.new_grad_buffer())
+    torch.cuda.synchronize()
+    assert torch.equal(eng2.read_param(v + "bn1.running_mean", tuple(sd[v + "bn1.running_mean"].shape)).cpu(), sd[v + "bn1.running_mean"])
 
 
 def test_fine_tuning_lowers_the_loss(golden_dir):
