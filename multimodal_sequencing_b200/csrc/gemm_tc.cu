@@ -253,7 +253,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + TC_A_BYTES;
-          if (PAIR) {
+          if (PAIR && ep.tn) {
+            // MN-major operands on a CTA pair: every CTA stages the 128 M columns / 128 N columns of its half of the tile as
+            // boxes of 64 contraction rows x 64 columns
+            const uint32_t lead_full = mapa_rank(full0 + 8 * stage, 0);
+            if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * STAGE_BYTES);
+#pragma unroll
+            for (int i = 0; i < TC_BM / 64; ++i) tma_load_2d_pair(sa + i * 8192, &tma_a, a_row + i * 64, kb * TC_BK, lead_full);
+#pragma unroll
+            for (int i = 0; i < Cfg::B_ROWS / 64; ++i) tma_load_2d_pair(sb + i * 8192, &tma_b, b_row + i * 64, kb * TC_BK, lead_full);
+          } else if (PAIR) {
             const uint32_t lead_full = mapa_rank(full0 + 8 * stage, 0);
             if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * STAGE_BYTES);
             tma_load_2d_pair(sa, &tma_a, ka + kb * TC_BK, a_row, lead_full);
@@ -279,7 +288,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0 && rank == 0) {
       // instruction descriptor: D=F32 [4,6), A=BF16 [7,10), B=BF16 [10,13), K-major A/B, N>>3 [17,23), M>>4 [24,29)
       // TN mode: A and B MN-major (bits 15, 16)
-      const bool tn = !PAIR && ep.tn;
+      const bool tn = ep.tn != 0;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(Cfg::TILE_M >> 4) << 24) |
                              (tn ? ((1u << 15) | (1u << 16)) : 0u);
       int stage = 0, acc = 0;
@@ -729,6 +738,11 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   // CTA pairs pay off once there are enough 256 x 256 tiles to occupy most SM pairs
   const int64_t pair_tiles = (int64_t)ceil_div(g.M, 256) * ceil_div(g.N, TC_BN);
   if (!g.tn && !force_single && pair_tiles >= sms / 4) return launch_gemm_tc<TO, true>(g, sms, st);
+  // MN-major operands (weight gradients): the output is a few dozen tiles and the split-K slices of one gradient run side by
+  // side on auxiliary streams, so the pair form is chosen on shape alone (whole 256 x 256 tiles), not on the tile count
+  static int tn_pair = -1;
+  if (tn_pair < 0) { const char* e = getenv("MSQ_WGRAD_PAIR"); tn_pair = (e && e[0] == '0') ? 0 : 1; }
+  if (g.tn && tn_pair && !force_single && g.M % 256 == 0 && g.N % 256 == 0) return launch_gemm_tc<TO, true>(g, sms, st);
   return launch_gemm_tc<TO, false>(g, sms, st);
 }
 template int gemm_tc<float>(const GemmArgs&, cudaStream_t);

@@ -23,6 +23,8 @@ eng = OrderingEngine(synth.full_state_dict(cfg, vit, seed=0), cfg, precise=False
 ids, labels, images = O.synthetic_manuals(B, 6, 64, image_px=224, seed=1)
 pb = eng.prepare(ids, labels, 6, images).to(eng.device)
 grads = eng.new_grad_buffer()
+if os.environ.get("MSQ_PROFILE_DROPOUT", "1") == "1":
+    eng.set_dropout(0.1, 0.1, 0.1, seed=1234)   # the reference's fine-tuning workload (bench.py --config 3)
 
 
 def step():
