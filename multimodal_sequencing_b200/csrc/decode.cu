@@ -569,37 +569,29 @@ __global__ void __launch_bounds__(512, 1) dec_select_kernel(DecodeWeights w, Dec
       const float* a2 = t >= 2 ? t4 + ((int64_t)seq[wslot][t - 2] * N + k) * H4 + H : nullptr;
       const float* k0 = io.key0 + (b * N + k) * (int64_t)H;
       float part = 0.f;
-      for (int d0 = lane; d0 < H; d0 += 32 * 4) {
-        float qv[4], a1v[4], a2v[4], kv[4], wv[4], fs[4], gs[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int d = d0 + 32 * u;
-          const bool ok = d < H;
-          kv[u] = ok ? __ldg(k0 + d) : 0.f;
-          wv[u] = ok ? __ldg(w.wt + d) : 0.f;
-          qv[u] = ok ? qp[d] : 0.f;
-          a1v[u] = (ok && a1) ? __ldg(a1 + d) : 0.f;
-          a2v[u] = (ok && a2) ? __ldg(a2 + d) : 0.f;
-          fs[u] = 0.f; gs[u] = 0.f;
-        }
+      // four consecutive features per lane and 128 per warp pass (H % 4 == 0, every row 16-byte aligned): one 16-byte load per
+      // operand instead of four 4-byte loads -- the kernel is issue-bound, and loads were ~40 % of its instructions
+      for (int d0 = 4 * lane; d0 < H; d0 += 128) {
+        const float4 kv = __ldg(reinterpret_cast<const float4*>(k0 + d0)), wv = __ldg(reinterpret_cast<const float4*>(w.wt + d0));
+        const float4 qv = *reinterpret_cast<const float4*>(qp + d0);
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 a1v = a1 ? __ldg(reinterpret_cast<const float4*>(a1 + d0)) : z4, a2v = a2 ? __ldg(reinterpret_cast<const float4*>(a2 + d0)) : z4;
+        float4 fs = z4, gs = z4;
 #pragma unroll
         for (int j = 0; j < DC_MAXN; ++j) {
           if (j < N && (need >> j & 1u)) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int d = d0 + 32 * u;
-              if (d < H) { fs[u] += Fs[(size_t)j * H + d]; gs[u] += Gs[(size_t)j * H + d]; }
-            }
+            const float4 f = *reinterpret_cast<const float4*>(Fs + (size_t)j * H + d0), g = *reinterpret_cast<const float4*>(Gs + (size_t)j * H + d0);
+            fs.x += f.x; fs.y += f.y; fs.z += f.z; fs.w += f.w;
+            gs.x += g.x; gs.y += g.y; gs.z += g.z; gs.w += g.w;
           }
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (d0 + 32 * u < H) {
-            float key = div_n(fs[u]) + div_n(gs[u]);
-            if (a1) key += a1v[u];
-            if (a2) key += a2v[u];
-            part = fmaf(wv[u], tanhf(qv[u] + key + kv[u]), part);
-          }
+        float4 key = make_float4(div_n(fs.x) + div_n(gs.x), div_n(fs.y) + div_n(gs.y), div_n(fs.z) + div_n(gs.z), div_n(fs.w) + div_n(gs.w));
+        if (a1) { key.x += a1v.x; key.y += a1v.y; key.z += a1v.z; key.w += a1v.w; }
+        if (a2) { key.x += a2v.x; key.y += a2v.y; key.z += a2v.z; key.w += a2v.w; }
+        part = fmaf(wv.x, tanhf(qv.x + key.x + kv.x), part);
+        part = fmaf(wv.y, tanhf(qv.y + key.y + kv.y), part);
+        part = fmaf(wv.z, tanhf(qv.z + key.z + kv.z), part);
+        part = fmaf(wv.w, tanhf(qv.w + key.w + kv.w), part);
       }
       part = warp_sum(part);
       if (lane == 0) e[wslot][k] = part + w.bt;
