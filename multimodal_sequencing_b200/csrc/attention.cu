@@ -405,14 +405,17 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
 // the serial chain S -> softmax -> PV of attention_tc_kernel (one tile in flight, 20 % tensor pipe) becomes a pipeline.
 // TMEM columns: S0 [0,128) | S1 [128,256) | O[tile parity][key block] 4 x 64 at [256,512).
 // ---------------------------------------------------------------------------------------------------
-template <int KP> struct AttnWsCfg {
+// SPL = false: plain bf16 operands (one MMA pass, one plane): an item is half as large, so TWO items are resident at every
+// sequence length and the next item's tiles are always in flight while the current one is computed.
+template <int KP, bool SPL = true> struct AttnWsCfg {
   static constexpr int NKB = KP / 128;                 // key blocks per item
   static constexpr int QT = KP / 128;                  // query tiles resident per item
-  static constexpr int STAGES = 256 / KP;              // items resident in shared memory
+  static constexpr int PLANES = SPL ? 2 : 1;           // hi plane (, lo plane)
+  static constexpr int STAGES = SPL ? 256 / KP : 2;    // items resident in shared memory
   static constexpr int TILE = 128 * 64 * 2;            // 128 rows x 64 dims of bf16, 128B swizzle
   static constexpr int PLANE = (QT + 2 * NKB) * TILE;  // Q tiles | K blocks | V blocks of one plane
-  static constexpr int STAGE_BYTES = 2 * PLANE;        // hi plane, lo plane
-  static constexpr int OPER = STAGES * STAGE_BYTES;    // 192 KB
+  static constexpr int STAGE_BYTES = PLANES * PLANE;
+  static constexpr int OPER = STAGES * STAGE_BYTES;    // <= 192 KB
   static constexpr int STG_OFF = OPER;                 // epilogue staging: one 32-row x 128-byte box per epilogue warp (1024-aligned)
   static constexpr int MASK_OFF = STG_OFF + 4 * 4096, STATS_OFF = MASK_OFF + 2 * 128 * 4, BAR_OFF = STATS_OFF + 4 * 2 * 128 * 8;
   static constexpr int SMEM = BAR_OFF + 256 + 1024;
@@ -458,13 +461,15 @@ __device__ __forceinline__ void umma_bf16_acc(uint32_t tmem_d, uint64_t a, uint6
   }
 }
 
-template <int KP>
-__global__ void __launch_bounds__(AttnWsCfg<KP>::THREADS, 1)
+template <int KP, bool SPL, bool DROP>
+__global__ void __launch_bounds__(AttnWsCfg<KP, SPL>::THREADS, 1)
 attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                     const __grid_constant__ CUtensorMap map_ctx, int L, int heads,
                     float scale_l2e, const float* __restrict__ mask_add, int mask_ld, int mask_len, bf16* __restrict__ ctx,
-                    int n_items, long long* trace) {
-  using Cfg = AttnWsCfg<KP>;
+                    int n_items, long long* trace, Drop drop) {
+  using Cfg = AttnWsCfg<KP, SPL>;
+  static_assert(!(SPL && DROP), "dropout is a training-path (bf16) feature");
+  constexpr int PLANES = Cfg::PLANES;
 #ifdef MSQ_ATTN_TRACE
   // event trace of CTA 0 (development aid): trace[role][n][k] = clock64 at event k of block / tile n
 #define TR(role, n, k) do { if (blockIdx.x == 0 && (n) < 64) trace[((role) * 64 + (n)) * 8 + (k)] = clock64(); } while (0)
@@ -518,17 +523,17 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         const int row0 = (item / heads) * L, hh = item % heads;
         const uint32_t st0 = base + s * Cfg::STAGE_BYTES;
         mbar_wait(qk_empty + 8 * s, (u & 1) ^ 1);
-        mbar_expect_tx(qk_full + 8 * s, (uint32_t)(2 * (nqt + NKB) * TILE));
+        mbar_expect_tx(qk_full + 8 * s, (uint32_t)(PLANES * (nqt + NKB) * TILE));
 #pragma unroll
-        for (int pl = 0; pl < 2; ++pl) {
+        for (int pl = 0; pl < PLANES; ++pl) {
           tma_load_2d(st0 + pl * PLANE + QT * TILE, &map_kv, pl * lo + heads * AT_D + hh * AT_D, row0, qk_full + 8 * s);
           for (int qt = 0; qt < nqt; ++qt)
             tma_load_2d(st0 + pl * PLANE + qt * TILE, &map_q, pl * lo + hh * AT_D, row0 + qt * 128, qk_full + 8 * s);
         }
         mbar_wait(v_empty + 8 * s, (u & 1) ^ 1);
-        mbar_expect_tx(v_full + 8 * s, (uint32_t)(2 * NKB * TILE));
+        mbar_expect_tx(v_full + 8 * s, (uint32_t)(PLANES * NKB * TILE));
 #pragma unroll
-        for (int pl = 0; pl < 2; ++pl)
+        for (int pl = 0; pl < PLANES; ++pl)
           tma_load_2d(st0 + pl * PLANE + (QT + NKB) * TILE, &map_kv, pl * lo + 2 * heads * AT_D + hh * AT_D, row0, v_full + 8 * s);
       }
     }
@@ -551,12 +556,14 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         const uint64_t qh = dk0 + (uint64_t)((s * Cfg::STAGE_BYTES + qt * TILE) >> 4), ql = qh + (PLANE >> 4);
         const uint64_t kh = dk0 + (uint64_t)((s * Cfg::STAGE_BYTES + (QT + kb) * TILE) >> 4), kl = kh + (PLANE >> 4);
         if (elect_one()) {
+          if (SPL) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_acc<false>(d, qh + 2 * k, kl + 2 * k, idesc_s, k != 0);
+            for (int k = 0; k < 4; ++k) umma_bf16_acc<false>(d, qh + 2 * k, kl + 2 * k, idesc_s, k != 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_acc<false>(d, ql + 2 * k, kh + 2 * k, idesc_s, true);
+            for (int k = 0; k < 4; ++k) umma_bf16_acc<false>(d, ql + 2 * k, kh + 2 * k, idesc_s, true);
+          }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_acc<false>(d, qh + 2 * k, kh + 2 * k, idesc_s, true);
+          for (int k = 0; k < 4; ++k) umma_bf16_acc<false>(d, qh + 2 * k, kh + 2 * k, idesc_s, SPL || k != 0);
           umma_commit(s_full + 8 * (n & 1));
           if (qt == nqt - 1 && kb == NKB - 1) umma_commit(qk_empty + 8 * s);   // Q / K of this item have been read
         }
@@ -575,15 +582,17 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         // P of 32-key chunk j: hi plane in columns [32 j, 32 j + 16), lo plane in [32 j + 16, 32 j + 32); 16 keys = 8 columns;
         // 16 keys of V (MN-major) = 2048 bytes
         if (elect_one()) {
+          if (SPL) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_bf16_acc<true>(d, (uint64_t)(p + 32 * (kk >> 1) + 8 * (kk & 1)), vl + 128 * kk, idesc_o, kk != 0);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_bf16_acc<true>(d, (uint64_t)(p + 32 * (kk >> 1) + 16 + 8 * (kk & 1)), vh + 128 * kk, idesc_o, true);
+          }
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_bf16_acc<true>(d, (uint64_t)(p + 32 * (kk >> 1) + 8 * (kk & 1)), vl + 128 * kk, idesc_o, kk != 0);
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_bf16_acc<true>(d, (uint64_t)(p + 32 * (kk >> 1) + 16 + 8 * (kk & 1)), vh + 128 * kk, idesc_o, true);
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_bf16_acc<true>(d, (uint64_t)(p + 32 * (kk >> 1) + 8 * (kk & 1)), vh + 128 * kk, idesc_o, true);
+            umma_bf16_acc<true>(d, (uint64_t)(p + 32 * (kk >> 1) + 8 * (kk & 1)), vh + 128 * kk, idesc_o, SPL || kk != 0);
           if (kb == NKB - 1) umma_commit(o_full + 8 * (t & 1));
           if (qt == nqt - 1 && kb == NKB - 1) umma_commit(v_empty + 8 * s);    // V of this item has been read
         }
@@ -649,35 +658,37 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       if (gtid == 0) TR(1, n, 2);
       // ---- pass 2: p = 2^(s c + mask - max), hi / lo planes written over the chunk's own S columns
       float sum = 0.f;
+      const int qrow = (t % nqt) * 128 + row;   // query index inside the item (dropout element index)
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
         uint32_t raw[32], ph[16], pl[16];
         tmem_ld32(sb + j * 32, raw);
-        if (masked || key0 + j * 32 + 32 > L) {
+        const bool slow = masked || key0 + j * 32 + 32 > L;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), scale_l2e, mk[j * 32 + 2 * i]) - mx);
-            const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), scale_l2e, mk[j * 32 + 2 * i + 1]) - mx);
-            sum += p0 + p1;
-            const __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);  // .x (low half) = even key
-            const __nv_bfloat162 c = __floats2bfloat162_rn(p0 - __low2float(b), p1 - __high2float(b));
-            ph[i] = *reinterpret_cast<const uint32_t*>(&b);
-            pl[i] = *reinterpret_cast<const uint32_t*>(&c);
+        for (int i = 0; i < 16; ++i) {
+          float p0, p1;
+          if (slow) {
+            p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), scale_l2e, mk[j * 32 + 2 * i]) - mx);
+            p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), scale_l2e, mk[j * 32 + 2 * i + 1]) - mx);
+          } else {
+            p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), scale_l2e, -mx));
+            p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), scale_l2e, -mx));
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), scale_l2e, -mx));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), scale_l2e, -mx));
-            sum += p0 + p1;
-            const __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
+          sum += p0 + p1;
+          if (DROP) {   // training: drop probabilities (the denominator `sum` stays the full one); same element index as
+                        // attention_tc_kernel / the backward kernels: ((item L + query) L + key)
+            const uint64_t e0 = ((uint64_t)item * L + (uint64_t)qrow) * L + (uint64_t)(key0 + j * 32 + 2 * i);
+            p0 *= drop_mul(drop, e0); p1 *= drop_mul(drop, e0 + 1);
+          }
+          const __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);  // .x (low half) = even key
+          ph[i] = *reinterpret_cast<const uint32_t*>(&b);
+          if (SPL) {
             const __nv_bfloat162 c = __floats2bfloat162_rn(p0 - __low2float(b), p1 - __high2float(b));
-            ph[i] = *reinterpret_cast<const uint32_t*>(&b);
             pl[i] = *reinterpret_cast<const uint32_t*>(&c);
           }
         }
         tmem_st16(sb + j * 32, ph);
-        tmem_st16(sb + j * 32 + 16, pl);
+        if (SPL) tmem_st16(sb + j * 32 + 16, pl);
       }
       stats[((t & 3) * 2 + kb) * 128 + row] = make_float2(mx, sum);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -724,13 +735,13 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty + 8 * (t & 1));   // O buffer drained: the tile after next may accumulate into it
-      // ctx rows = [hi(heads*64) | lo(heads*64)]: this warp's 32 rows x 64 columns go out as two TMA boxes (hi plane, lo plane)
-      // staged in shared memory (128B swizzle; piece j of row r at r*128 + ((j ^ (r & 7)) << 4)).  Per-thread 16-byte stores
-      // of whole rows (32 different lines per instruction) had flooded the memory pipeline the softmax warps' TMEM loads and
-      // the barrier polls share.  The 3-D map clips the box at the end of the token group (rows >= L are not written).
+      // ctx rows = [hi(heads*64) | lo(heads*64)] (plain bf16: the hi plane only): this warp's 32 rows x 64 columns go out as
+      // TMA boxes staged in shared memory (128B swizzle; piece j of row r at r*128 + ((j ^ (r & 7)) << 4)).  Per-thread 16-byte
+      // stores of whole rows (32 different lines per instruction) had flooded the memory pipeline the softmax warps' TMEM loads
+      // and the barrier polls share.  The 3-D map clips the box at the end of the token group (rows >= L are not written).
       const int q0 = qt * 128 + quarter * 32;
       const uint32_t stg = base + Cfg::STG_OFF + (warp - 10) * 4096 + lane * 128;
-      if (lane == 0) tma_store_wait_read<0>();   // the previous tile's lo box has been read out of the staging buffer
+      if (lane == 0) tma_store_wait_read<0>();   // the previous tile's last box has been read out of the staging buffer
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 8; ++i) {   // hi plane: round-to-nearest bf16 of the normalised outputs
@@ -741,23 +752,25 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0 && q0 < L) { tma_store_3d(&map_ctx, stg, h * AT_D, q0, r); tma_store_commit(); }
-      // lo plane: computed while the TMA reads the hi box
-      uint4 lo4[8];
+      if (lane == 0 && q0 < L) { tma_store_3d(&map_ctx, stg - lane * 128, h * AT_D, q0, r); tma_store_commit(); }
+      if (SPL) {
+        // lo plane: computed while the TMA reads the hi box
+        uint4 lo4[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        uint2 h0, l0, h1, l1;
-        split4(make_float4(o[8 * i], o[8 * i + 1], o[8 * i + 2], o[8 * i + 3]), h0, l0);
-        split4(make_float4(o[8 * i + 4], o[8 * i + 5], o[8 * i + 6], o[8 * i + 7]), h1, l1);
-        lo4[i] = make_uint4(l0.x, l0.y, l1.x, l1.y);
+        for (int i = 0; i < 8; ++i) {
+          uint2 h0, l0, h1, l1;
+          split4(make_float4(o[8 * i], o[8 * i + 1], o[8 * i + 2], o[8 * i + 3]), h0, l0);
+          split4(make_float4(o[8 * i + 4], o[8 * i + 5], o[8 * i + 6], o[8 * i + 7]), h1, l1);
+          lo4[i] = make_uint4(l0.x, l0.y, l1.x, l1.y);
+        }
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) st_shared_v4(stg + ((i ^ (lane & 7)) << 4), lo4[i].x, lo4[i].y, lo4[i].z, lo4[i].w);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && q0 < L) { tma_store_3d(&map_ctx, stg - lane * 128, heads * AT_D + h * AT_D, q0, r); tma_store_commit(); }
       }
-      if (lane == 0) tma_store_wait_read<0>();
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) st_shared_v4(stg + ((i ^ (lane & 7)) << 4), lo4[i].x, lo4[i].y, lo4[i].z, lo4[i].w);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0 && q0 < L) { tma_store_3d(&map_ctx, stg, heads * AT_D + h * AT_D, q0, r); tma_store_commit(); }
       if (tid == 320) TR(2, t, 2);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last boxes are in global memory
@@ -771,17 +784,20 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   }
 }
 
-template <int KP>
+template <int KP, bool SPL>
 static int launch_attention_ws(const bf16* qkv, int64_t R, int L, int heads, float scale, const float* mask_add, int mask_ld,
-                               int mask_len, bf16* ctx, cudaStream_t st) {
-  using Cfg = AttnWsCfg<KP>;
+                               int mask_len, bf16* ctx, cudaStream_t st, const Drop& drop = Drop()) {
+  using Cfg = AttnWsCfg<KP, SPL>;
+  constexpr int PL = Cfg::PLANES;
   CUtensorMap mq, mkv;
-  const int ld = 2 * 3 * heads * AT_D;   // bf16 elements per qkv row (hi | lo)
+  const int ld = PL * 3 * heads * AT_D;   // bf16 elements per qkv row (hi | lo)
   MSQ_TRY(make_map_bf16(&mq, qkv, R * L, ld, ld, AT_D, 128));
   MSQ_TRY(make_map_bf16(&mkv, qkv, R * L, ld, ld, AT_D, KP));
   CUtensorMap mctx;
-  MSQ_TRY(make_map_3d_bf16(&mctx, ctx, R, L, 2 * heads * AT_D, 2 * heads * AT_D, AT_D, 32));
-  MSQ_SMEM_ATTR(Cfg::SMEM, attention_ws_kernel<KP>);
+  MSQ_TRY(make_map_3d_bf16(&mctx, ctx, R, L, PL * heads * AT_D, PL * heads * AT_D, AT_D, 32));
+  const bool dropping = !SPL && drop.thresh != 0;
+  if (dropping) MSQ_SMEM_ATTR(Cfg::SMEM, (attention_ws_kernel<KP, SPL, !SPL>));
+  else MSQ_SMEM_ATTR(Cfg::SMEM, (attention_ws_kernel<KP, SPL, false>));
   int dev = 0, sms = 0;
   MSQ_CUDA(cudaGetDevice(&dev));
   MSQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -794,8 +810,13 @@ static int launch_attention_ws(const bf16* qkv, int64_t R, int L, int heads, flo
   MSQ_CUDA(cudaMemsetAsync(trace_dev, 0, 3 * 64 * 8 * sizeof(long long), st));
   trace = trace_dev;
 #endif
-  MSQ_CUDA(launch_k(attention_ws_kernel<KP>, dim3((unsigned)min((int64_t)sms, n_items)), dim3(Cfg::THREADS), Cfg::SMEM, st, mq, mkv, mctx, L,
-                    heads, scale * 1.4426950408889634f, mask_add, mask_ld, mask_len, ctx, (int)n_items, trace));
+  const dim3 grid((unsigned)min((int64_t)sms, n_items));
+  if (dropping)
+    MSQ_CUDA(launch_k(attention_ws_kernel<KP, SPL, !SPL>, grid, dim3(Cfg::THREADS), Cfg::SMEM, st, mq, mkv, mctx, L, heads,
+                      scale * 1.4426950408889634f, mask_add, mask_ld, mask_len, ctx, (int)n_items, trace, drop));
+  else
+    MSQ_CUDA(launch_k(attention_ws_kernel<KP, SPL, false>, grid, dim3(Cfg::THREADS), Cfg::SMEM, st, mq, mkv, mctx, L, heads,
+                      scale * 1.4426950408889634f, mask_add, mask_ld, mask_len, ctx, (int)n_items, trace, drop));
   MSQ_LAUNCH_CHECK();
 #ifdef MSQ_ATTN_TRACE
   {
@@ -864,14 +885,24 @@ int attention(const T* qkv, int64_t R, int L, int heads, int dhead, float scale,
     MSQ_REQUIRE(tc_supported_impl() && L <= 256 && (((uintptr_t)qkv) & 15) == 0, "attention: the bf16x3 mode needs the tcgen05 path (sm_100, L <= 256)");
     if (attention_use_ws()) {   // warp-specialised pipeline (MSQ_ATTN_WS=0: the one-tile-at-a-time kernel)
       if (L <= 128)
-        return launch_attention_ws<128>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
-      return launch_attention_ws<256>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
+        return launch_attention_ws<128, true>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
+      return launch_attention_ws<256, true>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
     }
     if (L <= 128)
       return launch_attention_tc<128, true>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
     return launch_attention_tc<256, true>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st);
   } else {
   if constexpr (sizeof(T) == 2) {
+    // plain bf16 operands: the warp-specialised pipeline is available (MSQ_ATTN_WS_BF16=1) but NOT the default: with one MMA
+    // pass the exponentials, not the tensor pipe, bound the kernel, and two co-resident CTAs of attention_tc_kernel put 512
+    // threads on them against the 256 of the two softmax groups -- measured 282 vs 367 us (L = 227), 105 vs 102 us (L = 99)
+    static int ws16 = -1;
+    if (ws16 < 0) { const char* e = getenv("MSQ_ATTN_WS_BF16"); ws16 = (e && e[0] == '1') ? 1 : 0; }
+    if (ws16 && attention_use_tc() && attention_use_ws() && L <= 256 && (((uintptr_t)qkv) & 15) == 0) {
+      if (L <= 128)
+        return launch_attention_ws<128, false>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st, drop);
+      return launch_attention_ws<256, false>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st, drop);
+    }
     if (attention_use_tc() && L <= 256 && (((uintptr_t)qkv) & 15) == 0) {
       if (L <= 128)
         return launch_attention_tc<128, false>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st, drop);
