@@ -241,7 +241,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           int kb = kq, ka = 0, kw = 0;
           if (PAIR && ep.share) {
             kb = kq >> 1;
-            ka = kw = (kq & 1) * ep.split_k;   // even stage: hi planes, odd stage: lo planes
+            ka = kw = ((kq & 1) ^ 1) * ep.split_k;   // even stage: LO planes (released first, after the second pass), odd stage: hi planes
           } else if (ep.split_k) {
             // (plane of A, plane of W) per pass, smallest products first.  two planes: (0,1) (1,0) (0,0);
             // three planes: (0,2) (1,1) (2,0) (0,1) (1,0) (0,0) -- every product a_i w_j with i + j <= 2
@@ -302,15 +302,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_wait(full0 + 8 * stage, phase);
             mbar_wait(full0 + 8 * (stage + 1), phase);
             tc_fence_after();
-            const uint32_t ah = base + stage * STAGE_BYTES, wh = ah + TC_A_BYTES, al = ah + STAGE_BYTES, wl = al + TC_A_BYTES;
+            const uint32_t al = base + stage * STAGE_BYTES, wl = al + TC_A_BYTES, ah = al + STAGE_BYTES, wh = ah + TC_A_BYTES;
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k)   // smallest products first
               umma_bf16_pair(tmem_d, umma_desc_sw128(ah + k * 32), umma_desc_sw128(wl + k * 32), idesc, (kb | k) != 0);
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) umma_bf16_pair(tmem_d, umma_desc_sw128(al + k * 32), umma_desc_sw128(wh + k * 32), idesc, 1);
+            if (ep.share == 1) umma_commit_pair(empty0 + 8 * stage);   // the lo planes are done: their stage refills a pass earlier
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) umma_bf16_pair(tmem_d, umma_desc_sw128(ah + k * 32), umma_desc_sw128(wh + k * 32), idesc, 1);
-            umma_commit_pair(empty0 + 8 * stage);
+            if (ep.share != 1) umma_commit_pair(empty0 + 8 * stage);
             umma_commit_pair(empty0 + 8 * (stage + 1));
             stage += 2;
             if (stage == STAGES) { stage = 0; phase ^= 1; }
@@ -631,7 +632,9 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
   ep.split_passes = g.split == 2 ? 6 : 3;
   static int share_env = -1;
   if (share_env < 0) { const char* e = getenv("MSQ_X3_SHARE"); share_env = (e && e[0] == '0') ? 0 : 1; }
-  ep.share = (PAIR && g.split == 1 && !g.tn && share_env) ? 1 : 0;
+  static int early_env = -1;
+  if (early_env < 0) { const char* e = getenv("MSQ_X3_EARLY"); early_env = (e && e[0] == '0') ? 0 : 1; }
+  ep.share = (PAIR && g.split == 1 && !g.tn && share_env) ? (early_env ? 1 : 2) : 0;
   static_assert(Cfg::STAGES % 2 == 0, "the shared bf16x3 slab occupies two consecutive stages");
   const int num_m = ceil_div(g.M, Cfg::TILE_M), num_n = ceil_div(g.N, TC_BN),
             num_k = ceil_div(g.K, TC_BK) * (ep.share ? 2 : (g.split ? ep.split_passes : 1));
