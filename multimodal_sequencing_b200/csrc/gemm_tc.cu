@@ -71,7 +71,6 @@ struct TcEpi {
   // bf16x3 on CTA pairs: a K slab is staged ONCE as two stages ([a_hi | w_hi], [a_lo | w_lo]) and the three MMA passes
   // read them crosswise, instead of three stages that fetch a_hi and w_hi twice: L2 -> shared-memory traffic -1/3
   int share;
-  int prefetch;   // L2 prefetch of the A boxes ahead of the ring (MSQ_X3_PREFETCH=0 disables)
 };
 
 // 8 consecutive output columns of one row: accumulator -> value to store (see GemmArgs for the modes)
@@ -251,18 +250,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const uint32_t pa = ep.split_passes == 3 ? 0x010u : 0x010210u, pw = ep.split_passes == 3 ? 0x001u : 0x001012u;
             ka = (int)((pa >> (4 * t)) & 0xFu) * ep.split_k;
             kw = (int)((pw >> (4 * t)) & 0xFu) * ep.split_k;
-          }
-          if (PAIR && ep.share && ep.prefetch) {
-            // A tiles are first touched in HBM (the weights stay in L2): their boxes are pulled into L2 TC_PF stage loads ahead
-            // -- of this tile, and at its start the first TC_PF of this pair's next tile -- so that the ring's loads, issued
-            // only ~1.3 us before the MMAs need them, find the data in L2
-            constexpr int TC_PF = 16;
-            const int kf = kq + TC_PF;
-            if (kf < num_k) tma_prefetch_2d(&tma_a, ((kf & 1) ^ 1) * ep.split_k + (kf >> 1) * TC_BK, a_row);
-            if (kq < TC_PF && kq < num_k && tile + num_units < num_tiles) {
-              const int a_next = ((tile + num_units) / num_n) * Cfg::TILE_M + (int)rank * TC_BM;
-              tma_prefetch_2d(&tma_a, ((kq & 1) ^ 1) * ep.split_k + (kq >> 1) * TC_BK, a_next);
-            }
           }
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + TC_A_BYTES;
@@ -648,9 +635,6 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
   static int early_env = -1;
   if (early_env < 0) { const char* e = getenv("MSQ_X3_EARLY"); early_env = (e && e[0] == '0') ? 0 : 1; }
   ep.share = (PAIR && g.split == 1 && !g.tn && share_env) ? (early_env ? 1 : 2) : 0;
-  static int pf_env = -1;
-  if (pf_env < 0) { const char* e = getenv("MSQ_X3_PREFETCH"); pf_env = (e && e[0] == '0') ? 0 : 1; }
-  ep.prefetch = pf_env;
   static_assert(Cfg::STAGES % 2 == 0, "the shared bf16x3 slab occupies two consecutive stages");
   const int num_m = ceil_div(g.M, Cfg::TILE_M), num_n = ceil_div(g.N, TC_BN),
             num_k = ceil_div(g.K, TC_BK) * (ep.share ? 2 : (g.split ? ep.split_passes : 1));
