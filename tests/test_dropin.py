@@ -56,6 +56,51 @@ def _build(g, N, W, device="cpu"):
     return model, args
 
 
+@pytest.mark.gpu
+def test_reference_training_loop_with_the_resnet_tower(golden_dir):
+    """trainers/train.py:340-363 on the drop-in module with the reference's wired backbone (ModifiedResNet, train() mode =
+    BatchNorm over the batch): loss and gradient norms of the first step equal the reference-generated fixture
+    (grads_tiny.pt 'mm_rn_bntrain'), the BatchNorm buffers of the module move like nn.BatchNorm2d's, the loop lowers the loss."""
+    g = torch.load(os.path.join(golden_dir, "mm_rn_tiny.pt"), weights_only=False)
+    r = torch.load(os.path.join(golden_dir, "grads_tiny.pt"), weights_only=False)["mm_rn_bntrain"]
+    ids, labels, images = O.synthetic_manuals(r["B"], r["N"], r["L"], vocab=1000, image_px=224, seed=r["seed"])
+    model, args = _build(g, r["N"], 4, "cuda")
+    model.config.hidden_dropout_prob = model.config.attention_probs_dropout_prob = 0.0
+    model.bert.config.hidden_dropout_prob = model.bert.config.attention_probs_dropout_prob = 0.0
+    args.para_dropout = 0.0
+    model.load_state_dict(g["sd"], strict=False)
+    model = model.cuda().train()
+    for mod in model.modules():
+        mod.precise = True
+    inp = O.prepare_inputs(ids, labels, r["N"], images)
+    inp = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    v = "bert.encoder.visual_model.visual."
+    rm0 = model.state_dict()[v + "bn1.running_mean"].clone()
+    nbt0 = int(model.state_dict()[v + "bn1.num_batches_tracked"]) if (v + "bn1.num_batches_tracked") in model.state_dict() else None
+    opt = torch.optim.AdamW([p for p in model.parameters()], lr=1e-3, weight_decay=0.0)
+    losses = []
+    with torch.enable_grad():
+        for step in range(3):
+            loss = model._forward(**inp)[0]
+            loss.backward()
+            if step == 0:
+                assert abs(loss.item() - r["loss"]) < 5e-5
+                named = dict(model.named_parameters())
+                for n, s_ in r["grads"].items():
+                    if n.startswith("bert.pooler"):
+                        continue
+                    a = named[n].grad.detach().double().cpu().reshape(-1)
+                    assert abs(float(a.norm()) - s_["norm"]) <= 1e-2 * s_["norm"] + 1e-7, n
+                assert (model.state_dict()[v + "bn1.running_mean"] - rm0).abs().max() > 1e-5   # nn.BatchNorm2d.train() bookkeeping
+                if nbt0 is not None:
+                    assert int(model.state_dict()[v + "bn1.num_batches_tracked"]) == nbt0 + 1
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
+            model.zero_grad()
+            losses.append(loss.item())
+    assert losses[-1] < losses[0] - 0.01, losses
+
+
 @pytest.mark.parametrize("name", ["text_tiny.pt", "mm_tiny.pt", "mm_rn_tiny.pt"])
 def test_state_dict_keys_match_reference(golden_dir, name):
     g = torch.load(os.path.join(golden_dir, name), weights_only=False)
