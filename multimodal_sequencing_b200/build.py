@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmsq_b200.so")
 STAMP = os.path.join(HERE, ".libmsq_b200.stamp")
-SOURCES = ["api.cu", "elementwise.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_ln.cu", "attention.cu", "pooling.cu", "decode.cu", "rn.cu", "train_kernels.cu", "train.cu", "train_heads.cu", "attention_bwd_mma.cu", "expand.cu", "train_rn.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_ln.cu", "attention.cu", "pooling.cu", "decode.cu", "rn.cu", "train_kernels.cu", "train.cu", "train_heads.cu", "attention_bwd_mma.cu", "expand.cu", "train_rn.cu", "attention_bwd_tc.cu"]
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("MSQ_EXTRA_NVCC_FLAGS", "").split()
 

@@ -113,15 +113,6 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
-      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
-
 // SPL (bf16x3 mode): q, k, v and the probabilities are carried as hi + lo bf16 pairs.  qkv rows are
 // [hi(3*heads*64) | lo(3*heads*64)], ctx rows [hi(heads*64) | lo(heads*64)]; every contraction is three MMA chains
 // (hi*lo, lo*hi, hi*hi) into the same fp32 accumulator; P_lo lives in its own TMEM columns [KP, KP + KP/2).
@@ -421,45 +412,6 @@ template <int KP, bool SPL = true> struct AttnWsCfg {
   static constexpr int SMEM = BAR_OFF + 256 + 1024;
   static constexpr int THREADS = 14 * 32;
 };
-
-__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ bool named_bar_or(int id, int n, bool pred) {
-  uint32_t r;
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.u32 q, %3, 0;\n\t"
-      "bar.red.or.pred p, %1, %2, q;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(r)
-      : "r"(id), "r"(n), "r"((uint32_t)pred)
-      : "memory");
-  return r != 0;
-}
-
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-// tcgen05.mma with a compile-time-foldable accumulate flag; TS: A operand in TMEM (address in the low word of `a`)
-template <bool TS>
-__device__ __forceinline__ void umma_bf16_acc(uint32_t tmem_d, uint64_t a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
-  if (TS) {
-    if (accumulate)
-      asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"((uint32_t)a), "l"(desc_b), "r"(idesc) : "memory");
-    else
-      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"((uint32_t)a), "l"(desc_b), "r"(idesc) : "memory");
-  } else {
-    if (accumulate)
-      asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(a), "l"(desc_b), "r"(idesc) : "memory");
-    else
-      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(a), "l"(desc_b), "r"(idesc) : "memory");
-  }
-}
 
 template <int KP, bool SPL, bool DROP>
 __global__ void __launch_bounds__(AttnWsCfg<KP, SPL>::THREADS, 1)

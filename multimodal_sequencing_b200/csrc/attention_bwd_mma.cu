@@ -501,6 +501,9 @@ int attention_bwd_mma(const bf16* qkv, const bf16* ctx, const bf16* dctx, int64_
   MSQ_SMEM_ATTR(smem_b, attention_bwd_dkv_mma_kernel);
   MSQ_CUDA(launch_k(attention_bwd_dq_mma_kernel, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem_a, st, qkv, ctx, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, lse, dsum, drop));
   MSQ_LAUNCH_CHECK();
+  // dK / dV: the tcgen05 pipeline (attention_bwd_tc.cu) when available, else the mma.sync kernel (MSQ_ATTN_BWD_TC=0)
+  if (attention_bwd_dkv_tc_supported(L))
+    return attention_bwd_dkv_tc(qkv, dctx, R, L, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, lse, dsum, st, drop);
   MSQ_CUDA(launch_k(attention_bwd_dkv_mma_kernel, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem_b, st, qkv, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, (const float*)lse, (const float*)dsum, drop));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;

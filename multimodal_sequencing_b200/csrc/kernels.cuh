@@ -189,6 +189,10 @@ int attention_bwd(const T* qkv, const T* dctx, int64_t R, int L, int heads, floa
 bool attention_bwd_mma_supported(int L);
 int attention_bwd_mma(const bf16* qkv, const bf16* ctx, const bf16* dctx, int64_t R, int L, int heads, float scale, const float* key_mask_add,
                       int mask_ld, int mask_len, bf16* dqkv, float* scratch, cudaStream_t st, const Drop& drop = Drop());   // scratch: attention_bwd_scratch_floats
+// attention_bwd_tc.cu: dK / dV on tcgen05 (lse / dsum: per-query vectors [R*heads, L] written by the dQ kernel)
+bool attention_bwd_dkv_tc_supported(int L);
+int attention_bwd_dkv_tc(const bf16* qkv, const bf16* dctx, int64_t R, int L, int heads, float scale, const float* mask_add, int mask_ld,
+                         int mask_len, bf16* dqkv, const float* lse, const float* dsum, cudaStream_t st, const Drop& drop);
 int mask_add_from_int(const int64_t* mask, int64_t n, float* out, cudaStream_t st);
 int scatter_rows(const float* src, int64_t rows, int H, int group, int dst_group, int off, float* dst, cudaStream_t st);
 size_t grad_norm_scratch_floats();

@@ -25,8 +25,7 @@ def keep_mask(seed, step, kind, layer, p, shape):
     site = np.uint64(KIND[kind] + 16 * layer)
     key = _fmix(np.uint64(seed) ^ _fmix(np.array((step + 0x9E3779B9) & 0xFFFFFFFF, dtype=np.uint64)) ^ ((site * np.uint64(0x85EBCA6B)) & _M))
     idx = np.arange(int(np.prod(shape)), dtype=np.uint64)
-    h = _fmix(key ^ (idx & _M))
-    h = _fmix((h + ((idx >> np.uint64(32)) * np.uint64(0xC2B2AE35) & _M) + np.uint64(0x27D4EB2F)) & _M)
+    h = _fmix(key ^ (idx & _M) ^ (((idx >> np.uint64(32)) * np.uint64(0x9E3779B1)) & _M))
     thresh = np.uint64(int(np.float64(np.float32(p)) * 4294967296.0))   # (uint32)((double)(float)p * 2^32), as the device computes it
     return (h >= thresh).reshape(shape)
 

@@ -148,8 +148,8 @@ def test_linear_schedule_matches_transformers():
         sch.step()
 
 
-KNOWN_E = [0, 1, 1, 1, 0, 0, 1, 0, 0, 1, 1, 1, 0, 0, 1, 1]
-KNOWN_PA = [1, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1]
+KNOWN_E = [1, 0, 0, 0, 0, 0, 1, 1, 1, 0, 1, 0, 0, 0, 1, 0]
+KNOWN_PA = [1, 0, 1, 1, 1, 0, 1, 1, 0, 1, 1, 1, 1, 1, 0, 1]
 
 
 def test_dropout_hash_known_answers():
