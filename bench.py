@@ -335,8 +335,6 @@ def run_ordering(ctx, args, cfg_id, steps, warmup, full=True):
     N, W = c["n_steps"], c["beam"]
     precision = args.precision or ("fp32" if args.precise else "bf16x3")
     mcfg, vit, rn = _model_cfg(args)
-    if rn is not None and precision == "bf16x3":
-        precision = "bf16"     # the bf16x3 mode does not cover the ModifiedResNet tower
     sd = synth.full_state_dict(mcfg, vit, seed=0, rn=rn)
     eng = OrderingEngine(sd, mcfg, precise=precision, device=ctx.dev)
 

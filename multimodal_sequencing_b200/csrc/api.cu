@@ -240,7 +240,8 @@ __global__ void training_loss_kernel(const float* __restrict__ nll, const float*
 }
 
 // K of a convolution GEMM, padded so that the tcgen05 path (64-wide K slabs) applies whenever K >= 64
-static int rn_kpad(int K) { return K < 64 ? (K + 15) / 16 * 16 : (K + 63) / 64 * 64; }
+// padded contraction length of a convolution GEMM; split (bf16x3) operands only run on the tcgen05 kernel: whole 64-column slabs
+static int rn_kpad(int K, bool split = false) { return (K < 64 && !split) ? (K + 15) / 16 * 16 : (K + 63) / 64 * 64; }
 
 // Fold a LayerNorm into the linear layer that consumes it (one block per output feature n):
 //   wf[n,k] = bf16(gamma_k w[n,k]);  svec[n] = sum_k float(wf[n,k]);  bf[n] = b[n] + sum_k beta_k w[n,k]
@@ -436,7 +437,7 @@ extern "C" int msq_model_create(const msq_config* cfg, msq_model** out) {
   }
   MSQ_REQUIRE(cfg->para_heads >= 1 && cfg->hidden % cfg->para_heads == 0 && cfg->para_ff % 16 == 0, "bad paragraph config");
   MSQ_REQUIRE(cfg->precise >= 0 && cfg->precise <= 2, "precise=%d: 0 bf16, 1 fp32, 2 bf16x3", cfg->precise);
-  MSQ_REQUIRE(!(cfg->precise == 2 && cfg->rn_width), "the bf16x3 mode does not cover the ModifiedResNet tower (use precise 0 or 1)");
+  MSQ_REQUIRE(!(cfg->precise == 2 && cfg->rn_width && cfg->rn_width % 64), "the bf16x3 mode needs a ModifiedResNet width that is a multiple of 64 (tcgen05 tiles)");
   MSQ_REQUIRE(!(cfg->precise == 2 && (cfg->inter % 64 || cfg->vit_width % 64)), "the bf16x3 mode needs inter and vit_width to be multiples of 64");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -595,7 +596,8 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
     const int w = c.rn_width, Cf = 32 * w, E = c.rn_embed, F = 2 * E, g = c.vit_res / 32, g2 = g * g;
     auto conv = [&](const std::string& cw, const std::string& bn, int cout, int cin, int k, Lin* out) -> int {
       const int K = k * k * cin;
-      MSQ_REQUIRE(k != 1 || rn_kpad(K) == K, "ResNet tower: 1x1 convolution with %d input channels is not GEMM-aligned", cin);
+      const bool split = c.precise == 2;
+      MSQ_REQUIRE(k != 1 || rn_kpad(K, split) == K, "ResNet tower: 1x1 convolution with %d input channels is not GEMM-aligned", cin);
       float *wf, *bf;
       MSQ_TRY(dev_alloc(m, (size_t)cout * K, &wf));
       MSQ_TRY(dev_alloc(m, (size_t)cout, &bf));
@@ -603,7 +605,7 @@ extern "C" int msq_model_pack(msq_model* m, void* stream) {
                   *pm = W(bn + ".running_mean", cout), *pv = W(bn + ".running_var", cout);
       if (!pw || !pg || !pb || !pm || !pv) return MSQ_ERR_WEIGHT;
       MSQ_TRY(rn_fold(pw, pg, pb, pm, pv, cout, cin, k, wf, bf, st));
-      return make_lin(m, wf, bf, cout, K, rn_kpad(K), w16, out, st);
+      return make_lin(m, wf, bf, cout, K, rn_kpad(K, split), w16, out, st);
     };
     MSQ_TRY(conv(v + "conv1.weight", v + "bn1", w / 2, 3, 3, &m->rn_stem[0]));
     MSQ_TRY(conv(v + "conv2.weight", v + "bn2", w / 2, w / 2, 3, &m->rn_stem[1]));
@@ -921,14 +923,16 @@ static RnDims rn_dims(const msq_config& c) {
   auto up = [](size_t& x, size_t v) { if (v > x) x = v; };
   const int w = c.rn_width, w2 = w / 2;
   size_t H = c.vit_res / 2;
-  up(d.a, H * H * rn_kpad(27)); up(d.a, H * H * rn_kpad(9 * w2));
+  const bool split = c.precise == 2;
+  up(d.a, H * H * rn_kpad(27, split)); up(d.a, H * H * rn_kpad(9 * w2, split));
+  up(d.f, H * H * w2);   // fp32 staging of the narrow stem outputs (bf16x3: split outputs need N % 64 == 0)
   up(d.t, H * H * w);
   H /= 2;
   size_t cin = w;
   for (int s = 0; s < 4; ++s)
     for (int b = 0; b < c.rn_blocks[s]; ++b) {
       const size_t p = (size_t)w << s, st = (b == 0 && s > 0) ? 2 : 1, Ho = H / st;
-      up(d.t, H * H * cin); up(d.t, H * H * p); up(d.a, H * H * rn_kpad(9 * (int)p));
+      up(d.t, H * H * cin); up(d.t, H * H * p); up(d.a, H * H * rn_kpad(9 * (int)p, split));
       up(d.t, Ho * Ho * 4 * p); up(d.f, Ho * Ho * 4 * p);
       H = Ho; cin = 4 * p;
     }
@@ -963,12 +967,23 @@ static int run_rn_trunk(msq_model* m, const float* images, int64_t n_img, VitBuf
     const int64_t n = min(RN_IMG_CHUNK, first + n_img - i0);
     int H = S / 2;
     int64_t M = n * H * H;
+    // conv + folded BatchNorm + ReLU; split outputs need N % 64 == 0: the narrow stem convolutions (width / 2 channels) go
+    // through an fp32 map and the ReLU / cast pass instead
+    auto conv_relu = [&](const T* in, const Lin& L, T* out, int cout) -> int {
+      if constexpr (is_split<T>::value) {
+        if (cout % 64 != 0) {
+          MSQ_TRY((run_gemm<T, float>(m, in, L.K, L, nullptr, 0, b.rF0, cout, M, ACT_NONE, st)));
+          return rn_relu_cast<T>(b.rF0, M * cout, cout, out, st);
+        }
+      }
+      return run_gemm<T, T>(m, in, L.K, L, nullptr, 0, out, cout, M, ACT_RELU, st);
+    };
     MSQ_TRY(rn_im2col_stem<T>(images + i0 * img_elems, n, S, m->rn_stem[0].K, A, st));
-    MSQ_TRY((run_gemm<T, T>(m, A, m->rn_stem[0].K, m->rn_stem[0], nullptr, 0, O1, w / 2, M, ACT_RELU, st)));
+    MSQ_TRY(conv_relu(A, m->rn_stem[0], O1, w / 2));
     MSQ_TRY(rn_im2col3<T>(O1, n, H, H, w / 2, m->rn_stem[1].K, A, st));
-    MSQ_TRY((run_gemm<T, T>(m, A, m->rn_stem[1].K, m->rn_stem[1], nullptr, 0, O2, w / 2, M, ACT_RELU, st)));
+    MSQ_TRY(conv_relu(A, m->rn_stem[1], O2, w / 2));
     MSQ_TRY(rn_im2col3<T>(O2, n, H, H, w / 2, m->rn_stem[2].K, A, st));
-    MSQ_TRY((run_gemm<T, T>(m, A, m->rn_stem[2].K, m->rn_stem[2], nullptr, 0, O1, w, M, ACT_RELU, st)));
+    MSQ_TRY(conv_relu(A, m->rn_stem[2], O1, w));
     MSQ_TRY(rn_avgpool2<T>(O1, n, H, H, w, X, st));
     H /= 2;
     for (const RnBlockW& B : m->rn_blocks) {
@@ -986,7 +1001,7 @@ static int run_rn_trunk(msq_model* m, const float* images, int64_t n_img, VitBuf
       }
       if (B.has_ds) MSQ_TRY((run_gemm<T, float>(m, xs, B.cin, B.ds, nullptr, 0, b.rF1, 4 * p, Mo, ACT_NONE, st)));
       MSQ_TRY((run_gemm<T, float>(m, o2, p, B.c3, B.has_ds ? b.rF1 : b.rF0, 4 * p, b.rF0, 4 * p, Mo, ACT_NONE, st)));
-      MSQ_TRY(rn_relu_cast<T>(b.rF0, Mo * 4 * p, X, st));
+      MSQ_TRY(rn_relu_cast<T>(b.rF0, Mo * 4 * p, 4 * p, X, st));
       H = Ho;
     }
     MSQ_CUDA(cudaMemcpyAsync(b.patch + i0 * g2 * Cf, b.rF0, (size_t)n * g2 * Cf * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1012,17 +1027,17 @@ static int run_rn_pool(msq_model* m, const int32_t* img_index, int64_t R, VitBuf
 // backbone dispatch: per-image part (patch embedding / ResNet trunk) and per-pair part (transformer / attention pool)
 template <typename T>
 static void plan_visual(const msq_config& c, Planner& p, int64_t n_img, int64_t R, VitBufs* b) {
-  if constexpr (!is_split<T>::value) { if (c.rn_width) { plan_rn<T>(c, p, n_img, R, b); return; } }
+  if (c.rn_width) { plan_rn<T>(c, p, n_img, R, b); return; }
   plan_vit<T>(c, p, n_img, R, b);
 }
 template <typename T>
 static int run_visual_images(msq_model* m, const float* images, int64_t n_img, VitBufs& b, cudaStream_t st, int64_t first = 0) {
-  if constexpr (!is_split<T>::value) { if (m->cfg.rn_width) return run_rn_trunk<T>(m, images, n_img, b, st, first); }
+  if (m->cfg.rn_width) return run_rn_trunk<T>(m, images, n_img, b, st, first);
   return run_patch_embed<T>(m, images, n_img, b, st, first);
 }
 template <typename T>
 static int run_visual_pairs(msq_model* m, const int32_t* img_index, int64_t R, VitBufs& b, cudaStream_t st) {
-  if constexpr (!is_split<T>::value) { if (m->cfg.rn_width) return run_rn_pool<T>(m, img_index, R, b, st); }
+  if (m->cfg.rn_width) return run_rn_pool<T>(m, img_index, R, b, st);
   return run_vit<T>(m, img_index, R, b, st);
 }
 

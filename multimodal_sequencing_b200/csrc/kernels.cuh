@@ -39,7 +39,7 @@ int rn_posadd(const float* xe, const float* ye, const float* te, int g, int F, f
 template <typename T> int rn_im2col_stem(const float* img, int64_t n, int S, int Kp, T* out, cudaStream_t st);
 template <typename T> int rn_im2col3(const T* x, int64_t n, int H, int W, int C, int Kp, T* out, cudaStream_t st);
 template <typename T> int rn_avgpool2(const T* x, int64_t n, int H, int W, int C, T* out, cudaStream_t st);
-template <typename T> int rn_relu_cast(float* x, int64_t n, T* out, cudaStream_t st);
+template <typename T> int rn_relu_cast(float* x, int64_t n, int C, T* out, cudaStream_t st);   // C = row length (channels)
 template <typename T>
 int rn_tokens(const float* feat, const int32_t* img_index, int64_t R, int g2, int C, const float* pos, T* out, cudaStream_t st);
 template <typename T> int rn_finish(const float* o, int64_t rows, int L, int E, const float* posadd, T* out, cudaStream_t st);

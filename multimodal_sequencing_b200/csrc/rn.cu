@@ -32,6 +32,32 @@ template <> struct V4<bf16> {
     *reinterpret_cast<uint2*>(p) = u;
   }
 };
+// Row-addressed access to an activation matrix [rows, C] of T.  Split rows (bf16x3 mode) are [hi(C) | lo(C)] bf16.
+template <typename T> struct RowIO {
+  static __device__ __forceinline__ float4 ld4(const T* base, int64_t row, int C, int c) { return V4<T>::load(base + row * C + c); }
+  static __device__ __forceinline__ void st4(T* base, int64_t row, int C, int c, float4 v) { V4<T>::store(base + row * C + c, v); }
+  static __device__ __forceinline__ void st1(T* base, int64_t row, int C, int c, float v) { base[row * C + c] = from_f<T>(v); }
+};
+template <> struct RowIO<bf16s> {
+  static __device__ __forceinline__ float4 ld4(const bf16s* base, int64_t row, int C, int c) {
+    const bf16* p = reinterpret_cast<const bf16*>(base) + row * 2 * C + c;
+    const float4 h = V4<bf16>::load(p), l = V4<bf16>::load(p + C);
+    return make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
+  }
+  static __device__ __forceinline__ void st4(bf16s* base, int64_t row, int C, int c, float4 v) {
+    bf16* p = reinterpret_cast<bf16*>(base) + row * 2 * C + c;
+    uint2 hi, lo;
+    split4(v, hi, lo);
+    *reinterpret_cast<uint2*>(p) = hi;
+    *reinterpret_cast<uint2*>(p + C) = lo;
+  }
+  static __device__ __forceinline__ void st1(bf16s* base, int64_t row, int C, int c, float v) {
+    bf16* p = reinterpret_cast<bf16*>(base) + row * 2 * C + c;
+    const bf16 h = __float2bfloat16_rn(v);
+    p[0] = h;
+    p[C] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+};
 inline dim3 grid_for(int64_t work) { return dim3((unsigned)max((int64_t)1, min((int64_t)148 * 16, (work + 255) / 256))); }
 }  // namespace
 
@@ -93,7 +119,7 @@ __global__ void __launch_bounds__(256) rn_im2col_stem_kernel(const float* __rest
       const int y = oy * 2 - 1 + ky, x = ox * 2 - 1 + kx;
       if (y >= 0 && y < S && x >= 0 && x < S) v = img[((im * 3 + c) * S + y) * (int64_t)S + x];
     }
-    out[i] = from_f<T>(v);
+    RowIO<T>::st1(out, row, Kp, col, v);
   }
 }
 template <typename T>
@@ -106,6 +132,7 @@ int rn_im2col_stem(const float* img, int64_t n, int S, int Kp, T* out, cudaStrea
 }
 template int rn_im2col_stem<float>(const float*, int64_t, int, int, float*, cudaStream_t);
 template int rn_im2col_stem<bf16>(const float*, int64_t, int, int, bf16*, cudaStream_t);
+template int rn_im2col_stem<bf16s>(const float*, int64_t, int, int, bf16s*, cudaStream_t);
 
 // ---- 3x3 / stride 1 / pad 1 over NHWC -> rows [n*H*W, Kp], col = (ky*3+kx)*C + c.  16 bytes per thread (8 bf16 or 4 fp32
 // channels), 32-bit index arithmetic (one launch covers at most RN_IMG_CHUNK images: < 2^31 vectors).
@@ -122,7 +149,7 @@ template <> struct VecIO<bf16> {
 };
 template <typename T>
 __global__ void __launch_bounds__(256) rn_im2col3_kernel(const T* __restrict__ x, uint32_t n, uint32_t H, uint32_t W, uint32_t C,
-                                                         uint32_t Kp, T* __restrict__ out) {
+                                                         uint32_t Kp, T* __restrict__ out, uint32_t in_pitch, uint32_t out_pitch) {
   pdl_sync();
   typedef typename VecIO<T>::V V;
   constexpr uint32_t VN = VecIO<T>::N;
@@ -135,24 +162,40 @@ __global__ void __launch_bounds__(256) rn_im2col3_kernel(const T* __restrict__ x
       const uint32_t kk = cv / CV, c = (cv - kk * CV) * VN, ky = kk / 3, kx = kk - ky * 3;
       const uint32_t im = row / HW, pix = row - im * HW, oy = pix / W, ox = pix - oy * W;
       const uint32_t y = oy + ky - 1, xx = ox + kx - 1;   // unsigned wrap-around makes -1 fail the range test
-      if (y < H && xx < W) v = *reinterpret_cast<const V*>(x + ((size_t)(im * H + y) * W + xx) * C + c);
+      if (y < H && xx < W) v = *reinterpret_cast<const V*>(x + ((size_t)(im * H + y) * W + xx) * in_pitch + c);
     }
-    *reinterpret_cast<V*>(out + (size_t)row * Kp + (size_t)cv * VN) = v;
+    *reinterpret_cast<V*>(out + (size_t)row * out_pitch + (size_t)cv * VN) = v;
   }
 }
 template <typename T>
 int rn_im2col3(const T* x, int64_t n, int H, int W, int C, int Kp, T* out, cudaStream_t st) {
+  if constexpr (is_split<T>::value) {
+    // split rows [hi(C) | lo(C)] -> [hi(Kp) | lo(Kp)]: the bf16 kernel once per plane with the row pitches of the split layout
+    MSQ_REQUIRE(C % 8 == 0 && Kp % 8 == 0 && Kp >= 9 * C, "rn_im2col3: C=%d Kp=%d", C, Kp);
+    MSQ_REQUIRE(n * H * W * (int64_t)(Kp / 8) < ((int64_t)1 << 31), "rn_im2col3: launch too large");
+    if (n == 0) return MSQ_OK;
+    const bf16* xi = reinterpret_cast<const bf16*>(x);
+    bf16* xo = reinterpret_cast<bf16*>(out);
+    for (int pl = 0; pl < 2; ++pl) {
+      MSQ_CUDA(launch_k(rn_im2col3_kernel<bf16>, grid_for(n * H * W * (int64_t)(Kp / 8)), dim3(256), 0, st, xi + pl * C, (uint32_t)n, (uint32_t)H,
+                        (uint32_t)W, (uint32_t)C, (uint32_t)Kp, xo + pl * Kp, (uint32_t)(2 * C), (uint32_t)(2 * Kp)));
+      MSQ_LAUNCH_CHECK();
+    }
+    return MSQ_OK;
+  } else {
   constexpr int VN = VecIO<T>::N;
   MSQ_REQUIRE(C % VN == 0 && Kp % VN == 0 && Kp >= 9 * C, "rn_im2col3: C=%d Kp=%d", C, Kp);
   MSQ_REQUIRE(n * H * W * (int64_t)(Kp / VN) < ((int64_t)1 << 31), "rn_im2col3: launch too large");
   if (n == 0) return MSQ_OK;
   MSQ_CUDA(launch_k(rn_im2col3_kernel<T>, grid_for(n * H * W * (int64_t)(Kp / VN)), dim3(256), 0, st, x, (uint32_t)n, (uint32_t)H,
-                    (uint32_t)W, (uint32_t)C, (uint32_t)Kp, out));
+                    (uint32_t)W, (uint32_t)C, (uint32_t)Kp, out, (uint32_t)C, (uint32_t)Kp));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
+  }
 }
 template int rn_im2col3<float>(const float*, int64_t, int, int, int, int, float*, cudaStream_t);
 template int rn_im2col3<bf16>(const bf16*, int64_t, int, int, int, int, bf16*, cudaStream_t);
+template int rn_im2col3<bf16s>(const bf16s*, int64_t, int, int, int, int, bf16s*, cudaStream_t);
 
 // ---- AvgPool2d(2) over NHWC
 template <typename T>
@@ -165,10 +208,11 @@ __global__ void __launch_bounds__(256) rn_avgpool2_kernel(const T* __restrict__ 
     const int c = (int)(i % C4) * 4;
     const int64_t pix = i / C4, im = pix / (Ho * Wo);
     const int oy = (int)(pix % (Ho * Wo)) / Wo, ox = (int)(pix % (Ho * Wo)) % Wo;
-    const T* p = x + ((im * H + 2 * oy) * W + 2 * ox) * (int64_t)C + c;
-    const float4 a = V4<T>::load(p), b = V4<T>::load(p + C), d = V4<T>::load(p + (int64_t)W * C), e = V4<T>::load(p + (int64_t)W * C + C);
-    V4<T>::store(out + pix * C + c, make_float4((a.x + b.x + d.x + e.x) * 0.25f, (a.y + b.y + d.y + e.y) * 0.25f,
-                                                (a.z + b.z + d.z + e.z) * 0.25f, (a.w + b.w + d.w + e.w) * 0.25f));
+    const int64_t r00 = (im * H + 2 * oy) * W + 2 * ox;
+    const float4 a = RowIO<T>::ld4(x, r00, C, c), b = RowIO<T>::ld4(x, r00 + 1, C, c), d = RowIO<T>::ld4(x, r00 + W, C, c),
+                 e = RowIO<T>::ld4(x, r00 + W + 1, C, c);
+    RowIO<T>::st4(out, pix, C, c, make_float4((a.x + b.x + d.x + e.x) * 0.25f, (a.y + b.y + d.y + e.y) * 0.25f,
+                                              (a.z + b.z + d.z + e.z) * 0.25f, (a.w + b.w + d.w + e.w) * 0.25f));
   }
 }
 template <typename T>
@@ -181,28 +225,31 @@ int rn_avgpool2(const T* x, int64_t n, int H, int W, int C, T* out, cudaStream_t
 }
 template int rn_avgpool2<float>(const float*, int64_t, int, int, int, float*, cudaStream_t);
 template int rn_avgpool2<bf16>(const bf16*, int64_t, int, int, int, bf16*, cudaStream_t);
+template int rn_avgpool2<bf16s>(const bf16s*, int64_t, int, int, int, bf16s*, cudaStream_t);
 
 // ---- x <- relu(x) in place (fp32 residual stream) + operand-type copy for the next convolution
 template <typename T>
-__global__ void __launch_bounds__(256) rn_relu_cast_kernel(float* __restrict__ x, int64_t n4, T* __restrict__ out) {
+__global__ void __launch_bounds__(256) rn_relu_cast_kernel(float* __restrict__ x, int64_t n4, int C, T* __restrict__ out) {
   pdl_sync();
+  const int C4 = C / 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = *reinterpret_cast<float4*>(x + i * 4);
     v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
     *reinterpret_cast<float4*>(x + i * 4) = v;
-    V4<T>::store(out + i * 4, v);
+    RowIO<T>::st4(out, i / C4, C, (int)(i % C4) * 4, v);
   }
 }
 template <typename T>
-int rn_relu_cast(float* x, int64_t n, T* out, cudaStream_t st) {
-  MSQ_REQUIRE(n % 4 == 0, "rn_relu_cast: n=%lld", (long long)n);
+int rn_relu_cast(float* x, int64_t n, int C, T* out, cudaStream_t st) {
+  MSQ_REQUIRE(C % 4 == 0 && n % C == 0, "rn_relu_cast: n=%lld C=%d", (long long)n, C);
   if (n == 0) return MSQ_OK;
-  MSQ_CUDA(launch_k(rn_relu_cast_kernel<T>, grid_for(n / 4), dim3(256), 0, st, x, n / 4, out));
+  MSQ_CUDA(launch_k(rn_relu_cast_kernel<T>, grid_for(n / 4), dim3(256), 0, st, x, n / 4, C, out));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
-template int rn_relu_cast<float>(float*, int64_t, float*, cudaStream_t);
-template int rn_relu_cast<bf16>(float*, int64_t, bf16*, cudaStream_t);
+template int rn_relu_cast<float>(float*, int64_t, int, float*, cudaStream_t);
+template int rn_relu_cast<bf16>(float*, int64_t, int, bf16*, cudaStream_t);
+template int rn_relu_cast<bf16s>(float*, int64_t, int, bf16s*, cudaStream_t);
 
 // ---- AttentionPool2d token matrix for R pair rows.  feat [n_img, g2, C] fp32 (NHWC).  The reference reshapes the NCHW
 // maps of a pair [2, C, g2] to [C, 2*g2] WITHOUT moving the image axis (model.py:76), so token t / channel c' is flat
@@ -218,16 +265,16 @@ __global__ void __launch_bounds__(128) rn_tokens_kernel(const float* __restrict_
   const int L2 = 2 * g2;
   const float* f0 = feat + (int64_t)img_index[r * 2] * g2 * C;
   const float* f1 = feat + (int64_t)img_index[r * 2 + 1] * g2 * C;
-  T* o = out + r * (int64_t)(1 + L2) * C + cp;
+  const int64_t orow = r * (int64_t)(1 + L2);
   float sum = 0.f;
   for (int t = 0; t < L2; ++t) {
     const int f = cp * L2 + t, im = f / (C * g2), rem = f % (C * g2), c = rem / g2, p = rem % g2;
     const float v = (im ? f1 : f0)[(int64_t)p * C + c];
     sum += v;
     const int pr = t < g2 ? 1 + t : t - g2;
-    o[(int64_t)(1 + t) * C] = from_f<T>(v + pos[(int64_t)pr * C + cp]);
+    RowIO<T>::st1(out, orow + 1 + t, C, cp, v + pos[(int64_t)pr * C + cp]);
   }
-  o[0] = from_f<T>(sum / (float)L2 + pos[cp]);
+  RowIO<T>::st1(out, orow, C, cp, sum / (float)L2 + pos[cp]);
 }
 template <typename T>
 int rn_tokens(const float* feat, const int32_t* img_index, int64_t R, int g2, int C, const float* pos, T* out, cudaStream_t st) {
@@ -238,6 +285,7 @@ int rn_tokens(const float* feat, const int32_t* img_index, int64_t R, int g2, in
 }
 template int rn_tokens<float>(const float*, const int32_t*, int64_t, int, int, const float*, float*, cudaStream_t);
 template int rn_tokens<bf16>(const float*, const int32_t*, int64_t, int, int, const float*, bf16*, cudaStream_t);
+template int rn_tokens<bf16s>(const float*, const int32_t*, int64_t, int, int, const float*, bf16s*, cudaStream_t);
 
 // ---- tower output: out[row, :] = cat(o[row], o[row]) (+ posadd[row % L])   (model.py:106, lxrt/modeling.py:1014-1030)
 template <typename T>
@@ -254,7 +302,7 @@ __global__ void __launch_bounds__(256) rn_finish_kernel(const float* __restrict_
       const float4 a = *reinterpret_cast<const float4*>(posadd + (row % L) * (int64_t)(2 * E) + f);
       v = make_float4(v.x + a.x, v.y + a.y, v.z + a.z, v.w + a.w);
     }
-    V4<T>::store(out + row * 2 * E + f, v);
+    RowIO<T>::st4(out, row, 2 * E, f, v);
   }
 }
 template <typename T>
@@ -267,5 +315,6 @@ int rn_finish(const float* o, int64_t rows, int L, int E, const float* posadd, T
 }
 template int rn_finish<float>(const float*, int64_t, int, int, const float*, float*, cudaStream_t);
 template int rn_finish<bf16>(const float*, int64_t, int, int, const float*, bf16*, cudaStream_t);
+template int rn_finish<bf16s>(const float*, int64_t, int, int, const float*, bf16s*, cudaStream_t);
 
 }  // namespace msq

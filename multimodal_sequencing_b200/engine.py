@@ -139,7 +139,7 @@ class OrderingEngine:
     """Owns one packed device model (msq_model) and runs the path through the C ABI.
 
     precise: False / "bf16" (bf16 tensor-core operands), True / "fp32" (CUDA-core fp32 parity mode) or
-    2 / "bf16x3" (split-bf16 operands on the tensor cores; evaluation only, ViT or text-only models)."""
+    2 / "bf16x3" (split-bf16 operands on the tensor cores; evaluation only; ViT, ModifiedResNet or text-only models)."""
 
     def __init__(self, state_dict, config, precise=False, device="cuda:0", inner_prefix="bert."):
         if not torch.cuda.is_available():

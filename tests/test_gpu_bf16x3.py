@@ -214,19 +214,20 @@ def test_tiny_goldens_bf16x3(golden_dir, name):
 
 def _full_cfg(mm):
     cfg = dict(synth.BERT_BASE)
-    cfg.update(vit=dict(synth.VIT_B32) if mm else None, rn=None, para_ff=3072)
+    cfg.update(vit=dict(synth.VIT_B32) if mm is True else None, rn=dict(synth.RN50) if mm == "rn50" else None, para_ff=3072)
     return cfg
 
 
-@pytest.mark.parametrize("mm", [False, True])
+@pytest.mark.parametrize("mm", [False, True, "rn50"])
 def test_full_size_vs_oracle_bf16x3(mm):
-    """BERT-base (+ ViT-B/32) against the CPU oracle: 10-tuple within 1e-3 relative (asserted), permutations identical."""
+    """BERT-base (+ ViT-B/32, or the ModifiedResNet "RN50" the reference wires by default) against the CPU oracle: 10-tuple
+    within 1e-3 relative (asserted), permutations identical."""
     cfg = _full_cfg(mm)
-    sd = synth.full_state_dict(cfg, cfg["vit"], seed=0)
+    sd = synth.full_state_dict(cfg, cfg["vit"], seed=0, rn=cfg["rn"])
     N, W, B = 5, 4, 2
     ids, labels, images = O.synthetic_manuals(B, N, 64, image_px=224 if mm else None, seed=1)
     torch.set_num_threads(os.cpu_count() or 1)
-    ocfg = dict(num_hidden_layers=12, num_attention_heads=12, vit=cfg["vit"], rn=None)
+    ocfg = dict(num_hidden_layers=12, num_attention_heads=12, vit=cfg["vit"], rn=cfg["rn"])
     oenc = O.encode(sd, ocfg, O.prepare_inputs(ids, labels, N, images))
     operm = [O.beam_search(sd, oenc, N, W, b) for b in range(B)]
     eng = _engine(sd, cfg, "bf16x3")
@@ -235,7 +236,7 @@ def test_full_size_vs_oracle_bf16x3(mm):
     tv = _rel_l2(enc["top_vec"].reshape(oenc["top_vec"].shape), oenc["top_vec"])
     assert tv <= REL_X3
     print("full-size %s bf16x3: worst relative L2 over the 10-tuple %.2e, top_vec %.2e; max-abs %s" %
-          ("mm" if mm else "text", worst, tv,
+          ({False: "text", True: "mm"}.get(mm, mm), worst, tv,
            {k: "%.1e" % (enc[k].reshape(oenc[k].shape).cpu() - oenc[k]).abs().max().item() for k in ENC}))
     assert eng.order(ids, labels, N, W, images) == operm
     assert eng.order_host(eng.prepare(ids, labels, N, images), W).tolist() == operm
