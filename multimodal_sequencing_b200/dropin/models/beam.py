@@ -1,32 +1,36 @@
-"""models/beam.py::Beam of the reference (models/beam.py:8-38) with the semantics of the live twin
-models/berson/generator.py:15-38 (`//` instead of the `/` that breaks on torch >= 1.5).
+"""Host-side stand-in for the reference's beam container (models/beam.py:8-38; live twin models/berson/generator.py:15-38):
+same attributes (`beam_size`, `candidates`, `scores`) and the same `step(prob, prev_beam, f_done) -> (done, remain)`
+contract, so code written against the reference's step-by-step loop keeps working.
 
-Host-side API parity only: the product path never calls it — top-k, expansion and the permutation-mask
-update run inside the persistent decode kernel (csrc/decode.cu)."""
-import itertools
+The product path never calls it: top-k, expansion and the permutation-mask update run inside the decode kernels
+(csrc/decode.cu).  The selection rule here is the device's: ascending total cost, ties to the lowest flat index
+`beam * n_tokens + token` (a stable sort), integer index arithmetic throughout (the reference's `/` breaks on torch >= 1.5,
+SURVEY §0.4)."""
+import torch
 
 
 class Beam(object):
     def __init__(self, beam_size):
         self.beam_size = beam_size
-        self.candidates = []
-        self.scores = []
+        self.candidates = []   # token sequences of the hypotheses kept by step()
+        self.scores = []       # their accumulated costs
 
     def step(self, prob, prev_beam, f_done):
-        pre_score = prob.new_tensor(prev_beam.scores)
-        score = prob + pre_score.unsqueeze(-1).expand_as(prob)
-        k = min(self.beam_size, score.numel())
-        nbest_score, nbest_ix = score.view(-1).topk(k, largest=False)
-        beam_ix = nbest_ix // prob.size(1)
-        token_ix = nbest_ix - beam_ix * prob.size(1)
-        done_list, remain_list = [], []
-        prev_candidates = prev_beam.candidates
-        for b_score, b_ix, t_ix in itertools.zip_longest(nbest_score.tolist(), beam_ix.tolist(), token_ix.tolist()):
-            candidate = prev_candidates[b_ix] + [t_ix]
-            if f_done(candidate):
-                done_list.append([candidate, b_score])
-            else:
-                remain_list.append(b_ix)
-                self.candidates.append(candidate)
-                self.scores.append(b_score)
-        return done_list, remain_list
+        """prob [live beams, tokens]: cost of appending each token; prev_beam: the Beam of the previous step.
+        Returns (finished [[sequence, cost], ...], parents of the hypotheses that stay alive)."""
+        n_tokens = prob.size(1)
+        totals = (prob + prob.new_tensor(prev_beam.scores)[:, None]).reshape(-1)
+        keep = min(self.beam_size, totals.numel())
+        order = torch.sort(totals, stable=True).indices[:keep].tolist()
+        finished, parents = [], []
+        for flat in order:
+            parent, token = divmod(flat, n_tokens)
+            sequence = prev_beam.candidates[parent] + [token]
+            cost = float(totals[flat])
+            if f_done(sequence):
+                finished.append([sequence, cost])
+                continue
+            parents.append(parent)
+            self.candidates.append(sequence)
+            self.scores.append(cost)
+        return finished, parents
