@@ -29,10 +29,12 @@ template <int KP> struct BwdKvCfg {
   static constexpr int STAGES = 2;
   static constexpr int OPER = STAGES * STAGE_BYTES;      // 192 KB (KP = 256) / 128 KB (KP = 128)
   static constexpr int STG_OFF = OPER;                   // epilogue staging: one 32-row x 128-byte box per epilogue warp
-  static constexpr int VEC_OFF = STG_OFF + 4 * 4096;     // per softmax group: lse2[KP] | D[KP]
-  static constexpr int BAR_OFF = VEC_OFF + 2 * 2 * KP * 4;
+  static constexpr int VEC_OFF = STG_OFF + 4 * 4096;     // per elementwise group (four of them): lse2[KP] | D[KP]
+  static constexpr int BAR_OFF = VEC_OFF + 4 * 2 * KP * 4;
   static constexpr int SMEM = BAR_OFF + 256 + 1024;
-  static constexpr int THREADS = 14 * 32;
+  // warps: 0 TMA, 1 MMA, 2-17 four elementwise groups (two per TMEM buffer, a 32-query chunk each: the kernel is bound by the
+  // exponentials / dropout decisions / dS products, not by the tensor pipe), 18-21 epilogue
+  static constexpr int THREADS = 22 * 32;
 };
 
 template <int KP, bool DROP>
@@ -66,7 +68,7 @@ attention_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_do) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
     for (int i = 0; i < 2; ++i) {
-      mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); mbar_init(s_full + 8 * i, 1); mbar_init(p_ready + 8 * i, 4);
+      mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); mbar_init(s_full + 8 * i, 1); mbar_init(p_ready + 8 * i, 8);
       mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -143,12 +145,12 @@ attention_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __
       issue_pv(n);
       if (n + 2 < NB) issue_s(n + 2);   // after PV(n) in issue order: buffer n & 1 is free by then
     }
-  } else if (warp < 10) {
-    // ===================== elementwise groups: one thread per key row =====================
-    const int w = (warp - 2) >> 2;
+  } else if (warp < 18) {
+    // ===================== elementwise groups: one thread per key row and 32-query chunk =====================
+    const int grp = (warp - 2) >> 2, w = grp >> 1, c = grp & 1;   // TMEM buffer (blocks with n & 1 == w), query chunk of the block
     const int quarter = warp & 3, row = quarter * 32 + lane, gtid = ((warp - 2) & 3) * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    float* lse2 = vecs + w * 2 * KP;
+    float* lse2 = vecs + grp * 2 * KP;
     float* dsm = lse2 + KP;
     const float scale_l2e = scale * LOG2E;
     int have = -1;
@@ -161,27 +163,31 @@ attention_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __
         item = g / NKB;
         key = (g % NKB) * 128 + row;
         const int r = item / heads;
-        named_bar_sync(1 + w, 128);   // the previous group's readers are done
+        named_bar_sync(1 + grp, 128);   // the previous group's readers are done
         for (int q = gtid; q < KP; q += 128) {
           lse2[q] = q < L ? lse_in[(int64_t)item * L + q] * LOG2E : INFINITY;   // queries beyond the sequence: p = 0
           dsm[q] = q < L ? dsum_in[(int64_t)item * L + q] : 0.f;
         }
         mr2 = key < L ? ((mask_add != nullptr && key < mask_len) ? mask_add[(int64_t)r * mask_ld + key] * LOG2E : 0.f) : -INFINITY;
-        named_bar_sync(1 + w, 128);
+        named_bar_sync(1 + grp, 128);
         have = gl;
       }
       const uint32_t sb = lane_addr + (n & 1) * 128;
       const uint64_t ebase = (uint64_t)item * L * L + (uint64_t)key;   // dropout element index = ebase + query * L
       mbar_wait(s_full + 8 * (n & 1), (n >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t st[32], dp[32], pp[16], dd[16];
-        tmem_ld32_nowait(sb + 32 * c, st);
-        tmem_ld32(sb + 64 + 32 * c, dp);
-        const int q0 = qb * 64 + 32 * c;
+      // two passes of 16 queries; dS^T of the first pass is held in registers until the second pass has read its S^T columns
+      // (the dS^T plane of the chunk lies over them)
+      uint32_t dd0[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+      for (int h = 0; h < 2; ++h) {
+        uint32_t st[16], dp[16], pp[8], dd[8];
+        tmem_ld16_nowait(sb + 32 * c + 16 * h, st);
+        tmem_ld16_nowait(sb + 64 + 32 * c + 16 * h, dp);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int q0 = qb * 64 + 32 * c + 16 * h;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
           float p0 = ex2_approx(fmaf(__uint_as_float(st[2 * i]), scale_l2e, mr2) - lse2[q0 + 2 * i]);
           float p1 = ex2_approx(fmaf(__uint_as_float(st[2 * i + 1]), scale_l2e, mr2) - lse2[q0 + 2 * i + 1]);
           float g0 = __uint_as_float(dp[2 * i]), g1 = __uint_as_float(dp[2 * i + 1]);
@@ -201,8 +207,14 @@ attention_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __
             dd[i] = *reinterpret_cast<const uint32_t*>(&b);
           }
         }
-        tmem_st16(sb + 32 * c, pp);
-        tmem_st16(sb + 32 * c + 16, dd);
+        tmem_st8(sb + 32 * c + 8 * h, pp);
+        if (h == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dd0[i] = dd[i];
+        } else {
+          tmem_st8(sb + 32 * c + 16, dd0);
+          tmem_st8(sb + 32 * c + 24, dd);
+        }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
@@ -210,10 +222,10 @@ attention_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __
       if (lane == 0) mbar_arrive(p_ready + 8 * (n & 1));
     }
   } else {
-    // ===================== epilogue group: dK (scaled) and dV rows of a key block =====================
+    // ===================== epilogue group (warps 18-21): dK (scaled) and dV rows of a key block =====================
     const int quarter = warp & 3;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t stg = base + Cfg::STG_OFF + (warp - 10) * 4096;
+    const uint32_t stg = base + Cfg::STG_OFF + (warp - 18) * 4096;
     for (int gl = 0; gl < my_groups; ++gl) {
       const int g = (int)blockIdx.x + gl * (int)gridDim.x, item = g / NKB, kb = g % NKB, r = item / heads, h = item % heads;
       mbar_wait(acc_full + 8 * (gl & 1), (gl >> 1) & 1);
