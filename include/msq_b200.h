@@ -43,7 +43,7 @@ typedef struct msq_config {
                           * 2: "bf16x3" tcgen05 encoder: every operand is carried as hi + lo bf16 (16 significand bits),
                           *    every product is a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with fp32 accumulation, activations
                           *    are exact (erff / tanhf): outputs within ~1e-5 of fp32 at tensor-core speed.  Evaluation
-                          *    only; ViT / text-only models (not the ModifiedResNet tower). */
+                          *    only; ViT, ModifiedResNet (rn_width % 64 == 0) and text-only models. */
   int32_t reserved;      /* flags.  bit 0 "cls_pooler": the inner encoder is a HuggingFace AutoModel (trainers/train.py:1928-1933)
                           * whose outputs[1] = tanh(pooler.dense(seq[:,0])): BertForOrdering.encode takes THAT as the pair's
                           * CLS vector (modeling_bert.py:1315) instead of seq[:,0].  Evaluation entry points only. */
@@ -62,8 +62,8 @@ typedef struct msq_config {
  *   (heads * 64 == hidden); vit_width a multiple of 128, <= 1024; inter % 16 == 0 (bf16x3: % 64); joint sequence
  *   length per pair (text + visual tokens) <= 320 (tcgen05 attention: <= 256); text tokens per pair Lt <= max_pos;
  *   manuals are encoded in micro-batches of MSQ_CHUNK_MANUALS (environment, default 32); the ModifiedResNet tower needs
- *   rn_width % 16 == 0, rn_embed % 32 == 0, image size a multiple of 32; fine-tuning (msq_train_*) covers the ViT-B/32 and
- *   text-only models in precise 0 / 1. */
+ *   rn_width % 16 == 0 (bf16x3: % 64), rn_embed % 32 == 0, image size a multiple of 32; fine-tuning (msq_train_*) covers the
+ *   ViT, ModifiedResNet and text-only models in precise 0 / 1. */
 const char* msq_last_error(void);
 int msq_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
