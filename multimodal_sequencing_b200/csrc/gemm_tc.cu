@@ -71,13 +71,14 @@ struct TcEpi {
   // bf16x3 on CTA pairs: a K slab is staged ONCE as two stages ([a_hi | w_hi], [a_lo | w_lo]) and the three MMA passes
   // read them crosswise, instead of three stages that fetch a_hi and w_hi twice: L2 -> shared-memory traffic -1/3
   int share;
+  Drop drop;   // GemmArgs::drop
 };
 
 // 8 consecutive output columns of one row: accumulator -> value to store (see GemmArgs for the modes)
 template <int ACT, int MODE>
 __device__ __forceinline__ void epi_compute8(float* v, const uint32_t* raw, const float* bias8, const float* s8, const float* beta8,
                                              float ra, float rc, bool has_ln, bool use_res, const float4& r0, const float4& r1,
-                                             bool exact_act = false) {
+                                             bool exact_act, const Drop& drop, uint64_t e0) {
   const float4 b0 = *reinterpret_cast<const float4*>(bias8), b1 = *reinterpret_cast<const float4*>(bias8 + 4);
   const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   if (MODE == 1) {
@@ -97,6 +98,10 @@ __device__ __forceinline__ void epi_compute8(float* v, const uint32_t* raw, cons
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = apply_act_fast(v[i], ACT);
     }
+  }
+  if (MODE == 0 && drop.thresh) {   // dropout of the dense output (fine-tuning), before the residual
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= drop_mul(drop, e0 + i);
   }
   if (use_res) {
     float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
@@ -480,10 +485,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (RES_TMA) {
               const float4 r0 = ld_shared_f4(rowp + (((2 * j) ^ (lane & 7)) << 4)), r1 = ld_shared_f4(rowp + (((2 * j + 1) ^ (lane & 7)) << 4));
               epi_compute8<ACT, MODE>(v, raw + j * 8, bias_s + ch * 32 + j * 8, svec_s + ch * 32 + j * 8, beta_s + ch * 32 + j * 8, ra, rc,
-                                      has_ln, true, r0, r1, exact_act);
+                                      has_ln, true, r0, r1, exact_act, ep.drop, (uint64_t)row * ep.N + (col0 + j * 8));
             } else {
               epi_compute8<ACT, MODE>(v, raw + j * 8, bias_s + ch * 32 + j * 8, svec_s + ch * 32 + j * 8, beta_s + ch * 32 + j * 8, ra, rc,
-                                      has_ln, use_res, res[2 * j], res[2 * j + 1], exact_act);
+                                      has_ln, use_res, res[2 * j], res[2 * j + 1], exact_act, ep.drop, (uint64_t)row * ep.N + (col0 + j * 8));
             }
             if (RESLN) {
 #pragma unroll
@@ -546,7 +551,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (col < ep.N) {  // N % 8 == 0
               float v[8];
               epi_compute8<ACT, MODE>(v, raw + j * 8, bias_s + ch * 32 + j * 8, svec_s + ch * 32 + j * 8, beta_s + ch * 32 + j * 8, ra, rc,
-                                      has_ln, use_res, res[2 * j], res[2 * j + 1], exact_act);
+                                      has_ln, use_res, res[2 * j], res[2 * j + 1], exact_act, ep.drop, (uint64_t)row * ep.N + col);
               if (RESLN) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { st_sum += v[i]; st_sq = fmaf(v[i], v[i], st_sq); }
@@ -629,6 +634,8 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
   ep.bias = g.bias; ep.resid = g.resid; ep.C = g.C; ep.M = g.M; ep.N = g.N; ep.ldc = g.ldc; ep.ldr = g.ldr; ep.act = g.act;
   ep.svec = g.svec; ep.beta = g.beta; ep.stats_in = g.stats_in; ep.stats_out = g.stats_out; ep.C2 = (bf16*)g.C2bf; ep.sp_in = g.sp_in;
   ep.inv_dim = g.ln_inv_dim; ep.eps = g.ln_eps; ep.tn = g.tn; ep.split_k = g.split ? g.K : 0;
+  ep.drop = g.drop;
+  MSQ_REQUIRE(g.drop.thresh == 0 || MODE == 0, "gemm_tc: dropout needs the plain epilogue");
   ep.split_passes = g.split == 2 ? 6 : 3;
   static int share_env = -1;
   if (share_env < 0) { const char* e = getenv("MSQ_X3_SHARE"); share_env = (e && e[0] == '0') ? 0 : 1; }

@@ -85,6 +85,9 @@ struct GemmArgs {
   float ln_inv_dim = 0.f, ln_eps = 0.f;
   float* stats_out = nullptr;
   void* C2bf = nullptr;
+  // gemm_tc only, plain epilogue: training-mode dropout of the dense output BEFORE the residual is added,
+  // C = dropout(act(acc + bias)) + resid, element index row * N + col (the flat index nn.Dropout sees)
+  Drop drop;
 };
 template <typename TA, typename TO> int gemm_simt(const GemmArgs& g, cudaStream_t st);
 
@@ -174,7 +177,8 @@ template <typename T> int act_bwd(const T* dh, const T* u, int64_t n, int act, T
 size_t ln_bwd_scratch_floats(int H);
 template <typename T>
 int ln_bwd(const float* dy, const float* x, const float* add, int64_t rows, int H, const float* gamma, float eps, float* dx, T* dx_t,
-           float* dgamma, float* dbeta, float* scratch, int in_group, int out_group, int out_off, cudaStream_t st);
+           float* dgamma, float* dbeta, float* scratch, int in_group, int out_group, int out_off, cudaStream_t st,
+           const Drop& drop = Drop());   // drop: dx_t = dx . mask (the dense output this LayerNorm normalised was dropped)
 int embed_ln_bwd(const float* dy, const int64_t* ids, const int64_t* tts, int64_t R, int Lt, int Lj, int H, const float* word,
                  const float* pos, const float* type, const float* gamma, float eps, float* dword, float* dpos, float* dtype,
                  float* dgamma, float* dbeta, float* scratch, int pad0, cudaStream_t st);

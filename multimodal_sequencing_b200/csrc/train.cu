@@ -253,7 +253,10 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
     MSQ_TRY((gemm_nt<T, T>(m, (const T*)t.x, H, wptr<T>(L.qkv), L.qkv.ld, L.qkv.b, nullptr, 0, (T*)t.qkv, 3 * H, Mj, 3 * H, H, ACT_NONE, st)));
     MSQ_TRY(attention<T>((const T*)t.qkv, R, Lj, c.heads, 64, 0.125f, ts->mask_add, Lt, Lt, (T*)t.ctx, st,
                          make_drop(dc, DROP_A, (int)l, dc.p_attn)));
-    if (drop_h) {   // s1 = dropout(dense(ctx) + b) + x
+    if (drop_h && gemm_nt_on_tc<T>(m, H, L.out.ld, H, H, H)) {   // s1 = dropout(dense(ctx) + b) + x, dropout inside the GEMM epilogue
+      MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.ctx, H, wptr<T>(L.out), L.out.ld, L.out.b, xf, H, t.s1, H, Mj, H, H, ACT_NONE, st,
+                                 make_drop(dc, DROP_O, (int)l, dc.p_hidden))));
+    } else if (drop_h) {
       MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.ctx, H, wptr<T>(L.out), L.out.ld, L.out.b, nullptr, 0, t.s1, H, Mj, H, H, ACT_NONE, st)));
       MSQ_TRY(dropout_add(t.s1, xf, Mj * H, make_drop(dc, DROP_O, (int)l, dc.p_hidden), st));
     } else {
@@ -262,7 +265,10 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
     MSQ_TRY(layernorm<T>(t.s1, Mj, H, L.ln1.g, L.ln1.b, 1e-12f, x1f, (T*)t.x1, 0, 0, 0, st));
     MSQ_TRY((gemm_nt<T, T>(m, (const T*)t.x1, H, wptr<T>(L.up), L.up.ld, L.up.b, nullptr, 0, (T*)t.u, I, Mj, I, H, ACT_NONE, st)));
     MSQ_TRY(act_fwd<T>((const T*)t.u, Mj * I, ACT_GELU_ERF, (T*)t.hb, st));
-    if (drop_h) {   // s2 = dropout(dense(h) + b) + x1
+    if (drop_h && gemm_nt_on_tc<T>(m, I, L.down.ld, H, H, I)) {   // s2 = dropout(dense(h) + b) + x1
+      MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.hb, I, wptr<T>(L.down), L.down.ld, L.down.b, x1f, H, t.s2, H, Mj, H, I, ACT_NONE, st,
+                                 make_drop(dc, DROP_F, (int)l, dc.p_hidden))));
+    } else if (drop_h) {
       MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.hb, I, wptr<T>(L.down), L.down.ld, L.down.b, nullptr, 0, t.s2, H, Mj, H, I, ACT_NONE, st)));
       MSQ_TRY(dropout_add(t.s2, x1f, Mj * H, make_drop(dc, DROP_F, (int)l, dc.p_hidden), st));
     } else {
@@ -341,17 +347,18 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
     float *dg2 = G(bn + "output.LayerNorm.weight"), *db2 = G(bn + "output.LayerNorm.bias");
     if (err) return err;
     // output.LayerNorm -> ds2 (gB fp32, gT operand copy)
-    MSQ_TRY(ln_bwd<T>(b.gA, t.s2, nullptr, Mj, H, L.ln2.g, 1e-12f, b.gB, (T*)b.gT, dg2, db2, b.ln_scr, 0, 0, 0, st));
-    // under dropout the dense output's gradient is ds2 * mask (operand copy gT); the residual branch keeps ds2 (gB)
-    MSQ_TRY(dropout_mask_copy<T>(b.gB, (T*)b.gT, Mj * H, make_drop(dc, DROP_F, (int)li, dc.p_hidden), st));
+    // under dropout the dense output's gradient is ds2 * mask (operand copy gT, written by the same kernel); the residual
+    // branch keeps ds2 (gB)
+    MSQ_TRY(ln_bwd<T>(b.gA, t.s2, nullptr, Mj, H, L.ln2.g, 1e-12f, b.gB, (T*)b.gT, dg2, db2, b.ln_scr, 0, 0, 0, st,
+                      make_drop(dc, DROP_F, (int)li, dc.p_hidden)));
     MSQ_TRY(wgrad<T>(m, (const T*)b.gT, H, H, (const T*)t.hb, I, I, ACT_NONE, Mj, dWd, dbd, b, st));
     MSQ_TRY((dgrad<T, T>(m, (const T*)b.gT, H, WT[3], I, nullptr, (T*)b.gH, Mj, st)));
     MSQ_TRY(act_bwd<T>((const T*)b.gH, (const T*)t.u, Mj * I, ACT_GELU_ERF, (T*)b.gH, st));
     MSQ_TRY(wgrad<T>(m, (const T*)b.gH, I, I, (const T*)t.x1, H, H, ACT_NONE, Mj, dWu, dbu, b, st));
     MSQ_TRY((dgrad<T, float>(m, (const T*)b.gH, I, WT[2], H, b.gB, b.gA, Mj, st)));            // dX1 = du Wup + ds2
     // attention.output.LayerNorm -> ds1
-    MSQ_TRY(ln_bwd<T>(b.gA, t.s1, nullptr, Mj, H, L.ln1.g, 1e-12f, b.gB, (T*)b.gT, dg1, db1, b.ln_scr, 0, 0, 0, st));
-    MSQ_TRY(dropout_mask_copy<T>(b.gB, (T*)b.gT, Mj * H, make_drop(dc, DROP_O, (int)li, dc.p_hidden), st));
+    MSQ_TRY(ln_bwd<T>(b.gA, t.s1, nullptr, Mj, H, L.ln1.g, 1e-12f, b.gB, (T*)b.gT, dg1, db1, b.ln_scr, 0, 0, 0, st,
+                      make_drop(dc, DROP_O, (int)li, dc.p_hidden)));
     MSQ_TRY(wgrad<T>(m, (const T*)b.gT, H, H, (const T*)t.ctx, H, H, ACT_NONE, Mj, dWo, dbo, b, st));
     MSQ_TRY((dgrad<T, T>(m, (const T*)b.gT, H, WT[1], H, nullptr, (T*)b.gC, Mj, st)));
     MSQ_TRY(attn_bwd<T>((const T*)t.qkv, (const T*)t.ctx, (const T*)b.gC, R, Lj, c.heads, ts->mask_add, Lt, (T*)b.gQ, b.at_scr, st,

@@ -140,17 +140,24 @@ template <> inline const float* wptr<float>(const Lin& l) { return l.w32; }
 template <> inline const bf16* wptr<bf16>(const Lin& l) { return l.w16; }
 
 // C[M,N] = act(A[M,K] W[N,K]^T + bias) + resid on the model's GEMM path (tcgen05 when available and aligned)
+template <typename T>
+static bool gemm_nt_on_tc(const msq_model* m, int lda, int ldw, int ldc, int N, int K) {
+  return sizeof(T) == 2 && model_use_tc(m) && K % 64 == 0 && N % 8 == 0 && ldc % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0;
+}
+// drop (tensor-core path only, see gemm_nt_on_tc): C = dropout(act(A W^T + bias)) + resid
 template <typename T, typename TO>
 static int gemm_nt(const msq_model* m, const T* A, int lda, const T* W, int ldw, const float* bias, const float* resid, int ldr, TO* C,
-                   int ldc, int64_t M, int N, int K, int act, cudaStream_t st) {
+                   int ldc, int64_t M, int N, int K, int act, cudaStream_t st, const Drop& drop = Drop()) {
   GemmArgs g;
   g.A = A; g.W = W; g.bias = bias; g.resid = resid; g.C = C; g.C2 = nullptr;
   g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldc = ldc; g.ldr = ldr; g.act = act;
   if constexpr (sizeof(T) == 4) {
     static_assert(sizeof(TO) == 4, "fp32 mode has fp32 outputs");
+    MSQ_REQUIRE(drop.thresh == 0, "gemm_nt: fused dropout is a tensor-core epilogue");
     return gemm_simt<float, float>(g, st);
   } else {
-    if (model_use_tc(m) && K % 64 == 0 && N % 8 == 0 && ldc % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0) return gemm_tc<TO>(g, st);
+    if (gemm_nt_on_tc<T>(m, lda, ldw, ldc, N, K)) { g.drop = drop; return gemm_tc<TO>(g, st); }
+    MSQ_REQUIRE(drop.thresh == 0, "gemm_nt: fused dropout is a tensor-core epilogue");
     return gemm_simt<bf16, TO>(g, st);
   }
 }

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) ln_bwd_kernel(const float* __r
                                                                 const float* add, int64_t rows, int H,   // dx may alias add
                                                                 const float* __restrict__ gamma, float eps, float* dx,
                                                                 T* __restrict__ dx_t, float* __restrict__ partial, int in_group,
-                                                                int out_group, int out_off) {
+                                                                int out_group, int out_off, Drop drop) {
   pdl_sync();
   __shared__ __align__(16) float sh[LNB_WARPS][2 * 128 * LNB_MAXV];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nv = H >> 7;
@@ -349,7 +349,15 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) ln_bwd_kernel(const float* __r
           d[i].x += a.x; d[i].y += a.y; d[i].z += a.z; d[i].w += a.w;
         }
         if (dx) Vec4<float>::store(dx + row * H + col, d[i]);
-        if (dx_t) Vec4<T>::store(dx_t + row * H + col, d[i]);
+        if (dx_t) {
+          // under dropout of the dense output this LayerNorm normalised, the operand copy is the gradient of that dense
+          // output (dx . mask, element index row * H + col as in the forward); the fp32 dx stays the residual branch's
+          if (drop.thresh) {
+            const uint64_t e = (uint64_t)row * H + col;
+            d[i].x *= drop_mul(drop, e); d[i].y *= drop_mul(drop, e + 1); d[i].z *= drop_mul(drop, e + 2); d[i].w *= drop_mul(drop, e + 3);
+          }
+          Vec4<T>::store(dx_t + row * H + col, d[i]);
+        }
       }
   }
   ln_bwd_flush(sh, ag, ab, nv, H, partial);
@@ -381,20 +389,20 @@ size_t ln_bwd_scratch_floats(int H) { return (size_t)148 * 4 * 2 * H; }
 
 template <typename T>
 int ln_bwd(const float* dy, const float* x, const float* add, int64_t rows, int H, const float* gamma, float eps, float* dx, T* dx_t,
-           float* dgamma, float* dbeta, float* scratch, int in_group, int out_group, int out_off, cudaStream_t st) {
+           float* dgamma, float* dbeta, float* scratch, int in_group, int out_group, int out_off, cudaStream_t st, const Drop& drop) {
   MSQ_REQUIRE(H % 128 == 0 && H <= 128 * LNB_MAXV, "ln_bwd: H=%d unsupported", H);
   if (rows == 0) return MSQ_OK;
   const int nblk = lnb_blocks(rows);
-  MSQ_CUDA(launch_k(ln_bwd_kernel<T>, dim3(nblk), dim3(LNB_WARPS * 32), 0, st, dy, x, add, rows, H, gamma, eps, dx, dx_t, scratch, in_group, out_group, out_off));
+  MSQ_CUDA(launch_k(ln_bwd_kernel<T>, dim3(nblk), dim3(LNB_WARPS * 32), 0, st, dy, x, add, rows, H, gamma, eps, dx, dx_t, scratch, in_group, out_group, out_off, drop));
   MSQ_LAUNCH_CHECK();
   MSQ_CUDA(launch_k(ln_partial_reduce_kernel, dim3(ceil_div(2 * H, 32)), dim3(256), 0, st, (const float*)scratch, nblk, H, dgamma, dbeta));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
 template int ln_bwd<float>(const float*, const float*, const float*, int64_t, int, const float*, float, float*, float*, float*, float*,
-                           float*, int, int, int, cudaStream_t);
+                           float*, int, int, int, cudaStream_t, const Drop&);
 template int ln_bwd<bf16>(const float*, const float*, const float*, int64_t, int, const float*, float, float*, bf16*, float*, float*,
-                          float*, int, int, int, cudaStream_t);
+                          float*, int, int, int, cudaStream_t, const Drop&);
 
 // ---------------------------------------------------------------------------------------------------
 // BertEmbeddings backward (lxrt/modeling.py:356-370): recompute e = word[ids] + pos[t] + type[tt], LayerNorm backward,
