@@ -235,6 +235,11 @@ int64_t msq_train_dropout_step(msq_model* m);
  * msq_train_read_param returns them, the packed evaluation weights pick them up at the next re-pack (msq_adamw_step /
  * msq_model_refresh).  No-op for other backbones. */
 int msq_train_set_bn_mode(msq_model* m, int32_t use_running_stats, void* stream);
+/* Optional time-contrastive objective (models/berson/modeling_bert.py:1176-1216; args.additional_wrapper_level_objectives
+ * contains "time_contrastive"): the NEXT msq_train_step adds weight * nn.TripletMarginLoss(margin=1, p=2)(a, p, n) with
+ * a, p, n = sents[b, triplets[b, 0..2]] (device int32 [B,3]: anchor, positive, negative sentence indices, drawn by the caller
+ * as the reference draws them) to the loss and its gradients.  The reference's weight is 0.1.  One-shot per step. */
+int msq_train_set_triplets(msq_model* m, const int32_t* triplets_dev, int64_t B, float weight, void* stream);
 
 /* Data-parallel overlap: msq_train_step records one CUDA event per REGION of the flat gradient buffer at the moment that
  * region is final (BERSON heads, BERT layers top -> bottom, embeddings, visn_fc, ViT blocks top -> bottom, ViT stem).

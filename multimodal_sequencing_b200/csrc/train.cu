@@ -560,6 +560,29 @@ extern "C" int msq_model_refresh(msq_model* m, void* stream) {
   return msq::model_weights_changed(m, (cudaStream_t)stream);
 }
 
+/* Optional time-contrastive objective (models/berson/modeling_bert.py:1176-1216, args.additional_wrapper_level_objectives):
+ * the NEXT msq_train_step adds weight * TripletMarginLoss(margin 1, p 2) over the sentence vectors sents[b, triplets[b, 0..2]]
+ * (anchor, positive, negative; the caller draws them as the reference does, with numpy's generator) to the loss and to the
+ * gradients.  One-shot: the step after that runs the default objective again. */
+extern "C" int msq_train_set_triplets(msq_model* m, const int32_t* triplets_dev, int64_t B, float weight, void* stream) {
+  DevGuard dev_guard__(m);
+  cudaStream_t st = (cudaStream_t)stream;
+  MSQ_TRY(ensure_train(m, st));
+  MSQ_REQUIRE(triplets_dev && B >= 1, "msq_train_set_triplets: null / empty");
+  TrainState* ts = m->train;
+  if (B > ts->trip_cap) {
+    if (ts->trip) MSQ_CUDA(cudaFree(ts->trip));
+    if (ts->trip_loss) MSQ_CUDA(cudaFree(ts->trip_loss));
+    ts->trip = nullptr; ts->trip_loss = nullptr; ts->trip_cap = 0;
+    MSQ_CUDA(cudaMalloc(&ts->trip, (size_t)B * 3 * sizeof(int32_t)));
+    MSQ_CUDA(cudaMalloc(&ts->trip_loss, (size_t)B * sizeof(float)));
+    ts->trip_cap = B;
+  }
+  MSQ_CUDA(cudaMemcpyAsync(ts->trip, triplets_dev, (size_t)B * 3 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  ts->trip_B = B; ts->trip_weight = weight;
+  return MSQ_OK;
+}
+
 extern "C" int msq_train_set_bn_mode(msq_model* m, int32_t use_running_stats, void* stream) {
   DevGuard dev_guard__(m);
   MSQ_TRY(ensure_train(m, (cudaStream_t)stream));

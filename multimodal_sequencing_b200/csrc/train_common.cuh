@@ -103,6 +103,11 @@ struct TrainState {
   HeadTape ht;
   SplitK splitk;
   RnTrain* rn = nullptr;                 // ModifiedResNet tower state (cfg.rn_width != 0)
+  // ---- optional time-contrastive objective of the NEXT msq_train_step (msq_train_set_triplets; consumed by that step)
+  int32_t* trip = nullptr;               // device [trip_B, 3]: anchor / positive / negative sentence index per manual
+  float* trip_loss = nullptr;            // device [trip_cap]
+  int64_t trip_B = 0, trip_cap = 0;
+  float trip_weight = 0.f;
   // ---- dropout (msq_train_set_dropout): probabilities + seed; `step` is the counter of the forward whose masks are live
   DropCfg drop;
   uint32_t drop_next_step = 0;
@@ -119,6 +124,8 @@ inline void train_state_free_impl(TrainState* ts) {
   for (void* p : ts->owned) cudaFree(p);
   rn_train_free(ts->rn);
   for (cudaEvent_t e : ts->ready_ev) cudaEventDestroy(e);
+  if (ts->trip) cudaFree(ts->trip);
+  if (ts->trip_loss) cudaFree(ts->trip_loss);
   if (ts->adam_m) cudaFree(ts->adam_m);
   if (ts->adam_v) cudaFree(ts->adam_v);
   if (ts->opt_scratch) cudaFree(ts->opt_scratch);

@@ -527,6 +527,45 @@ __global__ void __launch_bounds__(256) tf_pointer_kernel(const float* __restrict
   if (tid == 0) { partial[(int64_t)b * (H + 1) + H] = dbt_acc; nll[b] = nll_acc; }
 }
 
+// ---- time-contrastive objective (modeling_bert.py:1176-1216): weight * mean_b max(|a - p + eps| - |a - n + eps| + 1, 0) over the
+// sentence vectors a, p, n = sents[b, triplet[b]] (nn.TripletMarginLoss(margin=1, p=2): pairwise_distance adds eps = 1e-6 to the
+// difference).  One block per manual: loss term into tl[b], gradient rows added to dsents (the three rows are distinct).
+__global__ void __launch_bounds__(256) triplet_kernel(const float* __restrict__ sents, const int32_t* __restrict__ trip, int N, int H, float gscale,
+                                                      float* __restrict__ tl, float* __restrict__ dsents) {
+  pdl_sync();
+  __shared__ float red[2][8];
+  const int64_t b = blockIdx.x;
+  const int ia = trip[b * 3], ip = trip[b * 3 + 1], in = trip[b * 3 + 2];
+  const float *a = sents + (b * N + ia) * H, *p = sents + (b * N + ip) * H, *n = sents + (b * N + in) * H;
+  float sp = 0.f, sn = 0.f;
+  for (int d = threadIdx.x; d < H; d += blockDim.x) {
+    const float x = a[d] - p[d] + 1e-6f, y = a[d] - n[d] + 1e-6f;
+    sp = fmaf(x, x, sp); sn = fmaf(y, y, sn);
+  }
+  sp = warp_sum(sp); sn = warp_sum(sn);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sp; red[1][threadIdx.x >> 5] = sn; }
+  __syncthreads();
+  float tp = 0.f, tn = 0.f;
+  for (int i = 0; i < 8; ++i) { tp += red[0][i]; tn += red[1][i]; }
+  const float dap = sqrtf(tp), dan = sqrtf(tn), l = dap - dan + 1.0f;
+  if (threadIdx.x == 0) tl[b] = fmaxf(l, 0.f);
+  if (!(l > 0.f) || !dsents) return;
+  const float cp = dap > 0.f ? gscale / dap : 0.f, cn = dan > 0.f ? gscale / dan : 0.f;
+  float *ga = dsents + (b * N + ia) * H, *gp = dsents + (b * N + ip) * H, *gn = dsents + (b * N + in) * H;
+  for (int d = threadIdx.x; d < H; d += blockDim.x) {
+    const float x = (a[d] - p[d] + 1e-6f) * cp, y = (a[d] - n[d] + 1e-6f) * cn;
+    ga[d] += x - y; gp[d] -= x; gn[d] += y;
+  }
+}
+__global__ void triplet_loss_add_kernel(const float* __restrict__ tl, int64_t B, float w, float* __restrict__ loss) {
+  pdl_sync();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float s = 0.f;
+    for (int64_t b = 0; b < B; ++b) s += tl[b];
+    *loss += w * s / (float)B;
+  }
+}
+
 // loss = mean_b nll_b / (N - 1) + lam * mean_b sum_p NLL(softmax(rel6[p, 0:2]), label_p) / P   (1140-1174)
 __global__ void __launch_bounds__(256) train_loss_kernel(const float* __restrict__ nll, const float* __restrict__ rel6, const int64_t* __restrict__ labels,
                                                          int64_t B, int N, float lam, float* __restrict__ out) {
@@ -806,6 +845,17 @@ int heads_train(msq_model* m, const int64_t* sep, int64_t B, int N, const int32_
   MSQ_CUDA(cudaMemsetAsync(dsents, 0, (size_t)M * H * sizeof(float), st));
   MSQ_CUDA(launch_k(sents_ext_bwd_kernel, dim3(ceil_div(M * (int64_t)H, 256)), dim3(256), 0, st, (const float*)dext, B, N, H, dsents));
   MSQ_LAUNCH_CHECK();
+  if (ts->trip && ts->trip_weight != 0.f) {   // time-contrastive objective set for this step (msq_train_set_triplets)
+    MSQ_REQUIRE(ts->trip_B == B, "msq_train_step: %lld triplets were set for a batch of %lld manuals", (long long)ts->trip_B, (long long)B);
+    MSQ_CUDA(launch_k(triplet_kernel, dim3((unsigned)B), dim3(256), 0, st, (const float*)h.sents, (const int32_t*)ts->trip, N, H,
+                      ts->trip_weight / (float)B, ts->trip_loss, dsents));
+    MSQ_LAUNCH_CHECK();
+    if (loss_out) {
+      MSQ_CUDA(launch_k(triplet_loss_add_kernel, dim3(1), dim3(32), 0, st, (const float*)ts->trip_loss, B, ts->trip_weight, loss_out));
+      MSQ_LAUNCH_CHECK();
+    }
+    ts->trip_weight = 0.f;   // one-shot
+  }
   // key_linear, h0, paragraph encoder
   MSQ_TRY(wgrad<float>(m, dkey0, H, H, h.keyin, 2 * H, 2 * H, ACT_NONE, M, G("key_linear.weight"), G("key_linear.bias"), bb, st));
   MSQ_TRY((dgrad<float, float>(m, dkey0, H, ts->keyT, 2 * H, nullptr, dkeyin, M, st)));

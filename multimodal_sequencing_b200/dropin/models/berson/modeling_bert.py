@@ -283,6 +283,8 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
         if getattr(args, "multimodal_loss", False):
             raise NotImplementedError("multimodal_loss objective is outside the scoped path (SURVEY §2 row 18)")
         self.pw_k = nn.Linear((H + 2) * 4, H, False)
+        # "other losses" (modeling_bert.py:904-911): the optional time-contrastive objective
+        self.time_contrastive = "time_contrastive" in (getattr(args, "additional_wrapper_level_objectives", None) or ())
         for name, mod in self.named_modules():      # init_weights() (913): heads only, the inner model keeps its own
             if not name.startswith("bert"):
                 _init_bert_weights(mod, config.initializer_range)
@@ -361,12 +363,28 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
                 elif count and n.endswith("num_batches_tracked"):
                     b += 1
 
+    @staticmethod
+    def _time_contrastive_triplets(target):
+        """modeling_bert.py:1176-1209: anchor position, a neighbouring positive, a negative at least two positions away -- drawn
+        with numpy's global generator in the reference's call order -- each mapped through the ground-truth order of its manual."""
+        import numpy as np
+        target = target.tolist()
+        out = []
+        for tgt in target:
+            n = len(tgt)
+            anchor = np.random.choice(list(range(n)), 1, replace=False)[0]
+            positive = np.random.choice([i for i in (anchor - 1, anchor + 1) if 0 <= i < n], 1, replace=False)[0]
+            negative = np.random.choice([j for j in range(n) if abs(j - anchor) >= 2], 1, replace=False)[0]
+            out.append([tgt[anchor], tgt[positive], tgt[negative]])
+        return torch.tensor(out, dtype=torch.int32)
+
     def _train_forward(self, pb):
         eng = self.engine()
         self._apply_dropout_config(eng)
         flat = eng.new_grad_buffer()
+        trip = self._time_contrastive_triplets(pb.ground_truth) if self.time_contrastive else None
         with torch.no_grad():
-            loss = eng.train_step(pb, flat, self.pairwise_loss_lam)
+            loss = eng.train_step(pb, flat, self.pairwise_loss_lam, triplets=trip)
         self._pull_bn_buffers(eng)
         lay = {n: (o, k) for n, o, k, _ in eng.train_layout()}
         named = list(self.named_parameters())
@@ -395,8 +413,9 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
             flat = self.__dict__["_flat"] = eng.new_grad_buffer()
         flat.zero_()
         self.__dict__["_lib_masters"] = True   # from here on the library's fp32 masters are the truth (until pull_weights)
+        trip = self._time_contrastive_triplets(pb.ground_truth) if self.time_contrastive else None
         with torch.no_grad():
-            loss = eng.train_step(pb, flat, self.pairwise_loss_lam)
+            loss = eng.train_step(pb, flat, self.pairwise_loss_lam, triplets=trip)
             scale = allreduce_gradients(flat) if allreduce else 1.0
             eng.adamw_step(flat, lr, betas, eps, weight_decay, max_grad_norm, scale if grad_scale is None else grad_scale)
         for n, b in self.named_buffers():
@@ -425,7 +444,14 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
         if self.training:
             return (self._train_forward(pb),)
         with torch.no_grad():
-            return (self.engine().training_loss(pb, self.pairwise_loss_lam),)
+            loss = self.engine().training_loss(pb, self.pairwise_loss_lam)
+            if self.time_contrastive:   # evaluation: the same extra term on the sentence vectors (a [B, H]-sized host-side op)
+                trip = self._time_contrastive_triplets(pb.ground_truth).long().to(loss.device)
+                sents = self.engine().encode(pb)["sents"]
+                ar = torch.arange(sents.shape[0], device=sents.device)
+                a, p, n = (sents[ar, trip[:, i]] for i in range(3))
+                loss = loss + 0.1 * torch.nn.functional.triplet_margin_loss(a, p, n, margin=1.0, p=2)
+            return (loss,)
 
     # ---- encode ------------------------------------------------------------------------------
     def encode(self, input_ids, attention_mask=None, token_type_ids=None, pairs_list=None, passage_length=None,

@@ -385,12 +385,19 @@ class OrderingEngine:
         """counter that keyed the masks of the last training forward (-1: none yet); what oracle.dropout.DropSpec needs"""
         return int(self.lib.msq_train_dropout_step(self._h))
 
-    def train_step(self, batch: PairBatch, grads, lam=0.6):
+    def train_step(self, batch: PairBatch, grads, lam=0.6, triplets=None, triplet_weight=0.1):
         """One fine-tuning forward + backward of BertForOrdering._forward's default objective (modeling_bert.py:943-1174:
         pointer NLL / (N-1) + lam * pairwise NLL / P, batch mean): grads += dL/dparam for every parameter of the path
-        (encoder and heads).  Returns the loss as a 0-d device tensor.  Follow with adamw_step(grads, ...)."""
+        (encoder and heads).  Returns the loss as a 0-d device tensor.  Follow with adamw_step(grads, ...).
+        triplets [B,3] (anchor, positive, negative sentence index per manual): adds the reference's optional time-contrastive
+        term triplet_weight * TripletMarginLoss(margin 1, p 2) (modeling_bert.py:1176-1216)."""
         b = batch.to(self.device)
         B, P, Lt = b.input_ids.shape
+        if triplets is not None:
+            tr = torch.as_tensor(triplets).to(device=self.device, dtype=torch.int32).contiguous()
+            if tuple(tr.shape) != (B, 3):
+                raise ValueError("triplets must be [B, 3], got %s" % (tuple(tr.shape),))
+            _lib.check(self.lib.msq_train_set_triplets(self._h, self._p(tr), B, float(triplet_weight), self._stream()))
         gt = b.ground_truth.to(torch.int32).contiguous()
         loss = torch.zeros(1, device=self.device)
         n_img = 0 if b.images is None else b.images.shape[0]

@@ -478,9 +478,27 @@ def order_manuals(sd, cfg, input_ids, labels, n_steps, beam_size, images=None, t
 # --------------------------------------------------------------------------------------------
 
 
-def training_loss(sd, cfg, inp, lam=0.6):
-    """modeling_bert.py:943-1174 (default objectives only: pointer NLL + lam * pairwise NLL).
-    All manuals in the batch have N steps (tgt_len == num)."""
+def time_contrastive_triplets(target, rng=None):
+    """modeling_bert.py:1176-1209: per manual an anchor POSITION is drawn, a neighbouring position as the positive, a position at
+    least two away as the negative (np.random.choice, in this call order), and each is mapped through the ground-truth order
+    `target[b]` to a sentence index.  -> long [B, 3] (anchor, positive, negative) rows of the sentence matrix."""
+    import numpy as np
+    rng = np.random if rng is None else rng
+    B, N = target.shape
+    out = []
+    for b in range(B):
+        anchor = rng.choice(list(range(N)), 1, replace=False)[0]
+        pos = [i for i in (anchor - 1, anchor + 1) if 0 <= i < N]
+        positive = rng.choice(pos, 1, replace=False)[0]
+        negative = rng.choice([j for j in range(N) if abs(j - anchor) >= 2], 1, replace=False)[0]
+        out.append([int(target[b][anchor]), int(target[b][positive]), int(target[b][negative])])
+    return torch.tensor(out, dtype=torch.long)
+
+
+def training_loss(sd, cfg, inp, lam=0.6, triplets=None):
+    """modeling_bert.py:943-1174 (pointer NLL + lam * pairwise NLL), plus the optional time-contrastive term (1176-1216:
+    0.1 * TripletMarginLoss(margin 1, p 2) over the sentence vectors picked by `triplets` [B, 3], see
+    time_contrastive_triplets).  All manuals in the batch have N steps (tgt_len == num)."""
     enc = encode(sd, cfg, inp)
     target = inp["ground_truth"]
     B, N = target.shape
@@ -520,7 +538,11 @@ def training_loss(sd, cfg, inp, lam=0.6):
     pl = inp["pairwise_labels"].reshape(-1)
     pair = (-lp[torch.arange(lp.shape[0]), pl]).reshape(B, -1)
     pair = (pair.sum(-1) / (inp["pairs_num"].float() + 1e-20)).sum() / B
-    return ptr + lam * pair
+    loss = ptr + lam * pair
+    if triplets is not None:
+        a, p, n = (sents[ar, triplets[:, i]] for i in range(3))
+        loss = loss + 0.1 * F.triplet_margin_loss(a, p, n, margin=1.0, p=2)
+    return loss
 
 
 # --------------------------------------------------------------------------------------------

@@ -56,14 +56,14 @@ def inner_grads(sd, cfg, ids, tt, mask, images, g_lang, g_visn=None, pre="bert."
     return lang.detach(), (None if visn is None else visn.detach()), _padding_idx_rows(grads, pre, images is not None)
 
 
-def loss_grads(sd, cfg, inp, lam=0.6, dropout=None):
+def loss_grads(sd, cfg, inp, lam=0.6, dropout=None, triplets=None):
     """(loss, {name: grad}) of BertForOrdering._forward's default objective (modeling_bert.py:943-1174).
     dropout: None (p = 0) or an oracle.dropout.DropSpec -- the training-mode forward with those masks."""
     leaf = _leaf_sd(sd)
     O.DROPOUT = dropout
     try:
         with torch.enable_grad():
-            loss = O.training_loss(leaf, cfg, inp, lam)
+            loss = O.training_loss(leaf, cfg, inp, lam, triplets=triplets)
             loss.backward()
     finally:
         O.DROPOUT = None

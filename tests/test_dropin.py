@@ -544,7 +544,7 @@ def test_train_mode_autograd_bridge_host_logic(golden_dir):
         def new_grad_buffer(self):
             return torch.zeros(off)
 
-        def train_step(self, pb, flat, lam):
+        def train_step(self, pb, flat, lam, triplets=None):
             for i, (n, o, k, _) in enumerate(layout):
                 flat[o:o + k] += float(i + 1)
             return torch.tensor(2.5)

@@ -48,3 +48,44 @@ def test_live(mm, N, W):
     assert out.returncode == 0, out.stderr[-2000:]
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
     assert res["oracle"] == res["ref"]
+
+
+TC_SCRIPT = r'''
+import json, sys, numpy as np, torch
+sys.path.insert(0, %(golden)r); sys.path.insert(0, %(root)r)
+import ref_harness as rh
+from oracle import berson_oracle as O
+torch.set_grad_enabled(False)
+TINY = dict(vocab_size_or_config_json_file=600, hidden_size=128, num_hidden_layers=1, num_attention_heads=2,
+            intermediate_size=256, max_position_embeddings=128)
+N = 6
+ns = rh.load()
+args = rh.make_args(N, 4)
+args.ff_size = 128
+args.additional_wrapper_level_objectives = ["time_contrastive"]
+model = rh.build_text_model(ns, TINY, args, seed=9)
+model.tokenizer = rh.StubTokenizer()
+assert model.time_contrastive
+sd = {k: v.clone() for k, v in model.state_dict().items()}
+cfg = dict(num_hidden_layers=1, num_attention_heads=2, vit=None)
+ids, labels, _ = O.synthetic_manuals(3, N, 12, vocab=600, seed=21)
+inputs = {"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": labels}
+np.random.seed(1234)
+ref = float(model(inputs)[0])
+inp = O.prepare_inputs(ids, labels, N, None)
+np.random.seed(1234)
+trip = O.time_contrastive_triplets(inp["ground_truth"])
+print("RESULT " + json.dumps({"ref": ref, "oracle": float(O.training_loss(sd, cfg, inp, triplets=trip)),
+                              "plain": float(O.training_loss(sd, cfg, inp))}))
+'''
+
+
+def test_time_contrastive_objective_live():
+    """modeling_bert.py:1176-1216 on the real reference (numpy seeded) against the oracle's restatement of the index draw
+    and of the triplet term."""
+    code = TC_SCRIPT % dict(golden=os.path.join(HERE, "golden"), root=os.path.dirname(HERE))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    assert abs(res["oracle"] - res["ref"]) < 2e-5, res
+    assert abs(res["oracle"] - res["plain"]) > 1e-3, res      # the term was active
