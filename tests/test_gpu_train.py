@@ -320,6 +320,34 @@ def test_resnet_running_statistics_follow_the_batch(golden_dir):
     assert torch.equal(eng2.read_param(v + "bn1.running_mean", tuple(sd[v + "bn1.running_mean"].shape)).cpu(), sd[v + "bn1.running_mean"])
 
 
+@pytest.mark.parametrize("precise", [True, False])
+def test_train_step_with_time_contrastive_objective(golden_dir, precise):
+    """The reference's optional time-contrastive term (modeling_bert.py:1176-1216, 0.1 * TripletMarginLoss over sentence
+    vectors): loss and every gradient against torch autograd through the oracle with the same triplets."""
+    g = torch.load(os.path.join(golden_dir, "text_tiny.pt"), weights_only=False)
+    eng = _engine(g["sd"], _cfg_from_golden(g), precise)
+    B, N, L = 3, 5, 24
+    ids, labels, _ = O.synthetic_manuals(B, N, L, vocab=1000, seed=33)
+    pb = eng.prepare(ids, labels, N, None)
+    inp = O.prepare_inputs(ids, labels, N, None)
+    import numpy as np
+    trip = O.time_contrastive_triplets(inp["ground_truth"], np.random.RandomState(5))
+    assert all(len(set(t)) == 3 for t in trip.tolist())
+    grads = eng.new_grad_buffer()
+    loss = float(eng.train_step(pb, grads, triplets=trip))
+    torch.cuda.synchronize()
+    oloss, ref = TO.loss_grads(g["sd"], _ocfg(g), inp, triplets=trip)
+    o0, _ = TO.loss_grads(g["sd"], _ocfg(g), inp)
+    assert oloss - o0 > 1e-3, "the hinge must be active for the test to mean anything"
+    assert abs(loss - oloss) < (5e-5 if precise else 2e-2), (loss, oloss)
+    worst = _compare(eng.grads_by_name(grads), ref, 5e-4 if precise else 1e-1)
+    print("time-contrastive train step (%s): loss %.6f (oracle %.6f, without the term %.6f), worst relative L2 %.2e at %s" %
+          ("fp32" if precise else "bf16", loss, oloss, o0, worst[1], worst[0]))
+    # one-shot: the next step runs the default objective again
+    grads.zero_()
+    assert abs(float(eng.train_step(pb, grads)) - o0) < (5e-5 if precise else 2e-2)
+
+
 def test_fine_tuning_lowers_the_loss(golden_dir):
     """Five optimizer steps on one batch: the loss the step reports must fall (end-to-end sign / wiring check), and the
     eval-mode loss entry point must agree with the training one before and after."""
