@@ -170,12 +170,17 @@ __global__ void __launch_bounds__(256) colsum_partial_bf16_kernel(const bf16* __
     partial[(int64_t)blockIdx.y * N + blockIdx.x * 64 + threadIdx.x] = t;
   }
 }
-__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ partial, int N, float* __restrict__ out) {
+__global__ void __launch_bounds__(64) colsum_reduce_kernel(const float* __restrict__ partial, int N, float* __restrict__ out) {
   pdl_sync();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
+  // all 64 chunk loads are issued before the (ordered) adds: the kernel is a handful of blocks, latency is all it costs
+  float v[CS_CHUNKS];
+#pragma unroll
+  for (int c = 0; c < CS_CHUNKS; ++c) v[c] = __ldcg(partial + (int64_t)c * N + n);
   float s = 0.f;
-  for (int c = 0; c < CS_CHUNKS; ++c) s += partial[(int64_t)c * N + n];
+#pragma unroll
+  for (int c = 0; c < CS_CHUNKS; ++c) s += v[c];
   out[n] += s;
 }
 size_t colsum_scratch_floats(int N) { return (size_t)CS_CHUNKS * N; }
@@ -184,7 +189,7 @@ int colsum_accum_bf16(const bf16* G, int64_t M, int N, int ld, float* out, float
   if (M == 0) return MSQ_OK;
   MSQ_CUDA(launch_k(colsum_partial_bf16_kernel, dim3(ceil_div(N, 64), CS_CHUNKS), dim3(256), 0, st, G, M, N, ld, scratch));
   MSQ_LAUNCH_CHECK();
-  MSQ_CUDA(launch_k(colsum_reduce_kernel, dim3(ceil_div(N, 256)), dim3(256), 0, st, (const float*)scratch, N, out));
+  MSQ_CUDA(launch_k(colsum_reduce_kernel, dim3(ceil_div(N, 64)), dim3(64), 0, st, (const float*)scratch, N, out));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -262,16 +267,17 @@ constexpr int LNB_WARPS = 4;
 constexpr int LNB_MAXV = 8;   // H <= 1024
 
 // v: pre-LN row, d: dy row (in), dx row (out).  ag/ab accumulate dgamma/dbeta for this lane's columns.
+template <int MV = LNB_MAXV>
 __device__ __forceinline__ void ln_bwd_row(float4* v, float4* d, int nv, int H, int lane, const float* __restrict__ gamma, float eps,
                                            float4* ag, float4* ab) {
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LNB_MAXV; ++i)
+  for (int i = 0; i < MV; ++i)
     if (i < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   const float mean = warp_sum(s) / (float)H;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < LNB_MAXV; ++i)
+  for (int i = 0; i < MV; ++i)
     if (i < nv) {
       v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
       q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
@@ -279,7 +285,7 @@ __device__ __forceinline__ void ln_bwd_row(float4* v, float4* d, int nv, int H, 
   const float rstd = rsqrtf(warp_sum(q) / (float)H + eps);
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < LNB_MAXV; ++i)
+  for (int i = 0; i < MV; ++i)
     if (i < nv) {
       const float4 gm = *reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4);
       v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;          // xhat
@@ -292,18 +298,19 @@ __device__ __forceinline__ void ln_bwd_row(float4* v, float4* d, int nv, int H, 
     }
   const float m1 = warp_sum(s1) / (float)H, m2 = warp_sum(s2) / (float)H;
 #pragma unroll
-  for (int i = 0; i < LNB_MAXV; ++i)
+  for (int i = 0; i < MV; ++i)
     if (i < nv) {
       d[i].x = rstd * (d[i].x - m1 - v[i].x * m2); d[i].y = rstd * (d[i].y - m1 - v[i].y * m2);
       d[i].z = rstd * (d[i].z - m1 - v[i].z * m2); d[i].w = rstd * (d[i].w - m1 - v[i].w * m2);
     }
 }
 // combine the warps' dgamma / dbeta accumulators and write this block's partial sums
+template <int MV = LNB_MAXV>
 __device__ __forceinline__ void ln_bwd_flush(float (*sh)[2 * 128 * LNB_MAXV], const float4* ag, const float4* ab, int nv, int H,
                                              float* __restrict__ partial) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 0; i < LNB_MAXV; ++i)
+  for (int i = 0; i < MV; ++i)
     if (i < nv) {
       const int col = (i * 32 + lane) * 4;
       *reinterpret_cast<float4*>(&sh[warp][col]) = ag[i];
@@ -320,7 +327,7 @@ __device__ __forceinline__ int64_t remap_row_t(int64_t row, int in_group, int ou
   return in_group ? (row / in_group) * (int64_t)out_group + out_off + row % in_group : row;
 }
 
-template <typename T>
+template <typename T, int MV>
 __global__ void __launch_bounds__(LNB_WARPS * 32) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                 const float* add, int64_t rows, int H,   // dx may alias add
                                                                 const float* __restrict__ gamma, float eps, float* dx,
@@ -329,19 +336,19 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) ln_bwd_kernel(const float* __r
   pdl_sync();
   __shared__ __align__(16) float sh[LNB_WARPS][2 * 128 * LNB_MAXV];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nv = H >> 7;
-  float4 ag[LNB_MAXV], ab[LNB_MAXV];
+  float4 ag[MV], ab[MV];
 #pragma unroll
-  for (int i = 0; i < LNB_MAXV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < MV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t row = (int64_t)blockIdx.x * LNB_WARPS + warp; row < rows; row += (int64_t)gridDim.x * LNB_WARPS) {
-    float4 v[LNB_MAXV], d[LNB_MAXV];
+    float4 v[MV], d[MV];
     const float* xr = x + row * H;
     const float* dr = dy + remap_row_t(row, in_group, out_group, out_off) * H;
 #pragma unroll
-    for (int i = 0; i < LNB_MAXV; ++i)
+    for (int i = 0; i < MV; ++i)
       if (i < nv) { v[i] = Vec4<float>::load(xr + (i * 32 + lane) * 4); d[i] = Vec4<float>::load(dr + (i * 32 + lane) * 4); }
-    ln_bwd_row(v, d, nv, H, lane, gamma, eps, ag, ab);
+    ln_bwd_row<MV>(v, d, nv, H, lane, gamma, eps, ag, ab);
 #pragma unroll
-    for (int i = 0; i < LNB_MAXV; ++i)
+    for (int i = 0; i < MV; ++i)
       if (i < nv) {
         const int col = (i * 32 + lane) * 4;
         if (add) {
@@ -360,26 +367,35 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) ln_bwd_kernel(const float* __r
         }
       }
   }
-  ln_bwd_flush(sh, ag, ab, nv, H, partial);
+  ln_bwd_flush<MV>(sh, ag, ab, nv, H, partial);
 }
 
-// block = 32 columns x 8 groups of partial blocks; the groups' sums are combined in index order (deterministic)
-__global__ void __launch_bounds__(256) ln_partial_reduce_kernel(const float* __restrict__ partial, int nblk, int H,
+// block = 32 columns x 32 groups of partial blocks; the groups' sums are combined in index order (deterministic)
+constexpr int LNR_GROUPS = 32;
+__global__ void __launch_bounds__(LNR_GROUPS * 32) ln_partial_reduce_kernel(const float* __restrict__ partial, int nblk, int H,
                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta) {
   pdl_sync();
-  __shared__ float sh[8][33];
+  __shared__ float sh[LNR_GROUPS][33];
   const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   float s = 0.f;
   if (c < 2 * H) {
-    const int per = (nblk + 7) / 8, b0 = grp * per, b1 = min(nblk, b0 + per);
-    for (int b = b0; b < b1; ++b) s += partial[(int64_t)b * 2 * H + c];
+    const int per = (nblk + LNR_GROUPS - 1) / LNR_GROUPS, b0 = grp * per, b1 = min(nblk, b0 + per);
+    int b = b0;
+    for (; b + 8 <= b1; b += 8) {   // eight loads in flight per thread, added in index order
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(partial + (int64_t)(b + u) * 2 * H + c);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; b < b1; ++b) s += __ldcg(partial + (int64_t)b * 2 * H + c);
   }
   sh[grp][cl] = s;
   __syncthreads();
   if (grp == 0 && c < 2 * H) {
     float t = 0.f;
-    for (int g = 0; g < 8; ++g) t += sh[g][cl];
+    for (int g = 0; g < LNR_GROUPS; ++g) t += sh[g][cl];
     if (c < H) dgamma[c] += t; else dbeta[c - H] += t;
   }
 }
@@ -393,9 +409,11 @@ int ln_bwd(const float* dy, const float* x, const float* add, int64_t rows, int 
   MSQ_REQUIRE(H % 128 == 0 && H <= 128 * LNB_MAXV, "ln_bwd: H=%d unsupported", H);
   if (rows == 0) return MSQ_OK;
   const int nblk = lnb_blocks(rows);
-  MSQ_CUDA(launch_k(ln_bwd_kernel<T>, dim3(nblk), dim3(LNB_WARPS * 32), 0, st, dy, x, add, rows, H, gamma, eps, dx, dx_t, scratch, in_group, out_group, out_off, drop));
+  // H = 768 instantiation keeps six float4 per array instead of eight (fewer registers -> one more resident block per SM)
+  if (H <= 768) MSQ_CUDA(launch_k(ln_bwd_kernel<T, 6>, dim3(nblk), dim3(LNB_WARPS * 32), 0, st, dy, x, add, rows, H, gamma, eps, dx, dx_t, scratch, in_group, out_group, out_off, drop));
+  else MSQ_CUDA(launch_k(ln_bwd_kernel<T, LNB_MAXV>, dim3(nblk), dim3(LNB_WARPS * 32), 0, st, dy, x, add, rows, H, gamma, eps, dx, dx_t, scratch, in_group, out_group, out_off, drop));
   MSQ_LAUNCH_CHECK();
-  MSQ_CUDA(launch_k(ln_partial_reduce_kernel, dim3(ceil_div(2 * H, 32)), dim3(256), 0, st, (const float*)scratch, nblk, H, dgamma, dbeta));
+  MSQ_CUDA(launch_k(ln_partial_reduce_kernel, dim3(ceil_div(2 * H, 32)), dim3(LNR_GROUPS * 32), 0, st, (const float*)scratch, nblk, H, dgamma, dbeta));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -461,7 +479,7 @@ int embed_ln_bwd(const float* dy, const int64_t* ids, const int64_t* tts, int64_
   const int nblk = lnb_blocks(R * Lt);
   MSQ_CUDA(launch_k(embed_ln_bwd_kernel, dim3(nblk), dim3(LNB_WARPS * 32), 0, st, dy, ids, tts, R, Lt, Lj, H, word, pos, type, gamma, eps, dword, dpos, dtype, scratch, pad0));
   MSQ_LAUNCH_CHECK();
-  MSQ_CUDA(launch_k(ln_partial_reduce_kernel, dim3(ceil_div(2 * H, 32)), dim3(256), 0, st, (const float*)scratch, nblk, H, dgamma, dbeta));
+  MSQ_CUDA(launch_k(ln_partial_reduce_kernel, dim3(ceil_div(2 * H, 32)), dim3(LNR_GROUPS * 32), 0, st, (const float*)scratch, nblk, H, dgamma, dbeta));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -527,7 +545,7 @@ int vit_assemble_bwd(const float* dy, const float* patch, const int32_t* img_ind
   const int nblk = lnb_blocks(R * (1 + il * g2));
   MSQ_CUDA(launch_k(vit_assemble_bwd_kernel, dim3(nblk), dim3(LNB_WARPS * 32), 0, st, dy, patch, img_index, R, il, g2, W, cls, pos, gamma, eps, dpatch, dcls, dpos, scratch));
   MSQ_LAUNCH_CHECK();
-  MSQ_CUDA(launch_k(ln_partial_reduce_kernel, dim3(ceil_div(2 * W, 32)), dim3(256), 0, st, (const float*)scratch, nblk, W, dgamma, dbeta));
+  MSQ_CUDA(launch_k(ln_partial_reduce_kernel, dim3(ceil_div(2 * W, 32)), dim3(LNR_GROUPS * 32), 0, st, (const float*)scratch, nblk, W, dgamma, dbeta));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
