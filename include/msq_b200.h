@@ -240,6 +240,12 @@ int msq_train_set_bn_mode(msq_model* m, int32_t use_running_stats, void* stream)
  * a, p, n = sents[b, triplets[b, 0..2]] (device int32 [B,3]: anchor, positive, negative sentence indices, drawn by the caller
  * as the reference draws them) to the loss and its gradients.  The reference's weight is 0.1.  One-shot per step. */
 int msq_train_set_triplets(msq_model* m, const int32_t* triplets_dev, int64_t B, float weight, void* stream);
+/* Optional image pairwise objective (args.multimodal_loss; models/berson/modeling_bert.py:897-898, 1359-1364, 1218-1225):
+ * while on, every msq_train_step adds lam * mean_b sum_p NLL(softmax(pairwise_relationship(img_projection(visn[p, 0]))),
+ * pairwise_label_p) / P and the gradients of img_projection.*, the shared pairwise_relationship.* and the first visual token of
+ * every pair row.  img_projection.weight [H, H] / .bias [H] must be registered (msq_model_set_weight) before the first
+ * training call; the reference's Linear(v_feature_size, H) is fed the H-d token, i.e. it only runs when v_feature_size == H. */
+int msq_train_set_multimodal_loss(msq_model* m, int32_t on, void* stream);
 
 /* Data-parallel overlap: msq_train_step records one CUDA event per REGION of the flat gradient buffer at the moment that
  * region is final (BERSON heads, BERT layers top -> bottom, embeddings, visn_fc, ViT blocks top -> bottom, ViT stem).

@@ -57,6 +57,7 @@ SIGNATURES = {
     "msq_train_set_dropout": (C.c_int, [_P, _F, _F, _F, C.c_uint32, _P]),
     "msq_train_set_bn_mode": (C.c_int, [_P, _I32, _P]),
     "msq_train_set_triplets": (C.c_int, [_P, _P, _I64, _F, _P]),
+    "msq_train_set_multimodal_loss": (C.c_int, [_P, _I32, _P]),
     "msq_train_dropout_step": (_I64, [_P]),
     "msq_train_ready_count": (_I64, [_P]),
     "msq_train_ready_info": (C.c_int, [_P, _I64, C.POINTER(_I64), C.POINTER(_I64)]),

@@ -333,6 +333,10 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
   MSQ_CUDA(cudaMemsetAsync(b.gA, 0, (size_t)Mj * H * sizeof(float), st));
   if (d_lang) MSQ_TRY(scatter_rows(d_lang, R * Lt, H, Lt, Lj, 0, b.gA, st));
   if (d_visn && mm) MSQ_TRY(scatter_rows(d_visn, R * Lv, H, Lv, Lj, Lt, b.gA, st));
+  if (ts->ml_live && mm && d_lang == ts->ht.d_lang) {   // image pairwise objective of this step: gradient of visn[:, 0]
+    MSQ_TRY(add_first_visual(ts->ht.ml_dv, R, Lt, Lj, H, b.gA, st));
+    ts->ml_live = false;
+  }
 
   for (size_t li = nb; li-- > 0;) {
     BertLayerW& L = m->bert[li];
@@ -580,6 +584,24 @@ extern "C" int msq_train_set_triplets(msq_model* m, const int32_t* triplets_dev,
   }
   MSQ_CUDA(cudaMemcpyAsync(ts->trip, triplets_dev, (size_t)B * 3 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   ts->trip_B = B; ts->trip_weight = weight;
+  return MSQ_OK;
+}
+
+/* args.multimodal_loss of the reference (modeling_bert.py:897-898, 1359-1364, 1218-1225): when on, every msq_train_step adds
+ * lam * mean_b sum_p NLL(softmax(pairwise_relationship(img_projection(visn[p, 0]))), pairwise_label_p) / P to the loss, with the
+ * gradients of img_projection.*, of the shared pairwise_relationship.* and of the first visual token of every pair row.
+ * img_projection.weight [H, H] / .bias [H] must have been registered with msq_model_set_weight BEFORE the first training call
+ * (the reference builds Linear(v_feature_size, H) and feeds it the H-d token: it only runs when v_feature_size == H). */
+extern "C" int msq_train_set_multimodal_loss(msq_model* m, int32_t on, void* stream) {
+  DevGuard dev_guard__(m);
+  MSQ_TRY(ensure_train(m, (cudaStream_t)stream));
+  TrainState* ts = m->train;
+  if (on) {
+    MSQ_REQUIRE(ts->heads && m->cfg.vit_width != 0, "msq_train_set_multimodal_loss: needs a multimodal model with BERSON heads");
+    MSQ_REQUIRE(ts->index.count("img_projection.weight") && ts->index.count("img_projection.bias"),
+                "msq_train_set_multimodal_loss: img_projection.weight / .bias were not registered before the training state was built");
+  }
+  ts->mm_loss = on != 0;
   return MSQ_OK;
 }
 

@@ -66,6 +66,8 @@ struct HeadTape {
   int N = 0;
   void *topt = nullptr, *ttb = nullptr;                       // operand type [R*Lt, H]
   float *mix, *rel6, *sents, *r0, *para, *h0, *keyin, *key, *sents_ext, *xg, *t4, *act, *c_all, *hs, *hprev, *query, *nll, *d_lang;
+  // image pairwise head (args.multimodal_loss): projected image vector, its gradient, d(logits), d(first visual token), row losses
+  float *ml_u = nullptr, *ml_du = nullptr, *ml_dz = nullptr, *ml_dv = nullptr, *ml_loss = nullptr;
   std::vector<ParaTape> pl;
 };
 
@@ -108,6 +110,9 @@ struct TrainState {
   float* trip_loss = nullptr;            // device [trip_cap]
   int64_t trip_B = 0, trip_cap = 0;
   float trip_weight = 0.f;
+  // ---- optional image pairwise objective (msq_train_set_multimodal_loss; modeling_bert.py:1218-1225, 1359-1364)
+  bool mm_loss = false;                  // every msq_train_step adds lam * NLL(pairwise_relationship(img_projection(visn[:, 0])))
+  bool ml_live = false;                  // ht.ml_dv of the step in flight is to be added to the joint-stream gradient
   // ---- dropout (msq_train_set_dropout): probabilities + seed; `step` is the counter of the forward whose masks are live
   DropCfg drop;
   uint32_t drop_next_step = 0;
@@ -289,6 +294,7 @@ template <typename T> int rn_backward_train(msq_model* m, const float* dyp, floa
 // ---- train_heads.cu
 int heads_train_setup(msq_model* m, bool alloc, cudaStream_t st);
 std::vector<std::string> heads_param_names(const msq_model* m);
+int add_first_visual(const float* dv, int64_t R, int Lt, int Lj, int H, float* gA, cudaStream_t st);
 // train_kernels.cu: elementwise dropout sites
 template <typename T> int dropout_rows(float* xf, T* xt, int64_t R, int group, int off, int n, int H, const Drop& d, cudaStream_t st);
 int dropout_add(float* s, const float* resid, int64_t n, const Drop& d, cudaStream_t st);

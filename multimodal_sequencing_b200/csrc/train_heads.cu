@@ -566,6 +566,96 @@ __global__ void triplet_loss_add_kernel(const float* __restrict__ tl, int64_t B,
   }
 }
 
+// ---- image pairwise objective (args.multimodal_loss; modeling_bert.py:1359-1364 + 1218-1225): per pair row r
+//   v = visn[r, 0] (the first visual token of the final joint stream), u = img_projection(v), z = pairwise_relationship(u),
+//   loss += lam / (P B) * NLL(softmax(z), label_r).  One block per pair row: forward, d(z), d(u), d(v).
+__global__ void __launch_bounds__(256) img_pair_kernel(const float* __restrict__ x, int Lt, int Lj, int H, const float* __restrict__ Wp,
+                                                       const float* __restrict__ bp, const float* __restrict__ w_rel, const float* __restrict__ b_rel,
+                                                       const int64_t* __restrict__ labels, float scale, float* __restrict__ u_out,
+                                                       float* __restrict__ du_out, float* __restrict__ dz_out, float* __restrict__ dv_out,
+                                                       float* __restrict__ loss_rows) {
+  pdl_sync();
+  __shared__ float v[1024], u[1024], du[1024];
+  __shared__ float z[2], dz[2];
+  const int64_t r = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* vr = x + (r * Lj + Lt) * (int64_t)H;
+  for (int d = threadIdx.x; d < H; d += blockDim.x) v[d] = vr[d];
+  __syncthreads();
+  for (int i = warp; i < H; i += nw) {
+    const float* w = Wp + (int64_t)i * H;
+    float a = 0.f;
+    for (int d = lane; d < H; d += 32) a = fmaf(w[d], v[d], a);
+    a = warp_sum(a);
+    if (lane == 0) u[i] = a + bp[i];
+  }
+  __syncthreads();
+  if (warp < 2) {
+    float a = 0.f;
+    for (int d = lane; d < H; d += 32) a = fmaf(w_rel[warp * H + d], u[d], a);
+    a = warp_sum(a);
+    if (lane == 0) z[warp] = a + b_rel[warp];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float mx = fmaxf(z[0], z[1]), e0 = expf(z[0] - mx), e1 = expf(z[1] - mx), lse = mx + logf(e0 + e1);
+    const int lab = (int)labels[r];
+    loss_rows[r] = lse - z[lab];
+    dz[0] = scale * (e0 / (e0 + e1) - (lab == 0 ? 1.f : 0.f));
+    dz[1] = scale * (e1 / (e0 + e1) - (lab == 1 ? 1.f : 0.f));
+    dz_out[r * 2] = dz[0]; dz_out[r * 2 + 1] = dz[1];
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < H; d += blockDim.x) {
+    const float g = dz[0] * w_rel[d] + dz[1] * w_rel[H + d];
+    du[d] = g;
+    u_out[r * H + d] = u[d];
+    du_out[r * H + d] = g;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < H; k += blockDim.x) {   // dv = W^T du: consecutive threads read consecutive columns of a row
+    float a = 0.f;
+    for (int i = 0; i < H; ++i) a = fmaf(du[i], Wp[(int64_t)i * H + k], a);
+    dv_out[r * H + k] = a;
+  }
+}
+// dW[i, k] += sum_r du[r, i] v[r, k] (v = x[r, Lt, :]);  db[i] += sum_r du[r, i]   (thread per (i, k), ordered over r)
+__global__ void __launch_bounds__(256) img_proj_wgrad_kernel(const float* __restrict__ du, const float* __restrict__ x, int64_t R, int Lt, int Lj, int H,
+                                                             float* __restrict__ dW, float* __restrict__ db) {
+  pdl_sync();
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)H * H) return;
+  const int i = (int)(idx / H), k = (int)(idx % H);
+  float s = 0.f, sb = 0.f;
+  for (int64_t r = 0; r < R; ++r) {
+    const float g = du[r * H + i];
+    s = fmaf(g, x[(r * Lj + Lt) * (int64_t)H + k], s);
+    sb += g;
+  }
+  dW[idx] += s;
+  if (k == 0) db[i] += sb;
+}
+__global__ void rows_loss_add_kernel(const float* __restrict__ rows, int64_t n, float w, float* __restrict__ loss) {
+  pdl_sync();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float s = 0.f;
+    for (int64_t i = 0; i < n; ++i) s += rows[i];
+    *loss += w * s;
+  }
+}
+// d(joint stream)[r, Lt, :] += dv[r, :]   (backward_train, after the text rows were scattered)
+__global__ void __launch_bounds__(256) add_first_visual_kernel(const float* __restrict__ dv, int64_t R, int Lt, int Lj, int H, float* __restrict__ gA) {
+  pdl_sync();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * H) return;
+  gA[((i / H) * Lj + Lt) * (int64_t)H + i % H] += dv[i];
+}
+int add_first_visual(const float* dv, int64_t R, int Lt, int Lj, int H, float* gA, cudaStream_t st) {
+  MSQ_CUDA(launch_k(add_first_visual_kernel, dim3(ceil_div(R * (int64_t)H, 256)), dim3(256), 0, st, dv, R, Lt, Lj, H, gA));
+  MSQ_LAUNCH_CHECK();
+  return MSQ_OK;
+}
+
 // loss = mean_b nll_b / (N - 1) + lam * mean_b sum_p NLL(softmax(rel6[p, 0:2]), label_p) / P   (1140-1174)
 __global__ void __launch_bounds__(256) train_loss_kernel(const float* __restrict__ nll, const float* __restrict__ rel6, const int64_t* __restrict__ labels,
                                                          int64_t B, int N, float lam, float* __restrict__ out) {
@@ -653,6 +743,10 @@ std::vector<std::string> heads_param_names(const msq_model* m) {
                         "query_linear.bias", "tanh_linear.weight", "tanh_linear.bias", "decoder.weight_ih_l0", "decoder.weight_hh_l0",
                         "decoder.bias_ih_l0", "decoder.bias_hh_l0", "pw_k.weight"})
     v.push_back(e);
+  if (m->raw.count("img_projection.weight") && m->raw.count("img_projection.bias")) {   // args.multimodal_loss (modeling_bert.py:897-898)
+    v.push_back("img_projection.weight");
+    v.push_back("img_projection.bias");
+  }
   return v;
 }
 
@@ -706,6 +800,10 @@ int heads_train(msq_model* m, const int64_t* sep, int64_t B, int N, const int32_
     h.query = p.take<float>((size_t)M * H);        // [b][t]
     h.nll = p.take<float>((size_t)B);
     h.d_lang = p.take<float>((size_t)Mt * H);
+    if (ts->mm_loss) {
+      h.ml_u = p.take<float>((size_t)R * H); h.ml_du = p.take<float>((size_t)R * H); h.ml_dv = p.take<float>((size_t)R * H);
+      h.ml_dz = p.take<float>((size_t)R * 2); h.ml_loss = p.take<float>((size_t)R);
+    }
     if (pass == 0) MSQ_TRY(ts->htape.reserve(p.need + 4096, st));
   }
   // ---- transient buffers (forward + backward)
@@ -935,6 +1033,30 @@ int heads_train(msq_model* m, const int64_t* sep, int64_t B, int N, const int32_
   MSQ_TRY(wgrad<T>(m, (const T*)dpre, H, H, (const T*)h.topt, H, H, ACT_NONE, Mt, G("two_level_encoder.sentence_tran.weight"),
                    G("two_level_encoder.sentence_tran.bias"), bb, st));
   MSQ_TRY((dgrad<T, float>(m, (const T*)dpre, H, ts->sentT, H, h.d_lang, h.d_lang, Mt, st)));
+  ts->ml_live = false;
+  if (ts->mm_loss) {   // image pairwise objective: shares pairwise_relationship with the text head, adds into the same slots
+    MSQ_REQUIRE(ts->mm, "multimodal_loss: the model has no visual stream");
+    auto wp = m->raw.find("img_projection.weight");
+    auto bp = m->raw.find("img_projection.bias");
+    MSQ_REQUIRE(wp != m->raw.end() && bp != m->raw.end(), "multimodal_loss: img_projection.weight / .bias are not registered");
+    MSQ_REQUIRE(wp->second.second == (int64_t)H * H && bp->second.second == H,
+                "multimodal_loss: img_projection must map the %d-d visual token to %d features (the reference multiplies a [*, %d] matrix by it)", H, H, H);
+    float *dWp = G("img_projection.weight"), *dbp = G("img_projection.bias");
+    if (err) return err;
+    MSQ_CUDA(launch_k(img_pair_kernel, dim3((unsigned)R), dim3(256), 0, st, x, Lt, Lj, H, wp->second.first, bp->second.first, m->w_rel, m->b_rel,
+                      pair_labels, lam_scale, h.ml_u, h.ml_du, h.ml_dz, h.ml_dv, h.ml_loss));
+    MSQ_LAUNCH_CHECK();
+    MSQ_CUDA(launch_k(img_proj_wgrad_kernel, dim3(ceil_div((int64_t)H * H, 256)), dim3(256), 0, st, (const float*)h.ml_du, x, R, Lt, Lj, H, dWp, dbp));
+    MSQ_LAUNCH_CHECK();
+    MSQ_CUDA(launch_k(rel_wgrad_kernel, dim3(ceil_div(2 * H, 256)), dim3(256), 0, st, (const float*)h.ml_dz, (const float*)h.ml_u, R, 1, H,
+                      G("two_level_encoder.pairwise_relationship.weight"), G("two_level_encoder.pairwise_relationship.bias")));
+    MSQ_LAUNCH_CHECK();
+    if (loss_out) {
+      MSQ_CUDA(launch_k(rows_loss_add_kernel, dim3(1), dim3(32), 0, st, (const float*)h.ml_loss, R, lam_scale, loss_out));
+      MSQ_LAUNCH_CHECK();
+    }
+    ts->ml_live = true;
+  }
   return err;
 }
 template int heads_train<float>(msq_model*, const int64_t*, int64_t, int, const int32_t*, const int64_t*, float, float*, float*, cudaStream_t);

@@ -280,8 +280,11 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
         self.decoder = nn.LSTM(H, H, batch_first=True)
         self.two_level_encoder = HierarchicalAttention(config, args=args)
         self.pairwise_loss_lam = args.pairwise_loss_lam
-        if getattr(args, "multimodal_loss", False):
-            raise NotImplementedError("multimodal_loss objective is outside the scoped path (SURVEY §2 row 18)")
+        # optional image pairwise objective (modeling_bert.py:897-898): Linear(v_feature_size, H) applied to the H-d first visual
+        # token, i.e. the reference only runs it when v_feature_size == H (train.py:2022 hard-wires 1024 = RoBERTa-large)
+        self.multimodal_loss = bool(getattr(args, "multimodal_loss", False))
+        if self.multimodal_loss:
+            self.img_projection = nn.Linear(config.v_feature_size, H)
         self.pw_k = nn.Linear((H + 2) * 4, H, False)
         # "other losses" (modeling_bert.py:904-911): the optional time-contrastive objective
         self.time_contrastive = "time_contrastive" in (getattr(args, "additional_wrapper_level_objectives", None) or ())
@@ -333,6 +336,9 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
         if _pair_batch is not None:
             return _pair_batch
         B, P, Lt = input_ids.shape
+        if passage_length.numel() > 1 and bool((passage_length != passage_length.reshape(-1)[0]).any()):
+            raise ValueError("manuals with different step counts in one batch are not supported by the B200 path "
+                             "(the reference's data loaders batch manuals of one length): %s" % passage_length.tolist())
         img = idx = None
         if images is not None:
             img = images.reshape(B * P * 2, *images.shape[3:])
@@ -351,6 +357,12 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
         if self.__dict__.get("_drop_key") != key:
             eng.set_dropout(*probs, seed=torch.initial_seed() & 0xFFFFFFFF)
             self.__dict__["_drop_key"] = key
+        if self.multimodal_loss and self.__dict__.get("_ml_key") != id(eng):
+            if self.img_projection.in_features != self.hidden_size:
+                raise RuntimeError("multimodal_loss: img_projection expects %d features but the visual token has %d (the reference "
+                                   "fails on the same shapes)" % (self.img_projection.in_features, self.hidden_size))
+            eng.set_multimodal_loss(True)
+            self.__dict__["_ml_key"] = id(eng)
 
     def _pull_bn_buffers(self, eng, count=True):
         """ModifiedResNet tower: a training forward moved the library's running_mean / running_var (nn.BatchNorm2d.train()
@@ -451,7 +463,23 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
                 ar = torch.arange(sents.shape[0], device=sents.device)
                 a, p, n = (sents[ar, trip[:, i]] for i in range(3))
                 loss = loss + 0.1 * torch.nn.functional.triplet_margin_loss(a, p, n, margin=1.0, p=2)
+            if self.multimodal_loss:    # evaluation: the image pairwise term (1218-1225) on the [R, 2] logits
+                _, score_img = self._image_pair_scores(pb)
+                nll = -torch.log_softmax(score_img, -1).gather(1, pb.pairwise_labels.reshape(-1, 1).to(score_img.device))
+                B, P = pb.input_ids.shape[:2]
+                loss = loss + self.pairwise_loss_lam * (nll.reshape(B, P).sum(-1) / (P + 1e-20)).sum() / B
             return (loss,)
+
+    def _image_pair_scores(self, pb):
+        """modeling_bert.py:1295-1297, 1359-1362: the visual half of the inner model's output and
+        pairwise_relationship(img_projection(visn[:, 0])).  Evaluation-only helper (a second pass through the inner model)."""
+        eng = self.engine()
+        B, P, Lt = pb.input_ids.shape
+        _, visn, _ = eng.inner_forward(pb.input_ids.reshape(B * P, Lt), pb.token_type_ids.reshape(B * P, Lt),
+                                       pb.attention_mask.reshape(B * P, Lt), pb.images, pb.img_index.reshape(-1))
+        u = eng.linear(visn[:, 0].contiguous(), self.img_projection.weight, self.img_projection.bias)
+        rel = self.two_level_encoder.pairwise_relationship
+        return visn, eng.linear(u, rel.weight, rel.bias)
 
     # ---- encode ------------------------------------------------------------------------------
     def encode(self, input_ids, attention_mask=None, token_type_ids=None, pairs_list=None, passage_length=None,
@@ -471,9 +499,12 @@ class BertForOrdering(nn.Module, _EngineOwner, _Pretrained):
                            ground_truth, N, img, idx)
         with torch.no_grad():
             e = self.engine().encode(pb)
+            sents, cls_score = e["sents"], e["cls_score"]
+            if self.multimodal_loss:   # 1359-1364: (sentence vectors, visual tokens) and (text, image) pair logits
+                visn, score_img = self._image_pair_scores(pb)
+                sents, cls_score = (sents, visn), (cls_score, score_img)
         hcn = (e["h0"].unsqueeze(0), e["c0"].unsqueeze(0))
-        return (e["sents"], e["para"], hcn, e["key"], e["cls"], e["cls_mat"], e["cls_score"], e["score_mat"], e["his1"],
-                e["his2"])
+        return (sents, e["para"], hcn, e["key"], e["cls"], e["cls_mat"], cls_score, e["score_mat"], e["his1"], e["his2"])
 
     # ---- one decode step ---------------------------------------------------------------------
     def step(self, prev_y, prev_handc, original_keys, mask, rela_vec, rela_mask, hist_left1, hist_left2, l1_mask, l2_mask):
@@ -497,6 +528,8 @@ def beam_search_pointer(args, model, input_ids, attention_mask=None, token_type_
     (sents, _, hcn, key, _, cls_mat, _, score_mat, _, _) = model.encode(
         input_ids, attention_mask, token_type_ids, pairs_list, passage_length, pairs_num, sep_positions, ground_truth,
         mask_cls, pairwise_labels, cuda, head_mask, images=images, _pair_batch=_pair_batch)
+    if isinstance(sents, tuple):   # args.multimodal_loss (1432-1433)
+        sents, _ = sents
     N = int(passage_length[0])
     enc = dict(sents=sents, key=key, h0=hcn[0], cls_mat=cls_mat, score_mat=score_mat)
     perm = model.engine().beam_search(enc, N, args.beam_size).cpu().tolist()

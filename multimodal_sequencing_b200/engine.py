@@ -375,6 +375,13 @@ class OrderingEngine:
             _lib.check(self.lib.msq_train_set_dropout(self._h, float(p_hidden), float(p_attn), float(p_para), int(seed) & 0xFFFFFFFF,
                                                       self._stream()))
 
+    def set_multimodal_loss(self, on=True):
+        """args.multimodal_loss of the reference (modeling_bert.py:1218-1225): every later train_step adds the image pairwise term
+        lam * NLL(pairwise_relationship(img_projection(visn[:, 0]))).  The state dict must carry img_projection.weight [H, H]
+        and .bias [H]."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.msq_train_set_multimodal_loss(self._h, 1 if on else 0, self._stream()))
+
     def set_bn_mode(self, use_running_stats=False):
         """BatchNorm of the ModifiedResNet tower inside training steps: batch statistics (False, nn.BatchNorm2d.train(), what the
         reference fine-tunes with) or the frozen running statistics (True, eval() semantics)."""

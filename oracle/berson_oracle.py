@@ -495,10 +495,12 @@ def time_contrastive_triplets(target, rng=None):
     return torch.tensor(out, dtype=torch.long)
 
 
-def training_loss(sd, cfg, inp, lam=0.6, triplets=None):
+def training_loss(sd, cfg, inp, lam=0.6, triplets=None, multimodal_loss=False):
     """modeling_bert.py:943-1174 (pointer NLL + lam * pairwise NLL), plus the optional time-contrastive term (1176-1216:
     0.1 * TripletMarginLoss(margin 1, p 2) over the sentence vectors picked by `triplets` [B, 3], see
-    time_contrastive_triplets).  All manuals in the batch have N steps (tgt_len == num)."""
+    time_contrastive_triplets) and the optional image pairwise term (args.multimodal_loss: 1359-1364 img_projection of the first
+    visual token -> the SAME pairwise_relationship head, 1218-1225 its NLL / P averaged over the batch, times lam).
+    All manuals in the batch have N steps (tgt_len == num)."""
     enc = encode(sd, cfg, inp)
     target = inp["ground_truth"]
     B, N = target.shape
@@ -542,6 +544,11 @@ def training_loss(sd, cfg, inp, lam=0.6, triplets=None):
     if triplets is not None:
         a, p, n = (sents[ar, triplets[:, i]] for i in range(3))
         loss = loss + 0.1 * F.triplet_margin_loss(a, p, n, margin=1.0, p=2)
+    if multimodal_loss:
+        score_img = _lin(sd, "two_level_encoder.pairwise_relationship", _lin(sd, "img_projection", enc["visn"][:, 0]))
+        lpi = torch.log_softmax(score_img, -1)
+        pair_img = (-lpi[torch.arange(lpi.shape[0]), pl]).reshape(B, -1)
+        loss = loss + lam * (pair_img.sum(-1) / (inp["pairs_num"].float() + 1e-20)).sum() / B
     return loss
 
 

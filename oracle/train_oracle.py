@@ -56,14 +56,14 @@ def inner_grads(sd, cfg, ids, tt, mask, images, g_lang, g_visn=None, pre="bert."
     return lang.detach(), (None if visn is None else visn.detach()), _padding_idx_rows(grads, pre, images is not None)
 
 
-def loss_grads(sd, cfg, inp, lam=0.6, dropout=None, triplets=None):
+def loss_grads(sd, cfg, inp, lam=0.6, dropout=None, triplets=None, multimodal_loss=False):
     """(loss, {name: grad}) of BertForOrdering._forward's default objective (modeling_bert.py:943-1174).
     dropout: None (p = 0) or an oracle.dropout.DropSpec -- the training-mode forward with those masks."""
     leaf = _leaf_sd(sd)
     O.DROPOUT = dropout
     try:
         with torch.enable_grad():
-            loss = O.training_loss(leaf, cfg, inp, lam, triplets=triplets)
+            loss = O.training_loss(leaf, cfg, inp, lam, triplets=triplets, multimodal_loss=multimodal_loss)
             loss.backward()
     finally:
         O.DROPOUT = None

@@ -153,7 +153,7 @@ def build_text_model(ns, cfg_kwargs, args, seed=0):
     return m.eval()
 
 
-def build_multimodal_model(ns, cfg_kwargs, args, vit_cfg=None, seed=0, rn_cfg=None):
+def build_multimodal_model(ns, cfg_kwargs, args, vit_cfg=None, seed=0, rn_cfg=None, v_feature_size=1024):
     """BertForOrdering around LXRTModel + CLIP tower (train.py:1869-1880, 2024-2028).  vit_cfg -> ViT-B/32-shaped tower
     with skip_last_layer=True; rn_cfg -> the "RN50" ModifiedResNet branch exactly as wired (skip_last_layer=False,
     visual_feat_dim = 2*embed_dim), BatchNorm statistics randomised so eval-mode BN is not the identity."""
@@ -170,7 +170,7 @@ def build_multimodal_model(ns, cfg_kwargs, args, vit_cfg=None, seed=0, rn_cfg=No
     ns.param.VISUAL_CONFIG.clip_model_name = name
     cfg = ns.BersonBertConfig(**cfg_kwargs)
     cfg.wrapper_model_with_heatmap = False
-    cfg.v_feature_size = 1024
+    cfg.v_feature_size = v_feature_size   # train.py:2022 hard-wires 1024 (= RoBERTa-large's hidden size)
     lx = dict(cfg_kwargs)
     lx.pop("layer_norm_eps", None)
     lxcfg = ns.lxrt.BertConfig(**lx)  # lxrt has its own BertConfig class (lxrt/modeling.py:147)

@@ -35,13 +35,16 @@ def _args(N, W, ff, device="cpu", mm=False):
                                  multimodal_img_part=False, per_seq_max_length=64, max_story_length=N)
 
 
-def _build(g, N, W, device="cpu"):
+def _build(g, N, W, device="cpu", multimodal_loss=False):
     c = g["cfg"]
     cfg = BertConfig(c["vocab_size_or_config_json_file"], hidden_size=c["hidden_size"], num_hidden_layers=c["num_hidden_layers"],
                      num_attention_heads=c["num_attention_heads"], intermediate_size=c["intermediate_size"],
                      max_position_embeddings=c["max_position_embeddings"])
     mm = g.get("vit") is not None or g.get("rn") is not None
     args = _args(N, W, g["ff_size"], device, mm)
+    if multimodal_loss:
+        args.multimodal_loss = True
+        cfg.v_feature_size = c["hidden_size"]   # train.py:2022 hard-wires 1024 (= RoBERTa-large's H); the tiny model's H here
     if mm:
         inner = LXRTModel(LxrtBertConfig(c["vocab_size_or_config_json_file"], hidden_size=c["hidden_size"],
                                          num_hidden_layers=c["num_hidden_layers"], num_attention_heads=c["num_attention_heads"],
@@ -693,3 +696,58 @@ def test_bert_for_ordering_with_huggingface_inner_model():
     # and the module-level call sites of the reference: encode() / berson_pointer_network
     one = {"input_ids": ids[:1], "attention_mask": torch.ones_like(ids[:1]), "labels": labels[:1]}
     assert berson_pointer_network(args, model, Tok(), dict(one)) == perms[0]
+
+
+@pytest.mark.gpu
+def test_multimodal_loss_objective_through_the_module(golden_dir):
+    """args.multimodal_loss (modeling_bert.py:897-898, 1218-1225, 1359-1364) on the drop-in module: img_projection exists under the
+    reference's name, the training forward returns the loss with the image pairwise term and hands its gradients to p.grad
+    (checked against autograd through the oracle, itself pinned live to the reference), the eval-mode loss agrees, encode()
+    returns the reference's (sentences, visual tokens) / (text, image) score tuples and decoding is unchanged."""
+    from oracle import train_oracle as TO
+    g = torch.load(os.path.join(golden_dir, "mm_tiny.pt"), weights_only=False)
+    N = 4
+    ids, labels, images = O.synthetic_manuals(2, N, 12, vocab=1000, image_px=224, seed=57)
+    model, args = _build(g, N, 4, "cuda", multimodal_loss=True)
+    assert isinstance(model.img_projection, torch.nn.Linear) and "img_projection.weight" in model.state_dict()
+    model.config.hidden_dropout_prob = model.config.attention_probs_dropout_prob = 0.0
+    model.bert.config.hidden_dropout_prob = model.bert.config.attention_probs_dropout_prob = 0.0
+    args.para_dropout = 0.0
+    model.load_state_dict(g["sd"], strict=False)
+    model = model.cuda().train()
+    for mod in model.modules():
+        mod.precise = True
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    ocfg = dict(num_hidden_layers=g["cfg"]["num_hidden_layers"], num_attention_heads=g["cfg"]["num_attention_heads"], vit=g["vit"])
+    inp = O.prepare_inputs(ids, labels, N, images)
+    oloss, ref = TO.loss_grads(sd, ocfg, inp, multimodal_loss=True)
+    o0, _ = TO.loss_grads(sd, ocfg, inp)
+    inputs = {"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": labels, "images": images}
+    with torch.enable_grad():
+        loss = model(inputs)[0]
+        loss.backward()
+    assert abs(loss.item() - oloss) < 5e-5 and oloss - o0 > 1e-2, (loss.item(), oloss, o0)
+    for n in ("img_projection.weight", "img_projection.bias", "two_level_encoder.pairwise_relationship.weight",
+              "bert.encoder.visn_fc.visn_fc.weight"):
+        got, want = dict(model.named_parameters())[n].grad.detach().cpu(), ref[n]
+        assert float((got - want).norm() / want.norm()) < 5e-4, n
+    model.eval()
+    assert abs(model(inputs)[0].item() - oloss) < 5e-5
+    cuda_inp = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    enc = model.encode(**cuda_inp)
+    (sents, visn), (score, score_img) = enc[0], enc[6]
+    oe = O.encode(sd, ocfg, inp)
+    assert visn.shape == oe["visn"].shape and (visn.cpu() - oe["visn"]).abs().max() < 1e-4
+    want_img = O._lin(sd, "two_level_encoder.pairwise_relationship", O._lin(sd, "img_projection", oe["visn"][:, 0]))
+    assert (score_img.cpu() - want_img).abs().max() < 1e-4 and (sents.cpu() - oe["sents"]).abs().max() < 1e-4
+    got = [berson_pointer_network(args, model, Tok(), {k: v[b:b + 1] for k, v in inputs.items()}) for b in range(2)]
+    assert got == O.order_manuals(sd, ocfg, ids, labels, N, 4, images)
+
+
+def test_mixed_step_counts_in_one_batch_are_refused(golden_dir):
+    """The B200 path batches manuals of ONE length (as the reference's loaders do); a mixed batch must fail loudly."""
+    g = torch.load(os.path.join(golden_dir, "text_tiny.pt"), weights_only=False)
+    model, _ = _build(g, 5, 4)
+    ids = torch.zeros(2, 20, 16, dtype=torch.long)
+    with pytest.raises(ValueError, match="different step counts"):
+        model._pair_batch(ids, ids, ids, None, torch.tensor([5, 4]), None, None, None, None, None)

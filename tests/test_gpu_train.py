@@ -348,6 +348,44 @@ def test_train_step_with_time_contrastive_objective(golden_dir, precise):
     assert abs(float(eng.train_step(pb, grads)) - o0) < (5e-5 if precise else 2e-2)
 
 
+@pytest.mark.parametrize("precise", [True, False])
+def test_train_step_with_image_pairwise_objective(golden_dir, precise):
+    """args.multimodal_loss of the reference (modeling_bert.py:897-898, 1359-1364, 1218-1225): img_projection of the first visual
+    token through the shared pairwise_relationship head.  Loss and every gradient (img_projection.*, the shared head, the whole
+    encoder below the visual token) against torch autograd through the oracle, whose term is pinned live to the reference
+    (tests/test_oracle_vs_reference.py::test_multimodal_loss_objective_live)."""
+    g = torch.load(os.path.join(golden_dir, "mm_tiny.pt"), weights_only=False)
+    H = g["cfg"]["hidden_size"]
+    gen = torch.Generator().manual_seed(123)
+    sd = dict(g["sd"])
+    sd["img_projection.weight"] = torch.randn(H, H, generator=gen) * 0.05
+    sd["img_projection.bias"] = torch.randn(H, generator=gen) * 0.05
+    eng = _engine(sd, _cfg_from_golden(g), precise)
+    eng.set_multimodal_loss(True)
+    B, N, L = 2, 4, 12
+    ids, labels, images = O.synthetic_manuals(B, N, L, vocab=1000, image_px=224, seed=57)
+    pb = eng.prepare(ids, labels, N, images)
+    inp = O.prepare_inputs(ids, labels, N, images)
+    grads = eng.new_grad_buffer()
+    loss = float(eng.train_step(pb, grads))
+    torch.cuda.synchronize()
+    oloss, ref = TO.loss_grads(sd, _ocfg(g), inp, multimodal_loss=True)
+    o0, ref0 = TO.loss_grads(sd, _ocfg(g), inp)
+    assert oloss - o0 > 1e-2, "the image term must contribute for the test to mean anything"
+    assert "img_projection.weight" in ref and float(ref["img_projection.weight"].norm()) > 0
+    assert abs(loss - oloss) < (5e-5 if precise else 2e-2), (loss, oloss)
+    got = eng.grads_by_name(grads)
+    assert "img_projection.weight" in got and "img_projection.bias" in got
+    worst = _compare(got, ref, 5e-4 if precise else 1e-1)
+    print("image pairwise objective (%s): loss %.6f (oracle %.6f, without the term %.6f), worst relative L2 %.2e at %s" %
+          ("fp32" if precise else "bf16", loss, oloss, o0, worst[1], worst[0]))
+    # switching it off restores the default objective
+    eng.set_multimodal_loss(False)
+    grads.zero_()
+    assert abs(float(eng.train_step(pb, grads)) - o0) < (5e-5 if precise else 2e-2)
+    assert float(eng.grads_by_name(grads)["img_projection.weight"].abs().max()) == 0.0
+
+
 def test_fine_tuning_lowers_the_loss(golden_dir):
     """Five optimizer steps on one batch: the loss the step reports must fall (end-to-end sign / wiring check), and the
     eval-mode loss entry point must agree with the training one before and after."""
