@@ -471,7 +471,7 @@ def run_finetune(ctx, args, steps, warmup, full=True):
     def e2e_step():
         loss_host.copy_(step(pinned.to(ctx.dev, non_blocking=True)).reshape(1), non_blocking=True)
         return loss_host
-    e2e_ms, _ = ctx.timed(e2e_step, steps, 1)
+    e2e_ms, _ = ctx.timed(e2e_step, steps, max(2, warmup // 2))
     total = B * ctx.world
     traj = [float(x) for x in losses[::max(1, len(losses) // 6)]] + [float(loss_host)]
     del eng, grads
@@ -525,7 +525,7 @@ def run_decode(ctx, args, steps, warmup, full=True):
     def e2e_step():
         d = {k: enc_pin[k].to(ctx.dev, non_blocking=True) for k in keys}
         return eng.beam_search(d, N, W).cpu()
-    e2e_ms, _ = ctx.timed(e2e_step, steps, 1)
+    e2e_ms, _ = ctx.timed(e2e_step, steps, max(2, warmup // 2))
     total = B * ctx.world
     # algorithmic bytes (base-tensor formulation) per manual and decode step, and the recurrent GEMM work
     per_step = N * N * 770 * 4 + N * 768 * 4 + W * (4 * 768 * 4 + 2 * N * 4)

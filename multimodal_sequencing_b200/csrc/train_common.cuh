@@ -232,14 +232,16 @@ static int wgrad(const msq_model* m, const T* G, int ldg, int Nout, const T* X, 
           g.C = b.part + (size_t)s * Nout * Kin;
           MSQ_TRY(gemm_tc<float>(g, b.sk->aux[s]));
           MSQ_CUDA(cudaEventRecord(b.sk->join[s], b.sk->aux[s]));
-          MSQ_CUDA(cudaStreamWaitEvent(st, b.sk->join[s], 0));
         }
+        // the bias gradient (an HBM-bound column sum of dY) runs on the main stream UNDER the tensor-bound slices
+        if (db) MSQ_TRY(colsum_accum_bf16((const bf16*)G, M, Nout, ldg, db, b.ln_scr, st));
+        for (int s = 0; s < used; ++s) MSQ_CUDA(cudaStreamWaitEvent(st, b.sk->join[s], 0));
         MSQ_TRY(splitk_accumulate(b.part, used, (int64_t)Nout * Kin, dW, st));
       } else {
         g.A = G; g.W = Xo; g.K = (int)M; g.resid = dW; g.C = dW;
         MSQ_TRY(gemm_tc<float>(g, st));
+        if (db) MSQ_TRY(colsum_accum_bf16((const bf16*)G, M, Nout, ldg, db, b.ln_scr, st));
       }
-      if (db) MSQ_TRY(colsum_accum_bf16((const bf16*)G, M, Nout, ldg, db, b.ln_scr, st));
       return MSQ_OK;
     }
   }

@@ -218,37 +218,93 @@ __device__ __forceinline__ float act_grad(float x, int act) {
     default: return 1.f;
   }
 }
+// bf16 path: derivative with one or two SFU ops per element (the same tanh fit of erf as the forward epilogues, common.cuh;
+// error ~3e-5, far below the bf16 rounding of du); the fp32 parity mode keeps erff / expf.
+__device__ __forceinline__ float act_grad_fast(float x, int act) {
+  switch (act) {
+    case ACT_GELU_ERF: {
+      const float x2 = x * x, xc = fminf(x2, 36.0f);
+      const float p = x * fmaf(xc, fmaf(xc, -3.58618502e-04f, 3.70495807e-02f), 7.97459395e-01f);
+      const float pdf = 0.39894228040143267794f * ex2_approx(-0.72134752044448170368f * x2);   // exp(-x^2 / 2) / sqrt(2 pi)
+      return fmaf(x, pdf, fmaf(0.5f, tanh_approx(p), 0.5f));
+    }
+    case ACT_QUICK_GELU: {
+      const float sg = fmaf(0.5f, tanh_approx(0.851f * x), 0.5f);
+      return sg * fmaf(1.702f * x, 1.0f - sg, 1.0f);
+    }
+    default: return act_grad(x, act);
+  }
+}
+template <typename T> struct ActVec;   // elements per thread and per memory access: 4 fp32 (16 B) / 8 bf16 (16 B)
+template <> struct ActVec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float* v) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  static __device__ __forceinline__ void store(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+  static __device__ __forceinline__ float fwd(float x, int act) { return apply_act(x, act); }
+  static __device__ __forceinline__ float grad(float x, int act) { return act_grad(x, act); }
+};
+template <> struct ActVec<bf16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const bf16* p, float* v) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      v[2 * i] = __low2float(h); v[2 * i + 1] = __high2float(h);
+    }
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float* v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  static __device__ __forceinline__ float fwd(float x, int act) { return apply_act_fast(x, act); }
+  static __device__ __forceinline__ float grad(float x, int act) { return act_grad_fast(x, act); }
+};
 template <typename T>
-__global__ void __launch_bounds__(256) act_fwd_kernel(const T* __restrict__ u, int64_t n4, int act, T* __restrict__ h) {
+__global__ void __launch_bounds__(256) act_fwd_kernel(const T* __restrict__ u, int64_t nv, int act, T* __restrict__ h) {
   pdl_sync();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 v = Vec4<T>::load(u + i * 4);
-    v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
-    Vec4<T>::store(h + i * 4, v);
+  constexpr int V = ActVec<T>::N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[V];
+    ActVec<T>::load(u + i * V, v);
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = ActVec<T>::fwd(v[k], act);
+    ActVec<T>::store(h + i * V, v);
   }
 }
 template <typename T>
-__global__ void __launch_bounds__(256) act_bwd_kernel(const T* dh, const T* __restrict__ u, int64_t n4, int act, T* du) {   // du may alias dh
+__global__ void __launch_bounds__(256) act_bwd_kernel(const T* dh, const T* __restrict__ u, int64_t nv, int act, T* du) {   // du may alias dh
   pdl_sync();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 x = Vec4<T>::load(u + i * 4);
-    float4 g = Vec4<T>::load(dh + i * 4);
-    g.x *= act_grad(x.x, act); g.y *= act_grad(x.y, act); g.z *= act_grad(x.z, act); g.w *= act_grad(x.w, act);
-    Vec4<T>::store(du + i * 4, g);
+  constexpr int V = ActVec<T>::N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+    float x[V], g[V];
+    ActVec<T>::load(u + i * V, x);
+    ActVec<T>::load(dh + i * V, g);
+#pragma unroll
+    for (int k = 0; k < V; ++k) g[k] *= ActVec<T>::grad(x[k], act);
+    ActVec<T>::store(du + i * V, g);
   }
 }
 static inline dim3 ew_grid(int64_t n4) { return dim3((unsigned)min((int64_t)148 * 16, (n4 + 255) / 256)); }
 template <typename T> int act_fwd(const T* u, int64_t n, int act, T* h, cudaStream_t st) {
-  MSQ_REQUIRE(n % 4 == 0, "act_fwd: n %% 4");
+  constexpr int V = (int)(16 / sizeof(T));
+  MSQ_REQUIRE(n % V == 0 && ((uintptr_t)u & 15) == 0 && ((uintptr_t)h & 15) == 0, "act_fwd: n %% %d / alignment", V);
   if (n == 0) return MSQ_OK;
-  MSQ_CUDA(launch_k(act_fwd_kernel<T>, ew_grid(n / 4), dim3(256), 0, st, u, n / 4, act, h));
+  MSQ_CUDA(launch_k(act_fwd_kernel<T>, ew_grid(n / V), dim3(256), 0, st, u, n / V, act, h));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
 template <typename T> int act_bwd(const T* dh, const T* u, int64_t n, int act, T* du, cudaStream_t st) {
-  MSQ_REQUIRE(n % 4 == 0, "act_bwd: n %% 4");
+  constexpr int V = (int)(16 / sizeof(T));
+  MSQ_REQUIRE(n % V == 0 && ((uintptr_t)u & 15) == 0 && ((uintptr_t)dh & 15) == 0 && ((uintptr_t)du & 15) == 0, "act_bwd: n %% %d / alignment", V);
   if (n == 0) return MSQ_OK;
-  MSQ_CUDA(launch_k(act_bwd_kernel<T>, ew_grid(n / 4), dim3(256), 0, st, dh, u, n / 4, act, du));
+  MSQ_CUDA(launch_k(act_bwd_kernel<T>, ew_grid(n / V), dim3(256), 0, st, dh, u, n / V, act, du));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
