@@ -201,7 +201,7 @@ def cpu_finetune_run(n, budget_s):
     return times, cores
 
 
-def cpu_sample(cfg_id, n, budget_s, backbone="vit"):
+def cpu_sample(cfg_id, n, budget_s, backbone="vit", warm=1):
     """-> (manuals/s, cores, description) of a bounded CPU sample of config cfg_id."""
     if cfg_id == 3:
         times, cores = cpu_finetune_run(max(2, min(n, 3)), budget_s)
@@ -209,7 +209,8 @@ def cpu_sample(cfg_id, n, budget_s, backbone="vit"):
     else:
         times, cores = cpu_order_run(cfg_id, n, budget_s, backbone)
         what = "manual(s) of the same workload, one per call (the reference's batch size)"
-    timed = times[1:] if len(times) > 1 else times
+    warm = max(0, min(warm, len(times) - 1))   # a run the time budget cut short keeps at least one timed call
+    timed = times[warm:]
     return len(timed) / sum(timed), cores, "%d %s after %d warm-up, oracle port (torch fp32) on %d host threads, one host process" % (
         len(timed), what, len(times) - len(timed), cores), len(timed), len(times) - len(timed)
 
@@ -219,7 +220,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     n = args.steps + args.warmup
-    val, cores, sample, nt, nw = cpu_sample(args.config, n, 170.0, args.backbone)
+    val, cores, sample, nt, nw = cpu_sample(args.config, n, 170.0, args.backbone, warm=args.warmup)
     if args.gpus > 1:
         sample += "; at N > 1 this arm is still ONE host process on the box's cores (the ratio is N GPUs against one host)"
     line = {"metric": METRIC[args.config], "value": val, "unit": "manuals/s", "impl": "reference",
