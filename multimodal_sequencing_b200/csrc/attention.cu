@@ -129,7 +129,8 @@ template <int KP, bool SPL, bool DROP>
 __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant__ CUtensorMap map_q,
                                                            const __grid_constant__ CUtensorMap map_kv, int L, int heads,
                                                            float scale_l2e, const float* __restrict__ mask_add, int mask_ld,
-                                                           int mask_len, bf16* __restrict__ ctx, int n_items, Drop drop) {
+                                                           int mask_len, bf16* __restrict__ ctx, int n_items, Drop drop,
+                                                           float* __restrict__ lse_out) {
   using Cfg = AttnCfg<KP, SPL>;
   constexpr int Q_BYTES = Cfg::Q_BYTES, KV_BYTES = Cfg::KV_BYTES, QT = Cfg::QT, OPER = Cfg::OPER_BYTES;
   constexpr int CH = KP / 64;  // 32-column chunks per thread: two threads share a query row, half the keys each
@@ -340,6 +341,9 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
     // ---- O = (P V) / sum : this thread stores 32 of the row's 64 output columns
     const int q = qt * 128 + trow;
     const float inv = 1.0f / sum;
+    // training forward: the row's natural-log sum of exponentials of (scale s + mask), what the backward kernels subtract
+    // (mx and the exponentials live in the log2 domain here)
+    if (lse_out != nullptr && half == 0 && q < L) lse_out[(int64_t)item * L + q] = (mx + log2f(sum)) * 0.69314718055994530942f;
     {
       uint32_t raw[32];
       tmem_ld32(lane_addr + KP / 2 + half * 32, raw);
@@ -788,7 +792,7 @@ static bool attention_use_ws() {
 
 template <int KP, bool SPL>
 static int launch_attention_tc(const bf16* qkv, int64_t R, int L, int heads, float scale, const float* mask_add, int mask_ld,
-                               int mask_len, bf16* ctx, cudaStream_t st, const Drop& drop = Drop()) {
+                               int mask_len, bf16* ctx, cudaStream_t st, const Drop& drop = Drop(), float* lse_out = nullptr) {
   CUtensorMap mq, mkv;
   const int ld = (SPL ? 2 : 1) * 3 * heads * AT_D;   // bf16 elements per qkv row
   MSQ_TRY(make_map_bf16(&mq, qkv, R * L, ld, ld, AT_D, 128));
@@ -814,8 +818,8 @@ static int launch_attention_tc(const bf16* qkv, int64_t R, int L, int heads, flo
   MSQ_REQUIRE(n_items < ((int64_t)1 << 31), "attention: too many (row, head) items");
 
   const dim3 grid((unsigned)min((int64_t)resident, n_items));
-  if (dropping) MSQ_CUDA(launch_k(attention_tc_kernel<KP, SPL, !SPL>, grid, dim3(256), SMEM, st, mq, mkv, L, heads, scale * 1.4426950408889634f, mask_add, mask_ld, mask_len, ctx, (int)n_items, drop));
-  else MSQ_CUDA(launch_k(attention_tc_kernel<KP, SPL, false>, grid, dim3(256), SMEM, st, mq, mkv, L, heads, scale * 1.4426950408889634f, mask_add, mask_ld, mask_len, ctx, (int)n_items, drop));
+  if (dropping) MSQ_CUDA(launch_k(attention_tc_kernel<KP, SPL, !SPL>, grid, dim3(256), SMEM, st, mq, mkv, L, heads, scale * 1.4426950408889634f, mask_add, mask_ld, mask_len, ctx, (int)n_items, drop, lse_out));
+  else MSQ_CUDA(launch_k(attention_tc_kernel<KP, SPL, false>, grid, dim3(256), SMEM, st, mq, mkv, L, heads, scale * 1.4426950408889634f, mask_add, mask_ld, mask_len, ctx, (int)n_items, drop, lse_out));
   MSQ_LAUNCH_CHECK();
   return MSQ_OK;
 }
@@ -828,7 +832,8 @@ static bool attention_use_tc() {
 
 template <typename T>
 int attention(const T* qkv, int64_t R, int L, int heads, int dhead, float scale, const float* key_mask_add, int mask_ld,
-              int mask_len, T* ctx, cudaStream_t st, const Drop& drop) {
+              int mask_len, T* ctx, cudaStream_t st, const Drop& drop, float* lse_out, bool* lse_written) {
+  if (lse_written) *lse_written = false;
   MSQ_REQUIRE(dhead == AT_D, "attention: head dim %d != 64", dhead);
   MSQ_REQUIRE(L >= 1 && L <= 320, "attention: sequence length %d out of range", L);
   if (R == 0) return MSQ_OK;
@@ -856,9 +861,10 @@ int attention(const T* qkv, int64_t R, int L, int heads, int dhead, float scale,
       return launch_attention_ws<256, false>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st, drop);
     }
     if (attention_use_tc() && L <= 256 && (((uintptr_t)qkv) & 15) == 0) {
+      if (lse_written) *lse_written = lse_out != nullptr;   // this kernel emits the row log-sum-exp for the backward pass
       if (L <= 128)
-        return launch_attention_tc<128, false>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st, drop);
-      return launch_attention_tc<256, false>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st, drop);
+        return launch_attention_tc<128, false>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st, drop, lse_out);
+      return launch_attention_tc<256, false>((const bf16*)qkv, R, L, heads, scale, key_mask_add, mask_ld, mask_len, (bf16*)ctx, st, drop, lse_out);
     }
   }
   const int Lpad = (L + 31) & ~31;
@@ -869,8 +875,8 @@ int attention(const T* qkv, int64_t R, int L, int heads, int dhead, float scale,
   return MSQ_OK;
   }
 }
-template int attention<bf16s>(const bf16s*, int64_t, int, int, int, float, const float*, int, int, bf16s*, cudaStream_t, const Drop&);
-template int attention<float>(const float*, int64_t, int, int, int, float, const float*, int, int, float*, cudaStream_t, const Drop&);
-template int attention<bf16>(const bf16*, int64_t, int, int, int, float, const float*, int, int, bf16*, cudaStream_t, const Drop&);
+template int attention<bf16s>(const bf16s*, int64_t, int, int, int, float, const float*, int, int, bf16s*, cudaStream_t, const Drop&, float*, bool*);
+template int attention<float>(const float*, int64_t, int, int, int, float, const float*, int, int, float*, cudaStream_t, const Drop&, float*, bool*);
+template int attention<bf16>(const bf16*, int64_t, int, int, int, float, const float*, int, int, bf16*, cudaStream_t, const Drop&, float*, bool*);
 
 }  // namespace msq

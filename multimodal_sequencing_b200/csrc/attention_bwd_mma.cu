@@ -283,6 +283,8 @@ __device__ __forceinline__ void load_two(bf16* S0, bf16* S1, const bf16* G0, int
   }
 }
 
+// LSE_IN: the forward kernel saved the row log-sum-exp (lse_out is then an INPUT): S is formed once, not twice
+template <bool LSE_IN>
 __global__ void __launch_bounds__(ABM_WARPS * 32, 2) attention_bwd_dq_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ctx,
                                                                                  const bf16* __restrict__ dctx, int L, int Lp, int heads, float scale,
                                                                                  const float* __restrict__ mask_add, int mask_ld, int mask_len,
@@ -323,6 +325,15 @@ __global__ void __launch_bounds__(ABM_WARPS * 32, 2) attention_bwd_dq_mma_kernel
         dd[1] += __shfl_xor_sync(0xffffffffu, dd[1], o);
       }
     }
+    float lse[2];
+    if constexpr (LSE_IN) {
+#pragma unroll
+      for (int hr = 0; hr < 2; ++hr) {
+        const int row = ib * 16 + gid + hr * 8;
+        lse[hr] = row < L ? lse_out[(int64_t)blockIdx.x * L + row] : INFINITY;   // rows beyond the sequence: p = 0
+        if (tig == 0 && row < L) dsum_out[(int64_t)blockIdx.x * L + row] = dd[hr];
+      }
+    } else {
     float m[2] = {-INFINITY, -INFINITY}, s[2] = {0.f, 0.f};
     for (int kb = 0; kb < nblk; ++kb) {
       float acc[2][4];
@@ -342,7 +353,6 @@ __global__ void __launch_bounds__(ABM_WARPS * 32, 2) attention_bwd_dq_mma_kernel
         }
       }
     }
-    float lse[2];
 #pragma unroll
     for (int hr = 0; hr < 2; ++hr) {
 #pragma unroll
@@ -360,6 +370,7 @@ __global__ void __launch_bounds__(ABM_WARPS * 32, 2) attention_bwd_dq_mma_kernel
         lse_out[(int64_t)blockIdx.x * L + row] = lse[hr];
         dsum_out[(int64_t)blockIdx.x * L + row] = dd[hr];
       }
+    }
     }
     float dq[8][4];
 #pragma unroll
@@ -478,7 +489,7 @@ bool attention_bwd_mma_supported(int L) {
 }
 
 int attention_bwd_mma(const bf16* qkv, const bf16* ctx, const bf16* dctx, int64_t R, int L, int heads, float scale, const float* key_mask_add,
-                      int mask_ld, int mask_len, bf16* dqkv, float* scratch, cudaStream_t st, const Drop& drop) {
+                      int mask_ld, int mask_len, bf16* dqkv, float* scratch, cudaStream_t st, const Drop& drop, const float* lse_fwd) {
   MSQ_REQUIRE(L >= 1 && L <= 256, "attention_bwd_mma: sequence length %d out of range", L);
   MSQ_REQUIRE((((uintptr_t)qkv | (uintptr_t)ctx | (uintptr_t)dctx | (uintptr_t)dqkv) & 15) == 0, "attention_bwd_mma: unaligned pointer");
   if (R == 0) return MSQ_OK;
@@ -493,13 +504,15 @@ int attention_bwd_mma(const bf16* qkv, const bf16* ctx, const bf16* dctx, int64_
     MSQ_LAUNCH_CHECK();
     return MSQ_OK;
   }
-  float* lse = scratch;
+  float* lse = lse_fwd ? const_cast<float*>(lse_fwd) : scratch;   // saved by the forward kernel, or computed by the dQ kernel
   float* dsum = scratch + (size_t)R * heads * L;
   const size_t smem_a = (size_t)2 * Lp * ABM_LD * sizeof(bf16) + (size_t)Lp * sizeof(float);
   const size_t smem_b = (size_t)2 * Lp * ABM_LD * sizeof(bf16) + (size_t)2 * Lp * sizeof(float);
-  MSQ_SMEM_ATTR(smem_a, attention_bwd_dq_mma_kernel);
+  MSQ_SMEM_ATTR(smem_a, attention_bwd_dq_mma_kernel<false>);
+  MSQ_SMEM_ATTR(smem_a, attention_bwd_dq_mma_kernel<true>);
   MSQ_SMEM_ATTR(smem_b, attention_bwd_dkv_mma_kernel);
-  MSQ_CUDA(launch_k(attention_bwd_dq_mma_kernel, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem_a, st, qkv, ctx, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, lse, dsum, drop));
+  if (lse_fwd) MSQ_CUDA(launch_k(attention_bwd_dq_mma_kernel<true>, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem_a, st, qkv, ctx, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, lse, dsum, drop));
+  else MSQ_CUDA(launch_k(attention_bwd_dq_mma_kernel<false>, dim3((unsigned)(R * heads)), dim3(ABM_WARPS * 32), smem_a, st, qkv, ctx, dctx, L, Lp, heads, scale, key_mask_add, mask_ld, mask_len, dqkv, lse, dsum, drop));
   MSQ_LAUNCH_CHECK();
   // dK / dV: the tcgen05 pipeline (attention_bwd_tc.cu) when available, else the mma.sync kernel (MSQ_ATTN_BWD_TC=0)
   if (attention_bwd_dkv_tc_supported(L))

@@ -105,7 +105,9 @@ int gemm_ln(const bf16* A, int lda, const bf16* W, int ldw, const float* bias, c
 // drop: training-mode dropout of the probabilities (site A; element index ((r*heads + h)*L + q)*L + k); default = off
 template <typename T>
 int attention(const T* qkv, int64_t R, int L, int heads, int dhead, float scale, const float* key_mask_add, int mask_ld,
-              int mask_len, T* ctx, cudaStream_t st, const Drop& drop = Drop());
+              int mask_len, T* ctx, cudaStream_t st, const Drop& drop = Drop(), float* lse_out = nullptr, bool* lse_written = nullptr);
+// lse_out [R*heads, L] (optional, training forward): the row log-sum-exp of (scale q.k + mask); *lse_written says whether the
+// kernel that ran emits it (the tcgen05 bf16 kernel does; otherwise the backward pass recomputes it)
 
 // ---- pooling.cu
 template <typename T>
@@ -192,7 +194,8 @@ int attention_bwd(const T* qkv, const T* dctx, int64_t R, int L, int heads, floa
 // attention_bwd_mma.cu: bf16 tensor-core (mma.sync) version; ctx = the forward's output (for D_i = dO_i . O_i)
 bool attention_bwd_mma_supported(int L);
 int attention_bwd_mma(const bf16* qkv, const bf16* ctx, const bf16* dctx, int64_t R, int L, int heads, float scale, const float* key_mask_add,
-                      int mask_ld, int mask_len, bf16* dqkv, float* scratch, cudaStream_t st, const Drop& drop = Drop());   // scratch: attention_bwd_scratch_floats
+                      int mask_ld, int mask_len, bf16* dqkv, float* scratch, cudaStream_t st, const Drop& drop = Drop(),
+                      const float* lse_fwd = nullptr);   // scratch: attention_bwd_scratch_floats; lse_fwd: the forward's row log-sum-exp [R*heads, L] or null
 // attention_bwd_tc.cu: dK / dV on tcgen05 (lse / dsum: per-query vectors [R*heads, L] written by the dQ kernel)
 bool attention_bwd_dkv_tc_supported(int L);
 int attention_bwd_dkv_tc(const bf16* qkv, const bf16* dctx, int64_t R, int L, int heads, float scale, const float* mask_add, int mask_ld,

@@ -175,6 +175,7 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
         v.x = p.take<float>((size_t)Mv * Wd); v.y1 = p.take<T>((size_t)Mv * Wd); v.qkv = p.take<T>((size_t)Mv * 3 * Wd);
         v.ctx = p.take<T>((size_t)Mv * Wd); v.x1 = p.take<float>((size_t)Mv * Wd); v.y2 = p.take<T>((size_t)Mv * Wd);
         v.u = p.take<T>((size_t)Mv * 4 * Wd); v.hb = p.take<T>((size_t)Mv * 4 * Wd);
+        v.lse = p.take<float>((size_t)R * (Wd / 64) * Lv); v.have_lse = false;
       }
       ts->vx_last = p.take<float>((size_t)Mv * Wd);
       ts->y_post = p.take<T>((size_t)Mv * Wd);
@@ -184,6 +185,7 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
       b.x = p.take<T>((size_t)Mj * H); b.qkv = p.take<T>((size_t)Mj * 3 * H); b.ctx = p.take<T>((size_t)Mj * H);
       b.s1 = p.take<float>((size_t)Mj * H); b.x1 = p.take<T>((size_t)Mj * H); b.u = p.take<T>((size_t)Mj * I);
       b.s2 = p.take<float>((size_t)Mj * H); b.hb = p.take<T>((size_t)Mj * I);
+      b.lse = p.take<float>((size_t)R * c.heads * Lj); b.have_lse = false;
     }
     ts->x_last = p.take<T>((size_t)Mj * H);
     ts->x_out = p.take<float>((size_t)Mj * H);
@@ -232,7 +234,7 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
       float* xn = l + 1 < nvl ? ts->vt[l + 1].x : ts->vx_last;
       MSQ_TRY(layernorm<T>(t.x, Mv, Wd, L.ln1.g, L.ln1.b, 1e-5f, nullptr, (T*)t.y1, 0, 0, 0, st));
       MSQ_TRY((gemm_nt<T, T>(m, (const T*)t.y1, Wd, wptr<T>(L.qkv), L.qkv.ld, L.qkv.b, nullptr, 0, (T*)t.qkv, 3 * Wd, Mv, 3 * Wd, Wd, ACT_NONE, st)));
-      MSQ_TRY(attention<T>((const T*)t.qkv, R, Lv, heads, 64, 0.125f, nullptr, 0, 0, (T*)t.ctx, st));
+      MSQ_TRY(attention<T>((const T*)t.qkv, R, Lv, heads, 64, 0.125f, nullptr, 0, 0, (T*)t.ctx, st, Drop(), t.lse, &t.have_lse));
       MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.ctx, Wd, wptr<T>(L.out), L.out.ld, L.out.b, t.x, Wd, t.x1, Wd, Mv, Wd, Wd, ACT_NONE, st)));
       MSQ_TRY(layernorm<T>(t.x1, Mv, Wd, L.ln2.g, L.ln2.b, 1e-5f, nullptr, (T*)t.y2, 0, 0, 0, st));
       MSQ_TRY((gemm_nt<T, T>(m, (const T*)t.y2, Wd, wptr<T>(L.fc), L.fc.ld, L.fc.b, nullptr, 0, (T*)t.u, 4 * Wd, Mv, 4 * Wd, Wd, ACT_NONE, st)));
@@ -252,7 +254,7 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
     T* xn = l + 1 < nb ? (T*)ts->bt[l + 1].x : (T*)ts->x_last;
     MSQ_TRY((gemm_nt<T, T>(m, (const T*)t.x, H, wptr<T>(L.qkv), L.qkv.ld, L.qkv.b, nullptr, 0, (T*)t.qkv, 3 * H, Mj, 3 * H, H, ACT_NONE, st)));
     MSQ_TRY(attention<T>((const T*)t.qkv, R, Lj, c.heads, 64, 0.125f, ts->mask_add, Lt, Lt, (T*)t.ctx, st,
-                         make_drop(dc, DROP_A, (int)l, dc.p_attn)));
+                         make_drop(dc, DROP_A, (int)l, dc.p_attn), t.lse, &t.have_lse));
     if (drop_h && gemm_nt_on_tc<T>(m, H, L.out.ld, H, H, H)) {   // s1 = dropout(dense(ctx) + b) + x, dropout inside the GEMM epilogue
       MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.ctx, H, wptr<T>(L.out), L.out.ld, L.out.b, xf, H, t.s1, H, Mj, H, H, ACT_NONE, st,
                                  make_drop(dc, DROP_O, (int)l, dc.p_hidden))));
@@ -366,7 +368,7 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
     MSQ_TRY(wgrad<T>(m, (const T*)b.gT, H, H, (const T*)t.ctx, H, H, ACT_NONE, Mj, dWo, dbo, b, st));
     MSQ_TRY((dgrad<T, T>(m, (const T*)b.gT, H, WT[1], H, nullptr, (T*)b.gC, Mj, st)));
     MSQ_TRY(attn_bwd<T>((const T*)t.qkv, (const T*)t.ctx, (const T*)b.gC, R, Lj, c.heads, ts->mask_add, Lt, (T*)b.gQ, b.at_scr, st,
-                        make_drop(dc, DROP_A, (int)li, dc.p_attn)));
+                        make_drop(dc, DROP_A, (int)li, dc.p_attn), t.have_lse ? t.lse : nullptr));
     MSQ_TRY(wgrad<T>(m, (const T*)b.gQ, 3 * H, 3 * H, (const T*)t.x, H, H, ACT_NONE, Mj, dWqkv, dbqkv, b, st));
     MSQ_TRY((dgrad<T, float>(m, (const T*)b.gQ, 3 * H, WT[0], H, b.gB, b.gA, Mj, st)));        // dX0 = dqkv Wqkv + ds1
     MSQ_TRY(mark_ready(ts, bn + "attention.self.query.weight", bn + "output.LayerNorm.bias", st));
@@ -422,7 +424,8 @@ static int backward_train(msq_model* m, const float* d_lang, const float* d_visn
     MSQ_TRY(ln_bwd<T>(b.gA, t.x1, b.gB, Mv, Wd, L.ln2.g, 1e-5f, b.gB, (T*)b.gT, dg2, db2, b.ln_scr, 0, 0, 0, st));   // dx1 = dx + LN'
     MSQ_TRY(wgrad<T>(m, (const T*)b.gT, Wd, Wd, (const T*)t.ctx, Wd, Wd, ACT_NONE, Mv, dWo, dbo, b, st));
     MSQ_TRY((dgrad<T, T>(m, (const T*)b.gT, Wd, WT[1], Wd, nullptr, (T*)b.gC, Mv, st)));
-    MSQ_TRY(attn_bwd<T>((const T*)t.qkv, (const T*)t.ctx, (const T*)b.gC, R, Lv, vheads, nullptr, 0, (T*)b.gQ, b.at_scr, st));
+    MSQ_TRY(attn_bwd<T>((const T*)t.qkv, (const T*)t.ctx, (const T*)b.gC, R, Lv, vheads, nullptr, 0, (T*)b.gQ, b.at_scr, st, Drop(),
+                        t.have_lse ? t.lse : nullptr));
     MSQ_TRY(wgrad<T>(m, (const T*)b.gQ, 3 * Wd, 3 * Wd, (const T*)t.y1, Wd, Wd, ACT_NONE, Mv, dWqkv, dbqkv, b, st));
     MSQ_TRY((dgrad<T, float>(m, (const T*)b.gQ, 3 * Wd, WT[0], Wd, nullptr, b.gA, Mv, st)));      // d(ln_1 out)
     MSQ_TRY(ln_bwd<T>(b.gA, t.x, b.gB, Mv, Wd, L.ln1.g, 1e-5f, b.gB, (T*)b.gT, dg1, db1, b.ln_scr, 0, 0, 0, st));    // dx = dx1 + LN'

@@ -9,8 +9,8 @@
 namespace msq {
 
 struct ParamSlot { std::string name; int64_t off = 0, numel = 0; float* master = nullptr; bool decay = true; };
-struct BertTape { void *x, *qkv, *ctx, *x1, *u, *hb; float *s1, *s2; };   // hb = act(u): operand of the down-projection wgrad
-struct VitTape { float *x, *x1; void *y1, *qkv, *ctx, *y2, *u, *hb; };
+struct BertTape { void *x, *qkv, *ctx, *x1, *u, *hb; float *s1, *s2; float* lse; bool have_lse; };   // lse: attention row log-sum-exp [R*heads, L] saved by the forward kernel   // hb = act(u): operand of the down-projection wgrad
+struct VitTape { float *x, *x1; void *y1, *qkv, *ctx, *y2, *u, *hb; float* lse; bool have_lse; };
 
 // Split-K of the weight-gradient GEMMs: dW is only 9-72 output tiles (a fraction of the 148 SMs) against a contraction
 // of tens of thousands of rows, so the contraction is cut into S slices that run CONCURRENTLY as S launches of the same
@@ -278,9 +278,13 @@ static int dgrad(const msq_model* m, const T* G, int Nout, const void* WT, int K
 // attention backward: tensor cores (mma.sync) on the bf16 path, fp32 CUDA cores in the parity mode
 template <typename T>
 static int attn_bwd(const T* qkv, const T* ctx, const T* dctx, int64_t R, int L, int heads, const float* mask, int mask_len, T* dqkv, float* scratch,
-                    cudaStream_t st, const Drop& drop = Drop()) {
+                    cudaStream_t st, const Drop& drop = Drop(), const float* lse_fwd = nullptr) {
   if constexpr (sizeof(T) == 2) {
-    if (attention_bwd_mma_supported(L)) return attention_bwd_mma(qkv, ctx, dctx, R, L, heads, 0.125f, mask, mask_len, mask_len, dqkv, scratch, st, drop);
+    if (attention_bwd_mma_supported(L)) {
+      static int use_lse = -1;   // MSQ_ATTN_LSE=0: ignore the forward's saved log-sum-exp (the dQ kernel recomputes it)
+      if (use_lse < 0) { const char* e = getenv("MSQ_ATTN_LSE"); use_lse = (e && e[0] == '0') ? 0 : 1; }
+      return attention_bwd_mma(qkv, ctx, dctx, R, L, heads, 0.125f, mask, mask_len, mask_len, dqkv, scratch, st, drop, use_lse ? lse_fwd : nullptr);
+    }
   }
   return attention_bwd<T>(qkv, dctx, R, L, heads, 0.125f, mask, mask_len, mask_len, dqkv, scratch, st, drop);
 }
