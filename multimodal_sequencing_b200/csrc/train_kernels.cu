@@ -323,7 +323,8 @@ constexpr int LNB_WARPS = 4;
 constexpr int LNB_MAXV = 8;   // H <= 1024
 
 // v: pre-LN row, d: dy row (in), dx row (out).  ag/ab accumulate dgamma/dbeta for this lane's columns.
-template <int MV = LNB_MAXV>
+// AS: stride of the accumulator arrays (1: registers; 32: a per-warp shared-memory row, float4 index i * 32 + lane)
+template <int MV = LNB_MAXV, int AS = 1>
 __device__ __forceinline__ void ln_bwd_row(float4* v, float4* d, int nv, int H, int lane, const float* __restrict__ gamma, float eps,
                                            float4* ag, float4* ab) {
   float s = 0.f;
@@ -345,9 +346,9 @@ __device__ __forceinline__ void ln_bwd_row(float4* v, float4* d, int nv, int H, 
     if (i < nv) {
       const float4 gm = *reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4);
       v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;          // xhat
-      ag[i].x = fmaf(d[i].x, v[i].x, ag[i].x); ag[i].y = fmaf(d[i].y, v[i].y, ag[i].y);
-      ag[i].z = fmaf(d[i].z, v[i].z, ag[i].z); ag[i].w = fmaf(d[i].w, v[i].w, ag[i].w);
-      ab[i].x += d[i].x; ab[i].y += d[i].y; ab[i].z += d[i].z; ab[i].w += d[i].w;
+      ag[i * AS].x = fmaf(d[i].x, v[i].x, ag[i * AS].x); ag[i * AS].y = fmaf(d[i].y, v[i].y, ag[i * AS].y);
+      ag[i * AS].z = fmaf(d[i].z, v[i].z, ag[i * AS].z); ag[i * AS].w = fmaf(d[i].w, v[i].w, ag[i * AS].w);
+      ab[i * AS].x += d[i].x; ab[i * AS].y += d[i].y; ab[i * AS].z += d[i].z; ab[i * AS].w += d[i].w;
       d[i].x *= gm.x; d[i].y *= gm.y; d[i].z *= gm.z; d[i].w *= gm.w;          // g
       s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
       s2 += (d[i].x * v[i].x + d[i].y * v[i].y) + (d[i].z * v[i].z + d[i].w * v[i].w);
@@ -361,13 +362,13 @@ __device__ __forceinline__ void ln_bwd_row(float4* v, float4* d, int nv, int H, 
     }
 }
 // combine the warps' dgamma / dbeta accumulators and write this block's partial sums
-template <int MV = LNB_MAXV>
+template <int MV = LNB_MAXV, bool IN_SMEM = false>
 __device__ __forceinline__ void ln_bwd_flush(float (*sh)[2 * 128 * LNB_MAXV], const float4* ag, const float4* ab, int nv, int H,
                                              float* __restrict__ partial) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < MV; ++i)
-    if (i < nv) {
+    if (!IN_SMEM && i < nv) {
       const int col = (i * 32 + lane) * 4;
       *reinterpret_cast<float4*>(&sh[warp][col]) = ag[i];
       *reinterpret_cast<float4*>(&sh[warp][H + col]) = ab[i];
@@ -383,7 +384,9 @@ __device__ __forceinline__ int64_t remap_row_t(int64_t row, int in_group, int ou
   return in_group ? (row / in_group) * (int64_t)out_group + out_off + row % in_group : row;
 }
 
-template <typename T, int MV>
+// SMACC: the dgamma / dbeta accumulators live in the warp's shared-memory row instead of 2 * MV float4 registers per lane
+// (fewer registers -> more resident warps; the kernel is latency-bound on its row loads)
+template <typename T, int MV, bool SMACC>
 __global__ void __launch_bounds__(LNB_WARPS * 32) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                 const float* add, int64_t rows, int H,   // dx may alias add
                                                                 const float* __restrict__ gamma, float eps, float* dx,
@@ -392,9 +395,13 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) ln_bwd_kernel(const float* __r
   pdl_sync();
   __shared__ __align__(16) float sh[LNB_WARPS][2 * 128 * LNB_MAXV];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nv = H >> 7;
-  float4 ag[MV], ab[MV];
+  constexpr int AS = SMACC ? 32 : 1;
+  float4 ag_r[SMACC ? 1 : MV], ab_r[SMACC ? 1 : MV];
+  float4* ag = SMACC ? reinterpret_cast<float4*>(&sh[warp][0]) + lane : ag_r;
+  float4* ab = SMACC ? reinterpret_cast<float4*>(&sh[warp][H]) + lane : ab_r;
 #pragma unroll
-  for (int i = 0; i < MV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < MV; ++i)
+    if (!SMACC || i < nv) ag[i * AS] = ab[i * AS] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t row = (int64_t)blockIdx.x * LNB_WARPS + warp; row < rows; row += (int64_t)gridDim.x * LNB_WARPS) {
     float4 v[MV], d[MV];
     const float* xr = x + row * H;
@@ -402,7 +409,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) ln_bwd_kernel(const float* __r
 #pragma unroll
     for (int i = 0; i < MV; ++i)
       if (i < nv) { v[i] = Vec4<float>::load(xr + (i * 32 + lane) * 4); d[i] = Vec4<float>::load(dr + (i * 32 + lane) * 4); }
-    ln_bwd_row<MV>(v, d, nv, H, lane, gamma, eps, ag, ab);
+    ln_bwd_row<MV, AS>(v, d, nv, H, lane, gamma, eps, ag, ab);
 #pragma unroll
     for (int i = 0; i < MV; ++i)
       if (i < nv) {
@@ -423,7 +430,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) ln_bwd_kernel(const float* __r
         }
       }
   }
-  ln_bwd_flush<MV>(sh, ag, ab, nv, H, partial);
+  ln_bwd_flush<MV, SMACC>(sh, ag, ab, nv, H, partial);
 }
 
 // block = 32 columns x 32 groups of partial blocks; the groups' sums are combined in index order (deterministic)
@@ -456,8 +463,9 @@ __global__ void __launch_bounds__(LNR_GROUPS * 32) ln_partial_reduce_kernel(cons
   }
 }
 
-static inline int lnb_blocks(int64_t rows) { return (int)min((int64_t)148 * 4, (rows + LNB_WARPS - 1) / LNB_WARPS); }
-size_t ln_bwd_scratch_floats(int H) { return (size_t)148 * 4 * 2 * H; }
+constexpr int LNB_GRID = 148 * 6;   // persistent blocks: up to six are resident per SM with the shared-memory accumulators
+static inline int lnb_blocks(int64_t rows) { return (int)min((int64_t)LNB_GRID, (rows + LNB_WARPS - 1) / LNB_WARPS); }
+size_t ln_bwd_scratch_floats(int H) { return (size_t)LNB_GRID * 2 * H; }
 
 template <typename T>
 int ln_bwd(const float* dy, const float* x, const float* add, int64_t rows, int H, const float* gamma, float eps, float* dx, T* dx_t,
@@ -466,8 +474,11 @@ int ln_bwd(const float* dy, const float* x, const float* add, int64_t rows, int 
   if (rows == 0) return MSQ_OK;
   const int nblk = lnb_blocks(rows);
   // H = 768 instantiation keeps six float4 per array instead of eight (fewer registers -> one more resident block per SM)
-  if (H <= 768) MSQ_CUDA(launch_k(ln_bwd_kernel<T, 6>, dim3(nblk), dim3(LNB_WARPS * 32), 0, st, dy, x, add, rows, H, gamma, eps, dx, dx_t, scratch, in_group, out_group, out_off, drop));
-  else MSQ_CUDA(launch_k(ln_bwd_kernel<T, LNB_MAXV>, dim3(nblk), dim3(LNB_WARPS * 32), 0, st, dy, x, add, rows, H, gamma, eps, dx, dx_t, scratch, in_group, out_group, out_off, drop));
+  static int smacc = -1;   // MSQ_LNB_SMACC=0: register accumulators
+  if (smacc < 0) { const char* e = getenv("MSQ_LNB_SMACC"); smacc = (e && e[0] == '0') ? 0 : 1; }
+  if (H <= 768 && smacc) MSQ_CUDA(launch_k(ln_bwd_kernel<T, 6, true>, dim3(nblk), dim3(LNB_WARPS * 32), 0, st, dy, x, add, rows, H, gamma, eps, dx, dx_t, scratch, in_group, out_group, out_off, drop));
+  else if (H <= 768) MSQ_CUDA(launch_k(ln_bwd_kernel<T, 6, false>, dim3(nblk), dim3(LNB_WARPS * 32), 0, st, dy, x, add, rows, H, gamma, eps, dx, dx_t, scratch, in_group, out_group, out_off, drop));
+  else MSQ_CUDA(launch_k(ln_bwd_kernel<T, LNB_MAXV, false>, dim3(nblk), dim3(LNB_WARPS * 32), 0, st, dy, x, add, rows, H, gamma, eps, dx, dx_t, scratch, in_group, out_group, out_off, drop));
   MSQ_LAUNCH_CHECK();
   MSQ_CUDA(launch_k(ln_partial_reduce_kernel, dim3(ceil_div(2 * H, 32)), dim3(LNR_GROUPS * 32), 0, st, (const float*)scratch, nblk, H, dgamma, dbeta));
   MSQ_LAUNCH_CHECK();
