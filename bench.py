@@ -389,11 +389,14 @@ def run_ordering(ctx, args, cfg_id, steps, warmup, full=True):
                          "checker": "this library's fp32 FFMA mode, itself pinned to the oracle / reference goldens in tests/"}
         if full and precision == "bf16x3" and cfg_id == 1:
             fast = OrderingEngine(sd, mcfg, precise="bf16", device=ctx.dev)
-            fms, _ = ctx.timed(lambda: fast.order_device(devb, W), max(2, steps // 2), 2)
+            fms, fex = ctx.timed(lambda: fast.order_device(devb, W), max(2, steps // 2), 2, profile_lib=lib)
             pf_ = fast.order_device(sub, W).cpu()
             fsame = int(ctx.sum_over_ranks(int((pf_ == p32).all(1).sum())))
+            fach = (fex["kernel_flops"] / 1e12) / (fex["kernel_ms"] / 1e3) if fex.get("kernel_ms") else None
             rec["fast_mode"] = {"dtype": "bf16", "value": total * max(2, steps // 2) / (fms / 1e3), "unit": "manuals/s",
                                 "agreement_vs_fp32_path": fsame / (n_chk * ctx.world),
+                                # the same tcgen05 GEMM kernel with one MMA per product: algorithmic = executed FLOPs
+                                "gemm_tflops": fach, "gemm_frac_of_bf16_peak": (fach / peaks()["tf_sust"]) if fach else None,
                                 "note": "plain bf16 operands: ~2.5x the headline's speed, outside north_star's numeric gate "
                                         "(encoder outputs ~1e-2, some permutations flip under random-init margins)"}
             del fast
