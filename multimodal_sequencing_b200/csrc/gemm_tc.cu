@@ -31,6 +31,7 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_EPI_WARPS = 8, TC_THREADS = (2 + TC_EPI_WARPS) * 32;
 
 // MODE: 0 plain, 1 EPI_LNFOLD, 2 EPI_RESLN (bf16 copy), 3 EPI_RESLN with a SPLIT-bf16 copy (bf16x3 mode: hi and lo boxes)
+// 4 EPI_DUALACT (bf16 pre-activation in C + bf16 activation in C2; the second output uses MODE 2's bf16 box)
 template <bool PAIR, int MODE = 0> struct TcCfg {
   static constexpr int STAGES = 4;
   // MODE 3 (split copy: two more boxes per warp) keeps ONE fp32 box per warp instead of two, so that the operand ring stays at
@@ -186,9 +187,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                const __grid_constant__ CUtensorMap tma_r, TcEpi ep, int num_m, int num_n, int num_k) {
   using Cfg = TcCfg<PAIR, MODE>;
   constexpr bool F32 = same_type<TO, float>::value, SPL = is_split<TO>::value;
-  static_assert(MODE < 2 || F32, "EPI_RESLN writes the fp32 stream (+ its bf16 / split-bf16 copy)");
+  static_assert(MODE < 2 || MODE == 4 || F32, "EPI_RESLN writes the fp32 stream (+ its bf16 / split-bf16 copy)");
   static_assert(!SPL || MODE <= 1, "split-bf16 output: plain or LayerNorm-folded epilogue");
-  constexpr bool RESLN = MODE >= 2, C2SPL = MODE == 3;
+  static_assert(MODE != 4 || (!F32 && !SPL && ACT == ACT_NONE), "EPI_DUALACT: bf16 outputs, the activation is a run-time argument");
+  constexpr bool RESLN = MODE == 2 || MODE == 3, C2SPL = MODE == 3, DUAL = MODE == 4;
   constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -210,7 +212,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
     if (Cfg::TMA_STORE) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_c) : "memory");
-    if (Cfg::TMA_STORE && RESLN) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_c2) : "memory");
+    if (Cfg::TMA_STORE && (RESLN || DUAL)) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_c2) : "memory");
     if (Cfg::TMA_STORE && RESLN) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_r) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, TC_EPI_WARPS * (PAIR ? 2 : 1)); }
@@ -472,6 +474,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
             __syncwarp();
             mbar_wait(rbar + 8 * (rk & 1), (rk >> 1) & 1);   // residual chunk rk has landed in box rk&1
+          } else if (DUAL) {
+            // the activation box is rewritten every chunk: every store issued so far has been read out of shared memory
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
           } else if (new_box) {
             // the fp32 box used two chunks ago has been read out (split output: box 0 = hi, box 1 = lo, both reused)
             if (lane == 0) { if (SPL) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
@@ -507,6 +513,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                              *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
               }
             }
+            if (DUAL) {   // second output: act(v) as bf16 into the 64-byte-row box (same layout as MODE 2's copy)
+              float w[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) w[i] = apply_act_fast(v[i], ep.act);
+              const uint32_t o2 = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(w[0], w[1]), p1 = __floats2bfloat162_rn(w[2], w[3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(w[4], w[5]), p3 = __floats2bfloat162_rn(w[6], w[7]);
+              st_shared_v4(stg2 + o2, *reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                           *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+            }
             if (F32) {
               st_shared_v4(rowp + (((2 * j) ^ (lane & 7)) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
               st_shared_v4(rowp + (((2 * j + 1) ^ (lane & 7)) << 4), __float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
@@ -521,6 +537,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
               st_shared_v4(rowp + ((((ch & 1) * 4 + j) ^ (lane & 7)) << 4), *reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
                            *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+            }
+          }
+          if (DUAL) {   // the activation chunk (32 columns) leaves every chunk; the pre-activation box every second one
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && col0 < ep.N) {
+              tma_store_2d(&tma_c2, stg2, col0, (int)(row - lane));
+              tma_store_commit();
             }
           }
           if (F32 || (ch & 1) == 1) {
@@ -564,6 +588,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 } else {
                   epi_store8<bf16>(ep.C2 + row * ep.ldc + col, v);
                 }
+              }
+              if (DUAL) {
+                float w[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = apply_act_fast(v[i], ep.act);
+                epi_store8<bf16>(ep.C2 + row * ep.ldc + col, w);
               }
               if constexpr (SPL) {   // row of C = [hi(ldc) | lo(ldc)]
                 bf16* cb = reinterpret_cast<bf16*>(ep.C) + row * (2 * (int64_t)ep.ldc) + col;
@@ -625,10 +655,10 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
   constexpr bool F32 = same_type<TO, float>::value, SPL = is_split<TO>::value;
   if (Cfg::TMA_STORE && SPL) MSQ_TRY(make_map_2d(&mc, g.C, g.M, g.ldc + g.N, 2 * g.ldc, 64, 32, false));   // lo plane at column ldc
   else if (Cfg::TMA_STORE) MSQ_TRY(make_map_2d(&mc, g.C, g.M, g.N, g.ldc, F32 ? 32 : 64, 32, F32));
-  if (Cfg::TMA_STORE && MODE == 2) MSQ_TRY(make_map_2d(&mc2, g.C2bf, g.M, g.N, g.ldc, 32, 32, false, true));
+  if (Cfg::TMA_STORE && (MODE == 2 || MODE == 4)) MSQ_TRY(make_map_2d(&mc2, g.C2bf, g.M, g.N, g.ldc, 32, 32, false, true));
   if (Cfg::TMA_STORE && MODE == 3) MSQ_TRY(make_map_2d(&mc2, g.C2bf, g.M, g.ldc + g.N, 2 * g.ldc, 32, 32, false, true));   // [hi(ldc) | lo(ldc)]
   CUtensorMap mr = ma;
-  if (Cfg::TMA_STORE && MODE >= 2) MSQ_TRY(make_map_2d(&mr, g.resid, g.M, g.N, g.ldr, 32, 32, true));
+  if (Cfg::TMA_STORE && (MODE == 2 || MODE == 3)) MSQ_TRY(make_map_2d(&mr, g.resid, g.M, g.N, g.ldr, 32, 32, true));
   MSQ_SMEM_ATTR(Cfg::SMEM, gemm_tc_kernel<TO, PAIR, ACT, MODE>);
   TcEpi ep;
   ep.bias = g.bias; ep.resid = g.resid; ep.C = g.C; ep.M = g.M; ep.N = g.N; ep.ldc = g.ldc; ep.ldr = g.ldr; ep.act = g.act;
@@ -673,6 +703,17 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
 
 template <typename TO, bool PAIR>
 static int launch_gemm_tc(const GemmArgs& g, int sms, cudaStream_t st) {
+  if (g.mode == EPI_DUALACT) {
+    if constexpr (same_type<TO, bf16>::value) {
+      MSQ_REQUIRE(g.C2bf && !g.resid && !g.tn && !g.split && g.drop.thresh == 0 && ((uintptr_t)g.C2bf & 15) == 0,
+                  "gemm_tc: EPI_DUALACT needs C2bf and plain bf16 K-major operands, no residual / dropout");
+      MSQ_REQUIRE(g.act == ACT_GELU_ERF || g.act == ACT_QUICK_GELU || g.act == ACT_TANH || g.act == ACT_RELU, "gemm_tc: EPI_DUALACT activation %d", g.act);
+      return launch_gemm_tc_act<TO, PAIR, ACT_NONE, 4>(g, sms, st);
+    } else {
+      set_error("gemm_tc: EPI_DUALACT writes bf16 outputs");
+      return MSQ_ERR_ARG;
+    }
+  }
   if (g.mode == EPI_RESLN) {
     if constexpr (same_type<TO, float>::value) {
       MSQ_REQUIRE(g.act == ACT_NONE && g.C2bf && g.stats_out && g.resid, "gemm_tc: EPI_RESLN needs resid, C2bf, stats_out and no activation");

@@ -46,7 +46,7 @@ template <typename T> int rn_finish(const float* o, int64_t rows, int L, int E, 
 
 // ---- gemm_simt.cu : C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual), fp32 FFMA accumulate
 // epilogue modes of the tensor-core GEMM (deferred LayerNorm, see gemm_tc.cu)
-enum { EPI_PLAIN = 0, EPI_LNFOLD = 1, EPI_RESLN = 2 };
+enum { EPI_PLAIN = 0, EPI_LNFOLD = 1, EPI_RESLN = 2, EPI_DUALACT = 3 };
 
 struct GemmArgs {
   const void* A;       // [M, lda]  (TA)
@@ -65,6 +65,9 @@ struct GemmArgs {
   //   EPI_RESLN   C = acc + bias + LN_pending(resid) (raw resid when stats_in is null); also writes the bf16 copy C2bf
   //               and the partial statistics of the rows it produced (stats_out [M, 2*ceil(N/256), 2]), i.e. the
   //               NEXT pending LayerNorm's input.  svec/beta hold gamma/beta of the LayerNorm pending on resid.
+  //   EPI_DUALACT (bf16 in / out, fine-tuning forward of the up-projections): C = acc + bias (the pre-activation the
+  //               backward pass needs) AND C2bf = act(acc + bias) (the operand of the next GEMM) from one accumulator read:
+  //               the separate activation pass over [M, N] disappears
   // gemm_tc only, single-CTA path: "TN" operands for weight gradients.  A is [K, M] (row = contraction index, lda) and
   // W is [K, N] (ldw), both row-major, i.e. MN-major for the tensor core: C[M,N] = A^T W.  TMA boxes of 64 contraction
   // rows x 64 columns land in shared memory as the canonical MN-major SWIZZLE_128B atoms and are consumed through

@@ -237,8 +237,7 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
       MSQ_TRY(attention<T>((const T*)t.qkv, R, Lv, heads, 64, 0.125f, nullptr, 0, 0, (T*)t.ctx, st, Drop(), t.lse, &t.have_lse));
       MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.ctx, Wd, wptr<T>(L.out), L.out.ld, L.out.b, t.x, Wd, t.x1, Wd, Mv, Wd, Wd, ACT_NONE, st)));
       MSQ_TRY(layernorm<T>(t.x1, Mv, Wd, L.ln2.g, L.ln2.b, 1e-5f, nullptr, (T*)t.y2, 0, 0, 0, st));
-      MSQ_TRY((gemm_nt<T, T>(m, (const T*)t.y2, Wd, wptr<T>(L.fc), L.fc.ld, L.fc.b, nullptr, 0, (T*)t.u, 4 * Wd, Mv, 4 * Wd, Wd, ACT_NONE, st)));
-      MSQ_TRY(act_fwd<T>((const T*)t.u, Mv * 4 * Wd, ACT_QUICK_GELU, (T*)t.hb, st));
+      MSQ_TRY(gemm_nt_dualact<T>(m, (const T*)t.y2, Wd, wptr<T>(L.fc), L.fc.ld, L.fc.b, (T*)t.u, (T*)t.hb, 4 * Wd, Mv, 4 * Wd, Wd, ACT_QUICK_GELU, st));
       MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.hb, 4 * Wd, wptr<T>(L.proj), L.proj.ld, L.proj.b, t.x1, Wd, xn, Wd, Mv, Wd, 4 * Wd, ACT_NONE, st)));
     }
     MSQ_TRY(layernorm<T>(ts->vx_last, Mv, Wd, m->ln_post.g, m->ln_post.b, 1e-5f, nullptr, (T*)ts->y_post, 0, 0, 0, st));
@@ -265,8 +264,7 @@ static int forward_train(msq_model* m, const int64_t* ids, const int64_t* tt, co
       MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.ctx, H, wptr<T>(L.out), L.out.ld, L.out.b, xf, H, t.s1, H, Mj, H, H, ACT_NONE, st)));
     }
     MSQ_TRY(layernorm<T>(t.s1, Mj, H, L.ln1.g, L.ln1.b, 1e-12f, x1f, (T*)t.x1, 0, 0, 0, st));
-    MSQ_TRY((gemm_nt<T, T>(m, (const T*)t.x1, H, wptr<T>(L.up), L.up.ld, L.up.b, nullptr, 0, (T*)t.u, I, Mj, I, H, ACT_NONE, st)));
-    MSQ_TRY(act_fwd<T>((const T*)t.u, Mj * I, ACT_GELU_ERF, (T*)t.hb, st));
+    MSQ_TRY(gemm_nt_dualact<T>(m, (const T*)t.x1, H, wptr<T>(L.up), L.up.ld, L.up.b, (T*)t.u, (T*)t.hb, I, Mj, I, H, ACT_GELU_ERF, st));
     if (drop_h && gemm_nt_on_tc<T>(m, I, L.down.ld, H, H, I)) {   // s2 = dropout(dense(h) + b) + x1
       MSQ_TRY((gemm_nt<T, float>(m, (const T*)t.hb, I, wptr<T>(L.down), L.down.ld, L.down.b, x1f, H, t.s2, H, Mj, H, I, ACT_NONE, st,
                                  make_drop(dc, DROP_F, (int)l, dc.p_hidden))));

@@ -174,6 +174,26 @@ static int gemm_nt(const msq_model* m, const T* A, int lda, const T* W, int ldw,
   }
 }
 
+// U = A W^T + bias (kept for the backward pass) and Hb = act(U) (the next GEMM's operand): ONE tensor-core GEMM with two
+// outputs (GemmArgs EPI_DUALACT) where the tcgen05 path applies, else the GEMM followed by the activation pass.
+// MSQ_DUALACT=0 forces the two-kernel form.
+template <typename T>
+static int gemm_nt_dualact(const msq_model* m, const T* A, int lda, const T* W, int ldw, const float* bias, T* U, T* Hb, int ld, int64_t M,
+                           int N, int K, int act, cudaStream_t st) {
+  if constexpr (sizeof(T) == 2) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("MSQ_DUALACT"); on = (e && e[0] == '0') ? 0 : 1; }
+    if (on && ld == N && gemm_nt_on_tc<T>(m, lda, ldw, ld, N, K) && (act == ACT_GELU_ERF || act == ACT_QUICK_GELU)) {
+      GemmArgs g;
+      g.A = A; g.W = W; g.bias = bias; g.resid = nullptr; g.C = U; g.C2 = nullptr; g.C2bf = Hb;
+      g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldc = ld; g.ldr = 0; g.act = act; g.mode = EPI_DUALACT;
+      return gemm_tc<bf16>(g, st);
+    }
+  }
+  MSQ_TRY((gemm_nt<T, T>(m, A, lda, W, ldw, bias, nullptr, 0, U, ld, M, N, K, ACT_NONE, st)));
+  return act_fwd<T>(U, M * (int64_t)N, act, Hb, st);
+}
+
 int splitk_accumulate(const float* part, int S, int64_t n, float* dW, cudaStream_t st);   // train_kernels.cu
 
 struct BwdBufs {
