@@ -31,7 +31,7 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_EPI_WARPS = 8, TC_THREADS = (2 + TC_EPI_WARPS) * 32;
 
 // MODE: 0 plain, 1 EPI_LNFOLD, 2 EPI_RESLN (bf16 copy), 3 EPI_RESLN with a SPLIT-bf16 copy (bf16x3 mode: hi and lo boxes)
-// 4 EPI_DUALACT (bf16 pre-activation in C + bf16 activation in C2; the second output uses MODE 2's bf16 box)
+// 4 EPI_DUALACT (bf16 pre-activation in C + bf16 activation in C2: the warp's two 4 KB boxes hold one output each)
 template <bool PAIR, int MODE = 0> struct TcCfg {
   static constexpr int STAGES = 4;
   // MODE 3 (split copy: two more boxes per warp) keeps ONE fp32 box per warp instead of two, so that the operand ring stays at
@@ -43,7 +43,7 @@ template <bool PAIR, int MODE = 0> struct TcCfg {
   static constexpr bool TMA_STORE = PAIR;
   static constexpr int STAGING_F32 = TMA_STORE ? TC_EPI_WARPS * F32_BOXES * 4096 : 0;
   // EPI_RESLN: one more box per warp for the bf16 copy, 32 rows x 32 columns (64-byte rows, 64B swizzle), stored every chunk
-  static constexpr int STAGING_BYTES = STAGING_F32 + ((TMA_STORE && MODE >= 2) ? (MODE == 3 ? 2 : 1) * TC_EPI_WARPS * 2048 : 0);
+  static constexpr int STAGING_BYTES = STAGING_F32 + ((TMA_STORE && (MODE == 2 || MODE == 3)) ? (MODE == 3 ? 2 : 1) * TC_EPI_WARPS * 2048 : 0);
   static constexpr int VECS = MODE == 0 ? 1 : (MODE == 1 ? 2 : 3);   // per-column vectors held per warp: bias | svec/gamma | beta
   static constexpr int B_ROWS = PAIR ? 128 : 256;            // rows of W staged per CTA and stage
   static constexpr int B_BYTES = B_ROWS * TC_BK * 2;
@@ -475,15 +475,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             __syncwarp();
             mbar_wait(rbar + 8 * (rk & 1), (rk >> 1) & 1);   // residual chunk rk has landed in box rk&1
           } else if (DUAL) {
-            // the activation box is rewritten every chunk: every store issued so far has been read out of shared memory
-            if (lane == 0) tma_store_wait_read<0>();
-            __syncwarp();
+            // box 0 = pre-activation, box 1 = activation, 64 bf16 columns (two chunks) each: both are rewritten every second
+            // chunk, once the stores issued from them have been read out of shared memory
+            if (new_box) {
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+            }
           } else if (new_box) {
             // the fp32 box used two chunks ago has been read out (split output: box 0 = hi, box 1 = lo, both reused)
             if (lane == 0) { if (SPL) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
             __syncwarp();
           }
-          const uint32_t box = (SPL || !RES_DB) ? stg : stg + ((RES_TMA ? rk : (uint32_t)stg_use) & 1) * 4096;
+          const uint32_t box = (SPL || !RES_DB || DUAL) ? stg : stg + ((RES_TMA ? rk : (uint32_t)stg_use) & 1) * 4096;
           const uint32_t rowp = box + lane * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -513,14 +516,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                              *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
               }
             }
-            if (DUAL) {   // second output: act(v) as bf16 into the 64-byte-row box (same layout as MODE 2's copy)
+            if (DUAL) {   // second output: act(v) as bf16 into the warp's second box (same 128-byte-row layout as the first)
               float w[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) w[i] = apply_act_fast(v[i], ep.act);
-              const uint32_t o2 = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
               __nv_bfloat162 p0 = __floats2bfloat162_rn(w[0], w[1]), p1 = __floats2bfloat162_rn(w[2], w[3]);
               __nv_bfloat162 p2 = __floats2bfloat162_rn(w[4], w[5]), p3 = __floats2bfloat162_rn(w[6], w[7]);
-              st_shared_v4(stg2 + o2, *reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+              st_shared_v4(rowp + 4096 + ((((ch & 1) * 4 + j) ^ (lane & 7)) << 4), *reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
                            *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
             }
             if (F32) {
@@ -539,14 +541,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                            *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
             }
           }
-          if (DUAL) {   // the activation chunk (32 columns) leaves every chunk; the pre-activation box every second one
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0 && col0 < ep.N) {
-              tma_store_2d(&tma_c2, stg2, col0, (int)(row - lane));
-              tma_store_commit();
-            }
-          }
           if (F32 || (ch & 1) == 1) {
             fence_proxy_async_smem();
             __syncwarp();
@@ -562,6 +556,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               if (box_col < ep.N) {
                 tma_store_2d(&tma_c, box, box_col, (int)(row - lane));
                 if (SPL) tma_store_2d(&tma_c, box + 4096, ep.ldc + box_col, (int)(row - lane));   // lo plane (N % 64 == 0)
+                if (DUAL) tma_store_2d(&tma_c2, box + 4096, box_col, (int)(row - lane));          // activation box
               }
               tma_store_commit();
             }
@@ -655,7 +650,8 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
   constexpr bool F32 = same_type<TO, float>::value, SPL = is_split<TO>::value;
   if (Cfg::TMA_STORE && SPL) MSQ_TRY(make_map_2d(&mc, g.C, g.M, g.ldc + g.N, 2 * g.ldc, 64, 32, false));   // lo plane at column ldc
   else if (Cfg::TMA_STORE) MSQ_TRY(make_map_2d(&mc, g.C, g.M, g.N, g.ldc, F32 ? 32 : 64, 32, F32));
-  if (Cfg::TMA_STORE && (MODE == 2 || MODE == 4)) MSQ_TRY(make_map_2d(&mc2, g.C2bf, g.M, g.N, g.ldc, 32, 32, false, true));
+  if (Cfg::TMA_STORE && MODE == 2) MSQ_TRY(make_map_2d(&mc2, g.C2bf, g.M, g.N, g.ldc, 32, 32, false, true));
+  if (Cfg::TMA_STORE && MODE == 4) MSQ_TRY(make_map_2d(&mc2, g.C2bf, g.M, g.N, g.ldc, 64, 32, false));   // same box shape as C
   if (Cfg::TMA_STORE && MODE == 3) MSQ_TRY(make_map_2d(&mc2, g.C2bf, g.M, g.ldc + g.N, 2 * g.ldc, 32, 32, false, true));   // [hi(ldc) | lo(ldc)]
   CUtensorMap mr = ma;
   if (Cfg::TMA_STORE && (MODE == 2 || MODE == 3)) MSQ_TRY(make_map_2d(&mr, g.resid, g.M, g.N, g.ldr, 32, 32, true));
