@@ -276,7 +276,10 @@ int msq_gemm(int32_t dtype, const void* A_dev, const void* W_dev, const float* b
  *                      bias = b + W beta, svec[n] = sum_k W'[n,k]; mu / rstd from stats_in [M, sp_in, 2] partial sums
  *   mode 2 (residual)  C = A W^T + bias + LN(resid) in fp32 (raw resid when stats_in is NULL; gamma/beta in
  *                      svec_or_gamma/beta), plus C2bf = bf16(C) and stats_out [M, 2*ceil(N/256), 2] = per-row partial
- *                      (sum, sum of squares) of C over 128-column groups. */
+ *                      (sum, sum of squares) of C over 128-column groups.
+ *   mode 3 (dual)      out_bf16 = 1: C = bf16(A W^T + bias) AND C2bf = bf16(act(A W^T + bias)) from one accumulator read (the
+ *                      fine-tuning forward of the up-projections keeps the pre-activation for the backward pass and feeds the
+ *                      activation to the next GEMM); act: 1 erf-GELU, 2 QuickGELU, 3 tanh, 5 ReLU; no residual. */
 int msq_gemm_deferred_ln(int32_t mode, int32_t out_bf16, const void* A_dev, const void* W_dev, const float* bias_dev,
                          const float* resid_dev, const float* svec_or_gamma_dev, const float* beta_dev,
                          const float* stats_in_dev, int32_t sp_in, int32_t ln_dim, float eps, void* C_dev, void* C2bf_dev,

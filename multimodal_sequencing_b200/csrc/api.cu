@@ -1751,7 +1751,7 @@ extern "C" int msq_gemm_deferred_ln(int32_t mode, int32_t out_bf16, const void* 
                                     const float* resid_dev, const float* svec_or_gamma_dev, const float* beta_dev,
                                     const float* stats_in_dev, int32_t sp_in, int32_t ln_dim, float eps, void* C_dev, void* C2bf_dev,
                                     float* stats_out_dev, int64_t M, int32_t N, int32_t K, int32_t act, void* stream) {
-  MSQ_REQUIRE(mode == EPI_LNFOLD || mode == EPI_RESLN, "msq_gemm_deferred_ln: mode %d", mode);
+  MSQ_REQUIRE(mode == EPI_LNFOLD || mode == EPI_RESLN || mode == EPI_DUALACT, "msq_gemm_deferred_ln: mode %d", mode);
   GemmArgs g;
   g.A = A_dev; g.W = W_dev; g.bias = bias_dev; g.resid = resid_dev; g.C = C_dev; g.C2 = nullptr;
   g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldc = N; g.ldr = N; g.act = act;

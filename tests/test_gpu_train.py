@@ -460,6 +460,35 @@ def test_gemm_tn_operands_vs_float64(shape):
     assert err <= bound * max(1.0, ref.abs().max().item() / (K ** 0.5)), (err, bound)
 
 
+@pytest.mark.parametrize("shape,act", [((6810, 3072, 768), 1), ((23760, 3072, 768), 2), ((100, 512, 128), 1), ((300, 264, 64), 2)])
+def test_gemm_dual_output_vs_float64(shape, act):
+    """EPI_DUALACT of the tcgen05 GEMM (the up-projections of the fine-tuning forward): C = bf16(A W^T + b) and
+    C2 = bf16(act(A W^T + b)) from one accumulator read; CTA-pair path with a partial last row tile, and the single-CTA path
+    with partial column tiles.  act 1 = erf-GELU (lxrt/modeling.py:116-122), 2 = QuickGELU (clip/model.py:199-201)."""
+    import ctypes as C
+    from multimodal_sequencing_b200 import _lib
+    lib = _lib.load()
+    if not lib.msq_tc_available():
+        pytest.skip("no tcgen05 device")
+    M, N, K = shape
+    gen = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=gen) * 0.5).to(torch.bfloat16).cuda()
+    W = (torch.randn(N, K, generator=gen) * (2.0 / K ** 0.5)).to(torch.bfloat16).cuda()
+    b = torch.randn(N, generator=gen).cuda()
+    u = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+    h = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    _lib.check(lib.msq_gemm_deferred_ln(3, 1, p(A), p(W), p(b), None, None, None, None, 0, 0, 0.0, p(u), p(h), None, M, N, K, act,
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().t() + b.double()
+    ract = ref * 0.5 * (1 + torch.erf(ref / 2 ** 0.5)) if act == 1 else ref * torch.sigmoid(1.702 * ref)
+    assert not torch.isnan(u.float()).any() and not torch.isnan(h.float()).any(), "every element of both outputs must be written"
+    scale = max(1.0, ref.abs().max().item())
+    assert (u.double() - ref).abs().max().item() <= 2 ** -8 * scale + 1e-3          # bf16 rounding of the stored value
+    assert (h.double() - ract).abs().max().item() <= 2 ** -8 * scale + 2e-3         # + the tanh-fit of erf (|err| < 3e-5)
+
+
 @pytest.mark.parametrize("precise", [True, False])
 def test_multimodal_train_step_two_manuals(golden_dir, precise):
     """B = 2 multimodal manuals of 4 steps (unique-image table shared across the batch, pair rows of both manuals in one
