@@ -551,7 +551,9 @@ def line_decode(ctx, args, rec, steps, warmup):
     tc = rec["precision"] != "fp32"
     line = {"metric": METRIC[4], "value": rec["value"], "unit": "manuals/s", "n_gpus": ctx.world, "steps": steps, "warmup": warmup,
             "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (recurrent / pre-projection GEMMs as three-plane bf16 on tcgen05, fp32-grade)" if tc else "f32",
+            "dtype": ("f32 state / scoring; recurrent + pre-projection GEMMs on tcgen05 as " +
+                      ("bf16x6 (three bf16 planes, six MMAs per product, fp32-grade)" if os.environ.get("MSQ_DEC_X3", "1") == "0"
+                       else "bf16x3 (hi + lo bf16 planes, three MMAs per product; MSQ_DEC_X3=0: bf16x6)")) if tc else "f32",
             "data": "synthetic (seeded encoder outputs)", "config": config_dict(4, rec["B"], ctx.world, args.backbone, args.text), "impl": "ours",
             "e2e": {"value": rec["e2e_value"], "unit": "manuals/s", "h2d_bytes_per_step": rec["h2d"], "d2h_bytes_per_step": rec["d2h"],
                     "api": "OrderingEngine.beam_search -> msq_beam_search from pinned host encoder outputs; the orders come back"},

@@ -1238,6 +1238,7 @@ static int run_decode(msq_model* m, const float* sents, const float* key, const 
     GemmArgs g;
     g.A = s3; g.W = m->wih3; g.bias = m->xg_lin.b; g.resid = nullptr; g.C = xg; g.C2 = nullptr;
     g.M = B * (N + 1); g.N = 4 * H; g.K = H; g.lda = H; g.ldw = H; g.ldc = 4 * H; g.ldr = 0; g.act = ACT_NONE; g.split = 2;
+    g.trunc = decode_trunc(m->cfg.precise);
     MSQ_TRY(gemm_tc<float>(g, st));
     g.A = r3; g.W = m->wpw3; g.bias = nullptr; g.C = t4; g.M = B * N * N; g.K = m->Kp; g.lda = m->Kp; g.ldw = m->Kp;
     MSQ_TRY(gemm_tc<float>(g, st));
@@ -1250,6 +1251,7 @@ static int run_decode(msq_model* m, const float* sents, const float* key, const 
   io.xg = xg; io.t4 = t4; io.key0 = key; io.h0 = h0; io.B = B; io.N = N; io.W = beam; io.H = H;
   io.perm = perm; io.trace_ix = tr_ix; io.trace_cost = tr_cost; io.trace_logp = tr_logp;
   io.forced = forced; io.final_cost = final_cost; io.scratch = scratch; io.tc = tc ? 1 : 0;
+  io.trunc = tc ? decode_trunc(m->cfg.precise) : 0;
   return beam_search(m->dec, io, st);
 }
 

@@ -326,6 +326,16 @@ size_t beam_search_scratch_bytes(int64_t B, int N, int W, int H) {
   const size_t Kp = ((size_t)(H + 2) + 63) / 64 * 64;
   return beam_search_state_bytes(B, W, H) + ((((size_t)B * (N + 1) * 3 * H + 127) & ~size_t(127)) + (size_t)B * N * N * 3 * Kp) * 2 + 1024;
 }
+int decode_trunc(int precise) {
+  // default: bf16x3 in both tensor-core modes.  precise = 2 carries every encoder operand as hi + lo already (the decoder's
+  // inputs arrive with ~2e-5 relative error), precise = 0 is plain bf16 upstream; the fp32 parity mode never comes here
+  // (FFMA decode).  Beam indices stay bit-exact vs the reference fixtures either way (tests/test_gpu_parity.py).
+  // Read per call (two getenv per decode) so that a test can run both forms in one process.
+  (void)precise;
+  const char* e = getenv("MSQ_DEC_X3");
+  return e ? (atoi(e) != 0) : 1;
+}
+
 bool decode_tc_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("MSQ_DECODE_TC"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -498,12 +508,25 @@ static int launch_dec_gemm(const DecGemm& a, cudaStream_t st) {
   return MSQ_OK;
 }
 
+// tanh x = sign(x) (1 - 2 / (e^{2|x|} + 1)) on the SFU: ex2.approx (2 ulp) and rcp.approx (1 ulp) give an ABSOLUTE error of
+// <= ~2e-7 everywhere (libm's tanhf: 2 ulp, i.e. up to 1.2e-7 near 1) in 7 straight-line instructions instead of tanhf's two
+// divergent branches (polynomial below 0.55, exp + IEEE division above): dec_select is issue-bound and tanh was ~half of it.
+__device__ __forceinline__ float tanh_sfu(float x) {
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(x) * 2.8853900817779268f));   // e^{2|x|}; +inf for large |x| -> r = 0
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+  return copysignf(fmaf(-2.0f, r, 1.0f), x);
+}
+
 // One CTA per manual: pointer scores of every live beam over the N candidate steps, log-softmax, top-k, new tables.
+// SFU = true (tensor-core form): tanh_sfu; false (fp32 parity form): libm tanhf, bit-identical to the round-1 kernel.
+template <bool SFU>
 __global__ void __launch_bounds__(512, 1) dec_select_kernel(DecodeWeights w, DecodeIO io, DecState s, int t, int live, int cur, int nbuf) {
   pdl_sync();
   extern __shared__ __align__(16) float fg_s[];   // 2 x (F rows [N][H] | G rows [N][H]): candidate step being scored + the next
   const int H = io.H, N = io.N, W = io.W, H4 = 4 * H;
   __shared__ float e[16][DC_MAXN];
+  __shared__ float ep[8][16];   // blocked form: partial dot product of a 128-feature chunk (H <= 1024) per beam
   __shared__ float cost[16];
   __shared__ uint8_t seq[16][DC_MAXN];
   __shared__ uint32_t pickm[16];
@@ -530,13 +553,19 @@ __global__ void __launch_bounds__(512, 1) dec_select_kernel(DecodeWeights w, Dec
   auto stage = [&](int k, int buf) {
     float* F = fg_s + (size_t)buf * 2 * N * H;
     float* G = F + (size_t)N * H;
-    for (int idx = tid; idx < N * (H / 4); idx += nthr) {
-      const int j = idx / (H / 4), d4 = idx % (H / 4);
+    // row loop outside (block-uniform skip), 16-byte column loop inside: no integer division per copy -- the flat-index
+    // form of this loop (idx / (H/4), idx % (H/4) with a run-time H) was ~100 instructions per pair of copies, more than the
+    // scoring itself at small `live` (ncu: 2.7e7 warp instructions at t = 0, where one beam is scored)
+    const uint32_t fbase = (uint32_t)__cvta_generic_to_shared(F), gbase = (uint32_t)__cvta_generic_to_shared(G);
+    for (int j = 0; j < N; ++j) {
       if (j == k || !(any_rem >> j & 1u)) continue;
-      const uint32_t df = (uint32_t)__cvta_generic_to_shared(F + (size_t)j * H + 4 * d4);
-      const uint32_t dg = (uint32_t)__cvta_generic_to_shared(G + (size_t)j * H + 4 * d4);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(df), "l"(t4 + ((int64_t)k * N + j) * H4 + 2 * H + 4 * d4) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dg), "l"(t4 + ((int64_t)j * N + k) * H4 + 3 * H + 4 * d4) : "memory");
+      const float* fsrc = t4 + ((int64_t)k * N + j) * H4 + 2 * H;
+      const float* gsrc = t4 + ((int64_t)j * N + k) * H4 + 3 * H;
+      for (int d = 4 * tid; d < H; d += 4 * nthr) {
+        const uint32_t off = (uint32_t)(j * H + d) * 4u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(fbase + off), "l"(fsrc + d) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(gbase + off), "l"(gsrc + d) : "memory");
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -554,47 +583,134 @@ __global__ void __launch_bounds__(512, 1) dec_select_kernel(DecodeWeights w, Dec
     __syncthreads();
     const float* Fs = fg_s + (size_t)(nbuf == 2 ? (k & 1) : 0) * 2 * N * H;
     const float* Gs = Fs + (size_t)N * H;
-    // A warp scores candidate step k for one beam.  Lane-strided over d in batches of 4 (the global operands of a batch are
-    // loaded before any is used); the summation order is the reference order: j ascending inside fs / gs, d ascending
-    // inside the dot product, xor-tree over lanes.
-    for (int wslot = warp; wslot < live; wslot += nthr >> 5) {
-      const uint32_t picked = pickm[wslot];
-      if (picked >> k & 1u) {
-        if (lane == 0) e[wslot][k] = -1e9f;
-        continue;
-      }
-      const uint32_t need = ~picked & ~(1u << k) & ((1u << N) - 1u);
-      const float* qp = s.q + (b * s.q_rows + wslot) * (int64_t)s.q_ld;
-      const float* a1 = t >= 1 ? t4 + ((int64_t)seq[wslot][t - 1] * N + k) * H4 : nullptr;
-      const float* a2 = t >= 2 ? t4 + ((int64_t)seq[wslot][t - 2] * N + k) * H4 + H : nullptr;
-      const float* k0 = io.key0 + (b * N + k) * (int64_t)H;
-      float part = 0.f;
-      // four consecutive features per lane and 128 per warp pass (H % 4 == 0, every row 16-byte aligned): one 16-byte load per
-      // operand instead of four 4-byte loads -- the kernel is issue-bound, and loads were ~40 % of its instructions
-      for (int d0 = 4 * lane; d0 < H; d0 += 128) {
-        const float4 kv = __ldg(reinterpret_cast<const float4*>(k0 + d0)), wv = __ldg(reinterpret_cast<const float4*>(w.wt + d0));
-        const float4 qv = *reinterpret_cast<const float4*>(qp + d0);
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 a1v = a1 ? __ldg(reinterpret_cast<const float4*>(a1 + d0)) : z4, a2v = a2 ? __ldg(reinterpret_cast<const float4*>(a2 + d0)) : z4;
-        float4 fs = z4, gs = z4;
+    if constexpr (SFU) {
+      // Blocked form.  The warp-per-(beam, k) loop below re-reads every staged F / G row once per BEAM: W x N x |Rem| x 2 x H x 4
+      // bytes of shared-memory loads per manual and step (7.8 MB at N = 10, W = 16: ~61 k cycles of the SM's 128 B/clk, the
+      // real bound of that form).  Here a work item is (128-feature chunk, group of BB beams): an F / G row chunk is loaded once
+      // and added into the accumulators of the BB beams that need it, so the shared-memory traffic drops BB-fold and every warp
+      // has work whatever `live` is.  Per-chunk partial dot products meet in ep[chunk][beam] and are summed in chunk order
+      // (deterministic; the order differs from the parity form's lane-strided sum, both are fp32 sums of the same terms).
+      constexpr int BB = 4;
+      const int nchunk = (H + 127) >> 7, ngroup = (live + BB - 1) / BB;
+      for (int item = warp; item < nchunk * ngroup; item += nthr >> 5) {
+        const int c = item % nchunk, g0 = (item / nchunk) * BB;
+        const int d0 = 128 * c + 4 * lane;
+        const bool in = d0 < H;
+        uint32_t need[BB], uni = 0;
 #pragma unroll
-        for (int j = 0; j < DC_MAXN; ++j) {
-          if (j < N && (need >> j & 1u)) {
-            const float4 f = *reinterpret_cast<const float4*>(Fs + (size_t)j * H + d0), g = *reinterpret_cast<const float4*>(Gs + (size_t)j * H + d0);
-            fs.x += f.x; fs.y += f.y; fs.z += f.z; fs.w += f.w;
-            gs.x += g.x; gs.y += g.y; gs.z += g.z; gs.w += g.w;
+        for (int bb = 0; bb < BB; ++bb) {
+          const uint32_t picked = g0 + bb < live ? pickm[g0 + bb] : ~0u;
+          need[bb] = (picked >> k & 1u) ? 0u : (~picked & ~(1u << k) & ((1u << N) - 1u));
+          uni |= need[bb];
+        }
+        // beam bb of the group is live and has not picked k (need == 0 alone does not say so: the last unpicked step has an
+        // empty remainder)
+        auto need_score = [&](int, int wslot) { return wslot < live && !(pickm[wslot] >> k & 1u); };
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        // every global operand of the item is requested BEFORE the shared-memory sums: the kernel runs 8-16 warps per SM, so a
+        // load issued where it is used costs its whole DRAM / L2 latency (that, not the instruction count, bounded this kernel)
+        float4 qv[BB], av[BB];
+#pragma unroll
+        for (int bb = 0; bb < BB; ++bb) {
+          const int wslot = g0 + bb;
+          qv[bb] = av[bb] = z4;
+          if (need_score(bb, wslot) && in) {
+            qv[bb] = *reinterpret_cast<const float4*>(s.q + (b * s.q_rows + wslot) * (int64_t)s.q_ld + d0);
+            if (t >= 1) av[bb] = __ldg(reinterpret_cast<const float4*>(t4 + ((int64_t)seq[wslot][t - 1] * N + k) * H4 + d0));
+            if (t >= 2) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(t4 + ((int64_t)seq[wslot][t - 2] * N + k) * H4 + H + d0));
+              av[bb].x += a.x; av[bb].y += a.y; av[bb].z += a.z; av[bb].w += a.w;
+            }
           }
         }
-        float4 key = make_float4(div_n(fs.x) + div_n(gs.x), div_n(fs.y) + div_n(gs.y), div_n(fs.z) + div_n(gs.z), div_n(fs.w) + div_n(gs.w));
-        if (a1) { key.x += a1v.x; key.y += a1v.y; key.z += a1v.z; key.w += a1v.w; }
-        if (a2) { key.x += a2v.x; key.y += a2v.y; key.z += a2v.z; key.w += a2v.w; }
-        part = fmaf(wv.x, tanhf(qv.x + key.x + kv.x), part);
-        part = fmaf(wv.y, tanhf(qv.y + key.y + kv.y), part);
-        part = fmaf(wv.z, tanhf(qv.z + key.z + kv.z), part);
-        part = fmaf(wv.w, tanhf(qv.w + key.w + kv.w), part);
+        const float4 kv = in ? __ldg(reinterpret_cast<const float4*>(io.key0 + (b * N + k) * (int64_t)H + d0)) : z4;
+        const float4 wv = in ? __ldg(reinterpret_cast<const float4*>(w.wt + d0)) : z4;
+        float4 fs[BB], gs[BB];
+#pragma unroll
+        for (int bb = 0; bb < BB; ++bb) fs[bb] = gs[bb] = z4;
+        if (in) {
+#pragma unroll
+          for (int j = 0; j < DC_MAXN; ++j) {
+            if (j < N && (uni >> j & 1u)) {
+              const float4 f = *reinterpret_cast<const float4*>(Fs + (size_t)j * H + d0), g = *reinterpret_cast<const float4*>(Gs + (size_t)j * H + d0);
+#pragma unroll
+              for (int bb = 0; bb < BB; ++bb) {
+                if (need[bb] >> j & 1u) {
+                  fs[bb].x += f.x; fs[bb].y += f.y; fs[bb].z += f.z; fs[bb].w += f.w;
+                  gs[bb].x += g.x; gs[bb].y += g.y; gs[bb].z += g.z; gs[bb].w += g.w;
+                }
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int bb = 0; bb < BB; ++bb) {
+          const int wslot = g0 + bb;
+          if (wslot >= live) break;
+          float part = 0.f;
+          if (need_score(bb, wslot) && in) {
+            // key = mean F + mean G + (a1 + a2): a1 + a2 are added first here (the parity form adds them one after the other)
+            const float kx = div_n(fs[bb].x) + div_n(gs[bb].x) + av[bb].x, ky = div_n(fs[bb].y) + div_n(gs[bb].y) + av[bb].y;
+            const float kz = div_n(fs[bb].z) + div_n(gs[bb].z) + av[bb].z, kw = div_n(fs[bb].w) + div_n(gs[bb].w) + av[bb].w;
+            part = fmaf(wv.x, tanh_sfu(qv[bb].x + kx + kv.x), part);
+            part = fmaf(wv.y, tanh_sfu(qv[bb].y + ky + kv.y), part);
+            part = fmaf(wv.z, tanh_sfu(qv[bb].z + kz + kv.z), part);
+            part = fmaf(wv.w, tanh_sfu(qv[bb].w + kw + kv.w), part);
+          }
+          part = warp_sum(part);
+          if (lane == 0) ep[c][wslot] = part;
+        }
       }
-      part = warp_sum(part);
-      if (lane == 0) e[wslot][k] = part + w.bt;
+      __syncthreads();
+      if (tid < live) {
+        float sum = 0.f;
+        for (int c = 0; c < nchunk; ++c) sum += ep[c][tid];
+        e[tid][k] = (pickm[tid] >> k & 1u) ? -1e9f : sum + w.bt;
+      }
+    } else {
+      // A warp scores candidate step k for one beam.  Lane-strided over d in batches of 4 (the global operands of a batch are
+      // loaded before any is used); the summation order is the reference order: j ascending inside fs / gs, d ascending
+      // inside the dot product, xor-tree over lanes.
+      for (int wslot = warp; wslot < live; wslot += nthr >> 5) {
+        const uint32_t picked = pickm[wslot];
+        if (picked >> k & 1u) {
+          if (lane == 0) e[wslot][k] = -1e9f;
+          continue;
+        }
+        const uint32_t need = ~picked & ~(1u << k) & ((1u << N) - 1u);
+        const float* qp = s.q + (b * s.q_rows + wslot) * (int64_t)s.q_ld;
+        const float* a1 = t >= 1 ? t4 + ((int64_t)seq[wslot][t - 1] * N + k) * H4 : nullptr;
+        const float* a2 = t >= 2 ? t4 + ((int64_t)seq[wslot][t - 2] * N + k) * H4 + H : nullptr;
+        const float* k0 = io.key0 + (b * N + k) * (int64_t)H;
+        float part = 0.f;
+        // four consecutive features per lane and 128 per warp pass (H % 4 == 0, every row 16-byte aligned): one 16-byte load per
+        // operand instead of four 4-byte loads -- the kernel is issue-bound, and loads were ~40 % of its instructions
+        for (int d0 = 4 * lane; d0 < H; d0 += 128) {
+          const float4 kv = __ldg(reinterpret_cast<const float4*>(k0 + d0)), wv = __ldg(reinterpret_cast<const float4*>(w.wt + d0));
+          const float4 qv = *reinterpret_cast<const float4*>(qp + d0);
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 a1v = a1 ? __ldg(reinterpret_cast<const float4*>(a1 + d0)) : z4, a2v = a2 ? __ldg(reinterpret_cast<const float4*>(a2 + d0)) : z4;
+          float4 fs = z4, gs = z4;
+  #pragma unroll
+          for (int j = 0; j < DC_MAXN; ++j) {
+            if (j < N && (need >> j & 1u)) {
+              const float4 f = *reinterpret_cast<const float4*>(Fs + (size_t)j * H + d0), g = *reinterpret_cast<const float4*>(Gs + (size_t)j * H + d0);
+              fs.x += f.x; fs.y += f.y; fs.z += f.z; fs.w += f.w;
+              gs.x += g.x; gs.y += g.y; gs.z += g.z; gs.w += g.w;
+            }
+          }
+          float4 key = make_float4(div_n(fs.x) + div_n(gs.x), div_n(fs.y) + div_n(gs.y), div_n(fs.z) + div_n(gs.z), div_n(fs.w) + div_n(gs.w));
+          if (a1) { key.x += a1v.x; key.y += a1v.y; key.z += a1v.z; key.w += a1v.w; }
+          if (a2) { key.x += a2v.x; key.y += a2v.y; key.z += a2v.z; key.w += a2v.w; }
+          auto th = [](float v) { return SFU ? tanh_sfu(v) : tanhf(v); };
+          part = fmaf(wv.x, th(qv.x + key.x + kv.x), part);
+          part = fmaf(wv.y, th(qv.y + key.y + kv.y), part);
+          part = fmaf(wv.z, th(qv.z + key.z + kv.z), part);
+          part = fmaf(wv.w, th(qv.w + key.w + kv.w), part);
+        }
+        part = warp_sum(part);
+        if (lane == 0) e[wslot][k] = part + w.bt;
+      }
     }
     __syncthreads();
   }
@@ -626,9 +742,11 @@ __global__ void __launch_bounds__(512, 1) dec_select_kernel(DecodeWeights w, Dec
       kk = 1;   // teacher forcing (modeling_bert.py:998-1078): the single hypothesis follows the target order
       rank = (wslot == 0 && k == io.forced[b * N + t]) ? 0 : 1;
     } else {
-      for (int o = 0; o < numel; ++o) {
-        const float v = e[o / N][o % N];
-        rank += (v < mine) || (v == mine && o < flat);
+      for (int ob = 0, o = 0; ob < live; ++ob) {   // o = ob * N + ok without a division per element
+        for (int ok = 0; ok < N; ++ok, ++o) {
+          const float v = e[ob][ok];
+          rank += (v < mine) || (v == mine && o < flat);
+        }
       }
     }
     if (rank < kk) {
@@ -672,7 +790,7 @@ static int beam_search_tiled(const DecodeWeights& w, const DecodeIO& io, cudaStr
   for (int i = 0; i < 2; ++i) s.cost[i] = (float*)carve(rows * 4);
   s.parent = (int32_t*)carve(rows * 4);
   const size_t smem = (size_t)4 * N * H * sizeof(float);
-  MSQ_SMEM_ATTR(smem, dec_select_kernel);
+  MSQ_SMEM_ATTR(smem, dec_select_kernel<false>);
   int live = 1;
   for (int t = 0; t < N - 1; ++t) {
     const int cur = t & 1;   // tables (seq, cost) of step t live in slot cur; h'/c of step t are written to slot cur
@@ -692,7 +810,7 @@ static int beam_search_tiled(const DecodeWeights& w, const DecodeIO& io, cudaStr
       if (force == -2) { const char* e = getenv("MSQ_DEC_MANY"); force = e ? atoi(e) : -1; }
       const bool many = force >= 0 ? force != 0 : io.B > 148;
       const int nbuf = many ? 1 : 2;
-      MSQ_CUDA(launch_k(dec_select_kernel, dim3((unsigned)io.B), dim3((!many && live > 8) ? 512 : 256), smem / (many ? 2 : 1), st, w, io, s, t, live, cur, nbuf));
+      MSQ_CUDA(launch_k(dec_select_kernel<false>, dim3((unsigned)io.B), dim3((!many && live > 8) ? 512 : 256), smem / (many ? 2 : 1), st, w, io, s, t, live, cur, nbuf));
     }
     MSQ_LAUNCH_CHECK();
     live = io.forced ? 1 : next_live(live, N, W);
@@ -748,9 +866,12 @@ static int beam_search_tc(const DecodeWeights& w, const DecodeIO& io, cudaStream
   for (int i = 0; i < 2; ++i) s.cost[i] = (float*)carve(rows * 4);
   s.parent = (int32_t*)carve(rows * 4);
   const size_t smem = (size_t)4 * N * H * sizeof(float);
-  MSQ_SMEM_ATTR(smem, dec_select_kernel);
+  MSQ_SMEM_ATTR(smem, dec_select_kernel<true>);
+  MSQ_SMEM_ATTR(smem, dec_select_kernel<false>);
+  static int sfu = -1;   // MSQ_DEC_TANH=0: libm tanhf in the tensor-core form too
+  if (sfu < 0) { const char* e = getenv("MSQ_DEC_TANH"); sfu = e ? (atoi(e) != 0) : 1; }
   GemmArgs g;
-  g.bias = nullptr; g.resid = nullptr; g.C2 = nullptr; g.K = H; g.lda = H; g.ldw = H; g.ldc = 5 * H; g.ldr = 0; g.act = ACT_NONE; g.split = 2;
+  g.bias = nullptr; g.resid = nullptr; g.C2 = nullptr; g.K = H; g.lda = H; g.ldw = H; g.ldc = 5 * H; g.ldr = 0; g.act = ACT_NONE; g.split = 2; g.trunc = io.trunc;
   // h0 W_hh^T -> columns [H, 5H) of qh[1] (read by the first cell as "previous step")
   MSQ_TRY(pack_split3(io.h0, io.B, H, H, H, h0p, st));
   g.A = h0p; g.W = w.wcat3 + (size_t)H * 3 * H; g.C = qh[1] + H; g.M = io.B; g.N = 4 * H;
@@ -772,7 +893,8 @@ static int beam_search_tc(const DecodeWeights& w, const DecodeIO& io, cudaStream
       if (force == -2) { const char* e = getenv("MSQ_DEC_MANY"); force = e ? atoi(e) : -1; }
       const bool many = force >= 0 ? force != 0 : io.B > 148;
       const int nbuf = many ? 1 : 2;
-      MSQ_CUDA(launch_k(dec_select_kernel, dim3((unsigned)io.B), dim3((!many && live > 8) ? 512 : 256), smem / (many ? 2 : 1), st, w, io, s, t, live, cur, nbuf));
+      MSQ_CUDA(launch_k(sfu ? dec_select_kernel<true> : dec_select_kernel<false>, dim3((unsigned)io.B), dim3((!many && live > 8) ? 512 : 256),
+                        smem / (many ? 2 : 1), st, w, io, s, t, live, cur, nbuf));
     }
     MSQ_LAUNCH_CHECK();
     live_prev = live;

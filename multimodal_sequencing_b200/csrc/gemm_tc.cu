@@ -662,12 +662,12 @@ static int launch_gemm_tc_act(const GemmArgs& g, int sms, cudaStream_t st) {
   ep.inv_dim = g.ln_inv_dim; ep.eps = g.ln_eps; ep.tn = g.tn; ep.split_k = g.split ? g.K : 0;
   ep.drop = g.drop;
   MSQ_REQUIRE(g.drop.thresh == 0 || MODE == 0, "gemm_tc: dropout needs the plain epilogue");
-  ep.split_passes = g.split == 2 ? 6 : 3;
+  ep.split_passes = (g.split == 2 && !g.trunc) ? 6 : 3;   // trunc: planes 0 / 1 of a three-plane row only (bf16x3)
   static int share_env = -1;
   if (share_env < 0) { const char* e = getenv("MSQ_X3_SHARE"); share_env = (e && e[0] == '0') ? 0 : 1; }
   static int early_env = -1;
   if (early_env < 0) { const char* e = getenv("MSQ_X3_EARLY"); early_env = (e && e[0] == '0') ? 0 : 1; }
-  ep.share = (PAIR && g.split == 1 && !g.tn && share_env) ? (early_env ? 1 : 2) : 0;
+  ep.share = (PAIR && (g.split == 1 || (g.split == 2 && g.trunc)) && !g.tn && share_env) ? (early_env ? 1 : 2) : 0;
   static_assert(Cfg::STAGES % 2 == 0, "the shared bf16x3 slab occupies two consecutive stages");
   const int num_m = ceil_div(g.M, Cfg::TILE_M), num_n = ceil_div(g.N, TC_BN),
             num_k = ceil_div(g.K, TC_BK) * (ep.share ? 2 : (g.split ? ep.split_passes : 1));

@@ -80,6 +80,9 @@ struct GemmArgs {
   // split = 2: THREE planes [hi | mid | lo] (24 significand bits = every fp32 value exactly) and six MMAs per product
   // (all a_i w_j with i + j <= 2): fp32-grade products on the tensor cores ("bf16x6"; the decoder's GEMMs).  fp32 out.
   int split = 0;
+  // split = 2 only: run the three passes (0,1) (1,0) (0,0) over the top two planes of the three-plane rows -- bf16x3 products
+  // (16 significand bits) from the SAME operand buffers at half the tensor work (the decoder in the bf16x3 mode)
+  int trunc = 0;
   int mode = EPI_PLAIN;
   const float* svec = nullptr;
   const float* beta = nullptr;
@@ -149,9 +152,11 @@ struct DecodeIO {
   float* final_cost;      // optional [B]: cost of the best hypothesis
   void* scratch = nullptr;  // beam_search_scratch_bytes(B, N, W, H) bytes of device memory (tiled decode; null -> fused kernel)
   int tc = 0;               // 1: recurrent GEMMs on the tensor cores (bf16x6, needs DecodeWeights::wcat3); 0: fp32 FFMA
+  int trunc = 0;            // tc only: bf16x3 products on the top two planes instead of bf16x6 (GemmArgs::trunc)
 };
 size_t beam_search_state_bytes(int64_t B, int W, int H);             // search state (either decode form)
 size_t beam_search_scratch_bytes(int64_t B, int N, int W, int H);    // state + three-plane copies of sents_ext / r0 (tensor-core form)
+int decode_trunc(int precise);   // 1: decoder GEMMs as bf16x3 on the top two planes (default; MSQ_DEC_X3=0: bf16x6, fp32-grade products)
 bool decode_tc_enabled();                                             // MSQ_DECODE_TC=0 keeps the fp32 FFMA GEMMs in every mode
 int beam_search(const DecodeWeights& w, const DecodeIO& io, cudaStream_t st);
 struct StepIO {

@@ -246,12 +246,18 @@ def test_attention(L, heads, masked):
 # golden fixtures produced by the REAL reference
 # ---------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("precise", [True, False])
-def test_decode_full_width_golden(golden_dir, precise):
+@pytest.mark.parametrize("precise", [True, False, "x6"])
+def test_decode_full_width_golden(golden_dir, precise, monkeypatch):
     """H=768 decode stage fed with identical (seeded) encode outputs: bit-exact beam indices and
     permutations for N in {5,6,10} x W in {1,4,8,16} against the reference's beam_search_pointer.
-    precise=True: fp32 FFMA decode (tiled SGEMM); precise=False: the tensor-core decode (three-plane bf16 operands, six MMAs
-    per product) the bf16 / bf16x3 modes run -- held to the same bit-exact indices and the same cost tolerance."""
+    precise=True: fp32 FFMA decode (tiled SGEMM); precise=False: the tensor-core decode the bf16 / bf16x3 modes run (three-plane
+    bf16 operands, the three MMAs over the top two planes per product: bf16x3, the default); "x6": the same with all six
+    plane pairs (MSQ_DEC_X3=0, fp32-grade products) -- all held to the same bit-exact indices and the same cost tolerance."""
+    if precise == "x6":
+        monkeypatch.setenv("MSQ_DEC_X3", "0")
+        precise = False
+    else:
+        monkeypatch.delenv("MSQ_DEC_X3", raising=False)
     g = torch.load(os.path.join(golden_dir, "decode_full.pt"), weights_only=False)
     H = g["H"]
     cfg = dict(hidden_size=H, num_hidden_layers=1, num_attention_heads=12, intermediate_size=64, vocab_size=64,
