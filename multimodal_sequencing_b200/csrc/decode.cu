@@ -629,18 +629,31 @@ __global__ void __launch_bounds__(512, 1) dec_select_kernel(DecodeWeights w, Dec
 #pragma unroll
         for (int bb = 0; bb < BB; ++bb) fs[bb] = gs[bb] = z4;
         if (in) {
+          // rows of `uni` in ascending order (the reference's summation order), the NEXT row's chunk loaded before the current
+          // one is added: the unrolled `if (uni >> j & 1)` form left every row's shared-memory latency exposed (ncu: a third of
+          // the stall samples on the first FADD of a row)
+          uint32_t u = uni;
+          int j = -1;
+          float4 f = z4, g = z4;
+          if (u) {
+            j = __ffs(u) - 1; u &= u - 1;
+            f = *reinterpret_cast<const float4*>(Fs + (size_t)j * H + d0); g = *reinterpret_cast<const float4*>(Gs + (size_t)j * H + d0);
+          }
+          while (j >= 0) {
+            int jn = -1;
+            float4 fn = z4, gn = z4;
+            if (u) {
+              jn = __ffs(u) - 1; u &= u - 1;
+              fn = *reinterpret_cast<const float4*>(Fs + (size_t)jn * H + d0); gn = *reinterpret_cast<const float4*>(Gs + (size_t)jn * H + d0);
+            }
 #pragma unroll
-          for (int j = 0; j < DC_MAXN; ++j) {
-            if (j < N && (uni >> j & 1u)) {
-              const float4 f = *reinterpret_cast<const float4*>(Fs + (size_t)j * H + d0), g = *reinterpret_cast<const float4*>(Gs + (size_t)j * H + d0);
-#pragma unroll
-              for (int bb = 0; bb < BB; ++bb) {
-                if (need[bb] >> j & 1u) {
-                  fs[bb].x += f.x; fs[bb].y += f.y; fs[bb].z += f.z; fs[bb].w += f.w;
-                  gs[bb].x += g.x; gs[bb].y += g.y; gs[bb].z += g.z; gs[bb].w += g.w;
-                }
+            for (int bb = 0; bb < BB; ++bb) {
+              if (need[bb] >> j & 1u) {
+                fs[bb].x += f.x; fs[bb].y += f.y; fs[bb].z += f.z; fs[bb].w += f.w;
+                gs[bb].x += g.x; gs[bb].y += g.y; gs[bb].z += g.z; gs[bb].w += g.w;
               }
             }
+            f = fn; g = gn; j = jn;
           }
         }
 #pragma unroll
